@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""Benchmark of the covariance hot path (BASELINE.json metric and configs).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+
+One "step" is one pass of the hot path over BASELINE.json configs[1]: the dense float64
+Gram matrices of Matern-5/2 AND RatQuad over N = 32768 points in d = 3 (2 * N^2 entries,
+17.2 GB written).  With G > 1 GPUs (launched by torchrun, one rank per GPU) each rank builds
+its own 32768-row block of a (32768*G) x 32768 cross Gram -- weak scaling, no collective on
+the data path.  The JSON line also carries, under "extra", the single-kernel numbers (ExpQuad,
+Matern-5/2, RatQuad) and the matrix-free K.v of configs[2] (N = 2^20, d = 8), which IS
+row-sharded with an NCCL all-gather of the result vector.
+
+Timing: CUDA events on the stream the kernels are launched on, W warm-up steps, exactly K timed
+steps between barrier + synchronize, max over ranks.  Every step writes 8.6 GB per kernel, far
+more than the 126 MB L2, so no L2 flush is needed between iterations.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_GRAM = 32768
+D_GRAM = 3
+N_MV = 1 << 20
+D_MV = 8
+METRIC = "gram_entries_per_s"
+UNIT = "entries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-matvec", action="store_true", help="skip the K.v extra (configs[2])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--n", type=int, default=N_GRAM, help="Gram size (default: BASELINE config)")
+    ap.add_argument("--n-mv", type=int, default=N_MV)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.device_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": float(np.median(sm)) if sm else None,
+            "sm_max_mhz": float(max(mx)) if mx else None,
+            "power_w_max": float(max(power)) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy restatement of the reference algorithm)
+# --------------------------------------------------------------------------------------------
+def _oracle_specs():
+    from oracle import covfuncs_oracle as orc  # noqa: PLC0415
+
+    return [orc.KernelSpec("matern", (D_GRAM,), 1.0, nu=2.5),
+            orc.KernelSpec("ratquad", (D_GRAM,), 1.0, alpha=1.0)]
+
+
+def _cpu_rows(args):
+    """Worker: both Gram kernels for rows [lo, hi) against all N points (oracle)."""
+    lo, hi, n = args
+    from oracle import covfuncs_oracle as orc  # noqa: PLC0415
+
+    x = np.random.default_rng(42).normal(size=(n, D_GRAM))
+    t0 = time.perf_counter()
+    for spec in _oracle_specs():
+        orc.gram(spec, x[lo:hi], x, row_block=512)
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_sample(n: int, rows: int = 2048):
+    """Single-process oracle on a bounded sample: `rows` rows of both Gram matrices."""
+    dt = _cpu_rows((0, rows, n))
+    entries = 2.0 * rows * n
+    return {
+        "value": entries / dt, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"oracle (NumPy restatement of the reference), rows 0..{rows} of the Matern-5/2 and "
+                  f"RatQuad Gram matrices, N={n}, d={D_GRAM}: {entries:.3g} entries in {dt:.1f} s",
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm (oracle port; the reference is pure Python
+    and cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp  # noqa: PLC0415
+
+    n = args.n
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    rows_per_worker = 256
+    jobs = [(w * rows_per_worker, (w + 1) * rows_per_worker, n) for w in range(workers)]
+    entries_per_step = 2.0 * workers * rows_per_worker * n
+    with mp.get_context("fork").Pool(workers) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_rows, jobs)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_rows, jobs)
+        dt = time.perf_counter() - t0
+    value = entries_per_step * args.steps / dt
+    sample = (f"oracle port, {workers} processes x {rows_per_worker} rows x {n} columns of the Matern-5/2 "
+              f"and RatQuad Gram matrices per step ({entries_per_step:.3g} entries/step)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={D_GRAM}, float64 (BASELINE configs[1])",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch  # noqa: PLC0415
+    import torch.distributed as dist  # noqa: PLC0415
+
+    import probnum_b200 as pb  # noqa: PLC0415
+    from probnum_b200 import _lib  # noqa: PLC0415
+    from probnum_b200.sharded import ShardedCovarianceOperator  # noqa: PLC0415
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: probnum_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n, d = args.n, D_GRAM
+    # synthetic inputs as in benchmarks/covfuncs.py:56 (default_rng(42), standard normal)
+    x1_host = np.random.default_rng(42).normal(size=(n, d))
+    x0_host = x1_host if world == 1 else np.random.default_rng(1000 + rank).normal(size=(n, d))
+    kernels = {
+        "matern52": pb.Matern((d,), nu=2.5),
+        "ratquad": pb.RatQuad((d,)),
+        "expquad": pb.ExpQuad((d,)),
+    }
+    x0_dev = torch.from_numpy(x0_host).to(dev)
+    x1_dev = torch.from_numpy(x1_host).to(dev)
+    ops = {}
+    for name, k in kernels.items():
+        ops[name] = _lib.Operator(k._kernel_params(), x0_dev.data_ptr(),
+                                  None if world == 1 else x1_dev.data_ptr(),
+                                  device=local_rank, on_device=True, n0=n, n1=n, dtype=np.float64)
+    out = torch.empty((n, n), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def gram(name):
+        ops[name].gram_device(out.data_ptr(), n, stream=stream)
+
+    step_kernels = ["matern52", "ratquad"]
+
+    def step():
+        for name in step_kernels:
+            gram(name)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(step_kernels) + 1)] for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        ev[s][0].record()
+        for i, name in enumerate(step_kernels):
+            gram(name)
+            ev[s][i + 1].record()
+    barrier()
+    total_ms = ev[0][0].elapsed_time(ev[-1][-1])
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    per_kernel_ms = {
+        name: float(np.mean([ev[s][i].elapsed_time(ev[s][i + 1]) for s in range(args.steps)]))
+        for i, name in enumerate(step_kernels)
+    }
+    total_ms = max_over_ranks(total_ms)
+    entries_per_step = 2.0 * n * n * world
+    value = entries_per_step * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant launch (same kernel, slower epilogue)
+    peaks, peak_kind = measured_peaks()
+    dom = max(per_kernel_ms, key=per_kernel_ms.get)
+    alg_bytes = 8.0 * n * n + 8.0 * d * (n + n)
+    achieved = alg_bytes / (per_kernel_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("gram_strip_kernel_bytes_per_launch")
+    roofline = {
+        "bound": "hbm", "kernel": f"gram_strip_kernel<double,double> ({dom} epilogue)",
+        "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+        "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, copy read+write)",
+        "algorithmic_bytes_per_launch": alg_bytes,
+    }
+
+    extra = {"per_kernel_ms": per_kernel_ms,
+             "per_kernel_entries_per_s": {k: n * n / (v * 1e-3) for k, v in per_kernel_ms.items()}}
+
+    # ExpQuad Gram alone (north_star's 70 % target is quoted on it)
+    for _ in range(2):
+        gram("expquad")
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(reps):
+        gram("expquad")
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+    extra["expquad_gram"] = {"ms": ms, "entries_per_s": n * n * world / (ms * 1e-3),
+                             "hbm_gbs": alg_bytes / (ms * 1e-3) / 1e9,
+                             "frac_of_peak": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+    # ---- end to end through the public API: host arrays in, host ndarray out ------------------
+    e2e = None
+    if not args.no_e2e:
+        ks = [kernels[name] for name in step_kernels]
+        for k in ks:  # warm-up: pins the result buffers once
+            k.matrix(x0_host, None if world == 1 else x1_host)
+        barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for k in ks:
+                K = k.matrix(x0_host, None if world == 1 else x1_host)
+                del K
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {
+            "value": entries_per_step * e2e_steps / dt, "unit": UNIT,
+            "h2d_bytes_per_step": 2 * 8 * d * (n if world == 1 else 2 * n),
+            "d2h_bytes_per_step": int(2 * 8 * n * n),
+            "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+            "api": "probnum_b200.covfuncs.{Matern,RatQuad}.matrix(X) -> numpy.ndarray (pinned result pool)",
+        }
+    del out
+    torch.cuda.empty_cache()
+
+    # ---- configs[2]: matrix-free ExpQuad K.v, N = 2^20, d = 8, row-sharded + all-gather -----------
+    if not args.no_matvec:
+        nm = args.n_mv
+        xm = np.random.default_rng(42).normal(size=(nm, D_MV))
+        kmv = pb.ExpQuad((D_MV,))
+        if world > 1:
+            sop = ShardedCovarianceOperator(kmv, xm, device=local_rank)
+        else:
+            if not dist.is_initialized():
+                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+                os.environ.setdefault("MASTER_PORT", "29533")
+                dist.init_process_group("gloo", rank=0, world_size=1)
+            sop = ShardedCovarianceOperator(kmv, xm, device=local_rank)
+        v = torch.from_numpy(np.random.default_rng(7).normal(size=(nm, 1))).to(dev)
+        y = torch.empty((nm, 1), dtype=torch.float64, device=dev)
+        sop.matmul_device(v, out=y)
+        barrier()
+        reps = 2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(reps):
+            sop.matmul_device(v, out=y)
+        e1.record()
+        barrier()
+        launches += _lib.launch_count() - l0
+        ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        flop_per_pair = 3 * D_MV + 1 + 2  # 3d + 1 + 2K, FMA = 2
+        extra["matvec"] = {
+            "workload": f"ExpQuad K.v, N={nm}, d={D_MV}, K=1, float64, row-sharded over {world} GPU(s) + all-gather",
+            "ms": ms, "pairs_per_s": float(nm) * nm / (ms * 1e-3),
+            "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,
+            "flop_per_pair": flop_per_pair, "scaling": "strong",
+        }
+        sop.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_sample(n)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={d}, float64 (BASELINE configs[1])"
+                            + ("" if world == 1 else f"; each of {world} ranks builds its own {n}-row block of a "
+                               f"({n * world} x {n}) cross Gram"),
+                "l2": "each launch writes 8.6 GB >> 126 MB L2; no flush needed",
+                "inputs": "default_rng(42).normal, resident in HBM",
+            },
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line))
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

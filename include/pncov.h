@@ -1,0 +1,140 @@
+/* pncov -- C ABI of the B200 covariance-function library (libpncov.so).
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of ProbNum,
+ * probnum.randprocs.covfuncs: the dense Gram matrix K(X0, X1) and the matrix-free
+ * product K(X0, X1) @ V for the isotropic kernels ExpQuad, Matern (half-integer nu)
+ * and RatQuad.  Plain C types only; no torch / numpy types cross this boundary.
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference/src/probnum).
+ *
+ * Conventions
+ *   - all functions return 0 on success, a negative PNCOV_E* code for invalid
+ *     arguments and a positive code for CUDA runtime failures;
+ *     pncov_last_error() returns a thread-local message for the last failure.
+ *   - point sets are C-contiguous row-major (n, d) arrays of `dtype`
+ *     (scalar-input kernels use d = 1), exactly what
+ *     CovarianceFunction._preprocess_linop_input produces
+ *     (randprocs/covfuncs/_covariance_function.py:676-693).
+ *   - the caller owns every host buffer; the library keeps no host pointer after a
+ *     call returns.  Device buffers, streams and scratch belong to the handle.
+ *   - a handle is bound to one CUDA device and is not re-entrant.
+ *   - there is no CPU fallback anywhere: without a usable device every compute
+ *     entry point fails.
+ */
+#ifndef PNCOV_H_
+#define PNCOV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNCOV_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define PNCOV_API __attribute__((visibility("default")))
+#else
+#define PNCOV_API
+#endif
+
+/* kernel families (randprocs/covfuncs/_exponentiated_quadratic.py, _matern.py,
+ * _rational_quadratic.py) */
+#define PNCOV_EXPQUAD 0
+#define PNCOV_MATERN 1 /* nu = p + 1/2, p = 0..PNCOV_MAX_MATERN_P */
+#define PNCOV_RATQUAD 2
+
+#define PNCOV_F64 0
+#define PNCOV_F32 1
+
+#define PNCOV_MAX_MATERN_P 8
+
+/* error codes */
+#define PNCOV_EINVAL (-1)   /* invalid argument (shape, kind, parameter) */
+#define PNCOV_ENOTIMPL (-2) /* outside the accelerated scope (e.g. non-half-integer nu) */
+#define PNCOV_ENOMEM (-3)
+#define PNCOV_ENODEVICE (-4)
+
+typedef struct pncov_handle pncov_handle;
+
+/* library / device ---------------------------------------------------------------- */
+PNCOV_API int pncov_version(void);
+PNCOV_API const char* pncov_last_error(void);
+PNCOV_API int pncov_device_count(int* count);
+
+/* pinned host memory for result arrays (so D2H runs at PCIe rate) */
+PNCOV_API int pncov_host_alloc(void** ptr, int64_t nbytes);
+PNCOV_API int pncov_host_free(void* ptr);
+
+/* operator life cycle ---------------------------------------------------------------
+ * pncov_create binds a covariance function and its two point sets to a device:
+ * it replaces the construction of CovarianceLinearOperator(x0, x1, ...)
+ * (randprocs/covfuncs/_covariance_linear_operator.py:50-65) and the argument
+ * handling of CovarianceFunction.matrix / .linop (_covariance_function.py:359-488).
+ *
+ *   kind, dtype         PNCOV_* constants above
+ *   d                   input dimension (>= 1)
+ *   lengthscales        n_lengthscales = 1 (isotropic) or d (ARD) positive values;
+ *                       RatQuad accepts 1 only (_rational_quadratic.py:59-69)
+ *   nu                  Matern smoothness, must be p + 1/2 (_matern.py:136-151)
+ *   alpha               RatQuad scale mixture > 0 (_rational_quadratic.py:66-68)
+ *   x0, n0              first point set, n0 rows
+ *   x1, n1              second point set or NULL (then x1 = x0, n1 ignored)
+ *   points_on_device    0: x0/x1 are host pointers; 1: device pointers on `device`
+ */
+PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, int64_t d,
+                 const double* lengthscales, int64_t n_lengthscales, double nu, double alpha,
+                 const void* x0, int64_t n0, const void* x1, int64_t n1,
+                 int points_on_device);
+PNCOV_API int pncov_destroy(pncov_handle* h);
+
+PNCOV_API int pncov_shape(const pncov_handle* h, int64_t* n0, int64_t* n1);
+/* dtype of Gram entries: follows the reference under NumPy 2 (f64 -> f64;
+ * f32 -> f32 for ExpQuad, f64 for Matern and RatQuad) */
+PNCOV_API int pncov_gram_dtype(const pncov_handle* h, int* dtype);
+
+/* dense Gram matrix -----------------------------------------------------------------
+ * replaces CovarianceFunction._evaluate_matrix (_covariance_function.py:553-582)
+ * for scalar-output isotropic kernels, i.e. IsotropicMixin._squared_euclidean_distances
+ * (:757-781) fused with ExpQuad/Matern/RatQuad._evaluate.
+ *   out    (n0, n1) row-major, leading dimension ld (elements), dtype pncov_gram_dtype
+ *   transpose != 0 writes K^T, shape (n1, n0)  (CovarianceLinearOperator._transpose,
+ *   _covariance_linear_operator.py:83-90)
+ * pncov_gram:        `out` is host memory (pageable or pinned); blocks until done.
+ * pncov_gram_device: `out` is device memory on the handle's device; asynchronous on
+ *                    `stream` (a cudaStream_t, 0 = the handle's own stream).
+ */
+PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose);
+PNCOV_API int pncov_gram_device(pncov_handle* h, void* out, int64_t ld, int transpose, void* stream);
+
+/* matrix-free product Y = K(X0, X1) @ V  (or K^T @ V) ---------------------------------
+ * replaces CovarianceLinearOperator._matmul (_covariance_linear_operator.py:78-81),
+ * i.e. both `keops_lazy_tensor @ x` and `self.todense() @ x`; K is never stored.
+ *   V   (n1, k) row-major with leading dimension ldv; Y (n0, k) with ldy
+ *       (transpose: V is (n0, k), Y is (n1, k)); dtype = the handle's dtype
+ */
+PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy,
+                 int transpose);
+PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y,
+                        int64_t ldy, int transpose, void* stream);
+
+/* elementwise evaluation out[b] = k(x0[b], x1[b]) -------------------------------------
+ * replaces the broadcasting path of CovarianceFunction.__call__
+ * (_covariance_function.py:280-357) after the caller has broadcast both arguments
+ * to a common batch of B points.  Host pointers; out dtype as pncov_gram_dtype.
+ */
+PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const double* lengthscales,
+                int64_t n_lengthscales, double nu, double alpha, const void* x0, const void* x1,
+                int64_t b, void* out);
+
+/* diagnostics ------------------------------------------------------------------------
+ * number of kernel launches issued by this library in the calling process, and the
+ * device time in ms of the last pncov_gram / pncov_matmul call of this handle (CUDA
+ * events on the handle's stream around the kernels, excluding host<->device copies). */
+PNCOV_API int64_t pncov_launch_count(void);
+PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNCOV_H_ */

@@ -1,0 +1,256 @@
+"""ctypes binding of libpncov.so (the C ABI in ``include/pncov.h``).
+
+There is exactly one implementation behind this module: the CUDA library.  If the
+shared object is missing, or no B200 is visible when a compute call is made, the
+call raises -- nothing here falls back to NumPy.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpncov.so")
+
+EXPQUAD, MATERN, RATQUAD = 0, 1, 2
+F64, F32 = 0, 1
+MAX_MATERN_P = 8
+
+_c_i64 = ctypes.c_int64
+_c_vp = ctypes.c_void_p
+_c_dp = ctypes.POINTER(ctypes.c_double)
+
+# every exported symbol of include/pncov.h with its signature
+SIGNATURES = {
+    "pncov_version": (ctypes.c_int, []),
+    "pncov_last_error": (ctypes.c_char_p, []),
+    "pncov_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "pncov_host_alloc": (ctypes.c_int, [ctypes.POINTER(_c_vp), _c_i64]),
+    "pncov_host_free": (ctypes.c_int, [_c_vp]),
+    "pncov_create": (
+        ctypes.c_int,
+        [ctypes.POINTER(_c_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64,
+         ctypes.c_double, ctypes.c_double, _c_vp, _c_i64, _c_vp, _c_i64, ctypes.c_int],
+    ),
+    "pncov_destroy": (ctypes.c_int, [_c_vp]),
+    "pncov_shape": (ctypes.c_int, [_c_vp, ctypes.POINTER(_c_i64), ctypes.POINTER(_c_i64)]),
+    "pncov_gram_dtype": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_int)]),
+    "pncov_gram": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, ctypes.c_int]),
+    "pncov_gram_device": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, ctypes.c_int, _c_vp]),
+    "pncov_matmul": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int]),
+    "pncov_matmul_device": (
+        ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int, _c_vp]),
+    "pncov_pairs": (
+        ctypes.c_int,
+        [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64, ctypes.c_double,
+         ctypes.c_double, _c_vp, _c_vp, _c_i64, _c_vp],
+    ),
+    "pncov_launch_count": (_c_i64, []),
+    "pncov_last_kernel_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class PncovError(RuntimeError):
+    """Device-side failure reported by libpncov (CUDA error, no device, ...)."""
+
+
+def load() -> ctypes.CDLL:
+    """Load libpncov.so (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise PncovError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                    "g.build()'` (nvcc, sm_100a).  probnum_b200 has no CPU fallback."
+                )
+            lib = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+            for name, (restype, argtypes) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = restype
+                fn.argtypes = argtypes
+            _lib = lib
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc == 0:
+        return
+    msg = load().pncov_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(msg)
+    if rc == -2:
+        raise NotImplementedError(msg)
+    if rc == -3:
+        raise MemoryError(msg)
+    raise PncovError(f"libpncov error {rc}: {msg}")
+
+
+def device_count() -> int:
+    n = ctypes.c_int(0)
+    rc = load().pncov_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def default_device() -> int:
+    """One process per GPU: LOCAL_RANK selects the device under torchrun."""
+    return int(os.environ.get("PNCOV_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def launch_count() -> int:
+    return int(load().pncov_launch_count())
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _dtype_code(dt: np.dtype) -> int:
+    if dt == np.float64:
+        return F64
+    if dt == np.float32:
+        return F32
+    raise ValueError(f"unsupported dtype {dt}")
+
+
+class KernelParams:
+    """Plain description of one covariance function for the C ABI."""
+
+    __slots__ = ("kind", "d", "lengthscales", "nu", "alpha")
+
+    def __init__(self, kind: int, d: int, lengthscales, nu: float = 0.5, alpha: float = 1.0):
+        self.kind = int(kind)
+        self.d = int(d)
+        self.lengthscales = np.ascontiguousarray(np.atleast_1d(lengthscales), dtype=np.float64)
+        self.nu = float(nu)
+        self.alpha = float(alpha)
+
+    def _ls(self):
+        return self.lengthscales.ctypes.data_as(_c_dp), self.lengthscales.size
+
+
+class Operator:
+    """A covariance function bound to two point sets resident on one B200.
+
+    ``x0`` / ``x1`` are host arrays of shape (n, d), or integer device addresses when
+    ``on_device`` is set (then ``n0`` / ``n1`` / ``dtype`` must be given).
+    """
+
+    def __init__(self, params: KernelParams, x0, x1=None, *, device: Optional[int] = None,
+                 on_device: bool = False, n0: Optional[int] = None, n1: Optional[int] = None,
+                 dtype=None):
+        lib = load()
+        self._lib = lib
+        self._h = _c_vp()
+        self.params = params
+        self.device = default_device() if device is None else int(device)
+        if on_device:
+            self.dtype = np.dtype(dtype)
+            p0, p1 = _c_vp(int(x0)), (None if x1 is None else _c_vp(int(x1)))
+            n0, n1 = int(n0), (0 if x1 is None else int(n1))
+        else:
+            x0 = np.ascontiguousarray(x0)
+            x1 = None if x1 is None else np.ascontiguousarray(x1, dtype=x0.dtype)
+            if x0.ndim != 2 or x0.shape[1] != params.d or (x1 is not None and (x1.ndim != 2 or x1.shape[1] != params.d)):
+                raise ValueError("point sets must have shape (n, d)")
+            self.dtype = x0.dtype
+            self._keep = (x0, x1)
+            p0, p1 = _ptr(x0), _ptr(x1)
+            n0, n1 = x0.shape[0], (0 if x1 is None else x1.shape[0])
+        ls, nls = params._ls()
+        rc = lib.pncov_create(ctypes.byref(self._h), self.device, params.kind, _dtype_code(self.dtype),
+                              params.d, ls, nls, params.nu, params.alpha, p0, n0, p1, n1,
+                              1 if on_device else 0)
+        _check(rc)
+        self._keep = None
+        a, b = _c_i64(), _c_i64()
+        _check(lib.pncov_shape(self._h, ctypes.byref(a), ctypes.byref(b)))
+        self.shape = (a.value, b.value)
+        g = ctypes.c_int()
+        _check(lib.pncov_gram_dtype(self._h, ctypes.byref(g)))
+        self.gram_dtype = np.dtype(np.float32 if g.value == F32 else np.float64)
+
+    # -- life cycle -----------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pncov_destroy(self._h)
+            self._h = _c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- Gram -------------------------------------------------------------------------------
+    def gram(self, out: np.ndarray, transpose: bool = False) -> np.ndarray:
+        """Fill the host array ``out`` (C-contiguous rows, dtype ``gram_dtype``)."""
+        rows, cols = self.shape[::-1] if transpose else self.shape
+        if out.shape != (rows, cols) or out.dtype != self.gram_dtype:
+            raise ValueError("output array has the wrong shape or dtype")
+        if out.size and out.strides[1] != out.itemsize:
+            raise ValueError("output rows must be contiguous")
+        ld = out.strides[0] // out.itemsize if rows > 1 else max(cols, 1)
+        _check(self._lib.pncov_gram(self._h, _ptr(out), ld, 1 if transpose else 0))
+        return out
+
+    def gram_device(self, out_ptr: int, ld: int, transpose: bool = False, stream: int = 0) -> None:
+        _check(self._lib.pncov_gram_device(self._h, _c_vp(out_ptr), ld, 1 if transpose else 0,
+                                           _c_vp(stream)))
+
+    # -- matrix-free product ------------------------------------------------------------------
+    def matmul(self, v: np.ndarray, transpose: bool = False) -> np.ndarray:
+        """``K @ v`` for a host array ``v`` of shape (n1, k); returns (n0, k)."""
+        rows, cols = self.shape[::-1] if transpose else self.shape
+        v = np.ascontiguousarray(v, dtype=self.dtype)
+        if v.ndim != 2 or v.shape[0] != cols:
+            raise ValueError(f"operand must have shape ({cols}, k), got {v.shape}")
+        k = v.shape[1]
+        y = np.empty((rows, k), dtype=self.dtype)
+        _check(self._lib.pncov_matmul(self._h, _ptr(v), k, max(k, 1), _ptr(y), max(k, 1),
+                                      1 if transpose else 0))
+        if cols == 0:
+            y[...] = 0
+        return y
+
+    def matmul_device(self, v_ptr: int, k: int, ldv: int, y_ptr: int, ldy: int,
+                      transpose: bool = False, stream: int = 0) -> None:
+        _check(self._lib.pncov_matmul_device(self._h, _c_vp(v_ptr), k, ldv, _c_vp(y_ptr), ldy,
+                                             1 if transpose else 0, _c_vp(stream)))
+
+    def last_kernel_ms(self) -> float:
+        ms = ctypes.c_float()
+        _check(self._lib.pncov_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+
+def pairs(params: KernelParams, x0: np.ndarray, x1: np.ndarray, device: Optional[int] = None) -> np.ndarray:
+    """out[b] = k(x0[b], x1[b]) for two host arrays of shape (B, d)."""
+    lib = load()
+    x0 = np.ascontiguousarray(x0)
+    x1 = np.ascontiguousarray(x1, dtype=x0.dtype)
+    if x0.shape != x1.shape or x0.ndim != 2 or x0.shape[1] != params.d:
+        raise ValueError("pairs() needs two (B, d) arrays")
+    out_dtype = np.float32 if (x0.dtype == np.float32 and params.kind == EXPQUAD) else np.float64
+    out = np.empty(x0.shape[0], dtype=out_dtype)
+    ls, nls = params._ls()
+    _check(lib.pncov_pairs(default_device() if device is None else device, params.kind,
+                           _dtype_code(x0.dtype), params.d, ls, nls, params.nu, params.alpha,
+                           _ptr(x0), _ptr(x1), x0.shape[0], _ptr(out)))
+    return out

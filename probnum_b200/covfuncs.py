@@ -1,0 +1,436 @@
+"""Host-side mirror of ``probnum.randprocs.covfuncs`` for the accelerated kernels.
+
+Same class names, constructor arguments, methods, shapes and error behaviour as the
+reference (/root/reference/src/probnum/randprocs/covfuncs/), but every evaluation
+runs in libpncov on a B200:
+
+==================================  =====================================================
+reference                           here
+==================================  =====================================================
+``CovarianceFunction.__call__``     shape checks identical (:280-357, :606-674); the
+                                    Gram-shaped broadcast ``(N0,1,d) x (1,N1,d)`` goes to
+                                    the Gram kernel, every other broadcast pattern to the
+                                    elementwise ``pncov_pairs`` kernel
+``CovarianceFunction.matrix``       ``pncov_gram``  (:359-413, :553-582)
+``CovarianceFunction.linop``        :class:`CovarianceLinearOperator` over a resident
+                                    device operator (:415-488, :584-604)
+``CovarianceLinearOperator``        ``_matmul`` -> ``pncov_matmul`` (matrix-free),
+                                    ``_todense`` -> ``pncov_gram``, ``_transpose`` swaps the
+                                    point sets (_covariance_linear_operator.py:22-90)
+==================================  =====================================================
+
+There is no NumPy evaluation path in this module: without libpncov.so and a GPU the
+calls raise.
+"""
+
+from __future__ import annotations
+
+import abc
+import fractions
+import functools
+import operator
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib, hostmem, linops
+
+ShapeType = Tuple[int, ...]
+
+
+def _as_shape(x) -> ShapeType:
+    """probnum.utils.as_shape (utils/argutils.py:13): int or iterable of ints -> tuple."""
+    if isinstance(x, (int, np.integer)):
+        return (int(x),)
+    try:
+        shape = tuple(int(i) for i in x)
+    except TypeError as err:
+        raise TypeError(f"The given shape {x} must be an integer or an iterable of integers.") from err
+    return shape
+
+
+def _as_numpy_scalar(x, dtype=np.double):
+    """probnum.utils.as_numpy_scalar (utils/argutils.py:54)."""
+    if np.ndim(x) != 0:
+        raise ValueError("The given input is not a scalar.")
+    return np.asarray(x, dtype=dtype)[()]
+
+
+class CovarianceFunction(abc.ABC):
+    """(Cross-)covariance function with scalar output, evaluated on the GPU.
+
+    Mirrors the shape bookkeeping and argument validation of the reference base class
+    (_covariance_function.py:138-269, :606-693) for the case used by the isotropic
+    kernels: ``input_shape_0 == input_shape_1 == input_shape`` and ``output_shape = ()``.
+    """
+
+    def __init__(self, *, input_shape):
+        self._input_shape = _as_shape(input_shape)
+        if len(self._input_shape) > 1:
+            raise ValueError("The accelerated covariance functions take scalar or vector inputs.")
+
+    # -- shapes ------------------------------------------------------------------------------
+    @property
+    def input_shape(self) -> ShapeType:
+        return self._input_shape
+
+    input_shape_0 = input_shape
+    input_shape_1 = input_shape
+
+    @property
+    def input_ndim(self) -> int:
+        return len(self._input_shape)
+
+    input_ndim_0 = input_ndim
+    input_ndim_1 = input_ndim
+
+    @functools.cached_property
+    def input_size(self) -> int:
+        return functools.reduce(operator.mul, self._input_shape, 1)
+
+    output_shape_0: ShapeType = ()
+    output_shape_1: ShapeType = ()
+    output_ndim_0 = 0
+    output_ndim_1 = 0
+    output_size_0 = 1
+    output_size_1 = 1
+
+    def __repr__(self) -> str:
+        return (
+            f"<{self.__class__.__name__} with input_shape_0={self.input_shape_0},"
+            f" input_shape_1={self.input_shape_1}, output_shape_0={self.output_shape_0}, and"
+            f" output_shape_1={self.output_shape_1}>"
+        )
+
+    # -- public API ----------------------------------------------------------------------------
+    def __call__(self, x0, x1) -> np.ndarray:
+        """``k(x0, x1)`` vectorised over broadcast batch shapes (:280-357)."""
+        x0 = np.asarray(x0)
+        if x1 is not None:
+            x1 = np.asarray(x1)
+        batch_shape = self._check_shapes(x0.shape, x1.shape if x1 is not None else None)
+        out = self._evaluate(x0, x1)
+        assert out.shape == batch_shape
+        return out
+
+    def matrix(self, x0, x1=None) -> np.ndarray:
+        """Gram matrix of shape (N0, N1) over flattened batches (:359-413)."""
+        x0 = self._preprocess_linop_input(x0, argnum=0)
+        if x1 is not None:
+            x1 = self._preprocess_linop_input(x1, argnum=1)
+        K = self._evaluate_matrix(x0, x1)
+        assert isinstance(K, np.ndarray)
+        assert K.shape == (x0.shape[0], x1.shape[0] if x1 is not None else x0.shape[0])
+        return K
+
+    def linop(self, x0, x1=None) -> linops.LinearOperator:
+        """Matrix-free operator for the Gram matrix (:415-488)."""
+        x0 = self._preprocess_linop_input(x0, argnum=0)
+        if x1 is not None:
+            x1 = self._preprocess_linop_input(x1, argnum=1)
+        op = self._evaluate_linop(x0, x1)
+        assert isinstance(op, linops.LinearOperator)
+        assert op.shape == (x0.shape[0], x1.shape[0] if x1 is not None else x0.shape[0])
+        return op
+
+    # -- validation (same messages and exception types as the reference) ----------------------------
+    def _check_shapes(self, x0_shape: ShapeType, x1_shape: Optional[ShapeType] = None) -> ShapeType:
+        err_msg = (
+            "The shape of the input array `x{argnum}` must match "
+            "`input_shape_{argnum}`, i.e. `{input_shape}`, along its trailing "
+            "dimensions, but an array with shape `{shape}` was given."
+        )
+        nd = self.input_ndim
+        if x0_shape[len(x0_shape) - nd:] != self.input_shape:
+            raise ValueError(err_msg.format(argnum=0, input_shape=self.input_shape, shape=x0_shape))
+        batch = x0_shape[: len(x0_shape) - nd]
+        if x1_shape is not None:
+            if x1_shape[len(x1_shape) - nd:] != self.input_shape:
+                raise ValueError(err_msg.format(argnum=1, input_shape=self.input_shape, shape=x1_shape))
+            try:
+                batch = np.broadcast_shapes(batch, x1_shape[: len(x1_shape) - nd])
+            except ValueError as ve:
+                raise ValueError(
+                    f"The input arrays `x0` and `x1` with shapes {x0_shape} and "
+                    f"{x1_shape} can not be broadcast to a common shape."
+                ) from ve
+        return tuple(batch)
+
+    def _preprocess_linop_input(self, x, argnum: int) -> np.ndarray:
+        x = np.asarray(x)
+        nd = self.input_ndim
+        if not (x.ndim >= nd and x.shape[(x.ndim - nd):] == self.input_shape):
+            raise ValueError(
+                f"The shape of `x{argnum}` must must match `input_shape_{argnum}`, "
+                f"i.e. `{self.input_shape}`, of the covariance function along its "
+                f"trailing dimensions, but an array with shape `{x.shape}` was given."
+            )
+        return x.reshape((-1,) + self.input_shape, order="C")
+
+    # -- device dispatch ---------------------------------------------------------------------------
+    @abc.abstractmethod
+    def _kernel_params(self) -> _lib.KernelParams:
+        """Description of this covariance function for the C ABI."""
+
+    def _points(self, x: np.ndarray, dtype) -> np.ndarray:
+        """(N,) + input_shape -> C-contiguous (N, d) in the compute dtype."""
+        return np.ascontiguousarray(x.reshape(x.shape[0], max(self.input_size, 1)), dtype=dtype)
+
+    @staticmethod
+    def _compute_dtype(x0: np.ndarray, x1: Optional[np.ndarray]) -> np.dtype:
+        dt = x0.dtype if x1 is None else np.result_type(x0.dtype, x1.dtype)
+        return np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
+
+    def _result_dtype(self, compute_dtype: np.dtype) -> np.dtype:
+        """Dtype the reference returns under NumPy 2 for these inputs."""
+        if compute_dtype == np.float32 and isinstance(self, ExpQuad):
+            return np.dtype(np.float32)
+        return np.dtype(np.float64)
+
+    def _evaluate(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.ndarray:
+        nd = self.input_ndim
+        if x1 is None:
+            # k(x, x) = 1 for the three isotropic families: the reference returns exact
+            # ones as well (_exponentiated_quadratic.py:90-94, _rational_quadratic.py:72-76;
+            # Matern: c_0 * exp(-0) = 1, _matern.py:175-191)
+            dt = self._result_dtype(self._compute_dtype(x0, None))
+            return np.ones(x0.shape[: x0.ndim - nd], dtype=dt)
+        b0 = x0.shape[: x0.ndim - nd]
+        b1 = x1.shape[: x1.ndim - nd]
+        batch = np.broadcast_shapes(b0, b1)
+        dt = self._compute_dtype(x0, x1)
+        # Gram-shaped broadcast: x0 batch (N0, 1), x1 batch (1, N1)
+        if len(b0) == 2 and len(b1) == 2 and b0[1] == 1 and b1[0] == 1 and b0[0] * b1[1] > 1:
+            X0 = x0.reshape((b0[0],) + self.input_shape)
+            X1 = x1.reshape((b1[1],) + self.input_shape)
+            return self._gram(X0, X1, dt)
+        size = int(np.prod(batch, dtype=np.int64))
+        if size == 0:
+            return np.empty(batch, dtype=self._result_dtype(dt))
+        full = tuple(batch) + self.input_shape
+        p0 = np.broadcast_to(x0, full).reshape(size, -1)
+        p1 = np.broadcast_to(x1, full).reshape(size, -1)
+        out = _lib.pairs(self._kernel_params(), np.ascontiguousarray(p0, dtype=dt),
+                         np.ascontiguousarray(p1, dtype=dt))
+        return out.reshape(batch)
+
+    def _gram(self, x0: np.ndarray, x1: Optional[np.ndarray], dt: np.dtype) -> np.ndarray:
+        n0 = x0.shape[0]
+        n1 = n0 if x1 is None else x1.shape[0]
+        out_dt = self._result_dtype(dt)
+        if n0 == 0 or n1 == 0:
+            return np.empty((n0, n1), dtype=out_dt)
+        with _lib.Operator(self._kernel_params(), self._points(x0, dt),
+                           None if x1 is None else self._points(x1, dt)) as op:
+            K = hostmem.empty((n0, n1), op.gram_dtype)
+            op.gram(K)
+        return K
+
+    def _evaluate_matrix(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.ndarray:
+        """Override point #1 of the drop-in (:553-582)."""
+        return self._gram(x0, x1, self._compute_dtype(x0, x1))
+
+    def _evaluate_linop(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> linops.LinearOperator:
+        """Override point #2 of the drop-in (:584-604)."""
+        return CovarianceLinearOperator(self, x0, x1)
+
+
+class CovarianceLinearOperator(linops.LinearOperator):
+    """Pairwise covariances of two point sets as a matrix-free operator on the GPU.
+
+    Mirror of _covariance_linear_operator.py:22-90.  The points are uploaded once, when
+    the first product is requested, and stay resident; ``L @ v`` evaluates the kernel in
+    registers and never builds the matrix (the reference needs KeOps for that, and
+    silently caches the dense matrix without it, :78-81).
+    """
+
+    def __init__(self, covfunc: CovarianceFunction, x0: np.ndarray, x1: Optional[np.ndarray],
+                 *, _transposed_of: Optional["CovarianceLinearOperator"] = None):
+        self._covfunc = covfunc
+        self._x0 = x0
+        self._x1 = x1
+        self._parent = _transposed_of
+        self._op: Optional[_lib.Operator] = None
+        n0 = x0.shape[0]
+        n1 = n0 if x1 is None else x1.shape[0]
+        shape = (n0, n1) if _transposed_of is None else (n1, n0)
+        dtype = np.promote_types(x0.dtype, x1.dtype) if x1 is not None else x0.dtype
+        if dtype not in (np.float32, np.float64):
+            dtype = np.dtype(np.float64)
+        super().__init__(shape, dtype)
+
+    # the device operator is shared between an operator and its transpose
+    def _device_op(self) -> _lib.Operator:
+        root = self._parent if self._parent is not None else self
+        if root._op is None:
+            cf = root._covfunc
+            dt = cf._compute_dtype(root._x0, root._x1)
+            root._op = _lib.Operator(cf._kernel_params(), cf._points(root._x0, dt),
+                                     None if root._x1 is None else cf._points(root._x1, dt))
+        return root._op
+
+    @property
+    def _is_transposed(self) -> bool:
+        return self._parent is not None
+
+    def _matmul(self, x: np.ndarray) -> np.ndarray:
+        M, N = self.shape
+        op = self._device_op()
+        lead = x.shape[:-2]
+        k = x.shape[-1]
+        if M == 0 or k == 0:
+            return np.zeros(lead + (M, k), dtype=np.result_type(self.dtype, x.dtype))
+        if N == 0:
+            return np.zeros(lead + (M, k), dtype=np.result_type(self.dtype, x.dtype))
+        if lead:
+            # stacked operands (..., N, K): fold the stack into columns
+            B = int(np.prod(lead, dtype=np.int64))
+            v = np.moveaxis(x.reshape(B, N, k), 0, 1).reshape(N, B * k)
+            y = op.matmul(v, transpose=self._is_transposed)
+            y = np.moveaxis(y.reshape(M, B, k), 1, 0).reshape(lead + (M, k))
+        else:
+            y = op.matmul(x, transpose=self._is_transposed)
+        return y.astype(np.result_type(self.dtype, x.dtype), copy=False)
+
+    def _todense(self) -> np.ndarray:
+        op = self._device_op()
+        K = hostmem.empty(self.shape, op.gram_dtype)
+        if K.size:
+            op.gram(K, transpose=self._is_transposed)
+        return K
+
+    def _transpose(self) -> linops.LinearOperator:
+        if self._parent is not None:
+            return self._parent
+        return CovarianceLinearOperator(self._covfunc, self._x0, self._x1, _transposed_of=self)
+
+    def _diagonal(self) -> np.ndarray:
+        # k(x0_i, x1_i): O(N d) through the elementwise kernel instead of N matvecs
+        n = min(self.shape)
+        if self._x1 is None:
+            return np.ones(n, dtype=self._covfunc._result_dtype(np.dtype(self.dtype)))
+        return np.array(self._covfunc(self._x0[:n], self._x1[:n]))
+
+    def close(self) -> None:
+        root = self._parent if self._parent is not None else self
+        if root._op is not None:
+            root._op.close()
+            root._op = None
+
+
+def _lengthscales_for_device(lengthscales: np.ndarray, input_shape: ShapeType) -> np.ndarray:
+    if lengthscales.ndim == 0:
+        return lengthscales.reshape(1)
+    return np.ascontiguousarray(np.broadcast_to(lengthscales, input_shape), dtype=np.double).reshape(-1)
+
+
+class ExpQuad(CovarianceFunction):
+    r"""Exponentiated quadratic / RBF kernel
+    :math:`k(x_0,x_1)=\exp(-\frac12\sum_i((x_{0,i}-x_{1,i})/l_i)^2)`
+    (_exponentiated_quadratic.py:20-111)."""
+
+    def __init__(self, input_shape, *, lengthscales=1.0):
+        super().__init__(input_shape=input_shape)
+        lengthscales = np.asarray(lengthscales if lengthscales is not None else 1.0, dtype=np.double)
+        if np.any(lengthscales <= 0):
+            raise ValueError(f"Lengthscales l={lengthscales} must be positive.")
+        np.broadcast_to(lengthscales, self.input_shape)  # must broadcast to the input dimension
+        self._lengthscales = lengthscales
+
+    @property
+    def lengthscales(self) -> np.ndarray:
+        return self._lengthscales
+
+    @property
+    def lengthscale(self) -> np.ndarray:
+        if self._lengthscales.shape == ():
+            return self._lengthscales
+        raise ValueError("There is more than one lengthscale.")
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        return _lib.KernelParams(_lib.EXPQUAD, max(self.input_size, 1),
+                                 _lengthscales_for_device(self._lengthscales, self.input_shape))
+
+
+class Matern(CovarianceFunction):
+    r"""Matern kernel with half-integer smoothness :math:`\nu=p+\frac12`
+    (_matern.py:22-267).  The Bessel-function branch for other :math:`\nu`
+    (_matern.py:195, :270-279) is outside the accelerated scope and raises."""
+
+    def __init__(self, input_shape, nu=1.5, *, lengthscales=None):
+        super().__init__(input_shape=input_shape)
+        nu = _as_numpy_scalar(nu)
+        if nu <= 0:
+            raise ValueError(f"Hyperparameter nu={nu} must be positive.")
+        self._nu = nu
+        lengthscales = np.asarray(lengthscales if lengthscales is not None else 1.0, dtype=np.double)
+        if np.any(lengthscales <= 0):
+            raise ValueError(f"All lengthscales l={lengthscales} must be positive.")
+        np.broadcast_to(lengthscales, self.input_shape)
+        self._lengthscales = lengthscales
+
+    @property
+    def nu(self):
+        return self._nu
+
+    @functools.cached_property
+    def p(self) -> Optional[int]:
+        nu_minus_half = self._nu - 0.5
+        if nu_minus_half == int(nu_minus_half):
+            return int(nu_minus_half)
+        return None
+
+    @property
+    def is_half_integer(self) -> bool:
+        return self.p is not None
+
+    @property
+    def lengthscales(self) -> np.ndarray:
+        return self._lengthscales
+
+    @property
+    def lengthscale(self) -> np.ndarray:
+        if self._lengthscales.shape == ():
+            return self._lengthscales
+        raise ValueError("There is more than one lengthscale.")
+
+    @staticmethod
+    @functools.lru_cache(maxsize=None)
+    def half_integer_coefficients(p: int) -> Tuple[fractions.Fraction, ...]:
+        """Exact polynomial coefficients, degree i at index i (_matern.py:225-261)."""
+        coeffs = [fractions.Fraction(1)]
+        for i in reversed(range(p)):
+            coeffs.append(coeffs[-1] * fractions.Fraction(2 * (i + 1), (p + i + 1) * (p - i)))
+        return tuple(coeffs)
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        if not self.is_half_integer:
+            raise NotImplementedError(
+                f"Matern with nu={self._nu} needs the Bessel-function branch, which the B200 path "
+                "does not implement (half-integer nu only)."
+            )
+        if self.p > _lib.MAX_MATERN_P:
+            raise NotImplementedError(f"Matern degree p={self.p} exceeds {_lib.MAX_MATERN_P}.")
+        return _lib.KernelParams(_lib.MATERN, max(self.input_size, 1),
+                                 _lengthscales_for_device(self._lengthscales, self.input_shape),
+                                 nu=float(self._nu))
+
+
+class RatQuad(CovarianceFunction):
+    r"""Rational quadratic kernel
+    :math:`k(x_0,x_1)=(1+\lVert x_0-x_1\rVert^2/(2\alpha l^2))^{-\alpha}`
+    (_rational_quadratic.py:18-84)."""
+
+    def __init__(self, input_shape, lengthscale=1.0, alpha=1.0):
+        self.lengthscale = _as_numpy_scalar(lengthscale)
+        self.alpha = _as_numpy_scalar(alpha)
+        if not self.alpha > 0:
+            raise ValueError(f"Scale mixture alpha={self.alpha} must be positive.")
+        super().__init__(input_shape=input_shape)
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        if self.lengthscale == 0:
+            raise ValueError("Lengthscale l=0 makes the rational quadratic kernel undefined.")
+        # only l^2 enters the formula (_rational_quadratic.py:78-84)
+        return _lib.KernelParams(_lib.RATQUAD, max(self.input_size, 1), np.reshape(abs(self.lengthscale), 1),
+                                 alpha=float(self.alpha))

@@ -1,0 +1,677 @@
+// C ABI of libpncov (see include/pncov.h): handle management, host<->device staging,
+// argument validation and the small utility kernels (layout changes, packing, the
+// elementwise "pairs" evaluation).  The two hot kernels live in pncov_gram.cu and
+// pncov_matvec.cu.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/pncov.h"
+#include "pncov_internal.h"
+
+int64_t g_pn_launches = 0;
+
+namespace {
+
+thread_local std::string t_err;
+
+int fail(int code, const std::string& msg) {
+    t_err = msg;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* what) {
+    t_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    cudaGetLastError();  // clear sticky-less error state
+    return (int)e > 0 ? (int)e : 1;
+}
+
+#define PN_CUDA(expr)                                         \
+    do {                                                      \
+        cudaError_t pn_e_ = (expr);                           \
+        if (pn_e_ != cudaSuccess) return fail_cuda(pn_e_, #expr); \
+    } while (0)
+
+constexpr double kLog2e = 1.4426950408889634074;
+
+// ---- utility kernels ------------------------------------------------------------------------
+// (n, d) row-major -> (d, ld) coordinate-major; pad columns [n, ld) are left as zero-filled
+template <typename T>
+__global__ void aos_to_soa_kernel(const T* __restrict__ aos, T* __restrict__ soa, int64_t n, int d,
+                                  int64_t ld) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * d) return;
+    const int64_t i = idx / d;
+    const int m = (int)(idx % d);
+    soa[(size_t)m * ld + i] = aos[idx];
+}
+
+// V (rows, k) with leading dimension ldv -> packed (rows_pad, kc) chunk starting at column c0
+template <typename T>
+__global__ void pack_v_kernel(const T* __restrict__ v, int64_t ldv, int64_t rows, int64_t rows_pad,
+                              int64_t k, int64_t c0, int kc, T* __restrict__ vp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_pad * kc) return;
+    const int64_t j = idx / kc;
+    const int c = (int)(idx % kc);
+    vp[idx] = (j < rows && c0 + c < k) ? v[j * ldv + c0 + c] : T(0);
+}
+
+template <typename T>
+__global__ void unpack_y_kernel(const T* __restrict__ yp, int64_t rows, int kc, int64_t k, int64_t c0,
+                                T* __restrict__ y, int64_t ldy) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * kc) return;
+    const int64_t i = idx / kc;
+    const int c = (int)(idx % kc);
+    if (c0 + c < k) y[i * ldy + c0 + c] = yp[idx];
+}
+
+// out[b] = k(x0[b], x1[b]); one thread per pair (O(B d) work, not a hot path)
+template <typename T, typename TOut>
+__global__ void pairs_kernel(const __grid_constant__ PnPairsLaunch p) {
+    __shared__ double tabE[PN_EXP2_N];
+    __shared__ double tabL[2 * PN_LOG2_N];
+    pn_stage_tables(tabE, tabL, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.b) return;
+    const T* a = static_cast<const T*>(p.x0) + b * p.d;
+    const T* c = static_cast<const T*>(p.x1) + b * p.d;
+    const T* sc = static_cast<const T*>(p.scale);
+    T S = T(0);
+    for (int m = 0; m < p.d; ++m) {
+        T df = a[m] - c[m];
+        if (sc) df *= sc[m];
+        S += df * df;
+    }
+    TOut* out = static_cast<TOut*>(p.out);
+    if constexpr (sizeof(TOut) == 4) {
+        out[b] = exp2f(S * (float)p.epi.c_u);
+    } else {
+        out[b] = pn_epilogue((double)S, p.epi, tabE, tabL);
+    }
+}
+
+// ---- kernel description -----------------------------------------------------------------------
+struct KernelDesc {
+    int kind = 0, dtype = 0, d = 0;
+    bool ard = false;
+    std::vector<double> scale;  // per-dimension scale factors when ard
+    PnEpiParams epi{};
+    bool gram_f32() const { return dtype == PNCOV_F32 && kind == PNCOV_EXPQUAD; }
+    size_t elem() const { return dtype == PNCOV_F32 ? 4 : 8; }
+    size_t gram_elem() const { return gram_f32() ? 4 : 8; }
+};
+
+unsigned long long gcd_u(unsigned long long a, unsigned long long b) {
+    while (b) {
+        unsigned long long t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+// exact rational recursion of Matern.half_integer_coefficients (_matern.py:225-267);
+// coef[i] multiplies r^i
+bool matern_coefficients(int p, double* coef) {
+    unsigned long long num = 1, den = 1;
+    coef[0] = 1.0;
+    int idx = 1;
+    for (int i = p - 1; i >= 0; --i, ++idx) {
+        unsigned long long a = 2ULL * (unsigned long long)(i + 1);
+        unsigned long long b = (unsigned long long)(p + i + 1) * (unsigned long long)(p - i);
+        unsigned long long g = gcd_u(a, b);
+        a /= g;
+        b /= g;
+        g = gcd_u(num, b);
+        num /= g;
+        b /= g;
+        g = gcd_u(a, den);
+        a /= g;
+        den /= g;
+        if (num > (1ULL << 53) / a || den > (1ULL << 53) / b) return false;
+        num *= a;
+        den *= b;
+        coef[idx] = (double)num / (double)den;  // both exact in double: one correctly rounded division
+    }
+    return true;
+}
+
+int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, int64_t nls, double nu,
+               double alpha) {
+    if (kind != PNCOV_EXPQUAD && kind != PNCOV_MATERN && kind != PNCOV_RATQUAD)
+        return fail(PNCOV_EINVAL, "unknown kernel kind");
+    if (dtype != PNCOV_F64 && dtype != PNCOV_F32) return fail(PNCOV_EINVAL, "unknown dtype");
+    if (d < 1 || d > (1 << 20)) return fail(PNCOV_EINVAL, "input dimension d must be in [1, 2^20]");
+    if (!ls || (nls != 1 && nls != d)) return fail(PNCOV_EINVAL, "n_lengthscales must be 1 or d");
+    for (int64_t i = 0; i < nls; ++i)
+        if (!(ls[i] > 0)) return fail(PNCOV_EINVAL, "lengthscales must be positive");
+    k.kind = kind;
+    k.dtype = dtype;
+    k.d = (int)d;
+    k.ard = nls > 1;
+    k.epi = PnEpiParams{};
+    double base = 1.0;  // numerator of the scale factor
+    if (kind == PNCOV_EXPQUAD) {
+        base = sqrt(0.5);  // _exponentiated_quadratic.py:85-87
+        k.epi.epi = PN_EPI_EXPQUAD;
+    } else if (kind == PNCOV_MATERN) {
+        if (!(nu > 0)) return fail(PNCOV_EINVAL, "nu must be positive");
+        const double pm = nu - 0.5;
+        if (pm != floor(pm)) return fail(PNCOV_ENOTIMPL, "Matern with non-half-integer nu (Bessel branch) is outside the accelerated scope");
+        if (pm > PNCOV_MAX_MATERN_P) return fail(PNCOV_ENOTIMPL, "Matern degree p = nu - 1/2 above PNCOV_MAX_MATERN_P");
+        const int p = (int)pm;
+        base = sqrt(2 * nu);  // _matern.py:171-173
+        k.epi.p = p;
+        k.epi.epi = p == 0 ? PN_EPI_MATERN0 : p == 1 ? PN_EPI_MATERN1 : p == 2 ? PN_EPI_MATERN2 : PN_EPI_MATERNP;
+        if (!matern_coefficients(p, k.epi.coef)) return fail(PNCOV_ENOTIMPL, "Matern coefficients overflow");
+    } else {
+        if (nls != 1) return fail(PNCOV_EINVAL, "RatQuad takes a single lengthscale");
+        if (!(alpha > 0)) return fail(PNCOV_EINVAL, "alpha must be positive");
+        k.epi.c_s = 1.0 / (2.0 * alpha * (ls[0] * ls[0]));  // _rational_quadratic.py:78-84
+        k.epi.alpha = alpha;
+        k.epi.epi = alpha == 1.0 ? PN_EPI_RATQUAD1 : alpha == 2.0 ? PN_EPI_RATQUAD2 : PN_EPI_RATQUADG;
+        k.ard = false;
+        return 0;
+    }
+    if (k.ard) {
+        k.scale.resize(d);
+        for (int64_t i = 0; i < d; ++i) k.scale[i] = base / ls[i];
+        k.epi.c_u = -kLog2e;
+        k.epi.c_s = 1.0;
+    } else {
+        const double s = base / ls[0];
+        if (kind == PNCOV_EXPQUAD) {
+            k.epi.c_u = -kLog2e * (s * s);
+            k.epi.c_s = 1.0;
+        } else {
+            k.epi.c_u = -kLog2e;
+            k.epi.c_s = s;
+        }
+    }
+    return 0;
+}
+
+int64_t pad_up(int64_t n) { return ((n + PN_PAD - 1) / PN_PAD) * PN_PAD; }
+
+struct Points {
+    int64_t n = 0, npad = 0;
+    void* aos = nullptr;  // (npad, d)
+    void* soa = nullptr;  // (d, npad)
+};
+
+}  // namespace
+
+struct pncov_handle {
+    int device = 0;
+    int sm_count = 148;
+    KernelDesc k;
+    Points p0, p1;
+    bool symmetric = false;  // x1 was NULL: p1 aliases p0
+    void* scale_dev = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    // scratch (grown on demand)
+    void* vpack = nullptr;
+    size_t vpack_bytes = 0;
+    void* ypack = nullptr;
+    size_t ypack_bytes = 0;
+    void* partial = nullptr;
+    size_t partial_bytes = 0;
+    void* stage = nullptr;  // device staging for host entry points
+    size_t stage_bytes = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensure(void** buf, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *have = 0;
+    PN_CUDA(cudaMalloc(buf, need));
+    *have = need;
+    return 0;
+}
+
+int upload_points(pncov_handle* h, Points& P, const void* x, int64_t n, bool on_device) {
+    const size_t es = h->k.elem();
+    const int d = h->k.d;
+    P.n = n;
+    P.npad = pad_up(n > 0 ? n : 1);
+    const size_t bytes = (size_t)P.npad * d * es;
+    PN_CUDA(cudaMalloc(&P.aos, bytes));
+    PN_CUDA(cudaMalloc(&P.soa, bytes));
+    PN_CUDA(cudaMemsetAsync(P.aos, 0, bytes, h->stream));
+    PN_CUDA(cudaMemsetAsync(P.soa, 0, bytes, h->stream));
+    if (n > 0) {
+        PN_CUDA(cudaMemcpyAsync(P.aos, x, (size_t)n * d * es, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        const int64_t total = n * d;
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        if (es == 8)
+            aos_to_soa_kernel<double><<<blocks, 256, 0, h->stream>>>((const double*)P.aos, (double*)P.soa, n, d, P.npad);
+        else
+            aos_to_soa_kernel<float><<<blocks, 256, 0, h->stream>>>((const float*)P.aos, (float*)P.soa, n, d, P.npad);
+        ++g_pn_launches;
+        PN_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+void free_points(Points& P) {
+    if (P.aos) cudaFree(P.aos);
+    if (P.soa) cudaFree(P.soa);
+    P = Points{};
+}
+
+int upload_scale(const KernelDesc& k, void** dev, cudaStream_t stream) {
+    *dev = nullptr;
+    if (!k.ard) return 0;
+    PN_CUDA(cudaMalloc(dev, k.scale.size() * k.elem()));
+    if (k.dtype == PNCOV_F64) {
+        PN_CUDA(cudaMemcpyAsync(*dev, k.scale.data(), k.scale.size() * 8, cudaMemcpyHostToDevice, stream));
+        PN_CUDA(cudaStreamSynchronize(stream));
+    } else {
+        std::vector<float> s32(k.scale.begin(), k.scale.end());
+        PN_CUDA(cudaMemcpyAsync(*dev, s32.data(), s32.size() * 4, cudaMemcpyHostToDevice, stream));
+        PN_CUDA(cudaStreamSynchronize(stream));
+    }
+    return 0;
+}
+
+PnGramLaunch gram_launch(const pncov_handle* h, bool transpose, int64_t row0, int64_t rows, void* out, int64_t ld) {
+    const Points& R = transpose ? h->p1 : h->p0;  // rows of the output
+    const Points& C = transpose ? h->p0 : h->p1;
+    const size_t es = h->k.elem();
+    PnGramLaunch g{};
+    g.x0_soa = static_cast<const char*>(R.soa) + (size_t)row0 * es;
+    g.x1_soa = C.soa;
+    g.ld0 = R.npad;
+    g.ld1 = C.npad;
+    g.n0 = rows;
+    g.n1 = C.n;
+    g.scale = h->scale_dev;
+    g.d = h->k.d;
+    g.out = out;
+    g.ldo = ld;
+    g.in_f32 = h->k.dtype == PNCOV_F32;
+    g.out_f32 = h->k.gram_f32();
+    g.epi = h->k.epi;
+    return g;
+}
+
+int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy,
+                       bool transpose, cudaStream_t stream) {
+    const Points& R = transpose ? h->p1 : h->p0;
+    const Points& C = transpose ? h->p0 : h->p1;
+    const size_t es = h->k.elem();
+    if (k <= 0 || R.n <= 0) return 0;
+    if (C.n <= 0) {  // empty sum: Y = 0
+        PN_CUDA(cudaMemset2DAsync(y, (size_t)ldy * es, 0, (size_t)k * es, (size_t)R.n, stream));
+        return 0;
+    }
+    if (h->k.d > 1024) return fail(PNCOV_ENOTIMPL, "matrix-free product supports d <= 1024");
+    const int jsplit = pn_matvec_jsplit(R.n, C.n, h->k.d, h->sm_count);
+    const int kc_max = (k == 1) ? 1 : 4;
+    int rc;
+    if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * kc_max * es))) return rc;
+    if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)R.n * kc_max * es))) return rc;
+    if (jsplit > 1 && (rc = ensure(&h->partial, &h->partial_bytes, (size_t)jsplit * R.n * kc_max * 8))) return rc;
+
+    for (int64_t c0 = 0; c0 < k; c0 += kc_max) {
+        const int kc = kc_max;
+        {
+            const int64_t total = C.npad * kc;
+            const unsigned blocks = (unsigned)((total + 255) / 256);
+            if (es == 8)
+                pack_v_kernel<double><<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc, (double*)h->vpack);
+            else
+                pack_v_kernel<float><<<blocks, 256, 0, stream>>>((const float*)v, ldv, C.n, C.npad, k, c0, kc, (float*)h->vpack);
+            ++g_pn_launches;
+            PN_CUDA(cudaGetLastError());
+        }
+        PnMatvecLaunch m{};
+        m.x0_aos = R.aos;
+        m.x1_aos = C.aos;
+        m.x1_soa = C.soa;
+        m.ld1 = C.npad;
+        m.n0 = R.n;
+        m.n1 = C.n;
+        m.n1pad = C.npad;
+        m.scale = h->scale_dev;
+        m.d = h->k.d;
+        m.v = h->vpack;
+        m.y = h->ypack;
+        m.kc = kc;
+        m.partial = h->partial;
+        m.jsplit = jsplit;
+        m.in_f32 = h->k.dtype == PNCOV_F32;
+        m.epi = h->k.epi;
+        PN_CUDA(pn_launch_matvec(m, stream));
+        {
+            const int64_t total = R.n * kc;
+            const unsigned blocks = (unsigned)((total + 255) / 256);
+            if (es == 8)
+                unpack_y_kernel<double><<<blocks, 256, 0, stream>>>((const double*)h->ypack, R.n, kc, k, c0, (double*)y, ldy);
+            else
+                unpack_y_kernel<float><<<blocks, 256, 0, stream>>>((const float*)h->ypack, R.n, kc, k, c0, (float*)y, ldy);
+            ++g_pn_launches;
+            PN_CUDA(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+PNCOV_API int pncov_version(void) { return PNCOV_VERSION; }
+
+PNCOV_API const char* pncov_last_error(void) { return t_err.c_str(); }
+
+PNCOV_API int pncov_device_count(int* count) {
+    if (!count) return fail(PNCOV_EINVAL, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail_cuda(e, "cudaGetDeviceCount");
+    }
+    return 0;
+}
+
+PNCOV_API int pncov_host_alloc(void** ptr, int64_t nbytes) {
+    if (!ptr || nbytes < 0) return fail(PNCOV_EINVAL, "bad arguments");
+    *ptr = nullptr;
+    if (nbytes == 0) return 0;
+    PN_CUDA(cudaHostAlloc(ptr, (size_t)nbytes, cudaHostAllocPortable));
+    return 0;
+}
+
+PNCOV_API int pncov_host_free(void* ptr) {
+    if (ptr) PN_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, int64_t d, const double* lengthscales,
+                 int64_t n_lengthscales, double nu, double alpha, const void* x0, int64_t n0, const void* x1,
+                 int64_t n1, int points_on_device) {
+    if (!out) return fail(PNCOV_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n0 < 0 || (x1 && n1 < 0)) return fail(PNCOV_EINVAL, "negative point count");
+    if ((n0 > 0 && !x0)) return fail(PNCOV_EINVAL, "x0 is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PNCOV_ENODEVICE, "no CUDA device available (libpncov has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(PNCOV_EINVAL, "device index out of range");
+    pncov_handle* h = new (std::nothrow) pncov_handle();
+    if (!h) return fail(PNCOV_ENOMEM, "out of host memory");
+    int rc = build_desc(h->k, kind, dtype, d, lengthscales, n_lengthscales, nu, alpha);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    h->device = device;
+    DeviceGuard guard(device);
+    auto bail = [&](int code) {
+        pncov_destroy(h);
+        return code;
+    };
+    if (!guard.ok) return bail(fail(PNCOV_ENODEVICE, "cudaSetDevice failed"));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return bail(fail(PNCOV_ENODEVICE, "libpncov is built for sm_100a (B200) only"));
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
+    if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
+    if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+    if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
+    if ((rc = upload_scale(h->k, &h->scale_dev, h->stream))) return bail(rc);
+    if ((rc = upload_points(h, h->p0, x0, n0, points_on_device != 0))) return bail(rc);
+    if (x1) {
+        if ((rc = upload_points(h, h->p1, x1, n1, points_on_device != 0))) return bail(rc);
+    } else {
+        h->p1 = h->p0;
+        h->symmetric = true;
+    }
+    if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(fail_cuda(e, "upload"));
+    *out = h;
+    return 0;
+}
+
+PNCOV_API int pncov_destroy(pncov_handle* h) {
+    if (!h) return 0;
+    DeviceGuard guard(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (!h->symmetric) free_points(h->p1);
+    free_points(h->p0);
+    if (h->scale_dev) cudaFree(h->scale_dev);
+    if (h->vpack) cudaFree(h->vpack);
+    if (h->ypack) cudaFree(h->ypack);
+    if (h->partial) cudaFree(h->partial);
+    if (h->stage) cudaFree(h->stage);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return 0;
+}
+
+PNCOV_API int pncov_shape(const pncov_handle* h, int64_t* n0, int64_t* n1) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (n0) *n0 = h->p0.n;
+    if (n1) *n1 = h->p1.n;
+    return 0;
+}
+
+PNCOV_API int pncov_gram_dtype(const pncov_handle* h, int* dtype) {
+    if (!h || !dtype) return fail(PNCOV_EINVAL, "NULL argument");
+    *dtype = h->k.gram_f32() ? PNCOV_F32 : PNCOV_F64;
+    return 0;
+}
+
+PNCOV_API int pncov_gram_device(pncov_handle* h, void* out, int64_t ld, int transpose, void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    const int64_t rows = transpose ? h->p1.n : h->p0.n;
+    const int64_t cols = transpose ? h->p0.n : h->p1.n;
+    if (rows == 0 || cols == 0) return 0;
+    if (!out || ld < cols) return fail(PNCOV_EINVAL, "bad output buffer / leading dimension");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PN_CUDA(cudaEventRecord(h->ev0, stream));
+    PN_CUDA(pn_launch_gram(gram_launch(h, transpose != 0, 0, rows, out, ld), stream));
+    PN_CUDA(cudaEventRecord(h->ev1, stream));
+    h->timed = true;
+    return 0;
+}
+
+PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    const int64_t rows = transpose ? h->p1.n : h->p0.n;
+    const int64_t cols = transpose ? h->p0.n : h->p1.n;
+    if (rows == 0 || cols == 0) return 0;
+    if (!out || ld < cols) return fail(PNCOV_EINVAL, "bad output buffer / leading dimension");
+    DeviceGuard guard(h->device);
+    const size_t ge = h->k.gram_elem();
+    // row blocks of <= 1 GiB, double buffered: block b+1 is computed while block b is copied out
+    int64_t block_rows = (int64_t)((1ull << 30) / ((size_t)cols * ge));
+    block_rows = std::max<int64_t>(PN_PAD, (block_rows / PN_PAD) * PN_PAD);
+    block_rows = std::min<int64_t>(block_rows, pad_up(rows));
+    const size_t block_bytes = (size_t)block_rows * cols * ge;
+    const int nbuf = rows > block_rows ? 2 : 1;
+    int rc;
+    if ((rc = ensure(&h->stage, &h->stage_bytes, block_bytes * nbuf))) return rc;
+    cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    for (int i = 0; i < nbuf; ++i) {
+        PN_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        PN_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+    }
+    cudaError_t err = cudaSuccess;
+    err = cudaEventRecord(h->ev0, h->stream);
+    int b = 0;
+    for (int64_t r0 = 0; r0 < rows && err == cudaSuccess; r0 += block_rows, ++b) {
+        const int64_t nr = std::min(block_rows, rows - r0);
+        const int buf = b % nbuf;
+        char* dbuf = static_cast<char*>(h->stage) + (size_t)buf * block_bytes;
+        if (b >= nbuf) err = cudaStreamWaitEvent(h->stream, copied[buf], 0);
+        if (err == cudaSuccess) err = pn_launch_gram(gram_launch(h, transpose != 0, r0, nr, dbuf, cols), h->stream);
+        if (err == cudaSuccess) err = cudaEventRecord(done[buf], h->stream);
+        if (err == cudaSuccess) err = cudaStreamWaitEvent(h->copy_stream, done[buf], 0);
+        if (err == cudaSuccess)
+            err = cudaMemcpy2DAsync(static_cast<char*>(out) + (size_t)r0 * ld * ge, (size_t)ld * ge, dbuf, (size_t)cols * ge,
+                                    (size_t)cols * ge, (size_t)nr, cudaMemcpyDeviceToHost, h->copy_stream);
+        if (err == cudaSuccess) err = cudaEventRecord(copied[buf], h->copy_stream);
+    }
+    if (err == cudaSuccess) err = cudaEventRecord(h->ev1, h->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->copy_stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < nbuf; ++i) {
+        cudaEventDestroy(done[i]);
+        cudaEventDestroy(copied[i]);
+    }
+    h->timed = true;
+    if (err != cudaSuccess) return fail_cuda(err, "pncov_gram");
+    return 0;
+}
+
+PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy, int transpose,
+                        void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (k < 0 || ldv < k || ldy < k) return fail(PNCOV_EINVAL, "bad column count / leading dimension");
+    if (k > 0 && (!v || !y)) return fail(PNCOV_EINVAL, "NULL operand");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PN_CUDA(cudaEventRecord(h->ev0, stream));
+    int rc = matmul_device_impl(h, v, k, ldv, y, ldy, transpose != 0, stream);
+    if (rc) return rc;
+    PN_CUDA(cudaEventRecord(h->ev1, stream));
+    h->timed = true;
+    return 0;
+}
+
+PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy, int transpose) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (k < 0 || ldv < k || ldy < k) return fail(PNCOV_EINVAL, "bad column count / leading dimension");
+    const int64_t rows = transpose ? h->p1.n : h->p0.n;
+    const int64_t cols = transpose ? h->p0.n : h->p1.n;
+    if (k == 0 || rows == 0) return 0;
+    if (!v && cols > 0) return fail(PNCOV_EINVAL, "NULL operand");
+    if (!y) return fail(PNCOV_EINVAL, "NULL result");
+    DeviceGuard guard(h->device);
+    const size_t es = h->k.elem();
+    const size_t vbytes = (size_t)std::max<int64_t>(cols, 1) * k * es, ybytes = (size_t)rows * k * es;
+    int rc;
+    if ((rc = ensure(&h->stage, &h->stage_bytes, vbytes + ybytes + 256))) return rc;
+    char* dv = static_cast<char*>(h->stage);
+    char* dy = dv + ((vbytes + 255) / 256) * 256;
+    if (cols > 0)
+        PN_CUDA(cudaMemcpy2DAsync(dv, (size_t)k * es, v, (size_t)ldv * es, (size_t)k * es, (size_t)cols, cudaMemcpyHostToDevice, h->stream));
+    PN_CUDA(cudaEventRecord(h->ev0, h->stream));
+    if ((rc = matmul_device_impl(h, dv, k, k, dy, k, transpose != 0, h->stream))) return rc;
+    PN_CUDA(cudaEventRecord(h->ev1, h->stream));
+    PN_CUDA(cudaMemcpy2DAsync(y, (size_t)ldy * es, dy, (size_t)k * es, (size_t)k * es, (size_t)rows, cudaMemcpyDeviceToHost, h->stream));
+    PN_CUDA(cudaStreamSynchronize(h->stream));
+    h->timed = true;
+    return 0;
+}
+
+PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const double* lengthscales, int64_t n_lengthscales,
+                double nu, double alpha, const void* x0, const void* x1, int64_t b, void* out) {
+    KernelDesc k;
+    int rc = build_desc(k, kind, dtype, d, lengthscales, n_lengthscales, nu, alpha);
+    if (rc) return rc;
+    if (b < 0) return fail(PNCOV_EINVAL, "negative batch size");
+    if (b == 0) return 0;
+    if (!x0 || !x1 || !out) return fail(PNCOV_EINVAL, "NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PNCOV_ENODEVICE, "no CUDA device available (libpncov has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(PNCOV_EINVAL, "device index out of range");
+    DeviceGuard guard(device);
+    const size_t es = k.elem(), oe = k.gram_elem();
+    const size_t pbytes = (size_t)b * d * es;
+    char* buf = nullptr;
+    PN_CUDA(cudaMalloc(&buf, 2 * pbytes + (size_t)b * oe + 512));
+    void* scale_dev = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(buf);
+        if (scale_dev) cudaFree(scale_dev);
+    };
+    if ((rc = upload_scale(k, &scale_dev, 0))) {
+        cleanup();
+        return rc;
+    }
+    char* d0 = buf;
+    char* d1 = buf + ((pbytes + 255) / 256) * 256;
+    char* dout = d1 + ((pbytes + 255) / 256) * 256;
+    // note: buf was sized with 512 bytes of slack for the two roundings above
+    cudaError_t e = cudaMemcpy(d0, x0, pbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d1, x1, pbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        PnPairsLaunch p{};
+        p.x0 = d0;
+        p.x1 = d1;
+        p.b = b;
+        p.scale = scale_dev;
+        p.d = (int)d;
+        p.out = dout;
+        p.in_f32 = dtype == PNCOV_F32;
+        p.out_f32 = k.gram_f32();
+        p.epi = k.epi;
+        e = pn_launch_pairs(p, 0);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)b * oe, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail_cuda(e, "pncov_pairs");
+    return 0;
+}
+
+PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
+
+PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms) {
+    if (!h || !ms) return fail(PNCOV_EINVAL, "NULL argument");
+    if (!h->timed) return fail(PNCOV_EINVAL, "no timed call yet");
+    DeviceGuard guard(h->device);
+    PN_CUDA(cudaEventSynchronize(h->ev1));
+    PN_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+
+}  // extern "C"
+
+cudaError_t pn_launch_pairs(const PnPairsLaunch& p, cudaStream_t stream) {
+    const unsigned blocks = (unsigned)((p.b + 255) / 256);
+    if (!p.in_f32)
+        pairs_kernel<double, double><<<blocks, 256, 0, stream>>>(p);
+    else if (p.out_f32)
+        pairs_kernel<float, float><<<blocks, 256, 0, stream>>>(p);
+    else
+        pairs_kernel<float, double><<<blocks, 256, 0, stream>>>(p);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}

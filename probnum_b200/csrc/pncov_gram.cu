@@ -1,0 +1,359 @@
+// Dense Gram matrix K[i, j] = k(x0_i, x1_j) for the isotropic kernels.
+//
+// Replaces, fused into one pass over the output,
+//   IsotropicMixin._squared_euclidean_distances  randprocs/covfuncs/_covariance_function.py:757-781
+//   ExpQuad/Matern/RatQuad._evaluate             _exponentiated_quadratic.py:89-100, _matern.py:175-193,
+//                                                _rational_quadratic.py:71-84
+//   CovarianceFunction._evaluate_matrix          _covariance_function.py:553-582
+// (all paths relative to /root/reference/src/probnum).
+//
+// The kernel is bound by the N0 x N1 output write (HBM) as long as the FP64 work per
+// entry stays under ~22 instructions; see DESIGN.md for the budget.  Layout:
+//
+//   * a CTA of 256 threads owns a strip of 512 output columns; each thread owns two
+//     adjacent columns, so one row of the strip leaves the CTA as 256 16-byte
+//     streaming stores (512 contiguous bytes per warp instruction);
+//   * the strip's column points (coordinate-major, d x 512) are staged ONCE into shared
+//     memory by 1-D TMA bulk copies; row points arrive in tiles of 64 rows through a
+//     two-stage TMA + mbarrier pipeline, and are read back as warp-wide broadcasts;
+//   * distances are direct differences ((x0 - x1) * s)^2 like the reference, so there
+//     is no cancellation problem for near-duplicate or un-centred points.
+#include <type_traits>
+
+#include "pncov_internal.h"
+
+namespace {
+
+constexpr int G_THREADS = 256;
+constexpr int G_TN = 2 * G_THREADS;  // columns per strip
+constexpr int G_TM = 64;             // rows per pipelined x0 tile
+constexpr int G_R = 4;               // rows per register tile
+constexpr int G_DMAX = 16;           // strip kernel: all coordinates of a strip live in smem
+constexpr int G_CHUNK_ROWS = 8;      // chunk kernel (d > G_DMAX): rows per CTA tile
+constexpr int G_HDR_BYTES = 128 + 8 * (PN_EXP2_N + 2 * PN_LOG2_N);  // barriers + tables
+
+template <typename T>
+struct Pair;
+template <>
+struct Pair<double> {
+    using type = double2;
+};
+template <>
+struct Pair<float> {
+    using type = float2;
+};
+
+// ---- epilogue over a register tile ------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ double epi_one(double S, const PnEpiParams& P, const double* tabE,
+                                          const double* tabL) {
+    if constexpr (EPI == PN_EPI_EXPQUAD) {
+        return pn_exp2(S * P.c_u, tabE);
+    } else if constexpr (EPI == PN_EPI_MATERN0) {
+        return pn_exp2(pn_sqrt(S) * (P.c_s * P.c_u), tabE);
+    } else if constexpr (EPI == PN_EPI_MATERN1) {
+        double r = pn_sqrt(S) * P.c_s;
+        double e = pn_exp2(r * P.c_u, tabE);
+        return pn_fma(r, e, e);
+    } else if constexpr (EPI == PN_EPI_MATERN2) {
+        double r = pn_sqrt(S) * P.c_s;
+        double e = pn_exp2(r * P.c_u, tabE);
+        return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
+    } else if constexpr (EPI == PN_EPI_MATERNP) {
+        double r = pn_sqrt(S) * P.c_s;
+        double e = pn_exp2(r * P.c_u, tabE);
+        double poly = P.coef[P.p];
+        for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
+        return poly * e;
+    } else if constexpr (EPI == PN_EPI_RATQUAD1) {
+        return pn_rcp(pn_fma(S, P.c_s, 1.0));
+    } else if constexpr (EPI == PN_EPI_RATQUAD2) {
+        double y = pn_rcp(pn_fma(S, P.c_s, 1.0));
+        return y * y;
+    } else {
+        double L = pn_log2_ge1(pn_fma(S, P.c_s, 1.0), tabL);
+        return pn_exp2(-P.alpha * L, tabE);
+    }
+}
+
+template <int EPI, int N, typename T, typename TOut>
+__device__ __forceinline__ void epi_tile(const T (&S)[N], TOut (&K)[N], const PnEpiParams& P,
+                                         const double* tabE, const double* tabL) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if constexpr (std::is_same<TOut, float>::value) {
+            K[i] = exp2f(S[i] * (float)P.c_u);  // float32 ExpQuad stays in float
+        } else {
+            K[i] = epi_one<EPI>((double)S[i], P, tabE, tabL);
+        }
+    }
+}
+
+template <int N, typename T, typename TOut>
+__device__ __forceinline__ void epi_dispatch(const T (&S)[N], TOut (&K)[N], const PnEpiParams& P,
+                                             const double* tabE, const double* tabL) {
+    switch (P.epi) {  // uniform across the grid
+        case PN_EPI_EXPQUAD: epi_tile<PN_EPI_EXPQUAD>(S, K, P, tabE, tabL); break;
+        case PN_EPI_MATERN0: epi_tile<PN_EPI_MATERN0>(S, K, P, tabE, tabL); break;
+        case PN_EPI_MATERN1: epi_tile<PN_EPI_MATERN1>(S, K, P, tabE, tabL); break;
+        case PN_EPI_MATERN2: epi_tile<PN_EPI_MATERN2>(S, K, P, tabE, tabL); break;
+        case PN_EPI_MATERNP: epi_tile<PN_EPI_MATERNP>(S, K, P, tabE, tabL); break;
+        case PN_EPI_RATQUAD1: epi_tile<PN_EPI_RATQUAD1>(S, K, P, tabE, tabL); break;
+        case PN_EPI_RATQUAD2: epi_tile<PN_EPI_RATQUAD2>(S, K, P, tabE, tabL); break;
+        default: epi_tile<PN_EPI_RATQUADG>(S, K, P, tabE, tabL); break;
+    }
+}
+
+template <typename TOut>
+__device__ __forceinline__ void store_pair(TOut* row, int64_t j0, int64_t n1, TOut a, TOut b,
+                                           bool vec_ok) {
+    if (j0 + 1 < n1) {
+        if (vec_ok) {
+            pn_store_cs2(row + j0, a, b);
+        } else {
+            pn_store_cs1(row + j0, a);
+            pn_store_cs1(row + j0 + 1, b);
+        }
+    } else if (j0 < n1) {
+        pn_store_cs1(row + j0, a);
+    }
+}
+
+// ---- strip kernel (d <= G_DMAX) ----------------------------------------------------------
+template <typename T, typename TOut, bool ARD>
+__global__ void __launch_bounds__(G_THREADS)
+    gram_strip_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta, int vec_ok) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using P2 = typename Pair<T>::type;
+
+    const int tid = threadIdx.x;
+    const int d = g.d;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] x1 strip, [1],[2] x0 stages
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    T* sc = reinterpret_cast<T*>(smem + G_HDR_BYTES);
+    T* x1s = reinterpret_cast<T*>(smem + G_HDR_BYTES + 128);
+    T* x0s = x1s + (size_t)d * G_TN;  // [2][d][G_TM]
+
+    const int64_t n_tiles = (g.n0 + G_TM - 1) / G_TM;
+    const int64_t t0 = (int64_t)blockIdx.y * tiles_per_cta;
+    const int64_t t1 = (t0 + tiles_per_cta < n_tiles) ? t0 + tiles_per_cta : n_tiles;
+    if (t0 >= t1) return;
+    const int64_t col0 = (int64_t)blockIdx.x * G_TN;
+
+    const T* x0g = static_cast<const T*>(g.x0_soa);
+    const T* x1g = static_cast<const T*>(g.x1_soa);
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_init(&bars[2], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], (uint32_t)(d * G_TN * sizeof(T)));
+        for (int m = 0; m < d; ++m)
+            pn_bulk_g2s(x1s + (size_t)m * G_TN, x1g + (size_t)m * g.ld1 + col0, G_TN * sizeof(T), &bars[0]);
+        pn_mbar_expect_tx(&bars[1], (uint32_t)(d * G_TM * sizeof(T)));
+        for (int m = 0; m < d; ++m)
+            pn_bulk_g2s(x0s + (size_t)m * G_TM, x0g + (size_t)m * g.ld0 + t0 * G_TM, G_TM * sizeof(T), &bars[1]);
+    }
+    pn_stage_tables(tabE, tabL, tid, G_THREADS);
+    if (ARD && tid < d) sc[tid] = static_cast<const T*>(g.scale)[tid];
+    __syncthreads();
+    pn_mbar_wait(&bars[0], 0);
+
+    const int64_t j0 = col0 + 2 * tid;
+    TOut* out = static_cast<TOut*>(g.out);
+    const T* x1t = x1s + 2 * tid;
+
+    int it = 0;
+    for (int64_t t = t0; t < t1; ++t, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && t + 1 < t1) {
+            T* dst = x0s + (size_t)(buf ^ 1) * d * G_TM;
+            pn_mbar_expect_tx(&bars[1 + (buf ^ 1)], (uint32_t)(d * G_TM * sizeof(T)));
+            for (int m = 0; m < d; ++m)
+                pn_bulk_g2s(dst + (size_t)m * G_TM, x0g + (size_t)m * g.ld0 + (t + 1) * G_TM,
+                            G_TM * sizeof(T), &bars[1 + (buf ^ 1)]);
+        }
+        pn_mbar_wait(&bars[1 + buf], (uint32_t)((it >> 1) & 1));
+        const T* x0t = x0s + (size_t)buf * d * G_TM;
+        const int64_t row_base = t * G_TM;
+        const int rows_here = (g.n0 - row_base < G_TM) ? (int)(g.n0 - row_base) : G_TM;
+
+        for (int rg = 0; rg < rows_here; rg += G_R) {
+            T S[2 * G_R];
+#pragma unroll
+            for (int i = 0; i < 2 * G_R; ++i) S[i] = T(0);
+#pragma unroll 4
+            for (int m = 0; m < d; ++m) {
+                const P2 xb = *reinterpret_cast<const P2*>(x1t + (size_t)m * G_TN);
+                T xa[G_R];
+                if constexpr (std::is_same<T, double>::value) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * G_TM + rg);
+                    const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * G_TM + rg + 2);
+                    xa[0] = a01.x; xa[1] = a01.y; xa[2] = a23.x; xa[3] = a23.y;
+                } else {
+                    const float4 a = *reinterpret_cast<const float4*>(x0t + m * G_TM + rg);
+                    xa[0] = a.x; xa[1] = a.y; xa[2] = a.z; xa[3] = a.w;
+                }
+                T s = T(1);
+                if constexpr (ARD) s = sc[m];
+#pragma unroll
+                for (int r = 0; r < G_R; ++r) {
+                    T da = xa[r] - xb.x;
+                    T db = xa[r] - xb.y;
+                    if constexpr (ARD) {
+                        da *= s;
+                        db *= s;
+                    }
+                    if constexpr (std::is_same<T, double>::value) {
+                        S[2 * r] = pn_fma(da, da, S[2 * r]);
+                        S[2 * r + 1] = pn_fma(db, db, S[2 * r + 1]);
+                    } else {
+                        S[2 * r] = fmaf(da, da, S[2 * r]);
+                        S[2 * r + 1] = fmaf(db, db, S[2 * r + 1]);
+                    }
+                }
+            }
+            TOut K[2 * G_R];
+            epi_dispatch(S, K, g.epi, tabE, tabL);
+#pragma unroll
+            for (int r = 0; r < G_R; ++r) {
+                const int64_t row = row_base + rg + r;
+                if (row < g.n0) store_pair(out + row * g.ldo, j0, g.n1, K[2 * r], K[2 * r + 1], vec_ok != 0);
+            }
+        }
+        __syncthreads();  // everyone is done with x0 stage `buf` before it is refilled
+    }
+}
+
+// ---- chunk kernel (any d): coordinates streamed through shared memory in chunks ------------
+template <typename T, typename TOut, bool ARD>
+__global__ void __launch_bounds__(G_THREADS)
+    gram_chunk_kernel(const __grid_constant__ PnGramLaunch g, int vec_ok) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    using P2 = typename Pair<T>::type;
+    const int tid = threadIdx.x;
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    T* sc = reinterpret_cast<T*>(smem + G_HDR_BYTES);
+    T* x1c = reinterpret_cast<T*>(smem + G_HDR_BYTES + 128);  // [G_DMAX][G_TN]
+    T* x0c = x1c + (size_t)G_DMAX * G_TN;                      // [G_DMAX][G_CHUNK_ROWS]
+
+    const int64_t col0 = (int64_t)blockIdx.x * G_TN;
+    const int64_t row0 = (int64_t)blockIdx.y * G_CHUNK_ROWS;
+    const T* x0g = static_cast<const T*>(g.x0_soa);
+    const T* x1g = static_cast<const T*>(g.x1_soa);
+    pn_stage_tables(tabE, tabL, tid, G_THREADS);
+
+    T S[2 * G_CHUNK_ROWS];
+#pragma unroll
+    for (int i = 0; i < 2 * G_CHUNK_ROWS; ++i) S[i] = T(0);
+
+    for (int c0 = 0; c0 < g.d; c0 += G_DMAX) {
+        const int dc = (g.d - c0 < G_DMAX) ? g.d - c0 : G_DMAX;
+        __syncthreads();
+        for (int idx = tid; idx < dc * G_TN; idx += G_THREADS) {
+            const int m = idx / G_TN, j = idx % G_TN;
+            x1c[idx] = x1g[(size_t)(c0 + m) * g.ld1 + col0 + j];
+        }
+        if (tid < dc * G_CHUNK_ROWS) {
+            const int m = tid / G_CHUNK_ROWS, r = tid % G_CHUNK_ROWS;
+            x0c[tid] = x0g[(size_t)(c0 + m) * g.ld0 + row0 + r];
+        }
+        if (ARD && tid < dc) sc[tid] = static_cast<const T*>(g.scale)[c0 + tid];
+        __syncthreads();
+        for (int m = 0; m < dc; ++m) {
+            const P2 xb = *reinterpret_cast<const P2*>(x1c + (size_t)m * G_TN + 2 * tid);
+            T s = T(1);
+            if constexpr (ARD) s = sc[m];
+#pragma unroll
+            for (int r = 0; r < G_CHUNK_ROWS; ++r) {
+                const T xa = x0c[m * G_CHUNK_ROWS + r];
+                T da = xa - xb.x;
+                T db = xa - xb.y;
+                if constexpr (ARD) {
+                    da *= s;
+                    db *= s;
+                }
+                if constexpr (std::is_same<T, double>::value) {
+                    S[2 * r] = pn_fma(da, da, S[2 * r]);
+                    S[2 * r + 1] = pn_fma(db, db, S[2 * r + 1]);
+                } else {
+                    S[2 * r] = fmaf(da, da, S[2 * r]);
+                    S[2 * r + 1] = fmaf(db, db, S[2 * r + 1]);
+                }
+            }
+        }
+    }
+    TOut K[2 * G_CHUNK_ROWS];
+    epi_dispatch(S, K, g.epi, tabE, tabL);
+    const int64_t j0 = col0 + 2 * tid;
+    TOut* out = static_cast<TOut*>(g.out);
+#pragma unroll
+    for (int r = 0; r < G_CHUNK_ROWS; ++r) {
+        const int64_t row = row0 + r;
+        if (row < g.n0) store_pair(out + row * g.ldo, j0, g.n1, K[2 * r], K[2 * r + 1], vec_ok != 0);
+    }
+}
+
+template <typename T, typename TOut, bool ARD>
+cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
+    if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
+    const int64_t strips = (g.n1 + G_TN - 1) / G_TN;
+    const int vec_ok = ((g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % (2 * sizeof(TOut))) == 0) ? 1 : 0;
+    if (g.d <= G_DMAX) {
+        const int64_t n_tiles = (g.n0 + G_TM - 1) / G_TM;
+        // enough CTAs for ~16 waves on 148 SMs, at least one row tile each
+        int64_t tpc = (n_tiles * strips) / (148 * 48);
+        if (tpc < 1) tpc = 1;
+        if (tpc > 32) tpc = 32;
+        const int64_t gy = (n_tiles + tpc - 1) / tpc;
+        if (gy > 65535) return cudaErrorInvalidConfiguration;
+        const size_t smem = G_HDR_BYTES + 128 + sizeof(T) * ((size_t)g.d * G_TN + 2 * (size_t)g.d * G_TM);
+        auto kern = gram_strip_kernel<T, TOut, ARD>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        dim3 grid((unsigned)strips, (unsigned)gy);
+        kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc, vec_ok);
+    } else {
+        const int64_t gy = (g.n0 + G_CHUNK_ROWS - 1) / G_CHUNK_ROWS;
+        if (gy > 65535) {
+            // split tall outputs into several launches
+            cudaError_t err = cudaSuccess;
+            const int64_t rows_per_launch = 65535LL * G_CHUNK_ROWS;
+            for (int64_t r0 = 0; r0 < g.n0 && err == cudaSuccess; r0 += rows_per_launch) {
+                PnGramLaunch part = g;
+                part.n0 = (g.n0 - r0 < rows_per_launch) ? g.n0 - r0 : rows_per_launch;
+                part.x0_soa = static_cast<const T*>(g.x0_soa) + r0;
+                part.out = static_cast<TOut*>(g.out) + r0 * g.ldo;
+                err = launch_typed<T, TOut, ARD>(part, stream);
+            }
+            return err;
+        }
+        const size_t smem = G_HDR_BYTES + 128 + sizeof(T) * ((size_t)G_DMAX * G_TN + (size_t)G_DMAX * G_CHUNK_ROWS);
+        auto kern = gram_chunk_kernel<T, TOut, ARD>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        dim3 grid((unsigned)strips, (unsigned)gy);
+        kern<<<grid, G_THREADS, smem, stream>>>(g, vec_ok);
+    }
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
+    const bool ard = g.scale != nullptr;
+    if (!g.in_f32) {
+        return ard ? launch_typed<double, double, true>(g, stream) : launch_typed<double, double, false>(g, stream);
+    }
+    if (g.out_f32) {
+        return ard ? launch_typed<float, float, true>(g, stream) : launch_typed<float, float, false>(g, stream);
+    }
+    return ard ? launch_typed<float, double, true>(g, stream) : launch_typed<float, double, false>(g, stream);
+}

@@ -1,0 +1,62 @@
+// Host-side interfaces between the C-ABI layer (pncov_api.cu) and the kernel launchers.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pncov_common.cuh"
+
+// point sets are padded (with zeros) to a multiple of this many points so that every
+// tile is a full, 16-byte aligned TMA bulk copy
+#define PN_PAD 512
+
+struct PnGramLaunch {
+    const void* x0_soa;  // (d, ld0) row tile source: coordinate-major copy of the row point set
+    const void* x1_soa;  // (d, ld1) column point set
+    int64_t ld0, ld1;
+    int64_t n0, n1;      // logical Gram shape
+    const void* scale;   // d per-dimension scale factors (element type = point dtype) or nullptr
+    int d;
+    void* out;           // (n0, n1) row-major
+    int64_t ldo;
+    int in_f32;          // points are float32
+    int out_f32;         // Gram entries are float32 (only ExpQuad on float32 points)
+    PnEpiParams epi;
+};
+
+struct PnMatvecLaunch {
+    const void* x0_aos;  // (n0pad, d) row point set (rows of K)
+    const void* x1_aos;  // (n1pad, d) column point set, zero padded
+    const void* x1_soa;  // (d, ld1) coordinate-major copy of the same points (generic kernel)
+    int64_t ld1;
+    int64_t n0, n1, n1pad;
+    const void* scale;   // as above
+    int d;
+    const void* v;       // (n1pad, kc) packed, zero padded rows, element type = point dtype
+    void* y;             // (n0, kc) packed
+    int kc;              // columns in this pass (1, 2, 4 or 8)
+    void* partial;       // (jsplit, n0, kc) scratch when jsplit > 1
+    int jsplit;
+    int in_f32;
+    PnEpiParams epi;
+};
+
+struct PnPairsLaunch {
+    const void* x0;  // (b, d) row-major
+    const void* x1;
+    int64_t b;
+    const void* scale;
+    int d;
+    void* out;
+    int in_f32, out_f32;
+    PnEpiParams epi;
+};
+
+cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
+cudaError_t pn_launch_matvec(const PnMatvecLaunch& m, cudaStream_t stream);
+cudaError_t pn_launch_pairs(const PnPairsLaunch& p, cudaStream_t stream);
+// how many column-range splits pn_launch_matvec wants for this shape (scratch sizing)
+int pn_matvec_jsplit(int64_t n0, int64_t n1, int d, int sm_count);
+
+// small utility kernels (pncov_api.cu)
+extern int64_t g_pn_launches;

@@ -1,0 +1,419 @@
+// Matrix-free product Y = K(X0, X1) @ V: K is evaluated tile by tile in registers and
+// never stored.
+//
+// Replaces CovarianceLinearOperator._matmul
+// (/root/reference/src/probnum/randprocs/covfuncs/_covariance_linear_operator.py:78-81),
+// i.e. both the KeOps map-reduce (`keops_lazy_tensor @ x`, formulas built in
+// _covariance_function.py:805-846, _exponentiated_quadratic.py:102-111,
+// _matern.py:197-223) and the dense fallback `self.todense() @ x`.
+//
+// The work is O(N0 N1 d) FP64 operations on O((N0 + N1) d) bytes, so the FP64 pipe is the
+// roofline.  Layout of the main kernel (d <= 8, float64):
+//
+//   * each thread owns MV_R rows of K; their points stay in registers for the whole kernel;
+//   * column points and the matching rows of V stream through shared memory in tiles of
+//     MV_TJ points, fetched by 1-D TMA bulk copies into a two-stage mbarrier pipeline, and
+//     are read back as warp-wide broadcasts (every lane needs the same x1_j);
+//   * per pair: d DADD + d DFMA (+ d DMUL with ARD scale factors), the epilogue of
+//     pncov_math.cuh (8 FP64 ops for exp2), one DFMA per right-hand side;
+//   * accumulation over j is sequential per row and per column split, partial sums of the
+//     column splits are combined in a fixed order: results are run-to-run deterministic.
+#include <type_traits>
+
+#include "pncov_internal.h"
+
+namespace {
+
+constexpr int MV_THREADS = 128;
+constexpr int MV_R = 2;     // rows per thread
+constexpr int MV_TJ = 128;  // column points per pipeline stage
+constexpr int MV_HDR_BYTES = 128 + 8 * (PN_EXP2_N + 2 * PN_LOG2_N);
+
+template <int EPI>
+__device__ __forceinline__ double mv_epi_one(double S, const PnEpiParams& P, const double* tabE,
+                                             const double* tabL) {
+    if constexpr (EPI == PN_EPI_EXPQUAD) {
+        return pn_exp2(S * P.c_u, tabE);
+    } else if constexpr (EPI == PN_EPI_MATERN0) {
+        return pn_exp2(pn_sqrt(S) * (P.c_s * P.c_u), tabE);
+    } else if constexpr (EPI == PN_EPI_MATERN1) {
+        double r = pn_sqrt(S) * P.c_s;
+        double e = pn_exp2(r * P.c_u, tabE);
+        return pn_fma(r, e, e);
+    } else if constexpr (EPI == PN_EPI_MATERN2) {
+        double r = pn_sqrt(S) * P.c_s;
+        double e = pn_exp2(r * P.c_u, tabE);
+        return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
+    } else if constexpr (EPI == PN_EPI_MATERNP) {
+        double r = pn_sqrt(S) * P.c_s;
+        double e = pn_exp2(r * P.c_u, tabE);
+        double poly = P.coef[P.p];
+        for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
+        return poly * e;
+    } else if constexpr (EPI == PN_EPI_RATQUAD1) {
+        return pn_rcp(pn_fma(S, P.c_s, 1.0));
+    } else if constexpr (EPI == PN_EPI_RATQUAD2) {
+        double y = pn_rcp(pn_fma(S, P.c_s, 1.0));
+        return y * y;
+    } else {
+        double L = pn_log2_ge1(pn_fma(S, P.c_s, 1.0), tabL);
+        return pn_exp2(-P.alpha * L, tabE);
+    }
+}
+
+template <int EPI, int N>
+__device__ __forceinline__ void mv_epi_tile(double (&S)[N], const PnEpiParams& P, const double* tabE,
+                                            const double* tabL) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) S[i] = mv_epi_one<EPI>(S[i], P, tabE, tabL);
+}
+
+template <int N>
+__device__ __forceinline__ void mv_epi_dispatch(double (&S)[N], const PnEpiParams& P,
+                                                const double* tabE, const double* tabL) {
+    switch (P.epi) {
+        case PN_EPI_EXPQUAD: mv_epi_tile<PN_EPI_EXPQUAD>(S, P, tabE, tabL); break;
+        case PN_EPI_MATERN0: mv_epi_tile<PN_EPI_MATERN0>(S, P, tabE, tabL); break;
+        case PN_EPI_MATERN1: mv_epi_tile<PN_EPI_MATERN1>(S, P, tabE, tabL); break;
+        case PN_EPI_MATERN2: mv_epi_tile<PN_EPI_MATERN2>(S, P, tabE, tabL); break;
+        case PN_EPI_MATERNP: mv_epi_tile<PN_EPI_MATERNP>(S, P, tabE, tabL); break;
+        case PN_EPI_RATQUAD1: mv_epi_tile<PN_EPI_RATQUAD1>(S, P, tabE, tabL); break;
+        case PN_EPI_RATQUAD2: mv_epi_tile<PN_EPI_RATQUAD2>(S, P, tabE, tabL); break;
+        default: mv_epi_tile<PN_EPI_RATQUADG>(S, P, tabE, tabL); break;
+    }
+}
+
+// ---- main kernel: float64, compile-time d in 1..8 -------------------------------------------
+template <int D, bool ARD, int KC>
+__global__ void __launch_bounds__(MV_THREADS)
+    matvec_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    constexpr int STAGE_DOUBLES = MV_TJ * (D + KC);
+    double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
+
+    const int64_t n_jt = a.n1pad / MV_TJ;
+    const int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+
+    const double* x1g = static_cast<const double*>(a.x1_aos);
+    const double* vg = static_cast<const double*>(a.v);
+    constexpr uint32_t X_BYTES = MV_TJ * D * 8, V_BYTES = MV_TJ * KC * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && jt0 < jt1) {
+        pn_mbar_expect_tx(&bars[0], X_BYTES + V_BYTES);
+        pn_bulk_g2s(stage0, x1g + jt0 * MV_TJ * D, X_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + MV_TJ * D, vg + jt0 * MV_TJ * KC, V_BYTES, &bars[0]);
+    }
+    pn_stage_tables(tabE, tabL, tid, MV_THREADS);
+
+    // this thread's rows (the row point set is zero padded to a multiple of PN_PAD rows)
+    const int64_t row0 = (int64_t)blockIdx.x * (MV_THREADS * MV_R) + tid;
+    double xr[MV_R][D];
+    {
+        const double* x0g = static_cast<const double*>(a.x0_aos);
+#pragma unroll
+        for (int r = 0; r < MV_R; ++r)
+#pragma unroll
+            for (int m = 0; m < D; ++m) xr[r][m] = x0g[(row0 + (int64_t)r * MV_THREADS) * D + m];
+    }
+    double sc[D];
+    if constexpr (ARD) {
+#pragma unroll
+        for (int m = 0; m < D; ++m) sc[m] = static_cast<const double*>(a.scale)[m];
+    }
+    double acc[MV_R][KC];
+#pragma unroll
+    for (int r = 0; r < MV_R; ++r)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) acc[r][k] = 0.0;
+    __syncthreads();
+
+    int it = 0;
+    for (int64_t jt = jt0; jt < jt1; ++jt, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && jt + 1 < jt1) {
+            double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
+            pn_mbar_expect_tx(&bars[buf ^ 1], X_BYTES + V_BYTES);
+            pn_bulk_g2s(dst, x1g + (jt + 1) * MV_TJ * D, X_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + MV_TJ * D, vg + (jt + 1) * MV_TJ * KC, V_BYTES, &bars[buf ^ 1]);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* xt = stage0 + (size_t)buf * STAGE_DOUBLES;
+        const double* vt = xt + MV_TJ * D;
+
+#pragma unroll 1
+        for (int jj = 0; jj < MV_TJ; jj += 2) {
+            double xb[2][D];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                if constexpr (D % 2 == 0) {
+#pragma unroll
+                    for (int m = 0; m < D; m += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(xt + (jj + c) * D + m);
+                        xb[c][m] = t.x;
+                        xb[c][m + 1] = t.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < D; ++m) xb[c][m] = xt[(jj + c) * D + m];
+                }
+            }
+            double S[2 * MV_R];
+#pragma unroll
+            for (int r = 0; r < MV_R; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) {
+                        double df = xr[r][m] - xb[c][m];
+                        if constexpr (ARD) df *= sc[m];
+                        s = pn_fma(df, df, s);
+                    }
+                    S[2 * r + c] = s;
+                }
+            mv_epi_dispatch(S, a.epi, tabE, tabL);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const double vk = vt[(jj + c) * KC + k];
+#pragma unroll
+                    for (int r = 0; r < MV_R; ++r) acc[r][k] = pn_fma(S[2 * r + c], vk, acc[r][k]);
+                }
+        }
+        __syncthreads();
+    }
+
+    double* dst = (a.jsplit > 1) ? static_cast<double*>(a.partial) + (size_t)blockIdx.y * a.n0 * KC
+                                 : static_cast<double*>(a.y);
+#pragma unroll
+    for (int r = 0; r < MV_R; ++r) {
+        const int64_t row = row0 + (int64_t)r * MV_THREADS;
+        if (row < a.n0) {
+#pragma unroll
+            for (int k = 0; k < KC; ++k) dst[row * KC + k] = acc[r][k];
+        }
+    }
+}
+
+// ---- generic kernel: any d <= 1024, float64 or float32 points ---------------------------------
+// One row per thread, its point read through L1 each time; column points in coordinate-major
+// shared-memory tiles, four columns per register tile.  Slower than the main kernel (extra
+// L1 traffic); used for d > 8 and for float32.
+constexpr int MG_THREADS = 128;
+
+template <typename T, bool ARD, int KC>
+__global__ void __launch_bounds__(MG_THREADS)
+    matvec_generic_kernel(const __grid_constant__ PnMatvecLaunch a, const T* __restrict__ x1_soa,
+                          int64_t ld1, int tj, int tiles_per_split) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int d = a.d;
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    T* sc = reinterpret_cast<T*>(smem + MV_HDR_BYTES);        // [d]
+    T* xt = sc + ((d + 3) / 4) * 4;                            // [d][tj]
+    double* vt = reinterpret_cast<double*>(xt + (size_t)d * tj);  // [tj][KC] (8-byte aligned: d*tj*4 % 8 == 0)
+
+    pn_stage_tables(tabE, tabL, tid, MG_THREADS);
+    for (int m = tid; m < d; m += MG_THREADS) sc[m] = ARD ? static_cast<const T*>(a.scale)[m] : T(1);
+
+    const int64_t row = (int64_t)blockIdx.x * MG_THREADS + tid;
+    const T* xrow = static_cast<const T*>(a.x0_aos) + row * d;  // padded rows are readable
+    const T* vg = static_cast<const T*>(a.v);
+
+    const int64_t n_jt = (a.n1pad + tj - 1) / tj;
+    const int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+
+    double acc[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) acc[k] = 0.0;
+
+    for (int64_t jt = jt0; jt < jt1; ++jt) {
+        const int64_t jbase = jt * tj;
+        __syncthreads();
+        for (int idx = tid; idx < d * tj; idx += MG_THREADS) {
+            const int m = idx / tj, j = idx % tj;
+            xt[idx] = (jbase + j < a.n1pad) ? x1_soa[(size_t)m * ld1 + jbase + j] : T(0);
+        }
+        for (int idx = tid; idx < tj * KC; idx += MG_THREADS) {
+            const int64_t j = jbase + idx / KC;
+            vt[idx] = (j < a.n1pad) ? (double)vg[j * KC + idx % KC] : 0.0;
+        }
+        __syncthreads();
+        for (int jj = 0; jj < tj; jj += 4) {
+            T S[4] = {T(0), T(0), T(0), T(0)};
+            for (int m = 0; m < d; ++m) {
+                const T xa = __ldg(xrow + m);
+                T s = T(1);
+                if constexpr (ARD) s = sc[m];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    T df = xa - xt[m * tj + jj + c];
+                    if constexpr (ARD) df *= s;
+                    if constexpr (std::is_same<T, double>::value) S[c] = pn_fma(df, df, S[c]);
+                    else S[c] = fmaf(df, df, S[c]);
+                }
+            }
+            double Kv[4];
+            if constexpr (std::is_same<T, float>::value) {
+                if (a.epi.epi == PN_EPI_EXPQUAD) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Kv[c] = (double)exp2f(S[c] * (float)a.epi.c_u);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) Kv[c] = (double)S[c];
+                    mv_epi_dispatch(Kv, a.epi, tabE, tabL);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) Kv[c] = S[c];
+                mv_epi_dispatch(Kv, a.epi, tabE, tabL);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[k] = pn_fma(Kv[c], vt[(jj + c) * KC + k], acc[k]);
+        }
+    }
+    if (row < a.n0) {
+        if (a.jsplit > 1) {
+            double* dst = static_cast<double*>(a.partial) + ((size_t)blockIdx.y * a.n0 + row) * KC;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) dst[k] = acc[k];
+        } else {
+            T* dst = static_cast<T*>(a.y) + row * KC;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) dst[k] = (T)acc[k];
+        }
+    }
+}
+
+// partial[s][i] summed over s in increasing order (deterministic)
+template <typename T>
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, T* __restrict__ y,
+                                       int64_t n, int jsplit) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = partial[i];
+    for (int k = 1; k < jsplit; ++k) s += partial[(size_t)k * n + i];
+    y[i] = (T)s;
+}
+
+template <int D, bool ARD, int KC>
+cudaError_t launch_main(const PnMatvecLaunch& a, cudaStream_t stream) {
+    const int64_t n_jt = a.n1pad / MV_TJ;
+    const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MV_TJ * (D + KC);
+    auto kern = matvec_kernel<D, ARD, KC>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    dim3 grid((unsigned)((a.n0 + MV_THREADS * MV_R - 1) / (MV_THREADS * MV_R)), (unsigned)a.jsplit);
+    kern<<<grid, MV_THREADS, smem, stream>>>(a, (int)tps);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int D, bool ARD>
+cudaError_t launch_main_kc(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.kc) {
+        case 1: return launch_main<D, ARD, 1>(a, stream);
+        case 4: return launch_main<D, ARD, 4>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <bool ARD>
+cudaError_t launch_main_d(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.d) {
+        case 1: return launch_main_kc<1, ARD>(a, stream);
+        case 2: return launch_main_kc<2, ARD>(a, stream);
+        case 3: return launch_main_kc<3, ARD>(a, stream);
+        case 4: return launch_main_kc<4, ARD>(a, stream);
+        case 5: return launch_main_kc<5, ARD>(a, stream);
+        case 6: return launch_main_kc<6, ARD>(a, stream);
+        case 7: return launch_main_kc<7, ARD>(a, stream);
+        case 8: return launch_main_kc<8, ARD>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int generic_tj(int d, size_t elem) {
+    // coordinate-major tile of tj points: keep it under ~40 KB
+    int tj = (int)((40 * 1024) / ((size_t)d * elem));
+    tj = (tj / 4) * 4;
+    if (tj > 128) tj = 128;
+    return tj;
+}
+
+template <typename T, bool ARD, int KC>
+cudaError_t launch_generic(const PnMatvecLaunch& a, const void* x1_soa, int64_t ld1, cudaStream_t stream) {
+    const int tj = generic_tj(a.d, sizeof(T));
+    if (tj < 4) return cudaErrorInvalidValue;
+    const int64_t n_jt = (a.n1pad + tj - 1) / tj;
+    const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
+    const size_t smem = MV_HDR_BYTES + sizeof(T) * (((a.d + 3) / 4) * 4 + (size_t)a.d * tj) + 8 * (size_t)tj * KC + 16;
+    auto kern = matvec_generic_kernel<T, ARD, KC>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    dim3 grid((unsigned)((a.n0 + MG_THREADS - 1) / MG_THREADS), (unsigned)a.jsplit);
+    kern<<<grid, MG_THREADS, smem, stream>>>(a, static_cast<const T*>(x1_soa), ld1, tj, (int)tps);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int pn_matvec_jsplit(int64_t n0, int64_t n1, int d, int sm_count) {
+    // aim for >= 8 CTAs per SM in flight-equivalents; each CTA covers 256 rows (main kernel)
+    const int64_t row_ctas = (n0 + 255) / 256;
+    const int64_t want = (int64_t)sm_count * 8;
+    int64_t split = (want + row_ctas - 1) / row_ctas;
+    const int64_t max_split = (n1 + 4 * MV_TJ - 1) / (4 * MV_TJ);  // at least 4 tiles per split
+    if (split > max_split) split = max_split;
+    if (split > 64) split = 64;
+    if (split < 1) split = 1;
+    (void)d;
+    return (int)split;
+}
+
+cudaError_t pn_launch_matvec(const PnMatvecLaunch& a, cudaStream_t stream) {
+    if (a.n0 <= 0) return cudaSuccess;
+    const void* x1_soa = a.x1_soa;
+    const int64_t ld1 = a.ld1;
+    const bool ard = a.scale != nullptr;
+    cudaError_t err;
+    if (!a.in_f32 && a.d <= 8) {
+        err = ard ? launch_main_d<true>(a, stream) : launch_main_d<false>(a, stream);
+    } else if (!a.in_f32) {
+        if (a.kc == 1) err = ard ? launch_generic<double, true, 1>(a, x1_soa, ld1, stream) : launch_generic<double, false, 1>(a, x1_soa, ld1, stream);
+        else err = ard ? launch_generic<double, true, 4>(a, x1_soa, ld1, stream) : launch_generic<double, false, 4>(a, x1_soa, ld1, stream);
+    } else {
+        if (a.kc == 1) err = ard ? launch_generic<float, true, 1>(a, x1_soa, ld1, stream) : launch_generic<float, false, 1>(a, x1_soa, ld1, stream);
+        else err = ard ? launch_generic<float, true, 4>(a, x1_soa, ld1, stream) : launch_generic<float, false, 4>(a, x1_soa, ld1, stream);
+    }
+    if (err != cudaSuccess) return err;
+    if (a.jsplit > 1) {
+        const int64_t n = a.n0 * a.kc;
+        const unsigned blocks = (unsigned)((n + 255) / 256);
+        if (a.in_f32)
+            reduce_partials_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const double*>(a.partial), static_cast<float*>(a.y), n, a.jsplit);
+        else
+            reduce_partials_kernel<double><<<blocks, 256, 0, stream>>>(static_cast<const double*>(a.partial), static_cast<double*>(a.y), n, a.jsplit);
+        ++g_pn_launches;
+        err = cudaGetLastError();
+    }
+    return err;
+}

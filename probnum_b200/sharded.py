@@ -1,0 +1,123 @@
+"""Row-sharded covariance operator: one process per GPU over ``torch.distributed``.
+
+K(X0, X1) is partitioned by contiguous row blocks of X0: rank g keeps
+rows ``[lo_g, hi_g)`` of X0 and all of X1 resident on its GPU, computes its slice of
+``Y = K @ V`` with the matrix-free kernel and the slices are reassembled with ONE
+all-gather (NCCL over NVLink for device tensors, gloo in the CPU tests).  The Gram
+matrix shards the same way and needs no collective at all: each rank owns its row
+block.  The operand ``V`` is replicated (every rank of a linear solver holds the same
+iterate), so nothing else is exchanged.
+
+This is the only communication step of the path; it moves N0*K*8 bytes per product
+(8 MiB at N = 2^20, K = 1) next to O(N0*N1*d) flops, so it is latency-sized.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced row block of rank ``rank``: sizes differ by at most one."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("invalid rank / world size")
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist  # noqa: PLC0415
+
+    return dist
+
+
+class ShardedCovarianceOperator:
+    """``K(x0, x1)`` with the rows of ``x0`` split over the ranks of ``group``.
+
+    ``local_factory(params, x0_block, x1)`` builds the per-rank operator; it defaults to
+    the CUDA operator and exists so that the CPU (gloo) tests can exercise the sharding
+    and gather logic with a stand-in.  The object exposes the same ``shape`` / ``dtype`` /
+    ``@`` surface as :class:`probnum_b200.covfuncs.CovarianceLinearOperator`.
+    """
+
+    def __init__(self, covfunc, x0, x1=None, *, group=None,
+                 local_factory: Optional[Callable] = None, device: Optional[int] = None):
+        dist = _dist()
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        x0 = covfunc._preprocess_linop_input(x0, argnum=0)
+        x1 = x0 if x1 is None else covfunc._preprocess_linop_input(x1, argnum=1)
+        self.shape = (x0.shape[0], x1.shape[0])
+        dt = covfunc._compute_dtype(x0, x1)
+        self.dtype = dt
+        self.lo, self.hi = shard_bounds(self.shape[0], self.world, self.rank)
+        self.max_rows = shard_bounds(self.shape[0], self.world, 0)[1]
+        rows = covfunc._points(x0[self.lo:self.hi], dt)
+        cols = covfunc._points(x1, dt)
+        if local_factory is None:
+            self.local = _lib.Operator(covfunc._kernel_params(), rows, cols, device=device)
+        else:
+            self.local = local_factory(covfunc._kernel_params(), rows, cols)
+
+    # -- host operands (NumPy in, NumPy out; gloo or NCCL via a staging tensor) -------------------
+    def matmul(self, v: np.ndarray) -> np.ndarray:
+        """Full ``K @ v`` on every rank; ``v`` is (N1,) or (N1, K) and replicated."""
+        import torch  # noqa: PLC0415
+
+        dist = _dist()
+        vec = v.ndim == 1
+        v2 = np.ascontiguousarray(v.reshape(v.shape[0], -1), dtype=self.dtype)
+        k = v2.shape[1]
+        y_local = self.local.matmul(v2)  # (hi - lo, k)
+        pad = np.zeros((self.max_rows, k), dtype=self.dtype)
+        pad[: self.hi - self.lo] = y_local
+        backend = dist.get_backend(self.group)
+        send = torch.from_numpy(pad)
+        if backend == "nccl":
+            send = send.cuda(self.local.device)
+        gathered = torch.empty((self.world * self.max_rows, k), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(gathered, send, group=self.group)
+        g = gathered.cpu().numpy().reshape(self.world, self.max_rows, k)
+        sizes = [hi - lo for lo, hi in (shard_bounds(self.shape[0], self.world, r) for r in range(self.world))]
+        out = np.concatenate([g[r, :sizes[r]] for r in range(self.world)], axis=0)
+        return out[:, 0] if vec else out
+
+    def __matmul__(self, v):
+        return self.matmul(np.asarray(v))
+
+    # -- device operands (torch CUDA tensors; NCCL all-gather on the current stream) ----------------
+    def matmul_device(self, v, out=None):
+        """``v``: CUDA tensor (N1, K) replicated on every rank.  Returns the full
+        (N0, K) product on every rank.  Equal shards are required (N0 % world == 0) so the
+        all-gather writes straight into the result."""
+        import torch  # noqa: PLC0415
+
+        dist = _dist()
+        n0, n1 = self.shape
+        if n0 % self.world:
+            raise ValueError("matmul_device needs N0 divisible by the number of ranks")
+        if v.dim() != 2 or v.shape[0] != n1 or not v.is_contiguous():
+            raise ValueError("v must be a contiguous (N1, K) CUDA tensor")
+        k = v.shape[1]
+        rows = self.hi - self.lo
+        if out is None:
+            out = torch.empty((n0, k), dtype=v.dtype, device=v.device)
+        y_local = out[self.lo:self.hi]  # contiguous row block of the result
+        stream = torch.cuda.current_stream(v.device).cuda_stream
+        self.local.matmul_device(v.data_ptr(), k, k, y_local.data_ptr(), k, stream=stream)
+        if self.world > 1:
+            dist.all_gather_into_tensor(out, y_local, group=self.group)
+        assert rows * self.world == n0
+        return out
+
+    def close(self):
+        if hasattr(self.local, "close"):
+            self.local.close()

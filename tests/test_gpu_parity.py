@@ -1,0 +1,292 @@
+"""Parity of the CUDA path against the pinned oracle and the reference's golden vectors.
+
+Everything here runs on a B200 (``-m gpu``) and goes through the public mirror API
+(``probnum_b200.covfuncs``), i.e. through the C ABI of libpncov.so.  The tolerance is
+the reference's own: ``assert_allclose(rtol=1e-12, atol=1e-12)``
+(tests/test_randprocs/test_covfuncs/test_call.py:123-135, test_linop_matrix.py:111-154)
+for float64, 1e-5 for float32; matrix-free products use the componentwise bound
+``|dy_i| <= tol * (|K| |v|)_i`` of SURVEY.md 8d.
+"""
+
+import zlib
+
+import numpy as np
+import pytest
+
+import probnum_b200 as pb
+from oracle import covfuncs_oracle as orc
+from tests.conftest import load_golden, spec_from_dict
+
+pytestmark = pytest.mark.gpu
+
+G = load_golden()
+GRAM_CASES = [c for c in G.cases if c["type"] == "gram"]
+CALL_CASES = [c for c in G.cases if c["type"] == "call"]
+
+
+def make_kernel(spec: orc.KernelSpec):
+    if spec.kind == orc.EXPQUAD:
+        return pb.ExpQuad(spec.input_shape, lengthscales=spec.lengthscales)
+    if spec.kind == orc.MATERN:
+        return pb.Matern(spec.input_shape, nu=spec.nu, lengthscales=spec.lengthscales)
+    return pb.RatQuad(spec.input_shape, lengthscale=spec.lengthscales, alpha=spec.alpha)
+
+
+def tol_for(dtype):
+    return 1e-12 if np.dtype(dtype) == np.float64 else 1e-5
+
+
+def assert_matvec_close(got, want, bound, tol):
+    assert got.shape == want.shape
+    err = np.abs(got - want)
+    assert np.all(err <= tol * bound + 1e-300), float(np.max(err / (bound + 1e-300)))
+
+
+# ---------------------------------------------------------------------------------------------
+# golden vectors recorded from the real reference
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("entry", G.kat, ids=[e["cite"].split("/")[-1] for e in G.kat])
+def test_docstring_known_answers(entry):
+    spec = spec_from_dict(entry["spec"])
+    got = make_kernel(spec).matrix(G.get(entry["x"]))
+    np.testing.assert_allclose(got, np.asarray(entry["doc"]), rtol=5e-8)
+    np.testing.assert_allclose(got, G.get(entry["ref"]), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_gram_matches_reference_golden(chunk):
+    for case in GRAM_CASES[chunk::8]:
+        spec = spec_from_dict(case["spec"])
+        k = make_kernel(spec)
+        x0, x1, want = G.get(case["x0"]), G.get(case["x1"]), G.get(case["K"])
+        got = k.matrix(x0, x1)
+        tol = tol_for(case["dtype"])
+        assert got.dtype == want.dtype, case["spec"]
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=tol, atol=tol, err_msg=str(case["spec"]))
+
+
+@pytest.mark.parametrize("chunk", range(8))
+def test_linop_matches_reference_golden(chunk):
+    for case in GRAM_CASES[chunk::8]:
+        spec = spec_from_dict(case["spec"])
+        k = make_kernel(spec)
+        x0, x1, v = G.get(case["x0"]), G.get(case["x1"]), G.get(case["v"])
+        tol = tol_for(case["dtype"])
+        L = k.linop(x0, x1)
+        assert L.shape == G.get(case["K"]).shape
+        assert L.dtype == np.dtype(case["dtype"])
+        bound = np.abs(G.get(case["K"]).astype(np.float64)) @ np.abs(v.astype(np.float64))
+        assert_matvec_close(L @ v, G.get(case["Kv"]), bound, tol)
+        assert_matvec_close(L @ v[:, 0], G.get(case["Kv"])[:, 0], bound[:, 0], tol)
+        # todense == matrix (test_linop_matrix.py:111-123)
+        np.testing.assert_allclose(L.todense(), G.get(case["K"]), rtol=tol, atol=tol)
+        L.close()
+
+
+@pytest.mark.parametrize("chunk", range(4))
+def test_call_matches_reference_golden(chunk):
+    for case in CALL_CASES[chunk::4]:
+        spec = spec_from_dict(case["spec"])
+        got = make_kernel(spec)(G.get(case["x0"]), G.get(case["x1"]))
+        want = G.get(case["out"])
+        assert isinstance(got, (np.ndarray, np.floating))
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded comparisons with the oracle at sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------
+SPECS = [
+    orc.KernelSpec("expquad", (3,), 1.0),
+    orc.KernelSpec("expquad", (8,), 1.5),
+    orc.KernelSpec("matern", (3,), 0.7, nu=0.5),
+    orc.KernelSpec("matern", (3,), 1.0, nu=1.5),
+    orc.KernelSpec("matern", (3,), 1.0, nu=2.5),
+    orc.KernelSpec("matern", (4,), 1.3, nu=3.5),
+    orc.KernelSpec("ratquad", (3,), 1.0, alpha=1.0),
+    orc.KernelSpec("ratquad", (3,), 0.5, alpha=2.0),
+    orc.KernelSpec("ratquad", (5,), 1.7, alpha=0.37),
+]
+
+
+@pytest.mark.parametrize("spec", SPECS, ids=lambda s: f"{s.kind}-d{s.input_shape[0]}-nu{s.nu}-a{s.alpha}")
+@pytest.mark.parametrize("shape", [(1000, 777), (513, 1025), (2048, None)])
+def test_gram_vs_oracle(spec, shape):
+    rng = np.random.default_rng(zlib.crc32(repr((spec, shape)).encode()))
+    n0, n1 = shape
+    x0 = rng.normal(size=(n0,) + spec.input_shape)
+    x1 = None if n1 is None else rng.normal(size=(n1,) + spec.input_shape)
+    got = make_kernel(spec).matrix(x0, x1)
+    np.testing.assert_allclose(got, orc.gram(spec, x0, x1), rtol=1e-12, atol=1e-12)
+    if n1 is None:
+        np.testing.assert_array_equal(np.diag(got), np.ones(n0))
+        np.testing.assert_array_equal(got, got.T)
+
+
+@pytest.mark.parametrize("d", [1, 2, 5, 7, 10, 16, 17, 33, 100])
+@pytest.mark.parametrize("kind", ["expquad", "matern", "ratquad"])
+def test_gram_dimensions_and_ard(kind, d):
+    rng = np.random.default_rng(d)
+    ard = rng.gamma(1.0, size=d) + 0.5
+    ls = 0.9 * np.sqrt(d) if kind == "ratquad" else ard * np.sqrt(d)
+    spec = orc.KernelSpec(kind, (d,), ls, nu=2.5, alpha=1.5)
+    x0 = rng.normal(size=(301, d))
+    x1 = rng.normal(size=(155, d))
+    k = make_kernel(spec)
+    np.testing.assert_allclose(k.matrix(x0, x1), orc.gram(spec, x0, x1), rtol=1e-12, atol=1e-12)
+    v = rng.normal(size=(155, 3))
+    L = k.linop(x0, x1)
+    assert_matvec_close(L @ v, orc.matvec(spec, x0, x1, v), orc.abs_matvec(spec, x0, x1, v), 1e-12)
+    vt = rng.normal(size=(301,))
+    assert_matvec_close(L.T @ vt, orc.matvec(spec, x1, x0, vt), orc.abs_matvec(spec, x1, x0, vt), 1e-12)
+    L.close()
+
+
+@pytest.mark.parametrize("spec", SPECS[:7:2], ids=lambda s: s.kind + str(s.nu))
+def test_uncentred_and_duplicated_points(spec):
+    """Direct differences keep full accuracy for clouds far from the origin and for
+    coincident points (hard parts): the failure mode of the norm identity."""
+    rng = np.random.default_rng(7)
+    x = rng.normal(size=(400,) + spec.input_shape) + 1.0e4
+    x[10] = x[20]
+    x[11] = x[21] * (1 + 1e-15)
+    K = make_kernel(spec).matrix(x)
+    np.testing.assert_allclose(K, orc.gram(spec, x), rtol=1e-12, atol=1e-12)
+    assert K[10, 20] == 1.0 and K[20, 10] == 1.0
+
+
+def test_scalar_input_shape_and_batches():
+    """input_shape = () and multi-dimensional batch shapes are flattened in C order
+    (_covariance_function.py:676-693)."""
+    rng = np.random.default_rng(3)
+    spec = orc.KernelSpec("matern", (), 0.4, nu=1.5)
+    k = make_kernel(spec)
+    x0 = rng.normal(size=(6, 5))
+    x1 = rng.normal(size=(4, 3, 2))
+    K = k.matrix(x0, x1)
+    assert K.shape == (30, 24)
+    np.testing.assert_allclose(K, orc.gram(spec, x0, x1), rtol=1e-12, atol=1e-12)
+    spec3 = orc.KernelSpec("expquad", (3,), 1.1)
+    k3 = make_kernel(spec3)
+    y0 = rng.normal(size=(2, 5, 3))
+    np.testing.assert_allclose(k3.matrix(y0), orc.gram(spec3, y0), rtol=1e-12, atol=1e-12)
+
+
+def test_underflow_and_far_field():
+    """exp underflow to subnormals and zero takes the slow branch of pn_exp2."""
+    rng = np.random.default_rng(11)
+    spec = orc.KernelSpec("expquad", (2,), 0.02)
+    x = rng.uniform(-1.0, 1.0, size=(600, 2))
+    K = make_kernel(spec).matrix(x)
+    ref = orc.gram(spec, x)
+    np.testing.assert_allclose(K, ref, rtol=1e-12, atol=1e-12)
+    nz = ref > 1e-290
+    np.testing.assert_allclose(K[nz], ref[nz], rtol=2e-12, atol=0.0)  # relative, even in the tail
+    assert np.all(K[ref == 0.0] == 0.0)
+    sub = (ref > 0) & (ref < 2.3e-308)
+    assert sub.any()
+    np.testing.assert_allclose(K[sub], ref[sub], rtol=1e-9, atol=5e-324)
+
+
+def test_float32_dtypes_follow_the_reference():
+    rng = np.random.default_rng(5)
+    x0 = rng.normal(size=(200, 3)).astype(np.float32)
+    x1 = rng.normal(size=(90, 3)).astype(np.float32)
+    for spec in SPECS[:7:2]:
+        got = make_kernel(spec).matrix(x0, x1)
+        want = orc.gram(spec, x0, x1)
+        assert got.dtype == want.dtype
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+
+
+def test_stacked_and_left_operands():
+    """(B, N1, K) operands and v @ L (linops/_linear_operator.py:1206-1254)."""
+    rng = np.random.default_rng(9)
+    spec = orc.KernelSpec("expquad", (4,), 1.2)
+    k = make_kernel(spec)
+    x0, x1 = rng.normal(size=(130, 4)), rng.normal(size=(70, 4))
+    K = orc.gram(spec, x0, x1)
+    L = k.linop(x0, x1)
+    xs = rng.normal(size=(3, 70, 2))
+    np.testing.assert_allclose(L @ xs, K @ xs, rtol=1e-11, atol=1e-12)
+    w = rng.normal(size=(130,))
+    np.testing.assert_allclose(w @ L, w @ K, rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(L.T.todense(), K.T, rtol=1e-12, atol=1e-12)
+    assert L.T.shape == (70, 130)
+    # K + sigma^2 I as used by problinsolve callers
+    Ls = k.linop(x0)
+    A = Ls + 1e-3
+    z = rng.normal(size=130)
+    Ks = orc.gram(spec, x0)
+    np.testing.assert_allclose(A @ z, Ks @ z + 1e-3 * z, rtol=1e-11, atol=1e-12)
+    np.testing.assert_array_equal(Ls.diagonal(), np.ones(130))
+    assert Ls.trace() == 130.0
+    np.testing.assert_allclose(L.diagonal(), np.diag(K), rtol=1e-12, atol=1e-12)
+
+
+def test_linop_equals_matrix_times_identity():
+    """Mirror of test_keops_equals_no_keops (test_linop_matrix.py:141-154): the
+    matrix-free product applied to I reproduces the dense path."""
+    rng = np.random.default_rng(13)
+    for spec in SPECS:
+        k = make_kernel(spec)
+        x0 = rng.normal(size=(97,) + spec.input_shape)
+        x1 = rng.normal(size=(61,) + spec.input_shape)
+        L = k.linop(x0, x1)
+        np.testing.assert_allclose(L @ np.eye(61), k.matrix(x0, x1), rtol=1e-12, atol=1e-12)
+        L.close()
+
+
+def test_matvec_deterministic_and_split_columns():
+    """Large enough to use several column splits; two runs must agree bit for bit."""
+    rng = np.random.default_rng(17)
+    spec = orc.KernelSpec("expquad", (4,), 0.6)
+    k = make_kernel(spec)
+    x = rng.normal(size=(3000, 4))
+    v = rng.normal(size=(3000, 5))
+    L = k.linop(x)
+    y1 = L @ v
+    y2 = L @ v
+    np.testing.assert_array_equal(y1, y2)
+    assert_matvec_close(y1, orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
+    pos = np.abs(v)
+    np.testing.assert_allclose(L @ pos, orc.matvec(spec, x, None, pos), rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties + sampled rows against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("spec", [SPECS[4], SPECS[6]], ids=["matern52", "ratquad"])
+def test_config2_gram_32768(spec):
+    rng = np.random.default_rng(42)
+    n = 32768
+    x = rng.normal(size=(n, 3))
+    K = make_kernel(spec).matrix(x)
+    assert K.shape == (n, n) and K.dtype == np.float64
+    rows = rng.choice(n, size=48, replace=False)
+    np.testing.assert_allclose(K[rows], orc.gram(spec, x[rows], x), rtol=1e-12, atol=1e-12)
+    assert np.all(np.diagonal(K) == 1.0)
+    blk = slice(1000, 3000)
+    np.testing.assert_array_equal(K[blk, 20000:22000], K[20000:22000, blk].T)  # symmetry
+    assert np.all((K[rows] > 0) & (K[rows] <= 1.0))
+
+
+def test_config4_matvec_65536():
+    rng = np.random.default_rng(42)
+    n = 65536
+    spec = orc.KernelSpec("expquad", (4,), 1.0)
+    x = rng.normal(size=(n, 4))
+    v = rng.normal(size=n)
+    L = make_kernel(spec).linop(x)
+    y = L @ v
+    rows = rng.choice(n, size=64, replace=False)
+    Kr = orc.gram(spec, x[rows], x)
+    assert_matvec_close(y[rows], Kr @ v, np.abs(Kr) @ np.abs(v), 1e-12)
+    # linearity: K (a v + w) = a K v + K w
+    w = rng.uniform(size=n)
+    lhs = L @ (2.5 * v + w)
+    rhs = 2.5 * y + L @ w
+    np.testing.assert_allclose(lhs, rhs, rtol=1e-10, atol=1e-9)
+    L.close()
