@@ -143,6 +143,43 @@ bool matern_coefficients(int p, double* coef) {
     return true;
 }
 
+unsigned hi_word(double x) {
+    uint64_t b;
+    memcpy(&b, &x, 8);
+    return (unsigned)(b >> 32);
+}
+
+// Window of S (as hi words) in which PnEpilogue::fast is valid; see pncov_common.cuh.
+void fill_window(PnEpiParams& P) {
+    const double u_max = 1021.0;      // |exponent argument| bound: results stay normal
+    double s_max = ldexp(1.0, 1000);  // generic cap
+    double s_min = 0.0;
+    switch (P.epi) {
+        case PN_EPI_EXPQUAD:
+            s_max = fmin(s_max, u_max / fabs(P.c_u));
+            break;
+        case PN_EPI_MATERN0:
+        case PN_EPI_MATERN1:
+        case PN_EPI_MATERN2:
+        case PN_EPI_MATERNP: {
+            const double r_max = u_max / fabs(P.c_su);
+            s_max = fmin(s_max, r_max * r_max);
+            s_min = ldexp(1.0, -1000);  // sqrt_core needs a normal, non-zero argument
+            break;
+        }
+        default: {
+            double b_log2_max = 990.0;  // rcp_core / log2_core need b < 2^994
+            if (P.epi == PN_EPI_RATQUADG) b_log2_max = fmin(b_log2_max, u_max / P.alpha);
+            // b = 1 + c S < 2^b_log2_max
+            const double b_max = exp2(b_log2_max);
+            s_max = fmin(s_max, (b_max - 1.0) / P.c_s * (1.0 - 1e-12));
+            break;
+        }
+    }
+    P.s_hi_word = hi_word(s_max);                       // flag when hi(S) >= hi(s_max)
+    P.s_lo_word = s_min > 0.0 ? hi_word(s_min) + 1u : 0u;  // flag when hi(S) < this
+}
+
 int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, int64_t nls, double nu,
                double alpha) {
     if (kind != PNCOV_EXPQUAD && kind != PNCOV_MATERN && kind != PNCOV_RATQUAD)
@@ -157,6 +194,7 @@ int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, 
     k.d = (int)d;
     k.ard = nls > 1;
     k.epi = PnEpiParams{};
+    pn_fill_math_constants(k.epi);
     double base = 1.0;  // numerator of the scale factor
     if (kind == PNCOV_EXPQUAD) {
         base = sqrt(0.5);  // _exponentiated_quadratic.py:85-87
@@ -178,6 +216,7 @@ int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, 
         k.epi.alpha = alpha;
         k.epi.epi = alpha == 1.0 ? PN_EPI_RATQUAD1 : alpha == 2.0 ? PN_EPI_RATQUAD2 : PN_EPI_RATQUADG;
         k.ard = false;
+        fill_window(k.epi);
         return 0;
     }
     if (k.ard) {
@@ -195,6 +234,8 @@ int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, 
             k.epi.c_s = s;
         }
     }
+    k.epi.c_su = k.epi.c_s * k.epi.c_u;
+    fill_window(k.epi);
     return 0;
 }
 
@@ -330,8 +371,22 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         return 0;
     }
     if (h->k.d > 1024) return fail(PNCOV_ENOTIMPL, "matrix-free product supports d <= 1024");
-    const int jsplit = pn_matvec_jsplit(R.n, C.n, h->k.d, h->sm_count);
     const int kc_max = (k == 1) ? 1 : 4;
+    PnMatvecLaunch m{};
+    m.x0_aos = R.aos;
+    m.x1_aos = C.aos;
+    m.x1_soa = C.soa;
+    m.ld1 = C.npad;
+    m.n0 = R.n;
+    m.n1 = C.n;
+    m.n1pad = C.npad;
+    m.scale = h->scale_dev;
+    m.d = h->k.d;
+    m.kc = kc_max;
+    m.in_f32 = h->k.dtype == PNCOV_F32;
+    m.epi = h->k.epi;
+    PN_CUDA(pn_plan_matvec(m, h->sm_count));
+    const int jsplit = m.jsplit;
     int rc;
     if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * kc_max * es))) return rc;
     if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)R.n * kc_max * es))) return rc;
@@ -349,24 +404,12 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
             ++g_pn_launches;
             PN_CUDA(cudaGetLastError());
         }
-        PnMatvecLaunch m{};
-        m.x0_aos = R.aos;
-        m.x1_aos = C.aos;
-        m.x1_soa = C.soa;
-        m.ld1 = C.npad;
-        m.n0 = R.n;
-        m.n1 = C.n;
-        m.n1pad = C.npad;
-        m.scale = h->scale_dev;
-        m.d = h->k.d;
         m.v = h->vpack;
         m.y = h->ypack;
         m.kc = kc;
         m.partial = h->partial;
         m.jsplit = jsplit;
-        m.in_f32 = h->k.dtype == PNCOV_F32;
-        m.epi = h->k.epi;
-        PN_CUDA(pn_launch_matvec(m, stream));
+        PN_CUDA(pn_launch_matvec(m, h->sm_count, stream));
         {
             const int64_t total = R.n * kc;
             const unsigned blocks = (unsigned)((total + 255) / 256);

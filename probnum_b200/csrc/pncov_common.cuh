@@ -26,9 +26,22 @@ struct PnEpiParams {
     int p;
     double c_u;      // EXPQUAD: -log2(e) * s^2 (isotropic) or -log2(e) (ARD); MATERN: -log2(e)
     double c_s;      // MATERN: s (isotropic) or 1 (ARD), multiplies sqrt(S); RATQUAD: 1/(2 alpha l^2)
+    double c_su;     // MATERN0: c_s * c_u
     double alpha;    // RATQUADG
     double coef[PN_MAX_P + 1];  // MATERNP polynomial coefficients, degree i at index i
+    // polynomial coefficients of pn_exp2 / pn_log2, carried in the kernel-parameter constant
+    // bank so that every use is a c[0x0][..] operand instead of two UMOVs (see profiles/r01)
+    double e1, e2, e3;
+    double g1, g2, g3, g4, g5;
+    // validity window of the fast epilogue in terms of the hi word of S (see PnFlags)
+    unsigned s_lo_word, s_hi_word;
 };
+
+inline void pn_fill_math_constants(PnEpiParams& P) {
+    P.e1 = PNCOV_EXP2_E1; P.e2 = PNCOV_EXP2_E2; P.e3 = PNCOV_EXP2_E3;
+    P.g1 = PNCOV_LOG2_G1; P.g2 = PNCOV_LOG2_G2; P.g3 = PNCOV_LOG2_G3; P.g4 = PNCOV_LOG2_G4;
+    P.g5 = PNCOV_LOG2_G5;
+}
 
 // constant tables in global memory (one copy per translation unit, 6 KB); kernels stage
 // them into shared memory at start-up
@@ -41,18 +54,16 @@ __device__ __forceinline__ void pn_stage_tables(double* tabE, double* tabL, int 
 }
 
 // ---------------------------------------------------------------------------------------
-// FP64 epilogue: S = sum of squared (scaled) differences  ->  k
+// Robust FP64 epilogue (any S >= 0 including 0, subnormal, huge, inf, nan): the slow path.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double pn_epilogue(double S, const PnEpiParams& P,
-                                              const double* __restrict__ tabE,
-                                              const double* __restrict__ tabL) {
+static __device__ __noinline__ double pn_epilogue(double S, const PnEpiParams& P,
+                                           const double* __restrict__ tabE,
+                                           const double* __restrict__ tabL) {
     switch (P.epi) {
         case PN_EPI_EXPQUAD:
             return pn_exp2(S * P.c_u, tabE);
-        case PN_EPI_MATERN0: {
-            double r = pn_sqrt(S) * P.c_s;
-            return pn_exp2(r * P.c_u, tabE);
-        }
+        case PN_EPI_MATERN0:
+            return pn_exp2(pn_sqrt(S) * P.c_su, tabE);
         case PN_EPI_MATERN1: {
             double r = pn_sqrt(S) * P.c_s;
             double e = pn_exp2(r * P.c_u, tabE);
@@ -61,8 +72,7 @@ __device__ __forceinline__ double pn_epilogue(double S, const PnEpiParams& P,
         case PN_EPI_MATERN2: {
             double r = pn_sqrt(S) * P.c_s;
             double e = pn_exp2(r * P.c_u, tabE);
-            double poly = pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0);
-            return poly * e;
+            return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
         }
         case PN_EPI_MATERNP: {
             double r = pn_sqrt(S) * P.c_s;
@@ -83,6 +93,117 @@ __device__ __forceinline__ double pn_epilogue(double S, const PnEpiParams& P,
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------
+// Fast epilogue.  No per-entry branches: each call folds the hi word of S into a running
+// min and max (two integer instructions) and the caller tests them ONCE per register tile
+// against the window [s_lo_word, s_hi_word) computed on the host for this kernel; a
+// flagged tile is redone with pn_epilogue.  The window excludes S == 0 / subnormal under a
+// square root (the diagonal of a symmetric Gram), results that would underflow to
+// subnormals, overflow of 1 + c S, and non-finite input.
+// ---------------------------------------------------------------------------------------
+struct PnFlags {
+    unsigned lo, hi;
+    __device__ __forceinline__ void reset() {
+        lo = 0xffffffffu;
+        hi = 0u;
+    }
+    __device__ __forceinline__ void see(double S) {
+        const unsigned w = (unsigned)pn_hi(S);
+        lo = min(lo, w);
+        hi = max(hi, w);
+    }
+    __device__ __forceinline__ bool flagged(const PnEpiParams& P) const {
+        return lo < P.s_lo_word || hi >= P.s_hi_word;
+    }
+};
+
+// 2^(a*b) for |a*b| < 1021.  The product is never rounded: t = fma(a, b, magic) rounds it
+// to the table grid, r = fma(a, b, -(t - magic)) is the exact remainder (one rounding).
+__device__ __forceinline__ double pn_exp2_prod_core(double a, double b, const PnEpiParams& P,
+                                                    const double* __restrict__ tab) {
+    const double magic = PN_EXP2_MAGIC;
+    double t = pn_fma(a, b, magic);
+    int n = pn_lo(t);
+    double r = pn_fma(a, b, magic - t);
+    double q = pn_fma(P.e3, r, P.e2);
+    q = pn_fma(q, r, P.e1);
+    double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) +
+                                                ((n << 3) & ((PN_EXP2_N - 1) << 3)));
+    double res = pn_fma(T * r, q, T);
+    // (n >> BITS) << 20 == n << (20 - BITS) with the low 20 bits cleared
+    return pn_make(pn_hi(res) + ((n << (20 - PNCOV_EXP2_BITS)) & 0xfff00000), pn_lo(res));
+}
+__device__ __forceinline__ double pn_sqrt_core(double s) {
+    double y = pn_rsqrt_seed(s);
+    double g = s * y;
+    double h = 0.5 * y;
+    double e = pn_fma(-h, g, 0.5);
+    g = pn_fma(g, e, g);
+    double d = pn_fma(-g, g, s);
+    return pn_fma(d, h, g);
+}
+__device__ __forceinline__ double pn_rcp_core(double b) {
+    double y = pn_rcp_seed(b);
+    double e = pn_fma(-b, y, 1.0);
+    y = pn_fma(y, e, y);
+    e = pn_fma(-b, y, 1.0);
+    return pn_fma(y, e, y);
+}
+__device__ __forceinline__ double pn_log2_core(double b, const PnEpiParams& P,
+                                               const double* __restrict__ tab) {
+    int hi = pn_hi(b);
+    int e = (hi >> 20) - 1023;
+    double m = pn_make((hi & 0x000fffff) | 0x3ff00000, pn_lo(b));
+    const double2 t = *reinterpret_cast<const double2*>(
+        reinterpret_cast<const char*>(tab) + (((hi >> (20 - PNCOV_LOG2_BITS)) & (PN_LOG2_N - 1)) << 4));
+    double r = pn_fma(m, t.x, -1.0);
+    double q = pn_fma(P.g5, r, P.g4);
+    q = pn_fma(q, r, P.g3);
+    q = pn_fma(q, r, P.g2);
+    q = pn_fma(q, r, P.g1);
+    double ef = pn_make(0x43300000, (int)(0x80000000u ^ (unsigned)e)) - 4503601774854144.0;
+    return pn_fma(q, r, ef + t.y);
+}
+
+template <int EPI>
+struct PnEpilogue {
+    __device__ __forceinline__ static double fast(double S, const PnEpiParams& P,
+                                                  const double* __restrict__ tabE,
+                                                  const double* __restrict__ tabL, PnFlags& f) {
+        f.see(S);
+        if constexpr (EPI == PN_EPI_EXPQUAD) {
+            return pn_exp2_prod_core(S, P.c_u, P, tabE);
+        } else if constexpr (EPI >= PN_EPI_MATERN0 && EPI <= PN_EPI_MATERNP) {
+            double r0 = pn_sqrt_core(S);
+            double e = pn_exp2_prod_core(r0, P.c_su, P, tabE);
+            if constexpr (EPI == PN_EPI_MATERN0) {
+                return e;
+            } else {
+                double r = r0 * P.c_s;
+                if constexpr (EPI == PN_EPI_MATERN1) {
+                    return pn_fma(r, e, e);
+                } else if constexpr (EPI == PN_EPI_MATERN2) {
+                    return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
+                } else {
+                    double poly = P.coef[P.p];
+                    for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
+                    return poly * e;
+                }
+            }
+        } else {
+            double b = pn_fma(S, P.c_s, 1.0);
+            if constexpr (EPI == PN_EPI_RATQUAD1) {
+                return pn_rcp_core(b);
+            } else if constexpr (EPI == PN_EPI_RATQUAD2) {
+                double y = pn_rcp_core(b);
+                return y * y;
+            } else {
+                return pn_exp2_prod_core(pn_log2_core(b, P, tabL), -P.alpha, P, tabE);
+            }
+        }
+    }
+};
 
 // float32 inputs.  Distances are accumulated in float (as the reference does for
 // float32 arrays); ExpQuad stays in float, the other families continue in double

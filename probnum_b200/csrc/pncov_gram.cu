@@ -44,47 +44,20 @@ struct Pair<float> {
 };
 
 // ---- epilogue over a register tile ------------------------------------------------------
-template <int EPI>
-__device__ __forceinline__ double epi_one(double S, const PnEpiParams& P, const double* tabE,
-                                          const double* tabL) {
-    if constexpr (EPI == PN_EPI_EXPQUAD) {
-        return pn_exp2(S * P.c_u, tabE);
-    } else if constexpr (EPI == PN_EPI_MATERN0) {
-        return pn_exp2(pn_sqrt(S) * (P.c_s * P.c_u), tabE);
-    } else if constexpr (EPI == PN_EPI_MATERN1) {
-        double r = pn_sqrt(S) * P.c_s;
-        double e = pn_exp2(r * P.c_u, tabE);
-        return pn_fma(r, e, e);
-    } else if constexpr (EPI == PN_EPI_MATERN2) {
-        double r = pn_sqrt(S) * P.c_s;
-        double e = pn_exp2(r * P.c_u, tabE);
-        return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
-    } else if constexpr (EPI == PN_EPI_MATERNP) {
-        double r = pn_sqrt(S) * P.c_s;
-        double e = pn_exp2(r * P.c_u, tabE);
-        double poly = P.coef[P.p];
-        for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
-        return poly * e;
-    } else if constexpr (EPI == PN_EPI_RATQUAD1) {
-        return pn_rcp(pn_fma(S, P.c_s, 1.0));
-    } else if constexpr (EPI == PN_EPI_RATQUAD2) {
-        double y = pn_rcp(pn_fma(S, P.c_s, 1.0));
-        return y * y;
-    } else {
-        double L = pn_log2_ge1(pn_fma(S, P.c_s, 1.0), tabL);
-        return pn_exp2(-P.alpha * L, tabE);
-    }
-}
-
 template <int EPI, int N, typename T, typename TOut>
 __device__ __forceinline__ void epi_tile(const T (&S)[N], TOut (&K)[N], const PnEpiParams& P,
                                          const double* tabE, const double* tabL) {
+    if constexpr (std::is_same<TOut, float>::value) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        if constexpr (std::is_same<TOut, float>::value) {
-            K[i] = exp2f(S[i] * (float)P.c_u);  // float32 ExpQuad stays in float
-        } else {
-            K[i] = epi_one<EPI>((double)S[i], P, tabE, tabL);
+        for (int i = 0; i < N; ++i) K[i] = exp2f(S[i] * (float)P.c_u);  // float32 ExpQuad stays in float
+    } else {
+        PnFlags f;
+        f.reset();
+#pragma unroll
+        for (int i = 0; i < N; ++i) K[i] = PnEpilogue<EPI>::fast((double)S[i], P, tabE, tabL, f);
+        if (f.flagged(P)) {  // rare: diagonal tiles (sqrt of 0), subnormal results
+#pragma unroll
+            for (int i = 0; i < N; ++i) K[i] = pn_epilogue((double)S[i], P, tabE, tabL);
         }
     }
 }
@@ -230,6 +203,102 @@ __global__ void __launch_bounds__(G_THREADS)
     }
 }
 
+// ---- fast kernel: float64, compile-time d <= 8, compile-time epilogue, interior tiles only ------
+// Preconditions (checked by the launcher): n0 % G_TM == 0, n1 % G_TN == 0, rows of the
+// output 16-byte aligned.  Nothing in the loop is predicated; the column points of the
+// thread's two columns live in registers; the output pointer advances by one row stride.
+template <int D, bool ARD, int EPI>
+__global__ void __launch_bounds__(G_THREADS)
+    gram_fast_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    double* x0s = reinterpret_cast<double*>(smem + G_HDR_BYTES);  // [2][D][G_TM]
+
+    const int n_tiles = (int)(g.n0 / G_TM);
+    const int t0 = blockIdx.y * tiles_per_cta;
+    const int t1 = min(t0 + tiles_per_cta, n_tiles);
+    if (t0 >= t1) return;
+    const int64_t j0 = (int64_t)blockIdx.x * G_TN + 2 * tid;
+    const double* x0g = static_cast<const double*>(g.x0_soa);
+    const double* x1g = static_cast<const double*>(g.x1_soa);
+    constexpr uint32_t TILE_BYTES = D * G_TM * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], TILE_BYTES);
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+            pn_bulk_g2s(x0s + m * G_TM, x0g + (size_t)m * g.ld0 + (size_t)t0 * G_TM, G_TM * 8, &bars[0]);
+    }
+    pn_stage_tables(tabE, tabL, tid, G_THREADS);
+
+    double xb0[D], xb1[D], sc[D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        const double2 t = *reinterpret_cast<const double2*>(x1g + (size_t)m * g.ld1 + j0);
+        xb0[m] = t.x;
+        xb1[m] = t.y;
+        if constexpr (ARD) sc[m] = static_cast<const double*>(g.scale)[m];
+    }
+    double* optr = static_cast<double*>(g.out) + (size_t)t0 * G_TM * g.ldo + j0;
+    const size_t row_stride = (size_t)g.ldo;
+    __syncthreads();
+
+    int it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && t + 1 < t1) {
+            double* dst = x0s + (buf ^ 1) * (D * G_TM);
+            pn_mbar_expect_tx(&bars[buf ^ 1], TILE_BYTES);
+#pragma unroll
+            for (int m = 0; m < D; ++m)
+                pn_bulk_g2s(dst + m * G_TM, x0g + (size_t)m * g.ld0 + (size_t)(t + 1) * G_TM, G_TM * 8,
+                            &bars[buf ^ 1]);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* x0t = x0s + buf * (D * G_TM);
+#pragma unroll 1
+        for (int rg = 0; rg < G_TM; rg += G_R) {
+            double S[2 * G_R];
+#pragma unroll
+            for (int i = 0; i < 2 * G_R; ++i) S[i] = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * G_TM + rg);
+                const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * G_TM + rg + 2);
+                const double xa[G_R] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                for (int r = 0; r < G_R; ++r) {
+                    double da = xa[r] - xb0[m];
+                    double db = xa[r] - xb1[m];
+                    if constexpr (ARD) {
+                        da *= sc[m];
+                        db *= sc[m];
+                    }
+                    S[2 * r] = pn_fma(da, da, S[2 * r]);
+                    S[2 * r + 1] = pn_fma(db, db, S[2 * r + 1]);
+                }
+            }
+            double K[2 * G_R];
+            epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+#pragma unroll
+            for (int r = 0; r < G_R; ++r) {
+                pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
+                optr += row_stride;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- chunk kernel (any d): coordinates streamed through shared memory in chunks ------------
 template <typename T, typename TOut, bool ARD>
 __global__ void __launch_bounds__(G_THREADS)
@@ -300,6 +369,51 @@ __global__ void __launch_bounds__(G_THREADS)
     }
 }
 
+template <int D, bool ARD, int EPI>
+cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
+    const int64_t strips = g.n1 / G_TN;
+    const int64_t n_tiles = g.n0 / G_TM;
+    int64_t tpc = (n_tiles * strips) / (148 * 48);
+    tpc = tpc < 1 ? 1 : (tpc > 32 ? 32 : tpc);
+    const int64_t gy = (n_tiles + tpc - 1) / tpc;
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    const size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * G_TM;
+    auto kern = gram_fast_kernel<D, ARD, EPI>;
+    dim3 grid((unsigned)strips, (unsigned)gy);
+    kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int D, bool ARD>
+cudaError_t launch_fast_epi(const PnGramLaunch& g, cudaStream_t stream) {
+    switch (g.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_fast_inst<D, ARD, PN_EPI_EXPQUAD>(g, stream);
+        case PN_EPI_MATERN0: return launch_fast_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
+        case PN_EPI_MATERN1: return launch_fast_inst<D, ARD, PN_EPI_MATERN1>(g, stream);
+        case PN_EPI_MATERN2: return launch_fast_inst<D, ARD, PN_EPI_MATERN2>(g, stream);
+        case PN_EPI_MATERNP: return launch_fast_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
+        case PN_EPI_RATQUAD1: return launch_fast_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
+        case PN_EPI_RATQUAD2: return launch_fast_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
+        default: return launch_fast_inst<D, false, PN_EPI_RATQUADG>(g, stream);
+    }
+}
+
+template <bool ARD>
+cudaError_t launch_fast(const PnGramLaunch& g, cudaStream_t stream) {
+    switch (g.d) {
+        case 1: return launch_fast_epi<1, ARD>(g, stream);
+        case 2: return launch_fast_epi<2, ARD>(g, stream);
+        case 3: return launch_fast_epi<3, ARD>(g, stream);
+        case 4: return launch_fast_epi<4, ARD>(g, stream);
+        case 5: return launch_fast_epi<5, ARD>(g, stream);
+        case 6: return launch_fast_epi<6, ARD>(g, stream);
+        case 7: return launch_fast_epi<7, ARD>(g, stream);
+        case 8: return launch_fast_epi<8, ARD>(g, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <typename T, typename TOut, bool ARD>
 cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
     if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
@@ -347,7 +461,7 @@ cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
 
 }  // namespace
 
-cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
+static cudaError_t launch_generic(const PnGramLaunch& g, cudaStream_t stream) {
     const bool ard = g.scale != nullptr;
     if (!g.in_f32) {
         return ard ? launch_typed<double, double, true>(g, stream) : launch_typed<double, double, false>(g, stream);
@@ -356,4 +470,33 @@ cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
         return ard ? launch_typed<float, float, true>(g, stream) : launch_typed<float, float, false>(g, stream);
     }
     return ard ? launch_typed<float, double, true>(g, stream) : launch_typed<float, double, false>(g, stream);
+}
+
+cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
+    if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
+    const bool aligned = (g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
+    const int64_t n0i = (g.n0 / G_TM) * G_TM, n1i = (g.n1 / G_TN) * G_TN;  // interior extent
+    if (g.in_f32 || g.d > 8 || !aligned || n0i == 0 || n1i == 0) return launch_generic(g, stream);
+    // interior: whole 64-row tiles x whole 512-column strips, unpredicated specialised kernel
+    PnGramLaunch in = g;
+    in.n0 = n0i;
+    in.n1 = n1i;
+    cudaError_t err = g.scale ? launch_fast<true>(in, stream) : launch_fast<false>(in, stream);
+    if (err != cudaSuccess) return err;
+    if (n1i < g.n1) {  // right edge: all rows, remaining columns
+        PnGramLaunch e = g;
+        e.x1_soa = static_cast<const double*>(g.x1_soa) + n1i;
+        e.n1 = g.n1 - n1i;
+        e.out = static_cast<double*>(g.out) + n1i;
+        if ((err = launch_generic(e, stream)) != cudaSuccess) return err;
+    }
+    if (n0i < g.n0) {  // bottom edge: remaining rows, interior columns
+        PnGramLaunch e = g;
+        e.x0_soa = static_cast<const double*>(g.x0_soa) + n0i;
+        e.n0 = g.n0 - n0i;
+        e.n1 = n1i;
+        e.out = static_cast<double*>(g.out) + n0i * g.ldo;
+        if ((err = launch_generic(e, stream)) != cudaSuccess) return err;
+    }
+    return cudaSuccess;
 }

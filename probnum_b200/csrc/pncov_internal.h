@@ -53,10 +53,11 @@ struct PnPairsLaunch {
 };
 
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
-cudaError_t pn_launch_matvec(const PnMatvecLaunch& m, cudaStream_t stream);
+// pn_plan_matvec fills m.jsplit (how many column-range splits the launch will use, which
+// sizes the `partial` scratch); pn_launch_matvec then runs with that plan
+cudaError_t pn_plan_matvec(PnMatvecLaunch& m, int sm_count);
+cudaError_t pn_launch_matvec(const PnMatvecLaunch& m, int sm_count, cudaStream_t stream);
 cudaError_t pn_launch_pairs(const PnPairsLaunch& p, cudaStream_t stream);
-// how many column-range splits pn_launch_matvec wants for this shape (scratch sizing)
-int pn_matvec_jsplit(int64_t n0, int64_t n1, int d, int sm_count);
 
 // small utility kernels (pncov_api.cu)
 extern int64_t g_pn_launches;

@@ -5,8 +5,9 @@
 // push everything else (exponent manipulation, table indexing, special-case tests)
 // onto the integer/LSU/MUFU pipes, which issue in the shadow of the 2-cycle DFMA.
 //
-//   pn_exp2   2^u, u <= 0 typical      3 DADD + 4 DFMA/DMUL + 1 DFMA  (+ LDS, int)
-//   pn_sqrt   sqrt(s)                  MUFU.RSQ64H + 2 DMUL + 5 DFMA
+//   pn_exp2   2^(a*b)                  2 DFMA + DADD (reduction, product never formed)
+//                                      + 2 DFMA + DMUL + DFMA (2048-entry table, degree-2 q)
+//   pn_sqrt   sqrt(s)                  MUFU.RSQ64H + 2 DMUL + 4 DFMA
 //   pn_rcp    1/b, b >= 1              MUFU.RCP64H + 4 DFMA
 //   pn_log2   log2(b), b >= 1          1 DFMA + 5 poly + 3 DADD        (+ LDS.128, int)
 //
@@ -80,7 +81,7 @@ PN_HD double pn_rsqrt_seed(double x) {
     return y;
 #else
     double y = 1.0 / sqrt(x);
-    return pn_make(pn_hi(y) & ~0x3, 0) ;  // keep 18 mantissa bits + perturbation
+    return pn_make(pn_hi(y), pn_lo(y) & (int)0xC0000000);  // keep 22 mantissa bits like MUFU.RSQ64H
 #endif
 }
 PN_HD double pn_rcp_seed(double x) {
@@ -90,7 +91,7 @@ PN_HD double pn_rcp_seed(double x) {
     return y;
 #else
     double y = 1.0 / x;
-    return pn_make(pn_hi(y) & ~0x3, 0);
+    return pn_make(pn_hi(y), pn_lo(y) & (int)0xC0000000);
 #endif
 }
 
@@ -106,25 +107,31 @@ PN_HD bool pn_exp2_in_fast_range(double u) {
     return (unsigned)(pn_hi(u) & 0x7fffffff) < 0x408FF000u;
 }
 
+// magic constant whose ulp is 2^-PNCOV_EXP2_BITS: adding it rounds to the table grid
+#define PN_EXP2_MAGIC (0x1.8p+52 / (double)PN_EXP2_N)
+
 PN_HD double pn_exp2_fast(double u, const double* __restrict__ tab) {
-    const double magic = 0x1.8p+44;  // ulp(magic) = 2^-8: adding rounds u to a multiple of 1/256
+    const double magic = PN_EXP2_MAGIC;
     double t = u + magic;
-    int n = pn_lo(t);                // round(u * 256) as a 32-bit two's complement integer
+    int n = pn_lo(t);                // round(u * 2^BITS) as a 32-bit two's complement integer
     double kf = t - magic;           // exact
-    double r = u - kf;               // exact, |r| <= 2^-9
-    double q = pn_fma(PNCOV_EXP2_E4, r, PNCOV_EXP2_E3);
-    q = pn_fma(q, r, PNCOV_EXP2_E2);
+    double r = u - kf;               // exact, |r| <= 2^-(BITS+1)
+    double q = pn_fma(PNCOV_EXP2_E3, r, PNCOV_EXP2_E2);
     q = pn_fma(q, r, PNCOV_EXP2_E1);
-    double p = q * r;                // 2^r - 1
     double T = tab[n & (PN_EXP2_N - 1)];
-    double res = pn_fma(T, p, T);    // in [1, 2)
-    int e = n >> PNCOV_EXP2_BITS;    // floor(n / 256)
+    double res = pn_fma(T * r, q, T);  // T * 2^r, in [1, 2)
+    int e = n >> PNCOV_EXP2_BITS;      // floor(n / 2^BITS)
     return pn_make(pn_hi(res) + e * 1048576, pn_lo(res));  // scale by 2^e in the exponent field
 }
 
+// full-range version: the underflow band -1075.5 < u <= -1022 (subnormal results) is
+// evaluated as 2^(u+128) * 2^-128, where u + 128 is exact and the product rounds once
 PN_HD double pn_exp2(double u, const double* __restrict__ tab) {
     if (pn_exp2_in_fast_range(u)) return pn_exp2_fast(u, tab);
-    return exp2(u);  // underflow to subnormal/zero, inf, nan: rare, libm handles them
+    if (u != u) return u;
+    if (u > 0.0) return exp2(u);       // overflow side: never reached by the covariance kernels
+    if (u < -1075.5) return 0.0;       // also -inf
+    return pn_exp2_fast(u + 128.0, tab) * 0x1p-128;
 }
 
 // ------------------------------------------------------------------------------------
@@ -139,7 +146,7 @@ PN_HD double pn_sqrt(double s) {
         double hh = 0.5 * y;
         double e = pn_fma(-hh, g, 0.5);
         g = pn_fma(g, e, g);
-        hh = pn_fma(hh, e, hh);
+        // the final correction is ~2^-44 relative, so the 22-bit h is accurate enough for it
         double d = pn_fma(-g, g, s);
         return pn_fma(d, hh, g);
     }

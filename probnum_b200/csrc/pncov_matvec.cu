@@ -29,43 +29,20 @@ constexpr int MV_R = 2;     // rows per thread
 constexpr int MV_TJ = 128;  // column points per pipeline stage
 constexpr int MV_HDR_BYTES = 128 + 8 * (PN_EXP2_N + 2 * PN_LOG2_N);
 
-template <int EPI>
-__device__ __forceinline__ double mv_epi_one(double S, const PnEpiParams& P, const double* tabE,
-                                             const double* tabL) {
-    if constexpr (EPI == PN_EPI_EXPQUAD) {
-        return pn_exp2(S * P.c_u, tabE);
-    } else if constexpr (EPI == PN_EPI_MATERN0) {
-        return pn_exp2(pn_sqrt(S) * (P.c_s * P.c_u), tabE);
-    } else if constexpr (EPI == PN_EPI_MATERN1) {
-        double r = pn_sqrt(S) * P.c_s;
-        double e = pn_exp2(r * P.c_u, tabE);
-        return pn_fma(r, e, e);
-    } else if constexpr (EPI == PN_EPI_MATERN2) {
-        double r = pn_sqrt(S) * P.c_s;
-        double e = pn_exp2(r * P.c_u, tabE);
-        return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
-    } else if constexpr (EPI == PN_EPI_MATERNP) {
-        double r = pn_sqrt(S) * P.c_s;
-        double e = pn_exp2(r * P.c_u, tabE);
-        double poly = P.coef[P.p];
-        for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
-        return poly * e;
-    } else if constexpr (EPI == PN_EPI_RATQUAD1) {
-        return pn_rcp(pn_fma(S, P.c_s, 1.0));
-    } else if constexpr (EPI == PN_EPI_RATQUAD2) {
-        double y = pn_rcp(pn_fma(S, P.c_s, 1.0));
-        return y * y;
-    } else {
-        double L = pn_log2_ge1(pn_fma(S, P.c_s, 1.0), tabL);
-        return pn_exp2(-P.alpha * L, tabE);
-    }
-}
-
 template <int EPI, int N>
 __device__ __forceinline__ void mv_epi_tile(double (&S)[N], const PnEpiParams& P, const double* tabE,
                                             const double* tabL) {
+    PnFlags f;
+    f.reset();
+    double K[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) S[i] = mv_epi_one<EPI>(S[i], P, tabE, tabL);
+    for (int i = 0; i < N; ++i) K[i] = PnEpilogue<EPI>::fast(S[i], P, tabE, tabL, f);
+    if (f.flagged(P)) {  // rare: S == 0 under a sqrt (the diagonal), subnormal results
+#pragma unroll
+        for (int i = 0; i < N; ++i) K[i] = pn_epilogue(S[i], P, tabE, tabL);
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) S[i] = K[i];
 }
 
 template <int N>
@@ -84,7 +61,7 @@ __device__ __forceinline__ void mv_epi_dispatch(double (&S)[N], const PnEpiParam
 }
 
 // ---- main kernel: float64, compile-time d in 1..8 -------------------------------------------
-template <int D, bool ARD, int KC>
+template <int D, bool ARD, int KC, int EPI>
 __global__ void __launch_bounds__(MV_THREADS)
     matvec_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -182,7 +159,7 @@ __global__ void __launch_bounds__(MV_THREADS)
                     }
                     S[2 * r + c] = s;
                 }
-            mv_epi_dispatch(S, a.epi, tabE, tabL);
+            mv_epi_tile<EPI>(S, a.epi, tabE, tabL);
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -312,40 +289,80 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, T* __
     y[i] = (T)s;
 }
 
-template <int D, bool ARD, int KC>
-cudaError_t launch_main(const PnMatvecLaunch& a, cudaStream_t stream) {
-    const int64_t n_jt = a.n1pad / MV_TJ;
-    const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
+// Column splits: grid = row CTAs x jsplit.  Pick the split that fills whole waves of the
+// machine (slots = SMs x resident CTAs of this instantiation); more, shorter CTAs also
+// smooth the tail.  Each split keeps at least two column tiles.
+static int choose_jsplit(int64_t row_ctas, int64_t n_jt, int slots) {
+    int best = 1;
+    double best_eff = -1.0;
+    const int64_t max_split = n_jt / 2 < 1 ? 1 : (n_jt / 2 > 32 ? 32 : n_jt / 2);
+    for (int js = 1; js <= max_split; ++js) {
+        const int64_t total = row_ctas * js;
+        const int64_t waves = (total + slots - 1) / slots;
+        double eff = (double)total / (double)(waves * slots);
+        if (waves >= 8) eff = 1.0;  // long queues balance dynamically; stop splitting further
+        if (eff > best_eff + 1e-3) {
+            best_eff = eff;
+            best = js;
+        }
+    }
+    return best;
+}
+
+template <int D, bool ARD, int KC, int EPI>
+cudaError_t launch_main(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStream_t stream) {
+    auto kern = matvec_kernel<D, ARD, KC, EPI>;
     const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MV_TJ * (D + KC);
-    auto kern = matvec_kernel<D, ARD, KC>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    dim3 grid((unsigned)((a.n0 + MV_THREADS * MV_R - 1) / (MV_THREADS * MV_R)), (unsigned)a.jsplit);
+    const int64_t n_jt = a.n1pad / MV_TJ;
+    const int64_t row_ctas = (a.n0 + MV_THREADS * MV_R - 1) / (MV_THREADS * MV_R);
+    if (plan_only) {
+        int occ = 1;
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MV_THREADS, smem);
+        if (err != cudaSuccess) return err;
+        a.jsplit = choose_jsplit(row_ctas, n_jt, sm_count * (occ < 1 ? 1 : occ));
+        return cudaSuccess;
+    }
+    const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
+    dim3 grid((unsigned)row_ctas, (unsigned)a.jsplit);
     kern<<<grid, MV_THREADS, smem, stream>>>(a, (int)tps);
     ++g_pn_launches;
     return cudaGetLastError();
 }
 
+template <int D, bool ARD, int KC>
+cudaError_t launch_main_epi(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_main<D, ARD, KC, PN_EPI_EXPQUAD>(a, sm, plan, stream);
+        case PN_EPI_MATERN0: return launch_main<D, ARD, KC, PN_EPI_MATERN0>(a, sm, plan, stream);
+        case PN_EPI_MATERN1: return launch_main<D, ARD, KC, PN_EPI_MATERN1>(a, sm, plan, stream);
+        case PN_EPI_MATERN2: return launch_main<D, ARD, KC, PN_EPI_MATERN2>(a, sm, plan, stream);
+        case PN_EPI_MATERNP: return launch_main<D, ARD, KC, PN_EPI_MATERNP>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD1: return launch_main<D, false, KC, PN_EPI_RATQUAD1>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD2: return launch_main<D, false, KC, PN_EPI_RATQUAD2>(a, sm, plan, stream);
+        default: return launch_main<D, false, KC, PN_EPI_RATQUADG>(a, sm, plan, stream);
+    }
+}
+
 template <int D, bool ARD>
-cudaError_t launch_main_kc(const PnMatvecLaunch& a, cudaStream_t stream) {
+cudaError_t launch_main_kc(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     switch (a.kc) {
-        case 1: return launch_main<D, ARD, 1>(a, stream);
-        case 4: return launch_main<D, ARD, 4>(a, stream);
+        case 1: return launch_main_epi<D, ARD, 1>(a, sm, plan, stream);
+        case 4: return launch_main_epi<D, ARD, 4>(a, sm, plan, stream);
         default: return cudaErrorInvalidValue;
     }
 }
 
 template <bool ARD>
-cudaError_t launch_main_d(const PnMatvecLaunch& a, cudaStream_t stream) {
+cudaError_t launch_main_d(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     switch (a.d) {
-        case 1: return launch_main_kc<1, ARD>(a, stream);
-        case 2: return launch_main_kc<2, ARD>(a, stream);
-        case 3: return launch_main_kc<3, ARD>(a, stream);
-        case 4: return launch_main_kc<4, ARD>(a, stream);
-        case 5: return launch_main_kc<5, ARD>(a, stream);
-        case 6: return launch_main_kc<6, ARD>(a, stream);
-        case 7: return launch_main_kc<7, ARD>(a, stream);
-        case 8: return launch_main_kc<8, ARD>(a, stream);
+        case 1: return launch_main_kc<1, ARD>(a, sm, plan, stream);
+        case 2: return launch_main_kc<2, ARD>(a, sm, plan, stream);
+        case 3: return launch_main_kc<3, ARD>(a, sm, plan, stream);
+        case 4: return launch_main_kc<4, ARD>(a, sm, plan, stream);
+        case 5: return launch_main_kc<5, ARD>(a, sm, plan, stream);
+        case 6: return launch_main_kc<6, ARD>(a, sm, plan, stream);
+        case 7: return launch_main_kc<7, ARD>(a, sm, plan, stream);
+        case 8: return launch_main_kc<8, ARD>(a, sm, plan, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -376,27 +393,34 @@ cudaError_t launch_generic(const PnMatvecLaunch& a, const void* x1_soa, int64_t 
 
 }  // namespace
 
-int pn_matvec_jsplit(int64_t n0, int64_t n1, int d, int sm_count) {
-    // aim for >= 8 CTAs per SM in flight-equivalents; each CTA covers 256 rows (main kernel)
-    const int64_t row_ctas = (n0 + 255) / 256;
-    const int64_t want = (int64_t)sm_count * 8;
-    int64_t split = (want + row_ctas - 1) / row_ctas;
-    const int64_t max_split = (n1 + 4 * MV_TJ - 1) / (4 * MV_TJ);  // at least 4 tiles per split
-    if (split > max_split) split = max_split;
-    if (split > 64) split = 64;
-    if (split < 1) split = 1;
-    (void)d;
-    return (int)split;
+static bool uses_main_kernel(const PnMatvecLaunch& a) { return !a.in_f32 && a.d <= 8; }
+
+// fills a.jsplit for this shape (scratch sizing happens in the caller)
+cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
+    if (a.n0 <= 0 || a.n1 <= 0) {
+        a.jsplit = 1;
+        return cudaSuccess;
+    }
+    if (uses_main_kernel(a)) {
+        const bool ard = a.scale != nullptr;
+        return ard ? launch_main_d<true>(a, sm_count, true, nullptr) : launch_main_d<false>(a, sm_count, true, nullptr);
+    }
+    const int tj = generic_tj(a.d, a.in_f32 ? 4 : 8);
+    if (tj < 4) return cudaErrorInvalidValue;
+    const int64_t row_ctas = (a.n0 + MG_THREADS - 1) / MG_THREADS;
+    a.jsplit = choose_jsplit(row_ctas, (a.n1pad + tj - 1) / tj, sm_count * 6);
+    return cudaSuccess;
 }
 
-cudaError_t pn_launch_matvec(const PnMatvecLaunch& a, cudaStream_t stream) {
+cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStream_t stream) {
+    PnMatvecLaunch a = a_in;
     if (a.n0 <= 0) return cudaSuccess;
     const void* x1_soa = a.x1_soa;
     const int64_t ld1 = a.ld1;
     const bool ard = a.scale != nullptr;
     cudaError_t err;
-    if (!a.in_f32 && a.d <= 8) {
-        err = ard ? launch_main_d<true>(a, stream) : launch_main_d<false>(a, stream);
+    if (uses_main_kernel(a)) {
+        err = ard ? launch_main_d<true>(a, sm_count, false, stream) : launch_main_d<false>(a, sm_count, false, stream);
     } else if (!a.in_f32) {
         if (a.kc == 1) err = ard ? launch_generic<double, true, 1>(a, x1_soa, ld1, stream) : launch_generic<double, false, 1>(a, x1_soa, ld1, stream);
         else err = ard ? launch_generic<double, true, 4>(a, x1_soa, ld1, stream) : launch_generic<double, false, 4>(a, x1_soa, ld1, stream);

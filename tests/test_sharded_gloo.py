@@ -1,0 +1,82 @@
+"""Row-sharded operator over torch.distributed with world_size = 2 on CPU (gloo).
+
+The per-rank compute is a stand-in built from the oracle (there is no GPU here); what is
+under test is the N > 1 host path: row partition, replicated operand, all-gather and
+reassembly of uneven shards, identical results on every rank."""
+
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import probnum_b200 as pb
+from oracle import covfuncs_oracle as orc
+from probnum_b200.sharded import ShardedCovarianceOperator, shard_bounds
+
+SPEC = orc.KernelSpec("matern", (3,), 0.8, nu=1.5)
+
+
+class OracleLocal:
+    """Stand-in for _lib.Operator: same matmul() contract, NumPy arithmetic (test only)."""
+
+    device = 0
+
+    def __init__(self, params, rows, cols):
+        assert params.d == 3 and rows.flags.c_contiguous and cols.flags.c_contiguous
+        self.rows, self.cols = rows, cols
+
+    def matmul(self, v):
+        return orc.matvec(SPEC, self.rows, self.cols, v)
+
+
+def _worker(rank, world, port, n0, n1, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        x0 = rng.normal(size=(n0, 3))
+        x1 = rng.normal(size=(n1, 3))
+        v = rng.normal(size=(n1, 2))
+        k = pb.Matern((3,), nu=1.5, lengthscales=0.8)
+        op = ShardedCovarianceOperator(k, x0, x1, local_factory=OracleLocal)
+        assert op.shape == (n0, n1)
+        assert (op.lo, op.hi) == shard_bounds(n0, world, rank)
+        y = op @ v
+        y1 = op @ v[:, 0]
+        want = orc.matvec(SPEC, x0, x1, v)
+        np.testing.assert_allclose(y, want, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(y1, want[:, 0], rtol=1e-13, atol=1e-13)
+        # every rank must hold the same full vector (a solver iterates on it)
+        t = torch.from_numpy(np.ascontiguousarray(y))
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        assert all(torch.equal(g, gathered[0]) for g in gathered)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("n0,n1", [(101, 64), (64, 33)])
+def test_sharded_operator_world_size_2(n0, n1):
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n0, n1, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert list(out) == [1] * world

@@ -15,15 +15,17 @@ from probnum_b200 import _lib  # noqa: E402
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 32768
 nm = int(sys.argv[3]) if len(sys.argv) > 3 else 131072
+reps = 1 if os.environ.get("PROF_SINGLE") else 2
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream(dev).cuda_stream
 rng = np.random.default_rng(42)
 if what in ("gram", "all"):
     x = torch.from_numpy(rng.normal(size=(n, 3))).to(dev)
     out = torch.empty((n, n), dtype=torch.float64, device=dev)
-    for k in (pb.ExpQuad((3,)), pb.Matern((3,), nu=2.5), pb.RatQuad((3,)), pb.RatQuad((3,), alpha=1.5)):
+    kernels = (pb.ExpQuad((3,)), pb.Matern((3,), nu=2.5), pb.RatQuad((3,)), pb.RatQuad((3,), alpha=1.5))
+    for k in kernels[:2] if reps == 1 else kernels:
         op = _lib.Operator(k._kernel_params(), x.data_ptr(), None, on_device=True, n0=n, n1=n, dtype=np.float64)
-        for _ in range(2):
+        for _ in range(reps):
             op.gram_device(out.data_ptr(), n, stream=stream)
         torch.cuda.synchronize()
         print(type(k).__name__, "gram ms", op.last_kernel_ms())
@@ -33,9 +35,10 @@ if what in ("matvec", "all"):
     x = torch.from_numpy(rng.normal(size=(nm, 8))).to(dev)
     v = torch.from_numpy(rng.normal(size=(nm, 1))).to(dev)
     y = torch.empty((nm, 1), dtype=torch.float64, device=dev)
-    for k in (pb.ExpQuad((8,)), pb.Matern((8,), nu=2.5)):
+    mv_kernels = (pb.ExpQuad((8,)), pb.Matern((8,), nu=2.5))
+    for k in mv_kernels[:1] if reps == 1 else mv_kernels:
         op = _lib.Operator(k._kernel_params(), x.data_ptr(), None, on_device=True, n0=nm, n1=nm, dtype=np.float64)
-        for _ in range(2):
+        for _ in range(reps):
             op.matmul_device(v.data_ptr(), 1, 1, y.data_ptr(), 1, stream=stream)
         torch.cuda.synchronize()
         ms = op.last_kernel_ms()
