@@ -1,0 +1,148 @@
+"""Install the B200 path into an importable ``probnum`` in place (the drop-in).
+
+    import probnum
+    import probnum_b200.patch as pb_patch
+    pb_patch.enable()          # ExpQuad / Matern(nu = p + 1/2) / RatQuad now run on the GPU
+    ...
+    pb_patch.disable()         # restore the reference's NumPy methods
+
+Only the two override points named in SURVEY.md 8b are replaced, on the reference's own
+classes, so ``isinstance(kernel, ExpQuad)`` checks elsewhere in ProbNum (e.g. the kernel
+embeddings of ``probnum.quad``, quad/kernel_embeddings/_kernel_embedding.py:95-138) keep
+working and every caller -- ``CovarianceFunction.matrix / linop``, ``GaussianProcess.__call__``,
+``problinsolve`` on ``k.linop(X) + sigma^2 I``, the Bayesian-quadrature belief update -- picks
+the device path up without modification:
+
+* ``_evaluate_matrix(x0, x1)``  (randprocs/covfuncs/_covariance_function.py:553-582)
+* ``_evaluate_linop(x0, x1)``   (randprocs/covfuncs/_covariance_function.py:584-604)
+
+Kernels outside the accelerated scope (other classes, Matern with non-half-integer nu,
+multi-dimensional input shapes) keep the reference's own methods untouched: that is the
+reference's behaviour for them, not a fallback of ours.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+from . import covfuncs as _mirror
+
+_ORIGINALS = {}
+
+
+def numpy2_compat() -> None:
+    """Aliases removed in NumPy 2 that the reference still uses.  Needed to
+    import the reference at all under NumPy >= 2; harmless otherwise."""
+    if not hasattr(np, "float_"):
+        np.float_ = np.float64
+    if not hasattr(np, "Inf"):
+        np.Inf = np.inf
+    if not hasattr(np, "find_common_type"):
+        np.find_common_type = lambda array_types, scalar_types: np.result_type(*array_types, *scalar_types)
+    if not hasattr(np, "AxisError"):
+        np.AxisError = np.exceptions.AxisError
+
+
+def _mirror_of(k) -> Optional[_mirror.CovarianceFunction]:
+    """The probnum_b200 twin of a reference covariance function, or None if it is outside
+    the accelerated scope."""
+    import probnum  # noqa: PLC0415
+
+    cf = probnum.randprocs.covfuncs
+    try:
+        if len(k.input_shape) > 1:
+            return None
+    except ValueError:
+        return None
+    if type(k) is cf.ExpQuad:
+        return _mirror.ExpQuad(k.input_shape, lengthscales=k.lengthscales)
+    if type(k) is cf.Matern:
+        if not k.is_half_integer or k.p > _mirror._lib.MAX_MATERN_P:
+            return None
+        return _mirror.Matern(k.input_shape, nu=k.nu, lengthscales=k.lengthscales)
+    if type(k) is cf.RatQuad:
+        if k.lengthscale == 0:
+            return None
+        return _mirror.RatQuad(k.input_shape, lengthscale=k.lengthscale, alpha=k.alpha)
+    return None
+
+
+def _make_linop_class():
+    import probnum  # noqa: PLC0415
+
+    class GpuCovarianceLinearOperator(probnum.linops.LinearOperator):
+        """``probnum.linops.LinearOperator`` backed by the resident device operator
+        (replaces CovarianceLinearOperator, _covariance_linear_operator.py:22-90)."""
+
+        def __init__(self, inner: _mirror.CovarianceLinearOperator):
+            self._inner = inner
+            super().__init__(inner.shape, inner.dtype)
+
+        def _matmul(self, x: np.ndarray) -> np.ndarray:
+            return self._inner._matmul(np.asarray(x))
+
+        def _todense(self) -> np.ndarray:
+            return self._inner._todense()
+
+        def _transpose(self):
+            return GpuCovarianceLinearOperator(self._inner._transpose())
+
+        def _diagonal(self) -> np.ndarray:
+            return self._inner._diagonal()
+
+        def _trace(self):
+            return np.sum(self._inner._diagonal())
+
+    return GpuCovarianceLinearOperator
+
+
+def enable() -> None:
+    """Patch ExpQuad, Matern and RatQuad of the importable ``probnum``."""
+    numpy2_compat()
+    import probnum  # noqa: PLC0415
+
+    if _ORIGINALS:
+        return
+    cf = probnum.randprocs.covfuncs
+    linop_cls = _make_linop_class()
+
+    def make_matrix(original):
+        def _evaluate_matrix(self, x0, x1):
+            twin = _mirror_of(self)
+            if twin is None:
+                return original(self, x0, x1)
+            return twin._evaluate_matrix(x0, x1)
+
+        return _evaluate_matrix
+
+    def make_linop(original):
+        def _evaluate_linop(self, x0, x1):
+            twin = _mirror_of(self)
+            if twin is None:
+                return original(self, x0, x1)
+            return linop_cls(twin._evaluate_linop(x0, x1))
+
+        return _evaluate_linop
+
+    for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad):
+        _ORIGINALS[cls] = (cls._evaluate_matrix, cls._evaluate_linop)
+        cls._evaluate_matrix = make_matrix(cls._evaluate_matrix)
+        cls._evaluate_linop = make_linop(cls._evaluate_linop)
+
+
+def disable() -> None:
+    """Undo :func:`enable`."""
+    for cls, (matrix, linop) in _ORIGINALS.items():
+        # the methods are inherited from CovarianceFunction: remove our overrides
+        for name, orig in (("_evaluate_matrix", matrix), ("_evaluate_linop", linop)):
+            if name in cls.__dict__:
+                delattr(cls, name)
+            if getattr(cls, name) is not orig:
+                setattr(cls, name, orig)
+    _ORIGINALS.clear()
+
+
+def enabled() -> bool:
+    return bool(_ORIGINALS)

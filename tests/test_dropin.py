@@ -1,0 +1,166 @@
+"""The drop-in: probnum_b200.patch installed into the real ProbNum.
+
+The reference is imported from ``baseline/_ref`` (``pip install --target`` of
+/root/reference, git-ignored).  When it is absent every test here skips.
+CPU part: patch mechanics.  GPU part (``-m gpu``): reference callers -- covfuncs tests,
+``problinsolve`` (BASELINE configs[3], reduced size) and ``bayesquad_from_data``
+(configs[4], reduced size) -- give the same results with and without the device path."""
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+
+import probnum_b200.patch as pb_patch  # noqa: E402
+
+pb_patch.numpy2_compat()
+if os.path.isdir(os.path.join(REF, "probnum")) and REF not in sys.path:
+    sys.path.insert(0, REF)
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    pn = pytest.importorskip("probnum")
+
+cf = pn.randprocs.covfuncs
+
+
+@pytest.fixture
+def patched():
+    pb_patch.enable()
+    yield
+    pb_patch.disable()
+
+
+def test_enable_disable_restores_reference_methods():
+    base_matrix = cf.CovarianceFunction._evaluate_matrix
+    base_linop = cf.CovarianceFunction._evaluate_linop
+    pb_patch.enable()
+    assert pb_patch.enabled()
+    for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad):
+        assert cls._evaluate_matrix is not base_matrix and cls._evaluate_linop is not base_linop
+    assert cf.Linear._evaluate_matrix is base_matrix  # other kernels untouched
+    pb_patch.disable()
+    assert not pb_patch.enabled()
+    for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad):
+        assert cls._evaluate_matrix is base_matrix and cls._evaluate_linop is base_linop
+    # and the reference path really runs again
+    K = cf.ExpQuad((2,)).matrix(np.zeros((3, 2)))
+    np.testing.assert_array_equal(K, np.ones((3, 3)))
+
+
+def test_out_of_scope_kernels_keep_the_reference_path(patched):
+    x = np.random.default_rng(0).normal(size=(6, 2))
+    bessel = cf.Matern((2,), nu=0.7)  # Bessel branch: not accelerated, must still work
+    assert pb_patch._mirror_of(bessel) is None
+    K = bessel.matrix(x)
+    assert K.shape == (6, 6) and np.allclose(np.diag(K), 1.0)
+    assert pb_patch._mirror_of(cf.Linear((2,))) is None
+    twin = pb_patch._mirror_of(cf.Matern((2,), nu=2.5, lengthscales=[0.5, 2.0]))
+    assert twin is not None and twin.p == 2 and twin.lengthscales.tolist() == [0.5, 2.0]
+    twin = pb_patch._mirror_of(cf.RatQuad((2,), lengthscale=0.3, alpha=2.0))
+    assert float(twin.lengthscale) == 0.3 and float(twin.alpha) == 2.0
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU: the reference's callers with the device path installed
+# ---------------------------------------------------------------------------------------------
+KERNELS = [
+    (cf.ExpQuad, {"lengthscales": 1.5}),
+    (cf.RatQuad, {"lengthscale": 0.5, "alpha": 2.0}),
+    (cf.Matern, {"lengthscales": 0.5, "nu": 0.5}),
+    (cf.Matern, {"lengthscales": 0.5, "nu": 1.5}),
+    (cf.Matern, {"lengthscales": 1.5, "nu": 2.5}),
+]  # tests/test_randprocs/test_covfuncs/conftest.py:38-48 (the accelerated subset)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kdef", KERNELS, ids=lambda k: k[0].__name__ + str(k[1].get("nu", "")))
+@pytest.mark.parametrize("input_shape", [(), (1,), (10,), (100,)])
+def test_reference_fixtures_patched_equals_unpatched(kdef, input_shape):
+    rng = np.random.default_rng(0)
+    k = kdef[0](input_shape=input_shape, **kdef[1])
+    for b0, b1 in [((2,), None), ((10,), (3,)), ((100,), (10,)), ((10,), None)]:
+        x0 = rng.normal(size=b0 + input_shape)
+        x1 = None if b1 is None else rng.normal(size=b1 + input_shape)
+        want = k.matrix(x0, x1)
+        want_lin = k.linop(x0, x1) @ np.eye(want.shape[1])
+        pb_patch.enable()
+        try:
+            got = k.matrix(x0, x1)
+            L = k.linop(x0, x1)
+            assert isinstance(L, pn.linops.LinearOperator) and L.shape == want.shape
+            got_lin = L @ np.eye(want.shape[1])
+            np.testing.assert_allclose(L.todense(), want, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(L.T.todense(), want.T, rtol=1e-12, atol=1e-12)
+        finally:
+            pb_patch.disable()
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(got_lin, want_lin, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gaussian_process_marginal(patched):
+    gp = pn.randprocs.GaussianProcess(pn.functions.Zero(input_shape=()), cf.ExpQuad(input_shape=()))
+    x = np.linspace(-1, 1, 5)
+    rv = gp(x)
+    assert isinstance(gp.cov, cf.ExpQuad)
+    np.testing.assert_allclose(rv.cov[0], [1.0, 0.8824969, 0.60653066, 0.32465247, 0.13533528], rtol=1e-7)
+
+
+@pytest.mark.gpu
+def test_problinsolve_on_gpu_linop_matches_cpu_run():
+    """BASELINE configs[3] at reduced size: (K + 1e-3 I) x = y with the matrix-free GPU
+    operator inside the unmodified solver; iterates must agree with the CPU run."""
+    rng = np.random.default_rng(42)
+    n, d = 1500, 4
+    X = rng.normal(size=(n, d))
+    y = rng.normal(size=n)
+    k = cf.ExpQuad((d,), lengthscales=0.25)
+
+    def solve():
+        A = k.linop(X) + 1e-3 * pn.linops.Identity(n)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            x, _, _, info = pn.linalg.problinsolve(A, y, maxiter=60)
+        return x.mean, info
+
+    x_cpu, info_cpu = solve()
+    pb_patch.enable()
+    try:
+        x_gpu, info_gpu = solve()
+    finally:
+        pb_patch.disable()
+    assert info_gpu["iter"] == info_cpu["iter"]
+    # norm-wise 1e-8: the system has condition number ~1e5, which amplifies the
+    # ~1e-16 differences between the two matvec implementations
+    assert np.abs(x_gpu - x_cpu).max() <= 1e-8 * np.abs(x_cpu).max()
+
+
+@pytest.mark.gpu
+def test_bayesquad_from_data_matches_cpu_run():
+    """BASELINE configs[4] at reduced size: ExpQuad + Gaussian measure; the belief update
+    calls kernel.matrix(nodes) (quad/solvers/belief_updates/_standard_update.py:56)."""
+    rng = np.random.default_rng(42)
+    n, d = 1200, 4
+    nodes = rng.normal(size=(n, d))
+    fun_evals = np.sin(nodes).sum(axis=1)
+    measure = pn.quad.integration_measures.GaussianMeasure(mean=np.zeros(d), cov=np.eye(d))
+
+    def run():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            F, _ = pn.quad.bayesquad_from_data(nodes=nodes, fun_evals=fun_evals, measure=measure)
+        return float(F.mean), float(F.var)
+
+    m_cpu, v_cpu = run()
+    pb_patch.enable()
+    try:
+        m_gpu, v_gpu = run()
+    finally:
+        pb_patch.disable()
+    assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), 1e-3)
+    assert abs(v_gpu - v_cpu) <= 1e-7 * abs(v_cpu) + 1e-14
