@@ -289,7 +289,7 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("gram_strip_kernel_bytes_per_launch")
+            traffic = json.load(fh).get("gram_fast_kernel_bytes_per_launch")
     roofline = {
         "bound": "hbm", "kernel": f"gram_fast_kernel<D=3> ({dom} epilogue)",
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
