@@ -356,6 +356,7 @@ PnGramLaunch gram_launch(const pncov_handle* h, bool transpose, int64_t row0, in
     g.ldo = ld;
     g.in_f32 = h->k.dtype == PNCOV_F32;
     g.out_f32 = h->k.gram_f32();
+    g.symmetric = (h->symmetric && row0 == 0 && rows == R.n) ? 1 : 0;
     g.epi = h->k.epi;
     return g;
 }

@@ -207,7 +207,16 @@ __global__ void __launch_bounds__(G_THREADS)
 // Preconditions (checked by the launcher): n0 % G_TM == 0, n1 % G_TN == 0, rows of the
 // output 16-byte aligned.  Nothing in the loop is predicated; the column points of the
 // thread's two columns live in registers; the output pointer advances by one row stride.
-template <int D, bool ARD, int EPI>
+//
+// SYM (x1 is x0, square interior): the output is symmetric and K[i][j] is computed by the
+// very same instruction sequence as K[j][i] (the differences only change sign), so a CTA
+// whose row tile lies strictly above the diagonal 512 x 512 super-tile also stores the
+// transposed tile, and CTAs below the diagonal super-tile exit at once.  FP64 work per
+// stored entry halves, which moves Matern / general RatQuad from FP64-bound to HBM-bound.
+// The transposed tile goes through shared memory (16 rows x 512 columns, XOR-swizzled 16-byte
+// chunks, conflict-free both ways) so that every mirrored row leaves as a full 128-byte
+// line; direct 32-byte mirror stores were measured at half the DRAM efficiency.
+template <int D, bool ARD, int EPI, bool SYM>
 __global__ void __launch_bounds__(G_THREADS)
     gram_fast_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -216,10 +225,14 @@ __global__ void __launch_bounds__(G_THREADS)
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
     double* x0s = reinterpret_cast<double*>(smem + G_HDR_BYTES);  // [2][D][G_TM]
+    // SYM only: transposed staging, [G_TN columns][8 chunks of 2 rows], chunk index swizzled
+    double2* mir = reinterpret_cast<double2*>(smem + G_HDR_BYTES + 2 * D * G_TM * 8);
 
     const int n_tiles = (int)(g.n0 / G_TM);
     const int t0 = blockIdx.y * tiles_per_cta;
-    const int t1 = min(t0 + tiles_per_cta, n_tiles);
+    int t1 = min(t0 + tiles_per_cta, n_tiles);
+    // SYM: rows below this strip's diagonal super-tile are produced by mirror stores
+    if constexpr (SYM) t1 = min(t1, (int)(blockIdx.x + 1) * (G_TN / G_TM));
     if (t0 >= t1) return;
     const int64_t j0 = (int64_t)blockIdx.x * G_TN + 2 * tid;
     const double* x0g = static_cast<const double*>(g.x0_soa);
@@ -250,6 +263,9 @@ __global__ void __launch_bounds__(G_THREADS)
     }
     double* optr = static_cast<double*>(g.out) + (size_t)t0 * G_TM * g.ldo + j0;
     const size_t row_stride = (size_t)g.ldo;
+    // mirrored block of this strip: rows = the strip's columns, columns = this CTA's rows
+    double* mbase = static_cast<double*>(g.out) + (size_t)blockIdx.x * G_TN * g.ldo;
+    const int t_diag = (int)blockIdx.x * (G_TN / G_TM);  // first row tile of the diagonal super-tile
     __syncthreads();
 
     int it = 0;
@@ -293,6 +309,33 @@ __global__ void __launch_bounds__(G_THREADS)
             for (int r = 0; r < G_R; ++r) {
                 pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
                 optr += row_stride;
+            }
+            if constexpr (SYM) {
+                if (t < t_diag) {  // uniform per tile
+                    const int q = (rg >> 2) & 3;  // which 4-row group of the 16-row staging block
+                    const int sw = tid & 7;       // swizzle key: (local column >> 1) & 7
+                    double2* c0 = mir + (2 * tid) * 8;
+                    double2* c1 = c0 + 8;
+                    c0[(2 * q) ^ sw] = make_double2(K[0], K[2]);
+                    c0[(2 * q + 1) ^ sw] = make_double2(K[4], K[6]);
+                    c1[(2 * q) ^ sw] = make_double2(K[1], K[3]);
+                    c1[(2 * q + 1) ^ sw] = make_double2(K[5], K[7]);
+                    if (q == 3) {
+                        // a warp's 32 lanes own 64 adjacent columns, so the 64 staged columns it
+                        // just wrote are its own: warp-level sync is enough, no CTA barrier
+                        __syncwarp();
+                        const int lane = tid & 31;
+                        const int cbase = (tid >> 5) * 64;
+                        double* mrow = mbase + (size_t)t * G_TM + (rg - 12);
+#pragma unroll 4
+                        for (int i = 0; i < 16; ++i) {
+                            const int c = cbase + i * 4 + (lane >> 3), ch = lane & 7;
+                            const double2 v = mir[c * 8 + (ch ^ ((c >> 1) & 7))];
+                            __stcs(reinterpret_cast<double2*>(mrow + (size_t)c * row_stride + 2 * ch), v);
+                        }
+                        __syncwarp();
+                    }
+                }
             }
         }
         __syncthreads();
@@ -375,12 +418,19 @@ cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
     const int64_t n_tiles = g.n0 / G_TM;
     int64_t tpc = (n_tiles * strips) / (148 * 48);
     tpc = tpc < 1 ? 1 : (tpc > 32 ? 32 : tpc);
+    if (g.symmetric) tpc = tpc > 4 ? 4 : tpc;  // finer row chunks: half of the grid exits at once
     const int64_t gy = (n_tiles + tpc - 1) / tpc;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
-    const size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * G_TM;
-    auto kern = gram_fast_kernel<D, ARD, EPI>;
+    size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * G_TM;
     dim3 grid((unsigned)strips, (unsigned)gy);
-    kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
+    if (g.symmetric) {
+        smem += (size_t)G_TN * 8 * sizeof(double2);  // 64 KB transposed staging
+        auto kern = gram_fast_kernel<D, ARD, EPI, true>;
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
+    } else
+        gram_fast_kernel<D, ARD, EPI, false><<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
     ++g_pn_launches;
     return cudaGetLastError();
 }
@@ -481,21 +531,28 @@ cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
     PnGramLaunch in = g;
     in.n0 = n0i;
     in.n1 = n1i;
+    // mirror stores pay only where the FP64 pipe, not HBM, limits the general kernel
+    const bool fp64_heavy = g.epi.epi != PN_EPI_EXPQUAD && g.epi.epi != PN_EPI_RATQUAD1 && g.epi.epi != PN_EPI_RATQUAD2;
+    in.symmetric = (g.symmetric && fp64_heavy && g.n0 == g.n1 && g.x0_soa == g.x1_soa) ? 1 : 0;
+    if (in.symmetric) in.n0 = n1i;  // square interior on the 512 grid; the rest goes to the edge launches
+    const int64_t n0_done = in.n0;
     cudaError_t err = g.scale ? launch_fast<true>(in, stream) : launch_fast<false>(in, stream);
     if (err != cudaSuccess) return err;
     if (n1i < g.n1) {  // right edge: all rows, remaining columns
         PnGramLaunch e = g;
+        e.symmetric = 0;
         e.x1_soa = static_cast<const double*>(g.x1_soa) + n1i;
         e.n1 = g.n1 - n1i;
         e.out = static_cast<double*>(g.out) + n1i;
         if ((err = launch_generic(e, stream)) != cudaSuccess) return err;
     }
-    if (n0i < g.n0) {  // bottom edge: remaining rows, interior columns
+    if (n0_done < g.n0) {  // bottom edge: remaining rows, interior columns
         PnGramLaunch e = g;
-        e.x0_soa = static_cast<const double*>(g.x0_soa) + n0i;
-        e.n0 = g.n0 - n0i;
+        e.x0_soa = static_cast<const double*>(g.x0_soa) + n0_done;
+        e.n0 = g.n0 - n0_done;
         e.n1 = n1i;
-        e.out = static_cast<double*>(g.out) + n0i * g.ldo;
+        e.symmetric = 0;
+        e.out = static_cast<double*>(g.out) + n0_done * g.ldo;
         if ((err = launch_generic(e, stream)) != cudaSuccess) return err;
     }
     return cudaSuccess;

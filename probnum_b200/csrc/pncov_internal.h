@@ -21,6 +21,7 @@ struct PnGramLaunch {
     int64_t ldo;
     int in_f32;          // points are float32
     int out_f32;         // Gram entries are float32 (only ExpQuad on float32 points)
+    int symmetric;       // x1 is x0 and the whole square matrix is requested: mirror stores allowed
     PnEpiParams epi;
 };
 

@@ -162,5 +162,6 @@ def test_bayesquad_from_data_matches_cpu_run():
         m_gpu, v_gpu = run()
     finally:
         pb_patch.disable()
-    assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), 1e-3)
+    # the integral is ~0 by symmetry (cancellation of O(1) terms): compare on the scale of f
+    assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), np.abs(fun_evals).max())
     assert abs(v_gpu - v_cpu) <= 1e-7 * abs(v_cpu) + 1e-14

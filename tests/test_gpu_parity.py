@@ -290,3 +290,58 @@ def test_config4_matvec_65536():
     rhs = 2.5 * y + L @ w
     np.testing.assert_allclose(lhs, rhs, rtol=1e-10, atol=1e-9)
     L.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# symmetric mirror stores and the device-pointer entry points of the C ABI
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [512, 1024, 1537, 2048 + 64, 3000])
+@pytest.mark.parametrize("spec", [SPECS[0], SPECS[4], SPECS[8]], ids=["expquad", "matern52", "ratquad-general"])
+def test_symmetric_gram_is_bitwise_the_general_gram(spec, n):
+    """x1=None takes the mirror-store kernel; passing the same points as x1 takes the general
+    one.  K[i][j] and K[j][i] come from the same instruction sequence, so both must agree
+    bit for bit, and with the oracle to 1e-12."""
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(n,) + spec.input_shape)
+    k = make_kernel(spec)
+    Ks = k.matrix(x)
+    Kg = k.matrix(x, x.copy())
+    np.testing.assert_array_equal(Ks, Kg)
+    np.testing.assert_array_equal(Ks, Ks.T)
+    rows = rng.choice(n, size=40, replace=False)
+    np.testing.assert_allclose(Ks[rows], orc.gram(spec, x[rows], x), rtol=1e-12, atol=1e-12)
+    assert np.all(np.diagonal(Ks) == 1.0)
+
+
+def test_device_pointer_entry_points():
+    """pncov_gram_device / pncov_matmul_device on torch-owned memory and stream."""
+    torch = pytest.importorskip("torch")
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(23)
+    n0, n1, d = 1100, 1500, 4
+    spec = orc.KernelSpec("matern", (d,), 0.9, nu=1.5)
+    x0, x1 = rng.normal(size=(n0, d)), rng.normal(size=(n1, d))
+    dev = torch.device("cuda", 0)
+    tx0, tx1 = torch.from_numpy(x0).to(dev), torch.from_numpy(x1).to(dev)
+    op = _lib.Operator(make_kernel(spec)._kernel_params(), tx0.data_ptr(), tx1.data_ptr(), on_device=True,
+                       n0=n0, n1=n1, dtype=np.float64, device=0)
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        out = torch.full((n0, n1 + 6), -7.0, dtype=torch.float64, device=dev)  # padded leading dimension
+        op.gram_device(out.data_ptr(), n1 + 6, stream=side.cuda_stream)
+        v = torch.from_numpy(rng.normal(size=(n1, 3))).to(dev)
+        y = torch.empty((n0, 3), dtype=torch.float64, device=dev)
+        op.matmul_device(v.data_ptr(), 3, 3, y.data_ptr(), 3, stream=side.cuda_stream)
+        outT = torch.empty((n1, n0), dtype=torch.float64, device=dev)
+        op.gram_device(outT.data_ptr(), n0, transpose=True, stream=side.cuda_stream)
+    side.synchronize()
+    K = orc.gram(spec, x0, x1)
+    got = out.cpu().numpy()
+    np.testing.assert_allclose(got[:, :n1], K, rtol=1e-12, atol=1e-12)
+    assert np.all(got[:, n1:] == -7.0)  # padding columns untouched
+    np.testing.assert_allclose(outT.cpu().numpy(), K.T, rtol=1e-12, atol=1e-12)
+    vh = v.cpu().numpy()
+    assert_matvec_close(y.cpu().numpy(), K @ vh, np.abs(K) @ np.abs(vh), 1e-12)
+    assert op.last_kernel_ms() > 0
+    op.close()
