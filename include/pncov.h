@@ -132,6 +132,10 @@ PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const doub
  * device time in ms of the last pncov_gram / pncov_matmul call of this handle (CUDA
  * events on the handle's stream around the kernels, excluding host<->device copies). */
 PNCOV_API int64_t pncov_launch_count(void);
+/* which kernel family serves pncov_matmul for this handle: 0 = not decided yet (no product
+ * so far), 1 = norm-identity + DMMA (ExpQuad / RatQuad, d <= 8, error bound satisfied),
+ * 2 = direct differences */
+PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path);
 PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms);
 
 #ifdef __cplusplus

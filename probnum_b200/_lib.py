@@ -51,6 +51,7 @@ SIGNATURES = {
          ctypes.c_double, _c_vp, _c_vp, _c_i64, _c_vp],
     ),
     "pncov_launch_count": (_c_i64, []),
+    "pncov_matmul_path": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_int)]),
     "pncov_last_kernel_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
 }
 
@@ -233,6 +234,12 @@ class Operator:
                       transpose: bool = False, stream: int = 0) -> None:
         _check(self._lib.pncov_matmul_device(self._h, _c_vp(v_ptr), k, ldv, _c_vp(y_ptr), ldy,
                                              1 if transpose else 0, _c_vp(stream)))
+
+    def matmul_path(self) -> str:
+        """'undecided', 'norm-identity-dmma' or 'direct-differences' (see pncov_matmul_path)."""
+        p = ctypes.c_int()
+        _check(self._lib.pncov_matmul_path(self._h, ctypes.byref(p)))
+        return ("undecided", "norm-identity-dmma", "direct-differences")[p.value]
 
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_float()

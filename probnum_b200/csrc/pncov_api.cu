@@ -4,6 +4,7 @@
 // pncov_matvec.cu.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -69,6 +70,59 @@ __global__ void unpack_y_kernel(const T* __restrict__ yp, int64_t rows, int kc, 
     const int64_t i = idx / kc;
     const int c = (int)(idx % kc);
     if (c0 + c < k) y[i * ldy + c0 + c] = yp[idx];
+}
+
+// per-coordinate sums of a point set, one block, fixed summation order (deterministic centre)
+__global__ void coord_sums_kernel(const double* __restrict__ aos, int64_t n, int d, double* __restrict__ sums) {
+    __shared__ double red[1024];
+    for (int m = 0; m < d; ++m) {
+        double s = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += aos[i * d + m];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+            if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) sums[m] = red[0];
+        __syncthreads();
+    }
+}
+
+// centred + scaled operands of the norm-identity matvec: xt = (x - c) * s
+//   a12[i] = [xt_0..xt_7, |xt|^2, 0, 0, 0]      b12[i] = [-2 xt_0..-2 xt_7, |xt|^2, 0, 0, 0]
+// rows [n, npad) are zero.  max_norm receives max_i |xt_i|^2 (bit pattern of a non-negative
+// double, so an integer atomicMax is exact and order independent).
+__global__ void build_mma_operands_kernel(const double* __restrict__ aos, int64_t n, int64_t npad, int d,
+                                          const double* __restrict__ centre, const double* __restrict__ scale,
+                                          double iso_scale, double* __restrict__ a12, double* __restrict__ b12,
+                                          unsigned long long* __restrict__ max_norm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    double xt[8];
+    double nrm = 0.0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        double v = 0.0;
+        if (i < n && m < d) v = (aos[i * d + m] - centre[m]) * (scale ? scale[m] : iso_scale);
+        xt[m] = v;
+        nrm = fma(v, v, nrm);
+    }
+    double* pa = a12 + i * 12;
+    double* pb = b12 + i * 12;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        pa[m] = xt[m];
+        pb[m] = -2.0 * xt[m];
+    }
+    pa[8] = nrm;
+    pb[8] = nrm;
+#pragma unroll
+    for (int m = 9; m < 12; ++m) {
+        pa[m] = 0.0;
+        pb[m] = 0.0;
+    }
+    if (i < n) atomicMax(max_norm, (unsigned long long)__double_as_longlong(nrm));
 }
 
 // out[b] = k(x0[b], x1[b]); one thread per pair (O(B d) work, not a hot path)
@@ -269,6 +323,11 @@ struct pncov_handle {
     size_t partial_bytes = 0;
     void* stage = nullptr;  // device staging for host entry points
     size_t stage_bytes = 0;
+    // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
+    int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
+    void* a12[2] = {nullptr, nullptr};  // per point set (0: x0, 1: x1); aliases when symmetric
+    void* b12[2] = {nullptr, nullptr};
+    PnEpiParams mma_epi{};
 };
 
 namespace {
@@ -361,6 +420,89 @@ PnGramLaunch gram_launch(const pncov_handle* h, bool transpose, int64_t row0, in
     return g;
 }
 
+// Decide whether the norm-identity kernel may serve this handle and build its operands.
+//
+// With xt = (x - c) s the identity S = |xt_i|^2 + |yt_j|^2 - 2 xt_i.yt_j carries an absolute
+// error of at most about (4 d + 24) 2^-53 R^2, R^2 = max |xt|^2 (rounding of the centred and
+// scaled coordinates, of the two norms, of the d products and of the sums), where the
+// direct differences of the reference are exact to a few ulp of S itself.  For ExpQuad the
+// relative error of K equals the absolute error of S (in the scaled units); for RatQuad it
+// is bounded by alpha c |dS| = |dS| / (2 l^2).  The identity is used only if that bound stays
+// under 2e-13, a fifth of the 1e-12 parity contract; otherwise (clouds that are wide in units
+// of the lengthscale) the direct-difference kernel runs.  Matern needs sqrt(S), whose error
+// is unbounded as S -> 0, and always uses direct differences.
+int mma_prepare(pncov_handle* h, cudaStream_t stream) {
+    if (h->mma_state != 0) return 0;
+    h->mma_state = -1;
+    const KernelDesc& k = h->k;
+    if (k.dtype != PNCOV_F64 || k.d > 8 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
+    if (h->p0.n == 0 || h->p1.n == 0) return 0;
+    if (getenv("PNCOV_DISABLE_MMA")) return 0;
+    const int d = k.d;
+    double* sums = nullptr;
+    PN_CUDA(cudaMalloc(&sums, 16 * sizeof(double) + sizeof(unsigned long long)));
+    unsigned long long* max_norm = reinterpret_cast<unsigned long long*>(sums + 16);
+    auto fail_free = [&](int rc) {
+        cudaFree(sums);
+        return rc;
+    };
+    coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p0.aos, h->p0.n, d, sums);
+    coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p1.aos, h->p1.n, d, sums + 8);
+    g_pn_launches += 2;
+    double host_sums[16];
+    cudaError_t e = cudaMemcpyAsync(host_sums, sums, sizeof(host_sums), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
+    double centre[8] = {0};
+    const double ntot = (double)h->p0.n + (h->symmetric ? 0.0 : (double)h->p1.n);
+    for (int m = 0; m < d; ++m)
+        centre[m] = (host_sums[m] + (h->symmetric ? 0.0 : host_sums[8 + m])) / ntot;
+    e = cudaMemcpyAsync(sums, centre, sizeof(centre), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(max_norm, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
+    // ExpQuad: operands carry the scale factors, the exponent constant becomes -log2(e);
+    // RatQuad: unscaled (its c multiplies S in the epilogue)
+    const bool expq = k.kind == PNCOV_EXPQUAD;
+    double iso = 1.0;
+    if (expq && !k.ard) iso = sqrt(-k.epi.c_u / kLog2e);  // s, from c_u = -log2(e) s^2
+    const double* scale_dev = (expq && k.ard) ? (const double*)h->scale_dev : nullptr;
+    const int nsets = h->symmetric ? 1 : 2;
+    for (int sidx = 0; sidx < nsets; ++sidx) {
+        const Points& P = sidx == 0 ? h->p0 : h->p1;
+        const size_t bytes = (size_t)P.npad * 12 * sizeof(double);
+        e = cudaMalloc(&h->a12[sidx], bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&h->b12[sidx], bytes);
+        if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
+        build_mma_operands_kernel<<<(unsigned)((P.npad + 255) / 256), 256, 0, stream>>>(
+            (const double*)P.aos, P.n, P.npad, d, sums, scale_dev, iso, (double*)h->a12[sidx],
+            (double*)h->b12[sidx], max_norm);
+        ++g_pn_launches;
+    }
+    if (h->symmetric) {
+        h->a12[1] = h->a12[0];
+        h->b12[1] = h->b12[0];
+    }
+    unsigned long long bits = 0;
+    e = cudaMemcpyAsync(&bits, max_norm, sizeof(bits), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(sums);
+    if (e != cudaSuccess) return fail_cuda(e, "mma_prepare");
+    double r2;
+    memcpy(&r2, &bits, 8);
+    const double sens = expq ? 1.0 : k.epi.alpha * k.epi.c_s;  // d(log K)/dS bound
+    const double bound = (4.0 * d + 24.0) * ldexp(1.0, -53) * r2 * sens;
+    if (!(bound <= 2e-13)) return 0;  // stays at -1: direct differences
+    h->mma_epi = k.epi;
+    if (expq) {
+        h->mma_epi.c_u = -kLog2e;
+        h->mma_epi.c_s = 1.0;
+        h->mma_epi.c_su = -kLog2e;
+        fill_window(h->mma_epi);
+    }
+    h->mma_state = 1;
+    return 0;
+}
+
 int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy,
                        bool transpose, cudaStream_t stream) {
     const Points& R = transpose ? h->p1 : h->p0;
@@ -386,6 +528,16 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     m.kc = kc_max;
     m.in_f32 = h->k.dtype == PNCOV_F32;
     m.epi = h->k.epi;
+    {
+        int prc = mma_prepare(h, stream);
+        if (prc) return prc;
+    }
+    if (h->mma_state == 1) {
+        m.use_mma = 1;
+        m.a12 = h->a12[transpose ? 1 : 0];
+        m.b12 = h->b12[transpose ? 0 : 1];
+        m.epi = h->mma_epi;
+    }
     PN_CUDA(pn_plan_matvec(m, h->sm_count));
     const int jsplit = m.jsplit;
     int rc;
@@ -516,6 +668,12 @@ PNCOV_API int pncov_destroy(pncov_handle* h) {
     if (h->ypack) cudaFree(h->ypack);
     if (h->partial) cudaFree(h->partial);
     if (h->stage) cudaFree(h->stage);
+    if (h->a12[0]) cudaFree(h->a12[0]);
+    if (h->b12[0]) cudaFree(h->b12[0]);
+    if (!h->symmetric) {
+        if (h->a12[1]) cudaFree(h->a12[1]);
+        if (h->b12[1]) cudaFree(h->b12[1]);
+    }
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -696,6 +854,12 @@ PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const doub
 }
 
 PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
+
+PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {
+    if (!h || !path) return fail(PNCOV_EINVAL, "NULL argument");
+    *path = h->mma_state == 0 ? 0 : (h->mma_state == 1 ? 1 : 2);
+    return 0;
+}
 
 PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms) {
     if (!h || !ms) return fail(PNCOV_EINVAL, "NULL argument");

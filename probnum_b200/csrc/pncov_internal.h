@@ -38,6 +38,13 @@ struct PnMatvecLaunch {
     int kc;              // columns in this pass (1, 2, 4 or 8)
     void* partial;       // (jsplit, n0, kc) scratch when jsplit > 1
     int jsplit;
+    // norm-identity / DMMA variant (ExpQuad, RatQuad; float64; d <= 8; host-checked error bound):
+    // centred + scaled operands, 12 doubles per point: a12 = [xt(8), |xt|^2, 0, 0, 0] for the
+    // rows, b12 = [-2 xt(8), |xt|^2, 0, 0, 0] for the columns.  epi then holds the epilogue
+    // parameters in the scaled units.
+    const void* a12;
+    const void* b12;
+    int use_mma;
     int in_f32;
     PnEpiParams epi;
 };

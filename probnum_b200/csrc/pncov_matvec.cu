@@ -184,6 +184,140 @@ __global__ void __launch_bounds__(MV_THREADS)
     }
 }
 
+// ---- norm-identity kernel: S = |x|^2 + |y|^2 - 2 x.y with the inner products on DMMA ---------
+// ExpQuad / RatQuad, float64, d <= 8, used only when the host-side bound on the cancellation
+// error (pncov_api.cu: mma_admissible) keeps K within the parity contract.  On B200 the FP64
+// tensor path shares the FP64 pipe with DFMA (profiles/r01_microbench.json), so DMMA buys
+// FP64-pipe time only through the identity itself (d FMAs instead of d DADD + d DFMA per
+// pair) plus ~8 % higher DMMA issue rate, and it frees issue slots: one DMMA.8x8x4 replaces
+// eight DFMA warp instructions.
+//
+// Fragment layout of mma.m8n8k4.f64 (g = lane / 4, q = lane % 4):
+//   A[g][q]  B[q][g]  C[g][2q], C[g][2q + 1]
+// A warp owns MM_RG groups of 8 rows; per step of 8 columns every lane ends up with two
+// entries S[g][2q], S[g][2q + 1] per row group, runs the epilogue on them and accumulates
+// K * v for "its" row g; the four lanes that share a row are reduced with shuffles once,
+// at the end of the kernel.
+constexpr int MM_THREADS = 128;
+constexpr int MM_RG = 4;                          // row groups of 8 per warp
+constexpr int MM_ROWS = (MM_THREADS / 32) * MM_RG * 8;  // rows per CTA = 128
+constexpr int MM_TJ = 128;                        // columns per pipeline stage
+constexpr int MM_LD = 12;                         // doubles per point in a12 / b12
+
+__device__ __forceinline__ void pn_dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+template <int KSTEPS, int KC, int EPI>
+__global__ void __launch_bounds__(MM_THREADS)
+    matvec_mma_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    constexpr int STAGE_DOUBLES = MM_TJ * (MM_LD + KC);
+    double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
+
+    const int64_t n_jt = a.n1pad / MM_TJ;
+    const int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+    const double* bg = static_cast<const double*>(a.b12);
+    const double* vg = static_cast<const double*>(a.v);
+    constexpr uint32_t B_BYTES = MM_TJ * MM_LD * 8, V_BYTES = MM_TJ * KC * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0 && jt0 < jt1) {
+        pn_mbar_expect_tx(&bars[0], B_BYTES + V_BYTES);
+        pn_bulk_g2s(stage0, bg + jt0 * MM_TJ * MM_LD, B_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + MM_TJ * MM_LD, vg + jt0 * MM_TJ * KC, V_BYTES, &bars[0]);
+    }
+    pn_stage_tables(tabE, tabL, tid, MM_THREADS);
+
+    const int64_t row0 = (int64_t)blockIdx.x * MM_ROWS + warp * (MM_RG * 8);
+    double af[MM_RG][KSTEPS], nx[MM_RG], acc[MM_RG][KC];
+    {
+        const double* ag = static_cast<const double*>(a.a12);
+#pragma unroll
+        for (int rg = 0; rg < MM_RG; ++rg) {
+            const double* pr = ag + (row0 + rg * 8 + g) * MM_LD;  // rows are padded to PN_PAD
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) af[rg][kk] = pr[4 * kk + q];
+            nx[rg] = pr[8];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) acc[rg][k] = 0.0;
+        }
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (int64_t jt = jt0; jt < jt1; ++jt, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && jt + 1 < jt1) {
+            double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
+            pn_mbar_expect_tx(&bars[buf ^ 1], B_BYTES + V_BYTES);
+            pn_bulk_g2s(dst, bg + (jt + 1) * MM_TJ * MM_LD, B_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + MM_TJ * MM_LD, vg + (jt + 1) * MM_TJ * KC, V_BYTES, &bars[buf ^ 1]);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
+        const double* vt = bt + MM_TJ * MM_LD;
+
+#pragma unroll 1
+        for (int jj = 0; jj < MM_TJ; jj += 8) {
+            double bf[KSTEPS];
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(jj + g) * MM_LD + 4 * kk + q];
+            const double ny0 = bt[(jj + 2 * q) * MM_LD + 8];
+            const double ny1 = bt[(jj + 2 * q + 1) * MM_LD + 8];
+            double S[2 * MM_RG];
+#pragma unroll
+            for (int rg = 0; rg < MM_RG; ++rg) {
+                double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
+                S[2 * rg] = c0;
+                S[2 * rg + 1] = c1;
+            }
+            mv_epi_tile<EPI>(S, a.epi, tabE, tabL);
+#pragma unroll
+            for (int k = 0; k < KC; ++k) {
+                const double v0 = vt[(jj + 2 * q) * KC + k];
+                const double v1 = vt[(jj + 2 * q + 1) * KC + k];
+#pragma unroll
+                for (int rg = 0; rg < MM_RG; ++rg) {
+                    acc[rg][k] = pn_fma(S[2 * rg], v0, acc[rg][k]);
+                    acc[rg][k] = pn_fma(S[2 * rg + 1], v1, acc[rg][k]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    double* dst = (a.jsplit > 1) ? static_cast<double*>(a.partial) + (size_t)blockIdx.y * a.n0 * KC
+                                 : static_cast<double*>(a.y);
+#pragma unroll
+    for (int rg = 0; rg < MM_RG; ++rg) {
+        const int64_t row = row0 + rg * 8 + g;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            double s = acc[rg][k];
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0 && row < a.n0) dst[row * KC + k] = s;
+        }
+    }
+}
+
 // ---- generic kernel: any d <= 1024, float64 or float32 points ---------------------------------
 // One row per thread, its point read through L1 each time; column points in coordinate-major
 // shared-memory tiles, four columns per register tile.  Slower than the main kernel (extra
@@ -324,6 +458,10 @@ cudaError_t launch_main(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStr
     }
     const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
     dim3 grid((unsigned)row_ctas, (unsigned)a.jsplit);
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
     kern<<<grid, MV_THREADS, smem, stream>>>(a, (int)tps);
     ++g_pn_launches;
     return cudaGetLastError();
@@ -367,6 +505,48 @@ cudaError_t launch_main_d(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t str
     }
 }
 
+template <int KSTEPS, int KC, int EPI>
+cudaError_t launch_mma(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStream_t stream) {
+    auto kern = matvec_mma_kernel<KSTEPS, KC, EPI>;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MM_TJ * (MM_LD + KC);
+    const int64_t n_jt = a.n1pad / MM_TJ;
+    const int64_t row_ctas = (a.n0 + MM_ROWS - 1) / MM_ROWS;
+    if (plan_only) {
+        int occ = 1;
+        cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MM_THREADS, smem);
+        if (err != cudaSuccess) return err;
+        a.jsplit = choose_jsplit(row_ctas, n_jt, sm_count * (occ < 1 ? 1 : occ));
+        return cudaSuccess;
+    }
+    const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
+    dim3 grid((unsigned)row_ctas, (unsigned)a.jsplit);
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
+    kern<<<grid, MM_THREADS, smem, stream>>>(a, (int)tps);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int KSTEPS, int KC>
+cudaError_t launch_mma_epi(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_mma<KSTEPS, KC, PN_EPI_EXPQUAD>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD1: return launch_mma<KSTEPS, KC, PN_EPI_RATQUAD1>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD2: return launch_mma<KSTEPS, KC, PN_EPI_RATQUAD2>(a, sm, plan, stream);
+        case PN_EPI_RATQUADG: return launch_mma<KSTEPS, KC, PN_EPI_RATQUADG>(a, sm, plan, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_mma_any(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    const bool two = a.d > 4;
+    if (a.kc == 1) return two ? launch_mma_epi<2, 1>(a, sm, plan, stream) : launch_mma_epi<1, 1>(a, sm, plan, stream);
+    if (a.kc == 4) return two ? launch_mma_epi<2, 4>(a, sm, plan, stream) : launch_mma_epi<1, 4>(a, sm, plan, stream);
+    return cudaErrorInvalidValue;
+}
+
 int generic_tj(int d, size_t elem) {
     // coordinate-major tile of tj points: keep it under ~40 KB
     int tj = (int)((40 * 1024) / ((size_t)d * elem));
@@ -401,6 +581,7 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
         a.jsplit = 1;
         return cudaSuccess;
     }
+    if (a.use_mma) return launch_mma_any(a, sm_count, true, nullptr);
     if (uses_main_kernel(a)) {
         const bool ard = a.scale != nullptr;
         return ard ? launch_main_d<true>(a, sm_count, true, nullptr) : launch_main_d<false>(a, sm_count, true, nullptr);
@@ -419,7 +600,9 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     const int64_t ld1 = a.ld1;
     const bool ard = a.scale != nullptr;
     cudaError_t err;
-    if (uses_main_kernel(a)) {
+    if (a.use_mma) {
+        err = launch_mma_any(a, sm_count, false, stream);
+    } else if (uses_main_kernel(a)) {
         err = ard ? launch_main_d<true>(a, sm_count, false, stream) : launch_main_d<false>(a, sm_count, false, stream);
     } else if (!a.in_f32) {
         if (a.kc == 1) err = ard ? launch_generic<double, true, 1>(a, x1_soa, ld1, stream) : launch_generic<double, false, 1>(a, x1_soa, ld1, stream);

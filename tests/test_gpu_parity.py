@@ -345,3 +345,48 @@ def test_device_pointer_entry_points():
     assert_matvec_close(y.cpu().numpy(), K @ vh, np.abs(K) @ np.abs(vh), 1e-12)
     assert op.last_kernel_ms() > 0
     op.close()
+
+
+def test_matvec_path_selection_and_parity_of_both_paths():
+    """ExpQuad / RatQuad products use the norm-identity + DMMA kernel only when the host-side
+    error bound allows it; a cloud that is wide in units of the lengthscale must fall back to
+    direct differences.  Both paths have to meet the same componentwise bound."""
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(31)
+    n, d = 2500, 8
+    x = rng.normal(size=(n, d)) + 300.0  # far from the origin: the centring has to cope
+    v = rng.normal(size=(n, 2))
+    for spec, want_path in [
+        (orc.KernelSpec("expquad", (d,), 1.0), "norm-identity-dmma"),
+        (orc.KernelSpec("ratquad", (d,), 1.0, alpha=1.7), "norm-identity-dmma"),
+        (orc.KernelSpec("expquad", (d,), 0.02), "direct-differences"),   # R^2 ~ 1e5 scaled units
+        (orc.KernelSpec("matern", (d,), 1.0, nu=1.5), "direct-differences"),
+    ]:
+        k = make_kernel(spec)
+        op = _lib.Operator(k._kernel_params(), x)
+        assert op.matmul_path() == "undecided"
+        y = op.matmul(v)
+        assert op.matmul_path() == want_path, spec
+        yt = op.matmul(v, transpose=True)
+        ref = orc.matvec(spec, x, None, v)
+        bound = orc.abs_matvec(spec, x, None, v)
+        assert_matvec_close(y, ref, bound, 1e-12)
+        assert_matvec_close(yt, ref, bound, 1e-12)
+        op.close()
+
+
+def test_dmma_matvec_rectangular_small_d_and_columns():
+    rng = np.random.default_rng(37)
+    for d, k_cols in [(1, 1), (3, 4), (4, 1), (5, 3), (8, 8)]:
+        spec = orc.KernelSpec("expquad", (d,), 0.8 * np.sqrt(d))
+        x0 = rng.normal(size=(700, d))
+        x1 = rng.normal(size=(1301, d))
+        v = rng.uniform(0.0, 1.0, size=(1301, k_cols))
+        L = make_kernel(spec).linop(x0, x1)
+        y = L @ v
+        assert L._device_op().matmul_path() == "norm-identity-dmma"
+        np.testing.assert_allclose(y, orc.matvec(spec, x0, x1, v), rtol=1e-12)  # v >= 0: plain rtol
+        w = rng.normal(size=(700, k_cols))
+        assert_matvec_close(L.T @ w, orc.matvec(spec, x1, x0, w), orc.abs_matvec(spec, x1, x0, w), 1e-12)
+        L.close()
