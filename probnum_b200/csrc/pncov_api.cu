@@ -437,7 +437,10 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     const KernelDesc& k = h->k;
     if (k.dtype != PNCOV_F64 || k.d > 8 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
     if (h->p0.n == 0 || h->p1.n == 0) return 0;
-    if (getenv("PNCOV_DISABLE_MMA")) return 0;
+    {
+        const char* form = getenv("PNCOV_MATVEC_IDENT");  // "off": always direct differences
+        if (form && strcmp(form, "off") == 0) return 0;
+    }
     const int d = k.d;
     double* sums = nullptr;
     PN_CUDA(cudaMalloc(&sums, 16 * sizeof(double) + sizeof(unsigned long long)));
@@ -533,7 +536,9 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         if (prc) return prc;
     }
     if (h->mma_state == 1) {
-        m.use_mma = 1;
+        // norm identity: dot products on DMMA by default (fastest measured), DFMA form opt-in
+        const char* form = getenv("PNCOV_MATVEC_IDENT");
+        m.use_mma = (form && strcmp(form, "dfma") == 0) ? 1 : 2;
         m.a12 = h->a12[transpose ? 1 : 0];
         m.b12 = h->b12[transpose ? 0 : 1];
         m.epi = h->mma_epi;

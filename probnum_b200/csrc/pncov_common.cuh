@@ -32,6 +32,7 @@ struct PnEpiParams {
     // polynomial coefficients of pn_exp2 / pn_log2, carried in the kernel-parameter constant
     // bank so that every use is a c[0x0][..] operand instead of two UMOVs (see profiles/r01)
     double e1, e2, e3;
+    double f1, f2, f3, f4;  // degree-3 variant for the 256-entry replicated table
     double g1, g2, g3, g4, g5;
     // validity window of the fast epilogue in terms of the hi word of S (see PnFlags)
     unsigned s_lo_word, s_hi_word;
@@ -39,6 +40,7 @@ struct PnEpiParams {
 
 inline void pn_fill_math_constants(PnEpiParams& P) {
     P.e1 = PNCOV_EXP2_E1; P.e2 = PNCOV_EXP2_E2; P.e3 = PNCOV_EXP2_E3;
+    P.f1 = PNCOV_EXP2S_F1; P.f2 = PNCOV_EXP2S_F2; P.f3 = PNCOV_EXP2S_F3; P.f4 = PNCOV_EXP2S_F4;
     P.g1 = PNCOV_LOG2_G1; P.g2 = PNCOV_LOG2_G2; P.g3 = PNCOV_LOG2_G3; P.g4 = PNCOV_LOG2_G4;
     P.g5 = PNCOV_LOG2_G5;
 }
@@ -47,6 +49,22 @@ inline void pn_fill_math_constants(PnEpiParams& P) {
 // them into shared memory at start-up
 static __device__ const double pn_exp2_table_g[PN_EXP2_N] = PNCOV_EXP2_TABLE_INIT;
 static __device__ const double pn_log2_table_g[2 * PN_LOG2_N] = PNCOV_LOG2_TABLE_INIT;
+
+// 256-entry table replicated 16 times: entry j of copy c lives at [j * 16 + c], so the 16
+// lanes of a half-warp (the unit a 64-bit shared load is served in) read 16 different
+// 8-byte banks whatever their indices are: lookups are bank-conflict free (2 wavefronts per
+// warp instead of ~6.6 for random indices into a single copy).  Costs one more DFMA (degree-3
+// polynomial); used where shared-memory wavefronts, not the FP64 pipe, are the limiter.
+static __device__ const double pn_exp2s_table_g[256] = PNCOV_EXP2S_TABLE_INIT;
+#define PN_EXP2S_REP 16
+#define PN_EXP2S_DOUBLES (256 * PN_EXP2S_REP)
+
+__device__ __forceinline__ void pn_stage_tables_rep(double* tabE, double* tabL, int tid, int nthreads,
+                                                    bool need_log) {
+    for (int i = tid; i < PN_EXP2S_DOUBLES; i += nthreads) tabE[i] = pn_exp2s_table_g[i >> 4];
+    if (need_log)
+        for (int i = tid; i < 2 * PN_LOG2_N; i += nthreads) tabL[i] = pn_log2_table_g[i];
+}
 
 __device__ __forceinline__ void pn_stage_tables(double* tabE, double* tabL, int tid, int nthreads) {
     for (int i = tid; i < PN_EXP2_N; i += nthreads) tabE[i] = pn_exp2_table_g[i];
@@ -134,6 +152,22 @@ __device__ __forceinline__ double pn_exp2_prod_core(double a, double b, const Pn
     // (n >> BITS) << 20 == n << (20 - BITS) with the low 20 bits cleared
     return pn_make(pn_hi(res) + ((n << (20 - PNCOV_EXP2_BITS)) & 0xfff00000), pn_lo(res));
 }
+// same with the replicated 256-entry table (TAB = 1): one more DFMA, no bank conflicts
+__device__ __forceinline__ double pn_exp2_prod_core_rep(double a, double b, const PnEpiParams& P,
+                                                        const double* __restrict__ tab_lane) {
+    const double magic = 0x1.8p+44;  // ulp = 2^-8
+    double t = pn_fma(a, b, magic);
+    int n = pn_lo(t);
+    double r = pn_fma(a, b, magic - t);
+    double q = pn_fma(P.f4, r, P.f3);
+    q = pn_fma(q, r, P.f2);
+    q = pn_fma(q, r, P.f1);
+    // tab_lane = table + (lane & 15): entry j of this lane's copy is tab_lane[j * 16]
+    double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab_lane) + ((n & 255) << 7));
+    double res = pn_fma(T * r, q, T);
+    return pn_make(pn_hi(res) + ((n << 12) & 0xfff00000), pn_lo(res));
+}
+
 __device__ __forceinline__ double pn_sqrt_core(double s) {
     double y = pn_rsqrt_seed(s);
     double g = s * y;
@@ -166,17 +200,24 @@ __device__ __forceinline__ double pn_log2_core(double b, const PnEpiParams& P,
     return pn_fma(q, r, ef + t.y);
 }
 
-template <int EPI>
+// TAB = 0: tabE is the 2048-entry table; TAB = 1: tabE is this lane's view of the replicated
+// 256-entry table (base + (lane & 15))
+template <int EPI, int TAB = 0>
 struct PnEpilogue {
+    __device__ __forceinline__ static double exp2_prod(double a, double b, const PnEpiParams& P,
+                                                       const double* __restrict__ tabE) {
+        if constexpr (TAB == 0) return pn_exp2_prod_core(a, b, P, tabE);
+        else return pn_exp2_prod_core_rep(a, b, P, tabE);
+    }
     __device__ __forceinline__ static double fast(double S, const PnEpiParams& P,
                                                   const double* __restrict__ tabE,
                                                   const double* __restrict__ tabL, PnFlags& f) {
         f.see(S);
         if constexpr (EPI == PN_EPI_EXPQUAD) {
-            return pn_exp2_prod_core(S, P.c_u, P, tabE);
+            return exp2_prod(S, P.c_u, P, tabE);
         } else if constexpr (EPI >= PN_EPI_MATERN0 && EPI <= PN_EPI_MATERNP) {
             double r0 = pn_sqrt_core(S);
-            double e = pn_exp2_prod_core(r0, P.c_su, P, tabE);
+            double e = exp2_prod(r0, P.c_su, P, tabE);
             if constexpr (EPI == PN_EPI_MATERN0) {
                 return e;
             } else {
@@ -199,7 +240,7 @@ struct PnEpilogue {
                 double y = pn_rcp_core(b);
                 return y * y;
             } else {
-                return pn_exp2_prod_core(pn_log2_core(b, P, tabL), -P.alpha, P, tabE);
+                return exp2_prod(pn_log2_core(b, P, tabL), -P.alpha, P, tabE);
             }
         }
     }

@@ -44,7 +44,7 @@ struct PnMatvecLaunch {
     // parameters in the scaled units.
     const void* a12;
     const void* b12;
-    int use_mma;
+    int use_mma;         // 0: direct differences, 1: norm identity with DFMA, 2: norm identity with DMMA
     int in_f32;
     PnEpiParams epi;
 };

@@ -28,18 +28,22 @@ constexpr int MV_THREADS = 128;
 constexpr int MV_R = 2;     // rows per thread
 constexpr int MV_TJ = 128;  // column points per pipeline stage
 constexpr int MV_HDR_BYTES = 128 + 8 * (PN_EXP2_N + 2 * PN_LOG2_N);
+constexpr int MV_HDR_REP_BYTES = 128 + 8 * (PN_EXP2S_DOUBLES + 2 * PN_LOG2_N);  // replicated exp2 table
 
-template <int EPI, int N>
+template <int EPI, int N, int TAB = 0>
 __device__ __forceinline__ void mv_epi_tile(double (&S)[N], const PnEpiParams& P, const double* tabE,
                                             const double* tabL) {
     PnFlags f;
     f.reset();
     double K[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) K[i] = PnEpilogue<EPI>::fast(S[i], P, tabE, tabL, f);
+    for (int i = 0; i < N; ++i) K[i] = PnEpilogue<EPI, TAB>::fast(S[i], P, tabE, tabL, f);
     if (f.flagged(P)) {  // rare: S == 0 under a sqrt (the diagonal), subnormal results
+        // the robust path reads the 2048-entry table; TAB = 1 kernels leave it in global memory
+        const double* slow_tab = TAB == 0 ? tabE : pn_exp2_table_g;
+        const double* slow_log = TAB == 0 ? tabL : pn_log2_table_g;
 #pragma unroll
-        for (int i = 0; i < N; ++i) K[i] = pn_epilogue(S[i], P, tabE, tabL);
+        for (int i = 0; i < N; ++i) K[i] = pn_epilogue(S[i], P, slow_tab, slow_log);
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) S[i] = K[i];
@@ -61,24 +65,39 @@ __device__ __forceinline__ void mv_epi_dispatch(double (&S)[N], const PnEpiParam
 }
 
 // ---- main kernel: float64, compile-time d in 1..8 -------------------------------------------
-template <int D, bool ARD, int KC, int EPI>
+// IDENT = false: direct differences, S = sum_m ((x0_m - x1_m) s_m)^2 -- 2d (3d with ARD) FP64
+//                instructions per pair, exact like the reference; every kernel family.
+// IDENT = true : norm identity on centred, pre-scaled operands (a12 / b12, 12 doubles per
+//                point): S = (|xt|^2 + |yt|^2) + sum_m xt_m (-2 yt_m) -- 1 + d instructions
+//                per pair.  ExpQuad / RatQuad only, and only when the host-side bound on the
+//                cancellation error holds (pncov_api.cu: mma_prepare).
+// The same identity with the dot products on DMMA is matvec_mma_kernel below, which is the
+// default on B200 (732 vs 621 Gpair/s at N = 2^20, d = 8; profiles/README.md); this DFMA form
+// is selected with PNCOV_MATVEC_IDENT=dfma.
+constexpr int MV_LD12 = 12;
+
+template <int D, bool ARD, int KC, int EPI, bool IDENT>
 __global__ void __launch_bounds__(MV_THREADS)
     matvec_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split) {
+    constexpr int XLD = IDENT ? MV_LD12 : D;  // doubles per column point in the streamed tile
+    constexpr int TAB = 0;  // replicated conflict-free table (TAB = 1) measured slower: tools/mv_variants.cu
+    constexpr int HDR = TAB ? MV_HDR_REP_BYTES : MV_HDR_BYTES;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     double* tabE = reinterpret_cast<double*>(smem + 128);
-    double* tabL = tabE + PN_EXP2_N;
-    constexpr int STAGE_DOUBLES = MV_TJ * (D + KC);
-    double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
+    double* tabL = tabE + (TAB ? PN_EXP2S_DOUBLES : PN_EXP2_N);
+    const double* tab_epi = TAB ? tabE + (tid & 15) : tabE;
+    constexpr int STAGE_DOUBLES = MV_TJ * (XLD + KC);
+    double* stage0 = reinterpret_cast<double*>(smem + HDR);
 
     const int64_t n_jt = a.n1pad / MV_TJ;
     const int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
     const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
 
-    const double* x1g = static_cast<const double*>(a.x1_aos);
+    const double* x1g = static_cast<const double*>(IDENT ? a.b12 : a.x1_aos);
     const double* vg = static_cast<const double*>(a.v);
-    constexpr uint32_t X_BYTES = MV_TJ * D * 8, V_BYTES = MV_TJ * KC * 8;
+    constexpr uint32_t X_BYTES = MV_TJ * XLD * 8, V_BYTES = MV_TJ * KC * 8;
 
     if (tid == 0) {
         pn_mbar_init(&bars[0], 1);
@@ -88,20 +107,24 @@ __global__ void __launch_bounds__(MV_THREADS)
     __syncthreads();
     if (tid == 0 && jt0 < jt1) {
         pn_mbar_expect_tx(&bars[0], X_BYTES + V_BYTES);
-        pn_bulk_g2s(stage0, x1g + jt0 * MV_TJ * D, X_BYTES, &bars[0]);
-        pn_bulk_g2s(stage0 + MV_TJ * D, vg + jt0 * MV_TJ * KC, V_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0, x1g + jt0 * MV_TJ * XLD, X_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + MV_TJ * XLD, vg + jt0 * MV_TJ * KC, V_BYTES, &bars[0]);
     }
-    pn_stage_tables(tabE, tabL, tid, MV_THREADS);
+    if constexpr (TAB) pn_stage_tables_rep(tabE, tabL, tid, MV_THREADS, EPI == PN_EPI_RATQUADG);
+    else pn_stage_tables(tabE, tabL, tid, MV_THREADS);
 
     // this thread's rows (the row point set is zero padded to a multiple of PN_PAD rows)
     const int64_t row0 = (int64_t)blockIdx.x * (MV_THREADS * MV_R) + tid;
     double xr[MV_R][D];
+    double nxr[MV_R];
     {
-        const double* x0g = static_cast<const double*>(a.x0_aos);
+        const double* x0g = static_cast<const double*>(IDENT ? a.a12 : a.x0_aos);
 #pragma unroll
-        for (int r = 0; r < MV_R; ++r)
+        for (int r = 0; r < MV_R; ++r) {
 #pragma unroll
-            for (int m = 0; m < D; ++m) xr[r][m] = x0g[(row0 + (int64_t)r * MV_THREADS) * D + m];
+            for (int m = 0; m < D; ++m) xr[r][m] = x0g[(row0 + (int64_t)r * MV_THREADS) * XLD + m];
+            nxr[r] = IDENT ? x0g[(row0 + (int64_t)r * MV_THREADS) * XLD + 8] : 0.0;
+        }
     }
     double sc[D];
     if constexpr (ARD) {
@@ -121,45 +144,55 @@ __global__ void __launch_bounds__(MV_THREADS)
         if (tid == 0 && jt + 1 < jt1) {
             double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
             pn_mbar_expect_tx(&bars[buf ^ 1], X_BYTES + V_BYTES);
-            pn_bulk_g2s(dst, x1g + (jt + 1) * MV_TJ * D, X_BYTES, &bars[buf ^ 1]);
-            pn_bulk_g2s(dst + MV_TJ * D, vg + (jt + 1) * MV_TJ * KC, V_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst, x1g + (jt + 1) * MV_TJ * XLD, X_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + MV_TJ * XLD, vg + (jt + 1) * MV_TJ * KC, V_BYTES, &bars[buf ^ 1]);
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
         const double* xt = stage0 + (size_t)buf * STAGE_DOUBLES;
-        const double* vt = xt + MV_TJ * D;
+        const double* vt = xt + MV_TJ * XLD;
 
 #pragma unroll 1
         for (int jj = 0; jj < MV_TJ; jj += 2) {
             double xb[2][D];
+            double nyb[2];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                if constexpr (D % 2 == 0) {
+                if constexpr (XLD % 2 == 0) {  // rows of the tile are 16-byte aligned
 #pragma unroll
-                    for (int m = 0; m < D; m += 2) {
-                        const double2 t = *reinterpret_cast<const double2*>(xt + (jj + c) * D + m);
+                    for (int m = 0; m + 1 < D; m += 2) {
+                        const double2 t = *reinterpret_cast<const double2*>(xt + (jj + c) * XLD + m);
                         xb[c][m] = t.x;
                         xb[c][m + 1] = t.y;
                     }
+                    if constexpr (D % 2 == 1) xb[c][D - 1] = xt[(jj + c) * XLD + D - 1];
                 } else {
 #pragma unroll
-                    for (int m = 0; m < D; ++m) xb[c][m] = xt[(jj + c) * D + m];
+                    for (int m = 0; m < D; ++m) xb[c][m] = xt[(jj + c) * XLD + m];
                 }
+                nyb[c] = IDENT ? xt[(jj + c) * XLD + 8] : 0.0;
             }
             double S[2 * MV_R];
 #pragma unroll
             for (int r = 0; r < MV_R; ++r)
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    double s = 0.0;
+                    double s;
+                    if constexpr (IDENT) {
+                        s = nxr[r] + nyb[c];
 #pragma unroll
-                    for (int m = 0; m < D; ++m) {
-                        double df = xr[r][m] - xb[c][m];
-                        if constexpr (ARD) df *= sc[m];
-                        s = pn_fma(df, df, s);
+                        for (int m = 0; m < D; ++m) s = pn_fma(xr[r][m], xb[c][m], s);
+                    } else {
+                        s = 0.0;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) {
+                            double df = xr[r][m] - xb[c][m];
+                            if constexpr (ARD) df *= sc[m];
+                            s = pn_fma(df, df, s);
+                        }
                     }
                     S[2 * r + c] = s;
                 }
-            mv_epi_tile<EPI>(S, a.epi, tabE, tabL);
+            mv_epi_tile<EPI, 2 * MV_R, TAB>(S, a.epi, tab_epi, tabL);
 #pragma unroll
             for (int c = 0; c < 2; ++c)
 #pragma unroll
@@ -205,7 +238,7 @@ constexpr int MM_TJ = 128;                        // columns per pipeline stage
 constexpr int MM_LD = 12;                         // doubles per point in a12 / b12
 
 __device__ __forceinline__ void pn_dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
@@ -272,7 +305,7 @@ __global__ void __launch_bounds__(MM_THREADS)
         const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
         const double* vt = bt + MM_TJ * MM_LD;
 
-#pragma unroll 1
+#pragma unroll 2
         for (int jj = 0; jj < MM_TJ; jj += 8) {
             double bf[KSTEPS];
 #pragma unroll
@@ -443,12 +476,16 @@ static int choose_jsplit(int64_t row_ctas, int64_t n_jt, int slots) {
     return best;
 }
 
-template <int D, bool ARD, int KC, int EPI>
+template <int D, bool ARD, int KC, int EPI, bool IDENT = false>
 cudaError_t launch_main(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStream_t stream) {
-    auto kern = matvec_kernel<D, ARD, KC, EPI>;
-    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MV_TJ * (D + KC);
+    auto kern = matvec_kernel<D, ARD, KC, EPI, IDENT>;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MV_TJ * ((IDENT ? MV_LD12 : D) + KC);
     const int64_t n_jt = a.n1pad / MV_TJ;
     const int64_t row_ctas = (a.n0 + MV_THREADS * MV_R - 1) / (MV_THREADS * MV_R);
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
     if (plan_only) {
         int occ = 1;
         cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MV_THREADS, smem);
@@ -490,6 +527,39 @@ cudaError_t launch_main_kc(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t st
     }
 }
 
+// norm-identity (DFMA) instantiations: ExpQuad / RatQuad, scale folded into the operands
+template <int D, int KC>
+cudaError_t launch_ident_epi(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_main<D, false, KC, PN_EPI_EXPQUAD, true>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD1: return launch_main<D, false, KC, PN_EPI_RATQUAD1, true>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD2: return launch_main<D, false, KC, PN_EPI_RATQUAD2, true>(a, sm, plan, stream);
+        case PN_EPI_RATQUADG: return launch_main<D, false, KC, PN_EPI_RATQUADG, true>(a, sm, plan, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int D>
+cudaError_t launch_ident_kc(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    if (a.kc == 1) return launch_ident_epi<D, 1>(a, sm, plan, stream);
+    if (a.kc == 4) return launch_ident_epi<D, 4>(a, sm, plan, stream);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_ident_d(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    switch (a.d) {
+        case 1: return launch_ident_kc<1>(a, sm, plan, stream);
+        case 2: return launch_ident_kc<2>(a, sm, plan, stream);
+        case 3: return launch_ident_kc<3>(a, sm, plan, stream);
+        case 4: return launch_ident_kc<4>(a, sm, plan, stream);
+        case 5: return launch_ident_kc<5>(a, sm, plan, stream);
+        case 6: return launch_ident_kc<6>(a, sm, plan, stream);
+        case 7: return launch_ident_kc<7>(a, sm, plan, stream);
+        case 8: return launch_ident_kc<8>(a, sm, plan, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <bool ARD>
 cudaError_t launch_main_d(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     switch (a.d) {
@@ -511,6 +581,10 @@ cudaError_t launch_mma(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStre
     const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MM_TJ * (MM_LD + KC);
     const int64_t n_jt = a.n1pad / MM_TJ;
     const int64_t row_ctas = (a.n0 + MM_ROWS - 1) / MM_ROWS;
+    if (smem > 48 * 1024) {
+        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+    }
     if (plan_only) {
         int occ = 1;
         cudaError_t err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MM_THREADS, smem);
@@ -581,7 +655,8 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
         a.jsplit = 1;
         return cudaSuccess;
     }
-    if (a.use_mma) return launch_mma_any(a, sm_count, true, nullptr);
+    if (a.use_mma == 2) return launch_mma_any(a, sm_count, true, nullptr);
+    if (a.use_mma == 1) return launch_ident_d(a, sm_count, true, nullptr);
     if (uses_main_kernel(a)) {
         const bool ard = a.scale != nullptr;
         return ard ? launch_main_d<true>(a, sm_count, true, nullptr) : launch_main_d<false>(a, sm_count, true, nullptr);
@@ -600,8 +675,10 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     const int64_t ld1 = a.ld1;
     const bool ard = a.scale != nullptr;
     cudaError_t err;
-    if (a.use_mma) {
+    if (a.use_mma == 2) {
         err = launch_mma_any(a, sm_count, false, stream);
+    } else if (a.use_mma == 1) {
+        err = launch_ident_d(a, sm_count, false, stream);
     } else if (uses_main_kernel(a)) {
         err = ard ? launch_main_d<true>(a, sm_count, false, stream) : launch_main_d<false>(a, sm_count, false, stream);
     } else if (!a.in_f32) {

@@ -1,0 +1,217 @@
+// Design-space probe for the matrix-free ExpQuad product (d = 8, one right-hand side):
+// times variants of the norm-identity kernel (threads per CTA, rows per thread, tile size,
+// exp2 table style, split dot product) and the direct-difference baseline on synthetic data.
+// Results steer probnum_b200/csrc/pncov_matvec.cu; see profiles/README.md.
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Iprobnum_b200/csrc \
+//        -o tools/build/mv_variants tools/mv_variants.cu
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+#include <vector>
+
+#include "pncov_common.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
+
+constexpr int D = 8;
+constexpr int LD = 12;
+
+template <int TAB>
+__device__ __forceinline__ double epi(double S, const PnEpiParams& P, const double* tab, PnFlags& f) {
+    return PnEpilogue<PN_EPI_EXPQUAD, TAB>::fast(S, P, tab, nullptr, f);
+}
+
+// MODE 0: direct differences on raw points (ld = 8); MODE 1: identity, serial dot;
+// MODE 2: identity, dot split into two partial sums
+template <int THREADS, int R, int TJ, int TAB, int MODE, int C>
+__global__ void __launch_bounds__(THREADS)
+mv_kernel(const double* __restrict__ rows, const double* __restrict__ cols, const double* __restrict__ v,
+          double* __restrict__ y, int n0, int n1, const __grid_constant__ PnEpiParams P) {
+    constexpr int XLD = MODE == 0 ? D : LD;
+    constexpr int TABD = TAB ? PN_EXP2S_DOUBLES : PN_EXP2_N;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* stage0 = tabE + TABD;
+    constexpr int STAGE = TJ * (XLD + 1);
+    const int tid = threadIdx.x;
+    const double* tab_epi = TAB ? tabE + (tid & 15) : tabE;
+    constexpr uint32_t XB = TJ * XLD * 8, VB = TJ * 8;
+    const int n_jt = n1 / TJ;
+    if (tid == 0) { pn_mbar_init(&bars[0], 1); pn_mbar_init(&bars[1], 1); pn_mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], XB + VB);
+        pn_bulk_g2s(stage0, cols, XB, &bars[0]);
+        pn_bulk_g2s(stage0 + TJ * XLD, v, VB, &bars[0]);
+    }
+    if (TAB) { for (int i = tid; i < PN_EXP2S_DOUBLES; i += THREADS) tabE[i] = pn_exp2s_table_g[i >> 4]; }
+    else { for (int i = tid; i < PN_EXP2_N; i += THREADS) tabE[i] = pn_exp2_table_g[i]; }
+    const int64_t row0 = (int64_t)blockIdx.x * (THREADS * R) + tid;
+    double xr[R][D], nxr[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int m = 0; m < D; ++m) xr[r][m] = rows[(row0 + (int64_t)r * THREADS) * XLD + m];
+        nxr[r] = MODE ? rows[(row0 + (int64_t)r * THREADS) * XLD + 8] : 0.0;
+        acc[r] = 0.0;
+    }
+    __syncthreads();
+    for (int jt = 0; jt < n_jt; ++jt) {
+        const int buf = jt & 1;
+        if (tid == 0 && jt + 1 < n_jt) {
+            double* dst = stage0 + (buf ^ 1) * STAGE;
+            pn_mbar_expect_tx(&bars[buf ^ 1], XB + VB);
+            pn_bulk_g2s(dst, cols + (size_t)(jt + 1) * TJ * XLD, XB, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + TJ * XLD, v + (size_t)(jt + 1) * TJ, VB, &bars[buf ^ 1]);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((jt >> 1) & 1));
+        const double* xt = stage0 + buf * STAGE;
+        const double* vt = xt + TJ * XLD;
+#pragma unroll 1
+        for (int jj = 0; jj < TJ; jj += C) {
+            double xb[C][D], nyb[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int m = 0; m < D; m += 2) {
+                    const double2 t = *reinterpret_cast<const double2*>(xt + (jj + c) * XLD + m);
+                    xb[c][m] = t.x; xb[c][m + 1] = t.y;
+                }
+                nyb[c] = MODE ? xt[(jj + c) * XLD + 8] : 0.0;
+            }
+            double S[R * C];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    double s;
+                    if constexpr (MODE == 0) {
+                        s = 0.0;
+#pragma unroll
+                        for (int m = 0; m < D; ++m) { double df = xr[r][m] - xb[c][m]; s = pn_fma(df, df, s); }
+                    } else if constexpr (MODE == 1) {
+                        s = nxr[r] + nyb[c];
+#pragma unroll
+                        for (int m = 0; m < D; ++m) s = pn_fma(xr[r][m], xb[c][m], s);
+                    } else {
+                        double s0 = nxr[r], s1 = nyb[c];
+#pragma unroll
+                        for (int m = 0; m < D; m += 2) { s0 = pn_fma(xr[r][m], xb[c][m], s0); s1 = pn_fma(xr[r][m + 1], xb[c][m + 1], s1); }
+                        s = s0 + s1;
+                    }
+                    S[r * C + c] = s;
+                }
+            PnFlags f; f.reset();
+            double K[R * C];
+#pragma unroll
+            for (int i = 0; i < R * C; ++i) K[i] = epi<TAB>(S[i], P, tab_epi, f);
+            if (f.flagged(P)) {
+#pragma unroll
+                for (int i = 0; i < R * C; ++i) K[i] = pn_epilogue(S[i], P, pn_exp2_table_g, pn_log2_table_g);
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const double vk = vt[jj + c];
+#pragma unroll
+                for (int r = 0; r < R; ++r) acc[r] = pn_fma(K[r * C + c], vk, acc[r]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int64_t row = row0 + (int64_t)r * THREADS;
+        if (row < n0) y[row] = acc[r];
+    }
+}
+
+static PnEpiParams make_params(bool identity) {
+    PnEpiParams P{};
+    pn_fill_math_constants(P);
+    P.epi = PN_EPI_EXPQUAD;
+    const double log2e = 1.4426950408889634;
+    P.c_u = identity ? -log2e : -log2e * 0.5;
+    P.c_s = 1.0; P.c_su = P.c_u;
+    double smax = 1021.0 / fabs(P.c_u);
+    unsigned long long b; memcpy(&b, &smax, 8);
+    P.s_hi_word = (unsigned)(b >> 32); P.s_lo_word = 0;
+    return P;
+}
+
+template <int THREADS, int R, int TJ, int TAB, int MODE, int C>
+void run(const char* name, const double* raw, const double* a12, const double* b12, const double* v, double* y,
+         int n, double* ref_out) {
+    auto kern = mv_kernel<THREADS, R, TJ, TAB, MODE, C>;
+    constexpr int XLD = MODE == 0 ? D : LD;
+    const size_t smem = 128 + 8 * (TAB ? PN_EXP2S_DOUBLES : PN_EXP2_N) + 2 * 8 * TJ * (XLD + 1);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    PnEpiParams P = make_params(MODE != 0);
+    const double* rows = MODE == 0 ? raw : a12;
+    const double* cols = MODE == 0 ? raw : b12;
+    dim3 grid(n / (THREADS * R));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    kern<<<grid, THREADS, smem>>>(rows, cols, v, y, n, n, P);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, THREADS, smem>>>(rows, cols, v, y, n, n, P);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+    }
+    std::vector<double> h(64);
+    CK(cudaMemcpy(h.data(), y, 64 * 8, cudaMemcpyDeviceToHost));
+    double maxrel = 0;
+    if (ref_out[0] == 0.0 && MODE == 0) for (int i = 0; i < 64; ++i) ref_out[i] = h[i];
+    for (int i = 0; i < 64; ++i) maxrel = fmax(maxrel, fabs(h[i] - ref_out[i]) / fabs(ref_out[i]));
+    printf("%-44s thr=%3d R=%d TJ=%3d TAB=%d C=%d occ=%d warps/SM=%2d  %8.3f ms  %7.1f Gpair/s  maxrel=%.1e\n", name, THREADS, R,
+           TJ, TAB, C, occ, occ * THREADS / 32, best, (double)n * n / best / 1e6, maxrel);
+}
+
+int main(int argc, char** argv) {
+    const int n = argc > 1 ? atoi(argv[1]) : 131072;
+    std::vector<double> raw((size_t)n * D), a12((size_t)n * LD, 0.0), b12((size_t)n * LD, 0.0), v(n);
+    srand(1);
+    auto rnd = []() { double u = 0; for (int i = 0; i < 12; ++i) u += rand() / (double)RAND_MAX; return u - 6.0; };
+    const double s = sqrt(0.5);
+    for (int i = 0; i < n; ++i) {
+        double nrm = 0;
+        for (int m = 0; m < D; ++m) {
+            double x = rnd(); raw[(size_t)i * D + m] = x;
+            a12[(size_t)i * LD + m] = x * s; b12[(size_t)i * LD + m] = -2.0 * x * s; nrm += x * s * x * s;
+        }
+        a12[(size_t)i * LD + 8] = nrm; b12[(size_t)i * LD + 8] = nrm;
+        v[i] = rnd();
+    }
+    double *draw, *da, *db, *dv, *dy;
+    CK(cudaMalloc(&draw, raw.size() * 8)); CK(cudaMalloc(&da, a12.size() * 8)); CK(cudaMalloc(&db, b12.size() * 8));
+    CK(cudaMalloc(&dv, n * 8)); CK(cudaMalloc(&dy, n * 8));
+    CK(cudaMemcpy(draw, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(da, a12.data(), a12.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db, b12.data(), b12.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv, v.data(), n * 8, cudaMemcpyHostToDevice));
+    double ref[64] = {0};
+    run<128, 2, 128, 0, 0, 2>("direct (shipping kernel shape)", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 128, 0, 0, 2>("direct 256 threads", draw, da, db, dv, dy, n, ref);
+    run<128, 2, 128, 0, 1, 2>("identity serial dot", draw, da, db, dv, dy, n, ref);
+    run<128, 2, 64, 0, 1, 2>("identity serial dot TJ=64", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 128, 0, 1, 2>("identity serial dot 256 thr", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 64, 0, 1, 2>("identity serial dot 256 thr TJ=64", draw, da, db, dv, dy, n, ref);
+    run<128, 2, 64, 0, 2, 2>("identity split dot TJ=64", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 64, 0, 2, 2>("identity split dot 256 thr TJ=64", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 64, 1, 1, 2>("identity serial, replicated table 256 thr", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 64, 1, 2, 2>("identity split, replicated table 256 thr", draw, da, db, dv, dy, n, ref);
+    run<128, 4, 64, 0, 1, 2>("identity R=4", draw, da, db, dv, dy, n, ref);
+    run<256, 4, 64, 0, 1, 1>("identity R=4 C=1 256 thr", draw, da, db, dv, dy, n, ref);
+    run<256, 4, 64, 1, 1, 1>("identity R=4 C=1 256 thr replicated", draw, da, db, dv, dy, n, ref);
+    run<128, 2, 64, 0, 1, 4>("identity R=2 C=4", draw, da, db, dv, dy, n, ref);
+    run<256, 2, 64, 1, 1, 4>("identity R=2 C=4 256 thr replicated", draw, da, db, dv, dy, n, ref);
+    run<256, 1, 64, 0, 1, 4>("identity R=1 C=4 256 thr", draw, da, db, dv, dy, n, ref);
+    run<512, 1, 64, 1, 1, 4>("identity R=1 C=4 512 thr replicated", draw, da, db, dv, dy, n, ref);
+    run<512, 2, 64, 1, 1, 2>("identity R=2 C=2 512 thr replicated", draw, da, db, dv, dy, n, ref);
+    return 0;
+}
