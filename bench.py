@@ -291,7 +291,7 @@ def run_ours(args):
         with open(tpath) as fh:
             traffic = json.load(fh).get("gram_fast_kernel_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": f"gram_fast_kernel<D=3> ({dom} epilogue)",
+        "bound": "hbm", "kernel": f"gram_fast_kernel<D=3, {dom}" + (", SYM (mirror stores)>" if world == 1 and dom == "matern52" else ">"),
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, copy read+write)",
         "algorithmic_bytes_per_launch": alg_bytes,
@@ -370,6 +370,7 @@ def run_ours(args):
         ms = max_over_ranks(e0.elapsed_time(e1) / reps)
         flop_per_pair = 3 * D_MV + 1 + 2  # 3d + 1 + 2K, FMA = 2
         extra["matvec"] = {
+            "kernel": sop.local.matmul_path(),
             "workload": f"ExpQuad K.v, N={nm}, d={D_MV}, K=1, float64, row-sharded over {world} GPU(s) + all-gather",
             "ms": ms, "pairs_per_s": float(nm) * nm / (ms * 1e-3),
             "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,
