@@ -6,9 +6,9 @@
 
 One "step" is one pass of the hot path over BASELINE.json configs[1]: the dense float64
 Gram matrices of Matern-5/2 AND RatQuad over N = 32768 points in d = 3 (2 * N^2 entries,
-17.2 GB written).  With G > 1 GPUs (launched by torchrun, one rank per GPU) each rank builds
-its own 32768-row block of a (32768*G) x 32768 cross Gram -- weak scaling, no collective on
-the data path.  The JSON line also carries, under "extra", the single-kernel numbers (ExpQuad,
+17.2 GB written).  With G > 1 GPUs (launched by torchrun, one rank per GPU) the units are
+independent point clouds: each rank builds the two Gram matrices of its own 32768-point cloud
+(seeded per rank) -- weak scaling, identical per-GPU work, no collective on the data path.  The JSON line also carries, under "extra", the single-kernel numbers (ExpQuad,
 Matern-5/2, RatQuad) and the matrix-free K.v of configs[2] (N = 2^20, d = 8), which IS
 row-sharded with an NCCL all-gather of the result vector.
 
@@ -229,19 +229,16 @@ def run_ours(args):
 
     n, d = args.n, D_GRAM
     # synthetic inputs as in benchmarks/covfuncs.py:56 (default_rng(42), standard normal)
-    x1_host = np.random.default_rng(42).normal(size=(n, d))
-    x0_host = x1_host if world == 1 else np.random.default_rng(1000 + rank).normal(size=(n, d))
+    x0_host = np.random.default_rng(42 + 1000 * rank).normal(size=(n, d))
     kernels = {
         "matern52": pb.Matern((d,), nu=2.5),
         "ratquad": pb.RatQuad((d,)),
         "expquad": pb.ExpQuad((d,)),
     }
     x0_dev = torch.from_numpy(x0_host).to(dev)
-    x1_dev = torch.from_numpy(x1_host).to(dev)
     ops = {}
     for name, k in kernels.items():
-        ops[name] = _lib.Operator(k._kernel_params(), x0_dev.data_ptr(),
-                                  None if world == 1 else x1_dev.data_ptr(),
+        ops[name] = _lib.Operator(k._kernel_params(), x0_dev.data_ptr(), None,
                                   device=local_rank, on_device=True, n0=n, n1=n, dtype=np.float64)
     out = torch.empty((n, n), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -291,7 +288,7 @@ def run_ours(args):
         with open(tpath) as fh:
             traffic = json.load(fh).get("gram_fast_kernel_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": f"gram_fast_kernel<D=3, {dom}" + (", SYM (mirror stores)>" if world == 1 and dom == "matern52" else ">"),
+        "bound": "hbm", "kernel": f"gram_fast_kernel<D=3, {dom}" + (", SYM (mirror stores)>" if dom == "matern52" else ">"),
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, copy read+write)",
         "algorithmic_bytes_per_launch": alg_bytes,
@@ -321,20 +318,20 @@ def run_ours(args):
     if not args.no_e2e:
         ks = [kernels[name] for name in step_kernels]
         for k in ks:  # warm-up: pins the result buffers once
-            k.matrix(x0_host, None if world == 1 else x1_host)
+            k.matrix(x0_host)
         barrier()
         e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             for k in ks:
-                K = k.matrix(x0_host, None if world == 1 else x1_host)
+                K = k.matrix(x0_host)
                 del K
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {
             "value": entries_per_step * e2e_steps / dt, "unit": UNIT,
-            "h2d_bytes_per_step": 2 * 8 * d * (n if world == 1 else 2 * n),
-            "d2h_bytes_per_step": int(2 * 8 * n * n),
+            "h2d_bytes_per_step": 2 * 8 * d * n * world,
+            "d2h_bytes_per_step": int(2 * 8 * n * n) * world,
             "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
             "api": "probnum_b200.covfuncs.{Matern,RatQuad}.matrix(X) -> numpy.ndarray (pinned result pool)",
         }
@@ -389,8 +386,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={d}, float64 (BASELINE configs[1])"
-                            + ("" if world == 1 else f"; each of {world} ranks builds its own {n}-row block of a "
-                               f"({n * world} x {n}) cross Gram"),
+                            + ("" if world == 1 else f"; {world} independent point clouds, one per rank/GPU"),
                 "l2": "each launch writes 8.6 GB >> 126 MB L2; no flush needed",
                 "inputs": "default_rng(42).normal, resident in HBM",
             },
