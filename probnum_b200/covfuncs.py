@@ -251,6 +251,7 @@ class CovarianceLinearOperator(linops.LinearOperator):
         self._x1 = x1
         self._parent = _transposed_of
         self._op: Optional[_lib.Operator] = None
+        self._last_product = None  # (operand, result) of the most recent narrow product
         n0 = x0.shape[0]
         n1 = n0 if x1 is None else x1.shape[0]
         shape = (n0, n1) if _transposed_of is None else (n1, n0)
@@ -274,6 +275,21 @@ class CovarianceLinearOperator(linops.LinearOperator):
         return self._parent is not None
 
     def _matmul(self, x: np.ndarray) -> np.ndarray:
+        # The matrix-based solver applies A to the same vector twice per iteration
+        # (linalg/solvers/matrixbased.py:872 and :885).  The product is deterministic, so
+        # serving the repeat from the last (operand, result) pair is bit-identical and halves
+        # the device work of problinsolve.
+        narrow = x.ndim == 2 and x.shape[-1] <= 8
+        if narrow and self._last_product is not None:
+            last_x, last_y = self._last_product
+            if last_x.shape == x.shape and last_x.dtype == x.dtype and np.array_equal(last_x, x):
+                return last_y.copy()
+        y = self._matmul_device(x)
+        if narrow:
+            self._last_product = (np.array(x, copy=True), y.copy())
+        return y
+
+    def _matmul_device(self, x: np.ndarray) -> np.ndarray:
         M, N = self.shape
         op = self._device_op()
         lead = x.shape[:-2]

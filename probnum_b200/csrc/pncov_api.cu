@@ -39,6 +39,33 @@ int fail_cuda(cudaError_t e, const char* what) {
 
 constexpr double kLog2e = 1.4426950408889634074;
 
+// Device scratch comes from CUDA's stream-ordered pool so that creating / destroying an
+// operator does not pay cudaMalloc / cudaFree (hundreds of microseconds each, plus a device
+// synchronisation) every time: small Gram calls are otherwise dominated by that overhead.
+// The pool keeps up to 4 GiB cached per device.  Allocation is synchronous from the caller's
+// point of view (the buffer may be used on any stream afterwards); frees are issued after the
+// owning handle has drained its work.
+cudaError_t pn_dev_alloc(void** p, size_t bytes, cudaStream_t s) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = 4ull << 30;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        configured[dev] = true;
+    }
+    e = cudaMallocAsync(p, bytes ? bytes : 1, s);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(s);
+}
+void pn_dev_free(void* p, cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+}
+
 // ---- utility kernels ------------------------------------------------------------------------
 // (n, d) row-major -> (d, ld) coordinate-major; pad columns [n, ld) are left as zero-filled
 template <typename T>
@@ -324,6 +351,7 @@ struct pncov_handle {
     void* stage = nullptr;  // device staging for host entry points
     size_t stage_bytes = 0;
     // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
+    bool used_foreign_stream = false;  // a *_device entry point ran on a caller-owned stream
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
     void* a12[2] = {nullptr, nullptr};  // per point set (0: x0, 1: x1); aliases when symmetric
     void* b12[2] = {nullptr, nullptr};
@@ -343,12 +371,16 @@ struct DeviceGuard {
     }
 };
 
-int ensure(void** buf, size_t* have, size_t need) {
+int ensure(void** buf, size_t* have, size_t need, cudaStream_t s) {
     if (*have >= need) return 0;
-    if (*buf) cudaFree(*buf);
+    if (*buf) {
+        // earlier launches that used the old buffer ran on the caller's stream, not on `s`
+        PN_CUDA(cudaDeviceSynchronize());
+        pn_dev_free(*buf, s);
+    }
     *buf = nullptr;
     *have = 0;
-    PN_CUDA(cudaMalloc(buf, need));
+    PN_CUDA(pn_dev_alloc(buf, need, s));
     *have = need;
     return 0;
 }
@@ -359,8 +391,8 @@ int upload_points(pncov_handle* h, Points& P, const void* x, int64_t n, bool on_
     P.n = n;
     P.npad = pad_up(n > 0 ? n : 1);
     const size_t bytes = (size_t)P.npad * d * es;
-    PN_CUDA(cudaMalloc(&P.aos, bytes));
-    PN_CUDA(cudaMalloc(&P.soa, bytes));
+    PN_CUDA(pn_dev_alloc(&P.aos, bytes, h->stream));
+    PN_CUDA(pn_dev_alloc(&P.soa, bytes, h->stream));
     PN_CUDA(cudaMemsetAsync(P.aos, 0, bytes, h->stream));
     PN_CUDA(cudaMemsetAsync(P.soa, 0, bytes, h->stream));
     if (n > 0) {
@@ -377,16 +409,16 @@ int upload_points(pncov_handle* h, Points& P, const void* x, int64_t n, bool on_
     return 0;
 }
 
-void free_points(Points& P) {
-    if (P.aos) cudaFree(P.aos);
-    if (P.soa) cudaFree(P.soa);
+void free_points(Points& P, cudaStream_t s) {
+    pn_dev_free(P.aos, s);
+    pn_dev_free(P.soa, s);
     P = Points{};
 }
 
 int upload_scale(const KernelDesc& k, void** dev, cudaStream_t stream) {
     *dev = nullptr;
     if (!k.ard) return 0;
-    PN_CUDA(cudaMalloc(dev, k.scale.size() * k.elem()));
+    PN_CUDA(pn_dev_alloc(dev, k.scale.size() * k.elem(), stream));
     if (k.dtype == PNCOV_F64) {
         PN_CUDA(cudaMemcpyAsync(*dev, k.scale.data(), k.scale.size() * 8, cudaMemcpyHostToDevice, stream));
         PN_CUDA(cudaStreamSynchronize(stream));
@@ -443,10 +475,10 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     }
     const int d = k.d;
     double* sums = nullptr;
-    PN_CUDA(cudaMalloc(&sums, 16 * sizeof(double) + sizeof(unsigned long long)));
+    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&sums), 16 * sizeof(double) + sizeof(unsigned long long), stream));
     unsigned long long* max_norm = reinterpret_cast<unsigned long long*>(sums + 16);
     auto fail_free = [&](int rc) {
-        cudaFree(sums);
+        pn_dev_free(sums, stream);
         return rc;
     };
     coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p0.aos, h->p0.n, d, sums);
@@ -473,8 +505,8 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     for (int sidx = 0; sidx < nsets; ++sidx) {
         const Points& P = sidx == 0 ? h->p0 : h->p1;
         const size_t bytes = (size_t)P.npad * 12 * sizeof(double);
-        e = cudaMalloc(&h->a12[sidx], bytes);
-        if (e == cudaSuccess) e = cudaMalloc(&h->b12[sidx], bytes);
+        e = pn_dev_alloc(&h->a12[sidx], bytes, stream);
+        if (e == cudaSuccess) e = pn_dev_alloc(&h->b12[sidx], bytes, stream);
         if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
         build_mma_operands_kernel<<<(unsigned)((P.npad + 255) / 256), 256, 0, stream>>>(
             (const double*)P.aos, P.n, P.npad, d, sums, scale_dev, iso, (double*)h->a12[sidx],
@@ -488,7 +520,7 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     unsigned long long bits = 0;
     e = cudaMemcpyAsync(&bits, max_norm, sizeof(bits), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-    cudaFree(sums);
+    pn_dev_free(sums, stream);
     if (e != cudaSuccess) return fail_cuda(e, "mma_prepare");
     double r2;
     memcpy(&r2, &bits, 8);
@@ -546,9 +578,9 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     PN_CUDA(pn_plan_matvec(m, h->sm_count));
     const int jsplit = m.jsplit;
     int rc;
-    if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * kc_max * es))) return rc;
-    if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)R.n * kc_max * es))) return rc;
-    if (jsplit > 1 && (rc = ensure(&h->partial, &h->partial_bytes, (size_t)jsplit * R.n * kc_max * 8))) return rc;
+    if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * kc_max * es, h->stream))) return rc;
+    if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)R.n * kc_max * es, h->stream))) return rc;
+    if (jsplit > 1 && (rc = ensure(&h->partial, &h->partial_bytes, (size_t)jsplit * R.n * kc_max * 8, h->stream))) return rc;
 
     for (int64_t c0 = 0; c0 < k; c0 += kc_max) {
         const int kc = kc_max;
@@ -640,9 +672,10 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
         return code;
     };
     if (!guard.ok) return bail(fail(PNCOV_ENODEVICE, "cudaSetDevice failed"));
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
-    if (prop.major < 10) return bail(fail(PNCOV_ENODEVICE, "libpncov is built for sm_100a (B200) only"));
+    int cc_major = 0, sms = 0;
+    cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
+    if (cc_major < 10) return bail(fail(PNCOV_ENODEVICE, "libpncov is built for sm_100a (B200) only"));
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
     if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));
@@ -664,21 +697,26 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
 PNCOV_API int pncov_destroy(pncov_handle* h) {
     if (!h) return 0;
     DeviceGuard guard(h->device);
+    // device-pointer entry points may have queued work on caller-owned streams: drain the
+    // device (what cudaFree used to do implicitly) before the buffers go back to the pool
+    if (h->used_foreign_stream) cudaDeviceSynchronize();
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
-    if (!h->symmetric) free_points(h->p1);
-    free_points(h->p0);
-    if (h->scale_dev) cudaFree(h->scale_dev);
-    if (h->vpack) cudaFree(h->vpack);
-    if (h->ypack) cudaFree(h->ypack);
-    if (h->partial) cudaFree(h->partial);
-    if (h->stage) cudaFree(h->stage);
-    if (h->a12[0]) cudaFree(h->a12[0]);
-    if (h->b12[0]) cudaFree(h->b12[0]);
+    cudaStream_t fs = h->stream;
+    if (!h->symmetric) free_points(h->p1, fs);
+    free_points(h->p0, fs);
+    pn_dev_free(h->scale_dev, fs);
+    pn_dev_free(h->vpack, fs);
+    pn_dev_free(h->ypack, fs);
+    pn_dev_free(h->partial, fs);
+    pn_dev_free(h->stage, fs);
+    pn_dev_free(h->a12[0], fs);
+    pn_dev_free(h->b12[0], fs);
     if (!h->symmetric) {
-        if (h->a12[1]) cudaFree(h->a12[1]);
-        if (h->b12[1]) cudaFree(h->b12[1]);
+        pn_dev_free(h->a12[1], fs);
+        pn_dev_free(h->b12[1], fs);
     }
+    if (fs) cudaStreamSynchronize(fs);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -708,6 +746,7 @@ PNCOV_API int pncov_gram_device(pncov_handle* h, void* out, int64_t ld, int tran
     if (!out || ld < cols) return fail(PNCOV_EINVAL, "bad output buffer / leading dimension");
     DeviceGuard guard(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
     PN_CUDA(cudaEventRecord(h->ev0, stream));
     PN_CUDA(pn_launch_gram(gram_launch(h, transpose != 0, 0, rows, out, ld), stream));
     PN_CUDA(cudaEventRecord(h->ev1, stream));
@@ -730,7 +769,7 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
     const size_t block_bytes = (size_t)block_rows * cols * ge;
     const int nbuf = rows > block_rows ? 2 : 1;
     int rc;
-    if ((rc = ensure(&h->stage, &h->stage_bytes, block_bytes * nbuf))) return rc;
+    if ((rc = ensure(&h->stage, &h->stage_bytes, block_bytes * nbuf, h->stream))) return rc;
     cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     for (int i = 0; i < nbuf; ++i) {
         PN_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
@@ -771,6 +810,7 @@ PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int
     if (k > 0 && (!v || !y)) return fail(PNCOV_EINVAL, "NULL operand");
     DeviceGuard guard(h->device);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
     PN_CUDA(cudaEventRecord(h->ev0, stream));
     int rc = matmul_device_impl(h, v, k, ldv, y, ldy, transpose != 0, stream);
     if (rc) return rc;
@@ -791,7 +831,7 @@ PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ld
     const size_t es = h->k.elem();
     const size_t vbytes = (size_t)std::max<int64_t>(cols, 1) * k * es, ybytes = (size_t)rows * k * es;
     int rc;
-    if ((rc = ensure(&h->stage, &h->stage_bytes, vbytes + ybytes + 256))) return rc;
+    if ((rc = ensure(&h->stage, &h->stage_bytes, vbytes + ybytes + 256, h->stream))) return rc;
     char* dv = static_cast<char*>(h->stage);
     char* dy = dv + ((vbytes + 255) / 256) * 256;
     if (cols > 0)
@@ -823,11 +863,12 @@ PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const doub
     const size_t es = k.elem(), oe = k.gram_elem();
     const size_t pbytes = (size_t)b * d * es;
     char* buf = nullptr;
-    PN_CUDA(cudaMalloc(&buf, 2 * pbytes + (size_t)b * oe + 512));
+    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&buf), 2 * pbytes + (size_t)b * oe + 512, 0));
     void* scale_dev = nullptr;
     auto cleanup = [&]() {
-        cudaFree(buf);
-        if (scale_dev) cudaFree(scale_dev);
+        cudaStreamSynchronize(0);
+        pn_dev_free(buf, 0);
+        pn_dev_free(scale_dev, 0);
     };
     if ((rc = upload_scale(k, &scale_dev, 0))) {
         cleanup();

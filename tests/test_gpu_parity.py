@@ -390,3 +390,26 @@ def test_dmma_matvec_rectangular_small_d_and_columns():
         w = rng.normal(size=(700, k_cols))
         assert_matvec_close(L.T @ w, orc.matvec(spec, x1, x0, w), orc.abs_matvec(spec, x1, x0, w), 1e-12)
         L.close()
+
+
+def test_repeated_product_is_served_from_the_memo():
+    """Same operand twice in a row (what SymmetricMatrixBasedSolver does): identical result,
+    no second launch; a different operand invalidates the memo."""
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(41)
+    x = rng.normal(size=(900, 4))
+    L = pb.Matern((4,), nu=1.5).linop(x)
+    v = rng.normal(size=(900, 1))
+    y1 = L @ v
+    before = _lib.launch_count()
+    y2 = L @ v.copy()
+    assert _lib.launch_count() == before
+    np.testing.assert_array_equal(y1, y2)
+    y2[0] = 123.0  # the caller owns the returned array
+    np.testing.assert_array_equal(L @ v, y1)
+    w = v + 1.0
+    y3 = L @ w
+    assert _lib.launch_count() > before
+    spec = orc.KernelSpec("matern", (4,), 1.0, nu=1.5)
+    assert_matvec_close(y3, orc.matvec(spec, x, None, w), orc.abs_matvec(spec, x, None, w), 1e-12)
