@@ -103,7 +103,7 @@ def enable() -> None:
     numpy2_compat()
     import probnum  # noqa: PLC0415
 
-    if _ORIGINALS:
+    if enabled():
         return
     cf = probnum.randprocs.covfuncs
     linop_cls = _make_linop_class()
@@ -132,8 +132,75 @@ def enable() -> None:
         cls._evaluate_linop = make_linop(cls._evaluate_linop)
 
 
+# ---------------------------------------------------------------------------------------------
+# Cholesky + solves of the Bayesian-quadrature belief update on the device
+# ---------------------------------------------------------------------------------------------
+class DeviceCholesky:
+    """Upper-triangular-free stand-in for the ``(c, lower)`` pair of ``scipy.linalg.cho_factor``:
+    the factor of ``gram + jitter I`` stays in HBM (a torch tensor); only right-hand sides and
+    solutions cross PCIe.  Library code (cuSOLVER ``potrf`` / ``potrs`` through torch), i.e. the
+    baseline the survey names for this row, not a hand-written kernel."""
+
+    def __init__(self, factor):
+        self.factor = factor  # (n, n) lower-triangular torch.float64 CUDA tensor
+
+    # scipy returns a 2-tuple; the reference only ever passes it back to gram_cho_solve
+    def __iter__(self):
+        return iter((self, True))
+
+    def __len__(self):
+        return 2
+
+    def solve(self, z: np.ndarray) -> np.ndarray:
+        import torch  # noqa: PLC0415
+
+        zz = np.asarray(z, dtype=np.float64)
+        rhs = torch.from_numpy(np.ascontiguousarray(zz.reshape(zz.shape[0], -1))).to(self.factor.device)
+        sol = torch.cholesky_solve(rhs, self.factor, upper=False)
+        return sol.cpu().numpy().reshape(zz.shape)
+
+
+def enable_quad_cholesky() -> None:
+    """Route ``BQBeliefUpdate.compute_gram_cho_factor`` / ``gram_cho_solve``
+    (quad/solvers/belief_updates/_belief_update.py:61-103) through the GPU.  At 16384 nodes
+    the host ``dpotrf`` (1.5 TFLOP) takes ~15 s and dominates ``bayesquad_from_data`` once the
+    Gram matrix itself is built on the device."""
+    numpy2_compat()
+    import probnum  # noqa: PLC0415
+    import torch  # noqa: PLC0415
+    from probnum.quad.solvers.belief_updates import _belief_update as bu  # noqa: PLC0415
+
+    cls = bu.BQBeliefUpdate
+    if ("quad", cls) in _ORIGINALS:
+        return
+    _ORIGINALS[("quad", cls)] = (cls.__dict__["compute_gram_cho_factor"], cls.__dict__["gram_cho_solve"])
+    device = torch.device("cuda", _mirror._lib.default_device())
+
+    def compute_gram_cho_factor(self, gram):
+        g = torch.from_numpy(np.ascontiguousarray(gram, dtype=np.float64)).to(device)
+        g.diagonal().add_(self.jitter)
+        factor, info = torch.linalg.cholesky_ex(g, upper=False)
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError(f"{int(info.item())}-th leading minor of the array is not positive definite")
+        return DeviceCholesky(factor), True
+
+    def gram_cho_solve(gram_cho_factor, z):
+        chol = gram_cho_factor[0] if isinstance(gram_cho_factor, tuple) else gram_cho_factor
+        if isinstance(chol, DeviceCholesky):
+            return chol.solve(z)
+        return _ORIGINALS[("quad", cls)][1].__func__(gram_cho_factor, z)
+
+    cls.compute_gram_cho_factor = compute_gram_cho_factor
+    cls.gram_cho_solve = staticmethod(gram_cho_solve)
+
+
 def disable() -> None:
     """Undo :func:`enable`."""
+    quad = [k for k in _ORIGINALS if isinstance(k, tuple)]
+    for key in quad:
+        factor, solve = _ORIGINALS.pop(key)
+        key[1].compute_gram_cho_factor = factor
+        key[1].gram_cho_solve = solve
     for cls, (matrix, linop) in _ORIGINALS.items():
         # the methods are inherited from CovarianceFunction: remove our overrides
         for name, orig in (("_evaluate_matrix", matrix), ("_evaluate_linop", linop)):
@@ -145,4 +212,4 @@ def disable() -> None:
 
 
 def enabled() -> bool:
-    return bool(_ORIGINALS)
+    return any(not isinstance(k, tuple) for k in _ORIGINALS)

@@ -165,3 +165,34 @@ def test_bayesquad_from_data_matches_cpu_run():
     # the integral is ~0 by symmetry (cancellation of O(1) terms): compare on the scale of f
     assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), np.abs(fun_evals).max())
     assert abs(v_gpu - v_cpu) <= 1e-7 * abs(v_cpu) + 1e-14
+
+
+@pytest.mark.gpu
+def test_bayesquad_with_device_cholesky_matches_cpu_run():
+    """SURVEY 8f N1 (library baseline): Gram on the device AND cho_factor / cho_solve of the
+    belief update on the device (cuSOLVER through torch); integral belief as on the CPU."""
+    rng = np.random.default_rng(7)
+    n, d = 1500, 3
+    nodes = rng.normal(size=(n, d))
+    fun_evals = np.cos(nodes).prod(axis=1)
+    measure = pn.quad.integration_measures.GaussianMeasure(mean=np.zeros(d), cov=np.eye(d))
+
+    def run():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            F, info = pn.quad.bayesquad_from_data(nodes=nodes, fun_evals=fun_evals, measure=measure)
+        return float(F.mean), float(F.var)
+
+    m_cpu, v_cpu = run()
+    pb_patch.enable()
+    pb_patch.enable_quad_cholesky()
+    try:
+        m_gpu, v_gpu = run()
+    finally:
+        pb_patch.disable()
+    from probnum.quad.solvers.belief_updates import _belief_update as bu
+
+    assert bu.BQBeliefUpdate.gram_cho_solve.__module__ == bu.__name__  # reference methods restored
+    assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), np.abs(fun_evals).max())
+    # the variance is a difference of O(1) terms that cancels to ~1e-9: compare on that scale
+    assert abs(v_gpu - v_cpu) <= 1e-6 * abs(v_cpu) + 1e-13
