@@ -236,6 +236,7 @@ constexpr int MM_RG = 4;                          // row groups of 8 per warp
 constexpr int MM_ROWS = (MM_THREADS / 32) * MM_RG * 8;  // rows per CTA = 128
 constexpr int MM_TJ = 128;                        // columns per pipeline stage
 constexpr int MM_LD = 12;                         // doubles per point in a12 / b12
+constexpr int MM_NS = 2;                          // 8-column steps per inner iteration (tools/mv_variants.cu)
 
 __device__ __forceinline__ void pn_dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -305,31 +306,41 @@ __global__ void __launch_bounds__(MM_THREADS)
         const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
         const double* vt = bt + MM_TJ * MM_LD;
 
-#pragma unroll 2
-        for (int jj = 0; jj < MM_TJ; jj += 8) {
-            double bf[KSTEPS];
+#pragma unroll 1
+        for (int jj = 0; jj < MM_TJ; jj += 8 * MM_NS) {
+            // MM_NS steps of 8 columns: all DMMAs first, then the epilogues, so that the
+            // epilogue chains of one step overlap the DMMA latency of the next
+            double S[MM_NS][2 * MM_RG];
 #pragma unroll
-            for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(jj + g) * MM_LD + 4 * kk + q];
-            const double ny0 = bt[(jj + 2 * q) * MM_LD + 8];
-            const double ny1 = bt[(jj + 2 * q + 1) * MM_LD + 8];
-            double S[2 * MM_RG];
+            for (int s = 0; s < MM_NS; ++s) {
+                const int j = jj + 8 * s;
+                double bf[KSTEPS];
 #pragma unroll
-            for (int rg = 0; rg < MM_RG; ++rg) {
-                double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
-#pragma unroll
-                for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
-                S[2 * rg] = c0;
-                S[2 * rg + 1] = c1;
-            }
-            mv_epi_tile<EPI>(S, a.epi, tabE, tabL);
-#pragma unroll
-            for (int k = 0; k < KC; ++k) {
-                const double v0 = vt[(jj + 2 * q) * KC + k];
-                const double v1 = vt[(jj + 2 * q + 1) * KC + k];
+                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * MM_LD + 4 * kk + q];
+                const double ny0 = bt[(j + 2 * q) * MM_LD + 8];
+                const double ny1 = bt[(j + 2 * q + 1) * MM_LD + 8];
 #pragma unroll
                 for (int rg = 0; rg < MM_RG; ++rg) {
-                    acc[rg][k] = pn_fma(S[2 * rg], v0, acc[rg][k]);
-                    acc[rg][k] = pn_fma(S[2 * rg + 1], v1, acc[rg][k]);
+                    double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
+                    S[s][2 * rg] = c0;
+                    S[s][2 * rg + 1] = c1;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < MM_NS; ++s) {
+                const int j = jj + 8 * s;
+                mv_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    const double v0 = vt[(j + 2 * q) * KC + k];
+                    const double v1 = vt[(j + 2 * q + 1) * KC + k];
+#pragma unroll
+                    for (int rg = 0; rg < MM_RG; ++rg) {
+                        acc[rg][k] = pn_fma(S[s][2 * rg], v0, acc[rg][k]);
+                        acc[rg][k] = pn_fma(S[s][2 * rg + 1], v1, acc[rg][k]);
+                    }
                 }
             }
         }

@@ -258,7 +258,7 @@ def test_matvec_deterministic_and_split_columns():
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json sizes: size-independent properties + sampled rows against the oracle
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("spec", [SPECS[4], SPECS[6]], ids=["matern52", "ratquad"])
+@pytest.mark.parametrize("spec", [SPECS[0], SPECS[4], SPECS[6]], ids=["expquad", "matern52", "ratquad"])
 def test_config2_gram_32768(spec):
     rng = np.random.default_rng(42)
     n = 32768
@@ -413,3 +413,27 @@ def test_repeated_product_is_served_from_the_memo():
     assert _lib.launch_count() > before
     spec = orc.KernelSpec("matern", (4,), 1.0, nu=1.5)
     assert_matvec_close(y3, orc.matvec(spec, x, None, w), orc.abs_matvec(spec, x, None, w), 1e-12)
+
+
+def test_config3_matvec_2pow20():
+    """BASELINE configs[2]: matrix-free ExpQuad K.v at N = 1,048,576, d = 8.  Sampled rows
+    against the oracle with the componentwise bound, plus a checksum identity: 1^T (K v) =
+    (K 1)^T v because K is symmetric."""
+    rng = np.random.default_rng(42)
+    n, d = 1 << 20, 8
+    spec = orc.KernelSpec("expquad", (d,), 1.0)
+    x = rng.normal(size=(n, d))
+    v = rng.normal(size=n)
+    L = make_kernel(spec).linop(x)
+    y = L @ v
+    assert L._device_op().matmul_path() == "norm-identity-dmma"
+    rows = rng.choice(n, size=24, replace=False)
+    Kr = orc.gram(spec, x[rows], x, row_block=8)
+    assert_matvec_close(y[rows], Kr @ v, np.abs(Kr) @ np.abs(v), 1e-12)
+    ones = np.ones(n)
+    k1 = L @ ones
+    lhs, rhs = float(np.sum(y)), float(k1 @ v)
+    scale = float(k1 @ np.abs(v))
+    assert abs(lhs - rhs) <= 1e-11 * scale
+    assert np.all(k1 >= 1.0)  # every row contains the unit diagonal
+    L.close()

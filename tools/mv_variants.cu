@@ -172,6 +172,135 @@ void run(const char* name, const double* raw, const double* a12, const double* b
            TJ, TAB, C, occ, occ * THREADS / 32, best, (double)n * n / best / 1e6, maxrel);
 }
 
+
+// ---- DMMA variants --------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// THREADS per CTA, RG row groups of 8 per warp, TJ columns per stage, NS column-steps of 8 per
+// inner iteration, SPLITK: independent accumulators for the two k-steps
+template <int THREADS, int RG, int TJ, int NS, int SPLITK>
+__global__ void __launch_bounds__(THREADS)
+mma_kernel(const double* __restrict__ a12, const double* __restrict__ b12, const double* __restrict__ v,
+           double* __restrict__ y, int n0, int n1, const __grid_constant__ PnEpiParams P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* stage0 = tabE + PN_EXP2_N;
+    constexpr int STAGE = TJ * (LD + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    constexpr uint32_t XB = TJ * LD * 8, VB = TJ * 8;
+    const int n_jt = n1 / TJ;
+    if (tid == 0) { pn_mbar_init(&bars[0], 1); pn_mbar_init(&bars[1], 1); pn_mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], XB + VB);
+        pn_bulk_g2s(stage0, b12, XB, &bars[0]);
+        pn_bulk_g2s(stage0 + TJ * LD, v, VB, &bars[0]);
+    }
+    for (int i = tid; i < PN_EXP2_N; i += THREADS) tabE[i] = pn_exp2_table_g[i];
+    const int64_t row0 = (int64_t)blockIdx.x * (THREADS / 32 * RG * 8) + warp * (RG * 8);
+    double af[RG][2], nx[RG], acc[RG];
+#pragma unroll
+    for (int rg = 0; rg < RG; ++rg) {
+        const double* pr = a12 + (row0 + rg * 8 + g) * LD;
+        af[rg][0] = pr[q]; af[rg][1] = pr[4 + q]; nx[rg] = pr[8]; acc[rg] = 0.0;
+    }
+    __syncthreads();
+    for (int jt = 0; jt < n_jt; ++jt) {
+        const int buf = jt & 1;
+        if (tid == 0 && jt + 1 < n_jt) {
+            double* dst = stage0 + (buf ^ 1) * STAGE;
+            pn_mbar_expect_tx(&bars[buf ^ 1], XB + VB);
+            pn_bulk_g2s(dst, b12 + (size_t)(jt + 1) * TJ * LD, XB, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + TJ * LD, v + (size_t)(jt + 1) * TJ, VB, &bars[buf ^ 1]);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((jt >> 1) & 1));
+        const double* bt = stage0 + buf * STAGE;
+        const double* vt = bt + TJ * LD;
+#pragma unroll 1
+        for (int jj = 0; jj < TJ; jj += 8 * NS) {
+            double S[NS][2 * RG];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int j = jj + 8 * s;
+                const double b0 = bt[(j + g) * LD + q], b1 = bt[(j + g) * LD + 4 + q];
+                const double ny0 = bt[(j + 2 * q) * LD + 8], ny1 = bt[(j + 2 * q + 1) * LD + 8];
+#pragma unroll
+                for (int rg = 0; rg < RG; ++rg) {
+                    double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
+                    if (SPLITK) {
+                        double d0 = 0.0, d1 = 0.0;
+                        dmma884(c0, c1, af[rg][0], b0);
+                        dmma884(d0, d1, af[rg][1], b1);
+                        c0 += d0; c1 += d1;
+                    } else {
+                        dmma884(c0, c1, af[rg][0], b0);
+                        dmma884(c0, c1, af[rg][1], b1);
+                    }
+                    S[s][2 * rg] = c0; S[s][2 * rg + 1] = c1;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int j = jj + 8 * s;
+                PnFlags f; f.reset();
+                double K[2 * RG];
+#pragma unroll
+                for (int i = 0; i < 2 * RG; ++i) K[i] = epi<0>(S[s][i], P, tabE, f);
+                if (f.flagged(P)) {
+#pragma unroll
+                    for (int i = 0; i < 2 * RG; ++i) K[i] = pn_epilogue(S[s][i], P, pn_exp2_table_g, pn_log2_table_g);
+                }
+                const double2 vv = *reinterpret_cast<const double2*>(vt + j + 2 * q);
+#pragma unroll
+                for (int rg = 0; rg < RG; ++rg) {
+                    acc[rg] = pn_fma(K[2 * rg], vv.x, acc[rg]);
+                    acc[rg] = pn_fma(K[2 * rg + 1], vv.y, acc[rg]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int rg = 0; rg < RG; ++rg) {
+        double s = acc[rg];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        const int64_t row = row0 + rg * 8 + g;
+        if (q == 0 && row < n0) y[row] = s;
+    }
+}
+
+template <int THREADS, int RG, int TJ, int NS, int SPLITK>
+void run_mma(const char* name, const double* a12, const double* b12, const double* v, double* y, int n, double* ref) {
+    auto kern = mma_kernel<THREADS, RG, TJ, NS, SPLITK>;
+    const size_t smem = 128 + 8 * PN_EXP2_N + 2 * 8 * TJ * (LD + 1);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem));
+    PnEpiParams P = make_params(true);
+    dim3 grid(n / (THREADS / 32 * RG * 8));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    kern<<<grid, THREADS, smem>>>(a12, b12, v, y, n, n, P);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, THREADS, smem>>>(a12, b12, v, y, n, n, P);
+        CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (ms < best) best = ms;
+    }
+    std::vector<double> h(64);
+    CK(cudaMemcpy(h.data(), y, 64 * 8, cudaMemcpyDeviceToHost));
+    double maxrel = 0;
+    for (int i = 0; i < 64; ++i) maxrel = fmax(maxrel, fabs(h[i] - ref[i]) / fabs(ref[i]));
+    printf("%-44s thr=%3d RG=%d TJ=%3d NS=%d SPLITK=%d occ=%d warps/SM=%2d  %8.3f ms  %7.1f Gpair/s  maxrel=%.1e\n", name,
+           THREADS, RG, TJ, NS, SPLITK, occ, occ * THREADS / 32, best, (double)n * n / best / 1e6, maxrel);
+}
+
 int main(int argc, char** argv) {
     const int n = argc > 1 ? atoi(argv[1]) : 131072;
     std::vector<double> raw((size_t)n * D), a12((size_t)n * LD, 0.0), b12((size_t)n * LD, 0.0), v(n);
@@ -195,23 +324,25 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(db, b12.data(), b12.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dv, v.data(), n * 8, cudaMemcpyHostToDevice));
     double ref[64] = {0};
+    const bool dfma = argc > 2;
     run<128, 2, 128, 0, 0, 2>("direct (shipping kernel shape)", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 128, 0, 0, 2>("direct 256 threads", draw, da, db, dv, dy, n, ref);
-    run<128, 2, 128, 0, 1, 2>("identity serial dot", draw, da, db, dv, dy, n, ref);
-    run<128, 2, 64, 0, 1, 2>("identity serial dot TJ=64", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 128, 0, 1, 2>("identity serial dot 256 thr", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 64, 0, 1, 2>("identity serial dot 256 thr TJ=64", draw, da, db, dv, dy, n, ref);
-    run<128, 2, 64, 0, 2, 2>("identity split dot TJ=64", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 64, 0, 2, 2>("identity split dot 256 thr TJ=64", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 64, 1, 1, 2>("identity serial, replicated table 256 thr", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 64, 1, 2, 2>("identity split, replicated table 256 thr", draw, da, db, dv, dy, n, ref);
-    run<128, 4, 64, 0, 1, 2>("identity R=4", draw, da, db, dv, dy, n, ref);
-    run<256, 4, 64, 0, 1, 1>("identity R=4 C=1 256 thr", draw, da, db, dv, dy, n, ref);
-    run<256, 4, 64, 1, 1, 1>("identity R=4 C=1 256 thr replicated", draw, da, db, dv, dy, n, ref);
-    run<128, 2, 64, 0, 1, 4>("identity R=2 C=4", draw, da, db, dv, dy, n, ref);
-    run<256, 2, 64, 1, 1, 4>("identity R=2 C=4 256 thr replicated", draw, da, db, dv, dy, n, ref);
-    run<256, 1, 64, 0, 1, 4>("identity R=1 C=4 256 thr", draw, da, db, dv, dy, n, ref);
-    run<512, 1, 64, 1, 1, 4>("identity R=1 C=4 512 thr replicated", draw, da, db, dv, dy, n, ref);
-    run<512, 2, 64, 1, 1, 2>("identity R=2 C=2 512 thr replicated", draw, da, db, dv, dy, n, ref);
+    if (dfma) {
+        run<128, 2, 64, 0, 1, 2>("identity serial dot TJ=64", draw, da, db, dv, dy, n, ref);
+        run<128, 2, 64, 0, 2, 2>("identity split dot TJ=64", draw, da, db, dv, dy, n, ref);
+        run<128, 4, 64, 0, 1, 2>("identity R=4", draw, da, db, dv, dy, n, ref);
+    }
+    run_mma<128, 4, 128, 1, 0>("dmma shipping shape", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 2, 0>("dmma 16 columns per step", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 1, 1>("dmma split k", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 2, 1>("dmma 16 columns, split k", da, db, dv, dy, n, ref);
+    run_mma<256, 4, 128, 1, 0>("dmma 256 threads", da, db, dv, dy, n, ref);
+    run_mma<256, 4, 64, 1, 0>("dmma 256 threads TJ=64", da, db, dv, dy, n, ref);
+    run_mma<128, 2, 128, 2, 0>("dmma RG=2, 16 columns", da, db, dv, dy, n, ref);
+    run_mma<128, 2, 128, 4, 0>("dmma RG=2, 32 columns", da, db, dv, dy, n, ref);
+    run_mma<256, 2, 128, 2, 0>("dmma RG=2, 16 columns, 256 thr", da, db, dv, dy, n, ref);
+    run_mma<128, 6, 128, 1, 0>("dmma RG=6", da, db, dv, dy, n, ref);
+    run_mma<128, 8, 128, 1, 0>("dmma RG=8", da, db, dv, dy, n, ref);
+    run_mma<64, 4, 128, 1, 0>("dmma 64 threads", da, db, dv, dy, n, ref);
+    run_mma<64, 8, 128, 1, 0>("dmma 64 threads RG=8", da, db, dv, dy, n, ref);
     return 0;
 }
