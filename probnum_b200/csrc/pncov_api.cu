@@ -763,10 +763,13 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
     DeviceGuard guard(h->device);
     const size_t ge = h->k.gram_elem();
     // row blocks of <= 1 GiB, double buffered: block b+1 is computed while block b is copied out
-    int64_t block_rows = (int64_t)((1ull << 30) / ((size_t)cols * ge));
+    // the staging rows are padded to an even length so that every row starts 16-byte aligned
+    // (the fast kernel's vector stores); the copy below strips the padding again
+    const int64_t ld_stage = cols + (cols & 1);
+    int64_t block_rows = (int64_t)((1ull << 30) / ((size_t)ld_stage * ge));
     block_rows = std::max<int64_t>(PN_PAD, (block_rows / PN_PAD) * PN_PAD);
     block_rows = std::min<int64_t>(block_rows, pad_up(rows));
-    const size_t block_bytes = (size_t)block_rows * cols * ge;
+    const size_t block_bytes = (size_t)block_rows * ld_stage * ge;
     const int nbuf = rows > block_rows ? 2 : 1;
     int rc;
     if ((rc = ensure(&h->stage, &h->stage_bytes, block_bytes * nbuf, h->stream))) return rc;
@@ -783,11 +786,11 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
         const int buf = b % nbuf;
         char* dbuf = static_cast<char*>(h->stage) + (size_t)buf * block_bytes;
         if (b >= nbuf) err = cudaStreamWaitEvent(h->stream, copied[buf], 0);
-        if (err == cudaSuccess) err = pn_launch_gram(gram_launch(h, transpose != 0, r0, nr, dbuf, cols), h->stream);
+        if (err == cudaSuccess) err = pn_launch_gram(gram_launch(h, transpose != 0, r0, nr, dbuf, ld_stage), h->stream);
         if (err == cudaSuccess) err = cudaEventRecord(done[buf], h->stream);
         if (err == cudaSuccess) err = cudaStreamWaitEvent(h->copy_stream, done[buf], 0);
         if (err == cudaSuccess)
-            err = cudaMemcpy2DAsync(static_cast<char*>(out) + (size_t)r0 * ld * ge, (size_t)ld * ge, dbuf, (size_t)cols * ge,
+            err = cudaMemcpy2DAsync(static_cast<char*>(out) + (size_t)r0 * ld * ge, (size_t)ld * ge, dbuf, (size_t)ld_stage * ge,
                                     (size_t)cols * ge, (size_t)nr, cudaMemcpyDeviceToHost, h->copy_stream);
         if (err == cudaSuccess) err = cudaEventRecord(copied[buf], h->copy_stream);
     }
