@@ -21,10 +21,11 @@ stream = torch.cuda.current_stream(dev).cuda_stream
 rng = np.random.default_rng(42)
 if what in ("gram", "all"):
     x = torch.from_numpy(rng.normal(size=(n, 3))).to(dev)
+    x1 = torch.from_numpy(rng.normal(size=(n, 3))).to(dev) if os.environ.get("PROF_CROSS") else None
     out = torch.empty((n, n), dtype=torch.float64, device=dev)
     kernels = (pb.ExpQuad((3,)), pb.Matern((3,), nu=2.5), pb.RatQuad((3,)), pb.RatQuad((3,), alpha=1.5))
     for k in kernels[:2] if reps == 1 else kernels:
-        op = _lib.Operator(k._kernel_params(), x.data_ptr(), None, on_device=True, n0=n, n1=n, dtype=np.float64)
+        op = _lib.Operator(k._kernel_params(), x.data_ptr(), None if x1 is None else x1.data_ptr(), on_device=True, n0=n, n1=n, dtype=np.float64)
         for _ in range(reps):
             op.gram_device(out.data_ptr(), n, stream=stream)
         torch.cuda.synchronize()
