@@ -437,3 +437,16 @@ def test_config3_matvec_2pow20():
     assert abs(lhs - rhs) <= 1e-11 * scale
     assert np.all(k1 >= 1.0)  # every row contains the unit diagonal
     L.close()
+
+
+@pytest.mark.parametrize("k_cols", [5, 8, 9, 16])
+def test_wide_right_hand_sides(k_cols):
+    """More than four right-hand sides run 8 columns per pass in the norm-identity kernel
+    (and 4 per pass in the direct kernel)."""
+    rng = np.random.default_rng(k_cols)
+    x0, x1 = rng.normal(size=(1000, 6)), rng.normal(size=(1400, 6))
+    v = rng.normal(size=(1400, k_cols))
+    for spec in (orc.KernelSpec("expquad", (6,), 1.3), orc.KernelSpec("matern", (6,), 1.3, nu=2.5)):
+        L = make_kernel(spec).linop(x0, x1)
+        assert_matvec_close(L @ v, orc.matvec(spec, x0, x1, v), orc.abs_matvec(spec, x0, x1, v), 1e-12)
+        L.close()
