@@ -16,6 +16,13 @@ the device path up without modification:
 * ``_evaluate_matrix(x0, x1)``  (randprocs/covfuncs/_covariance_function.py:553-582)
 * ``_evaluate_linop(x0, x1)``   (randprocs/covfuncs/_covariance_function.py:584-604)
 
+plus ``_evaluate`` for the Gram-shaped broadcast ``(N0, 1, d) x (1, N1, d)``: that is what the
+covariance arithmetic of the reference calls on each operand
+(``ScaledCovarianceFunction._evaluate`` / ``SumCovarianceFunction._evaluate`` /
+``ProductCovarianceFunction._evaluate``, randprocs/covfuncs/_arithmetic_fallbacks.py:55-56,
+:101-104, :163-166), so ``(k1 + 0.1 * k2).matrix(X)`` builds every operand on the device and
+only the final combination stays in NumPy (first step).
+
 Kernels outside the accelerated scope (other classes, Matern with non-half-integer nu,
 multi-dimensional input shapes) keep the reference's own methods untouched: that is the
 reference's behaviour for them, not a fallback of ours.
@@ -126,10 +133,24 @@ def enable() -> None:
 
         return _evaluate_linop
 
+    def make_evaluate(original):
+        def _evaluate(self, x0, x1=None):
+            # only the Gram-shaped broadcast with enough pairs to be worth a launch; every other
+            # pattern is O(N d) work and stays with the reference
+            if (x1 is not None and x0.ndim == self.input_ndim + 2 and x1.ndim == self.input_ndim + 2
+                    and x0.shape[1] == 1 and x1.shape[0] == 1 and x0.shape[0] * x1.shape[1] >= 4096):
+                twin = _mirror_of(self)
+                if twin is not None:
+                    return twin._evaluate(x0, x1)
+            return original(self, x0, x1)
+
+        return _evaluate
+
     for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad):
-        _ORIGINALS[cls] = (cls._evaluate_matrix, cls._evaluate_linop)
+        _ORIGINALS[cls] = (cls._evaluate_matrix, cls._evaluate_linop, cls.__dict__["_evaluate"])
         cls._evaluate_matrix = make_matrix(cls._evaluate_matrix)
         cls._evaluate_linop = make_linop(cls._evaluate_linop)
+        cls._evaluate = make_evaluate(cls.__dict__["_evaluate"])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -201,13 +222,14 @@ def disable() -> None:
         factor, solve = _ORIGINALS.pop(key)
         key[1].compute_gram_cho_factor = factor
         key[1].gram_cho_solve = solve
-    for cls, (matrix, linop) in _ORIGINALS.items():
-        # the methods are inherited from CovarianceFunction: remove our overrides
+    for cls, (matrix, linop, evaluate) in _ORIGINALS.items():
+        # the two hooks are inherited from CovarianceFunction: remove our overrides
         for name, orig in (("_evaluate_matrix", matrix), ("_evaluate_linop", linop)):
             if name in cls.__dict__:
                 delattr(cls, name)
             if getattr(cls, name) is not orig:
                 setattr(cls, name, orig)
+        cls._evaluate = evaluate  # defined on the class itself
     _ORIGINALS.clear()
 
 

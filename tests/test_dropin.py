@@ -196,3 +196,39 @@ def test_bayesquad_with_device_cholesky_matches_cpu_run():
     assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), np.abs(fun_evals).max())
     # the variance is a difference of O(1) terms that cancels to ~1e-9: compare on that scale
     assert abs(v_gpu - v_cpu) <= 1e-6 * abs(v_cpu) + 1e-13
+
+
+def test_evaluate_hook_is_restored():
+    before = {cls: cls.__dict__["_evaluate"] for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad)}
+    pb_patch.enable()
+    assert all(cls.__dict__["_evaluate"] is not before[cls] for cls in before)
+    # small broadcasts are not routed to the device (no GPU needed for this call)
+    np.testing.assert_array_equal(cf.ExpQuad((2,))(np.zeros((3, 1, 2)), np.zeros((1, 3, 2))), np.ones((3, 3)))
+    pb_patch.disable()
+    assert all(cls.__dict__["_evaluate"] is before[cls] for cls in before)
+
+
+@pytest.mark.gpu
+def test_covariance_arithmetic_runs_operands_on_the_device(patched):
+    """k1 + c * k2 + k3 * k4: every supported operand is evaluated by the Gram kernel, the
+    combination is the reference's own NumPy code (_arithmetic_fallbacks.py)."""
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(5)
+    X = rng.normal(size=(300, 3))
+    Y = rng.normal(size=(200, 3))
+    k = cf.ExpQuad((3,), lengthscales=0.7) + 0.25 * cf.Matern((3,), nu=1.5) + cf.RatQuad((3,)) * cf.Matern((3,), nu=0.5)
+    k_noise = cf.ExpQuad((3,)) + 0.1 * cf.WhiteNoise((3,))
+    launches = _lib.launch_count()
+    got, got_noise = k.matrix(X, Y), k_noise.matrix(X)
+    assert _lib.launch_count() - launches >= 5
+    v = rng.normal(size=200)
+    got_lin = (cf.ExpQuad((3,), lengthscales=0.7) + 0.25 * cf.Matern((3,), nu=1.5)).linop(X, Y) @ v
+    pb_patch.disable()
+    try:
+        np.testing.assert_allclose(got, k.matrix(X, Y), rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(got_noise, k_noise.matrix(X), rtol=1e-12, atol=1e-12)
+        want_lin = (cf.ExpQuad((3,), lengthscales=0.7) + 0.25 * cf.Matern((3,), nu=1.5)).matrix(X, Y) @ v
+        np.testing.assert_allclose(got_lin, want_lin, rtol=1e-10, atol=1e-12)
+    finally:
+        pb_patch.enable()
