@@ -102,7 +102,10 @@ PNCOV_API int pncov_gram_dtype(const pncov_handle* h, int* dtype);
  *   _covariance_linear_operator.py:83-90)
  * pncov_gram:        `out` is host memory (pageable or pinned); blocks until done.
  * pncov_gram_device: `out` is device memory on the handle's device; asynchronous on
- *                    `stream` (a cudaStream_t, 0 = the handle's own stream).
+ *                    `stream` (a cudaStream_t passed through unchanged; 0 is the legacy
+ *                    default stream, which is what torch's default stream is).  The
+ *                    handle's scratch is reused across calls, so issue all *_device calls
+ *                    of one handle on the same stream.
  */
 PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose);
 PNCOV_API int pncov_gram_device(pncov_handle* h, void* out, int64_t ld, int transpose, void* stream);

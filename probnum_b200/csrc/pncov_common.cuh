@@ -246,14 +246,6 @@ struct PnEpilogue {
     }
 };
 
-// float32 inputs.  Distances are accumulated in float (as the reference does for
-// float32 arrays); ExpQuad stays in float, the other families continue in double
-// because the reference's float64 hyper-parameter scalars promote there (NumPy 2).
-__device__ __forceinline__ float pn_epilogue_f32_expquad(float S, const PnEpiParams& P) {
-    // S already carries the float32-rounded scale factors; c_u = -log2(e) * (s^2 or 1)
-    return exp2f(S * (float)P.c_u);
-}
-
 // ---------------------------------------------------------------------------------------
 // TMA (1-D bulk copy) + mbarrier
 // ---------------------------------------------------------------------------------------

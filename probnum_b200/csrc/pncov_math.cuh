@@ -26,10 +26,8 @@
 
 #if defined(__CUDACC__)
 #define PN_HD __host__ __device__ __forceinline__
-#define PN_D __device__ __forceinline__
 #else
 #define PN_HD inline
-#define PN_D inline
 #include <string.h>
 #endif
 
@@ -100,7 +98,7 @@ PN_HD double pn_rcp_seed(double x) {
 // ------------------------------------------------------------------------------------
 #define PN_EXP2_N (1 << PNCOV_EXP2_BITS)
 
-// Fast path valid for |u| < 1022 (result normal).  tab = 2^(j/256) table (shared memory
+// Fast path valid for |u| < 1022 (result normal).  tab = the 2^(j/2048) table (shared memory
 // on the device).  Returns false if the caller must take the slow path.
 PN_HD bool pn_exp2_in_fast_range(double u) {
     // |u| < 1022  <=>  (hi & 0x7fffffff) < hi(1022.0) = 0x408FF000; also rejects inf/nan

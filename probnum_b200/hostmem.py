@@ -19,7 +19,7 @@ import numpy as np
 from . import _lib
 
 PINNED_THRESHOLD_BYTES = 4 << 20
-_MAX_CACHED_BYTES = 40 << 30
+_MAX_CACHED_BYTES = 20 << 30
 _free = {}  # nbytes -> [ptr, ...]
 _cached_bytes = 0
 _lock = threading.Lock()
