@@ -138,8 +138,12 @@ __global__ void __launch_bounds__(G_THREADS)
     pn_mbar_wait(&bars[0], 0);
 
     const int64_t j0 = col0 + 2 * tid;
-    TOut* out = static_cast<TOut*>(g.out);
     const T* x1t = x1s + 2 * tid;
+    // how this thread stores its two columns (constant for the whole kernel): 3 = one vector
+    // store, 2 = two scalar stores, 1 = first column only (last, odd column), 0 = outside
+    const int store_mode = (j0 + 1 < g.n1) ? (vec_ok ? 3 : 2) : (j0 < g.n1 ? 1 : 0);
+    const size_t row_stride = (size_t)g.ldo;
+    TOut* optr = static_cast<TOut*>(g.out) + (size_t)t0 * G_TM * row_stride + j0;
 
     int it = 0;
     for (int64_t t = t0; t < t1; ++t, ++it) {
@@ -193,12 +197,21 @@ __global__ void __launch_bounds__(G_THREADS)
             }
             TOut K[2 * G_R];
             epi_dispatch(S, K, g.epi, tabE, tabL);
+            const int rows_left = rows_here - rg;  // >= 1
 #pragma unroll
             for (int r = 0; r < G_R; ++r) {
-                const int64_t row = row_base + rg + r;
-                if (row < g.n0) store_pair(out + row * g.ldo, j0, g.n1, K[2 * r], K[2 * r + 1], vec_ok != 0);
+                if (r < rows_left) {
+                    if (store_mode == 3) {
+                        pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
+                    } else if (store_mode != 0) {
+                        pn_store_cs1(optr, K[2 * r]);
+                        if (store_mode == 2) pn_store_cs1(optr + 1, K[2 * r + 1]);
+                    }
+                }
+                optr += row_stride;
             }
         }
+        optr += (size_t)(G_TM - ((rows_here + G_R - 1) / G_R) * G_R) * row_stride;  // to the next tile
         __syncthreads();  // everyone is done with x0 stage `buf` before it is refilled
     }
 }
