@@ -1,0 +1,43 @@
+"""Run under torchrun on >= 2 GPUs: checks ShardedCovarianceOperator (host and device operands,
+NCCL all-gather) against the oracle on every rank.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29517 tools/check_sharded_nccl.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import probnum_b200 as pb  # noqa: E402
+from oracle import covfuncs_oracle as orc  # noqa: E402
+from probnum_b200.sharded import ShardedCovarianceOperator  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+rng = np.random.default_rng(3)
+for (n0, n1, d, kernel, spec) in [
+    (4099, 3001, 4, pb.ExpQuad((4,), lengthscales=1.1), orc.KernelSpec("expquad", (4,), 1.1)),
+    (4096, 4096, 3, pb.Matern((3,), nu=2.5), orc.KernelSpec("matern", (3,), 1.0, nu=2.5)),
+]:
+    x0, x1 = rng.normal(size=(n0, d)), rng.normal(size=(n1, d))
+    v = rng.normal(size=(n1, 2))
+    op = ShardedCovarianceOperator(kernel, x0, x1, device=local)
+    y = op @ v                                     # host operands, uneven shards allowed
+    want = orc.matvec(spec, x0, x1, v)
+    bound = orc.abs_matvec(spec, x0, x1, v)
+    assert np.all(np.abs(y - want) <= 1e-12 * bound), f"rank {rank}: host path mismatch"
+    if n0 % world == 0:
+        vd = torch.from_numpy(v).to(dev)
+        yd = op.matmul_device(vd).cpu().numpy()     # device operands, in-place all-gather
+        assert np.all(np.abs(yd - want) <= 1e-12 * bound), f"rank {rank}: device path mismatch"
+    op.close()
+dist.barrier()
+if rank == 0:
+    print(f"sharded NCCL check ok on {world} GPUs")
+dist.destroy_process_group()
