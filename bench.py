@@ -373,6 +373,16 @@ def run_ours(args):
             "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,
             "flop_per_pair": flop_per_pair, "scaling": "strong",
         }
+        # FP64 roofline of this kernel: algorithmic flops against the DFMA rate measured on this
+        # pool by tools/microbench.cu (profiles/r01_microbench.json), per GPU
+        mb = os.path.join(ROOT, "profiles", "r01_microbench.json")
+        if os.path.exists(mb):
+            with open(mb) as fh:
+                dfma = json.load(fh).get("dfma_tflops_sustained")
+            if dfma:
+                ach = extra["matvec"]["gflops"] / 1e3 / world
+                extra["matvec"]["roofline"] = {"bound": "fp64 pipe", "achieved": ach, "peak": dfma, "unit": "TFLOP/s",
+                                               "frac": ach / dfma, "peak_source": "profiles/r01_microbench.json dfma_tflops_sustained"}
         sop.close()
 
     cpu = None
