@@ -171,7 +171,8 @@ __device__ __forceinline__ double pn_exp2_prod_core_rep(double a, double b, cons
 __device__ __forceinline__ double pn_sqrt_core(double s) {
     double y = pn_rsqrt_seed(s);
     double g = s * y;
-    double h = 0.5 * y;
+    // h = y / 2 on the integer pipe (exponent - 1; y is a normal number in the fast window)
+    double h = pn_make(pn_hi(y) - 0x00100000, pn_lo(y));
     double e = pn_fma(-h, g, 0.5);
     g = pn_fma(g, e, g);
     double d = pn_fma(-g, g, s);

@@ -7,7 +7,7 @@
 //
 //   pn_exp2   2^(a*b)                  2 DFMA + DADD (reduction, product never formed)
 //                                      + 2 DFMA + DMUL + DFMA (2048-entry table, degree-2 q)
-//   pn_sqrt   sqrt(s)                  MUFU.RSQ64H + 2 DMUL + 4 DFMA
+//   pn_sqrt   sqrt(s)                  MUFU.RSQ64H + 1 DMUL + 4 DFMA (+ integer halving)
 //   pn_rcp    1/b, b >= 1              MUFU.RCP64H + 4 DFMA
 //   pn_log2   log2(b), b >= 1          1 DFMA + 5 poly + 3 DADD        (+ LDS.128, int)
 //
@@ -141,7 +141,7 @@ PN_HD double pn_sqrt(double s) {
     if (h - 0x01000000u < 0x7ee00000u) {
         double y = pn_rsqrt_seed(s);
         double g = s * y;
-        double hh = 0.5 * y;
+        double hh = pn_make(pn_hi(y) - 0x00100000, pn_lo(y));  // y / 2 without an FP64 instruction
         double e = pn_fma(-hh, g, 0.5);
         g = pn_fma(g, e, g);
         // the final correction is ~2^-44 relative, so the 22-bit h is accurate enough for it
