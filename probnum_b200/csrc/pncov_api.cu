@@ -350,8 +350,8 @@ struct pncov_handle {
     size_t partial_bytes = 0;
     void* stage = nullptr;  // device staging for host entry points
     size_t stage_bytes = 0;
-    // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
     bool used_foreign_stream = false;  // a *_device entry point ran on a caller-owned stream
+    // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
     void* a12[2] = {nullptr, nullptr};  // per point set (0: x0, 1: x1); aliases when symmetric
     void* b12[2] = {nullptr, nullptr};

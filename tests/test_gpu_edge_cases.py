@@ -134,3 +134,39 @@ def test_float32_products_and_call():
         want = orc.evaluate(spec, x0[:50], x1[:50])
         assert out.dtype == want.dtype
         np.testing.assert_allclose(out, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomized_shapes_and_kernels(seed):
+    """Seeded sweep over shapes that straddle every dispatch boundary: 64-row tiles, 512-column
+    strips, d = 8 / 16 transitions, odd leading dimensions, column splits of the matvec."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(8):
+        d = int(rng.choice([1, 2, 3, 4, 7, 8, 9, 15, 16, 17, 31]))
+        n0 = int(rng.choice([1, 63, 64, 65, 511, 512, 513, 1023, 1025, 1536, 2049])) + int(rng.integers(0, 3))
+        n1 = int(rng.choice([1, 2, 127, 128, 129, 511, 512, 513, 1024, 1100])) + int(rng.integers(0, 3))
+        kind = rng.choice(["expquad", "matern", "ratquad"])
+        ard = kind != "ratquad" and rng.random() < 0.5 and d > 1
+        ls = (rng.gamma(2.0, size=d) + 0.5) * np.sqrt(d) if ard else float(rng.uniform(0.5, 2.0) * np.sqrt(d))
+        nu = float(rng.choice([0.5, 1.5, 2.5, 4.5]))
+        alpha = float(rng.choice([1.0, 2.0, 0.6, 5.5]))
+        spec = orc.KernelSpec(kind, (d,), ls, nu=nu, alpha=alpha)
+        if kind == "expquad":
+            k = pb.ExpQuad((d,), lengthscales=ls)
+        elif kind == "matern":
+            k = pb.Matern((d,), nu=nu, lengthscales=ls)
+        else:
+            k = pb.RatQuad((d,), lengthscale=ls, alpha=alpha)
+        x0 = rng.normal(size=(n0, d)) + rng.choice([0.0, 25.0])
+        same = rng.random() < 0.3
+        x1 = None if same else rng.normal(size=(n1, d)) + rng.choice([0.0, 25.0])
+        tag = f"{kind} d={d} n0={n0} n1={'same' if same else n1} ard={ard} nu={nu} alpha={alpha}"
+        want = orc.gram(spec, x0, x1)
+        np.testing.assert_allclose(k.matrix(x0, x1), want, rtol=1e-12, atol=1e-12, err_msg=tag)
+        cols = want.shape[1]
+        v = rng.normal(size=(cols, int(rng.choice([1, 2, 4, 5]))))
+        L = k.linop(x0, x1)
+        y = L @ v
+        bound = np.abs(want) @ np.abs(v)
+        assert np.all(np.abs(y - want @ v) <= 1e-12 * bound + 1e-300), tag
+        L.close()
