@@ -345,29 +345,29 @@ def run_ours(args):
         kmv = pb.ExpQuad((D_MV,))
         if world > 1:
             sop = ShardedCovarianceOperator(kmv, xm, device=local_rank)
-        else:
-            if not dist.is_initialized():
-                os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-                os.environ.setdefault("MASTER_PORT", "29533")
-                dist.init_process_group("gloo", rank=0, world_size=1)
-            sop = ShardedCovarianceOperator(kmv, xm, device=local_rank)
+            local_op = sop.local
+            run_product = lambda: sop.matmul_device(v, out=y)  # noqa: E731
+        else:  # one GPU: the plain operator, no process group needed
+            sop = None
+            local_op = _lib.Operator(kmv._kernel_params(), np.ascontiguousarray(xm), None, device=local_rank)
+            run_product = lambda: local_op.matmul_device(v.data_ptr(), 1, 1, y.data_ptr(), 1, stream=stream)  # noqa: E731
         v = torch.from_numpy(np.random.default_rng(7).normal(size=(nm, 1))).to(dev)
         y = torch.empty((nm, 1), dtype=torch.float64, device=dev)
-        sop.matmul_device(v, out=y)
+        run_product()
         barrier()
         reps = 2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
         for _ in range(reps):
-            sop.matmul_device(v, out=y)
+            run_product()
         e1.record()
         barrier()
         launches += _lib.launch_count() - l0
         ms = max_over_ranks(e0.elapsed_time(e1) / reps)
         flop_per_pair = 3 * D_MV + 1 + 2  # 3d + 1 + 2K, FMA = 2
         extra["matvec"] = {
-            "kernel": sop.local.matmul_path(),
+            "kernel": local_op.matmul_path(),
             "workload": f"ExpQuad K.v, N={nm}, d={D_MV}, K=1, float64, row-sharded over {world} GPU(s) + all-gather",
             "ms": ms, "pairs_per_s": float(nm) * nm / (ms * 1e-3),
             "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,
@@ -383,7 +383,10 @@ def run_ours(args):
                 ach = extra["matvec"]["gflops"] / 1e3 / world
                 extra["matvec"]["roofline"] = {"bound": "fp64 pipe", "achieved": ach, "peak": dfma, "unit": "TFLOP/s",
                                                "frac": ach / dfma, "peak_source": "profiles/r01_microbench.json dfma_tflops_sustained"}
-        sop.close()
+        if sop is not None:
+            sop.close()
+        else:
+            local_op.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -409,6 +412,9 @@ def run_ours(args):
 
 
 def main():
+    # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; keep stdout to the one JSON line
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
