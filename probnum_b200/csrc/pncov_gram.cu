@@ -344,7 +344,9 @@ __global__ void __launch_bounds__(G_THREADS)
                         for (int i = 0; i < 16; ++i) {
                             const int c = cbase + i * 4 + (lane >> 3), ch = lane & 7;
                             const double2 v = mir[c * 8 + (ch ^ ((c >> 1) & 7))];
-                            __stcs(reinterpret_cast<double2*>(mrow + (size_t)c * row_stride + 2 * ch), v);
+                            // default (evict-normal) policy: measured 2.6 % faster than the streaming
+                            // hint for these scattered lines (evict-last is slower again)
+                            *reinterpret_cast<double2*>(mrow + (size_t)c * row_stride + 2 * ch) = v;
                         }
                         __syncwarp();
                     }

@@ -22,6 +22,19 @@ __device__ __forceinline__ double epi(double S, const PnEpiParams& P, const doub
     return PnEpilogue<PN_EPI_EXPQUAD, TAB>::fast(S, P, tab, nullptr, f);
 }
 
+// exp2 with all constants forced into registers (tests whether constant-bank operands slow DFMA)
+struct RegCoef { double cu, e1, e2, e3, magic; };
+__device__ __forceinline__ double epi_reg(double S, const RegCoef& C, const double* tab) {
+    double t = pn_fma(S, C.cu, C.magic);
+    int n = pn_lo(t);
+    double r = pn_fma(S, C.cu, C.magic - t);
+    double q = pn_fma(C.e3, r, C.e2);
+    q = pn_fma(q, r, C.e1);
+    double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tab) + ((n << 3) & ((PN_EXP2_N - 1) << 3)));
+    double res = pn_fma(T * r, q, T);
+    return pn_make(pn_hi(res) + ((n << (20 - PNCOV_EXP2_BITS)) & 0xfff00000), pn_lo(res));
+}
+
 // MODE 0: direct differences on raw points (ld = 8); MODE 1: identity, serial dot;
 // MODE 2: identity, dot split into two partial sums
 template <int THREADS, int R, int TJ, int TAB, int MODE, int C>
@@ -202,6 +215,8 @@ mma_kernel(const double* __restrict__ a12, const double* __restrict__ b12, const
     }
     for (int i = tid; i < PN_EXP2_N; i += THREADS) tabE[i] = pn_exp2_table_g[i];
     const int64_t row0 = (int64_t)blockIdx.x * (THREADS / 32 * RG * 8) + warp * (RG * 8);
+    RegCoef rc = {P.c_u, P.e1, P.e2, P.e3, PN_EXP2_MAGIC};
+    asm volatile("" : "+d"(rc.cu), "+d"(rc.e1), "+d"(rc.e2), "+d"(rc.e3), "+d"(rc.magic));
     double af[RG][2], nx[RG], acc[RG];
 #pragma unroll
     for (int rg = 0; rg < RG; ++rg) {
@@ -231,7 +246,7 @@ mma_kernel(const double* __restrict__ a12, const double* __restrict__ b12, const
 #pragma unroll
                 for (int rg = 0; rg < RG; ++rg) {
                     double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
-                    if (SPLITK) {
+                    if (SPLITK == 1) {
                         double d0 = 0.0, d1 = 0.0;
                         dmma884(c0, c1, af[rg][0], b0);
                         dmma884(d0, d1, af[rg][1], b1);
@@ -248,9 +263,14 @@ mma_kernel(const double* __restrict__ a12, const double* __restrict__ b12, const
                 const int j = jj + 8 * s;
                 PnFlags f; f.reset();
                 double K[2 * RG];
+                if (SPLITK == 2) {
+#pragma unroll
+                    for (int i = 0; i < 2 * RG; ++i) K[i] = epi_reg(S[s][i], rc, tabE);
+                } else {
 #pragma unroll
                 for (int i = 0; i < 2 * RG; ++i) K[i] = epi<0>(S[s][i], P, tabE, f);
-                if (f.flagged(P)) {
+                }
+                if (SPLITK != 2 && f.flagged(P)) {
 #pragma unroll
                     for (int i = 0; i < 2 * RG; ++i) K[i] = pn_epilogue(S[s][i], P, pn_exp2_table_g, pn_log2_table_g);
                 }
@@ -331,18 +351,11 @@ int main(int argc, char** argv) {
         run<128, 2, 64, 0, 2, 2>("identity split dot TJ=64", draw, da, db, dv, dy, n, ref);
         run<128, 4, 64, 0, 1, 2>("identity R=4", draw, da, db, dv, dy, n, ref);
     }
-    run_mma<128, 4, 128, 1, 0>("dmma shipping shape", da, db, dv, dy, n, ref);
-    run_mma<128, 4, 128, 2, 0>("dmma 16 columns per step", da, db, dv, dy, n, ref);
-    run_mma<128, 4, 128, 1, 1>("dmma split k", da, db, dv, dy, n, ref);
-    run_mma<128, 4, 128, 2, 1>("dmma 16 columns, split k", da, db, dv, dy, n, ref);
-    run_mma<256, 4, 128, 1, 0>("dmma 256 threads", da, db, dv, dy, n, ref);
-    run_mma<256, 4, 64, 1, 0>("dmma 256 threads TJ=64", da, db, dv, dy, n, ref);
-    run_mma<128, 2, 128, 2, 0>("dmma RG=2, 16 columns", da, db, dv, dy, n, ref);
-    run_mma<128, 2, 128, 4, 0>("dmma RG=2, 32 columns", da, db, dv, dy, n, ref);
-    run_mma<256, 2, 128, 2, 0>("dmma RG=2, 16 columns, 256 thr", da, db, dv, dy, n, ref);
-    run_mma<128, 6, 128, 1, 0>("dmma RG=6", da, db, dv, dy, n, ref);
-    run_mma<128, 8, 128, 1, 0>("dmma RG=8", da, db, dv, dy, n, ref);
-    run_mma<64, 4, 128, 1, 0>("dmma 64 threads", da, db, dv, dy, n, ref);
-    run_mma<64, 8, 128, 1, 0>("dmma 64 threads RG=8", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 2, 0>("dmma NS=2 (shipping)", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 2, 2>("dmma NS=2, constants in registers, no flags", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 4, 0>("dmma NS=4", da, db, dv, dy, n, ref);
+    run_mma<128, 4, 128, 4, 2>("dmma NS=4, register constants", da, db, dv, dy, n, ref);
+    run_mma<128, 2, 128, 4, 2>("dmma RG=2 NS=4, register constants", da, db, dv, dy, n, ref);
+    run_mma<256, 2, 128, 4, 2>("dmma RG=2 NS=4 256thr, register constants", da, db, dv, dy, n, ref);
     return 0;
 }
