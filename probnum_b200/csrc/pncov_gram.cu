@@ -220,32 +220,19 @@ __global__ void __launch_bounds__(G_THREADS)
 // Preconditions (checked by the launcher): n0 % G_TM == 0, n1 % G_TN == 0, rows of the
 // output 16-byte aligned.  Nothing in the loop is predicated; the column points of the
 // thread's two columns live in registers; the output pointer advances by one row stride.
-//
-// SYM (x1 is x0, square interior): the output is symmetric and K[i][j] is computed by the
-// very same instruction sequence as K[j][i] (the differences only change sign), so a CTA
-// whose row tile lies strictly above the diagonal 512 x 512 super-tile also stores the
-// transposed tile, and CTAs below the diagonal super-tile exit at once.  FP64 work per
-// stored entry halves, which moves Matern / general RatQuad from FP64-bound to HBM-bound.
-// The transposed tile goes through shared memory (16 rows x 512 columns, XOR-swizzled 16-byte
-// chunks, conflict-free both ways) so that every mirrored row leaves as a full 128-byte
-// line; direct 32-byte mirror stores were measured at half the DRAM efficiency.
-template <int D, bool ARD, int EPI, bool SYM>
+template <int D, bool ARD, int EPI>
 __global__ void __launch_bounds__(G_THREADS)
     gram_fast_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages, [2]: tables
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
     double* x0s = reinterpret_cast<double*>(smem + G_HDR_BYTES);  // [2][D][G_TM]
-    // SYM only: transposed staging, [G_TN columns][8 chunks of 2 rows], chunk index swizzled
-    double2* mir = reinterpret_cast<double2*>(smem + G_HDR_BYTES + 2 * D * G_TM * 8);
 
     const int n_tiles = (int)(g.n0 / G_TM);
     const int t0 = blockIdx.y * tiles_per_cta;
-    int t1 = min(t0 + tiles_per_cta, n_tiles);
-    // SYM: rows below this strip's diagonal super-tile are produced by mirror stores
-    if constexpr (SYM) t1 = min(t1, (int)(blockIdx.x + 1) * (G_TN / G_TM));
+    const int t1 = min(t0 + tiles_per_cta, n_tiles);
     if (t0 >= t1) return;
     const int64_t j0 = (int64_t)blockIdx.x * G_TN + 2 * tid;
     const double* x0g = static_cast<const double*>(g.x0_soa);
@@ -255,6 +242,7 @@ __global__ void __launch_bounds__(G_THREADS)
     if (tid == 0) {
         pn_mbar_init(&bars[0], 1);
         pn_mbar_init(&bars[1], 1);
+        pn_mbar_init(&bars[2], 1);
         pn_mbar_fence_init();
     }
     __syncthreads();
@@ -263,8 +251,8 @@ __global__ void __launch_bounds__(G_THREADS)
 #pragma unroll
         for (int m = 0; m < D; ++m)
             pn_bulk_g2s(x0s + m * G_TM, x0g + (size_t)m * g.ld0 + (size_t)t0 * G_TM, G_TM * 8, &bars[0]);
+        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
     }
-    pn_stage_tables(tabE, tabL, tid, G_THREADS);
 
     double xb0[D], xb1[D], sc[D];
 #pragma unroll
@@ -276,10 +264,7 @@ __global__ void __launch_bounds__(G_THREADS)
     }
     double* optr = static_cast<double*>(g.out) + (size_t)t0 * G_TM * g.ldo + j0;
     const size_t row_stride = (size_t)g.ldo;
-    // mirrored block of this strip: rows = the strip's columns, columns = this CTA's rows
-    double* mbase = static_cast<double*>(g.out) + (size_t)blockIdx.x * G_TN * g.ldo;
-    const int t_diag = (int)blockIdx.x * (G_TN / G_TM);  // first row tile of the diagonal super-tile
-    __syncthreads();
+    pn_mbar_wait(&bars[2], 0);
 
     int it = 0;
     for (int t = t0; t < t1; ++t, ++it) {
@@ -323,37 +308,155 @@ __global__ void __launch_bounds__(G_THREADS)
                 pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
                 optr += row_stride;
             }
-            if constexpr (SYM) {
-                if (t < t_diag) {  // uniform per tile
-                    const int q = (rg >> 2) & 3;  // which 4-row group of the 16-row staging block
-                    const int sw = tid & 7;       // swizzle key: (local column >> 1) & 7
-                    double2* c0 = mir + (2 * tid) * 8;
-                    double2* c1 = c0 + 8;
-                    c0[(2 * q) ^ sw] = make_double2(K[0], K[2]);
-                    c0[(2 * q + 1) ^ sw] = make_double2(K[4], K[6]);
-                    c1[(2 * q) ^ sw] = make_double2(K[1], K[3]);
-                    c1[(2 * q + 1) ^ sw] = make_double2(K[5], K[7]);
-                    if (q == 3) {
-                        // a warp's 32 lanes own 64 adjacent columns, so the 64 staged columns it
-                        // just wrote are its own: warp-level sync is enough, no CTA barrier
-                        __syncwarp();
-                        const int lane = tid & 31;
-                        const int cbase = (tid >> 5) * 64;
-                        double* mrow = mbase + (size_t)t * G_TM + (rg - 12);
-#pragma unroll 4
-                        for (int i = 0; i < 16; ++i) {
-                            const int c = cbase + i * 4 + (lane >> 3), ch = lane & 7;
-                            const double2 v = mir[c * 8 + (ch ^ ((c >> 1) & 7))];
-                            // default (evict-normal) policy: measured 2.6 % faster than the streaming
-                            // hint for these scattered lines (evict-last is slower again)
-                            *reinterpret_cast<double2*>(mrow + (size_t)c * row_stride + 2 * ch) = v;
-                        }
-                        __syncwarp();
-                    }
+        }
+        __syncthreads();  // everyone is done with x0 stage `buf` before it is refilled
+    }
+}
+
+// ---- symmetric kernel: x1 is x0, square interior on the 64 grid ---------------------------------
+// Only tiles on or above the diagonal are computed; every tile strictly above it is also stored
+// transposed.  K[i][j] and K[j][i] come from the very same instruction sequence (the differences
+// only change sign), so the result is bit-identical to the general kernel.  FP64 work per stored
+// entry halves, which moves Matern / general RatQuad from FP64-pipe-bound to HBM-bound.
+//
+// The DRAM side wants LONG contiguous runs in both directions (measured: scattered 128-byte
+// lines of a mirrored half cost 20 % of the launch, 512-byte runs cost nothing), so the CTA tile
+// is 64 x 64: a warp owns 8 rows of it (two 4-row register tiles over the warp's 64 columns, two
+// columns per lane), direct rows leave as one 512-byte STG.128 per warp, the tile is staged
+// transposed in XOR-swizzled shared memory (conflict-free both ways), and after ONE CTA barrier
+// per tile (the staging buffer is double-buffered) each warp writes 8 mirrored rows, again as one
+// 512-byte STG.128 per row.
+constexpr int Y_T = 64;                               // tile edge
+constexpr int Y_STAGE_BYTES = Y_T * Y_T * 8;          // one transposed tile
+template <int D, bool ARD, int EPI>
+__global__ void __launch_bounds__(G_THREADS, 2)
+    gram_sym_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    double* x0s = reinterpret_cast<double*>(smem + G_HDR_BYTES);  // [2][D][Y_T]
+    // transposed staging: [2 buffers][64 columns][32 chunks of 2 rows], chunk index ^ ((column >> 1) & 7)
+    double2* mir = reinterpret_cast<double2*>(smem + G_HDR_BYTES + 2 * D * Y_T * 8);
+
+    const int t_diag = (int)blockIdx.x;  // the strip's diagonal tile
+    const int t0 = blockIdx.y * tiles_per_cta;
+    const int t1 = min(t0 + tiles_per_cta, t_diag + 1);
+    if (t0 >= t1) return;
+    const int64_t c0 = (int64_t)blockIdx.x * Y_T;
+    const double* xg = static_cast<const double*>(g.x0_soa);
+    constexpr uint32_t TILE_BYTES = D * Y_T * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_init(&bars[2], 1);  // tables
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], TILE_BYTES);
+#pragma unroll
+        for (int m = 0; m < D; ++m)
+            pn_bulk_g2s(x0s + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)t0 * Y_T, Y_T * 8, &bars[0]);
+        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
+    }
+
+    double xb0[D], xb1[D], sc[D];
+#pragma unroll
+    for (int m = 0; m < D; ++m) {
+        const double2 t = *reinterpret_cast<const double2*>(xg + (size_t)m * g.ld0 + c0 + 2 * lane);
+        xb0[m] = t.x;
+        xb1[m] = t.y;
+        if constexpr (ARD) sc[m] = static_cast<const double*>(g.scale)[m];
+    }
+    const size_t row_stride = (size_t)g.ldo;
+    // direct: row (t * 64 + 8 * warp + r), columns c0 + 2 * lane
+    double* optr = static_cast<double*>(g.out) + ((size_t)t0 * Y_T + 8 * warp) * row_stride + c0 + 2 * lane;
+    // mirrored: row (c0 + 8 * warp + i), columns t * 64 + 2 * lane
+    double* mptr = static_cast<double*>(g.out) + ((size_t)c0 + 8 * warp) * row_stride + (size_t)t0 * Y_T + 2 * lane;
+    const int sw = lane & 7;  // swizzle key of this lane's columns: ((2 * lane) >> 1) & 7
+    pn_mbar_wait(&bars[2], 0);
+
+    int it = 0;
+    for (int t = t0; t < t1; ++t, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && t + 1 < t1) {
+            double* dst = x0s + (buf ^ 1) * (D * Y_T);
+            pn_mbar_expect_tx(&bars[buf ^ 1], TILE_BYTES);
+#pragma unroll
+            for (int m = 0; m < D; ++m)
+                pn_bulk_g2s(dst + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)(t + 1) * Y_T, Y_T * 8, &bars[buf ^ 1]);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* x0t = x0s + buf * (D * Y_T) + 8 * warp;
+        double2* stage = mir + buf * (Y_T * 32);
+        const double2* prev = mir + (buf ^ 1) * (Y_T * 32);  // transposed tile t - 1 (always a mirrored one)
+        double2* s0 = stage + (2 * lane) * 32;  // this lane's first column
+        double2* s1 = s0 + 32;
+        const bool mirror = t < t_diag;  // uniform per tile
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            // mirrored rows of the previous tile, spread over this tile's arithmetic so that the
+            // stores leave the SM as a steady stream rather than a burst after the barrier
+            if (it > 0) {
+#pragma unroll
+                for (int i = 4 * h; i < 4 * h + 4; ++i) {
+                    const int c = 8 * warp + i;
+                    const double2 v = prev[c * 32 + (lane ^ ((c >> 1) & 7))];
+                    pn_store_cs2(mptr + (size_t)i * row_stride, v.x, v.y);
                 }
             }
+            double S[2 * G_R];
+#pragma unroll
+            for (int i = 0; i < 2 * G_R; ++i) S[i] = 0.0;
+#pragma unroll
+            for (int m = 0; m < D; ++m) {
+                const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + 4 * h);
+                const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * Y_T + 4 * h + 2);
+                const double xa[G_R] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                for (int r = 0; r < G_R; ++r) {
+                    double da = xa[r] - xb0[m];
+                    double db = xa[r] - xb1[m];
+                    if constexpr (ARD) {
+                        da *= sc[m];
+                        db *= sc[m];
+                    }
+                    S[2 * r] = pn_fma(da, da, S[2 * r]);
+                    S[2 * r + 1] = pn_fma(db, db, S[2 * r + 1]);
+                }
+            }
+            double K[2 * G_R];
+            epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+#pragma unroll
+            for (int r = 0; r < G_R; ++r) {
+                pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
+                optr += row_stride;
+            }
+            if (mirror) {
+                const int k = 4 * warp + 2 * h;  // chunk (row pair) index of rows 8 * warp + 4 * h
+                s0[k ^ sw] = make_double2(K[0], K[2]);
+                s0[(k + 1) ^ sw] = make_double2(K[4], K[6]);
+                s1[k ^ sw] = make_double2(K[1], K[3]);
+                s1[(k + 1) ^ sw] = make_double2(K[5], K[7]);
+            }
         }
+        optr += (size_t)(Y_T - 8) * row_stride;
+        if (it > 0) mptr += Y_T;
+        // staging buffer `buf` is complete and buffer buf^1 (tile t-1) has been drained by everyone;
+        // also orders this tile's reads of x0 stage `buf` before its refill two iterations on
         __syncthreads();
+    }
+    if (t1 - 1 < t_diag) {  // the last tile of this CTA was a mirrored one: drain it
+        const double2* prev = mir + ((it - 1) & 1) * (Y_T * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = 8 * warp + i;
+            const double2 v = prev[c * 32 + (lane ^ ((c >> 1) & 7))];
+            pn_store_cs2(mptr + (size_t)i * row_stride, v.x, v.y);
+        }
     }
 }
 
@@ -433,19 +536,27 @@ cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
     const int64_t n_tiles = g.n0 / G_TM;
     int64_t tpc = (n_tiles * strips) / (148 * 48);
     tpc = tpc < 1 ? 1 : (tpc > 32 ? 32 : tpc);
-    if (g.symmetric) tpc = tpc > 4 ? 4 : tpc;  // finer row chunks: half of the grid exits at once
     const int64_t gy = (n_tiles + tpc - 1) / tpc;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
-    size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * G_TM;
+    const size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * G_TM;
     dim3 grid((unsigned)strips, (unsigned)gy);
-    if (g.symmetric) {
-        smem += (size_t)G_TN * 8 * sizeof(double2);  // 64 KB transposed staging
-        auto kern = gram_fast_kernel<D, ARD, EPI, true>;
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
-    } else
-        gram_fast_kernel<D, ARD, EPI, false><<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
+    gram_fast_kernel<D, ARD, EPI><<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int D, bool ARD, int EPI>
+cudaError_t launch_sym_inst(const PnGramLaunch& g, cudaStream_t stream) {
+    const int64_t n_tiles = g.n0 / Y_T;
+    const int64_t tpc = 16;  // row tiles per CTA: amortises the prologue; 8..32 measured within 3 %
+    const int64_t gy = (n_tiles + tpc - 1) / tpc;
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    const size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * Y_T + 2 * Y_STAGE_BYTES;
+    auto kern = gram_sym_kernel<D, ARD, EPI>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    dim3 grid((unsigned)n_tiles, (unsigned)gy);
+    kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
     ++g_pn_launches;
     return cudaGetLastError();
 }
@@ -454,13 +565,23 @@ template <int D, bool ARD>
 cudaError_t launch_fast_epi(const PnGramLaunch& g, cudaStream_t stream) {
     switch (g.epi.epi) {
         case PN_EPI_EXPQUAD: return launch_fast_inst<D, ARD, PN_EPI_EXPQUAD>(g, stream);
-        case PN_EPI_MATERN0: return launch_fast_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
-        case PN_EPI_MATERN1: return launch_fast_inst<D, ARD, PN_EPI_MATERN1>(g, stream);
-        case PN_EPI_MATERN2: return launch_fast_inst<D, ARD, PN_EPI_MATERN2>(g, stream);
-        case PN_EPI_MATERNP: return launch_fast_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
+        case PN_EPI_MATERN0:
+            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
+            return launch_fast_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
+        case PN_EPI_MATERN1:
+            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN1>(g, stream);
+            return launch_fast_inst<D, ARD, PN_EPI_MATERN1>(g, stream);
+        case PN_EPI_MATERN2:
+            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN2>(g, stream);
+            return launch_fast_inst<D, ARD, PN_EPI_MATERN2>(g, stream);
+        case PN_EPI_MATERNP:
+            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
+            return launch_fast_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
         case PN_EPI_RATQUAD1: return launch_fast_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
         case PN_EPI_RATQUAD2: return launch_fast_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
-        default: return launch_fast_inst<D, false, PN_EPI_RATQUADG>(g, stream);
+        default:
+            if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUADG>(g, stream);
+            return launch_fast_inst<D, false, PN_EPI_RATQUADG>(g, stream);
     }
 }
 
@@ -540,16 +661,19 @@ static cudaError_t launch_generic(const PnGramLaunch& g, cudaStream_t stream) {
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
     if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
     const bool aligned = (g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
-    const int64_t n0i = (g.n0 / G_TM) * G_TM, n1i = (g.n1 / G_TN) * G_TN;  // interior extent
+    int64_t n0i = (g.n0 / G_TM) * G_TM, n1i = (g.n1 / G_TN) * G_TN;  // interior extent
+    // mirror stores pay only where the FP64 pipe, not HBM, limits the general kernel
+    const bool fp64_heavy = g.epi.epi != PN_EPI_EXPQUAD && g.epi.epi != PN_EPI_RATQUAD1 && g.epi.epi != PN_EPI_RATQUAD2;
+    const bool sym = g.symmetric && fp64_heavy && g.n0 == g.n1 && g.x0_soa == g.x1_soa && !g.in_f32 && g.d <= 8 &&
+                     aligned && g.n0 >= 4 * Y_T;
+    if (sym) n0i = n1i = (g.n0 / Y_T) * Y_T;  // the symmetric kernel works on the 64 grid
     if (g.in_f32 || g.d > 8 || !aligned || n0i == 0 || n1i == 0) return launch_generic(g, stream);
     // interior: whole 64-row tiles x whole 512-column strips, unpredicated specialised kernel
     PnGramLaunch in = g;
     in.n0 = n0i;
     in.n1 = n1i;
-    // mirror stores pay only where the FP64 pipe, not HBM, limits the general kernel
-    const bool fp64_heavy = g.epi.epi != PN_EPI_EXPQUAD && g.epi.epi != PN_EPI_RATQUAD1 && g.epi.epi != PN_EPI_RATQUAD2;
-    in.symmetric = (g.symmetric && fp64_heavy && g.n0 == g.n1 && g.x0_soa == g.x1_soa) ? 1 : 0;
-    if (in.symmetric) in.n0 = n1i;  // square interior on the 512 grid; the rest goes to the edge launches
+    in.symmetric = sym ? 1 : 0;
+    if (in.symmetric) in.n0 = n1i;  // square interior; the rest goes to the edge launches
     const int64_t n0_done = in.n0;
     cudaError_t err = g.scale ? launch_fast<true>(in, stream) : launch_fast<false>(in, stream);
     if (err != cudaSuccess) return err;

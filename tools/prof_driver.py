@@ -24,7 +24,9 @@ if what in ("gram", "all"):
     x1 = torch.from_numpy(rng.normal(size=(n, 3))).to(dev) if os.environ.get("PROF_CROSS") else None
     out = torch.empty((n, n), dtype=torch.float64, device=dev)
     kernels = (pb.ExpQuad((3,)), pb.Matern((3,), nu=2.5), pb.RatQuad((3,)), pb.RatQuad((3,), alpha=1.5))
-    for k in kernels[:2] if reps == 1 else kernels:
+    sel = os.environ.get("PROF_KERNELS")  # e.g. "1,3": indices into `kernels`
+    chosen = [kernels[int(i)] for i in sel.split(",")] if sel else (kernels[:2] if reps == 1 else kernels)
+    for k in chosen:
         op = _lib.Operator(k._kernel_params(), x.data_ptr(), None if x1 is None else x1.data_ptr(), on_device=True, n0=n, n1=n, dtype=np.float64)
         for _ in range(reps):
             op.gram_device(out.data_ptr(), n, stream=stream)
