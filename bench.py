@@ -2,7 +2,7 @@
 """Benchmark of the covariance hot path (BASELINE.json metric and configs).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
+    python bench.py --impl reference --gpus N --steps K ...   # the reference itself on host cores
 
 One "step" is one pass of the hot path over BASELINE.json configs[1]: the dense float64
 Gram matrices of Matern-5/2 AND RatQuad over N = 32768 points in d = 3 (2 * N^2 entries,
@@ -133,6 +133,30 @@ def _oracle_specs():
             orc.KernelSpec("ratquad", (D_GRAM,), 1.0, alpha=1.0)]
 
 
+def _import_reference():
+    """The unmodified reference (pip-installed into baseline/_ref, which travels to the GPU box),
+    or None.  Only the four NumPy-2 aliases of SURVEY.md 8c are added before the import."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "probnum")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    for name, val in (("float_", np.float64), ("Inf", np.inf),
+                      ("find_common_type", lambda a, s: np.result_type(*a, *s)),
+                      ("AxisError", np.exceptions.AxisError)):
+        if not hasattr(np, name):
+            setattr(np, name, val)
+    try:
+        import warnings  # noqa: PLC0415
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from probnum.randprocs import covfuncs  # noqa: PLC0415
+        return covfuncs
+    except Exception:  # noqa: BLE001 - any import problem means "not available"
+        return None
+
+
 def _cpu_rows(args):
     """Worker: both Gram kernels for rows [lo, hi) against all N points (oracle)."""
     lo, hi, n = args
@@ -142,6 +166,17 @@ def _cpu_rows(args):
     t0 = time.perf_counter()
     for spec in _oracle_specs():
         orc.gram(spec, x[lo:hi], x, row_block=512)
+    return time.perf_counter() - t0
+
+
+def _ref_rows(args):
+    """Worker: the same rows through the reference's own ``CovarianceFunction.matrix``."""
+    lo, hi, n = args
+    cf = _import_reference()
+    x = np.random.default_rng(42).normal(size=(n, D_GRAM))
+    t0 = time.perf_counter()
+    for k in (cf.Matern((D_GRAM,), nu=2.5), cf.RatQuad((D_GRAM,))):
+        k.matrix(x[lo:hi], x)
     return time.perf_counter() - t0
 
 
@@ -157,8 +192,9 @@ def cpu_baseline_sample(n: int, rows: int = 2048):
 
 
 def run_reference(args):
-    """--impl reference: the reference algorithm (oracle port; the reference is pure Python
-    and cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path on all host cores, bounded
+    sample per step.  Uses the unmodified reference from baseline/_ref (kind "reference") when it
+    is importable, else the oracle port (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -170,15 +206,19 @@ def run_reference(args):
     rows_per_worker = 256
     jobs = [(w * rows_per_worker, (w + 1) * rows_per_worker, n) for w in range(workers)]
     entries_per_step = 2.0 * workers * rows_per_worker * n
+    have_ref = _import_reference() is not None
+    worker, kind = (_ref_rows, "reference") if have_ref else (_cpu_rows, "port")
+    what = ("probnum (unmodified, baseline/_ref) CovarianceFunction.matrix" if have_ref
+            else "oracle port (NumPy restatement of the reference)")
     with mp.get_context("fork").Pool(workers) as pool:
         for _ in range(args.warmup):
-            pool.map(_cpu_rows, jobs)
+            pool.map(worker, jobs)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_cpu_rows, jobs)
+            pool.map(worker, jobs)
         dt = time.perf_counter() - t0
     value = entries_per_step * args.steps / dt
-    sample = (f"oracle port, {workers} processes x {rows_per_worker} rows x {n} columns of the Matern-5/2 "
+    sample = (f"{what}, {workers} processes x {rows_per_worker} rows x {n} columns of the Matern-5/2 "
               f"and RatQuad Gram matrices per step ({entries_per_step:.3g} entries/step)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -187,7 +227,7 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={D_GRAM}, float64 (BASELINE configs[1])",
                    "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -288,7 +328,8 @@ def run_ours(args):
         with open(tpath) as fh:
             traffic = json.load(fh).get("gram_fast_kernel_bytes_per_launch")
     roofline = {
-        "bound": "hbm", "kernel": f"gram_fast_kernel<D=3, {dom}" + (", SYM (mirror stores)>" if dom == "matern52" else ">"),
+        "bound": "hbm", "kernel": (f"gram_sym_kernel<D=3, {dom}> (upper triangle + mirrored stores)" if dom == "matern52"
+                                    else f"gram_fast_kernel<D=3, {dom}>"),
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
         "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, copy read+write)",
         "algorithmic_bytes_per_launch": alg_bytes,

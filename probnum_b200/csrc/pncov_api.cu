@@ -316,6 +316,14 @@ int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, 
         }
     }
     k.epi.c_su = k.epi.c_s * k.epi.c_u;
+    if (kind == PNCOV_MATERN) {
+        // the device evaluates the polynomial in r0 = sqrt(S) (r = c_s r0): fold c_s^i into c_i
+        long double pw = 1.0L;
+        for (int i = 1; i <= k.epi.p; ++i) {
+            pw *= (long double)k.epi.c_s;
+            k.epi.coef[i] = (double)((long double)k.epi.coef[i] * pw);
+        }
+    }
     fill_window(k.epi);
     return 0;
 }

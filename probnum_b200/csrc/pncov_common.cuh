@@ -28,7 +28,7 @@ struct PnEpiParams {
     double c_s;      // MATERN: s (isotropic) or 1 (ARD), multiplies sqrt(S); RATQUAD: 1/(2 alpha l^2)
     double c_su;     // MATERN0: c_s * c_u
     double alpha;    // RATQUADG
-    double coef[PN_MAX_P + 1];  // MATERNP polynomial coefficients, degree i at index i
+    double coef[PN_MAX_P + 1];  // MATERN: coefficients of the polynomial in r0 = sqrt(S): c_i * c_s^i, degree i at index i
     // polynomial coefficients of pn_exp2 / pn_log2, carried in the kernel-parameter constant
     // bank so that every use is a c[0x0][..] operand instead of two UMOVs (see profiles/r01)
     double e1, e2, e3;
@@ -82,21 +82,14 @@ static __device__ __noinline__ double pn_epilogue(double S, const PnEpiParams& P
             return pn_exp2(S * P.c_u, tabE);
         case PN_EPI_MATERN0:
             return pn_exp2(pn_sqrt(S) * P.c_su, tabE);
-        case PN_EPI_MATERN1: {
-            double r = pn_sqrt(S) * P.c_s;
-            double e = pn_exp2(r * P.c_u, tabE);
-            return pn_fma(r, e, e);
-        }
-        case PN_EPI_MATERN2: {
-            double r = pn_sqrt(S) * P.c_s;
-            double e = pn_exp2(r * P.c_u, tabE);
-            return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
-        }
+        case PN_EPI_MATERN1:
+        case PN_EPI_MATERN2:
         case PN_EPI_MATERNP: {
-            double r = pn_sqrt(S) * P.c_s;
-            double e = pn_exp2(r * P.c_u, tabE);
+            // coef[] holds the Horner coefficients in the variable r0 = sqrt(S): c_i * c_s^i
+            double r0 = pn_sqrt(S);
+            double e = pn_exp2(r0 * P.c_su, tabE);
             double poly = P.coef[P.p];
-            for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
+            for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r0, P.coef[i]);
             return poly * e;
         }
         case PN_EPI_RATQUAD1:
@@ -219,19 +212,18 @@ struct PnEpilogue {
         } else if constexpr (EPI >= PN_EPI_MATERN0 && EPI <= PN_EPI_MATERNP) {
             double r0 = pn_sqrt_core(S);
             double e = exp2_prod(r0, P.c_su, P, tabE);
+            // The scale c_s of r = c_s r0 is folded into the coefficients on the host
+            // (coef[i] = c_i c_s^i, coef[0] = 1): one FP64 instruction less per entry.
             if constexpr (EPI == PN_EPI_MATERN0) {
                 return e;
+            } else if constexpr (EPI == PN_EPI_MATERN1) {
+                return pn_fma(r0, P.coef[1], 1.0) * e;
+            } else if constexpr (EPI == PN_EPI_MATERN2) {
+                return pn_fma(pn_fma(r0, P.coef[2], P.coef[1]), r0, 1.0) * e;
             } else {
-                double r = r0 * P.c_s;
-                if constexpr (EPI == PN_EPI_MATERN1) {
-                    return pn_fma(r, e, e);
-                } else if constexpr (EPI == PN_EPI_MATERN2) {
-                    return pn_fma(pn_fma(r, 1.0 / 3.0, 1.0), r, 1.0) * e;
-                } else {
-                    double poly = P.coef[P.p];
-                    for (int i = P.p - 1; i >= 0; --i) poly = pn_fma(poly, r, P.coef[i]);
-                    return poly * e;
-                }
+                double poly = P.coef[P.p];
+                for (int i = P.p - 1; i >= 1; --i) poly = pn_fma(poly, r0, P.coef[i]);
+                return pn_fma(poly, r0, 1.0) * e;
             }
         } else {
             double b = pn_fma(S, P.c_s, 1.0);
