@@ -44,6 +44,20 @@ extern "C" {
 #define PNCOV_MATERN 1 /* nu = p + 1/2, p = 0..PNCOV_MAX_MATERN_P */
 #define PNCOV_RATQUAD 2
 
+/* Non-isotropic families, float64 points, dense Gram and elementwise evaluation
+ * only (pncov_matmul returns PNCOV_ENOTIMPL for them).  They reuse pncov_create's arguments:
+ *   PNCOV_LINEAR          k = <x0, x1> + c            alpha = c                 (_linear.py:44-50)
+ *   PNCOV_POLYNOMIAL      k = (<x0, x1> + c)^q        alpha = c, nu = q in {0..64}  (_polynomial.py:50-56)
+ *   PNCOV_WHITENOISE      k = sigma^2 [x0 == x1]      alpha = sigma^2           (_white_noise.py:38-55)
+ *   PNCOV_PRODUCT_MATERN  k = prod_m Matern_{nu_m}(|x0_m - x1_m| / l_m)
+ *                         lengthscales = [l_0 .. l_{d-1}, nu_0 .. nu_{d-1}], n_lengthscales = 2 d
+ *                         (_product_matern.py:60-122)
+ * lengthscales may be NULL (n_lengthscales 0) for the first three. */
+#define PNCOV_LINEAR 3
+#define PNCOV_POLYNOMIAL 4
+#define PNCOV_WHITENOISE 5
+#define PNCOV_PRODUCT_MATERN 6
+
 #define PNCOV_F64 0
 #define PNCOV_F32 1
 
@@ -129,6 +143,24 @@ PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int
 PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const double* lengthscales,
                 int64_t n_lengthscales, double nu, double alpha, const void* x0, const void* x1,
                 int64_t b, void* out);
+
+/* covariance arithmetic on device-resident Gram matrices --------------------------------
+ * replaces ScaledCovarianceFunction / SumCovarianceFunction / ProductCovarianceFunction._evaluate
+ * (randprocs/covfuncs/_arithmetic_fallbacks.py:55-56, :101-104, :163-166), which combine full
+ * host matrices with NumPy: the operands are built with pncov_gram_device into buffers from
+ * pncov_device_alloc, combined in place, and only the result crosses PCIe.
+ *   pncov_combine_device   n float64 elements, 16-byte aligned buffers on `device`, asynchronous on `stream`
+ *       PNCOV_COMBINE_LINEAR    dst = alpha * dst + beta * src   (src may be NULL when beta == 0)
+ *       PNCOV_COMBINE_MULTIPLY  dst = dst * src
+ *   pncov_copy_to_host     device -> host copy of the result, ordered after `stream`, blocking
+ */
+#define PNCOV_COMBINE_LINEAR 0
+#define PNCOV_COMBINE_MULTIPLY 1
+PNCOV_API int pncov_device_alloc(int device, void** ptr, int64_t nbytes);
+PNCOV_API int pncov_device_free(int device, void* ptr);
+PNCOV_API int pncov_copy_to_host(int device, void* dst_host, const void* src_device, int64_t nbytes, void* stream);
+PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64_t n, int op, double alpha,
+                                   double beta, void* stream);
 
 /* diagnostics ------------------------------------------------------------------------
  * number of kernel launches issued by this library in the calling process, and the

@@ -13,7 +13,9 @@ kernels behind the C ABI of ``include/pncov.h``.  See DESIGN.md.
 """
 
 from . import covfuncs, linops
-from .covfuncs import CovarianceFunction, CovarianceLinearOperator, ExpQuad, Matern, RatQuad
+from .covfuncs import (CovarianceFunction, CovarianceLinearOperator, ExpQuad, Linear, Matern, Polynomial,
+                       ProductCovarianceFunction, ProductMatern, RatQuad, ScaledCovarianceFunction,
+                       SumCovarianceFunction, WhiteNoise)
 
 __all__ = [
     "covfuncs",
@@ -23,5 +25,12 @@ __all__ = [
     "ExpQuad",
     "Matern",
     "RatQuad",
+    "Linear",
+    "Polynomial",
+    "WhiteNoise",
+    "ProductMatern",
+    "ScaledCovarianceFunction",
+    "SumCovarianceFunction",
+    "ProductCovarianceFunction",
 ]
 __version__ = "0.1.0"

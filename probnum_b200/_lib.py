@@ -18,6 +18,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpncov.so")
 
 EXPQUAD, MATERN, RATQUAD = 0, 1, 2
+LINEAR, POLYNOMIAL, WHITENOISE, PRODUCT_MATERN = 3, 4, 5, 6
+COMBINE_LINEAR, COMBINE_MULTIPLY = 0, 1
 F64, F32 = 0, 1
 MAX_MATERN_P = 8
 
@@ -50,6 +52,11 @@ SIGNATURES = {
         [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64, ctypes.c_double,
          ctypes.c_double, _c_vp, _c_vp, _c_i64, _c_vp],
     ),
+    "pncov_device_alloc": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_c_vp), _c_i64]),
+    "pncov_device_free": (ctypes.c_int, [ctypes.c_int, _c_vp]),
+    "pncov_copy_to_host": (ctypes.c_int, [ctypes.c_int, _c_vp, _c_vp, _c_i64, _c_vp]),
+    "pncov_combine_device": (
+        ctypes.c_int, [ctypes.c_int, _c_vp, _c_vp, _c_i64, ctypes.c_int, ctypes.c_double, ctypes.c_double, _c_vp]),
     "pncov_launch_count": (_c_i64, []),
     "pncov_matmul_path": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_int)]),
     "pncov_last_kernel_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -132,12 +139,20 @@ class KernelParams:
     def __init__(self, kind: int, d: int, lengthscales, nu: float = 0.5, alpha: float = 1.0):
         self.kind = int(kind)
         self.d = int(d)
-        self.lengthscales = np.ascontiguousarray(np.atleast_1d(lengthscales), dtype=np.float64)
+        self.lengthscales = np.ascontiguousarray(
+            np.atleast_1d(lengthscales if lengthscales is not None else np.empty(0)), dtype=np.float64)
         self.nu = float(nu)
         self.alpha = float(alpha)
 
     def _ls(self):
+        if self.lengthscales.size == 0:
+            return None, 0
         return self.lengthscales.ctypes.data_as(_c_dp), self.lengthscales.size
+
+    @property
+    def matrix_free(self) -> bool:
+        """Whether pncov_matmul serves this family (the isotropic kernels only)."""
+        return self.kind in (EXPQUAD, MATERN, RATQUAD)
 
 
 class Operator:
@@ -261,3 +276,46 @@ def pairs(params: KernelParams, x0: np.ndarray, x1: np.ndarray, device: Optional
                            _dtype_code(x0.dtype), params.d, ls, nls, params.nu, params.alpha,
                            _ptr(x0), _ptr(x1), x0.shape[0], _ptr(out)))
     return out
+
+
+# -- device buffers and covariance arithmetic (include/pncov.h, "covariance arithmetic") ------------
+class DeviceBuffer:
+    """``nbytes`` of device memory on one GPU, freed on close / garbage collection."""
+
+    def __init__(self, nbytes: int, device: Optional[int] = None):
+        self.device = default_device() if device is None else int(device)
+        self.nbytes = int(nbytes)
+        p = _c_vp()
+        _check(load().pncov_device_alloc(self.device, ctypes.byref(p), self.nbytes))
+        self.ptr = int(p.value or 0)
+
+    def close(self) -> None:
+        if getattr(self, "ptr", 0):
+            load().pncov_device_free(self.device, _c_vp(self.ptr))
+            self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def to_host(self, out: np.ndarray, stream: int = 0) -> np.ndarray:
+        if not out.flags.c_contiguous or out.nbytes > self.nbytes:
+            raise ValueError("to_host needs a C-contiguous array no larger than the buffer")
+        _check(load().pncov_copy_to_host(self.device, _ptr(out), _c_vp(self.ptr), out.nbytes, _c_vp(stream)))
+        return out
+
+
+def combine(dst: DeviceBuffer, src: Optional[DeviceBuffer], n: int, op: int, alpha: float = 1.0,
+            beta: float = 1.0, stream: int = 0) -> None:
+    """``dst = alpha * dst + beta * src`` (COMBINE_LINEAR) or ``dst *= src`` (COMBINE_MULTIPLY) over
+    ``n`` float64 elements on the device."""
+    _check(load().pncov_combine_device(dst.device, _c_vp(dst.ptr), None if src is None else _c_vp(src.ptr),
+                                       int(n), int(op), float(alpha), float(beta), _c_vp(stream)))

@@ -176,10 +176,16 @@ class CovarianceFunction(abc.ABC):
         """(N,) + input_shape -> C-contiguous (N, d) in the compute dtype."""
         return np.ascontiguousarray(x.reshape(x.shape[0], max(self.input_size, 1)), dtype=dtype)
 
-    @staticmethod
-    def _compute_dtype(x0: np.ndarray, x1: Optional[np.ndarray]) -> np.dtype:
+    # families without a float32 device path (Linear, Polynomial, WhiteNoise, ProductMatern and
+    # arithmetic nodes) promote float32 points to float64, which is also the dtype the
+    # reference's NumPy-2 arithmetic returns for them
+    _float64_only = False
+
+    def _compute_dtype(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.dtype:
         dt = x0.dtype if x1 is None else np.result_type(x0.dtype, x1.dtype)
-        return np.dtype(np.float32) if dt == np.float32 else np.dtype(np.float64)
+        if dt == np.float32 and not self._float64_only:
+            return np.dtype(np.float32)
+        return np.dtype(np.float64)
 
     def _result_dtype(self, compute_dtype: np.dtype) -> np.dtype:
         """Dtype the reference returns under NumPy 2 for these inputs."""
@@ -187,14 +193,41 @@ class CovarianceFunction(abc.ABC):
             return np.dtype(np.float32)
         return np.dtype(np.float64)
 
+    # -- arithmetic (_covariance_function.py:709-741, _arithmetic.py) ---------------------------------
+    __array_ufunc__ = None  # NumPy scalars defer to __rmul__ / __radd__ (:713-717)
+
+    def __add__(self, other):
+        return SumCovarianceFunction(self, other)
+
+    def __radd__(self, other):
+        return SumCovarianceFunction(other, self)
+
+    def __mul__(self, other):
+        return _mul(self, other)
+
+    def __rmul__(self, other):
+        return _mul(other, self)
+
+    def _diag_self(self, x0: np.ndarray) -> np.ndarray:
+        """k(x, x) over a batch, the ``x1 is None`` branch of ``_evaluate``.  k(x, x) = 1 for the
+        three isotropic families: the reference returns exact ones as well
+        (_exponentiated_quadratic.py:90-94, _rational_quadratic.py:72-76; Matern:
+        c_0 * exp(-0) = 1, _matern.py:175-191)."""
+        dt = self._result_dtype(self._compute_dtype(x0, None))
+        return np.ones(x0.shape[: x0.ndim - self.input_ndim], dtype=dt)
+
+    def _gram_to_device(self, x0: np.ndarray, x1: Optional[np.ndarray], out: "_lib.DeviceBuffer") -> None:
+        """Gram matrix (n0, n1), float64, row-major, into device memory (covariance arithmetic)."""
+        n1 = x0.shape[0] if x1 is None else x1.shape[0]
+        dt = np.dtype(np.float64)
+        with _lib.Operator(self._kernel_params(), self._points(x0, dt),
+                           None if x1 is None else self._points(x1, dt), device=out.device) as op:
+            op.gram_device(out.ptr, n1)
+
     def _evaluate(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.ndarray:
         nd = self.input_ndim
         if x1 is None:
-            # k(x, x) = 1 for the three isotropic families: the reference returns exact
-            # ones as well (_exponentiated_quadratic.py:90-94, _rational_quadratic.py:72-76;
-            # Matern: c_0 * exp(-0) = 1, _matern.py:175-191)
-            dt = self._result_dtype(self._compute_dtype(x0, None))
-            return np.ones(x0.shape[: x0.ndim - nd], dtype=dt)
+            return self._diag_self(x0)
         b0 = x0.shape[: x0.ndim - nd]
         b1 = x1.shape[: x1.ndim - nd]
         batch = np.broadcast_shapes(b0, b1)
@@ -450,3 +483,299 @@ class RatQuad(CovarianceFunction):
         # only l^2 enters the formula (_rational_quadratic.py:78-84)
         return _lib.KernelParams(_lib.RATQUAD, max(self.input_size, 1), np.reshape(abs(self.lengthscale), 1),
                                  alpha=float(self.alpha))
+
+
+# =================================================================================================
+# the remaining covariance functions and covariance arithmetic
+# =================================================================================================
+class _DenseOnly(CovarianceFunction):
+    """Families served by the dense Gram and elementwise kernels only (pncov_extra.cu)."""
+
+    _float64_only = True
+
+    def _diag_self(self, x0: np.ndarray) -> np.ndarray:
+        # k(x_b, x_b) through the elementwise kernel
+        batch = x0.shape[: x0.ndim - self.input_ndim]
+        size = int(np.prod(batch, dtype=np.int64))
+        if size == 0:
+            return np.empty(batch, dtype=np.float64)
+        p = np.ascontiguousarray(x0.reshape(size, -1), dtype=np.float64)
+        return _lib.pairs(self._kernel_params(), p, p).reshape(batch)
+
+    def _evaluate_linop(self, x0, x1):
+        # the reference has no matrix-free form for these either: its operator caches the dense
+        # matrix (_covariance_linear_operator.py:78-81); here that matrix is built on the device
+        return linops.Matrix(self._evaluate_matrix(x0, x1))
+
+
+class Linear(_DenseOnly):
+    r"""Linear kernel :math:`k(x_0,x_1)=x_0^\top x_1+c` (_linear.py:14-50)."""
+
+    def __init__(self, input_shape, constant=0.0):
+        self.constant = _as_numpy_scalar(constant)
+        super().__init__(input_shape=input_shape)
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        return _lib.KernelParams(_lib.LINEAR, max(self.input_size, 1), None, alpha=float(self.constant))
+
+
+class Polynomial(_DenseOnly):
+    r"""Polynomial kernel :math:`k(x_0,x_1)=(x_0^\top x_1+c)^q` (_polynomial.py:14-56).  The device
+    path takes integer exponents 0..64 (repeated multiplication); others raise."""
+
+    def __init__(self, input_shape, constant=0.0, exponent=1.0):
+        self.constant = _as_numpy_scalar(constant)
+        self.exponent = _as_numpy_scalar(exponent)
+        super().__init__(input_shape=input_shape)
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        q = float(self.exponent)
+        if not (0 <= q <= 64 and q == int(q)):
+            raise NotImplementedError(f"Polynomial exponent {q} is outside the device path (integers 0..64).")
+        return _lib.KernelParams(_lib.POLYNOMIAL, max(self.input_size, 1), None, nu=q, alpha=float(self.constant))
+
+
+class WhiteNoise(_DenseOnly):
+    r"""White noise :math:`k(x_0,x_1)=\sigma^2\delta(x_0,x_1)` (_white_noise.py:14-55)."""
+
+    def __init__(self, input_shape, sigma_sq=1.0):
+        if sigma_sq < 0:
+            raise ValueError(f"Noise level sigma_sq={sigma_sq} must be non-negative.")
+        self._sigma_sq = _as_numpy_scalar(sigma_sq)
+        super().__init__(input_shape=input_shape)
+
+    @property
+    def sigma_sq(self):
+        return self._sigma_sq
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        return _lib.KernelParams(_lib.WHITENOISE, max(self.input_size, 1), None, alpha=float(self._sigma_sq))
+
+
+class ProductMatern(_DenseOnly):
+    r"""Product of one-dimensional Matern kernels
+    :math:`k(x_0,x_1)=\prod_i k_i(x_{0,i},x_{1,i})` (_product_matern.py:17-122), half-integer
+    smoothness in every dimension."""
+
+    def __init__(self, input_shape, lengthscales, nus):
+        input_shape = _as_shape(input_shape)
+        if input_shape == () and not (np.isscalar(lengthscales) and np.isscalar(nus)):
+            raise ValueError(f"'lengthscales' and 'nus' must be scalar if 'input_shape' is {input_shape}.")
+        input_dim = 1 if input_shape == () else input_shape[0]
+
+        def expand(x):
+            x = np.asarray(x, dtype=np.double)
+            return np.full((input_dim,), x[()]) if x.shape == () else x
+
+        self.lengthscales = expand(lengthscales)
+        self.nus = expand(nus)
+        if self.lengthscales.shape != (input_dim,) or self.nus.shape != (input_dim,):
+            raise ValueError("'lengthscales' and 'nus' must be scalars or have one entry per input dimension.")
+        # the reference builds one Matern per dimension, whose constructor validates these
+        self.univariate_materns = [Matern((), nu=self.nus[i], lengthscales=self.lengthscales[i])
+                                   for i in range(input_dim)]
+        super().__init__(input_shape=input_shape)
+
+    def _diag_self(self, x0: np.ndarray) -> np.ndarray:
+        return np.ones(x0.shape[: x0.ndim - self.input_ndim], dtype=np.float64)  # product of ones
+
+    def _kernel_params(self) -> _lib.KernelParams:
+        for m in self.univariate_materns:
+            if not m.is_half_integer or m.p > _lib.MAX_MATERN_P:
+                raise NotImplementedError("ProductMatern needs half-integer nu in every dimension on the device path.")
+        return _lib.KernelParams(_lib.PRODUCT_MATERN, max(self.input_size, 1),
+                                 np.concatenate([self.lengthscales, self.nus]))
+
+
+# -- arithmetic (_arithmetic.py, _arithmetic_fallbacks.py) ----------------------------------------------
+_ARITH_BLOCK_BYTES = 4 << 30  # device-side row blocks of arithmetic results
+
+
+class _ArithmeticNode(CovarianceFunction):
+    """Shared evaluation of Scaled / Sum / Product covariance functions: every operand's Gram
+    block is built on the device and combined there in place (pncov_combine_device); only the
+    result crosses PCIe.  The reference combines full host matrices with NumPy
+    (_arithmetic_fallbacks.py:55-56, :101-104, :163-166)."""
+
+    _float64_only = True
+
+    def _kernel_params(self):
+        raise NotImplementedError("arithmetic nodes are evaluated operand by operand")
+
+    def _children(self):
+        raise NotImplementedError
+
+    def _combine_into(self, x0, x1, out, n_elems) -> None:
+        raise NotImplementedError
+
+    def _gram_to_device(self, x0, x1, out) -> None:
+        n1 = x0.shape[0] if x1 is None else x1.shape[0]
+        self._combine_into(x0, x1, out, x0.shape[0] * n1)
+
+    def _result_dtype(self, compute_dtype: np.dtype) -> np.dtype:
+        return np.dtype(np.float64)
+
+    def _leaf_result_dtype(self, in_dtype: np.dtype) -> np.dtype:
+        """NumPy promotion of the operands' result dtypes (float32 points: ExpQuad stays float32,
+        everything else, and every NumPy-scalar factor, is float64)."""
+        dts = []
+        for c in self._children():
+            if isinstance(c, _ArithmeticNode):
+                dts.append(c._leaf_result_dtype(in_dtype))
+            else:
+                dts.append(c._result_dtype(np.dtype(np.float32) if in_dtype == np.float32 and not c._float64_only
+                                           else np.dtype(np.float64)))
+        if isinstance(self, ScaledCovarianceFunction):
+            dts.append(np.dtype(np.float64))
+        return np.result_type(*dts)
+
+    def _evaluate_matrix(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.ndarray:
+        n0 = x0.shape[0]
+        n1 = n0 if x1 is None else x1.shape[0]
+        in_dt = x0.dtype if x1 is None else np.result_type(x0.dtype, x1.dtype)
+        out_dt = self._leaf_result_dtype(np.dtype(in_dt))
+        if n0 == 0 or n1 == 0:
+            return np.empty((n0, n1), dtype=out_dt)
+        K = hostmem.empty((n0, n1), np.float64)
+        rows = max(1, min(n0, _ARITH_BLOCK_BYTES // (8 * n1)))
+        if rows >= n0:  # one block: keeps x1 = None, so the symmetric kernels apply
+            with _lib.DeviceBuffer(8 * n0 * n1) as acc:
+                self._gram_to_device(x0, x1, acc)
+                acc.to_host(K)
+        else:
+            x1e = x0 if x1 is None else x1
+            with _lib.DeviceBuffer(8 * rows * n1) as acc:
+                for r0 in range(0, n0, rows):
+                    blk = x0[r0:r0 + rows]
+                    self._gram_to_device(blk, x1e, acc)
+                    acc.to_host(K[r0:r0 + blk.shape[0]])
+        return K if out_dt == np.float64 else K.astype(out_dt)
+
+    def _evaluate(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.ndarray:
+        nd = self.input_ndim
+        if x1 is not None:
+            b0 = x0.shape[: x0.ndim - nd]
+            b1 = x1.shape[: x1.ndim - nd]
+            if len(b0) == 2 and len(b1) == 2 and b0[1] == 1 and b1[0] == 1 and b0[0] * b1[1] > 1:
+                return self._evaluate_matrix(x0.reshape((b0[0],) + self.input_shape),
+                                             x1.reshape((b1[1],) + self.input_shape))
+        # O(N d) broadcasts: operand by operand through the elementwise kernels
+        return self._evaluate_elementwise(x0, x1)
+
+    def _evaluate_linop(self, x0, x1):
+        return linops.Matrix(self._evaluate_matrix(x0, x1))
+
+
+def _check_same_shapes(operands, what: str) -> None:
+    if not all(isinstance(o, CovarianceFunction) for o in operands):
+        raise TypeError(f"All {what} must be covariance functions.")
+    if not all(o.input_shape == operands[0].input_shape for o in operands):
+        raise ValueError(f"All {what} must have the same in- and output shape.")
+
+
+class ScaledCovarianceFunction(_ArithmeticNode):
+    r""":math:`k(x_0,x_1)=o\,k'(x_0,x_1)` (_arithmetic_fallbacks.py:21-66)."""
+
+    def __init__(self, covfunc: CovarianceFunction, scalar):
+        if not isinstance(covfunc, CovarianceFunction):
+            raise TypeError("`covfunc` must be a `CovarianceFunction`")
+        if np.ndim(scalar) != 0:
+            raise TypeError("`scalar` must be a scalar.")
+        self._covfunc = covfunc
+        self._scalar = _as_numpy_scalar(scalar)
+        super().__init__(input_shape=covfunc.input_shape)
+
+    def _children(self):
+        return (self._covfunc,)
+
+    def _combine_into(self, x0, x1, out, n_elems) -> None:
+        self._covfunc._gram_to_device(x0, x1, out)
+        _lib.combine(out, None, n_elems, _lib.COMBINE_LINEAR, alpha=float(self._scalar), beta=0.0)
+
+    def _evaluate_elementwise(self, x0, x1):
+        return self._scalar * self._covfunc(x0, x1)
+
+    def linop(self, x0, x1=None):
+        return self._scalar * self._covfunc.linop(x0, x1)
+
+    def __repr__(self) -> str:
+        return f"{self._scalar} * {self._covfunc}"
+
+
+class SumCovarianceFunction(_ArithmeticNode):
+    r""":math:`k(x_0,x_1)=\sum_i k_i(x_0,x_1)` (_arithmetic_fallbacks.py:69-135)."""
+
+    def __init__(self, *summands: CovarianceFunction):
+        _check_same_shapes(summands, "summands")
+        expanded = []
+        for s_ in summands:
+            expanded.extend(s_._summands if isinstance(s_, SumCovarianceFunction) else (s_,))
+        self._summands = tuple(expanded)
+        super().__init__(input_shape=summands[0].input_shape)
+
+    def _children(self):
+        return self._summands
+
+    def _combine_into(self, x0, x1, out, n_elems) -> None:
+        self._summands[0]._gram_to_device(x0, x1, out)
+        if len(self._summands) == 1:
+            return
+        with _lib.DeviceBuffer(8 * n_elems, device=out.device) as tmp:
+            for s_ in self._summands[1:]:
+                if isinstance(s_, ScaledCovarianceFunction):  # out += o * k': one pass instead of two
+                    s_._covfunc._gram_to_device(x0, x1, tmp)
+                    _lib.combine(out, tmp, n_elems, _lib.COMBINE_LINEAR, alpha=1.0, beta=float(s_._scalar))
+                else:
+                    s_._gram_to_device(x0, x1, tmp)
+                    _lib.combine(out, tmp, n_elems, _lib.COMBINE_LINEAR, alpha=1.0, beta=1.0)
+
+    def _evaluate_elementwise(self, x0, x1):
+        return functools.reduce(operator.add, (s_(x0, x1) for s_ in self._summands))
+
+    def linop(self, x0, x1=None):
+        return functools.reduce(operator.add, (s_.linop(x0, x1) for s_ in self._summands))
+
+    def __repr__(self):
+        return "SumCovarianceFunction [\n\t" + ",\n\t".join(repr(s_) for s_ in self._summands) + "\n]"
+
+
+class ProductCovarianceFunction(_ArithmeticNode):
+    r""":math:`k(x_0,x_1)=\prod_i k_i(x_0,x_1)` (_arithmetic_fallbacks.py:138-199)."""
+
+    def __init__(self, *factors: CovarianceFunction):
+        _check_same_shapes(factors, "factors")
+        expanded = []
+        for f in factors:
+            expanded.extend(f._factors if isinstance(f, ProductCovarianceFunction) else (f,))
+        self._factors = tuple(expanded)
+        super().__init__(input_shape=factors[0].input_shape)
+
+    def _children(self):
+        return self._factors
+
+    def _combine_into(self, x0, x1, out, n_elems) -> None:
+        self._factors[0]._gram_to_device(x0, x1, out)
+        if len(self._factors) == 1:
+            return
+        with _lib.DeviceBuffer(8 * n_elems, device=out.device) as tmp:
+            for f in self._factors[1:]:
+                f._gram_to_device(x0, x1, tmp)
+                _lib.combine(out, tmp, n_elems, _lib.COMBINE_MULTIPLY)
+
+    def _evaluate_elementwise(self, x0, x1):
+        return functools.reduce(operator.mul, (f(x0, x1) for f in self._factors))
+
+    def __repr__(self):
+        return "ProductCovarianceFunction [\n\t" + ",\n\t".join(repr(f) for f in self._factors) + "\n]"
+
+
+def _mul(op1, op2):
+    """_arithmetic_fallbacks.py:202-222 (``_mul_fallback``)."""
+    if isinstance(op1, CovarianceFunction):
+        if isinstance(op2, CovarianceFunction):
+            return ProductCovarianceFunction(op1, op2)
+        if np.ndim(op2) == 0:
+            return ScaledCovarianceFunction(op1, scalar=op2)
+    elif isinstance(op2, CovarianceFunction) and np.ndim(op1) == 0:
+        return ScaledCovarianceFunction(op2, scalar=op1)
+    return NotImplemented

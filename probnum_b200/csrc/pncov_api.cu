@@ -184,6 +184,11 @@ struct KernelDesc {
     bool ard = false;
     std::vector<double> scale;  // per-dimension scale factors when ard
     PnEpiParams epi{};
+    // non-isotropic families (pncov_extra.cu): mode >= 0 selects them
+    int extra_mode = -1;
+    double constant = 0.0;   // Linear / Polynomial: c; WhiteNoise: sigma^2
+    int exponent = 1;        // Polynomial
+    std::vector<double> pm;  // ProductMatern: (d, PN_PM_LD) per-dimension {scale, p, c_0..c_8}
     bool gram_f32() const { return dtype == PNCOV_F32 && kind == PNCOV_EXPQUAD; }
     size_t elem() const { return dtype == PNCOV_F32 ? 4 : 8; }
     size_t gram_elem() const { return gram_f32() ? 4 : 8; }
@@ -263,10 +268,47 @@ void fill_window(PnEpiParams& P) {
 
 int build_desc(KernelDesc& k, int kind, int dtype, int64_t d, const double* ls, int64_t nls, double nu,
                double alpha) {
-    if (kind != PNCOV_EXPQUAD && kind != PNCOV_MATERN && kind != PNCOV_RATQUAD)
-        return fail(PNCOV_EINVAL, "unknown kernel kind");
+    if (kind < PNCOV_EXPQUAD || kind > PNCOV_PRODUCT_MATERN) return fail(PNCOV_EINVAL, "unknown kernel kind");
     if (dtype != PNCOV_F64 && dtype != PNCOV_F32) return fail(PNCOV_EINVAL, "unknown dtype");
     if (d < 1 || d > (1 << 20)) return fail(PNCOV_EINVAL, "input dimension d must be in [1, 2^20]");
+    if (kind >= PNCOV_LINEAR) {
+        // _linear.py:44-50, _polynomial.py:50-56, _white_noise.py:38-55, _product_matern.py:60-122
+        if (dtype != PNCOV_F64) return fail(PNCOV_EINVAL, "Linear / Polynomial / WhiteNoise / ProductMatern take float64 points");
+        k.kind = kind;
+        k.dtype = dtype;
+        k.d = (int)d;
+        k.ard = false;
+        k.epi = PnEpiParams{};
+        k.constant = alpha;
+        k.exponent = 1;
+        if (kind == PNCOV_LINEAR) {
+            k.extra_mode = 0;
+        } else if (kind == PNCOV_POLYNOMIAL) {
+            if (!(nu >= 0 && nu <= 64 && nu == floor(nu)))
+                return fail(PNCOV_ENOTIMPL, "Polynomial exponent must be an integer in [0, 64] on the device path");
+            k.extra_mode = 0;
+            k.exponent = (int)nu;
+        } else if (kind == PNCOV_WHITENOISE) {
+            k.extra_mode = 1;
+        } else {
+            if (!ls || nls != 2 * d) return fail(PNCOV_EINVAL, "ProductMatern takes d lengthscales followed by d smoothness values");
+            k.extra_mode = 2;
+            k.pm.assign((size_t)d * PN_PM_LD, 0.0);
+            for (int64_t m = 0; m < d; ++m) {
+                const double l = ls[m], nu_m = ls[d + m];
+                if (!(l > 0)) return fail(PNCOV_EINVAL, "lengthscales must be positive");
+                if (!(nu_m > 0)) return fail(PNCOV_EINVAL, "nu must be positive");
+                const double pm_ = nu_m - 0.5;
+                if (pm_ != floor(pm_) || pm_ > PNCOV_MAX_MATERN_P)
+                    return fail(PNCOV_ENOTIMPL, "ProductMatern needs half-integer nu <= PNCOV_MAX_MATERN_P + 1/2 in every dimension");
+                double* row = &k.pm[(size_t)m * PN_PM_LD];
+                row[0] = sqrt(2 * nu_m) / l;  // _matern.py:171-173
+                row[1] = pm_;
+                if (!matern_coefficients((int)pm_, row + 2)) return fail(PNCOV_ENOTIMPL, "Matern coefficients overflow");
+            }
+        }
+        return 0;
+    }
     if (!ls || (nls != 1 && nls != d)) return fail(PNCOV_EINVAL, "n_lengthscales must be 1 or d");
     for (int64_t i = 0; i < nls; ++i)
         if (!(ls[i] > 0)) return fail(PNCOV_EINVAL, "lengthscales must be positive");
@@ -345,6 +387,7 @@ struct pncov_handle {
     Points p0, p1;
     bool symmetric = false;  // x1 was NULL: p1 aliases p0
     void* scale_dev = nullptr;
+    void* pm_dev = nullptr;  // ProductMatern per-dimension parameters
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -460,6 +503,38 @@ PnGramLaunch gram_launch(const pncov_handle* h, bool transpose, int64_t row0, in
     return g;
 }
 
+int upload_pm(const KernelDesc& k, void** dev, cudaStream_t stream) {
+    *dev = nullptr;
+    if (k.pm.empty()) return 0;
+    PN_CUDA(pn_dev_alloc(dev, k.pm.size() * 8, stream));
+    PN_CUDA(cudaMemcpyAsync(*dev, k.pm.data(), k.pm.size() * 8, cudaMemcpyHostToDevice, stream));
+    PN_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+// one Gram launch (rows [row0, row0 + rows) of K or K^T) of whichever family the handle holds
+cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0, int64_t rows, void* out, int64_t ld,
+                            cudaStream_t stream) {
+    if (h->k.extra_mode < 0) return pn_launch_gram(gram_launch(h, transpose, row0, rows, out, ld), stream);
+    const Points& R = transpose ? h->p1 : h->p0;
+    const Points& C = transpose ? h->p0 : h->p1;
+    PnExtraLaunch g{};
+    g.mode = h->k.extra_mode;
+    g.x0_soa = static_cast<const char*>(R.soa) + (size_t)row0 * 8;
+    g.x1_soa = C.soa;
+    g.ld0 = R.npad;
+    g.ld1 = C.npad;
+    g.n0 = rows;
+    g.n1 = C.n;
+    g.d = h->k.d;
+    g.pm = h->pm_dev;
+    g.constant = h->k.constant;
+    g.exponent = h->k.exponent;
+    g.out = out;
+    g.ldo = ld;
+    return pn_launch_gram_extra(g, stream);
+}
+
 // Decide whether the norm-identity kernel may serve this handle and build its operands.
 //
 // With xt = (x - c) s the identity S = |xt_i|^2 + |yt_j|^2 - 2 xt_i.yt_j carries an absolute
@@ -556,6 +631,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         PN_CUDA(cudaMemset2DAsync(y, (size_t)ldy * es, 0, (size_t)k * es, (size_t)R.n, stream));
         return 0;
     }
+    if (h->k.extra_mode >= 0)
+        return fail(PNCOV_ENOTIMPL, "the matrix-free product covers ExpQuad, Matern and RatQuad; use the dense Gram for this kernel");
     if (h->k.d > 1024) return fail(PNCOV_ENOTIMPL, "matrix-free product supports d <= 1024");
     const int kc_max = (k == 1) ? 1 : 4;
     PnMatvecLaunch m{};
@@ -690,6 +767,7 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
     if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return bail(fail_cuda(e, "cudaEventCreate"));
     if ((rc = upload_scale(h->k, &h->scale_dev, h->stream))) return bail(rc);
+    if ((rc = upload_pm(h->k, &h->pm_dev, h->stream))) return bail(rc);
     if ((rc = upload_points(h, h->p0, x0, n0, points_on_device != 0))) return bail(rc);
     if (x1) {
         if ((rc = upload_points(h, h->p1, x1, n1, points_on_device != 0))) return bail(rc);
@@ -714,6 +792,7 @@ PNCOV_API int pncov_destroy(pncov_handle* h) {
     if (!h->symmetric) free_points(h->p1, fs);
     free_points(h->p0, fs);
     pn_dev_free(h->scale_dev, fs);
+    pn_dev_free(h->pm_dev, fs);
     pn_dev_free(h->vpack, fs);
     pn_dev_free(h->ypack, fs);
     pn_dev_free(h->partial, fs);
@@ -756,7 +835,7 @@ PNCOV_API int pncov_gram_device(pncov_handle* h, void* out, int64_t ld, int tran
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     h->used_foreign_stream = true;
     PN_CUDA(cudaEventRecord(h->ev0, stream));
-    PN_CUDA(pn_launch_gram(gram_launch(h, transpose != 0, 0, rows, out, ld), stream));
+    PN_CUDA(launch_gram_any(h, transpose != 0, 0, rows, out, ld, stream));
     PN_CUDA(cudaEventRecord(h->ev1, stream));
     h->timed = true;
     return 0;
@@ -794,7 +873,7 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
         const int buf = b % nbuf;
         char* dbuf = static_cast<char*>(h->stage) + (size_t)buf * block_bytes;
         if (b >= nbuf) err = cudaStreamWaitEvent(h->stream, copied[buf], 0);
-        if (err == cudaSuccess) err = pn_launch_gram(gram_launch(h, transpose != 0, r0, nr, dbuf, ld_stage), h->stream);
+        if (err == cudaSuccess) err = launch_gram_any(h, transpose != 0, r0, nr, dbuf, ld_stage, h->stream);
         if (err == cudaSuccess) err = cudaEventRecord(done[buf], h->stream);
         if (err == cudaSuccess) err = cudaStreamWaitEvent(h->copy_stream, done[buf], 0);
         if (err == cudaSuccess)
@@ -876,12 +955,14 @@ PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const doub
     char* buf = nullptr;
     PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&buf), 2 * pbytes + (size_t)b * oe + 512, 0));
     void* scale_dev = nullptr;
+    void* pm_dev = nullptr;
     auto cleanup = [&]() {
         cudaStreamSynchronize(0);
         pn_dev_free(buf, 0);
         pn_dev_free(scale_dev, 0);
+        pn_dev_free(pm_dev, 0);
     };
-    if ((rc = upload_scale(k, &scale_dev, 0))) {
+    if ((rc = upload_scale(k, &scale_dev, 0)) || (rc = upload_pm(k, &pm_dev, 0))) {
         cleanup();
         return rc;
     }
@@ -891,7 +972,19 @@ PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const doub
     // note: buf was sized with 512 bytes of slack for the two roundings above
     cudaError_t e = cudaMemcpy(d0, x0, pbytes, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(d1, x1, pbytes, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
+    if (e == cudaSuccess && k.extra_mode >= 0) {
+        PnExtraLaunch g{};
+        g.mode = k.extra_mode;
+        g.x0_soa = d0;
+        g.x1_soa = d1;
+        g.n0 = b;
+        g.d = (int)d;
+        g.pm = pm_dev;
+        g.constant = k.constant;
+        g.exponent = k.exponent;
+        g.out = dout;
+        e = pn_launch_pairs_extra(g, 0);
+    } else if (e == cudaSuccess) {
         PnPairsLaunch p{};
         p.x0 = d0;
         p.x1 = d1;
@@ -907,6 +1000,56 @@ PNCOV_API int pncov_pairs(int device, int kind, int dtype, int64_t d, const doub
     if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)b * oe, cudaMemcpyDeviceToHost);
     cleanup();
     if (e != cudaSuccess) return fail_cuda(e, "pncov_pairs");
+    return 0;
+}
+
+// ---- device buffers and covariance arithmetic on them ---------------------------------------------
+PNCOV_API int pncov_device_alloc(int device, void** ptr, int64_t nbytes) {
+    if (!ptr || nbytes < 0) return fail(PNCOV_EINVAL, "bad arguments");
+    *ptr = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PNCOV_ENODEVICE, "no CUDA device available (libpncov has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(PNCOV_EINVAL, "device index out of range");
+    DeviceGuard guard(device);
+    cudaError_t e = cudaMalloc(ptr, (size_t)std::max<int64_t>(nbytes, 1));
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        return fail(PNCOV_ENOMEM, "out of device memory");
+    }
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMalloc");
+    return 0;
+}
+
+PNCOV_API int pncov_device_free(int device, void* ptr) {
+    if (!ptr) return 0;
+    DeviceGuard guard(device);
+    PN_CUDA(cudaFree(ptr));
+    return 0;
+}
+
+PNCOV_API int pncov_copy_to_host(int device, void* dst, const void* src, int64_t nbytes, void* stream_) {
+    if (nbytes < 0 || (nbytes > 0 && (!dst || !src))) return fail(PNCOV_EINVAL, "bad arguments");
+    if (nbytes == 0) return 0;
+    DeviceGuard guard(device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    PN_CUDA(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDeviceToHost, stream));
+    PN_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64_t n, int op, double alpha, double beta,
+                                   void* stream_) {
+    if (n < 0 || (n > 0 && !dst)) return fail(PNCOV_EINVAL, "bad arguments");
+    if (op != PNCOV_COMBINE_LINEAR && op != PNCOV_COMBINE_MULTIPLY) return fail(PNCOV_EINVAL, "unknown combine op");
+    if (op == PNCOV_COMBINE_MULTIPLY && !src) return fail(PNCOV_EINVAL, "multiply needs a source");
+    if (op == PNCOV_COMBINE_LINEAR && !src && beta != 0.0) return fail(PNCOV_EINVAL, "beta != 0 needs a source");
+    if (n == 0) return 0;
+    DeviceGuard guard(device);
+    PN_CUDA(pn_launch_combine(static_cast<double*>(dst), static_cast<const double*>(src), n, op, alpha, beta,
+                              static_cast<cudaStream_t>(stream_)));
     return 0;
 }
 

@@ -1,0 +1,278 @@
+// Gram matrices of the non-isotropic covariance functions and device-side covariance arithmetic
+// (SURVEY.md 8f, row N3).  Paths relative to /root/reference/src/probnum/randprocs/covfuncs:
+//
+//   Linear        k = <x0, x1> + c                          _linear.py:44-50
+//   Polynomial    k = (<x0, x1> + c)^q, q = 0, 1, 2, ...      _polynomial.py:50-56
+//   WhiteNoise    k = sigma^2 [x0 == x1]                    _white_noise.py:38-55
+//   ProductMatern k = prod_m Matern_{nu_m}(|x0_m - x1_m| / l_m)   _product_matern.py:103-122
+//   Scaled / Sum / Product covariance functions             _arithmetic_fallbacks.py:21-180
+//
+// All of them are HBM-write-bound for small d, like the isotropic Gram kernel, so the layout is
+// the same: a CTA of 256 threads owns a strip of 512 columns, a thread owns two adjacent columns
+// and emits one 16-byte streaming store per row; the strip's column points are staged once in
+// shared memory (coordinate-major, up to X_DC coordinates at a time), row points are read as
+// warp broadcasts.  float64 only (the host side promotes float32 inputs, which is also what the
+// reference's NumPy-2 arithmetic produces for these kernels).
+#include "pncov_internal.h"
+
+namespace {
+
+constexpr int X_THREADS = 256;
+constexpr int X_TN = 2 * X_THREADS;  // columns per strip
+constexpr int X_R = 8;               // rows per register tile
+constexpr int X_DC = 16;             // coordinates staged per chunk
+
+enum { X_DOT = 0, X_EQUAL = 1, X_PRODMATERN = 2 };
+
+// (x + c)^q by binary powering: q - 1 roundings at most for q <= 3, O(log q) multiplications
+__device__ __forceinline__ double x_powi(double b, int q) {
+    double r = 1.0;
+    while (q > 0) {
+        if (q & 1) r *= b;
+        b *= b;
+        q >>= 1;
+    }
+    return r;
+}
+
+// univariate half-integer Matern polynomial in r0 = |x0_m - x1_m| * s_m with exp(-r) deferred:
+// returns poly(r0); pm = {s_m, p_m, c_0 .. c_8}
+__device__ __forceinline__ double x_matern_poly(double r, const double* pm) {
+    const int p = (int)pm[1];
+    double poly = pm[2 + p];
+    for (int i = p - 1; i >= 0; --i) poly = pn_fma(poly, r, pm[2 + i]);
+    return poly;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(X_THREADS)
+    gram_extra_kernel(const __grid_constant__ PnExtraLaunch g, int groups_per_cta) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* tabE = reinterpret_cast<double*>(smem);                   // PRODMATERN only
+    double* x1c = reinterpret_cast<double*>(smem + 8 * PN_EXP2_N);   // [X_DC][X_TN]
+    double* x0c = x1c + X_DC * X_TN;                                  // [X_DC][X_R]
+    double* pmc = x0c + X_DC * X_R;                                   // [X_DC][PN_PM_LD]
+    const int tid = threadIdx.x;
+    const int64_t col0 = (int64_t)blockIdx.x * X_TN;
+    const int64_t j0 = col0 + 2 * tid;
+    const double* x0g = static_cast<const double*>(g.x0_soa);
+    const double* x1g = static_cast<const double*>(g.x1_soa);
+    if constexpr (MODE == X_PRODMATERN) {
+        for (int i = tid; i < PN_EXP2_N; i += X_THREADS) tabE[i] = pn_exp2_table_g[i];
+    }
+    const int64_t n_groups = (g.n0 + X_R - 1) / X_R;
+    const int64_t gr0 = (int64_t)blockIdx.y * groups_per_cta;
+    const int64_t gr1 = (gr0 + groups_per_cta < n_groups) ? gr0 + groups_per_cta : n_groups;
+    const bool one_chunk = g.d <= X_DC;  // then the column chunk is staged once per CTA
+
+    for (int64_t gr = gr0; gr < gr1; ++gr) {
+        const int64_t row0 = gr * X_R;
+        double A[2 * X_R], B[2 * X_R];  // DOT: A = sum; EQUAL: A = #differences; PRODMATERN: A = sum r, B = prod poly
+#pragma unroll
+        for (int i = 0; i < 2 * X_R; ++i) {
+            A[i] = 0.0;
+            B[i] = 1.0;
+        }
+        for (int c0 = 0; c0 < g.d; c0 += X_DC) {
+            const int dc = (g.d - c0 < X_DC) ? g.d - c0 : X_DC;
+            __syncthreads();
+            if (!one_chunk || gr == gr0) {
+                for (int idx = tid; idx < dc * X_TN; idx += X_THREADS) {
+                    const int m = idx / X_TN, j = idx % X_TN;
+                    x1c[idx] = x1g[(size_t)(c0 + m) * g.ld1 + col0 + j];  // padded to PN_PAD columns
+                }
+                if constexpr (MODE == X_PRODMATERN) {
+                    for (int idx = tid; idx < dc * PN_PM_LD; idx += X_THREADS)
+                        pmc[idx] = static_cast<const double*>(g.pm)[(size_t)c0 * PN_PM_LD + idx];
+                }
+            }
+            if (tid < dc * X_R) {
+                const int m = tid / X_R, r = tid % X_R;
+                x0c[tid] = x0g[(size_t)(c0 + m) * g.ld0 + row0 + r];  // rows padded to PN_PAD as well
+            }
+            __syncthreads();
+            for (int m = 0; m < dc; ++m) {
+                const double2 xb = *reinterpret_cast<const double2*>(x1c + (size_t)m * X_TN + 2 * tid);
+#pragma unroll
+                for (int r = 0; r < X_R; ++r) {
+                    const double xa = x0c[m * X_R + r];
+                    if constexpr (MODE == X_DOT) {
+                        A[2 * r] = pn_fma(xa, xb.x, A[2 * r]);
+                        A[2 * r + 1] = pn_fma(xa, xb.y, A[2 * r + 1]);
+                    } else if constexpr (MODE == X_EQUAL) {
+                        A[2 * r] += (xa == xb.x) ? 0.0 : 1.0;  // NaN != NaN, as in NumPy
+                        A[2 * r + 1] += (xa == xb.y) ? 0.0 : 1.0;
+                    } else {
+                        const double* pm = pmc + m * PN_PM_LD;
+                        const double ra = fabs(xa - xb.x) * pm[0];
+                        const double rb = fabs(xa - xb.y) * pm[0];
+                        A[2 * r] += ra;
+                        A[2 * r + 1] += rb;
+                        B[2 * r] *= x_matern_poly(ra, pm);
+                        B[2 * r + 1] *= x_matern_poly(rb, pm);
+                    }
+                }
+            }
+        }
+        double* out = static_cast<double*>(g.out);
+#pragma unroll
+        for (int r = 0; r < X_R; ++r) {
+            double k0, k1;
+            if constexpr (MODE == X_DOT) {
+                k0 = A[2 * r] + g.constant;
+                k1 = A[2 * r + 1] + g.constant;
+                if (g.exponent != 1) {
+                    k0 = x_powi(k0, g.exponent);
+                    k1 = x_powi(k1, g.exponent);
+                }
+            } else if constexpr (MODE == X_EQUAL) {
+                k0 = A[2 * r] == 0.0 ? g.constant : 0.0;
+                k1 = A[2 * r + 1] == 0.0 ? g.constant : 0.0;
+            } else {
+                // exp(-sum_m r_m) once for the whole product; pn_exp2 takes the robust path for
+                // huge or non-finite arguments
+                k0 = B[2 * r] * pn_exp2(A[2 * r] * -1.4426950408889634074, tabE);
+                k1 = B[2 * r + 1] * pn_exp2(A[2 * r + 1] * -1.4426950408889634074, tabE);
+            }
+            const int64_t row = row0 + r;
+            if (row < g.n0) {
+                double* p = out + row * g.ldo + j0;
+                if (j0 + 1 < g.n1) {
+                    if (g.vec_ok) pn_store_cs2(p, k0, k1);
+                    else {
+                        pn_store_cs1(p, k0);
+                        pn_store_cs1(p + 1, k1);
+                    }
+                } else if (j0 < g.n1) {
+                    pn_store_cs1(p, k0);
+                }
+            }
+        }
+    }
+}
+
+// out[b] = k(x0[b], x1[b]); one thread per pair
+template <int MODE>
+__global__ void pairs_extra_kernel(const __grid_constant__ PnExtraLaunch g) {
+    __shared__ double tabE[PN_EXP2_N];
+    if constexpr (MODE == X_PRODMATERN) {
+        for (int i = threadIdx.x; i < PN_EXP2_N; i += blockDim.x) tabE[i] = pn_exp2_table_g[i];
+        __syncthreads();
+    }
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= g.n0) return;
+    const double* a = static_cast<const double*>(g.x0_soa) + b * g.d;  // here: (B, d) row-major
+    const double* c = static_cast<const double*>(g.x1_soa) + b * g.d;
+    double A = 0.0, B = 1.0;
+    for (int m = 0; m < g.d; ++m) {
+        if constexpr (MODE == X_DOT) A = pn_fma(a[m], c[m], A);
+        else if constexpr (MODE == X_EQUAL) A += (a[m] == c[m]) ? 0.0 : 1.0;
+        else {
+            const double* pm = static_cast<const double*>(g.pm) + (size_t)m * PN_PM_LD;
+            const double r = fabs(a[m] - c[m]) * pm[0];
+            A += r;
+            B *= x_matern_poly(r, pm);
+        }
+    }
+    double k;
+    if constexpr (MODE == X_DOT) k = g.exponent == 1 ? A + g.constant : x_powi(A + g.constant, g.exponent);
+    else if constexpr (MODE == X_EQUAL) k = A == 0.0 ? g.constant : 0.0;
+    else k = B * pn_exp2(A * -1.4426950408889634074, tabE);
+    static_cast<double*>(g.out)[b] = k;
+}
+
+// dst = alpha * dst + beta * src (op 0; src may be null when beta == 0) or dst = dst * src (op 1)
+template <int OP, bool HAS_SRC>
+__global__ void __launch_bounds__(256) combine_kernel(double* __restrict__ dst, const double* __restrict__ src,
+                                                       int64_t n2, int64_t n, double alpha, double beta) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 a = reinterpret_cast<double2*>(dst)[i];
+        if constexpr (OP == 0) {
+            if constexpr (HAS_SRC) {
+                const double2 b = __ldcs(reinterpret_cast<const double2*>(src) + i);
+                a.x = pn_fma(beta, b.x, alpha * a.x);
+                a.y = pn_fma(beta, b.y, alpha * a.y);
+            } else {
+                a.x *= alpha;
+                a.y *= alpha;
+            }
+        } else {
+            const double2 b = __ldcs(reinterpret_cast<const double2*>(src) + i);
+            a.x *= b.x;
+            a.y *= b.y;
+        }
+        reinterpret_cast<double2*>(dst)[i] = a;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (n & 1)) {  // odd tail element
+        const int64_t i = n - 1;
+        if constexpr (OP == 0) dst[i] = HAS_SRC ? pn_fma(beta, src[i], alpha * dst[i]) : alpha * dst[i];
+        else dst[i] *= src[i];
+    }
+}
+
+template <int MODE>
+cudaError_t launch_gram_mode(const PnExtraLaunch& g, cudaStream_t stream) {
+    const int64_t strips = (g.n1 + X_TN - 1) / X_TN;
+    const int64_t n_groups = (g.n0 + X_R - 1) / X_R;
+    // ~16 CTAs per SM; at least one row group each
+    int64_t gpc = (n_groups * strips) / (148 * 16);
+    gpc = gpc < 1 ? 1 : (gpc > 64 ? 64 : gpc);
+    const int64_t gy = (n_groups + gpc - 1) / gpc;
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    const size_t smem = 8 * PN_EXP2_N + sizeof(double) * (X_DC * X_TN + X_DC * X_R + X_DC * PN_PM_LD);
+    auto kern = gram_extra_kernel<MODE>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    dim3 grid((unsigned)strips, (unsigned)gy);
+    kern<<<grid, X_THREADS, smem, stream>>>(g, (int)gpc);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t pn_launch_gram_extra(const PnExtraLaunch& g0, cudaStream_t stream) {
+    if (g0.n0 <= 0 || g0.n1 <= 0) return cudaSuccess;
+    PnExtraLaunch g = g0;
+    g.vec_ok = ((g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0) ? 1 : 0;
+    switch (g.mode) {
+        case X_DOT: return launch_gram_mode<X_DOT>(g, stream);
+        case X_EQUAL: return launch_gram_mode<X_EQUAL>(g, stream);
+        case X_PRODMATERN: return launch_gram_mode<X_PRODMATERN>(g, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t pn_launch_pairs_extra(const PnExtraLaunch& g, cudaStream_t stream) {
+    if (g.n0 <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((g.n0 + 255) / 256);
+    switch (g.mode) {
+        case X_DOT: pairs_extra_kernel<X_DOT><<<blocks, 256, 0, stream>>>(g); break;
+        case X_EQUAL: pairs_extra_kernel<X_EQUAL><<<blocks, 256, 0, stream>>>(g); break;
+        case X_PRODMATERN: pairs_extra_kernel<X_PRODMATERN><<<blocks, 256, 0, stream>>>(g); break;
+        default: return cudaErrorInvalidValue;
+    }
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op, double alpha, double beta,
+                              cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    if (reinterpret_cast<uintptr_t>(dst) % 16 || (src && reinterpret_cast<uintptr_t>(src) % 16))
+        return cudaErrorMisalignedAddress;
+    const int64_t n2 = n / 2;
+    int64_t blocks = (n2 + 255) / 256;
+    blocks = blocks < 1 ? 1 : (blocks > 148 * 32 ? 148 * 32 : blocks);
+    if (op == 0 && src)
+        combine_kernel<0, true><<<(unsigned)blocks, 256, 0, stream>>>(dst, src, n2, n, alpha, beta);
+    else if (op == 0)
+        combine_kernel<0, false><<<(unsigned)blocks, 256, 0, stream>>>(dst, src, n2, n, alpha, beta);
+    else if (op == 1 && src)
+        combine_kernel<1, true><<<(unsigned)blocks, 256, 0, stream>>>(dst, src, n2, n, alpha, beta);
+    else
+        return cudaErrorInvalidValue;
+    ++g_pn_launches;
+    return cudaGetLastError();
+}

@@ -60,6 +60,27 @@ struct PnPairsLaunch {
     PnEpiParams epi;
 };
 
+// non-isotropic families and covariance arithmetic (pncov_extra.cu)
+#define PN_PM_LD 12  // per-dimension ProductMatern parameters: {scale, p, c_0 .. c_8, pad}
+struct PnExtraLaunch {
+    int mode;            // 0: <x0, x1> (Linear / Polynomial), 1: equality (WhiteNoise), 2: ProductMatern
+    const void* x0_soa;  // Gram: (d, ld0) coordinate-major; pairs: (B, d) row-major
+    const void* x1_soa;
+    int64_t ld0, ld1;
+    int64_t n0, n1;      // pairs: n0 = B
+    int d;
+    const void* pm;      // ProductMatern: (d, PN_PM_LD) device array
+    double constant;     // Linear / Polynomial: c; WhiteNoise: sigma^2
+    int exponent;        // Polynomial: q >= 0 (Linear: 1)
+    void* out;
+    int64_t ldo;
+    int vec_ok;          // filled by the launcher
+};
+cudaError_t pn_launch_gram_extra(const PnExtraLaunch& g, cudaStream_t stream);
+cudaError_t pn_launch_pairs_extra(const PnExtraLaunch& g, cudaStream_t stream);
+cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op, double alpha, double beta,
+                              cudaStream_t stream);
+
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
 // pn_plan_matvec fills m.jsplit (how many column-range splits the launch will use, which
 // sizes the `partial` scratch); pn_launch_matvec then runs with that plan

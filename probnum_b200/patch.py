@@ -73,6 +73,34 @@ def _mirror_of(k) -> Optional[_mirror.CovarianceFunction]:
         if k.lengthscale == 0:
             return None
         return _mirror.RatQuad(k.input_shape, lengthscale=k.lengthscale, alpha=k.alpha)
+    # the remaining families and covariance arithmetic (dense Gram only)
+    if type(k) is cf.Linear:
+        return _mirror.Linear(k.input_shape, constant=k.constant)
+    if type(k) is cf.Polynomial:
+        q = float(k.exponent)
+        if not (0 <= q <= 64 and q == int(q)):
+            return None
+        return _mirror.Polynomial(k.input_shape, constant=k.constant, exponent=k.exponent)
+    if type(k) is cf.WhiteNoise:
+        return _mirror.WhiteNoise(k.input_shape, sigma_sq=k.sigma_sq)
+    if type(k) is cf.ProductMatern:
+        nus = np.atleast_1d(np.asarray(k.nus, dtype=float))
+        if not all((nu - 0.5) == int(nu - 0.5) and nu - 0.5 <= _mirror._lib.MAX_MATERN_P for nu in nus):
+            return None
+        if k.input_shape == ():
+            return _mirror.ProductMatern((), lengthscales=float(np.ravel(k.lengthscales)[0]), nus=float(nus[0]))
+        return _mirror.ProductMatern(k.input_shape, lengthscales=np.asarray(k.lengthscales, dtype=float), nus=nus)
+    from probnum.randprocs.covfuncs import _arithmetic_fallbacks as af  # noqa: PLC0415
+
+    if type(k) is af.ScaledCovarianceFunction:
+        inner = _mirror_of(k._covfunc)
+        return None if inner is None else _mirror.ScaledCovarianceFunction(inner, k._scalar)
+    if type(k) in (af.SumCovarianceFunction, af.ProductCovarianceFunction):
+        parts = [_mirror_of(c) for c in (k._summands if type(k) is af.SumCovarianceFunction else k._factors)]
+        if any(c is None for c in parts):
+            return None
+        return (_mirror.SumCovarianceFunction if type(k) is af.SumCovarianceFunction
+                else _mirror.ProductCovarianceFunction)(*parts)
     return None
 
 
@@ -106,7 +134,9 @@ def _make_linop_class():
 
 
 def enable() -> None:
-    """Patch ExpQuad, Matern and RatQuad of the importable ``probnum``."""
+    """Patch ExpQuad, Matern and RatQuad (Gram, operator, Gram-shaped calls) and the Gram hook of
+    Linear, Polynomial, WhiteNoise, ProductMatern and the arithmetic nodes of the importable
+    ``probnum``."""
     numpy2_compat()
     import probnum  # noqa: PLC0415
 
@@ -151,6 +181,14 @@ def enable() -> None:
         cls._evaluate_matrix = make_matrix(cls._evaluate_matrix)
         cls._evaluate_linop = make_linop(cls._evaluate_linop)
         cls._evaluate = make_evaluate(cls.__dict__["_evaluate"])
+    # dense-only families and arithmetic nodes: only the Gram hook.  Their operators keep the
+    # reference's dense-cached CovarianceLinearOperator, whose matrix now comes from the device.
+    from probnum.randprocs.covfuncs import _arithmetic_fallbacks as af  # noqa: PLC0415
+
+    for cls in (cf.Linear, cf.Polynomial, cf.WhiteNoise, cf.ProductMatern, af.ScaledCovarianceFunction,
+                af.SumCovarianceFunction, af.ProductCovarianceFunction):
+        _ORIGINALS[("matrix", cls)] = cls._evaluate_matrix
+        cls._evaluate_matrix = make_matrix(cls._evaluate_matrix)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -217,11 +255,17 @@ def enable_quad_cholesky() -> None:
 
 def disable() -> None:
     """Undo :func:`enable`."""
-    quad = [k for k in _ORIGINALS if isinstance(k, tuple)]
+    quad = [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "quad"]
     for key in quad:
         factor, solve = _ORIGINALS.pop(key)
         key[1].compute_gram_cho_factor = factor
         key[1].gram_cho_solve = solve
+    for key in [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "matrix"]:
+        orig = _ORIGINALS.pop(key)
+        if "_evaluate_matrix" in key[1].__dict__:
+            delattr(key[1], "_evaluate_matrix")
+        if getattr(key[1], "_evaluate_matrix") is not orig:
+            key[1]._evaluate_matrix = orig
     for cls, (matrix, linop, evaluate) in _ORIGINALS.items():
         # the two hooks are inherited from CovarianceFunction: remove our overrides
         for name, orig in (("_evaluate_matrix", matrix), ("_evaluate_linop", linop)):

@@ -21,12 +21,12 @@ def pytest_configure(config):
 class Golden:
     """Inputs and outputs recorded from the real reference (tests/golden/make_golden.py)."""
 
-    def __init__(self):
-        with open(os.path.join(GOLDEN_DIR, "covfuncs_golden.json")) as fh:
+    def __init__(self, stem="covfuncs_golden"):
+        with open(os.path.join(GOLDEN_DIR, stem + ".json")) as fh:
             meta = json.load(fh)
         self.kat = meta["kat"]
         self.cases = meta["cases"]
-        self.arrays = np.load(os.path.join(GOLDEN_DIR, "covfuncs_golden.npz"))
+        self.arrays = np.load(os.path.join(GOLDEN_DIR, stem + ".npz"))
 
     def get(self, name):
         return None if name is None else self.arrays[name]
@@ -40,6 +40,50 @@ def load_golden():
     if _GOLDEN is None:
         _GOLDEN = Golden()
     return _GOLDEN
+
+
+_GOLDEN_EXTRA = None
+
+
+def load_golden_extra():
+    """Fixtures of tests/golden/make_golden_extra.py (SURVEY.md 8f N3 families and arithmetic)."""
+    global _GOLDEN_EXTRA
+    if _GOLDEN_EXTRA is None:
+        _GOLDEN_EXTRA = Golden("covfuncs_extra_golden")
+    return _GOLDEN_EXTRA
+
+
+def mirror_from_spec(spec):
+    """probnum_b200 covariance function for a spec dict of oracle/covfuncs_extra_oracle.py."""
+    import probnum_b200 as pb
+
+    kind = spec["kind"]
+    if kind == "scaled":
+        return spec["scalar"] * mirror_from_spec(spec["child"])
+    if kind in ("sum", "product"):
+        parts = [mirror_from_spec(c) for c in spec["children"]]
+        out = parts[0]
+        for p in parts[1:]:
+            out = out + p if kind == "sum" else out * p
+        return out
+    shape = tuple(spec["input_shape"])
+    if kind == "expquad":
+        return pb.ExpQuad(shape, lengthscales=np.asarray(spec["lengthscales"]))
+    if kind == "matern":
+        return pb.Matern(shape, nu=spec["nu"], lengthscales=np.asarray(spec["lengthscales"]))
+    if kind == "ratquad":
+        return pb.RatQuad(shape, lengthscale=spec["lengthscales"], alpha=spec["alpha"])
+    if kind == "linear":
+        return pb.Linear(shape, constant=spec["constant"])
+    if kind == "polynomial":
+        return pb.Polynomial(shape, constant=spec["constant"], exponent=spec["exponent"])
+    if kind == "whitenoise":
+        return pb.WhiteNoise(shape, sigma_sq=spec["sigma_sq"])
+    if kind == "productmatern":
+        ls, nus = spec["lengthscales"], spec["nus"]
+        return pb.ProductMatern(shape, lengthscales=np.asarray(ls) if np.ndim(ls) else ls,
+                                nus=np.asarray(nus) if np.ndim(nus) else nus)
+    raise ValueError(kind)
 
 
 @pytest.fixture(scope="session")

@@ -42,10 +42,16 @@ def test_enable_disable_restores_reference_methods():
     assert pb_patch.enabled()
     for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad):
         assert cls._evaluate_matrix is not base_matrix and cls._evaluate_linop is not base_linop
-    assert cf.Linear._evaluate_matrix is base_matrix  # other kernels untouched
+    # dense-only families and arithmetic nodes: only the Gram hook is replaced
+    from probnum.randprocs.covfuncs import _arithmetic_fallbacks as af
+
+    dense_only = (cf.Linear, cf.Polynomial, cf.WhiteNoise, cf.ProductMatern, af.SumCovarianceFunction,
+                  af.ScaledCovarianceFunction, af.ProductCovarianceFunction)
+    for cls in dense_only:
+        assert cls._evaluate_matrix is not base_matrix and cls._evaluate_linop is base_linop
     pb_patch.disable()
     assert not pb_patch.enabled()
-    for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad):
+    for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad) + dense_only:
         assert cls._evaluate_matrix is base_matrix and cls._evaluate_linop is base_linop
     # and the reference path really runs again
     K = cf.ExpQuad((2,)).matrix(np.zeros((3, 2)))
@@ -58,7 +64,10 @@ def test_out_of_scope_kernels_keep_the_reference_path(patched):
     assert pb_patch._mirror_of(bessel) is None
     K = bessel.matrix(x)
     assert K.shape == (6, 6) and np.allclose(np.diag(K), 1.0)
-    assert pb_patch._mirror_of(cf.Linear((2,))) is None
+    assert pb_patch._mirror_of(cf.Polynomial((2,), exponent=2.5)) is None  # non-integer power: reference path
+    twin = pb_patch._mirror_of(cf.Linear((2,), constant=0.5) + 2.0 * cf.ProductMatern((2,), lengthscales=1.0, nus=1.5))
+    assert twin is not None and len(twin._summands) == 2
+    assert pb_patch._mirror_of(cf.ExpQuad((2,)) + bessel) is None  # one out-of-scope operand: whole node stays
     twin = pb_patch._mirror_of(cf.Matern((2,), nu=2.5, lengthscales=[0.5, 2.0]))
     assert twin is not None and twin.p == 2 and twin.lengthscales.tolist() == [0.5, 2.0]
     twin = pb_patch._mirror_of(cf.RatQuad((2,), lengthscale=0.3, alpha=2.0))
@@ -210,8 +219,9 @@ def test_evaluate_hook_is_restored():
 
 @pytest.mark.gpu
 def test_covariance_arithmetic_runs_operands_on_the_device(patched):
-    """k1 + c * k2 + k3 * k4: every supported operand is evaluated by the Gram kernel, the
-    combination is the reference's own NumPy code (_arithmetic_fallbacks.py)."""
+    """k1 + c * k2 + k3 * k4: every operand is evaluated by a Gram kernel and the combination runs
+    on the device too (pncov_combine_device); unsupported operands keep the reference's NumPy
+    combination (_arithmetic_fallbacks.py)."""
     from probnum_b200 import _lib
 
     rng = np.random.default_rng(5)
@@ -232,3 +242,32 @@ def test_covariance_arithmetic_runs_operands_on_the_device(patched):
         np.testing.assert_allclose(got_lin, want_lin, rtol=1e-10, atol=1e-12)
     finally:
         pb_patch.enable()
+
+
+@pytest.mark.gpu
+def test_dense_only_families_patched_equal_unpatched():
+    """Linear / Polynomial / WhiteNoise / ProductMatern through the reference's own classes."""
+    rng = np.random.default_rng(8)
+    X = rng.normal(size=(257, 4))
+    Y = rng.normal(size=(100, 4))
+    X[5] = X[9]
+    kernels = [cf.Linear((4,), constant=0.3), cf.Polynomial((4,), constant=1.0, exponent=3),
+               cf.WhiteNoise((4,), sigma_sq=0.2),
+               cf.ProductMatern((4,), lengthscales=np.array([0.5, 1.0, 1.5, 2.0]), nus=np.array([0.5, 1.5, 2.5, 3.5])),
+               2.0 * cf.Matern((4,), nu=2.5) + cf.WhiteNoise((4,), sigma_sq=0.1)]
+    want = [(k.matrix(X), k.matrix(X, Y)) for k in kernels]
+    pb_patch.enable()
+    try:
+        from probnum_b200 import _lib
+
+        for k, (w0, w1) in zip(kernels, want):
+            before = _lib.launch_count()
+            g0, g1 = k.matrix(X), k.matrix(X, Y)
+            assert _lib.launch_count() > before, type(k).__name__
+            np.testing.assert_allclose(g0, w0, rtol=1e-12, atol=1e-12)
+            np.testing.assert_allclose(g1, w1, rtol=1e-12, atol=1e-12)
+            # the reference's dense-cached operator now holds the device-built matrix
+            v = rng.normal(size=257)
+            np.testing.assert_allclose(k.linop(X) @ v, w0 @ v, rtol=1e-10, atol=1e-10)
+    finally:
+        pb_patch.disable()
