@@ -21,11 +21,14 @@ constexpr int X_THREADS = 256;
 constexpr int X_TN = 2 * X_THREADS;  // columns per strip
 constexpr int X_R = 8;               // rows per register tile
 constexpr int X_DC = 16;             // coordinates staged per chunk
+constexpr int X_RS = 64;             // rows staged at a time when d <= X_DC
 
 enum { X_DOT = 0, X_EQUAL = 1, X_PRODMATERN = 2 };
 
-// (x + c)^q by binary powering: q - 1 roundings at most for q <= 3, O(log q) multiplications
+// (x + c)^q: q - 1 roundings for q <= 3, binary powering (O(log q) multiplications) above
 __device__ __forceinline__ double x_powi(double b, int q) {
+    if (q == 2) return b * b;
+    if (q == 3) return b * b * b;
     double r = 1.0;
     while (q > 0) {
         if (q & 1) r *= b;
@@ -35,8 +38,8 @@ __device__ __forceinline__ double x_powi(double b, int q) {
     return r;
 }
 
-// univariate half-integer Matern polynomial in r0 = |x0_m - x1_m| * s_m with exp(-r) deferred:
-// returns poly(r0); pm = {s_m, p_m, c_0 .. c_8}
+// univariate half-integer Matern polynomial in r = |x0_m - x1_m| * s_m with exp(-r) deferred;
+// pm = {s_m, p_m, c_0 .. c_8}
 __device__ __forceinline__ double x_matern_poly(double r, const double* pm) {
     const int p = (int)pm[1];
     double poly = pm[2 + p];
@@ -44,14 +47,127 @@ __device__ __forceinline__ double x_matern_poly(double r, const double* pm) {
     return poly;
 }
 
+// one coordinate of the ProductMatern accumulation for a register tile, degree known at compile
+// time: A += r, B *= poly_P(r); 4 + P FP64 instructions per entry
+template <int P>
+__device__ __forceinline__ void x_pm_dim(double (&A)[2 * X_R], double (&B)[2 * X_R], const double* __restrict__ xa,
+                                         double2 xb, const double* __restrict__ pm) {
+    const double s = pm[0];
+    double c[P + 1];
+#pragma unroll
+    for (int i = 0; i <= P; ++i) c[i] = pm[2 + i];
+#pragma unroll
+    for (int r = 0; r < X_R; ++r) {
+        const double ra = fabs(xa[r] - xb.x) * s;
+        const double rb = fabs(xa[r] - xb.y) * s;
+        A[2 * r] += ra;
+        A[2 * r + 1] += rb;
+        if constexpr (P > 0) {
+            double pa = c[P], pb = c[P];
+#pragma unroll
+            for (int i = P - 1; i >= 0; --i) {
+                pa = pn_fma(pa, ra, c[i]);
+                pb = pn_fma(pb, rb, c[i]);
+            }
+            B[2 * r] *= pa;
+            B[2 * r + 1] *= pb;
+        }
+    }
+}
+
+// accumulate `dc` coordinates into the register tile; xa0 points at this tile's first row of the
+// staged row coordinates (coordinate stride lda), x1c is the staged column chunk
+template <int MODE>
+__device__ __forceinline__ void x_accumulate(double (&A)[2 * X_R], double (&B)[2 * X_R], const double* __restrict__ xa0,
+                                             int lda, const double* __restrict__ x1c, const double* __restrict__ pmc,
+                                             int dc, int tid) {
+    for (int m = 0; m < dc; ++m) {
+        const double2 xb = *reinterpret_cast<const double2*>(x1c + (size_t)m * X_TN + 2 * tid);
+        const double* xa = xa0 + m * lda;
+        if constexpr (MODE == X_DOT) {
+#pragma unroll
+            for (int r = 0; r < X_R; ++r) {
+                A[2 * r] = pn_fma(xa[r], xb.x, A[2 * r]);
+                A[2 * r + 1] = pn_fma(xa[r], xb.y, A[2 * r + 1]);
+            }
+        } else if constexpr (MODE == X_EQUAL) {
+#pragma unroll
+            for (int r = 0; r < X_R; ++r) {
+                A[2 * r] += (xa[r] == xb.x) ? 0.0 : 1.0;  // NaN != NaN, as in NumPy
+                A[2 * r + 1] += (xa[r] == xb.y) ? 0.0 : 1.0;
+            }
+        } else {
+            const double* pm = pmc + m * PN_PM_LD;
+            switch ((int)pm[1]) {  // uniform across the CTA
+                case 0: x_pm_dim<0>(A, B, xa, xb, pm); break;
+                case 1: x_pm_dim<1>(A, B, xa, xb, pm); break;
+                case 2: x_pm_dim<2>(A, B, xa, xb, pm); break;
+                case 3: x_pm_dim<3>(A, B, xa, xb, pm); break;
+                default:
+#pragma unroll
+                    for (int r = 0; r < X_R; ++r) {
+                        const double ra = fabs(xa[r] - xb.x) * pm[0];
+                        const double rb = fabs(xa[r] - xb.y) * pm[0];
+                        A[2 * r] += ra;
+                        A[2 * r + 1] += rb;
+                        B[2 * r] *= x_matern_poly(ra, pm);
+                        B[2 * r + 1] *= x_matern_poly(rb, pm);
+                    }
+            }
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void x_finish_store(const double (&A)[2 * X_R], const double (&B)[2 * X_R],
+                                               const PnExtraLaunch& g, const double* tabE, int64_t row0, int64_t j0) {
+    double* out = static_cast<double*>(g.out);
+#pragma unroll
+    for (int r = 0; r < X_R; ++r) {
+        double k0, k1;
+        if constexpr (MODE == X_DOT) {
+            k0 = A[2 * r] + g.constant;
+            k1 = A[2 * r + 1] + g.constant;
+            if (g.exponent != 1) {
+                k0 = x_powi(k0, g.exponent);
+                k1 = x_powi(k1, g.exponent);
+            }
+        } else if constexpr (MODE == X_EQUAL) {
+            k0 = A[2 * r] == 0.0 ? g.constant : 0.0;
+            k1 = A[2 * r + 1] == 0.0 ? g.constant : 0.0;
+        } else {
+            // exp(-sum_m r_m) once for the whole product; pn_exp2 takes its robust path for huge
+            // or non-finite arguments
+            k0 = B[2 * r] * pn_exp2(A[2 * r] * -1.4426950408889634074, tabE);
+            k1 = B[2 * r + 1] * pn_exp2(A[2 * r + 1] * -1.4426950408889634074, tabE);
+        }
+        const int64_t row = row0 + r;
+        if (row < g.n0) {
+            double* p = out + row * g.ldo + j0;
+            if (j0 + 1 < g.n1) {
+                if (g.vec_ok) pn_store_cs2(p, k0, k1);
+                else {
+                    pn_store_cs1(p, k0);
+                    pn_store_cs1(p + 1, k1);
+                }
+            } else if (j0 < g.n1) {
+                pn_store_cs1(p, k0);
+            }
+        }
+    }
+}
+
+// d <= X_DC: the strip's column coordinates are staged once per CTA, row coordinates X_RS rows at
+// a time (one barrier pair per 64 rows); d > X_DC: coordinates stream through shared memory in
+// chunks of X_DC and a CTA iteration covers one 8-row register tile.
 template <int MODE>
 __global__ void __launch_bounds__(X_THREADS)
-    gram_extra_kernel(const __grid_constant__ PnExtraLaunch g, int groups_per_cta) {
+    gram_extra_kernel(const __grid_constant__ PnExtraLaunch g, int rows_per_cta) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* tabE = reinterpret_cast<double*>(smem);                   // PRODMATERN only
     double* x1c = reinterpret_cast<double*>(smem + 8 * PN_EXP2_N);   // [X_DC][X_TN]
-    double* x0c = x1c + X_DC * X_TN;                                  // [X_DC][X_R]
-    double* pmc = x0c + X_DC * X_R;                                   // [X_DC][PN_PM_LD]
+    double* x0c = x1c + X_DC * X_TN;                                  // [X_DC][X_RS]
+    double* pmc = x0c + X_DC * X_RS;                                  // [X_DC][PN_PM_LD]
     const int tid = threadIdx.x;
     const int64_t col0 = (int64_t)blockIdx.x * X_TN;
     const int64_t j0 = col0 + 2 * tid;
@@ -60,13 +176,41 @@ __global__ void __launch_bounds__(X_THREADS)
     if constexpr (MODE == X_PRODMATERN) {
         for (int i = tid; i < PN_EXP2_N; i += X_THREADS) tabE[i] = pn_exp2_table_g[i];
     }
-    const int64_t n_groups = (g.n0 + X_R - 1) / X_R;
-    const int64_t gr0 = (int64_t)blockIdx.y * groups_per_cta;
-    const int64_t gr1 = (gr0 + groups_per_cta < n_groups) ? gr0 + groups_per_cta : n_groups;
-    const bool one_chunk = g.d <= X_DC;  // then the column chunk is staged once per CTA
+    const int64_t rbeg = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t rend = (rbeg + rows_per_cta < g.n0) ? rbeg + rows_per_cta : g.n0;
 
-    for (int64_t gr = gr0; gr < gr1; ++gr) {
-        const int64_t row0 = gr * X_R;
+    if (g.d <= X_DC) {
+        const int dc = g.d;
+        for (int idx = tid; idx < dc * X_TN; idx += X_THREADS) {
+            const int m = idx / X_TN, j = idx % X_TN;
+            x1c[idx] = x1g[(size_t)m * g.ld1 + col0 + j];  // padded to PN_PAD columns
+        }
+        if constexpr (MODE == X_PRODMATERN) {
+            for (int idx = tid; idx < dc * PN_PM_LD; idx += X_THREADS) pmc[idx] = static_cast<const double*>(g.pm)[idx];
+        }
+        for (int64_t s0 = rbeg; s0 < rend; s0 += X_RS) {
+            __syncthreads();
+            for (int idx = tid; idx < dc * X_RS; idx += X_THREADS) {
+                const int m = idx / X_RS, r = idx % X_RS;
+                x0c[idx] = (s0 + r < g.n0) ? x0g[(size_t)m * g.ld0 + s0 + r] : 0.0;
+            }
+            __syncthreads();
+            const int nrows = (rend - s0 < X_RS) ? (int)(rend - s0) : X_RS;
+            for (int rt = 0; rt < nrows; rt += X_R) {
+                double A[2 * X_R], B[2 * X_R];
+#pragma unroll
+                for (int i = 0; i < 2 * X_R; ++i) {
+                    A[i] = 0.0;
+                    B[i] = 1.0;
+                }
+                x_accumulate<MODE>(A, B, x0c + rt, X_RS, x1c, pmc, dc, tid);
+                x_finish_store<MODE>(A, B, g, tabE, s0 + rt, j0);
+            }
+        }
+        return;
+    }
+
+    for (int64_t row0 = rbeg; row0 < rend; row0 += X_R) {
         double A[2 * X_R], B[2 * X_R];  // DOT: A = sum; EQUAL: A = #differences; PRODMATERN: A = sum r, B = prod poly
 #pragma unroll
         for (int i = 0; i < 2 * X_R; ++i) {
@@ -76,78 +220,22 @@ __global__ void __launch_bounds__(X_THREADS)
         for (int c0 = 0; c0 < g.d; c0 += X_DC) {
             const int dc = (g.d - c0 < X_DC) ? g.d - c0 : X_DC;
             __syncthreads();
-            if (!one_chunk || gr == gr0) {
-                for (int idx = tid; idx < dc * X_TN; idx += X_THREADS) {
-                    const int m = idx / X_TN, j = idx % X_TN;
-                    x1c[idx] = x1g[(size_t)(c0 + m) * g.ld1 + col0 + j];  // padded to PN_PAD columns
-                }
-                if constexpr (MODE == X_PRODMATERN) {
-                    for (int idx = tid; idx < dc * PN_PM_LD; idx += X_THREADS)
-                        pmc[idx] = static_cast<const double*>(g.pm)[(size_t)c0 * PN_PM_LD + idx];
-                }
+            for (int idx = tid; idx < dc * X_TN; idx += X_THREADS) {
+                const int m = idx / X_TN, j = idx % X_TN;
+                x1c[idx] = x1g[(size_t)(c0 + m) * g.ld1 + col0 + j];
+            }
+            if constexpr (MODE == X_PRODMATERN) {
+                for (int idx = tid; idx < dc * PN_PM_LD; idx += X_THREADS)
+                    pmc[idx] = static_cast<const double*>(g.pm)[(size_t)c0 * PN_PM_LD + idx];
             }
             if (tid < dc * X_R) {
                 const int m = tid / X_R, r = tid % X_R;
-                x0c[tid] = x0g[(size_t)(c0 + m) * g.ld0 + row0 + r];  // rows padded to PN_PAD as well
+                x0c[m * X_RS + r] = (row0 + r < g.n0) ? x0g[(size_t)(c0 + m) * g.ld0 + row0 + r] : 0.0;
             }
             __syncthreads();
-            for (int m = 0; m < dc; ++m) {
-                const double2 xb = *reinterpret_cast<const double2*>(x1c + (size_t)m * X_TN + 2 * tid);
-#pragma unroll
-                for (int r = 0; r < X_R; ++r) {
-                    const double xa = x0c[m * X_R + r];
-                    if constexpr (MODE == X_DOT) {
-                        A[2 * r] = pn_fma(xa, xb.x, A[2 * r]);
-                        A[2 * r + 1] = pn_fma(xa, xb.y, A[2 * r + 1]);
-                    } else if constexpr (MODE == X_EQUAL) {
-                        A[2 * r] += (xa == xb.x) ? 0.0 : 1.0;  // NaN != NaN, as in NumPy
-                        A[2 * r + 1] += (xa == xb.y) ? 0.0 : 1.0;
-                    } else {
-                        const double* pm = pmc + m * PN_PM_LD;
-                        const double ra = fabs(xa - xb.x) * pm[0];
-                        const double rb = fabs(xa - xb.y) * pm[0];
-                        A[2 * r] += ra;
-                        A[2 * r + 1] += rb;
-                        B[2 * r] *= x_matern_poly(ra, pm);
-                        B[2 * r + 1] *= x_matern_poly(rb, pm);
-                    }
-                }
-            }
+            x_accumulate<MODE>(A, B, x0c, X_RS, x1c, pmc, dc, tid);
         }
-        double* out = static_cast<double*>(g.out);
-#pragma unroll
-        for (int r = 0; r < X_R; ++r) {
-            double k0, k1;
-            if constexpr (MODE == X_DOT) {
-                k0 = A[2 * r] + g.constant;
-                k1 = A[2 * r + 1] + g.constant;
-                if (g.exponent != 1) {
-                    k0 = x_powi(k0, g.exponent);
-                    k1 = x_powi(k1, g.exponent);
-                }
-            } else if constexpr (MODE == X_EQUAL) {
-                k0 = A[2 * r] == 0.0 ? g.constant : 0.0;
-                k1 = A[2 * r + 1] == 0.0 ? g.constant : 0.0;
-            } else {
-                // exp(-sum_m r_m) once for the whole product; pn_exp2 takes the robust path for
-                // huge or non-finite arguments
-                k0 = B[2 * r] * pn_exp2(A[2 * r] * -1.4426950408889634074, tabE);
-                k1 = B[2 * r + 1] * pn_exp2(A[2 * r + 1] * -1.4426950408889634074, tabE);
-            }
-            const int64_t row = row0 + r;
-            if (row < g.n0) {
-                double* p = out + row * g.ldo + j0;
-                if (j0 + 1 < g.n1) {
-                    if (g.vec_ok) pn_store_cs2(p, k0, k1);
-                    else {
-                        pn_store_cs1(p, k0);
-                        pn_store_cs1(p + 1, k1);
-                    }
-                } else if (j0 < g.n1) {
-                    pn_store_cs1(p, k0);
-                }
-            }
-        }
+        x_finish_store<MODE>(A, B, g, tabE, row0, j0);
     }
 }
 
@@ -214,18 +302,19 @@ __global__ void __launch_bounds__(256) combine_kernel(double* __restrict__ dst, 
 template <int MODE>
 cudaError_t launch_gram_mode(const PnExtraLaunch& g, cudaStream_t stream) {
     const int64_t strips = (g.n1 + X_TN - 1) / X_TN;
-    const int64_t n_groups = (g.n0 + X_R - 1) / X_R;
-    // ~16 CTAs per SM; at least one row group each
-    int64_t gpc = (n_groups * strips) / (148 * 16);
-    gpc = gpc < 1 ? 1 : (gpc > 64 ? 64 : gpc);
-    const int64_t gy = (n_groups + gpc - 1) / gpc;
+    // ~16 CTAs per SM; whole row stages per CTA
+    const int64_t unit = g.d <= X_DC ? X_RS : X_R;
+    const int64_t n_units = (g.n0 + unit - 1) / unit;
+    int64_t upc = (n_units * strips) / (148 * 16);
+    upc = upc < 1 ? 1 : (upc > 64 ? 64 : upc);
+    const int64_t gy = (n_units + upc - 1) / upc;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
-    const size_t smem = 8 * PN_EXP2_N + sizeof(double) * (X_DC * X_TN + X_DC * X_R + X_DC * PN_PM_LD);
+    const size_t smem = 8 * PN_EXP2_N + sizeof(double) * (X_DC * X_TN + X_DC * X_RS + X_DC * PN_PM_LD);
     auto kern = gram_extra_kernel<MODE>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)strips, (unsigned)gy);
-    kern<<<grid, X_THREADS, smem, stream>>>(g, (int)gpc);
+    kern<<<grid, X_THREADS, smem, stream>>>(g, (int)(upc * unit));
     ++g_pn_launches;
     return cudaGetLastError();
 }

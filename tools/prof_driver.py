@@ -34,6 +34,23 @@ if what in ("gram", "all"):
         print(type(k).__name__, "gram ms", op.last_kernel_ms())
         op.close()
     del out
+if what == "extra":  # SURVEY.md 8f N3 kernels: Linear, ProductMatern Gram and the combine kernel
+    import ctypes
+
+    x = torch.from_numpy(rng.normal(size=(n, 3))).to(dev)
+    out = torch.empty((n, n), dtype=torch.float64, device=dev)
+    tmp = torch.empty((n, n), dtype=torch.float64, device=dev)
+    for k in (pb.Linear((3,), constant=0.5), pb.ProductMatern((3,), lengthscales=1.0, nus=2.5)):
+        op = _lib.Operator(k._kernel_params(), x.data_ptr(), None, on_device=True, n0=n, n1=n, dtype=np.float64)
+        for _ in range(reps):
+            op.gram_device(out.data_ptr(), n, stream=stream)
+        torch.cuda.synchronize()
+        print(type(k).__name__, "gram ms", op.last_kernel_ms())
+        op.close()
+    for _ in range(reps):
+        _lib.load().pncov_combine_device(0, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(tmp.data_ptr()), n * n, 0,
+                                         1.0, 0.5, None)
+    torch.cuda.synchronize()
 if what in ("matvec", "all"):
     x = torch.from_numpy(rng.normal(size=(nm, 8))).to(dev)
     v = torch.from_numpy(rng.normal(size=(nm, 1))).to(dev)
