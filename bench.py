@@ -326,7 +326,8 @@ def run_ours(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as fh:
-            traffic = json.load(fh).get("gram_fast_kernel_bytes_per_launch")
+            tr = json.load(fh)
+            traffic = tr.get("gram_sym_kernel_bytes_per_launch" if dom == "matern52" else "gram_fast_kernel_bytes_per_launch")
     roofline = {
         "bound": "hbm", "kernel": (f"gram_sym_kernel<D=3, {dom}> (upper triangle + mirrored stores)" if dom == "matern52"
                                     else f"gram_fast_kernel<D=3, {dom}>"),
