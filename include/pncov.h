@@ -135,6 +135,20 @@ PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ld
 PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y,
                         int64_t ldy, int transpose, void* stream);
 
+/* Symmetric operators (x1 == NULL at creation), one right-hand side, float64, norm-identity kernel
+ * admissible: pncov_matmul* evaluate every off-diagonal tile of K once and use it for both y_I and
+ * y_J (half the exp / DMMA work; the partial sums are combined with atomic adds, so the summation
+ * order, not the set of addends, varies between runs; PNCOV_MATVEC_SYM=off in the environment
+ * selects the order-preserving kernel).
+ * pncov_matmul_sym_part_device is the multi-GPU form: caller `part` of `nparts` (one per GPU, each
+ * with a handle over the SAME full point set) gets the contribution of row blocks part,
+ * part + nparts, ... in the full-length vector y (n0 doubles, device memory, overwritten); the sum
+ * of all parts (an all-reduce) is K @ v.  This is the reduce-scatter form of the row-sharded
+ * product + all-gather named in SURVEY.md 8e.  Returns PNCOV_ENOTIMPL when the symmetric kernel
+ * does not apply to the handle. */
+PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void* y, int part, int nparts,
+                                           void* stream);
+
 /* elementwise evaluation out[b] = k(x0[b], x1[b]) -------------------------------------
  * replaces the broadcasting path of CovarianceFunction.__call__
  * (_covariance_function.py:280-357) after the caller has broadcast both arguments
@@ -169,7 +183,7 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
 PNCOV_API int64_t pncov_launch_count(void);
 /* which kernel family serves pncov_matmul for this handle: 0 = not decided yet (no product
  * so far), 1 = norm-identity + DMMA (ExpQuad / RatQuad, d <= 8, error bound satisfied),
- * 2 = direct differences */
+ * 2 = direct differences, 3 = norm-identity + DMMA with symmetric halving */
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path);
 PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "pncov_matmul": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int]),
     "pncov_matmul_device": (
         ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int, _c_vp]),
+    "pncov_matmul_sym_part_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
     "pncov_pairs": (
         ctypes.c_int,
         [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64, ctypes.c_double,
@@ -254,7 +255,14 @@ class Operator:
         """'undecided', 'norm-identity-dmma' or 'direct-differences' (see pncov_matmul_path)."""
         p = ctypes.c_int()
         _check(self._lib.pncov_matmul_path(self._h, ctypes.byref(p)))
-        return ("undecided", "norm-identity-dmma", "direct-differences")[p.value]
+        return ("undecided", "norm-identity-dmma", "direct-differences", "norm-identity-dmma-symmetric")[p.value]
+
+    def matmul_sym_part_device(self, v_ptr: int, y_ptr: int, part: int, nparts: int, stream: int = 0) -> None:
+        """Contribution of row blocks ``part, part + nparts, ...`` to ``K @ v`` (full-length ``y``);
+        the sum over all parts is the product.  Raises NotImplementedError if the symmetric kernel
+        does not apply (then use row sharding)."""
+        _check(self._lib.pncov_matmul_sym_part_device(self._h, _c_vp(v_ptr), _c_vp(y_ptr), int(part), int(nparts),
+                                                      _c_vp(stream)))
 
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_float()

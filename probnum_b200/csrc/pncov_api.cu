@@ -404,6 +404,7 @@ struct pncov_handle {
     bool used_foreign_stream = false;  // a *_device entry point ran on a caller-owned stream
     // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
+    bool last_sym = false;       // the last product ran the symmetric-halving kernel
     void* a12[2] = {nullptr, nullptr};  // per point set (0: x0, 1: x1); aliases when symmetric
     void* b12[2] = {nullptr, nullptr};
     PnEpiParams mma_epi{};
@@ -621,8 +622,11 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     return 0;
 }
 
+// sym_nparts > 0 asks for the symmetric-halving kernel restricted to row blocks sym_part, sym_part +
+// sym_nparts, ... (the caller sums the partial vectors of all parts); it fails with PNCOV_ENOTIMPL
+// when that kernel does not apply to this handle.  sym_nparts == 0: whole product, best kernel.
 int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy,
-                       bool transpose, cudaStream_t stream) {
+                       bool transpose, cudaStream_t stream, int sym_part = 0, int sym_nparts = 0) {
     const Points& R = transpose ? h->p1 : h->p0;
     const Points& C = transpose ? h->p0 : h->p1;
     const size_t es = h->k.elem();
@@ -659,6 +663,19 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.a12 = h->a12[transpose ? 1 : 0];
         m.b12 = h->b12[transpose ? 0 : 1];
         m.epi = h->mma_epi;
+    }
+    {
+        // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
+        // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
+        const char* symenv = getenv("PNCOV_MATVEC_SYM");
+        const bool sym_ok = h->symmetric && m.use_mma == 2 && kc_max == 1 && es == 8 && R.n >= 2048 &&
+                            !(symenv && strcmp(symenv, "off") == 0);
+        if (sym_nparts > 0 && !sym_ok)
+            return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64 and the norm-identity kernel");
+        m.sym = sym_ok ? 1 : 0;
+        m.sym_part = sym_part;
+        m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;
+        h->last_sym = m.sym != 0;
     }
     PN_CUDA(pn_plan_matvec(m, h->sm_count));
     const int jsplit = m.jsplit;
@@ -909,6 +926,21 @@ PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int
     return 0;
 }
 
+PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void* y, int part, int nparts, void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNCOV_EINVAL, "bad part / nparts");
+    if (!v || !y) return fail(PNCOV_EINVAL, "NULL operand");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
+    PN_CUDA(cudaEventRecord(h->ev0, stream));
+    int rc = matmul_device_impl(h, v, 1, 1, y, 1, false, stream, part, nparts);
+    if (rc) return rc;
+    PN_CUDA(cudaEventRecord(h->ev1, stream));
+    h->timed = true;
+    return 0;
+}
+
 PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy, int transpose) {
     if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
     if (k < 0 || ldv < k || ldy < k) return fail(PNCOV_EINVAL, "bad column count / leading dimension");
@@ -1057,7 +1089,7 @@ PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
 
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {
     if (!h || !path) return fail(PNCOV_EINVAL, "NULL argument");
-    *path = h->mma_state == 0 ? 0 : (h->mma_state == 1 ? 1 : 2);
+    *path = h->mma_state == 0 ? 0 : (h->mma_state == 1 ? (h->last_sym ? 3 : 1) : 2);
     return 0;
 }
 

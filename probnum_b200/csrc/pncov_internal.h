@@ -45,6 +45,10 @@ struct PnMatvecLaunch {
     const void* a12;
     const void* b12;
     int use_mma;         // 0: direct differences, 1: norm identity with DFMA, 2: norm identity with DMMA
+    // symmetric halving (x1 is x0, kc == 1, use_mma == 2): each off-diagonal tile is evaluated once
+    // and serves y_I and y_J; row blocks part, part + nparts, ... only (multi-GPU), y accumulated
+    // with atomics from zero
+    int sym, sym_part, sym_nparts;
     int in_f32;
     PnEpiParams epi;
 };

@@ -362,6 +362,167 @@ __global__ void __launch_bounds__(MM_THREADS)
     }
 }
 
+// ---- symmetric variant: x1 is x0, one right-hand side ------------------------------------------------
+// K is symmetric, so an off-diagonal tile pair (I, J) / (J, I) needs its kernel values only once:
+// the CTA of row block I walks the column tiles J >= I, accumulates y_I += K_IJ v_J in registers
+// as above and ALSO y_J += K_IJ^T v_I: per 8-column step one more DFMA per pair, a shuffle
+// reduction over the eight lanes that hold the same columns, a per-warp slot in shared memory,
+// and once per tile 128 `red.global.add.f64` (one per column).  The exp2 / DMMA work per
+// ordered pair halves: 19.25 instead of 35 FP64-pipe slots per two ordered pairs.  Row sums leave
+// through the same atomics at the end of the CTA, so y must be zero on entry (the launcher
+// memsets it) and the summation order of a component is not fixed: results agree to rounding
+// between runs, not bit-for-bit (PNCOV_MATVEC_SYM=off selects the order-preserving kernel).
+// Row blocks are dealt round-robin to `nparts` callers (multi-GPU: rank r takes blocks
+// I = r mod nparts and the partial vectors are summed by an all-reduce).
+template <int KSTEPS, int EPI>
+__global__ void __launch_bounds__(MM_THREADS)
+    matvec_mma_sym_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split, int part, int nparts) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    constexpr int STAGE_DOUBLES = MM_TJ * (MM_LD + 1);
+    double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
+    double* colw = stage0 + 2 * STAGE_DOUBLES;  // [2][warps][MM_TJ] per-warp column sums of a tile
+
+    static_assert(MM_ROWS == MM_TJ, "row blocks and column tiles must coincide on the diagonal");
+    const int64_t n_jt = a.n1pad / MM_TJ;
+    const int64_t bx = (int64_t)blockIdx.x * nparts + part;  // this CTA's row block = its diagonal tile
+    if (bx >= n_jt) return;
+    int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+    if (jt0 < bx) jt0 = bx;
+    if (jt0 >= jt1) return;
+    const double* bg = static_cast<const double*>(a.b12);
+    const double* vg = static_cast<const double*>(a.v);
+    double* yg = static_cast<double*>(a.y);
+    constexpr uint32_t B_BYTES = MM_TJ * MM_LD * 8, V_BYTES = MM_TJ * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_init(&bars[2], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], B_BYTES + V_BYTES);
+        pn_bulk_g2s(stage0, bg + jt0 * MM_TJ * MM_LD, B_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + MM_TJ * MM_LD, vg + jt0 * MM_TJ, V_BYTES, &bars[0]);
+        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
+    }
+
+    const int64_t row0 = bx * MM_ROWS + warp * (MM_RG * 8);
+    double af[MM_RG][KSTEPS], nx[MM_RG], vrow[MM_RG], acc[MM_RG];
+    {
+        const double* ag = static_cast<const double*>(a.a12);
+#pragma unroll
+        for (int rg = 0; rg < MM_RG; ++rg) {
+            const int64_t row = row0 + rg * 8 + g;
+            const double* pr = ag + row * MM_LD;  // rows are padded to PN_PAD
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) af[rg][kk] = pr[4 * kk + q];
+            nx[rg] = pr[8];
+            vrow[rg] = vg[row];  // zero in the padding, so padded rows add nothing to column sums
+            acc[rg] = 0.0;
+        }
+    }
+    pn_mbar_wait(&bars[2], 0);
+
+    int it = 0;
+    for (int64_t jt = jt0; jt < jt1; ++jt, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && jt + 1 < jt1) {
+            double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
+            pn_mbar_expect_tx(&bars[buf ^ 1], B_BYTES + V_BYTES);
+            pn_bulk_g2s(dst, bg + (jt + 1) * MM_TJ * MM_LD, B_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + MM_TJ * MM_LD, vg + (jt + 1) * MM_TJ, V_BYTES, &bars[buf ^ 1]);
+        }
+        // column sums of the previous tile: one atomic per column (the slot was completed before
+        // the barrier that ended the previous iteration)
+        if (it > 0 && jt - 1 > bx) {
+            const double* cw = colw + (buf ^ 1) * (MM_THREADS / 32) * MM_TJ;
+            double s = cw[tid];
+#pragma unroll
+            for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * MM_TJ + tid];
+            const int64_t col = (jt - 1) * MM_TJ + tid;
+            if (col < a.n1) atomicAdd(yg + col, s);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
+        const double* vt = bt + MM_TJ * MM_LD;
+        double* cw = colw + buf * (MM_THREADS / 32) * MM_TJ + warp * MM_TJ;
+        const bool mirror = jt > bx;  // uniform; the diagonal tile holds both (i, j) and (j, i) itself
+
+#pragma unroll 1
+        for (int jj = 0; jj < MM_TJ; jj += 8 * MM_NS) {
+            double S[MM_NS][2 * MM_RG];
+#pragma unroll
+            for (int s = 0; s < MM_NS; ++s) {
+                const int j = jj + 8 * s;
+                double bf[KSTEPS];
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * MM_LD + 4 * kk + q];
+                const double ny0 = bt[(j + 2 * q) * MM_LD + 8];
+                const double ny1 = bt[(j + 2 * q + 1) * MM_LD + 8];
+#pragma unroll
+                for (int rg = 0; rg < MM_RG; ++rg) {
+                    double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
+                    S[s][2 * rg] = c0;
+                    S[s][2 * rg + 1] = c1;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < MM_NS; ++s) {
+                const int j = jj + 8 * s;
+                mv_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
+                const double2 v01 = *reinterpret_cast<const double2*>(vt + j + 2 * q);
+                double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                for (int rg = 0; rg < MM_RG; ++rg) {
+                    acc[rg] = pn_fma(S[s][2 * rg], v01.x, acc[rg]);
+                    acc[rg] = pn_fma(S[s][2 * rg + 1], v01.y, acc[rg]);
+                    t0 = pn_fma(S[s][2 * rg], vrow[rg], t0);
+                    t1 = pn_fma(S[s][2 * rg + 1], vrow[rg], t1);
+                }
+                if (mirror) {
+                    // sum over the 8 lanes (g = 0..7) that hold columns 2q, 2q + 1 of this step
+#pragma unroll
+                    for (int m = 4; m < 32; m <<= 1) {
+                        t0 += __shfl_xor_sync(0xffffffffu, t0, m);
+                        t1 += __shfl_xor_sync(0xffffffffu, t1, m);
+                    }
+                    if (g == 0) *reinterpret_cast<double2*>(cw + j + 2 * q) = make_double2(t0, t1);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // column sums of the last tile
+    if (jt1 - 1 > bx) {
+        const double* cw = colw + ((it - 1) & 1) * (MM_THREADS / 32) * MM_TJ;
+        double s = cw[tid];
+#pragma unroll
+        for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * MM_TJ + tid];
+        const int64_t col = (jt1 - 1) * MM_TJ + tid;
+        if (col < a.n1) atomicAdd(yg + col, s);
+    }
+    // row sums
+#pragma unroll
+    for (int rg = 0; rg < MM_RG; ++rg) {
+        const int64_t row = row0 + rg * 8 + g;
+        double s = acc[rg];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0 && row < a.n0) atomicAdd(yg + row, s);
+    }
+}
+
 // ---- generic kernel: any d <= 1024, float64 or float32 points ---------------------------------
 // One row per thread, its point read through L1 each time; column points in coordinate-major
 // shared-memory tiles, four columns per register tile.  Slower than the main kernel (extra
@@ -625,6 +786,39 @@ cudaError_t launch_mma_epi(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t st
     }
 }
 
+template <int KSTEPS, int EPI>
+cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
+    auto kern = matvec_mma_sym_kernel<KSTEPS, EPI>;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MM_TJ * (MM_LD + 1) +
+                        2 * sizeof(double) * (MM_THREADS / 32) * MM_TJ;
+    const int64_t n_jt = a.n1pad / MM_TJ;
+    const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
+    const int64_t row_ctas = (n_jt + nparts - 1) / nparts;
+    // chunks of column tiles: short enough to balance the triangle, long enough to amortise the prologue
+    int64_t tps = 256;
+    while (tps > 8 && row_ctas * ((n_jt + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    const int64_t chunks = (n_jt + tps - 1) / tps;
+    if (chunks > 65535) return cudaErrorInvalidConfiguration;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(a.y, 0, (size_t)a.n0 * sizeof(double), stream)) != cudaSuccess) return err;
+    dim3 grid((unsigned)row_ctas, (unsigned)chunks);
+    kern<<<grid, MM_THREADS, smem, stream>>>(a, (int)tps, a.sym_part, nparts);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int KSTEPS>
+cudaError_t launch_mma_sym_epi(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_mma_sym<KSTEPS, PN_EPI_EXPQUAD>(a, stream);
+        case PN_EPI_RATQUAD1: return launch_mma_sym<KSTEPS, PN_EPI_RATQUAD1>(a, stream);
+        case PN_EPI_RATQUAD2: return launch_mma_sym<KSTEPS, PN_EPI_RATQUAD2>(a, stream);
+        case PN_EPI_RATQUADG: return launch_mma_sym<KSTEPS, PN_EPI_RATQUADG>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_mma_any(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     const bool two = a.d > 4;
     if (a.kc == 1) return two ? launch_mma_epi<2, 1>(a, sm, plan, stream) : launch_mma_epi<1, 1>(a, sm, plan, stream);
@@ -666,6 +860,10 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
         a.jsplit = 1;
         return cudaSuccess;
     }
+    if (a.use_mma == 2 && a.sym) {
+        a.jsplit = 1;  // no partial buffers: the symmetric kernel accumulates with atomics
+        return cudaSuccess;
+    }
     if (a.use_mma == 2) return launch_mma_any(a, sm_count, true, nullptr);
     if (a.use_mma == 1) return launch_ident_d(a, sm_count, true, nullptr);
     if (uses_main_kernel(a)) {
@@ -686,7 +884,9 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     const int64_t ld1 = a.ld1;
     const bool ard = a.scale != nullptr;
     cudaError_t err;
-    if (a.use_mma == 2) {
+    if (a.use_mma == 2 && a.sym) {
+        return a.d > 4 ? launch_mma_sym_epi<2>(a, stream) : launch_mma_sym_epi<1>(a, stream);
+    } else if (a.use_mma == 2) {
         err = launch_mma_any(a, sm_count, false, stream);
     } else if (a.use_mma == 1) {
         err = launch_ident_d(a, sm_count, false, stream);

@@ -10,6 +10,13 @@ iterate), so nothing else is exchanged.
 
 This is the only communication step of the path; it moves N0*K*8 bytes per product
 (8 MiB at N = 2^20, K = 1) next to O(N0*N1*d) flops, so it is latency-sized.
+
+Symmetric operators (``x1 is None``) with one right-hand side take the reduce form of the same
+exchange ("symmetric-halving ... reduce-scatter"): every rank holds the whole point
+set, evaluates each off-diagonal tile of its round-robin share of row blocks ONCE for both
+``y_I`` and ``y_J`` (``pncov_matmul_sym_part_device``), and the full-length partial vectors are
+summed with one all-reduce.  Half the kernel evaluations per product; still one collective of
+N0*8 bytes.
 """
 
 from __future__ import annotations
@@ -46,7 +53,8 @@ class ShardedCovarianceOperator:
     """
 
     def __init__(self, covfunc, x0, x1=None, *, group=None,
-                 local_factory: Optional[Callable] = None, device: Optional[int] = None):
+                 local_factory: Optional[Callable] = None, device: Optional[int] = None,
+                 symmetric: bool = True):
         dist = _dist()
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
@@ -54,6 +62,7 @@ class ShardedCovarianceOperator:
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         x0 = covfunc._preprocess_linop_input(x0, argnum=0)
+        is_symmetric = x1 is None
         x1 = x0 if x1 is None else covfunc._preprocess_linop_input(x1, argnum=1)
         self.shape = (x0.shape[0], x1.shape[0])
         dt = covfunc._compute_dtype(x0, x1)
@@ -66,6 +75,17 @@ class ShardedCovarianceOperator:
             self.local = _lib.Operator(covfunc._kernel_params(), rows, cols, device=device)
         else:
             self.local = local_factory(covfunc._kernel_params(), rows, cols)
+        # symmetric halving: a second operator over the whole point set (x1 = None).  Whether the
+        # symmetric kernel applies to this data is known after the first product (the library
+        # answers NotImplementedError, identically on every rank); then the row shards serve.
+        self.local_sym = None
+        params = covfunc._kernel_params()
+        if symmetric and is_symmetric and self.world > 1 and dt == np.float64:
+            if local_factory is None:
+                if params.kind in (_lib.EXPQUAD, _lib.RATQUAD) and params.d <= 8 and self.shape[0] >= 2048:
+                    self.local_sym = _lib.Operator(params, cols, None, device=device)
+            else:
+                self.local_sym = local_factory(params, cols, None)
 
     # -- host operands (NumPy in, NumPy out; gloo or NCCL via a staging tensor) -------------------
     def matmul(self, v: np.ndarray) -> np.ndarray:
@@ -76,6 +96,10 @@ class ShardedCovarianceOperator:
         vec = v.ndim == 1
         v2 = np.ascontiguousarray(v.reshape(v.shape[0], -1), dtype=self.dtype)
         k = v2.shape[1]
+        if self.local_sym is not None and k == 1:
+            y = self._matmul_symmetric_host(v2)
+            if y is not None:
+                return y[:, 0] if vec else y
         y_local = self.local.matmul(v2)  # (hi - lo, k)
         pad = np.zeros((self.max_rows, k), dtype=self.dtype)
         pad[: self.hi - self.lo] = y_local
@@ -89,6 +113,38 @@ class ShardedCovarianceOperator:
         sizes = [hi - lo for lo, hi in (shard_bounds(self.shape[0], self.world, r) for r in range(self.world))]
         out = np.concatenate([g[r, :sizes[r]] for r in range(self.world)], axis=0)
         return out[:, 0] if vec else out
+
+    def _matmul_symmetric_host(self, v2: np.ndarray) -> Optional[np.ndarray]:
+        """One column, symmetric operator: partial vector of this rank's row blocks + all-reduce."""
+        import torch  # noqa: PLC0415
+
+        dist = _dist()
+        backend = dist.get_backend(self.group)
+        if hasattr(self.local_sym, "matmul_sym_part"):  # CPU stand-in of the gloo tests
+            part = torch.from_numpy(np.ascontiguousarray(self.local_sym.matmul_sym_part(v2, self.rank, self.world)))
+            if backend == "nccl":
+                part = part.cuda()
+        else:
+            vd = torch.from_numpy(v2).cuda(self.local_sym.device)
+            part = self._sym_part_device(vd)
+            if part is None:
+                return None
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return part.cpu().numpy()
+
+    def _sym_part_device(self, v):
+        """This rank's partial vector (CUDA tensor) or None if the symmetric kernel does not apply."""
+        import torch  # noqa: PLC0415
+
+        part = torch.empty((self.shape[0], 1), dtype=v.dtype, device=v.device)
+        stream = torch.cuda.current_stream(v.device).cuda_stream
+        try:
+            self.local_sym.matmul_sym_part_device(v.data_ptr(), part.data_ptr(), self.rank, self.world, stream=stream)
+        except NotImplementedError:
+            self.local_sym.close()
+            self.local_sym = None
+            return None
+        return part
 
     def __matmul__(self, v):
         return self.matmul(np.asarray(v))
@@ -108,6 +164,14 @@ class ShardedCovarianceOperator:
             raise ValueError("v must be a contiguous (N1, K) CUDA tensor")
         k = v.shape[1]
         rows = self.hi - self.lo
+        if self.local_sym is not None and k == 1 and v.dtype == torch.float64:
+            part = self._sym_part_device(v)
+            if part is not None:
+                dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+                if out is None:
+                    return part
+                out.copy_(part)
+                return out
         if out is None:
             out = torch.empty((n0, k), dtype=v.dtype, device=v.device)
         y_local = out[self.lo:self.hi]  # contiguous row block of the result
@@ -121,3 +185,6 @@ class ShardedCovarianceOperator:
     def close(self):
         if hasattr(self.local, "close"):
             self.local.close()
+        if self.local_sym is not None and hasattr(self.local_sym, "close"):
+            self.local_sym.close()
+            self.local_sym = None

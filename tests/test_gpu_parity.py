@@ -426,7 +426,7 @@ def test_config3_matvec_2pow20():
     v = rng.normal(size=n)
     L = make_kernel(spec).linop(x)
     y = L @ v
-    assert L._device_op().matmul_path() == "norm-identity-dmma"
+    assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
     rows = rng.choice(n, size=24, replace=False)
     Kr = orc.gram(spec, x[rows], x, row_block=8)
     assert_matvec_close(y[rows], Kr @ v, np.abs(Kr) @ np.abs(v), 1e-12)
@@ -450,3 +450,68 @@ def test_wide_right_hand_sides(k_cols):
         L = make_kernel(spec).linop(x0, x1)
         assert_matvec_close(L @ v, orc.matvec(spec, x0, x1, v), orc.abs_matvec(spec, x0, x1, v), 1e-12)
         L.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# symmetric halving of the matrix-free product (x1 is x0, one right-hand side)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,d,n", [("expquad", 8, 5000), ("expquad", 3, 2177), ("ratquad", 4, 4096),
+                                      ("ratquad", 8, 6001)])
+def test_symmetric_matvec_matches_oracle(kind, d, n):
+    rng = np.random.default_rng(n)
+    spec = orc.KernelSpec(kind, (d,), 0.9, alpha=1.5)
+    k = make_kernel(spec)
+    x = rng.normal(size=(n, d))
+    L = k.linop(x)
+    for v in (rng.normal(size=(n, 1)), rng.uniform(size=(n, 1))):
+        y = L._matmul_device(v)
+        assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
+        assert_matvec_close(y, orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
+    # several columns take the ordered kernel and must agree with the one-column results
+    V = rng.normal(size=(n, 3))
+    Y = L._matmul_device(V)
+    assert L._device_op().matmul_path() == "norm-identity-dmma"
+    y0 = L._matmul_device(V[:, :1])
+    bound = orc.abs_matvec(spec, x, None, V[:, :1])
+    assert np.all(np.abs(Y[:, :1] - y0) <= 1e-13 * bound)
+    L.close()
+
+
+def test_symmetric_matvec_parts_sum_to_the_product():
+    """pncov_matmul_sym_part_device: the multi-GPU decomposition, here all parts on one device."""
+    import torch
+
+    from probnum_b200 import _lib
+
+    n, d = 3333, 8
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(n, d))
+    v = rng.normal(size=(n, 1))
+    spec = orc.KernelSpec("expquad", (d,), 1.0)
+    op = _lib.Operator(make_kernel(spec)._kernel_params(), x)
+    vd = torch.from_numpy(v).cuda()
+    total = torch.zeros((n, 1), dtype=torch.float64, device="cuda")
+    part = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+    for p in range(3):
+        op.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), p, 3)
+        torch.cuda.synchronize()
+        total += part
+    assert_matvec_close(total.cpu().numpy(), orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
+    op.close()
+    # a kernel without the identity path (Matern) reports that the decomposition does not apply
+    opm = _lib.Operator(pb.Matern((d,), nu=1.5)._kernel_params(), x)
+    with pytest.raises(NotImplementedError):
+        opm.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
+    opm.close()
+
+
+def test_symmetric_matvec_can_be_switched_off(monkeypatch):
+    monkeypatch.setenv("PNCOV_MATVEC_SYM", "off")
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(2500, 5))
+    v = rng.normal(size=(2500, 1))
+    L = pb.ExpQuad((5,)).linop(x)
+    y1 = L._matmul_device(v)
+    assert L._device_op().matmul_path() == "norm-identity-dmma"
+    np.testing.assert_array_equal(L._matmul_device(v), y1)  # the ordered kernel is bit-reproducible
+    L.close()

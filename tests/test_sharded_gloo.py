@@ -26,11 +26,27 @@ class OracleLocal:
     device = 0
 
     def __init__(self, params, rows, cols):
-        assert params.d == 3 and rows.flags.c_contiguous and cols.flags.c_contiguous
+        assert params.d == 3 and rows.flags.c_contiguous and (cols is None or cols.flags.c_contiguous)
         self.rows, self.cols = rows, cols
 
     def matmul(self, v):
-        return orc.matvec(SPEC, self.rows, self.cols, v)
+        return orc.matvec(SPEC, self.rows, self.cols if self.cols is not None else self.rows, v)
+
+    def matmul_sym_part(self, v, part, nparts, block=16):
+        """Contribution of row blocks part, part + nparts, ... to K @ v, each off-diagonal tile
+        used for y_I and y_J (the decomposition of pncov_matmul_sym_part_device)."""
+        x = self.rows
+        n = x.shape[0]
+        y = np.zeros((n, v.shape[1]))
+        nb = (n + block - 1) // block
+        for bi in range(part, nb, nparts):
+            i0, i1 = bi * block, min((bi + 1) * block, n)
+            y[i0:i1] += orc.gram(SPEC, x[i0:i1], x[i0:i1]) @ v[i0:i1]
+            if i1 < n:
+                K = orc.gram(SPEC, x[i0:i1], x[i1:])
+                y[i0:i1] += K @ v[i1:]
+                y[i1:] += K.T @ v[i0:i1]
+        return y
 
 
 def _worker(rank, world, port, n0, n1, out):
@@ -56,6 +72,14 @@ def _worker(rank, world, port, n0, n1, out):
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
         assert all(torch.equal(g, gathered[0]) for g in gathered)
+        # symmetric operator, one column: partial vectors + all-reduce
+        ops = ShardedCovarianceOperator(k, x0, None, local_factory=OracleLocal)
+        assert ops.local_sym is not None
+        ys = ops @ v[:n0, 0] if n0 <= n1 else ops @ np.resize(v[:, 0], n0)
+        vs = v[:n0, 0] if n0 <= n1 else np.resize(v[:, 0], n0)
+        np.testing.assert_allclose(ys, orc.matvec(SPEC, x0, None, vs[:, None])[:, 0], rtol=1e-12, atol=1e-13)
+        ys2 = ops @ np.stack([vs, vs], axis=1)  # two columns: row-sharded path
+        np.testing.assert_allclose(ys2[:, 1], ys, rtol=1e-12, atol=1e-13)
         out[rank] = 1
     finally:
         dist.destroy_process_group()

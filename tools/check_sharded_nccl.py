@@ -37,6 +37,25 @@ for (n0, n1, d, kernel, spec) in [
         yd = op.matmul_device(vd).cpu().numpy()     # device operands, in-place all-gather
         assert np.all(np.abs(yd - want) <= 1e-12 * bound), f"rank {rank}: device path mismatch"
     op.close()
+# symmetric operators, one column: round-robin row blocks + all-reduce (pncov_matmul_sym_part_device)
+for (n, d, kernel, spec) in [
+    (5003, 8, pb.ExpQuad((8,)), orc.KernelSpec("expquad", (8,), 1.0)),
+    (4096, 3, pb.RatQuad((3,), alpha=2.0), orc.KernelSpec("ratquad", (3,), 1.0, alpha=2.0)),
+    (4096, 3, pb.Matern((3,), nu=1.5), orc.KernelSpec("matern", (3,), 1.0, nu=1.5)),  # falls back to row shards
+]:
+    x = rng.normal(size=(n, d))
+    v = rng.normal(size=(n, 1))
+    op = ShardedCovarianceOperator(kernel, x, None, device=local)
+    want = orc.matvec(spec, x, None, v)
+    bound = orc.abs_matvec(spec, x, None, v)
+    y = op @ v
+    assert np.all(np.abs(y - want) <= 1e-12 * bound), f"rank {rank}: symmetric host path mismatch"
+    used_sym = op.local_sym is not None
+    assert used_sym == (spec.kind != "matern"), (spec.kind, used_sym)
+    if n % world == 0:
+        yd = op.matmul_device(torch.from_numpy(v).to(dev)).cpu().numpy()
+        assert np.all(np.abs(yd - want) <= 1e-12 * bound), f"rank {rank}: symmetric device path mismatch"
+    op.close()
 dist.barrier()
 if rank == 0:
     print(f"sharded NCCL check ok on {world} GPUs")
