@@ -374,8 +374,11 @@ __global__ void __launch_bounds__(MM_THREADS)
 // between runs, not bit-for-bit (PNCOV_MATVEC_SYM=off selects the order-preserving kernel).
 // Row blocks are dealt round-robin to `nparts` callers (multi-GPU: rank r takes blocks
 // I = r mod nparts and the partial vectors are summed by an all-reduce).
+#ifndef MMS_MINB
+#define MMS_MINB 4
+#endif
 template <int KSTEPS, int EPI>
-__global__ void __launch_bounds__(MM_THREADS)
+__global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
     matvec_mma_sym_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split, int part, int nparts) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
