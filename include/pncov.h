@@ -135,8 +135,8 @@ PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ld
 PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y,
                         int64_t ldy, int transpose, void* stream);
 
-/* Symmetric operators (x1 == NULL at creation), one right-hand side, float64, norm-identity kernel
- * admissible: pncov_matmul* evaluate every off-diagonal tile of K once and use it for both y_I and
+/* Symmetric operators (x1 == NULL at creation), one right-hand side, float64, d <= 8, n >= 2048:
+ * pncov_matmul* evaluate every off-diagonal tile of K once and use it for both y_I and
  * y_J (half the exp / DMMA work; the partial sums are combined with atomic adds, so the summation
  * order, not the set of addends, varies between runs; PNCOV_MATVEC_SYM=off in the environment
  * selects the order-preserving kernel).
@@ -183,7 +183,8 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
 PNCOV_API int64_t pncov_launch_count(void);
 /* which kernel family serves pncov_matmul for this handle: 0 = not decided yet (no product
  * so far), 1 = norm-identity + DMMA (ExpQuad / RatQuad, d <= 8, error bound satisfied),
- * 2 = direct differences, 3 = norm-identity + DMMA with symmetric halving */
+ * 2 = direct differences, 3 = norm-identity + DMMA with symmetric halving, 4 = direct differences
+ * with symmetric halving */
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path);
 PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms);
 

@@ -255,7 +255,8 @@ class Operator:
         """'undecided', 'norm-identity-dmma' or 'direct-differences' (see pncov_matmul_path)."""
         p = ctypes.c_int()
         _check(self._lib.pncov_matmul_path(self._h, ctypes.byref(p)))
-        return ("undecided", "norm-identity-dmma", "direct-differences", "norm-identity-dmma-symmetric")[p.value]
+        return ("undecided", "norm-identity-dmma", "direct-differences", "norm-identity-dmma-symmetric",
+                "direct-differences-symmetric")[p.value]
 
     def matmul_sym_part_device(self, v_ptr: int, y_ptr: int, part: int, nparts: int, stream: int = 0) -> None:
         """Contribution of row blocks ``part, part + nparts, ...`` to ``K @ v`` (full-length ``y``);

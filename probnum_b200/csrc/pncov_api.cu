@@ -668,10 +668,11 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
         // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
         const char* symenv = getenv("PNCOV_MATVEC_SYM");
-        const bool sym_ok = h->symmetric && m.use_mma == 2 && kc_max == 1 && es == 8 && R.n >= 2048 &&
+        const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 8);  // DMMA identity or direct differences
+        const bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 &&
                             !(symenv && strcmp(symenv, "off") == 0);
         if (sym_nparts > 0 && !sym_ok)
-            return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64 and the norm-identity kernel");
+            return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 8 and n >= 2048");
         m.sym = sym_ok ? 1 : 0;
         m.sym_part = sym_part;
         m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;
@@ -1089,7 +1090,7 @@ PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
 
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {
     if (!h || !path) return fail(PNCOV_EINVAL, "NULL argument");
-    *path = h->mma_state == 0 ? 0 : (h->mma_state == 1 ? (h->last_sym ? 3 : 1) : 2);
+    *path = h->mma_state == 0 ? 0 : (h->mma_state == 1 ? (h->last_sym ? 3 : 1) : (h->last_sym ? 4 : 2));
     return 0;
 }
 

@@ -526,6 +526,156 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
     }
 }
 
+// ---- symmetric variant of the direct-difference kernel (x1 is x0, one right-hand side) ----------------
+// Same halving for the kernels that cannot use the norm identity (Matern: sqrt(S) near 0; ExpQuad /
+// RatQuad on clouds that are wide in lengthscale units): the CTA of row block I (256 rows = two
+// column tiles) walks the column tiles J >= 2I, and for tiles right of its diagonal pair also
+// accumulates y_J += K_IJ^T v_I.  A thread holds K for its 2 rows x 2 columns: two DFMAs give
+// the partial column sums, one butterfly step folds the two columns onto the two half-warps and
+// four more shuffle rounds finish the warp sum (1.25 DADD per pair); warps meet in shared memory
+// and one atomic per column leaves the CTA per tile.  Matern-5/2, d = 8: 32 -> 17.75 FP64
+// instructions per ordered pair.
+constexpr int MS_ROWS = MV_THREADS * MV_R;
+static_assert(MS_ROWS == 2 * MV_TJ, "a row block must span exactly two column tiles");
+
+template <int D, bool ARD, int EPI>
+__global__ void __launch_bounds__(MV_THREADS)
+    matvec_sym_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split, int part, int nparts) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    constexpr int STAGE_DOUBLES = MV_TJ * (D + 1);
+    double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
+    double* colw = stage0 + 2 * STAGE_DOUBLES + 2;  // [2][warps][MV_TJ]; +2 keeps 16-byte alignment for odd D
+
+    const int64_t n_jt = a.n1pad / MV_TJ;
+    const int64_t bx = (int64_t)blockIdx.x * nparts + part;  // row block; its diagonal tiles are 2 bx, 2 bx + 1
+    if (2 * bx >= n_jt) return;
+    int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+    if (jt0 < 2 * bx) jt0 = 2 * bx;
+    if (jt0 >= jt1) return;
+    const double* x1g = static_cast<const double*>(a.x1_aos);
+    const double* vg = static_cast<const double*>(a.v);
+    double* yg = static_cast<double*>(a.y);
+    constexpr uint32_t X_BYTES = MV_TJ * D * 8, V_BYTES = MV_TJ * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_init(&bars[2], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], X_BYTES + V_BYTES);
+        pn_bulk_g2s(stage0, x1g + jt0 * MV_TJ * D, X_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + MV_TJ * D, vg + jt0 * MV_TJ, V_BYTES, &bars[0]);
+        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
+    }
+    const int64_t row0 = bx * MS_ROWS + tid;
+    double xr[MV_R][D], vrow[MV_R], acc[MV_R];
+    {
+        const double* x0g = static_cast<const double*>(a.x0_aos);
+#pragma unroll
+        for (int r = 0; r < MV_R; ++r) {
+            const int64_t row = row0 + (int64_t)r * MV_THREADS;  // padded to PN_PAD rows
+#pragma unroll
+            for (int m = 0; m < D; ++m) xr[r][m] = x0g[row * D + m];
+            vrow[r] = vg[row];  // zero in the padding
+            acc[r] = 0.0;
+        }
+    }
+    double sc[D];
+    if constexpr (ARD) {
+#pragma unroll
+        for (int m = 0; m < D; ++m) sc[m] = static_cast<const double*>(a.scale)[m];
+    }
+    pn_mbar_wait(&bars[2], 0);
+
+    int it = 0;
+    for (int64_t jt = jt0; jt < jt1; ++jt, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && jt + 1 < jt1) {
+            double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
+            pn_mbar_expect_tx(&bars[buf ^ 1], X_BYTES + V_BYTES);
+            pn_bulk_g2s(dst, x1g + (jt + 1) * MV_TJ * D, X_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + MV_TJ * D, vg + (jt + 1) * MV_TJ, V_BYTES, &bars[buf ^ 1]);
+        }
+        if (it > 0 && jt - 1 > 2 * bx + 1) {  // column sums of the previous tile
+            const double* cwp = colw + (buf ^ 1) * (MV_THREADS / 32) * MV_TJ;
+            double s = cwp[tid];
+#pragma unroll
+            for (int w = 1; w < MV_THREADS / 32; ++w) s += cwp[w * MV_TJ + tid];
+            const int64_t col = (jt - 1) * MV_TJ + tid;
+            if (col < a.n1) atomicAdd(yg + col, s);
+        }
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* xt = stage0 + (size_t)buf * STAGE_DOUBLES;
+        const double* vt = xt + MV_TJ * D;
+        double* cw = colw + buf * (MV_THREADS / 32) * MV_TJ + warp * MV_TJ;
+        const bool mirror = jt > 2 * bx + 1;  // uniform
+
+#pragma unroll 1
+        for (int jj = 0; jj < MV_TJ; jj += 2) {
+            double xb[2][D];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int m = 0; m < D; ++m) xb[c][m] = xt[(jj + c) * D + m];
+            double S[2 * MV_R];
+#pragma unroll
+            for (int r = 0; r < MV_R; ++r)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int m = 0; m < D; ++m) {
+                        double df = xr[r][m] - xb[c][m];
+                        if constexpr (ARD) df *= sc[m];
+                        s = pn_fma(df, df, s);
+                    }
+                    S[2 * r + c] = s;
+                }
+            mv_epi_tile<EPI, 2 * MV_R>(S, a.epi, tabE, tabL);
+            const double v0 = vt[jj], v1 = vt[jj + 1];
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < MV_R; ++r) {
+                acc[r] = pn_fma(S[2 * r], v0, acc[r]);
+                acc[r] = pn_fma(S[2 * r + 1], v1, acc[r]);
+                t0 = pn_fma(S[2 * r], vrow[r], t0);
+                t1 = pn_fma(S[2 * r + 1], vrow[r], t1);
+            }
+            if (mirror) {
+                // butterfly: the lower half-warp ends up with column jj, the upper with jj + 1
+                const bool upper = (lane & 16) != 0;
+                const double send = upper ? t0 : t1;
+                double t = (upper ? t1 : t0) + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+                for (int m = 8; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+                if ((lane & 15) == 0) cw[jj + (lane >> 4)] = t;
+            }
+        }
+        __syncthreads();
+    }
+    if (jt1 - 1 > 2 * bx + 1) {  // column sums of the last tile
+        const double* cwp = colw + ((it - 1) & 1) * (MV_THREADS / 32) * MV_TJ;
+        double s = cwp[tid];
+#pragma unroll
+        for (int w = 1; w < MV_THREADS / 32; ++w) s += cwp[w * MV_TJ + tid];
+        const int64_t col = (jt1 - 1) * MV_TJ + tid;
+        if (col < a.n1) atomicAdd(yg + col, s);
+    }
+#pragma unroll
+    for (int r = 0; r < MV_R; ++r) {
+        const int64_t row = row0 + (int64_t)r * MV_THREADS;
+        if (row < a.n0) atomicAdd(yg + row, acc[r]);
+    }
+}
+
 // ---- generic kernel: any d <= 1024, float64 or float32 points ---------------------------------
 // One row per thread, its point read through L1 each time; column points in coordinate-major
 // shared-memory tiles, four columns per register tile.  Slower than the main kernel (extra
@@ -789,6 +939,57 @@ cudaError_t launch_mma_epi(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t st
     }
 }
 
+template <int D, bool ARD, int EPI>
+cudaError_t launch_direct_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
+    auto kern = matvec_sym_kernel<D, ARD, EPI>;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MV_TJ * (D + 1) + 16 +
+                        2 * sizeof(double) * (MV_THREADS / 32) * MV_TJ;
+    const int64_t n_jt = a.n1pad / MV_TJ;
+    const int64_t n_blocks = (n_jt + 1) / 2;
+    const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
+    const int64_t row_ctas = (n_blocks + nparts - 1) / nparts;
+    int64_t tps = 256;
+    while (tps > 8 && row_ctas * ((n_jt + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    const int64_t chunks = (n_jt + tps - 1) / tps;
+    if (chunks > 65535) return cudaErrorInvalidConfiguration;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(a.y, 0, (size_t)a.n0 * sizeof(double), stream)) != cudaSuccess) return err;
+    dim3 grid((unsigned)row_ctas, (unsigned)chunks);
+    kern<<<grid, MV_THREADS, smem, stream>>>(a, (int)tps, a.sym_part, nparts);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int D, bool ARD>
+cudaError_t launch_direct_sym_epi(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_direct_sym<D, ARD, PN_EPI_EXPQUAD>(a, stream);
+        case PN_EPI_MATERN0: return launch_direct_sym<D, ARD, PN_EPI_MATERN0>(a, stream);
+        case PN_EPI_MATERN1: return launch_direct_sym<D, ARD, PN_EPI_MATERN1>(a, stream);
+        case PN_EPI_MATERN2: return launch_direct_sym<D, ARD, PN_EPI_MATERN2>(a, stream);
+        case PN_EPI_MATERNP: return launch_direct_sym<D, ARD, PN_EPI_MATERNP>(a, stream);
+        case PN_EPI_RATQUAD1: return launch_direct_sym<D, false, PN_EPI_RATQUAD1>(a, stream);
+        case PN_EPI_RATQUAD2: return launch_direct_sym<D, false, PN_EPI_RATQUAD2>(a, stream);
+        default: return launch_direct_sym<D, false, PN_EPI_RATQUADG>(a, stream);
+    }
+}
+
+template <bool ARD>
+cudaError_t launch_direct_sym_d(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.d) {
+        case 1: return launch_direct_sym_epi<1, ARD>(a, stream);
+        case 2: return launch_direct_sym_epi<2, ARD>(a, stream);
+        case 3: return launch_direct_sym_epi<3, ARD>(a, stream);
+        case 4: return launch_direct_sym_epi<4, ARD>(a, stream);
+        case 5: return launch_direct_sym_epi<5, ARD>(a, stream);
+        case 6: return launch_direct_sym_epi<6, ARD>(a, stream);
+        case 7: return launch_direct_sym_epi<7, ARD>(a, stream);
+        case 8: return launch_direct_sym_epi<8, ARD>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 template <int KSTEPS, int EPI>
 cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     auto kern = matvec_mma_sym_kernel<KSTEPS, EPI>;
@@ -863,8 +1064,8 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
         a.jsplit = 1;
         return cudaSuccess;
     }
-    if (a.use_mma == 2 && a.sym) {
-        a.jsplit = 1;  // no partial buffers: the symmetric kernel accumulates with atomics
+    if (a.sym && (a.use_mma == 2 || (a.use_mma == 0 && !a.in_f32 && a.d <= 8))) {
+        a.jsplit = 1;  // no partial buffers: the symmetric kernels accumulate with atomics
         return cudaSuccess;
     }
     if (a.use_mma == 2) return launch_mma_any(a, sm_count, true, nullptr);
@@ -889,6 +1090,8 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     cudaError_t err;
     if (a.use_mma == 2 && a.sym) {
         return a.d > 4 ? launch_mma_sym_epi<2>(a, stream) : launch_mma_sym_epi<1>(a, stream);
+    } else if (a.sym && a.use_mma == 0 && uses_main_kernel(a)) {
+        return ard ? launch_direct_sym_d<true>(a, stream) : launch_direct_sym_d<false>(a, stream);
     } else if (a.use_mma == 2) {
         err = launch_mma_any(a, sm_count, false, stream);
     } else if (a.use_mma == 1) {

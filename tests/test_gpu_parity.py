@@ -455,22 +455,28 @@ def test_wide_right_hand_sides(k_cols):
 # ---------------------------------------------------------------------------------------------
 # symmetric halving of the matrix-free product (x1 is x0, one right-hand side)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind,d,n", [("expquad", 8, 5000), ("expquad", 3, 2177), ("ratquad", 4, 4096),
-                                      ("ratquad", 8, 6001)])
-def test_symmetric_matvec_matches_oracle(kind, d, n):
+@pytest.mark.parametrize("kind,d,n,nu,ls", [
+    ("expquad", 8, 5000, 0, 0.9), ("expquad", 3, 2177, 0, 0.9), ("ratquad", 4, 4096, 0, 0.9), ("ratquad", 8, 6001, 0, 0.9),
+    ("matern", 8, 5000, 2.5, 0.9), ("matern", 3, 2305, 0.5, 0.9), ("matern", 5, 4096, 3.5, [0.5, 0.7, 0.9, 1.1, 1.3]),
+    ("expquad", 6, 3000, 0, 0.01),  # wide cloud in lengthscale units: identity inadmissible -> direct differences
+])
+def test_symmetric_matvec_matches_oracle(kind, d, n, nu, ls):
     rng = np.random.default_rng(n)
-    spec = orc.KernelSpec(kind, (d,), 0.9, alpha=1.5)
+    spec = orc.KernelSpec(kind, (d,), np.asarray(ls) if np.ndim(ls) else ls, nu=nu or 1.5, alpha=1.5)
     k = make_kernel(spec)
     x = rng.normal(size=(n, d))
+    x[17] = x[n - 5]  # a duplicated point far off the diagonal: sqrt(0) inside a mirrored tile
     L = k.linop(x)
+    direct = kind == "matern" or np.ndim(ls) == 0 and ls < 0.1
+    family = "direct-differences" if direct else "norm-identity-dmma"
     for v in (rng.normal(size=(n, 1)), rng.uniform(size=(n, 1))):
         y = L._matmul_device(v)
-        assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
+        assert L._device_op().matmul_path() == family + "-symmetric"
         assert_matvec_close(y, orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
     # several columns take the ordered kernel and must agree with the one-column results
     V = rng.normal(size=(n, 3))
     Y = L._matmul_device(V)
-    assert L._device_op().matmul_path() == "norm-identity-dmma"
+    assert L._device_op().matmul_path() == family
     y0 = L._matmul_device(V[:, :1])
     bound = orc.abs_matvec(spec, x, None, V[:, :1])
     assert np.all(np.abs(Y[:, :1] - y0) <= 1e-13 * bound)
@@ -498,11 +504,22 @@ def test_symmetric_matvec_parts_sum_to_the_product():
         total += part
     assert_matvec_close(total.cpu().numpy(), orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
     op.close()
-    # a kernel without the identity path (Matern) reports that the decomposition does not apply
-    opm = _lib.Operator(pb.Matern((d,), nu=1.5)._kernel_params(), x)
-    with pytest.raises(NotImplementedError):
-        opm.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
+    # Matern takes the direct-difference form of the same decomposition
+    specm = orc.KernelSpec("matern", (d,), 1.0, nu=1.5)
+    opm = _lib.Operator(make_kernel(specm)._kernel_params(), x)
+    total.zero_()
+    for p in range(2):
+        opm.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), p, 2)
+        torch.cuda.synchronize()
+        total += part
+    assert_matvec_close(total.cpu().numpy(), orc.matvec(specm, x, None, v), orc.abs_matvec(specm, x, None, v), 1e-12)
     opm.close()
+    # d > 8 has no symmetric kernel: the library says so and the caller shards rows instead
+    x9 = rng.normal(size=(n, 9))
+    op9 = _lib.Operator(pb.ExpQuad((9,))._kernel_params(), x9)
+    with pytest.raises(NotImplementedError):
+        op9.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
+    op9.close()
 
 
 def test_symmetric_matvec_can_be_switched_off(monkeypatch):
