@@ -237,6 +237,26 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------
+def _bind_to_gpu_numa_node(index: int) -> None:
+    """One process per GPU: run on the CPUs NVML names as local to this GPU, so that the pinned
+    result buffers of the end-to-end leg are allocated on the GPU's own NUMA node and its D2H
+    traffic does not cross the socket interconnect.  Best effort; silent if NVML is unavailable."""
+    try:
+        import pynvml  # noqa: PLC0415
+
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            print(f"[bench] rank on GPU {index}: bound to {len(cpus)} CPUs local to the GPU", file=sys.stderr)
+    except Exception as exc:  # noqa: BLE001
+        print(f"[bench] no NUMA binding for GPU {index}: {exc}", file=sys.stderr)
+
+
 def run_ours(args):
     import torch  # noqa: PLC0415
     import torch.distributed as dist  # noqa: PLC0415
@@ -253,6 +273,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        _bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
