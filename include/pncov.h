@@ -176,6 +176,30 @@ PNCOV_API int pncov_copy_to_host(int device, void* dst_host, const void* src_dev
 PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64_t n, int op, double alpha,
                                    double beta, void* stream);
 
+/* Cholesky factor and solves on the device ------------------------------
+ * replaces BQBeliefUpdate.compute_gram_cho_factor / gram_cho_solve
+ * (quad/solvers/belief_updates/_belief_update.py:61-103), i.e. scipy.linalg.cho_factor of
+ * `gram + jitter * I` and scipy.linalg.cho_solve with that factor.  float64, hand-written blocked
+ * right-looking factorisation with the trailing updates on FP64 DMMA (csrc/pncov_chol.cu).
+ *   pncov_chol_create       handle for matrices of order n on `device` (owns the n x n device copy)
+ *   pncov_chol_factor       a: (n, n) row-major symmetric matrix, leading dimension ld, host memory
+ *                           (a_on_device = 0) or device memory on the handle's device (the call waits
+ *                           for all work already queued on that device first); only the lower
+ *                           triangle is read.  *info = 0 on success, else the 1-based index of the
+ *                           first non-positive pivot (scipy raises LinAlgError there); blocking.
+ *   pncov_chol_solve        x = (L L^T)^-1 b for b, x: (n, nrhs) row-major HOST arrays
+ *   pncov_chol_get_factor   lower-triangular factor to a host array (the strict upper triangle of
+ *                           the output is unspecified, as with scipy.linalg.cho_factor)
+ *   pncov_chol_last_factor_ms   device time of the last factorisation (CUDA events)
+ */
+typedef struct pncov_chol pncov_chol;
+PNCOV_API int pncov_chol_create(pncov_chol** out, int device, int64_t n);
+PNCOV_API int pncov_chol_destroy(pncov_chol* c);
+PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, double jitter, int a_on_device, int* info);
+PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx);
+PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld);
+PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms);
+
 /* diagnostics ------------------------------------------------------------------------
  * number of kernel launches issued by this library in the calling process, and the
  * device time in ms of the last pncov_gram / pncov_matmul call of this handle (CUDA

@@ -58,6 +58,12 @@ SIGNATURES = {
     "pncov_copy_to_host": (ctypes.c_int, [ctypes.c_int, _c_vp, _c_vp, _c_i64, _c_vp]),
     "pncov_combine_device": (
         ctypes.c_int, [ctypes.c_int, _c_vp, _c_vp, _c_i64, ctypes.c_int, ctypes.c_double, ctypes.c_double, _c_vp]),
+    "pncov_chol_create": (ctypes.c_int, [ctypes.POINTER(_c_vp), ctypes.c_int, _c_i64]),
+    "pncov_chol_destroy": (ctypes.c_int, [_c_vp]),
+    "pncov_chol_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "pncov_chol_solve": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
+    "pncov_chol_get_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
+    "pncov_chol_last_factor_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
     "pncov_launch_count": (_c_i64, []),
     "pncov_matmul_path": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_int)]),
     "pncov_last_kernel_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -328,3 +334,70 @@ def combine(dst: DeviceBuffer, src: Optional[DeviceBuffer], n: int, op: int, alp
     ``n`` float64 elements on the device."""
     _check(load().pncov_combine_device(dst.device, _c_vp(dst.ptr), None if src is None else _c_vp(src.ptr),
                                        int(n), int(op), float(alpha), float(beta), _c_vp(stream)))
+
+
+# -- Cholesky (include/pncov.h, "Cholesky factor and solves on the device") ---------------------------
+class Cholesky:
+    """Device-resident Cholesky factor of ``a + jitter * I`` (float64, lower triangle of ``a`` read).
+
+    ``a`` is a host array or, with ``on_device``, an integer device address of an (n, n) row-major
+    matrix.  Raises ``numpy.linalg.LinAlgError`` like ``scipy.linalg.cho_factor`` if the matrix is
+    not positive definite."""
+
+    def __init__(self, a, jitter: float = 0.0, *, device: Optional[int] = None, on_device: bool = False,
+                 n: Optional[int] = None, ld: Optional[int] = None):
+        lib = load()
+        self._lib = lib
+        self._h = _c_vp()
+        self.device = default_device() if device is None else int(device)
+        if on_device:
+            self.n = int(n)
+            ptr, lda = _c_vp(int(a)), int(ld if ld is not None else n)
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            if a.ndim != 2 or a.shape[0] != a.shape[1]:
+                raise ValueError("expected a square matrix")
+            self.n = a.shape[0]
+            ptr, lda = _ptr(a), a.shape[1]
+        _check(lib.pncov_chol_create(ctypes.byref(self._h), self.device, self.n))
+        info = ctypes.c_int(0)
+        try:
+            _check(lib.pncov_chol_factor(self._h, ptr, lda, float(jitter), 1 if on_device else 0, ctypes.byref(info)))
+        except Exception:
+            self.close()
+            raise
+        if info.value != 0:
+            self.close()
+            raise np.linalg.LinAlgError(f"{info.value}-th leading minor of the array is not positive definite")
+
+    def solve(self, b: np.ndarray) -> np.ndarray:
+        """``(L L^T)^-1 b`` for a host array of shape (n,) or (n, k)."""
+        b = np.asarray(b, dtype=np.float64)
+        b2 = np.ascontiguousarray(b.reshape(self.n, -1))
+        x = np.empty_like(b2)
+        k = b2.shape[1]
+        if k:
+            _check(self._lib.pncov_chol_solve(self._h, _ptr(b2), k, k, _ptr(x), k))
+        return x.reshape(b.shape)
+
+    def factor(self) -> np.ndarray:
+        """Lower-triangular factor as a host array (upper triangle zeroed)."""
+        L = np.empty((self.n, self.n), dtype=np.float64)
+        _check(self._lib.pncov_chol_get_factor(self._h, _ptr(L), self.n))
+        return np.tril(L)
+
+    def last_factor_ms(self) -> float:
+        ms = ctypes.c_float()
+        _check(self._lib.pncov_chol_last_factor_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pncov_chol_destroy(self._h)
+            self._h = _c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass

@@ -1086,6 +1086,135 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
     return 0;
 }
 
+// ---- Cholesky factor of a Gram matrix + jitter I, resident on the device ---------------------------
+struct pncov_chol {
+    int device = 0;
+    int64_t n = 0, npad = 0;
+    double* M = nullptr;      // (npad, npad) row-major; lower triangle = L after pncov_chol_factor
+    double* panel = nullptr;  // (npad, 128) contiguous block column
+    double* invd = nullptr;   // (npad / 128) inverse diagonal blocks, 128 x 128 each
+    double* rhs = nullptr;    // (npad, 8)
+    int* info = nullptr;
+    cudaStream_t stream = nullptr, side = nullptr;  // side: look-ahead factorisation of the next diagonal block
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_panel = nullptr, ev_diag = nullptr;
+    bool factored = false;
+};
+
+PNCOV_API int pncov_chol_create(pncov_chol** out, int device, int64_t n) {
+    if (!out) return fail(PNCOV_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n < 1) return fail(PNCOV_EINVAL, "matrix order must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PNCOV_ENODEVICE, "no CUDA device available (libpncov has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(PNCOV_EINVAL, "device index out of range");
+    pncov_chol* c = new (std::nothrow) pncov_chol();
+    if (!c) return fail(PNCOV_ENOMEM, "out of host memory");
+    c->device = device;
+    c->n = n;
+    c->npad = ((n + 127) / 128) * 128;
+    DeviceGuard guard(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_diag, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->M), (size_t)c->npad * c->npad * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->panel), (size_t)c->npad * 128 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->invd), (size_t)c->npad * 128 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->rhs), (size_t)c->npad * 8 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->info), sizeof(int));
+    if (e != cudaSuccess) {
+        const bool oom = e == cudaErrorMemoryAllocation;
+        int rc = oom ? fail(PNCOV_ENOMEM, "out of device memory") : fail_cuda(e, "pncov_chol_create");
+        cudaGetLastError();
+        pncov_chol_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+PNCOV_API int pncov_chol_destroy(pncov_chol* c) {
+    if (!c) return 0;
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
+    cudaFree(c->M);
+    cudaFree(c->panel);
+    cudaFree(c->invd);
+    cudaFree(c->rhs);
+    cudaFree(c->info);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_panel) cudaEventDestroy(c->ev_panel);
+    if (c->ev_diag) cudaEventDestroy(c->ev_diag);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, double jitter, int a_on_device, int* info) {
+    if (!c || !a || !info) return fail(PNCOV_EINVAL, "NULL argument");
+    if (ld < c->n) return fail(PNCOV_EINVAL, "leading dimension smaller than the matrix order");
+    DeviceGuard guard(c->device);
+    c->factored = false;
+    // a device-resident input may still be in flight on the caller's stream: the handle works on
+    // its own stream, so wait for the device once (microseconds next to the factorisation)
+    if (a_on_device) PN_CUDA(cudaDeviceSynchronize());
+    if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->M, 0, (size_t)c->npad * c->npad * 8, c->stream));
+    PN_CUDA(cudaMemcpy2DAsync(c->M, (size_t)c->npad * 8, a, (size_t)ld * 8, (size_t)c->n * 8, (size_t)c->n,
+                              a_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    PN_CUDA(cudaEventRecord(c->ev0, c->stream));
+    PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->stream, c->side, c->ev_panel, c->ev_diag));
+    PN_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PN_CUDA(cudaMemcpyAsync(info, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    c->factored = *info == 0;
+    return 0;
+}
+
+PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx) {
+    if (!c || !b || !x) return fail(PNCOV_EINVAL, "NULL argument");
+    if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");
+    if (nrhs < 0 || ldb < nrhs || ldx < nrhs) return fail(PNCOV_EINVAL, "bad right-hand-side shape");
+    DeviceGuard guard(c->device);
+    for (int64_t c0 = 0; c0 < nrhs; c0 += 8) {
+        const int k = (int)std::min<int64_t>(8, nrhs - c0);
+        if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->rhs, 0, (size_t)c->npad * k * 8, c->stream));
+        PN_CUDA(cudaMemcpy2DAsync(c->rhs, (size_t)k * 8, b + c0, (size_t)ldb * 8, (size_t)k * 8, (size_t)c->n,
+                                  cudaMemcpyHostToDevice, c->stream));
+        PN_CUDA(pn_chol_solve(c->M, c->npad, c->invd, c->rhs, k, c->stream));
+        PN_CUDA(cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, c->rhs, (size_t)k * 8, (size_t)k * 8, (size_t)c->n,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    }
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld) {
+    if (!c || !l) return fail(PNCOV_EINVAL, "NULL argument");
+    if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");
+    if (ld < c->n) return fail(PNCOV_EINVAL, "leading dimension smaller than the matrix order");
+    DeviceGuard guard(c->device);
+    PN_CUDA(cudaMemcpy2DAsync(l, (size_t)ld * 8, c->M, (size_t)c->npad * 8, (size_t)c->n * 8, (size_t)c->n,
+                              cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms) {
+    if (!c || !ms) return fail(PNCOV_EINVAL, "NULL argument");
+    DeviceGuard guard(c->device);
+    PN_CUDA(cudaEventSynchronize(c->ev1));
+    PN_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
 PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
 
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {

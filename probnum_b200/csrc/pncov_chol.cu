@@ -1,0 +1,423 @@
+// FP64 Cholesky factorisation and solves on the device.
+//
+// Replaces scipy.linalg.cho_factor / cho_solve in the Bayesian-quadrature belief update
+// (/root/reference/src/probnum/quad/solvers/belief_updates/_belief_update.py:61-103:
+// compute_gram_cho_factor adds `jitter` to the diagonal and factors, gram_cho_solve solves with
+// the factor).  At 16384 nodes the host dpotrf (1.47 TFLOP) takes ~15 s and dominates
+// bayesquad_from_data once the Gram matrix itself is built on the GPU.
+//
+// Right-looking blocked algorithm on a row-major n x n matrix (lower triangle), block size 128:
+//   for every block column k
+//     chol_diag_kernel   one CTA: unblocked Cholesky of the 128 x 128 diagonal block in shared
+//                        memory (one barrier per column) and the explicit inverse of its factor
+//     chol_gemm_kernel   mode 0 ("TRSM as GEMM"): L[i,k] = A[i,k] inv(L_kk)^T for all i > k,
+//                        also copied into a contiguous panel
+//                        mode 1: A[i,j] -= L[i,k] L[j,k]^T for all i >= j > k  (n^3/3 of the flops)
+// Both GEMM modes are C = A B^T with K-contiguous operands, i.e. exactly the "row.col" form of
+// mma.sync.m8n8k4.f64 (DMMA, the only FP64 tensor path of sm_100a): a CTA of 8 warps owns a
+// 128 x 128 tile, a warp 32 x 64 of it (64 accumulators per lane), operands stream through a
+// two-stage cp.async pipeline in K-chunks of 32 with a row stride of 36 doubles, which makes the
+// fragment loads bank-conflict free.
+// Solves use the stored inverse diagonal blocks: every substitution step is a 128 x 128 product
+// plus one pass over a block row / block column of L.
+#include "pncov_internal.h"
+
+namespace {
+
+constexpr int CB = 128;          // block size
+constexpr int CK = 32;           // K chunk of the GEMM pipeline
+constexpr int CLD = CK + 4;      // shared-memory row stride in doubles (= 4 mod 16: conflict-free)
+constexpr int CG_THREADS = 256;
+constexpr int CD_LD = CB + 1;    // diagonal kernel: padded row stride
+
+__device__ __forceinline__ void ch_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void ch_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pn_smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void ch_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ch_cp_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+struct ChGemm {
+    const double* A;  // mode 0: first row block of the panel inside the matrix; mode 1: contiguous panel
+    int64_t lda;
+    const double* B;  // mode 0: inverse of the diagonal factor (128 x 128); mode 1: contiguous panel
+    int64_t ldb;
+    double* C;        // mode 0: = A (in place); mode 1: first trailing tile
+    int64_t ldc;
+    double* panel;    // mode 0: contiguous copy of the new block column (ld = 128)
+    int mode;
+    int tile0;        // mode 1: index of the first tile of this launch (tile 0 = the next diagonal block)
+};
+
+__global__ void __launch_bounds__(CG_THREADS, 1) chol_gemm_kernel(const __grid_constant__ ChGemm p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* As = reinterpret_cast<double*>(smem);  // [2][CB * CLD]
+    double* Bs = As + 2 * CB * CLD;                // [2][CB * CLD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps: 32 rows x 64 columns each
+
+    int64_t bi, bj;
+    if (p.mode == 0) {
+        bi = blockIdx.x;
+        bj = 0;
+    } else {  // linear index over the lower triangle (bj <= bi)
+        const int64_t t = (int64_t)blockIdx.x + p.tile0;
+        bi = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        bj = t - bi * (bi + 1) / 2;
+    }
+    const double* At = p.A + bi * CB * p.lda;
+    const double* Bt = p.mode == 0 ? p.B : p.B + bj * CB * p.ldb;
+    double* Ct = p.C + bi * CB * p.ldc + (p.mode == 0 ? 0 : bj * CB);
+
+    auto load_chunk = [&](int kc, int buf) {
+        double* as = As + buf * CB * CLD;
+        double* bs = Bs + buf * CB * CLD;
+        constexpr int PIECES = CK / 2;  // 16-byte pieces per row
+#pragma unroll
+        for (int i = 0; i < CB * PIECES / CG_THREADS; ++i) {
+            const int idx = tid + i * CG_THREADS;
+            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
+            ch_cp_async16(as + row * CLD + c2, At + (int64_t)row * p.lda + kc * CK + c2);
+            ch_cp_async16(bs + row * CLD + c2, Bt + (int64_t)row * p.ldb + kc * CK + c2);
+        }
+        ch_cp_commit();
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    load_chunk(0, 0);
+    constexpr int NCHUNK = CB / CK;
+    for (int kc = 0; kc < NCHUNK; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < NCHUNK) {
+            load_chunk(kc + 1, buf ^ 1);
+            ch_cp_wait<1>();
+        } else {
+            ch_cp_wait<0>();
+        }
+        __syncthreads();
+        const double* as = As + buf * CB * CLD + (wm * 32 + g) * CLD + q;
+        const double* bs = Bs + buf * CB * CLD + (wn * 64 + g) * CLD + q;
+#pragma unroll
+        for (int k4 = 0; k4 < CK / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = as[r * 8 * CLD + k4 * 4];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) b[c] = bs[c * 8 * CLD + k4 * 4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ch_dmma(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+        }
+        __syncthreads();  // everyone is done with `buf` before chunk kc + 2 lands in it
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = wm * 32 + r * 8 + g;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int col = wn * 64 + c * 8 + 2 * q;
+            double2* dst = reinterpret_cast<double2*>(Ct + (int64_t)row * p.ldc + col);
+            if (p.mode == 0) {
+                const double2 v = make_double2(acc[r][c][0], acc[r][c][1]);
+                *dst = v;
+                *reinterpret_cast<double2*>(p.panel + (bi * CB + row) * CB + col) = v;
+            } else {
+                double2 v = *dst;
+                v.x -= acc[r][c][0];
+                v.y -= acc[r][c][1];
+                *dst = v;
+            }
+        }
+    }
+}
+
+// 16 elimination steps j = 16 JJ .. 16 JJ + 15 of the in-register Cholesky of chol_diag_kernel.
+// Thread (ty, tx) owns a[ty + 16 ii][tx + 16 cc] in r[ii][cc]; column block JJ is a compile-time
+// constant, so every register index is static and finished column blocks cost nothing.
+template <int JJ>
+__device__ __forceinline__ void chol_diag_steps(double (&r)[8][8], double* colbuf, int ty, int tx, int tid, int* info,
+                                                int pivot_base) {
+#pragma unroll 1
+    for (int jt = 0; jt < 16; ++jt) {
+        const int j = 16 * JJ + jt;
+        double* cb = colbuf + (j & 1) * CB;  // double-buffered: one barrier per step
+        if (tx == jt) {                       // the owners of column j publish it (unscaled)
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) cb[ty + 16 * ii] = r[ii][JJ];
+        }
+        __syncthreads();
+        double ajj = cb[j];
+        if (!(ajj > 0.0)) {  // not positive definite (or NaN): record the first offender, keep going
+            if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
+            ajj = 1.0;
+        }
+        const double dj = rsqrt(ajj);
+        double li[8], lc[8 - JJ];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) li[ii] = cb[ty + 16 * ii] * dj;  // L[i][j] for my rows (i >= j)
+#pragma unroll
+        for (int cc = JJ; cc < 8; ++cc) lc[cc - JJ] = cb[tx + 16 * cc] * dj;  // L[c][j] for my columns
+        // a[i][c] -= L[i][j] L[c][j] for the columns right of j; rows above the diagonal hold dead
+        // values that never feed a live one, so they need no predicate
+#pragma unroll
+        for (int cc = JJ; cc < 8; ++cc) {
+            const bool upd = (cc > JJ) || (tx > jt);
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii)
+                if (upd) r[ii][cc] = pn_fma(-li[ii], lc[cc - JJ], r[ii][cc]);
+        }
+        if (tx == jt) {  // column j is final: L[j][j] = a_jj / sqrt(a_jj), L[i][j] = a_ij / sqrt(a_jj)
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) r[ii][JJ] = li[ii];
+        }
+    }
+}
+
+// One CTA: Cholesky of the 128 x 128 diagonal block (lower triangle of A, row-major) and the
+// inverse of its factor.  The block lives in registers (8 x 8 per thread, cyclic 16 x 16
+// distribution); per elimination step the owners publish one column through shared memory, one
+// barrier, and everybody updates its registers.  info receives the 1-based index of the first
+// non-positive pivot.
+__global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ invL,
+                                                         int* __restrict__ info, int pivot_base) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* a = reinterpret_cast<double*>(smem);  // [CB][CD_LD]: upper triangle L^T, lower triangle inv(L)
+    double* dg = a + CB * CD_LD;                  // [CB] diagonal of L
+    double* colbuf = dg + CB;                     // [2][CB]
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    double r[8][8];
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int i = ty + 16 * ii, c = tx + 16 * cc;
+            r[ii][cc] = (c <= i) ? A[(int64_t)i * lda + c] : 0.0;
+        }
+    chol_diag_steps<0>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<1>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<2>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<3>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<4>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<5>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<6>(r, colbuf, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<7>(r, colbuf, ty, tx, tid, info, pivot_base);
+    // L to global memory (lower triangle) and, transposed, to shared memory for the inverse
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            const int i = ty + 16 * ii, c = tx + 16 * cc;
+            if (c <= i) A[(int64_t)i * lda + c] = r[ii][cc];
+            if (c < i) a[c * CD_LD + i] = r[ii][cc];
+            else if (c == i) dg[i] = r[ii][cc];
+        }
+    __syncthreads();
+    // inverse of L by forward substitution, one column per thread.  The lower triangle of `a` is
+    // free now and receives X = inv(L) (X[l][c] at a[l][c], c <= l); L[i][l] sits at a[l][i].  Loop
+    // bounds are uniform per warp (reads of L broadcast), entries above the diagonal are masked.
+    if (tid < CB) {
+        const int c = tid;
+        const int l0 = (tid >> 5) << 5;
+        for (int i = l0; i < CB; ++i) {
+            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int l = l0;
+            for (; l + 3 < i; l += 4) {
+                s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
+                s1 = pn_fma(-a[(l + 1) * CD_LD + i], (l + 1 >= c) ? a[(l + 1) * CD_LD + c] : 0.0, s1);
+                s2 = pn_fma(-a[(l + 2) * CD_LD + i], (l + 2 >= c) ? a[(l + 2) * CD_LD + c] : 0.0, s2);
+                s3 = pn_fma(-a[(l + 3) * CD_LD + i], (l + 3 >= c) ? a[(l + 3) * CD_LD + c] : 0.0, s3);
+            }
+            for (; l < i; ++l) s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
+            const double xi = (i < c) ? 0.0 : ((s0 + s1) + (s2 + s3)) / dg[i];
+            if (i >= c) a[i * CD_LD + c] = xi;  // own column only: no other thread reads it
+            invL[i * CB + c] = xi;
+        }
+        for (int i = 0; i < l0; ++i) invL[i * CB + c] = 0.0;
+    }
+}
+
+// M[i][i] += jitter for i < n; padded diagonal (i >= n) = 1
+__global__ void chol_prepare_diag_kernel(double* M, int64_t ld, int64_t n, int64_t npad, double jitter) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) M[i * ld + i] += jitter;
+    else if (i < npad) M[i * ld + i] = 1.0;
+}
+
+// y = op(invL_k) b_k for one diagonal block (trans = 0: invL b, 1: invL^T b); nrhs columns, ld = nrhs
+__global__ void __launch_bounds__(CB) chol_diag_apply_kernel(const double* __restrict__ invL, double* __restrict__ b,
+                                                              int nrhs, int trans) {
+    __shared__ double bs[CB];
+    const int t = threadIdx.x;
+    for (int r = 0; r < nrhs; ++r) {
+        __syncthreads();
+        bs[t] = b[(int64_t)t * nrhs + r];
+        __syncthreads();
+        double s = 0.0;
+        if (!trans) {
+            for (int l = 0; l <= t; ++l) s = pn_fma(invL[t * CB + l], bs[l], s);  // lower triangular
+        } else {
+            for (int l = t; l < CB; ++l) s = pn_fma(invL[l * CB + t], bs[l], s);
+        }
+        __syncthreads();
+        b[(int64_t)t * nrhs + r] = s;
+    }
+}
+
+// forward: b_i -= L[i, k] y_k for the row blocks i > k.  One CTA per 32 rows, a warp per row.
+__global__ void __launch_bounds__(128) chol_fwd_update_kernel(const double* __restrict__ L, int64_t ld,
+                                                               const double* __restrict__ yk, double* __restrict__ b,
+                                                               int64_t rows, int nrhs) {
+    __shared__ double ys[CB * 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < CB * nrhs; idx += 128) ys[idx] = yk[idx];
+    __syncthreads();
+    for (int rr = 0; rr < 8; ++rr) {
+        const int64_t row = (int64_t)blockIdx.x * 32 + warp * 8 + rr;
+        if (row >= rows) break;
+        const double* lr = L + row * ld;
+        const double4 lv = *reinterpret_cast<const double4*>(lr + 4 * lane);
+        for (int r = 0; r < nrhs; ++r) {
+            double s = lv.x * ys[(4 * lane) * nrhs + r];
+            s = pn_fma(lv.y, ys[(4 * lane + 1) * nrhs + r], s);
+            s = pn_fma(lv.z, ys[(4 * lane + 2) * nrhs + r], s);
+            s = pn_fma(lv.w, ys[(4 * lane + 3) * nrhs + r], s);
+#pragma unroll
+            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+            if (lane == 0) b[row * nrhs + r] -= s;
+        }
+    }
+}
+
+// backward: y_k -= L[i, k]^T x_i for all column blocks k < i.  One CTA per column block, a thread
+// per column, coalesced reads of the 128 rows of block row i.
+__global__ void __launch_bounds__(CB) chol_bwd_update_kernel(const double* __restrict__ Li, int64_t ld,
+                                                              const double* __restrict__ xi, double* __restrict__ y,
+                                                              int nrhs) {
+    __shared__ double xs[CB * 8];
+    const int t = threadIdx.x;
+    for (int idx = t; idx < CB * nrhs; idx += CB) xs[idx] = xi[idx];
+    __syncthreads();
+    const int64_t col = (int64_t)blockIdx.x * CB + t;
+    double s[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[r] = 0.0;
+    for (int l = 0; l < CB; ++l) {
+        const double v = Li[(int64_t)l * ld + col];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < nrhs) s[r] = pn_fma(v, xs[l * nrhs + r], s[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+        if (r < nrhs) y[col * nrhs + r] -= s[r];
+}
+
+}  // namespace
+
+// M: (npad, npad) row-major with ld = npad (a multiple of 128); the Gram matrix occupies the leading
+// n x n block (lower triangle is read).  On return the lower triangle holds L, invd the inverses
+// of the diagonal blocks of L; *info_dev the 1-based index of the first bad pivot (0: success).
+cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, double* panel, double* invd,
+                           int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
+                           cudaEvent_t ev_diag) {
+    cudaError_t err;
+    if ((err = cudaMemsetAsync(info_dev, 0, sizeof(int), stream)) != cudaSuccess) return err;
+    chol_prepare_diag_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(M, npad, n, npad, jitter);
+    ++g_pn_launches;
+    const size_t smem_diag = sizeof(double) * (CB * CD_LD + 3 * CB);
+    const size_t smem_gemm = sizeof(double) * 4 * CB * CLD;
+    if ((err = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(chol_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
+    const int64_t T = npad / CB;
+    // Look-ahead: the factorisation of diagonal block k + 1 (one CTA, latency-bound) runs on `side`
+    // as soon as ITS tile of the trailing update is done, under the rest of the update of step k.
+    chol_diag_kernel<<<1, 256, smem_diag, stream>>>(M, npad, invd, info_dev, 0);
+    ++g_pn_launches;
+    for (int64_t k = 0; k < T; ++k) {
+        double* diag = M + k * CB * (npad + 1);
+        const int64_t nb = T - k - 1;
+        if (nb == 0) break;
+        ChGemm p{};
+        p.A = diag + CB * npad;  // block (k + 1, k)
+        p.lda = npad;
+        p.B = invd + k * CB * CB;
+        p.ldb = CB;
+        p.C = const_cast<double*>(p.A);
+        p.ldc = npad;
+        p.panel = panel;
+        p.mode = 0;
+        chol_gemm_kernel<<<(unsigned)nb, CG_THREADS, smem_gemm, stream>>>(p);
+        ++g_pn_launches;
+        if ((err = cudaEventRecord(ev_panel, stream)) != cudaSuccess) return err;
+        ChGemm u{};
+        u.A = panel;
+        u.lda = CB;
+        u.B = panel;
+        u.ldb = CB;
+        u.C = diag + CB * (npad + 1);  // block (k + 1, k + 1)
+        u.ldc = npad;
+        u.panel = nullptr;
+        u.mode = 1;
+        // side stream: tile (k + 1, k + 1) of the update, then the next diagonal factorisation
+        if ((err = cudaStreamWaitEvent(side, ev_panel, 0)) != cudaSuccess) return err;
+        u.tile0 = 0;
+        chol_gemm_kernel<<<1, CG_THREADS, smem_gemm, side>>>(u);
+        ++g_pn_launches;
+        chol_diag_kernel<<<1, 256, smem_diag, side>>>(u.C, npad, invd + (k + 1) * CB * CB, info_dev, (int)((k + 1) * CB));
+        ++g_pn_launches;
+        if ((err = cudaEventRecord(ev_diag, side)) != cudaSuccess) return err;
+        // main stream: the other tiles of the trailing update
+        const int64_t tiles = nb * (nb + 1) / 2 - 1;
+        if (tiles > 0) {
+            u.tile0 = 1;
+            chol_gemm_kernel<<<(unsigned)tiles, CG_THREADS, smem_gemm, stream>>>(u);
+            ++g_pn_launches;
+        }
+        if ((err = cudaStreamWaitEvent(stream, ev_diag, 0)) != cudaSuccess) return err;
+    }
+    return cudaGetLastError();
+}
+
+// b: (npad, nrhs) row-major, nrhs <= 8, overwritten with the solution of L L^T x = b
+cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream) {
+    const int64_t T = npad / CB;
+    for (int64_t k = 0; k < T; ++k) {  // L y = b
+        double* bk = b + k * CB * nrhs;
+        chol_diag_apply_kernel<<<1, CB, 0, stream>>>(invd + k * CB * CB, bk, nrhs, 0);
+        ++g_pn_launches;
+        const int64_t rows = npad - (k + 1) * CB;
+        if (rows > 0) {
+            chol_fwd_update_kernel<<<(unsigned)((rows + 31) / 32), 128, 0, stream>>>(
+                M + (k + 1) * CB * npad + k * CB, npad, bk, bk + CB * nrhs, rows, nrhs);
+            ++g_pn_launches;
+        }
+    }
+    for (int64_t i = T - 1; i >= 0; --i) {  // L^T x = y
+        double* bi = b + i * CB * nrhs;
+        chol_diag_apply_kernel<<<1, CB, 0, stream>>>(invd + i * CB * CB, bi, nrhs, 1);
+        ++g_pn_launches;
+        if (i > 0) {
+            chol_bwd_update_kernel<<<(unsigned)i, CB, 0, stream>>>(M + i * CB * npad, npad, bi, b, nrhs);
+            ++g_pn_launches;
+        }
+    }
+    return cudaGetLastError();
+}

@@ -85,6 +85,12 @@ cudaError_t pn_launch_pairs_extra(const PnExtraLaunch& g, cudaStream_t stream);
 cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op, double alpha, double beta,
                               cudaStream_t stream);
 
+// FP64 Cholesky (pncov_chol.cu)
+cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, double* panel, double* invd,
+                           int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
+                           cudaEvent_t ev_diag);
+cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream);
+
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
 // pn_plan_matvec fills m.jsplit (how many column-range splits the launch will use, which
 // sizes the `partial` scratch); pn_launch_matvec then runs with that plan
