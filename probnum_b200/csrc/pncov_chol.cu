@@ -14,9 +14,10 @@
 //                        also copied into a contiguous panel
 //                        mode 1: A[i,j] -= L[i,k] L[j,k]^T for all i >= j > k  (n^3/3 of the flops)
 // Both GEMM modes are C = A B^T with K-contiguous operands, i.e. exactly the "row.col" form of
-// mma.sync.m8n8k4.f64 (DMMA, the only FP64 tensor path of sm_100a): a CTA of 8 warps owns a
-// 128 x 128 tile, a warp 32 x 64 of it (64 accumulators per lane), operands stream through a
-// two-stage cp.async pipeline in K-chunks of 32 with a row stride of 36 doubles, which makes the
+// mma.sync.m8n8k4.f64 (DMMA, the only FP64 tensor path of sm_100a): a CTA of 4 warps owns a
+// 128 x 64 tile, a warp 32 x 64 of it (64 accumulators per lane; three CTAs per SM cover each
+// other's prologue and read-modify-write epilogue), operands stream through a
+// two-stage cp.async pipeline in K-chunks of 16 with a row stride of 20 doubles, which makes the
 // fragment loads bank-conflict free.
 // Solves use the stored inverse diagonal blocks: every substitution step is a 128 x 128 product
 // plus one pass over a block row / block column of L.
@@ -25,9 +26,10 @@
 namespace {
 
 constexpr int CB = 128;          // block size
-constexpr int CK = 32;           // K chunk of the GEMM pipeline
+constexpr int CK = 16;           // K chunk of the GEMM pipeline
 constexpr int CLD = CK + 4;      // shared-memory row stride in doubles (= 4 mod 16: conflict-free)
-constexpr int CG_THREADS = 256;
+constexpr int CG_THREADS = 128;
+constexpr int CTN = 64;          // columns of a GEMM tile (rows: CB)
 constexpr int CD_LD = CB + 1;    // diagonal kernel: padded row stride
 
 __device__ __forceinline__ void ch_dmma(double& c0, double& c1, double a, double b) {
@@ -53,41 +55,49 @@ struct ChGemm {
     int64_t ldc;
     double* panel;    // mode 0: contiguous copy of the new block column (ld = 128)
     int mode;
-    int tile0;        // mode 1: index of the first tile of this launch (tile 0 = the next diagonal block)
+    int tile0;        // index of the first half tile of this launch (mode 1: half tiles 0, 1 = the next diagonal block)
 };
 
-__global__ void __launch_bounds__(CG_THREADS, 1) chol_gemm_kernel(const __grid_constant__ ChGemm p) {
+__global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_constant__ ChGemm p) {
     extern __shared__ __align__(128) unsigned char smem[];
     double* As = reinterpret_cast<double*>(smem);  // [2][CB * CLD]
-    double* Bs = As + 2 * CB * CLD;                // [2][CB * CLD]
+    double* Bs = As + 2 * CB * CLD;                // [2][CTN * CLD]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int wm = warp & 3, wn = warp >> 2;  // 4 x 2 warps: 32 rows x 64 columns each
+    const int wm = warp;  // 4 warps: 32 rows x 64 columns each
 
+    // a CTA owns 128 rows x 64 columns: block (bi, bj), column half h
     int64_t bi, bj;
+    const int64_t t2 = (int64_t)blockIdx.x + p.tile0;
+    const int h = (int)(t2 & 1);
     if (p.mode == 0) {
-        bi = blockIdx.x;
+        bi = t2 >> 1;
         bj = 0;
     } else {  // linear index over the lower triangle (bj <= bi)
-        const int64_t t = (int64_t)blockIdx.x + p.tile0;
+        const int64_t t = t2 >> 1;
         bi = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
         while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
         while (bi * (bi + 1) / 2 > t) --bi;
         bj = t - bi * (bi + 1) / 2;
     }
     const double* At = p.A + bi * CB * p.lda;
-    const double* Bt = p.mode == 0 ? p.B : p.B + bj * CB * p.ldb;
-    double* Ct = p.C + bi * CB * p.ldc + (p.mode == 0 ? 0 : bj * CB);
+    const double* Bt = (p.mode == 0 ? p.B : p.B + bj * CB * p.ldb) + (int64_t)h * CTN * p.ldb;
+    double* Ct = p.C + bi * CB * p.ldc + (p.mode == 0 ? 0 : bj * CB) + h * CTN;
 
     auto load_chunk = [&](int kc, int buf) {
         double* as = As + buf * CB * CLD;
-        double* bs = Bs + buf * CB * CLD;
+        double* bs = Bs + buf * CTN * CLD;
         constexpr int PIECES = CK / 2;  // 16-byte pieces per row
 #pragma unroll
         for (int i = 0; i < CB * PIECES / CG_THREADS; ++i) {
             const int idx = tid + i * CG_THREADS;
             const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
             ch_cp_async16(as + row * CLD + c2, At + (int64_t)row * p.lda + kc * CK + c2);
+        }
+#pragma unroll
+        for (int i = 0; i < CTN * PIECES / CG_THREADS; ++i) {
+            const int idx = tid + i * CG_THREADS;
+            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
             ch_cp_async16(bs + row * CLD + c2, Bt + (int64_t)row * p.ldb + kc * CK + c2);
         }
         ch_cp_commit();
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chol_gemm_kernel(const __grid_c
         }
         __syncthreads();
         const double* as = As + buf * CB * CLD + (wm * 32 + g) * CLD + q;
-        const double* bs = Bs + buf * CB * CLD + (wn * 64 + g) * CLD + q;
+        const double* bs = Bs + buf * CTN * CLD + g * CLD + q;
 #pragma unroll
         for (int k4 = 0; k4 < CK / 4; ++k4) {
             double a[4], b[8];
@@ -132,12 +142,12 @@ __global__ void __launch_bounds__(CG_THREADS, 1) chol_gemm_kernel(const __grid_c
         const int row = wm * 32 + r * 8 + g;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            const int col = wn * 64 + c * 8 + 2 * q;
+            const int col = c * 8 + 2 * q;
             double2* dst = reinterpret_cast<double2*>(Ct + (int64_t)row * p.ldc + col);
             if (p.mode == 0) {
                 const double2 v = make_double2(acc[r][c][0], acc[r][c][1]);
                 *dst = v;
-                *reinterpret_cast<double2*>(p.panel + (bi * CB + row) * CB + col) = v;
+                *reinterpret_cast<double2*>(p.panel + (bi * CB + row) * CB + h * CTN + col) = v;
             } else {
                 double2 v = *dst;
                 v.x -= acc[r][c][0];
@@ -230,27 +240,56 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
             else if (c == i) dg[i] = r[ii][cc];
         }
     __syncthreads();
-    // inverse of L by forward substitution, one column per thread.  The lower triangle of `a` is
-    // free now and receives X = inv(L) (X[l][c] at a[l][c], c <= l); L[i][l] sits at a[l][i].  Loop
-    // bounds are uniform per warp (reads of L broadcast), entries above the diagonal are masked.
+    // inverse X of L, blocked 4 x 4 with 32 x 32 blocks.  L[i][l] sits at a[l][i] (upper triangle),
+    // X[i][c] goes to a[i][c] (lower triangle, free now).
+    // (A) diagonal blocks: forward substitution inside the block, one column per thread
     if (tid < CB) {
-        const int c = tid;
-        const int l0 = (tid >> 5) << 5;
-        for (int i = l0; i < CB; ++i) {
-            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int l = l0;
-            for (; l + 3 < i; l += 4) {
+        const int c = tid, b0 = (tid >> 5) << 5;
+        for (int i = b0; i < b0 + 32; ++i) {
+            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
+            int l = b0;
+            for (; l + 1 < i; l += 2) {
                 s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
                 s1 = pn_fma(-a[(l + 1) * CD_LD + i], (l + 1 >= c) ? a[(l + 1) * CD_LD + c] : 0.0, s1);
-                s2 = pn_fma(-a[(l + 2) * CD_LD + i], (l + 2 >= c) ? a[(l + 2) * CD_LD + c] : 0.0, s2);
-                s3 = pn_fma(-a[(l + 3) * CD_LD + i], (l + 3 >= c) ? a[(l + 3) * CD_LD + c] : 0.0, s3);
             }
-            for (; l < i; ++l) s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
-            const double xi = (i < c) ? 0.0 : ((s0 + s1) + (s2 + s3)) / dg[i];
-            if (i >= c) a[i * CD_LD + c] = xi;  // own column only: no other thread reads it
-            invL[i * CB + c] = xi;
+            if (l < i) s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
+            if (i >= c) a[i * CD_LD + c] = (s0 + s1) / dg[i];  // own column only
         }
-        for (int i = 0; i < l0; ++i) invL[i * CB + c] = 0.0;
+    }
+    __syncthreads();
+    // (B) off-diagonal blocks by block distance: X_ib = -X_ii (sum_{m=b}^{i-1} L_im X_mb); the blocks
+    // of one distance are independent.  T lives in colbuf's neighbourhood: reuse the (dead) first
+    // rows of the upper triangle?  No: L is still needed, so T gets its own 3 x 32 x 33 doubles.
+    double* T = colbuf + 2 * CB;
+    const int cc = tid & 31, rr0 = tid >> 5;  // a warp walks 32 adjacent columns of one row: L broadcasts
+    for (int dist = 1; dist < 4; ++dist) {
+        const int nblk = 4 - dist;
+        for (int o = rr0; o < nblk * 32; o += 8) {  // T[blk][rr][cc]
+            const int blk = o >> 5, rr = o & 31;
+            const int b = blk, i = blk + dist;
+            const int row = 32 * i + rr, col = 32 * b + cc;
+            double s0 = 0.0, s1 = 0.0;
+            for (int l = 32 * b; l < 32 * i; l += 2) {
+                s0 = pn_fma(a[l * CD_LD + row], (l >= col) ? a[l * CD_LD + col] : 0.0, s0);
+                s1 = pn_fma(a[(l + 1) * CD_LD + row], (l + 1 >= col) ? a[(l + 1) * CD_LD + col] : 0.0, s1);
+            }
+            T[(blk * 32 + rr) * 33 + cc] = s0 + s1;
+        }
+        __syncthreads();
+        for (int o = rr0; o < nblk * 32; o += 8) {  // X_ib = -X_ii T
+            const int blk = o >> 5, rr = o & 31;
+            const int b = blk, i = blk + dist;
+            const int row = 32 * i + rr, col = 32 * b + cc;
+            double s = 0.0;
+            for (int k = 0; k <= rr; ++k) s = pn_fma(a[row * CD_LD + 32 * i + k], T[(blk * 32 + k) * 33 + cc], s);
+            a[row * CD_LD + col] = -s;
+        }
+        __syncthreads();
+    }
+    // X to global memory, row-major, zeros above the diagonal
+    for (int idx = tid; idx < CB * CB; idx += 256) {
+        const int i = idx / CB, c = idx % CB;
+        invL[idx] = (c <= i) ? a[i * CD_LD + c] : 0.0;
     }
 }
 
@@ -342,8 +381,8 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
     if ((err = cudaMemsetAsync(info_dev, 0, sizeof(int), stream)) != cudaSuccess) return err;
     chol_prepare_diag_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(M, npad, n, npad, jitter);
     ++g_pn_launches;
-    const size_t smem_diag = sizeof(double) * (CB * CD_LD + 3 * CB);
-    const size_t smem_gemm = sizeof(double) * 4 * CB * CLD;
+    const size_t smem_diag = sizeof(double) * (CB * CD_LD + 3 * CB + 3 * 32 * 33);
+    const size_t smem_gemm = sizeof(double) * 2 * (CB + CTN) * CLD;
     if ((err = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(chol_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
     const int64_t T = npad / CB;
@@ -364,7 +403,7 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         p.ldc = npad;
         p.panel = panel;
         p.mode = 0;
-        chol_gemm_kernel<<<(unsigned)nb, CG_THREADS, smem_gemm, stream>>>(p);
+        chol_gemm_kernel<<<(unsigned)(2 * nb), CG_THREADS, smem_gemm, stream>>>(p);
         ++g_pn_launches;
         if ((err = cudaEventRecord(ev_panel, stream)) != cudaSuccess) return err;
         ChGemm u{};
@@ -379,7 +418,7 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         // side stream: tile (k + 1, k + 1) of the update, then the next diagonal factorisation
         if ((err = cudaStreamWaitEvent(side, ev_panel, 0)) != cudaSuccess) return err;
         u.tile0 = 0;
-        chol_gemm_kernel<<<1, CG_THREADS, smem_gemm, side>>>(u);
+        chol_gemm_kernel<<<2, CG_THREADS, smem_gemm, side>>>(u);
         ++g_pn_launches;
         chol_diag_kernel<<<1, 256, smem_diag, side>>>(u.C, npad, invd + (k + 1) * CB * CB, info_dev, (int)((k + 1) * CB));
         ++g_pn_launches;
@@ -387,8 +426,8 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         // main stream: the other tiles of the trailing update
         const int64_t tiles = nb * (nb + 1) / 2 - 1;
         if (tiles > 0) {
-            u.tile0 = 1;
-            chol_gemm_kernel<<<(unsigned)tiles, CG_THREADS, smem_gemm, stream>>>(u);
+            u.tile0 = 2;
+            chol_gemm_kernel<<<(unsigned)(2 * tiles), CG_THREADS, smem_gemm, stream>>>(u);
             ++g_pn_launches;
         }
         if ((err = cudaStreamWaitEvent(stream, ev_diag, 0)) != cudaSuccess) return err;
