@@ -195,13 +195,16 @@ def enable() -> None:
 # Cholesky + solves of the Bayesian-quadrature belief update on the device
 # ---------------------------------------------------------------------------------------------
 class DeviceCholesky:
-    """Upper-triangular-free stand-in for the ``(c, lower)`` pair of ``scipy.linalg.cho_factor``:
-    the factor of ``gram + jitter I`` stays in HBM (a torch tensor); only right-hand sides and
-    solutions cross PCIe.  Library code (cuSOLVER ``potrf`` / ``potrs`` through torch), i.e. the
-    baseline the survey names for this row, not a hand-written kernel."""
+    """Stand-in for the ``(c, lower)`` pair of ``scipy.linalg.cho_factor``: the factor of
+    ``gram + jitter I`` stays in HBM; only right-hand sides and solutions cross PCIe.
 
-    def __init__(self, factor):
-        self.factor = factor  # (n, n) lower-triangular torch.float64 CUDA tensor
+    ``backend="pncov"`` (default): the hand-written blocked FP64 Cholesky of libpncov
+    (csrc/pncov_chol.cu, DMMA trailing updates).  ``backend="cusolver"``: cuSOLVER ``potrf`` /
+    ``potrs`` through torch, the library baseline the survey names for this row."""
+
+    def __init__(self, factor, backend: str):
+        self.factor = factor  # _lib.Cholesky, or an (n, n) lower-triangular torch.float64 CUDA tensor
+        self.backend = backend
 
     # scipy returns a 2-tuple; the reference only ever passes it back to gram_cho_solve
     def __iter__(self):
@@ -211,37 +214,50 @@ class DeviceCholesky:
         return 2
 
     def solve(self, z: np.ndarray) -> np.ndarray:
+        zz = np.asarray(z, dtype=np.float64)
+        if self.backend == "pncov":
+            return self.factor.solve(zz.reshape(zz.shape[0], -1)).reshape(zz.shape)
         import torch  # noqa: PLC0415
 
-        zz = np.asarray(z, dtype=np.float64)
         rhs = torch.from_numpy(np.ascontiguousarray(zz.reshape(zz.shape[0], -1))).to(self.factor.device)
         sol = torch.cholesky_solve(rhs, self.factor, upper=False)
         return sol.cpu().numpy().reshape(zz.shape)
 
 
-def enable_quad_cholesky() -> None:
+def enable_quad_cholesky(backend: str = "pncov") -> None:
     """Route ``BQBeliefUpdate.compute_gram_cho_factor`` / ``gram_cho_solve``
     (quad/solvers/belief_updates/_belief_update.py:61-103) through the GPU.  At 16384 nodes
     the host ``dpotrf`` (1.5 TFLOP) takes ~15 s and dominates ``bayesquad_from_data`` once the
     Gram matrix itself is built on the device."""
+    if backend not in ("pncov", "cusolver"):
+        raise ValueError("backend must be 'pncov' or 'cusolver'")
     numpy2_compat()
-    import probnum  # noqa: PLC0415
-    import torch  # noqa: PLC0415
+    import probnum  # noqa: F401, PLC0415
     from probnum.quad.solvers.belief_updates import _belief_update as bu  # noqa: PLC0415
 
     cls = bu.BQBeliefUpdate
     if ("quad", cls) in _ORIGINALS:
-        return
+        factor0, solve0 = _ORIGINALS.pop(("quad", cls))  # switching backends: start from the originals
+        cls.compute_gram_cho_factor = factor0
+        cls.gram_cho_solve = solve0
     _ORIGINALS[("quad", cls)] = (cls.__dict__["compute_gram_cho_factor"], cls.__dict__["gram_cho_solve"])
-    device = torch.device("cuda", _mirror._lib.default_device())
 
-    def compute_gram_cho_factor(self, gram):
-        g = torch.from_numpy(np.ascontiguousarray(gram, dtype=np.float64)).to(device)
-        g.diagonal().add_(self.jitter)
-        factor, info = torch.linalg.cholesky_ex(g, upper=False)
-        if int(info.item()) != 0:
-            raise np.linalg.LinAlgError(f"{int(info.item())}-th leading minor of the array is not positive definite")
-        return DeviceCholesky(factor), True
+    if backend == "pncov":
+        def compute_gram_cho_factor(self, gram):
+            # raises numpy.linalg.LinAlgError for a non-positive pivot, like scipy
+            return DeviceCholesky(_mirror._lib.Cholesky(gram, jitter=float(self.jitter)), "pncov"), True
+    else:
+        import torch  # noqa: PLC0415
+
+        device = torch.device("cuda", _mirror._lib.default_device())
+
+        def compute_gram_cho_factor(self, gram):
+            g = torch.from_numpy(np.ascontiguousarray(gram, dtype=np.float64)).to(device)
+            g.diagonal().add_(self.jitter)
+            factor, info = torch.linalg.cholesky_ex(g, upper=False)
+            if int(info.item()) != 0:
+                raise np.linalg.LinAlgError(f"{int(info.item())}-th leading minor of the array is not positive definite")
+            return DeviceCholesky(factor, "cusolver"), True
 
     def gram_cho_solve(gram_cho_factor, z):
         chol = gram_cho_factor[0] if isinstance(gram_cho_factor, tuple) else gram_cho_factor

@@ -193,18 +193,23 @@ def test_bayesquad_with_device_cholesky_matches_cpu_run():
         return float(F.mean), float(F.var)
 
     m_cpu, v_cpu = run()
-    pb_patch.enable()
-    pb_patch.enable_quad_cholesky()
-    try:
-        m_gpu, v_gpu = run()
-    finally:
-        pb_patch.disable()
     from probnum.quad.solvers.belief_updates import _belief_update as bu
+    from probnum_b200 import _lib
 
-    assert bu.BQBeliefUpdate.gram_cho_solve.__module__ == bu.__name__  # reference methods restored
-    assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), np.abs(fun_evals).max())
-    # the variance is a difference of O(1) terms that cancels to ~1e-9: compare on that scale
-    assert abs(v_gpu - v_cpu) <= 1e-6 * abs(v_cpu) + 1e-13
+    for backend in ("pncov", "cusolver"):  # hand-written Cholesky of libpncov, and the library baseline
+        pb_patch.enable()
+        pb_patch.enable_quad_cholesky(backend)
+        launches = _lib.launch_count()
+        try:
+            m_gpu, v_gpu = run()
+        finally:
+            pb_patch.disable()
+        if backend == "pncov":
+            assert _lib.launch_count() - launches > 30  # Gram + the factorisation / solve kernels
+        assert bu.BQBeliefUpdate.gram_cho_solve.__module__ == bu.__name__  # reference methods restored
+        assert abs(m_gpu - m_cpu) <= 1e-9 * max(abs(m_cpu), np.abs(fun_evals).max()), backend
+        # the variance is a difference of O(1) terms that cancels to ~1e-9: compare on that scale
+        assert abs(v_gpu - v_cpu) <= 1e-6 * abs(v_cpu) + 1e-13, backend
 
 
 def test_evaluate_hook_is_restored():

@@ -114,17 +114,20 @@ m_big, v_big = bq(args.n_bq, tim_big)
 t0 = time.perf_counter()
 K = cf.ExpQuad((4,)).matrix(np.random.default_rng(42).normal(size=(args.n_bq, 4)))
 tim_big["gram_only_s"] = time.perf_counter() - t0
-gpu.enable_quad_cholesky()
-tim_chol = {}
-m_ch, v_ch = bq(args.n_bq, tim_chol)  # first call pays cuSOLVER initialisation
-tim_chol2 = {}
-m_ch, v_ch = bq(args.n_bq, tim_chol2)
+for backend in ("cusolver", "pncov"):
+    gpu.enable_quad_cholesky(backend)
+    tim_chol = {}
+    m_ch, v_ch = bq(args.n_bq, tim_chol)  # first call pays library initialisation / allocation
+    tim_chol2 = {}
+    m_ch, v_ch = bq(args.n_bq, tim_chol2)
+    out[f"config4_bayesquad_device_cholesky_{backend}"] = {
+        "n": args.n_bq, "first_call": tim_chol, "second_call": tim_chol2, "mean": m_ch, "var": v_ch,
+        "mean_abs_diff_vs_host_cholesky": abs(m_ch - m_big),
+        "note": ("SURVEY 8f N1 baseline: cho_factor / cho_solve through torch (cuSOLVER)" if backend == "cusolver" else
+                 "SURVEY 8f N1: hand-written blocked FP64 Cholesky of libpncov (csrc/pncov_chol.cu)")
+                + ", Gram still returned to the host",
+    }
 gpu.disable()
-out["config4_bayesquad_device_cholesky"] = {
-    "n": args.n_bq, "first_call": tim_chol, "second_call": tim_chol2, "mean": m_ch, "var": v_ch,
-    "mean_abs_diff_vs_host_cholesky": abs(m_ch - m_big),
-    "note": "SURVEY 8f N1 baseline: cho_factor / cho_solve through torch (cuSOLVER), Gram still returned to the host",
-}
 out["config4_bayesquad"] = {
     "n_compare": args.n_bq_cpu, "reference_cpu": tim_cpu, "gpu_gram": tim_gpu,
     "mean_abs_diff": abs(m_gpu - m_cpu), "var_rel_diff": abs(v_gpu - v_cpu) / abs(v_cpu),
