@@ -1,7 +1,18 @@
-import sys, os, numpy as np
-sys.path.insert(0, os.getcwd())
-from probnum_b200 import _lib
-n = 1024
-rng = np.random.default_rng(0)
-B = rng.normal(size=(n, n + 8)); A = B @ B.T / n + 0.1 * np.eye(n)
-ch = _lib.Cholesky(A); print(ch.last_factor_ms()); ch.close()
+"""One factorisation of a random SPD matrix (ncu driver): python tools/chol_probe.py [n]"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from probnum_b200 import _lib  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+torch.manual_seed(0)
+B = torch.randn((n, n + 64), dtype=torch.float64, device="cuda")
+A = B @ B.T / n
+A.diagonal().add_(0.1)
+torch.cuda.synchronize()
+ch = _lib.Cholesky(A.data_ptr(), on_device=True, n=n)
+print("factor ms", ch.last_factor_ms())
+ch.close()
