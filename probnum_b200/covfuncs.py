@@ -503,9 +503,13 @@ class _DenseOnly(CovarianceFunction):
         return _lib.pairs(self._kernel_params(), p, p).reshape(batch)
 
     def _evaluate_linop(self, x0, x1):
-        # the reference has no matrix-free form for these either: its operator caches the dense
-        # matrix (_covariance_linear_operator.py:78-81); here that matrix is built on the device
-        return linops.Matrix(self._evaluate_matrix(x0, x1))
+        # The reference has no matrix-free form for these families either: its operator caches the
+        # dense matrix and multiplies with NumPy (_covariance_linear_operator.py:78-81).  There is no
+        # device product for them here and no CPU stand-in: fail loudly.  Under patch.enable() the
+        # reference's own dense-cached operator is kept and only its matrix comes from the device.
+        raise NotImplementedError(
+            f"{type(self).__name__} has no matrix-free product on the device; use .matrix() "
+            "(the dense Gram is built on the GPU)")
 
 
 class Linear(_DenseOnly):
@@ -663,7 +667,10 @@ class _ArithmeticNode(CovarianceFunction):
         return self._evaluate_elementwise(x0, x1)
 
     def _evaluate_linop(self, x0, x1):
-        return linops.Matrix(self._evaluate_matrix(x0, x1))
+        # Scaled and Sum nodes compose the operators of their operands (linop() below); a Product has
+        # no operator form short of the dense matrix, which this module does not multiply on the CPU
+        raise NotImplementedError(
+            f"{type(self).__name__} has no matrix-free product on the device; use .matrix()")
 
 
 def _check_same_shapes(operands, what: str) -> None:

@@ -99,6 +99,26 @@ __global__ void unpack_y_kernel(const T* __restrict__ yp, int64_t rows, int kc, 
     if (c0 + c < k) y[i * ldy + c0 + c] = yp[idx];
 }
 
+// factorised ExpQuad product: v'_j = f_j v_j on the way in, y_i = f_i y'_i on the way out, with
+// f = slot 9 of the 12-double operand rows built by build_mma_operands_kernel
+__global__ void pack_v_scaled_kernel(const double* __restrict__ v, int64_t ldv, int64_t rows, int64_t rows_pad,
+                                     int64_t k, int64_t c0, int kc, const double* __restrict__ op12,
+                                     double* __restrict__ vp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows_pad * kc) return;
+    const int64_t j = idx / kc;
+    const int c = (int)(idx % kc);
+    vp[idx] = (j < rows && c0 + c < k) ? v[j * ldv + c0 + c] * op12[j * 12 + 9] : 0.0;
+}
+__global__ void unpack_y_scaled_kernel(const double* __restrict__ yp, int64_t rows, int kc, int64_t k, int64_t c0,
+                                       const double* __restrict__ op12, double* __restrict__ y, int64_t ldy) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * kc) return;
+    const int64_t i = idx / kc;
+    const int c = (int)(idx % kc);
+    if (c0 + c < k) y[i * ldy + c0 + c] = yp[idx] * op12[i * 12 + 9];
+}
+
 // per-coordinate sums of a point set, one block, fixed summation order (deterministic centre)
 __global__ void coord_sums_kernel(const double* __restrict__ aos, int64_t n, int d, double* __restrict__ sums) {
     __shared__ double red[1024];
@@ -123,7 +143,7 @@ __global__ void coord_sums_kernel(const double* __restrict__ aos, int64_t n, int
 __global__ void build_mma_operands_kernel(const double* __restrict__ aos, int64_t n, int64_t npad, int d,
                                           const double* __restrict__ centre, const double* __restrict__ scale,
                                           double iso_scale, double* __restrict__ a12, double* __restrict__ b12,
-                                          unsigned long long* __restrict__ max_norm) {
+                                          unsigned long long* __restrict__ max_norm, int expquad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
     double xt[8];
@@ -144,8 +164,12 @@ __global__ void build_mma_operands_kernel(const double* __restrict__ aos, int64_
     }
     pa[8] = nrm;
     pb[8] = nrm;
+    // ExpQuad: the outer factors exp(-|xt|^2) of the factorised product (PN_EPI_EXPQUAD_FACT)
+    const double ef = expquad ? exp(-nrm) : 0.0;
+    pa[9] = ef;
+    pb[9] = ef;
 #pragma unroll
-    for (int m = 9; m < 12; ++m) {
+    for (int m = 10; m < 12; ++m) {
         pa[m] = 0.0;
         pb[m] = 0.0;
     }
@@ -594,7 +618,7 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
         if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
         build_mma_operands_kernel<<<(unsigned)((P.npad + 255) / 256), 256, 0, stream>>>(
             (const double*)P.aos, P.n, P.npad, d, sums, scale_dev, iso, (double*)h->a12[sidx],
-            (double*)h->b12[sidx], max_norm);
+            (double*)h->b12[sidx], max_norm, expq ? 1 : 0);
         ++g_pn_launches;
     }
     if (h->symmetric) {
@@ -663,6 +687,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.a12 = h->a12[transpose ? 1 : 0];
         m.b12 = h->b12[transpose ? 0 : 1];
         m.epi = h->mma_epi;
+        const char* fenv = getenv("PNCOV_MATVEC_FACT");
+        m.fact = (m.use_mma == 2 && h->k.kind == PNCOV_EXPQUAD && !(fenv && strcmp(fenv, "off") == 0)) ? 1 : 0;
     }
     {
         // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
@@ -690,7 +716,10 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         {
             const int64_t total = C.npad * kc;
             const unsigned blocks = (unsigned)((total + 255) / 256);
-            if (es == 8)
+            if (m.fact)
+                pack_v_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc,
+                                                                 (const double*)m.b12, (double*)h->vpack);
+            else if (es == 8)
                 pack_v_kernel<double><<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc, (double*)h->vpack);
             else
                 pack_v_kernel<float><<<blocks, 256, 0, stream>>>((const float*)v, ldv, C.n, C.npad, k, c0, kc, (float*)h->vpack);
@@ -706,7 +735,10 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         {
             const int64_t total = R.n * kc;
             const unsigned blocks = (unsigned)((total + 255) / 256);
-            if (es == 8)
+            if (m.fact)
+                unpack_y_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)h->ypack, R.n, kc, k, c0,
+                                                                   (const double*)m.a12, (double*)y, ldy);
+            else if (es == 8)
                 unpack_y_kernel<double><<<blocks, 256, 0, stream>>>((const double*)h->ypack, R.n, kc, k, c0, (double*)y, ldy);
             else
                 unpack_y_kernel<float><<<blocks, 256, 0, stream>>>((const float*)h->ypack, R.n, kc, k, c0, (float*)y, ldy);

@@ -19,6 +19,9 @@ enum PnEpi : int {
     PN_EPI_RATQUAD1 = 5, // 1 / b
     PN_EPI_RATQUAD2 = 6, // 1 / b^2
     PN_EPI_RATQUADG = 7, // b^-alpha
+    // matrix-free product only: ExpQuad through exp(-|x|^2) exp(-|y|^2) exp(2 x.y); the kernel sees
+    // u = -2 x.y straight from the DMMA accumulators and the two outer factors ride on v and y
+    PN_EPI_EXPQUAD_FACT = 8,
 };
 
 struct PnEpiParams {

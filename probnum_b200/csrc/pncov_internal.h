@@ -49,6 +49,9 @@ struct PnMatvecLaunch {
     // and serves y_I and y_J; row blocks part, part + nparts, ... only (multi-GPU), y accumulated
     // with atomics from zero
     int sym, sym_part, sym_nparts;
+    // ExpQuad in factorised form (use_mma == 2): a12[.][9] / b12[.][9] hold exp(-|xt|^2); v arrives
+    // multiplied by the column factors, y leaves to be multiplied by the row factors
+    int fact;
     int in_f32;
     PnEpiParams epi;
 };

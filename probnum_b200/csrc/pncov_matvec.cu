@@ -49,6 +49,19 @@ __device__ __forceinline__ void mv_epi_tile(double (&S)[N], const PnEpiParams& P
     for (int i = 0; i < N; ++i) S[i] = K[i];
 }
 
+// epilogue of the norm-identity kernels: the factorised ExpQuad form needs no validity window (the
+// host admits it only for |u| <= 2 R^2 <= 128, far inside the fast exp2 range)
+template <int EPI, int N>
+__device__ __forceinline__ void mm_epi_tile(double (&S)[N], const PnEpiParams& P, const double* tabE,
+                                            const double* tabL) {
+    if constexpr (EPI == PN_EPI_EXPQUAD_FACT) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) S[i] = pn_exp2_prod_core(S[i], P.c_u, P, tabE);
+    } else {
+        mv_epi_tile<EPI>(S, P, tabE, tabL);
+    }
+}
+
 template <int N>
 __device__ __forceinline__ void mv_epi_dispatch(double (&S)[N], const PnEpiParams& P,
                                                 const double* tabE, const double* tabL) {
@@ -321,7 +334,14 @@ __global__ void __launch_bounds__(MM_THREADS)
                 const double ny1 = bt[(j + 2 * q + 1) * MM_LD + 8];
 #pragma unroll
                 for (int rg = 0; rg < MM_RG; ++rg) {
-                    double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
+                    double c0, c1;
+                    if constexpr (EPI == PN_EPI_EXPQUAD_FACT) {
+                        c0 = 0.0;
+                        c1 = 0.0;
+                    } else {
+                        c0 = nx[rg] + ny0;
+                        c1 = nx[rg] + ny1;
+                    }
 #pragma unroll
                     for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
                     S[s][2 * rg] = c0;
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(MM_THREADS)
 #pragma unroll
             for (int s = 0; s < MM_NS; ++s) {
                 const int j = jj + 8 * s;
-                mv_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
+                mm_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
 #pragma unroll
                 for (int k = 0; k < KC; ++k) {
                     const double v0 = vt[(j + 2 * q) * KC + k];
@@ -473,7 +493,14 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
                 const double ny1 = bt[(j + 2 * q + 1) * MM_LD + 8];
 #pragma unroll
                 for (int rg = 0; rg < MM_RG; ++rg) {
-                    double c0 = nx[rg] + ny0, c1 = nx[rg] + ny1;
+                    double c0, c1;
+                    if constexpr (EPI == PN_EPI_EXPQUAD_FACT) {
+                        c0 = 0.0;
+                        c1 = 0.0;
+                    } else {
+                        c0 = nx[rg] + ny0;
+                        c1 = nx[rg] + ny1;
+                    }
 #pragma unroll
                     for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
                     S[s][2 * rg] = c0;
@@ -483,7 +510,7 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
 #pragma unroll
             for (int s = 0; s < MM_NS; ++s) {
                 const int j = jj + 8 * s;
-                mv_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
+                mm_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
                 const double2 v01 = *reinterpret_cast<const double2*>(vt + j + 2 * q);
                 double t0 = 0.0, t1 = 0.0;
 #pragma unroll
@@ -931,7 +958,9 @@ cudaError_t launch_mma(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStre
 template <int KSTEPS, int KC>
 cudaError_t launch_mma_epi(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     switch (a.epi.epi) {
-        case PN_EPI_EXPQUAD: return launch_mma<KSTEPS, KC, PN_EPI_EXPQUAD>(a, sm, plan, stream);
+        case PN_EPI_EXPQUAD:
+            if (a.fact) return launch_mma<KSTEPS, KC, PN_EPI_EXPQUAD_FACT>(a, sm, plan, stream);
+            return launch_mma<KSTEPS, KC, PN_EPI_EXPQUAD>(a, sm, plan, stream);
         case PN_EPI_RATQUAD1: return launch_mma<KSTEPS, KC, PN_EPI_RATQUAD1>(a, sm, plan, stream);
         case PN_EPI_RATQUAD2: return launch_mma<KSTEPS, KC, PN_EPI_RATQUAD2>(a, sm, plan, stream);
         case PN_EPI_RATQUADG: return launch_mma<KSTEPS, KC, PN_EPI_RATQUADG>(a, sm, plan, stream);
@@ -1015,7 +1044,9 @@ cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
 template <int KSTEPS>
 cudaError_t launch_mma_sym_epi(const PnMatvecLaunch& a, cudaStream_t stream) {
     switch (a.epi.epi) {
-        case PN_EPI_EXPQUAD: return launch_mma_sym<KSTEPS, PN_EPI_EXPQUAD>(a, stream);
+        case PN_EPI_EXPQUAD:
+            if (a.fact) return launch_mma_sym<KSTEPS, PN_EPI_EXPQUAD_FACT>(a, stream);
+            return launch_mma_sym<KSTEPS, PN_EPI_EXPQUAD>(a, stream);
         case PN_EPI_RATQUAD1: return launch_mma_sym<KSTEPS, PN_EPI_RATQUAD1>(a, stream);
         case PN_EPI_RATQUAD2: return launch_mma_sym<KSTEPS, PN_EPI_RATQUAD2>(a, stream);
         case PN_EPI_RATQUADG: return launch_mma_sym<KSTEPS, PN_EPI_RATQUADG>(a, stream);

@@ -133,10 +133,16 @@ def test_dense_only_families_have_no_matrix_free_product():
     with pytest.raises(NotImplementedError):
         with _lib.Operator(pb.Linear((3,))._kernel_params(), x0) as op:
             op.matmul(np.ones((50, 1)))
-    # the mirror's linop is the dense matrix, like the reference's cached operator
-    L = pb.Linear((3,), constant=1.0).linop(x0)
+    # no CPU stand-in for the product either: the mirror says so
+    with pytest.raises(NotImplementedError):
+        pb.Linear((3,), constant=1.0).linop(x0)
+    with pytest.raises(NotImplementedError):
+        (pb.ExpQuad((3,)) * pb.Matern((3,))).linop(x0)
+    # Scaled / Sum nodes compose the matrix-free operators of isotropic operands
+    L = (2.0 * pb.ExpQuad((3,)) + pb.Matern((3,), nu=1.5)).linop(x0)
     v = np.random.default_rng(11).normal(size=(50, 2))
-    np.testing.assert_allclose(L @ v, (x0 @ x0.T + 1.0) @ v, rtol=1e-12)
+    want = (2.0 * pb.ExpQuad((3,)).matrix(x0) + pb.Matern((3,), nu=1.5).matrix(x0)) @ v
+    np.testing.assert_allclose(L @ v, want, rtol=1e-12, atol=1e-13)
 
 
 def test_error_behaviour():
