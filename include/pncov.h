@@ -187,6 +187,9 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
  *                           for all work already queued on that device first); only the lower
  *                           triangle is read.  *info = 0 on success, else the 1-based index of the
  *                           first non-positive pivot (scipy raises LinAlgError there); blocking.
+ *   pncov_chol_factor_gram  same, but the matrix is the Gram matrix of a (square, float64) operator
+ *                           handle: it is evaluated straight into the factorisation buffer and never
+ *                           visits the host ("keep gram device-resident")
  *   pncov_chol_solve        x = (L L^T)^-1 b for b, x: (n, nrhs) row-major HOST arrays
  *   pncov_chol_get_factor   lower-triangular factor to a host array (the strict upper triangle of
  *                           the output is unspecified, as with scipy.linalg.cho_factor)
@@ -196,6 +199,7 @@ typedef struct pncov_chol pncov_chol;
 PNCOV_API int pncov_chol_create(pncov_chol** out, int device, int64_t n);
 PNCOV_API int pncov_chol_destroy(pncov_chol* c);
 PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, double jitter, int a_on_device, int* info);
+PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitter, int* info);
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx);
 PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld);
 PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms);

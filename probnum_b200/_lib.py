@@ -61,6 +61,7 @@ SIGNATURES = {
     "pncov_chol_create": (ctypes.c_int, [ctypes.POINTER(_c_vp), ctypes.c_int, _c_i64]),
     "pncov_chol_destroy": (ctypes.c_int, [_c_vp]),
     "pncov_chol_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+    "pncov_chol_factor_gram": (ctypes.c_int, [_c_vp, _c_vp, ctypes.c_double, ctypes.POINTER(ctypes.c_int)]),
     "pncov_chol_solve": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
     "pncov_chol_get_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
     "pncov_chol_last_factor_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -350,6 +351,22 @@ class Cholesky:
         self._lib = lib
         self._h = _c_vp()
         self.device = default_device() if device is None else int(device)
+        if isinstance(a, Operator):  # Gram matrix of a square operator, evaluated into the factor buffer
+            if a.shape[0] != a.shape[1]:
+                raise ValueError("expected a square operator")
+            self.n = a.shape[0]
+            self.device = a.device
+            _check(lib.pncov_chol_create(ctypes.byref(self._h), self.device, self.n))
+            info = ctypes.c_int(0)
+            try:
+                _check(lib.pncov_chol_factor_gram(self._h, a._h, float(jitter), ctypes.byref(info)))
+            except Exception:
+                self.close()
+                raise
+            if info.value != 0:
+                self.close()
+                raise np.linalg.LinAlgError(f"{info.value}-th leading minor of the array is not positive definite")
+            return
         if on_device:
             self.n = int(n)
             ptr, lda = _c_vp(int(a)), int(ld if ld is not None else n)

@@ -26,9 +26,11 @@ calls raise.
 from __future__ import annotations
 
 import abc
+import collections
 import fractions
 import functools
 import operator
+import weakref
 from typing import Optional, Tuple
 
 import numpy as np
@@ -36,6 +38,44 @@ import numpy as np
 from . import _lib, hostmem, linops
 
 ShapeType = Tuple[int, ...]
+
+# Provenance of recent symmetric float64 Gram matrices returned by ``matrix(X)``: lets a consumer that
+# is handed the HOST array (the Bayesian-quadrature belief update passes it to its Cholesky) rebuild
+# the matrix on the device in a millisecond instead of uploading N^2 doubles.  Keyed by id(), guarded
+# by a weak reference and a sampled checksum, a handful of entries.
+_GRAM_PROVENANCE: "collections.OrderedDict" = collections.OrderedDict()
+_PROVENANCE_SAMPLES = 257
+
+
+def _sample_positions(n: int) -> np.ndarray:
+    return (np.arange(_PROVENANCE_SAMPLES, dtype=np.int64) * 2654435761) % (n * n)
+
+
+def _remember_gram(K: np.ndarray, params, x0: np.ndarray) -> None:
+    n = K.shape[0]
+    if K.ndim != 2 or K.shape[1] != n or K.dtype != np.float64 or n < 512:
+        return
+    try:
+        ref = weakref.ref(K)
+    except TypeError:
+        return
+    _GRAM_PROVENANCE[id(K)] = (ref, params, np.array(x0, dtype=np.float64, copy=True),
+                               K.reshape(-1)[_sample_positions(n)].copy())
+    while len(_GRAM_PROVENANCE) > 4:
+        _GRAM_PROVENANCE.popitem(last=False)
+
+
+def gram_provenance(K: np.ndarray):
+    """``(kernel_params, points)`` if ``K`` is an unmodified symmetric Gram matrix returned by this
+    module (same object, sampled entries unchanged), else ``None``."""
+    entry = _GRAM_PROVENANCE.get(id(K))
+    if entry is None:
+        return None
+    ref, params, x0, samples = entry
+    if ref() is not K or not np.array_equal(K.reshape(-1)[_sample_positions(K.shape[0])], samples):
+        _GRAM_PROVENANCE.pop(id(K), None)
+        return None
+    return params, x0
 
 
 def _as_shape(x) -> ShapeType:
@@ -253,10 +293,12 @@ class CovarianceFunction(abc.ABC):
         out_dt = self._result_dtype(dt)
         if n0 == 0 or n1 == 0:
             return np.empty((n0, n1), dtype=out_dt)
-        with _lib.Operator(self._kernel_params(), self._points(x0, dt),
-                           None if x1 is None else self._points(x1, dt)) as op:
+        pts0 = self._points(x0, dt)
+        with _lib.Operator(self._kernel_params(), pts0, None if x1 is None else self._points(x1, dt)) as op:
             K = hostmem.empty((n0, n1), op.gram_dtype)
             op.gram(K)
+        if x1 is None:
+            _remember_gram(K, self._kernel_params(), pts0)
         return K
 
     def _evaluate_matrix(self, x0: np.ndarray, x1: Optional[np.ndarray]) -> np.ndarray:

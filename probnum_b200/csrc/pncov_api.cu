@@ -1210,6 +1210,25 @@ PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, doub
     return 0;
 }
 
+PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitter, int* info) {
+    if (!c || !h || !info) return fail(PNCOV_EINVAL, "NULL argument");
+    if (h->device != c->device) return fail(PNCOV_EINVAL, "operator and Cholesky handle live on different devices");
+    if (h->p0.n != c->n || h->p1.n != c->n) return fail(PNCOV_EINVAL, "the operator is not square of the handle's order");
+    if (h->k.gram_elem() != 8) return fail(PNCOV_EINVAL, "float64 Gram matrices only");
+    DeviceGuard guard(c->device);
+    c->factored = false;
+    // the Gram matrix is written straight into the factorisation buffer: it never visits the host
+    if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->M, 0, (size_t)c->npad * c->npad * 8, c->stream));
+    PN_CUDA(launch_gram_any(h, false, 0, c->n, c->M, c->npad, c->stream));
+    PN_CUDA(cudaEventRecord(c->ev0, c->stream));
+    PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->stream, c->side, c->ev_panel, c->ev_diag));
+    PN_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PN_CUDA(cudaMemcpyAsync(info, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    c->factored = *info == 0;
+    return 0;
+}
+
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx) {
     if (!c || !b || !x) return fail(PNCOV_EINVAL, "NULL argument");
     if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");

@@ -244,8 +244,17 @@ def enable_quad_cholesky(backend: str = "pncov") -> None:
 
     if backend == "pncov":
         def compute_gram_cho_factor(self, gram):
-            # raises numpy.linalg.LinAlgError for a non-positive pivot, like scipy
-            return DeviceCholesky(_mirror._lib.Cholesky(gram, jitter=float(self.jitter)), "pncov"), True
+            # raises numpy.linalg.LinAlgError for a non-positive pivot, like scipy.  A Gram matrix that
+            # this module built itself (and that is unchanged) is re-evaluated on the device straight
+            # into the factorisation buffer: a millisecond instead of an N^2 host-to-device copy.
+            origin = _mirror.gram_provenance(gram) if isinstance(gram, np.ndarray) else None
+            if origin is not None:
+                params, pts = origin
+                with _mirror._lib.Operator(params, pts) as op:
+                    chol = _mirror._lib.Cholesky(op, jitter=float(self.jitter))
+            else:
+                chol = _mirror._lib.Cholesky(gram, jitter=float(self.jitter))
+            return DeviceCholesky(chol, "pncov"), True
     else:
         import torch  # noqa: PLC0415
 

@@ -73,3 +73,28 @@ def test_device_input_and_timing():
     np.testing.assert_allclose(ch.factor(), np.linalg.cholesky(A), rtol=1e-11, atol=1e-13)
     assert ch.last_factor_ms() > 0
     ch.close()
+
+
+def test_factor_from_operator_keeps_the_gram_on_the_device():
+    """pncov_chol_factor_gram: the Gram matrix goes straight into the factorisation buffer."""
+    from probnum_b200 import covfuncs
+
+    rng = np.random.default_rng(5)
+    for n in (640, 1000):  # a multiple of 128 and a padded size
+        x = rng.normal(size=(n, 3))
+        k = pb.Matern((3,), nu=2.5)
+        K = k.matrix(x)
+        z = rng.normal(size=n)
+        ref = _lib.Cholesky(K, jitter=1e-6)
+        with _lib.Operator(k._kernel_params(), x) as op:
+            ch = _lib.Cholesky(op, jitter=1e-6)
+        np.testing.assert_allclose(ch.factor(), ref.factor(), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(ch.solve(z), ref.solve(z), rtol=1e-9, atol=1e-12)
+        # provenance: the host array returned by matrix() is recognised while it is unchanged
+        origin = covfuncs.gram_provenance(K)
+        assert origin is not None and np.array_equal(origin[1], x)
+        K[0, 0] += 1.0
+        assert covfuncs.gram_provenance(K) is None
+        assert covfuncs.gram_provenance(K.copy()) is None
+        ch.close()
+        ref.close()
