@@ -1237,11 +1237,19 @@ PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int
     for (int64_t c0 = 0; c0 < nrhs; c0 += 8) {
         const int k = (int)std::min<int64_t>(8, nrhs - c0);
         if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->rhs, 0, (size_t)c->npad * k * 8, c->stream));
-        PN_CUDA(cudaMemcpy2DAsync(c->rhs, (size_t)k * 8, b + c0, (size_t)ldb * 8, (size_t)k * 8, (size_t)c->n,
-                                  cudaMemcpyHostToDevice, c->stream));
+        // contiguous operands (the usual case) go as one linear copy: a pitched copy of 16-byte rows
+        // from pageable memory costs milliseconds
+        if (ldb == k)
+            PN_CUDA(cudaMemcpyAsync(c->rhs, b + c0, (size_t)c->n * k * 8, cudaMemcpyHostToDevice, c->stream));
+        else
+            PN_CUDA(cudaMemcpy2DAsync(c->rhs, (size_t)k * 8, b + c0, (size_t)ldb * 8, (size_t)k * 8, (size_t)c->n,
+                                      cudaMemcpyHostToDevice, c->stream));
         PN_CUDA(pn_chol_solve(c->M, c->npad, c->invd, c->rhs, k, c->stream));
-        PN_CUDA(cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, c->rhs, (size_t)k * 8, (size_t)k * 8, (size_t)c->n,
-                                  cudaMemcpyDeviceToHost, c->stream));
+        if (ldx == k)
+            PN_CUDA(cudaMemcpyAsync(x + c0, c->rhs, (size_t)c->n * k * 8, cudaMemcpyDeviceToHost, c->stream));
+        else
+            PN_CUDA(cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, c->rhs, (size_t)k * 8, (size_t)k * 8, (size_t)c->n,
+                                      cudaMemcpyDeviceToHost, c->stream));
     }
     PN_CUDA(cudaStreamSynchronize(c->stream));
     return 0;

@@ -300,65 +300,167 @@ __global__ void chol_prepare_diag_kernel(double* M, int64_t ld, int64_t n, int64
     else if (i < npad) M[i * ld + i] = 1.0;
 }
 
-// y = op(invL_k) b_k for one diagonal block (trans = 0: invL b, 1: invL^T b); nrhs columns, ld = nrhs
-__global__ void __launch_bounds__(CB) chol_diag_apply_kernel(const double* __restrict__ invL, double* __restrict__ b,
-                                                              int nrhs, int trans) {
-    __shared__ double bs[CB];
-    const int t = threadIdx.x;
-    for (int r = 0; r < nrhs; ++r) {
-        __syncthreads();
-        bs[t] = b[(int64_t)t * nrhs + r];
-        __syncthreads();
-        double s = 0.0;
-        if (!trans) {
-            for (int l = 0; l <= t; ++l) s = pn_fma(invL[t * CB + l], bs[l], s);  // lower triangular
-        } else {
-            for (int l = t; l < CB; ++l) s = pn_fma(invL[l * CB + t], bs[l], s);
+// ---- solves -------------------------------------------------------------------------------------------
+// Substitution runs over SUPER blocks of CS = 4 diagonal blocks (512 rows): one CTA resolves the
+// 512 x 512 triangle of a super block (diagonal blocks through their stored inverses, the six
+// off-diagonal blocks as 128 x 128 products), then one wide kernel applies the super block to
+// everything below (forward) or left of it (backward).  The dependency chain is 2 x n / 512
+// launches instead of 2 x n / 128.
+constexpr int CS = 4;
+constexpr int SV_THREADS = 256;
+
+// out (op)= op(M) v for a 128 x 128 block M, v in shared memory as [nrhs][CB]; (row-major, ld); trans = 0: M v, 1: M^T v.
+// acc = 0: out = result, acc = 1: out -= result (out: global [CB][nrhs]).  All SV_THREADS threads call it.
+__device__ __forceinline__ void sv_block_apply(const double* __restrict__ M, int64_t ld, int trans,
+                                               const double* __restrict__ vs, double* __restrict__ out, int nrhs,
+                                               int acc, double* __restrict__ red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!trans) {  // a warp per row, lanes read 4 adjacent columns: coalesced 1 KB per row
+        constexpr int RPW = CB / (SV_THREADS / 32);  // rows per warp; all loads in flight before the math
+        double4 mr[RPW];
+#pragma unroll
+        for (int i = 0; i < RPW; ++i)
+            mr[i] = *reinterpret_cast<const double4*>(M + (int64_t)(warp + i * (SV_THREADS / 32)) * ld + 4 * lane);
+#pragma unroll
+        for (int i = 0; i < RPW; ++i) {
+            const int row = warp + i * (SV_THREADS / 32);
+            const double4 m = mr[i];
+            for (int r = 0; r < nrhs; ++r) {
+                const double4 v4 = *reinterpret_cast<const double4*>(vs + r * CB + 4 * lane);  // vs is [rhs][CB]
+                double s = m.x * v4.x;
+                s = pn_fma(m.y, v4.y, s);
+                s = pn_fma(m.z, v4.z, s);
+                s = pn_fma(m.w, v4.w, s);
+#pragma unroll
+                for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+                if (lane == 0) out[row * nrhs + r] = acc ? out[row * nrhs + r] - s : s;
+            }
+        }
+    } else {  // a thread per column, the two halves of the rows on the two thread halves; one pass over
+              // the block for all right-hand sides
+        const int col = tid & (CB - 1), half = tid >> 7;
+        double s[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s[r] = 0.0;
+#pragma unroll 8
+        for (int l = half * (CB / 2); l < (half + 1) * (CB / 2); ++l) {
+            const double m = M[(int64_t)l * ld + col];
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < nrhs) s[r] = pn_fma(m, vs[r * CB + l], s[r]);
+        }
+        if (half) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < nrhs) red[r * CB + col] = s[r];
         }
         __syncthreads();
-        b[(int64_t)t * nrhs + r] = s;
+        if (!half) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < nrhs) {
+                    const double t = s[r] + red[r * CB + col];
+                    out[col * nrhs + r] = acc ? out[col * nrhs + r] - t : t;
+                }
+        }
+        __syncthreads();
     }
 }
 
-// forward: b_i -= L[i, k] y_k for the row blocks i > k.  One CTA per 32 rows, a warp per row.
-__global__ void __launch_bounds__(128) chol_fwd_update_kernel(const double* __restrict__ L, int64_t ld,
-                                                               const double* __restrict__ yk, double* __restrict__ b,
-                                                               int64_t rows, int nrhs) {
-    __shared__ double ys[CB * 8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < CB * nrhs; idx += 128) ys[idx] = yk[idx];
+// One CTA: the triangle of a super block.  fwd: for j = 0..nb-1: y_j = invL_j b_j; b_{j2} -= L[j2,j] y_j (j2 > j).
+// bwd: for j = nb-1..0: x_j = invL_j^T y_j; y_{j2} -= L[j,j2]^T x_j (j2 < j).  Ld: the (sb,sb) diagonal
+// super block of L (row-major, ld), invd: its nb inverse diagonal blocks, b: its rows of the rhs.
+__global__ void __launch_bounds__(SV_THREADS) chol_super_diag_kernel(const double* __restrict__ Ld, int64_t ld,
+                                                                      const double* __restrict__ invd,
+                                                                      double* __restrict__ b, int nrhs, int nb, int bwd) {
+    __shared__ double bs[CS * CB * 8];  // the super block's rows of the right-hand side live here throughout
+    __shared__ __align__(32) double vs[CB * 8];  // [rhs][CB]
+    __shared__ double red[CB * 8];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < nb * CB * nrhs; idx += SV_THREADS) bs[idx] = b[idx];
+    for (int step = 0; step < nb; ++step) {
+        const int j = bwd ? nb - 1 - step : step;
+        double* bj = bs + j * CB * nrhs;
+        __syncthreads();
+        for (int idx = tid; idx < CB * nrhs; idx += SV_THREADS) vs[(idx % nrhs) * CB + idx / nrhs] = bj[idx];
+        __syncthreads();
+        sv_block_apply(invd + (int64_t)j * CB * CB, CB, bwd, vs, bj, nrhs, 0, red);
+        __syncthreads();
+        for (int idx = tid; idx < CB * nrhs; idx += SV_THREADS) vs[(idx % nrhs) * CB + idx / nrhs] = bj[idx];  // the solved block
+        __syncthreads();
+        if (!bwd) {
+            for (int j2 = j + 1; j2 < nb; ++j2)
+                sv_block_apply(Ld + ((int64_t)j2 * CB) * ld + j * CB, ld, 0, vs, bs + j2 * CB * nrhs, nrhs, 1, red);
+        } else {
+            for (int j2 = 0; j2 < j; ++j2)
+                sv_block_apply(Ld + ((int64_t)j * CB) * ld + j2 * CB, ld, 1, vs, bs + j2 * CB * nrhs, nrhs, 1, red);
+        }
+    }
     __syncthreads();
-    for (int rr = 0; rr < 8; ++rr) {
-        const int64_t row = (int64_t)blockIdx.x * 32 + warp * 8 + rr;
+    for (int idx = tid; idx < nb * CB * nrhs; idx += SV_THREADS) b[idx] = bs[idx];
+}
+
+// forward: b_rows -= L[rows, super block] y_sb for the rows below the super block.  One CTA per 8
+// rows, a warp per row; width = columns of the super block (<= 512).
+__global__ void __launch_bounds__(128) chol_fwd_update_kernel(const double* __restrict__ L, int64_t ld,
+                                                               const double* __restrict__ ysb, double* __restrict__ b,
+                                                               int64_t rows, int nrhs, int width) {
+    __shared__ double ys[CS * CB * 8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int idx = tid; idx < width * nrhs; idx += 128) ys[idx] = ysb[idx];
+    __syncthreads();
+    for (int rr = 0; rr < 2; ++rr) {
+        const int64_t row = (int64_t)blockIdx.x * 8 + warp * 2 + rr;
         if (row >= rows) break;
         const double* lr = L + row * ld;
-        const double4 lv = *reinterpret_cast<const double4*>(lr + 4 * lane);
-        for (int r = 0; r < nrhs; ++r) {
-            double s = lv.x * ys[(4 * lane) * nrhs + r];
-            s = pn_fma(lv.y, ys[(4 * lane + 1) * nrhs + r], s);
-            s = pn_fma(lv.z, ys[(4 * lane + 2) * nrhs + r], s);
-            s = pn_fma(lv.w, ys[(4 * lane + 3) * nrhs + r], s);
+        double s[8];
 #pragma unroll
-            for (int m = 16; m > 0; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
-            if (lane == 0) b[row * nrhs + r] -= s;
+        for (int r = 0; r < 8; ++r) s[r] = 0.0;
+        double4 lvs[CS];  // the whole row segment in flight before the math
+#pragma unroll
+        for (int c = 0; c < CS; ++c)
+            if (c * CB < width) lvs[c] = *reinterpret_cast<const double4*>(lr + c * CB + 4 * lane);
+#pragma unroll
+        for (int c = 0; c < CS; ++c) {
+            if (c * CB >= width) break;
+            const int c0 = c * CB;
+            const double4 lv = lvs[c];
+            const double* yv = ys + (c0 + 4 * lane) * nrhs;
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+                if (r < nrhs) {
+                    s[r] = pn_fma(lv.x, yv[r], s[r]);
+                    s[r] = pn_fma(lv.y, yv[nrhs + r], s[r]);
+                    s[r] = pn_fma(lv.z, yv[2 * nrhs + r], s[r]);
+                    s[r] = pn_fma(lv.w, yv[3 * nrhs + r], s[r]);
+                }
         }
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+            if (r < nrhs) {
+                double t = s[r];
+#pragma unroll
+                for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+                if (lane == 0) b[row * nrhs + r] -= t;
+            }
     }
 }
 
-// backward: y_k -= L[i, k]^T x_i for all column blocks k < i.  One CTA per column block, a thread
-// per column, coalesced reads of the 128 rows of block row i.
+// backward: y_cols -= L[super block rows, cols]^T x_sb for all columns left of the super block.  One
+// CTA per 128 columns, a thread per column, coalesced reads of the `height` rows of the super block.
 __global__ void __launch_bounds__(CB) chol_bwd_update_kernel(const double* __restrict__ Li, int64_t ld,
-                                                              const double* __restrict__ xi, double* __restrict__ y,
-                                                              int nrhs) {
-    __shared__ double xs[CB * 8];
+                                                              const double* __restrict__ xsb, double* __restrict__ y,
+                                                              int nrhs, int height) {
+    __shared__ double xs[CS * CB * 8];
     const int t = threadIdx.x;
-    for (int idx = t; idx < CB * nrhs; idx += CB) xs[idx] = xi[idx];
+    for (int idx = t; idx < height * nrhs; idx += CB) xs[idx] = xsb[idx];
     __syncthreads();
     const int64_t col = (int64_t)blockIdx.x * CB + t;
     double s[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) s[r] = 0.0;
-    for (int l = 0; l < CB; ++l) {
+#pragma unroll 8
+    for (int l = 0; l < height; ++l) {
         const double v = Li[(int64_t)l * ld + col];
 #pragma unroll
         for (int r = 0; r < 8; ++r)
@@ -438,23 +540,30 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
 // b: (npad, nrhs) row-major, nrhs <= 8, overwritten with the solution of L L^T x = b
 cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream) {
     const int64_t T = npad / CB;
-    for (int64_t k = 0; k < T; ++k) {  // L y = b
-        double* bk = b + k * CB * nrhs;
-        chol_diag_apply_kernel<<<1, CB, 0, stream>>>(invd + k * CB * CB, bk, nrhs, 0);
+    const int64_t SB = (T + CS - 1) / CS;
+    for (int64_t sb = 0; sb < SB; ++sb) {  // L y = b
+        const int64_t k0 = sb * CS;
+        const int nb = (int)((T - k0 < CS) ? T - k0 : CS);
+        double* bk = b + k0 * CB * nrhs;
+        chol_super_diag_kernel<<<1, SV_THREADS, 0, stream>>>(M + k0 * CB * (npad + 1), npad, invd + k0 * CB * CB, bk, nrhs,
+                                                             nb, 0);
         ++g_pn_launches;
-        const int64_t rows = npad - (k + 1) * CB;
+        const int64_t rows = npad - (k0 + nb) * CB;
         if (rows > 0) {
-            chol_fwd_update_kernel<<<(unsigned)((rows + 31) / 32), 128, 0, stream>>>(
-                M + (k + 1) * CB * npad + k * CB, npad, bk, bk + CB * nrhs, rows, nrhs);
+            chol_fwd_update_kernel<<<(unsigned)((rows + 7) / 8), 128, 0, stream>>>(
+                M + (k0 + nb) * CB * npad + k0 * CB, npad, bk, bk + (int64_t)nb * CB * nrhs, rows, nrhs, nb * CB);
             ++g_pn_launches;
         }
     }
-    for (int64_t i = T - 1; i >= 0; --i) {  // L^T x = y
-        double* bi = b + i * CB * nrhs;
-        chol_diag_apply_kernel<<<1, CB, 0, stream>>>(invd + i * CB * CB, bi, nrhs, 1);
+    for (int64_t sb = SB - 1; sb >= 0; --sb) {  // L^T x = y
+        const int64_t k0 = sb * CS;
+        const int nb = (int)((T - k0 < CS) ? T - k0 : CS);
+        double* bk = b + k0 * CB * nrhs;
+        chol_super_diag_kernel<<<1, SV_THREADS, 0, stream>>>(M + k0 * CB * (npad + 1), npad, invd + k0 * CB * CB, bk, nrhs,
+                                                             nb, 1);
         ++g_pn_launches;
-        if (i > 0) {
-            chol_bwd_update_kernel<<<(unsigned)i, CB, 0, stream>>>(M + i * CB * npad, npad, bi, b, nrhs);
+        if (k0 > 0) {
+            chol_bwd_update_kernel<<<(unsigned)k0, CB, 0, stream>>>(M + k0 * CB * npad, npad, bk, b, nrhs, nb * CB);
             ++g_pn_launches;
         }
     }

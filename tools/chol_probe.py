@@ -1,7 +1,8 @@
-"""One factorisation of a random SPD matrix (ncu driver): python tools/chol_probe.py [n]"""
+"""One factorisation (+ one 2-column solve) of a random SPD matrix (ncu driver): python tools/chol_probe.py [n]"""
 import os
 import sys
 
+import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,4 +16,5 @@ A.diagonal().add_(0.1)
 torch.cuda.synchronize()
 ch = _lib.Cholesky(A.data_ptr(), on_device=True, n=n)
 print("factor ms", ch.last_factor_ms())
+x = ch.solve(np.ones((n, 2)))
 ch.close()
