@@ -133,17 +133,97 @@ def _make_linop_class():
     return GpuCovarianceLinearOperator
 
 
-def enable() -> None:
+_SHARDED: Optional[bool] = None
+_LOCAL_FACTORY = None
+
+
+def _use_sharded() -> bool:
+    """One process per GPU under torchrun: operators shard over the ranks of the default group."""
+    if _SHARDED is not None:
+        return _SHARDED
+    try:
+        import torch.distributed as dist  # noqa: PLC0415
+    except ImportError:
+        return False
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _make_sharded_linop_class():
+    import probnum  # noqa: PLC0415
+
+    from .sharded import ShardedCovarianceOperator  # noqa: PLC0415
+
+    class GpuShardedCovarianceLinearOperator(probnum.linops.LinearOperator):
+        """``k.linop(X)`` with the product spread over all ranks (probnum_b200.sharded): every rank
+        runs the same (sequential) solver on the same iterate and receives the full product after one
+        collective (BASELINE.json configs[3]: problinsolve via the GPU operator + NCCL)."""
+
+        def __init__(self, twin, x0, x1):
+            self._twin, self._x0, self._x1 = twin, x0, x1
+            n0 = x0.shape[0]
+            n1 = n0 if x1 is None else x1.shape[0]
+            dtype = np.promote_types(x0.dtype, x1.dtype) if x1 is not None else x0.dtype
+            if dtype not in (np.float32, np.float64):
+                dtype = np.dtype(np.float64)
+            self._sop = None
+            super().__init__((n0, n1), dtype)
+
+        def _sharded(self):
+            if self._sop is None:
+                self._sop = ShardedCovarianceOperator(self._twin, self._x0, self._x1, local_factory=_LOCAL_FACTORY)
+            return self._sop
+
+        def _matmul(self, x: np.ndarray) -> np.ndarray:
+            x = np.asarray(x)
+            lead, (n, k) = x.shape[:-2], x.shape[-2:]
+            if lead:  # stacked operands: fold the stack into columns
+                B = int(np.prod(lead, dtype=np.int64))
+                v = np.moveaxis(x.reshape(B, n, k), 0, 1).reshape(n, B * k)
+                y = self._sharded().matmul(v)
+                y = np.moveaxis(y.reshape(self.shape[0], B, k), 1, 0).reshape(lead + (self.shape[0], k))
+            else:
+                y = self._sharded().matmul(x)
+            return y.astype(np.result_type(self.dtype, x.dtype), copy=False)
+
+        def _transpose(self):
+            if self._x1 is None:
+                return self  # isotropic kernels: K(X, X) is symmetric
+            return GpuShardedCovarianceLinearOperator(self._twin, self._x1, self._x0)
+
+        def _todense(self) -> np.ndarray:
+            return self._twin._evaluate_matrix(self._x0, self._x1)
+
+        def _diagonal(self) -> np.ndarray:
+            n = min(self.shape)
+            if self._x1 is None:
+                return np.ones(n, dtype=self._twin._result_dtype(np.dtype(self.dtype)))
+            return np.array(self._twin(self._x0[:n], self._x1[:n]))
+
+        def _trace(self):
+            return np.sum(self._diagonal())
+
+    return GpuShardedCovarianceLinearOperator
+
+
+def enable(sharded: Optional[bool] = None, _local_factory=None) -> None:
     """Patch ExpQuad, Matern and RatQuad (Gram, operator, Gram-shaped calls) and the Gram hook of
     Linear, Polynomial, WhiteNoise, ProductMatern and the arithmetic nodes of the importable
-    ``probnum``."""
+    ``probnum``.
+
+    ``sharded``: ``None`` (default) shards ``k.linop(X)`` over the ranks of ``torch.distributed``
+    whenever a process group with more than one rank is initialised (one process per GPU under
+    torchrun), ``True`` / ``False`` force the choice.  ``_local_factory`` replaces the per-rank device
+    operator (CPU tests of the host logic only)."""
+    global _SHARDED, _LOCAL_FACTORY
     numpy2_compat()
     import probnum  # noqa: PLC0415
 
     if enabled():
         return
+    _SHARDED, _LOCAL_FACTORY = sharded, _local_factory
     cf = probnum.randprocs.covfuncs
     linop_cls = _make_linop_class()
+    sharded_cls = _make_sharded_linop_class()
 
     def make_matrix(original):
         def _evaluate_matrix(self, x0, x1):
@@ -159,6 +239,8 @@ def enable() -> None:
             twin = _mirror_of(self)
             if twin is None:
                 return original(self, x0, x1)
+            if _use_sharded():
+                return sharded_cls(twin, x0, x1)
             return linop_cls(twin._evaluate_linop(x0, x1))
 
         return _evaluate_linop

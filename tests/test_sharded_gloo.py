@@ -104,3 +104,64 @@ def test_sharded_operator_world_size_2(n0, n1):
         p.join(timeout=180)
     assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
     assert list(out) == [1] * world
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own caller over two ranks: problinsolve on k.linop(X) + sigma^2 I with the drop-in
+# installed in sharded mode (BASELINE.json configs[3]); per-rank compute is the oracle stand-in
+# ---------------------------------------------------------------------------------------------
+def _solver_worker(rank, world, port, n, out):
+    import sys
+    import warnings
+
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    sys.path.insert(0, ref)
+    import probnum_b200.patch as pb_patch
+
+    pb_patch.numpy2_compat()
+    warnings.simplefilter("ignore")
+    import probnum as pn
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(11)
+        X = rng.normal(size=(n, 3))
+        y = rng.normal(size=n)
+        k = pn.randprocs.covfuncs.Matern((3,), nu=1.5, lengthscales=0.8)
+        A_ref = k.linop(X) + 1e-2 * pn.linops.Identity(n)          # reference operator (dense cached)
+        x_ref, _, _, info_ref = pn.linalg.problinsolve(A_ref, y, maxiter=15)
+        pb_patch.enable(_local_factory=OracleLocal)                  # sharded: a process group with 2 ranks exists
+        try:
+            L = k.linop(X)
+            assert type(L).__name__ == "GpuShardedCovarianceLinearOperator"
+            x_gpu, _, _, info = pn.linalg.problinsolve(L + 1e-2 * pn.linops.Identity(n), y, maxiter=15)
+        finally:
+            pb_patch.disable()
+        assert info["iter"] == info_ref["iter"]
+        np.testing.assert_allclose(x_gpu.mean, x_ref.mean, rtol=1e-8, atol=1e-10)
+        t = torch.from_numpy(np.ascontiguousarray(x_gpu.mean))
+        gathered = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        assert all(torch.equal(g, gathered[0]) for g in gathered)  # replicas stay in lock step
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                   "baseline", "_ref", "probnum")),
+                    reason="needs the installed reference (baseline/_ref)")
+def test_problinsolve_over_two_ranks_with_the_sharded_dropin():
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    port = _free_port()
+    procs = [ctx.Process(target=_solver_worker, args=(r, world, port, 150, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    assert list(out) == [1] * world
