@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
     }
     __syncthreads();
     // (B) off-diagonal blocks by block distance: X_ib = -X_ii (sum_{m=b}^{i-1} L_im X_mb); the blocks
-    // of one distance are independent.  T lives in colbuf's neighbourhood: reuse the (dead) first
-    // rows of the upper triangle?  No: L is still needed, so T gets its own 3 x 32 x 33 doubles.
+    // of one distance are independent.  The inner sums T (up to 3 blocks of 32 x 32 at a time, row
+    // stride 33) have their own shared-memory area: both triangles of `a` are still in use.
     double* T = colbuf + 2 * CB;
     const int cc = tid & 31, rr0 = tid >> 5;  // a warp walks 32 adjacent columns of one row: L broadcasts
     for (int dist = 1; dist < 4; ++dist) {
