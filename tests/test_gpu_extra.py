@@ -154,3 +154,28 @@ def test_error_behaviour():
         pb.Polynomial((3,), exponent=2.5).matrix(np.ones((4, 3)))
     with pytest.raises(ValueError):
         pb.Linear((3,)).matrix(np.ones((4, 2)))
+
+
+def test_edge_shapes_of_the_dense_only_families():
+    """Empty point sets, a single point, scalar inputs, wide d (several coordinate chunks)."""
+    rng = np.random.default_rng(12)
+    for k, spec in [
+        (pb.Linear((3,), constant=0.5), dict(kind="linear", input_shape=[3], constant=0.5)),
+        (pb.WhiteNoise((3,), sigma_sq=0.2), dict(kind="whitenoise", input_shape=[3], sigma_sq=0.2)),
+        (pb.ProductMatern((3,), lengthscales=1.0, nus=1.5), dict(kind="productmatern", input_shape=[3], lengthscales=1.0, nus=1.5)),
+    ]:
+        assert k.matrix(np.empty((0, 3))).shape == (0, 0)
+        assert k.matrix(np.empty((0, 3)), rng.normal(size=(4, 3))).shape == (0, 4)
+        assert k.matrix(rng.normal(size=(4, 3)), np.empty((0, 3))).shape == (4, 0)
+        one = rng.normal(size=(1, 3))
+        np.testing.assert_allclose(k.matrix(one), xo.gram(spec, one), rtol=1e-12, atol=1e-12)
+    ks = pb.Polynomial((), constant=1.0, exponent=2)
+    x = rng.normal(size=9)
+    np.testing.assert_allclose(ks.matrix(x), (x[:, None] * x[None, :] + 1.0) ** 2, rtol=1e-12, atol=1e-12)
+    # d = 70: five coordinate chunks in gram_extra_kernel
+    spec = dict(kind="productmatern", input_shape=[70], lengthscales=3.0, nus=0.5)
+    x0, x1 = rng.normal(size=(130, 70)), rng.normal(size=(77, 70))
+    np.testing.assert_allclose(pb.ProductMatern((70,), lengthscales=3.0, nus=0.5).matrix(x0, x1), xo.gram(spec, x0, x1),
+                               rtol=1e-12, atol=1e-12)
+    # arithmetic with an empty operand set keeps shapes and dtypes
+    assert (2.0 * pb.ExpQuad((3,)) + pb.Linear((3,))).matrix(np.empty((0, 3))).shape == (0, 0)
