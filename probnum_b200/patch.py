@@ -362,6 +362,8 @@ def enable_quad_cholesky(backend: str = "pncov") -> None:
 
 def disable() -> None:
     """Undo :func:`enable`."""
+    global _SHARDED, _LOCAL_FACTORY
+    _SHARDED, _LOCAL_FACTORY = None, None
     quad = [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "quad"]
     for key in quad:
         factor, solve = _ORIGINALS.pop(key)
