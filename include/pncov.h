@@ -149,6 +149,16 @@ PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int
 PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void* y, int part, int nparts,
                                            void* stream);
 
+/* Per-handle choice of the product kernels (value: 1 on, 0 off, -1 default = automatic, subject to the
+ * PNCOV_MATVEC_IDENT / _SYM / _FACT environment switches).  Switching all three off selects the most
+ * conservative kernel -- direct differences like the reference, fixed summation order -- which is the
+ * analogue of the reference's `_use_keops = False`
+ * (tests/test_randprocs/test_covfuncs/test_linop_matrix.py:38-43). */
+#define PNCOV_OPT_IDENTITY 0   /* norm identity |x|^2 + |y|^2 - 2 x.y on DMMA (ExpQuad / RatQuad) */
+#define PNCOV_OPT_SYMMETRIC 1  /* symmetric halving (atomics: run-dependent summation order) */
+#define PNCOV_OPT_FACTORISED 2 /* ExpQuad as exp(-|x|^2) exp(-|y|^2) exp(2 x.y) */
+PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value);
+
 /* elementwise evaluation out[b] = k(x0[b], x1[b]) -------------------------------------
  * replaces the broadcasting path of CovarianceFunction.__call__
  * (_covariance_function.py:280-357) after the caller has broadcast both arguments

@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpncov.so")
 EXPQUAD, MATERN, RATQUAD = 0, 1, 2
 LINEAR, POLYNOMIAL, WHITENOISE, PRODUCT_MATERN = 3, 4, 5, 6
 COMBINE_LINEAR, COMBINE_MULTIPLY = 0, 1
+OPT_IDENTITY, OPT_SYMMETRIC, OPT_FACTORISED = 0, 1, 2
 F64, F32 = 0, 1
 MAX_MATERN_P = 8
 
@@ -48,6 +49,7 @@ SIGNATURES = {
     "pncov_matmul_device": (
         ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int, _c_vp]),
     "pncov_matmul_sym_part_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
+    "pncov_set_option": (ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.c_int]),
     "pncov_pairs": (
         ctypes.c_int,
         [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64, ctypes.c_double,
@@ -257,6 +259,15 @@ class Operator:
                       transpose: bool = False, stream: int = 0) -> None:
         _check(self._lib.pncov_matmul_device(self._h, _c_vp(v_ptr), k, ldv, _c_vp(y_ptr), ldy,
                                              1 if transpose else 0, _c_vp(stream)))
+
+    def set_option(self, option: int, value: Optional[bool]) -> None:
+        """OPT_IDENTITY / OPT_SYMMETRIC / OPT_FACTORISED: True, False or None (automatic)."""
+        _check(self._lib.pncov_set_option(self._h, int(option), -1 if value is None else int(bool(value))))
+
+    def conservative(self) -> None:
+        """Direct differences and a fixed summation order for every product of this operator."""
+        for opt in (OPT_IDENTITY, OPT_SYMMETRIC, OPT_FACTORISED):
+            self.set_option(opt, False)
 
     def matmul_path(self) -> str:
         """'undecided', 'norm-identity-dmma' or 'direct-differences' (see pncov_matmul_path)."""

@@ -327,6 +327,10 @@ class CovarianceLinearOperator(linops.LinearOperator):
         self._parent = _transposed_of
         self._op: Optional[_lib.Operator] = None
         self._last_product = None  # (operand, result) of the most recent narrow product
+        # The reference's tests switch its accelerated path off per operator with `_use_keops = False`
+        # (test_linop_matrix.py:38-43).  Same attribute here: False selects the conservative device
+        # kernels (direct differences like the reference, fixed summation order), never a CPU path.
+        self._use_keops = True
         n0 = x0.shape[0]
         n1 = n0 if x1 is None else x1.shape[0]
         shape = (n0, n1) if _transposed_of is None else (n1, n0)
@@ -343,6 +347,13 @@ class CovarianceLinearOperator(linops.LinearOperator):
             dt = cf._compute_dtype(root._x0, root._x1)
             root._op = _lib.Operator(cf._kernel_params(), cf._points(root._x0, dt),
                                      None if root._x1 is None else cf._points(root._x1, dt))
+            root._op_conservative = False
+        want = not (self._use_keops and root._use_keops)
+        if want != root._op_conservative:
+            for opt in (_lib.OPT_IDENTITY, _lib.OPT_SYMMETRIC, _lib.OPT_FACTORISED):
+                root._op.set_option(opt, False if want else None)
+            root._op_conservative = want
+            root._last_product = None
         return root._op
 
     @property

@@ -429,6 +429,8 @@ struct pncov_handle {
     // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
     bool last_sym = false;       // the last product ran the symmetric-halving kernel
+    // per-handle kernel selection (pncov_set_option); -1 = default (environment / automatic)
+    int opt_identity = -1, opt_symmetric = -1, opt_factorised = -1;
     void* a12[2] = {nullptr, nullptr};  // per point set (0: x0, 1: x1); aliases when symmetric
     void* b12[2] = {nullptr, nullptr};
     PnEpiParams mma_epi{};
@@ -579,7 +581,7 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     if (h->p0.n == 0 || h->p1.n == 0) return 0;
     {
         const char* form = getenv("PNCOV_MATVEC_IDENT");  // "off": always direct differences
-        if (form && strcmp(form, "off") == 0) return 0;
+        if (h->opt_identity < 0 && form && strcmp(form, "off") == 0) return 0;
     }
     const int d = k.d;
     double* sums = nullptr;
@@ -676,11 +678,11 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     m.kc = kc_max;
     m.in_f32 = h->k.dtype == PNCOV_F32;
     m.epi = h->k.epi;
-    {
+    if (h->opt_identity != 0) {
         int prc = mma_prepare(h, stream);
         if (prc) return prc;
     }
-    if (h->mma_state == 1) {
+    if (h->mma_state == 1 && h->opt_identity != 0) {
         // norm identity: dot products on DMMA by default (fastest measured), DFMA form opt-in
         const char* form = getenv("PNCOV_MATVEC_IDENT");
         m.use_mma = (form && strcmp(form, "dfma") == 0) ? 1 : 2;
@@ -688,15 +690,16 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.b12 = h->b12[transpose ? 0 : 1];
         m.epi = h->mma_epi;
         const char* fenv = getenv("PNCOV_MATVEC_FACT");
-        m.fact = (m.use_mma == 2 && h->k.kind == PNCOV_EXPQUAD && !(fenv && strcmp(fenv, "off") == 0)) ? 1 : 0;
+        const bool fact_on = h->opt_factorised >= 0 ? h->opt_factorised != 0 : !(fenv && strcmp(fenv, "off") == 0);
+        m.fact = (m.use_mma == 2 && h->k.kind == PNCOV_EXPQUAD && fact_on) ? 1 : 0;
     }
     {
         // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
         // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
         const char* symenv = getenv("PNCOV_MATVEC_SYM");
         const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 8);  // DMMA identity or direct differences
-        const bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 &&
-                            !(symenv && strcmp(symenv, "off") == 0);
+        const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : !(symenv && strcmp(symenv, "off") == 0);
+        const bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;
         if (sym_nparts > 0 && !sym_ok)
             return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 8 and n >= 2048");
         m.sym = sym_ok ? 1 : 0;
@@ -1276,9 +1279,21 @@ PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms) {
 
 PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
 
+PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (value < -1 || value > 1) return fail(PNCOV_EINVAL, "option values are -1 (default), 0 (off) or 1 (on)");
+    switch (option) {
+        case PNCOV_OPT_IDENTITY: h->opt_identity = value; return 0;  // gates the use, not the admissibility test
+        case PNCOV_OPT_SYMMETRIC: h->opt_symmetric = value; return 0;
+        case PNCOV_OPT_FACTORISED: h->opt_factorised = value; return 0;
+        default: return fail(PNCOV_EINVAL, "unknown option");
+    }
+}
+
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {
     if (!h || !path) return fail(PNCOV_EINVAL, "NULL argument");
-    *path = h->mma_state == 0 ? 0 : (h->mma_state == 1 ? (h->last_sym ? 3 : 1) : (h->last_sym ? 4 : 2));
+    const bool ident = h->mma_state == 1 && h->opt_identity != 0;
+    *path = (h->mma_state == 0 && h->opt_identity != 0) ? 0 : (ident ? (h->last_sym ? 3 : 1) : (h->last_sym ? 4 : 2));
     return 0;
 }
 

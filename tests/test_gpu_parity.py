@@ -532,3 +532,27 @@ def test_symmetric_matvec_can_be_switched_off(monkeypatch):
     assert L._device_op().matmul_path() == "norm-identity-dmma"
     np.testing.assert_array_equal(L._matmul_device(v), y1)  # the ordered kernel is bit-reproducible
     L.close()
+
+
+def test_use_keops_false_selects_the_conservative_device_kernels():
+    """The reference's tests switch its accelerated operator path off with `linop._use_keops = False`
+    (test_linop_matrix.py:38-43).  Here the same attribute selects direct differences and a fixed
+    summation order -- still on the device -- and the results agree with the default kernels."""
+    rng = np.random.default_rng(21)
+    x = rng.normal(size=(2600, 6))
+    v = rng.normal(size=(2600, 1))
+    spec = orc.KernelSpec("expquad", (6,), 1.1)
+    L = make_kernel(spec).linop(x)
+    y_fast = L._matmul_device(v)
+    assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
+    L._use_keops = False
+    y_cons = L._matmul_device(v)
+    assert L._device_op().matmul_path() == "direct-differences"
+    np.testing.assert_array_equal(L._matmul_device(v), y_cons)  # order-preserving: bit-reproducible
+    bound = orc.abs_matvec(spec, x, None, v)
+    assert_matvec_close(y_cons, orc.matvec(spec, x, None, v), bound, 1e-12)
+    assert np.all(np.abs(y_fast - y_cons) <= 1e-12 * bound)
+    L._use_keops = True
+    L._matmul_device(v)
+    assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
+    L.close()
