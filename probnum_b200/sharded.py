@@ -149,6 +149,18 @@ class ShardedCovarianceOperator:
     def __matmul__(self, v):
         return self.matmul(np.asarray(v))
 
+    # -- Gram matrix: row blocks per rank, no collective --------------------------------
+    def gram_block(self) -> np.ndarray:
+        """This rank's rows ``[lo, hi)`` of the Gram matrix, shape (hi - lo, N1), as a host array
+        (pinned when large).  Stacking the blocks of all ranks in rank order gives ``K(x0, x1)``."""
+        from . import hostmem  # noqa: PLC0415
+
+        rows, cols = self.hi - self.lo, self.shape[1]
+        out = hostmem.empty((rows, cols), getattr(self.local, "gram_dtype", self.dtype))
+        if rows and cols:
+            self.local.gram(out)
+        return out
+
     # -- device operands (torch CUDA tensors; NCCL all-gather on the current stream) ----------------
     def matmul_device(self, v, out=None):
         """``v``: CUDA tensor (N1, K) replicated on every rank.  Returns the full

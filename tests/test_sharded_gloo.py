@@ -32,6 +32,12 @@ class OracleLocal:
     def matmul(self, v):
         return orc.matvec(SPEC, self.rows, self.cols if self.cols is not None else self.rows, v)
 
+    gram_dtype = np.float64
+
+    def gram(self, out):
+        out[...] = orc.gram(SPEC, self.rows, self.cols if self.cols is not None else self.rows)
+        return out
+
     def matmul_sym_part(self, v, part, nparts, block=16):
         """Contribution of row blocks part, part + nparts, ... to K @ v, each off-diagonal tile
         used for y_I and y_J (the decomposition of pncov_matmul_sym_part_device)."""
@@ -72,6 +78,9 @@ def _worker(rank, world, port, n0, n1, out):
         gathered = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t)
         assert all(torch.equal(g, gathered[0]) for g in gathered)
+        # Gram matrix: each rank owns its row block, no collective
+        Kb = op.gram_block()
+        np.testing.assert_array_equal(Kb, orc.gram(SPEC, x0[op.lo:op.hi], x1))
         # symmetric operator, one column: partial vectors + all-reduce
         ops = ShardedCovarianceOperator(k, x0, None, local_factory=OracleLocal)
         assert ops.local_sym is not None

@@ -32,6 +32,8 @@ for (n0, n1, d, kernel, spec) in [
     want = orc.matvec(spec, x0, x1, v)
     bound = orc.abs_matvec(spec, x0, x1, v)
     assert np.all(np.abs(y - want) <= 1e-12 * bound), f"rank {rank}: host path mismatch"
+    Kb = op.gram_block()                           # this rank's row block of the Gram matrix
+    np.testing.assert_allclose(Kb, orc.gram(spec, x0[op.lo:op.hi], x1), rtol=1e-12, atol=1e-12)
     if n0 % world == 0:
         vd = torch.from_numpy(v).to(dev)
         yd = op.matmul_device(vd).cpu().numpy()     # device operands, in-place all-gather
