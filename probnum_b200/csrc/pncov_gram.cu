@@ -461,48 +461,73 @@ __global__ void __launch_bounds__(G_THREADS, 2)
 }
 
 // ---- chunk kernel (any d): coordinates streamed through shared memory in chunks ------------
+// d > G_DMAX.  The strip's column coordinates and the CTA's row coordinates arrive G_CD
+// coordinates at a time through a two-stage TMA bulk-copy + mbarrier pipeline, so the loads of
+// chunk c + 1 run under the arithmetic of chunk c (the first, unpipelined version spent more time
+// waiting for a chunk than computing on it: 2.3 x off the FP64 roofline at d = 32..100).
+constexpr int G_CD = 8;  // coordinates per pipeline stage
 template <typename T, typename TOut, bool ARD>
 __global__ void __launch_bounds__(G_THREADS)
     gram_chunk_kernel(const __grid_constant__ PnGramLaunch g, int vec_ok) {
     extern __shared__ __align__(128) unsigned char smem[];
     using P2 = typename Pair<T>::type;
     const int tid = threadIdx.x;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: chunk stages
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
-    T* sc = reinterpret_cast<T*>(smem + G_HDR_BYTES);
-    T* x1c = reinterpret_cast<T*>(smem + G_HDR_BYTES + 128);  // [G_DMAX][G_TN]
-    T* x0c = x1c + (size_t)G_DMAX * G_TN;                      // [G_DMAX][G_CHUNK_ROWS]
+    T* sc = reinterpret_cast<T*>(smem + G_HDR_BYTES);                 // [2][G_CD]
+    T* x1c = reinterpret_cast<T*>(smem + G_HDR_BYTES + 128);          // [2][G_CD][G_TN]
+    T* x0c = x1c + (size_t)2 * G_CD * G_TN;                            // [2][G_CD][G_CHUNK_ROWS]
+    constexpr int X1_STAGE = G_CD * G_TN, X0_STAGE = G_CD * G_CHUNK_ROWS;
 
     const int64_t col0 = (int64_t)blockIdx.x * G_TN;
     const int64_t row0 = (int64_t)blockIdx.y * G_CHUNK_ROWS;
     const T* x0g = static_cast<const T*>(g.x0_soa);
     const T* x1g = static_cast<const T*>(g.x1_soa);
+    const int n_chunks = (g.d + G_CD - 1) / G_CD;
+
+    auto issue = [&](int c, int buf) {  // thread 0 only
+        const int c0 = c * G_CD;
+        const int dc = (g.d - c0 < G_CD) ? g.d - c0 : G_CD;
+        pn_mbar_expect_tx(&bars[buf], (uint32_t)(dc * (G_TN + G_CHUNK_ROWS) * sizeof(T)));
+        for (int m = 0; m < dc; ++m) {
+            pn_bulk_g2s(x1c + (size_t)buf * X1_STAGE + (size_t)m * G_TN, x1g + (size_t)(c0 + m) * g.ld1 + col0,
+                        G_TN * sizeof(T), &bars[buf]);
+            pn_bulk_g2s(x0c + (size_t)buf * X0_STAGE + (size_t)m * G_CHUNK_ROWS, x0g + (size_t)(c0 + m) * g.ld0 + row0,
+                        G_CHUNK_ROWS * sizeof(T), &bars[buf]);  // rows are padded to PN_PAD
+        }
+    };
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) issue(0, 0);
     pn_stage_tables(tabE, tabL, tid, G_THREADS);
 
     T S[2 * G_CHUNK_ROWS];
 #pragma unroll
     for (int i = 0; i < 2 * G_CHUNK_ROWS; ++i) S[i] = T(0);
 
-    for (int c0 = 0; c0 < g.d; c0 += G_DMAX) {
-        const int dc = (g.d - c0 < G_DMAX) ? g.d - c0 : G_DMAX;
-        __syncthreads();
-        for (int idx = tid; idx < dc * G_TN; idx += G_THREADS) {
-            const int m = idx / G_TN, j = idx % G_TN;
-            x1c[idx] = x1g[(size_t)(c0 + m) * g.ld1 + col0 + j];
-        }
-        if (tid < dc * G_CHUNK_ROWS) {
-            const int m = tid / G_CHUNK_ROWS, r = tid % G_CHUNK_ROWS;
-            x0c[tid] = x0g[(size_t)(c0 + m) * g.ld0 + row0 + r];
-        }
-        if (ARD && tid < dc) sc[tid] = static_cast<const T*>(g.scale)[c0 + tid];
-        __syncthreads();
+    for (int c = 0; c < n_chunks; ++c) {
+        const int buf = c & 1;
+        const int c0 = c * G_CD;
+        const int dc = (g.d - c0 < G_CD) ? g.d - c0 : G_CD;
+        if (tid == 0 && c + 1 < n_chunks) issue(c + 1, buf ^ 1);
+        if (ARD && tid < dc) sc[buf * G_CD + tid] = static_cast<const T*>(g.scale)[c0 + tid];
+        __syncthreads();  // scale factors of this chunk visible (and the tables, first time round)
+        pn_mbar_wait(&bars[buf], (uint32_t)((c >> 1) & 1));
+        const T* x1b = x1c + (size_t)buf * X1_STAGE;
+        const T* x0b = x0c + (size_t)buf * X0_STAGE;
         for (int m = 0; m < dc; ++m) {
-            const P2 xb = *reinterpret_cast<const P2*>(x1c + (size_t)m * G_TN + 2 * tid);
+            const P2 xb = *reinterpret_cast<const P2*>(x1b + (size_t)m * G_TN + 2 * tid);
             T s = T(1);
-            if constexpr (ARD) s = sc[m];
+            if constexpr (ARD) s = sc[buf * G_CD + m];
 #pragma unroll
             for (int r = 0; r < G_CHUNK_ROWS; ++r) {
-                const T xa = x0c[m * G_CHUNK_ROWS + r];
+                const T xa = x0b[m * G_CHUNK_ROWS + r];
                 T da = xa - xb.x;
                 T db = xa - xb.y;
                 if constexpr (ARD) {
@@ -518,6 +543,7 @@ __global__ void __launch_bounds__(G_THREADS)
                 }
             }
         }
+        __syncthreads();  // everyone is done with stage `buf` before chunk c + 2 lands in it
     }
     TOut K[2 * G_CHUNK_ROWS];
     epi_dispatch(S, K, g.epi, tabE, tabL);
@@ -634,7 +660,7 @@ cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
             }
             return err;
         }
-        const size_t smem = G_HDR_BYTES + 128 + sizeof(T) * ((size_t)G_DMAX * G_TN + (size_t)G_DMAX * G_CHUNK_ROWS);
+        const size_t smem = G_HDR_BYTES + 128 + sizeof(T) * 2 * ((size_t)G_CD * G_TN + (size_t)G_CD * G_CHUNK_ROWS);
         auto kern = gram_chunk_kernel<T, TOut, ARD>;
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
