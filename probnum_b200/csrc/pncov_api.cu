@@ -670,6 +670,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     m.x1_aos = C.aos;
     m.x1_soa = C.soa;
     m.ld1 = C.npad;
+    m.x0_soa = R.soa;
+    m.ld0 = R.npad;
     m.n0 = R.n;
     m.n1 = C.n;
     m.n1pad = C.npad;

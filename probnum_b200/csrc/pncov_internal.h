@@ -28,8 +28,10 @@ struct PnGramLaunch {
 struct PnMatvecLaunch {
     const void* x0_aos;  // (n0pad, d) row point set (rows of K)
     const void* x1_aos;  // (n1pad, d) column point set, zero padded
-    const void* x1_soa;  // (d, ld1) coordinate-major copy of the same points (generic kernel)
+    const void* x1_soa;  // (d, ld1) coordinate-major copy of the same points (generic kernels)
     int64_t ld1;
+    const void* x0_soa;  // (d, ld0) coordinate-major copy of the row points (row-staged kernel, d > 8)
+    int64_t ld0;
     int64_t n0, n1, n1pad;
     const void* scale;   // as above
     int d;

@@ -803,6 +803,104 @@ __global__ void __launch_bounds__(MG_THREADS)
     }
 }
 
+// ---- direct-difference kernel for 8 < d <= MR_DMAX (and float32 points) ---------------------------
+// The generic kernel above re-reads its row point through L1 for every tile (32 scattered sectors
+// per warp load: 8x below the FP64 roofline at d = 16..64).  Here the CTA's 128 row points sit in
+// shared memory coordinate-major ([d][128]: consecutive lanes, conflict-free), column points
+// stream in coordinate-major tiles of MR_TJ, and a thread evaluates its row against 8 columns at
+// a time: per coordinate 1 + 4 shared loads (the column values as broadcast double2) for 16 FP64
+// instructions.
+constexpr int MR_THREADS = 128;
+constexpr int MR_TJ = 64;
+constexpr int MR_C = 8;      // columns per register tile
+constexpr int MR_DMAX = 96;  // row block fits 96 KB of shared memory in float64
+
+template <typename T, bool ARD, int KC>
+__global__ void __launch_bounds__(MR_THREADS)
+    matvec_rows_kernel(const __grid_constant__ PnMatvecLaunch a, const T* __restrict__ x0_soa, int64_t ld0,
+                       const T* __restrict__ x1_soa, int64_t ld1, int tiles_per_split) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int d = a.d;
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    T* sc = reinterpret_cast<T*>(smem + MV_HDR_BYTES);                     // [d]
+    T* xr = sc + ((d + 3) / 4) * 4;                                         // [d][MR_THREADS]
+    T* xt = xr + (size_t)d * MR_THREADS;                                    // [d][MR_TJ]
+    double* vt = reinterpret_cast<double*>(xt + (size_t)d * MR_TJ);         // [MR_TJ][KC]
+
+    pn_stage_tables(tabE, tabL, tid, MR_THREADS);
+    for (int m = tid; m < d; m += MR_THREADS) sc[m] = ARD ? static_cast<const T*>(a.scale)[m] : T(1);
+    const int64_t row = (int64_t)blockIdx.x * MR_THREADS + tid;  // padded rows are readable (zeros)
+    for (int m = 0; m < d; ++m) xr[m * MR_THREADS + tid] = x0_soa[(size_t)m * ld0 + row];
+    const T* vg = static_cast<const T*>(a.v);
+
+    const int64_t n_jt = (a.n1pad + MR_TJ - 1) / MR_TJ;
+    const int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+    double acc[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) acc[k] = 0.0;
+
+    for (int64_t jt = jt0; jt < jt1; ++jt) {
+        const int64_t jbase = jt * MR_TJ;
+        __syncthreads();
+        for (int idx = tid; idx < d * MR_TJ; idx += MR_THREADS) {
+            const int m = idx / MR_TJ, j = idx % MR_TJ;
+            xt[idx] = x1_soa[(size_t)m * ld1 + jbase + j];  // n1pad is a multiple of MR_TJ
+        }
+        for (int idx = tid; idx < MR_TJ * KC; idx += MR_THREADS) vt[idx] = (double)vg[jbase * KC + idx];
+        __syncthreads();
+        for (int jj = 0; jj < MR_TJ; jj += MR_C) {
+            T S[MR_C];
+#pragma unroll
+            for (int c = 0; c < MR_C; ++c) S[c] = T(0);
+            for (int m = 0; m < d; ++m) {
+                const T xa = xr[m * MR_THREADS + tid];
+                T s = T(1);
+                if constexpr (ARD) s = sc[m];
+#pragma unroll
+                for (int c = 0; c < MR_C; ++c) {
+                    T df = xa - xt[m * MR_TJ + jj + c];
+                    if constexpr (ARD) df *= s;
+                    if constexpr (std::is_same<T, double>::value) S[c] = pn_fma(df, df, S[c]);
+                    else S[c] = fmaf(df, df, S[c]);
+                }
+            }
+            double Kv[MR_C];
+            if constexpr (std::is_same<T, float>::value) {
+                if (a.epi.epi == PN_EPI_EXPQUAD) {
+#pragma unroll
+                    for (int c = 0; c < MR_C; ++c) Kv[c] = (double)exp2f(S[c] * (float)a.epi.c_u);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < MR_C; ++c) Kv[c] = (double)S[c];
+                    mv_epi_dispatch(Kv, a.epi, tabE, tabL);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < MR_C; ++c) Kv[c] = S[c];
+                mv_epi_dispatch(Kv, a.epi, tabE, tabL);
+            }
+#pragma unroll
+            for (int c = 0; c < MR_C; ++c)
+#pragma unroll
+                for (int k = 0; k < KC; ++k) acc[k] = pn_fma(Kv[c], vt[(jj + c) * KC + k], acc[k]);
+        }
+    }
+    if (row < a.n0) {
+        if (a.jsplit > 1) {
+            double* dst = static_cast<double*>(a.partial) + ((size_t)blockIdx.y * a.n0 + row) * KC;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) dst[k] = acc[k];
+        } else {
+            T* dst = static_cast<T*>(a.y) + row * KC;
+#pragma unroll
+            for (int k = 0; k < KC; ++k) dst[k] = (T)acc[k];
+        }
+    }
+}
+
 // partial[s][i] summed over s in increasing order (deterministic)
 template <typename T>
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, T* __restrict__ y,
@@ -1091,9 +1189,26 @@ cudaError_t launch_generic(const PnMatvecLaunch& a, const void* x1_soa, int64_t 
     return cudaGetLastError();
 }
 
+template <typename T, bool ARD, int KC>
+cudaError_t launch_rows(const PnMatvecLaunch& a, cudaStream_t stream) {
+    const int64_t n_jt = (a.n1pad + MR_TJ - 1) / MR_TJ;
+    const int64_t tps = (n_jt + a.jsplit - 1) / a.jsplit;
+    const size_t smem = MV_HDR_BYTES + sizeof(T) * (((a.d + 3) / 4) * 4 + (size_t)a.d * (MR_THREADS + MR_TJ)) +
+                        8 * (size_t)MR_TJ * KC + 16;
+    auto kern = matvec_rows_kernel<T, ARD, KC>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    dim3 grid((unsigned)((a.n0 + MR_THREADS - 1) / MR_THREADS), (unsigned)a.jsplit);
+    kern<<<grid, MR_THREADS, smem, stream>>>(a, static_cast<const T*>(a.x0_soa), a.ld0, static_cast<const T*>(a.x1_soa),
+                                             a.ld1, (int)tps);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 static bool uses_main_kernel(const PnMatvecLaunch& a) { return !a.in_f32 && a.d <= 8; }
+static bool uses_rows_kernel(const PnMatvecLaunch& a) { return a.d <= MR_DMAX && a.x0_soa != nullptr; }
 
 // fills a.jsplit for this shape (scratch sizing happens in the caller)
 cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
@@ -1110,6 +1225,11 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
     if (uses_main_kernel(a)) {
         const bool ard = a.scale != nullptr;
         return ard ? launch_main_d<true>(a, sm_count, true, nullptr) : launch_main_d<false>(a, sm_count, true, nullptr);
+    }
+    if (uses_rows_kernel(a)) {
+        const int64_t row_ctas = (a.n0 + MR_THREADS - 1) / MR_THREADS;
+        a.jsplit = choose_jsplit(row_ctas, (a.n1pad + MR_TJ - 1) / MR_TJ, sm_count * 2);
+        return cudaSuccess;
     }
     const int tj = generic_tj(a.d, a.in_f32 ? 4 : 8);
     if (tj < 4) return cudaErrorInvalidValue;
@@ -1135,6 +1255,14 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
         err = launch_ident_d(a, sm_count, false, stream);
     } else if (uses_main_kernel(a)) {
         err = ard ? launch_main_d<true>(a, sm_count, false, stream) : launch_main_d<false>(a, sm_count, false, stream);
+    } else if (uses_rows_kernel(a)) {
+        if (!a.in_f32) {
+            if (a.kc == 1) err = ard ? launch_rows<double, true, 1>(a, stream) : launch_rows<double, false, 1>(a, stream);
+            else err = ard ? launch_rows<double, true, 4>(a, stream) : launch_rows<double, false, 4>(a, stream);
+        } else {
+            if (a.kc == 1) err = ard ? launch_rows<float, true, 1>(a, stream) : launch_rows<float, false, 1>(a, stream);
+            else err = ard ? launch_rows<float, true, 4>(a, stream) : launch_rows<float, false, 4>(a, stream);
+        }
     } else if (!a.in_f32) {
         if (a.kc == 1) err = ard ? launch_generic<double, true, 1>(a, x1_soa, ld1, stream) : launch_generic<double, false, 1>(a, x1_soa, ld1, stream);
         else err = ard ? launch_generic<double, true, 4>(a, x1_soa, ld1, stream) : launch_generic<double, false, 4>(a, x1_soa, ld1, stream);
