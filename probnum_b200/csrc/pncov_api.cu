@@ -102,21 +102,22 @@ __global__ void unpack_y_kernel(const T* __restrict__ yp, int64_t rows, int kc, 
 // factorised ExpQuad product: v'_j = f_j v_j on the way in, y_i = f_i y'_i on the way out, with
 // f = slot 9 of the 12-double operand rows built by build_mma_operands_kernel
 __global__ void pack_v_scaled_kernel(const double* __restrict__ v, int64_t ldv, int64_t rows, int64_t rows_pad,
-                                     int64_t k, int64_t c0, int kc, const double* __restrict__ op12,
+                                     int64_t k, int64_t c0, int kc, const double* __restrict__ op12, int ld, int fi,
                                      double* __restrict__ vp) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows_pad * kc) return;
     const int64_t j = idx / kc;
     const int c = (int)(idx % kc);
-    vp[idx] = (j < rows && c0 + c < k) ? v[j * ldv + c0 + c] * op12[j * 12 + 9] : 0.0;
+    vp[idx] = (j < rows && c0 + c < k) ? v[j * ldv + c0 + c] * op12[j * ld + fi] : 0.0;
 }
 __global__ void unpack_y_scaled_kernel(const double* __restrict__ yp, int64_t rows, int kc, int64_t k, int64_t c0,
-                                       const double* __restrict__ op12, double* __restrict__ y, int64_t ldy) {
+                                       const double* __restrict__ op12, int ld, int fi, double* __restrict__ y,
+                                       int64_t ldy) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * kc) return;
     const int64_t i = idx / kc;
     const int c = (int)(idx % kc);
-    if (c0 + c < k) y[i * ldy + c0 + c] = yp[idx] * op12[i * 12 + 9];
+    if (c0 + c < k) y[i * ldy + c0 + c] = yp[idx] * op12[i * ld + fi];
 }
 
 // per-coordinate sums of a point set, one block, fixed summation order (deterministic centre)
@@ -136,43 +137,35 @@ __global__ void coord_sums_kernel(const double* __restrict__ aos, int64_t n, int
     }
 }
 
-// centred + scaled operands of the norm-identity matvec: xt = (x - c) * s
-//   a12[i] = [xt_0..xt_7, |xt|^2, 0, 0, 0]      b12[i] = [-2 xt_0..-2 xt_7, |xt|^2, 0, 0, 0]
-// rows [n, npad) are zero.  max_norm receives max_i |xt_i|^2 (bit pattern of a non-negative
-// double, so an integer atomicMax is exact and order independent).
-__global__ void build_mma_operands_kernel(const double* __restrict__ aos, int64_t n, int64_t npad, int d,
+// centred + scaled operands of the norm-identity matvec: xt = (x - c) * s, `ld` = dpad + 4 doubles per point
+//   a[i] = [xt_0..xt_{dpad-1}, |xt|^2, f, 0, 0]      b[i] = [-2 xt_0..-2 xt_{dpad-1}, |xt|^2, f, 0, 0]
+// with f = exp(-|xt|^2) for ExpQuad (the outer factors of the factorised product, PN_EPI_EXPQUAD_FACT)
+// and 0 otherwise; coordinates m >= d and rows [n, npad) are zero.  max_norm receives max_i |xt_i|^2
+// (bit pattern of a non-negative double, so an integer atomicMax is exact and order independent).
+__global__ void build_mma_operands_kernel(const double* __restrict__ aos, int64_t n, int64_t npad, int d, int dpad,
                                           const double* __restrict__ centre, const double* __restrict__ scale,
                                           double iso_scale, double* __restrict__ a12, double* __restrict__ b12,
                                           unsigned long long* __restrict__ max_norm, int expquad) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npad) return;
-    double xt[8];
+    const int ld = dpad + 4;
+    double* pa = a12 + i * ld;
+    double* pb = b12 + i * ld;
     double nrm = 0.0;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
+    for (int m = 0; m < dpad; ++m) {
         double v = 0.0;
         if (i < n && m < d) v = (aos[i * d + m] - centre[m]) * (scale ? scale[m] : iso_scale);
-        xt[m] = v;
+        pa[m] = v;
+        pb[m] = -2.0 * v;
         nrm = fma(v, v, nrm);
     }
-    double* pa = a12 + i * 12;
-    double* pb = b12 + i * 12;
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        pa[m] = xt[m];
-        pb[m] = -2.0 * xt[m];
-    }
-    pa[8] = nrm;
-    pb[8] = nrm;
-    // ExpQuad: the outer factors exp(-|xt|^2) of the factorised product (PN_EPI_EXPQUAD_FACT)
+    pa[dpad] = nrm;
+    pb[dpad] = nrm;
     const double ef = expquad ? exp(-nrm) : 0.0;
-    pa[9] = ef;
-    pb[9] = ef;
-#pragma unroll
-    for (int m = 10; m < 12; ++m) {
-        pa[m] = 0.0;
-        pb[m] = 0.0;
-    }
+    pa[dpad + 1] = ef;
+    pb[dpad + 1] = ef;
+    pa[dpad + 2] = pa[dpad + 3] = 0.0;
+    pb[dpad + 2] = pb[dpad + 3] = 0.0;
     if (i < n) atomicMax(max_norm, (unsigned long long)__double_as_longlong(nrm));
 }
 
@@ -428,7 +421,9 @@ struct pncov_handle {
     bool used_foreign_stream = false;  // a *_device entry point ran on a caller-owned stream
     // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
+    int mma_dpad = 8;            // coordinates per operand row (d padded to 8, 16 or 32)
     bool last_sym = false;       // the last product ran the symmetric-halving kernel
+    int last_use_mma = -1;       // kernel family of the last product (-1: none yet)
     // per-handle kernel selection (pncov_set_option); -1 = default (environment / automatic)
     int opt_identity = -1, opt_symmetric = -1, opt_factorised = -1;
     void* a12[2] = {nullptr, nullptr};  // per point set (0: x0, 1: x1); aliases when symmetric
@@ -577,7 +572,7 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     if (h->mma_state != 0) return 0;
     h->mma_state = -1;
     const KernelDesc& k = h->k;
-    if (k.dtype != PNCOV_F64 || k.d > 8 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
+    if (k.dtype != PNCOV_F64 || k.d > 32 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
     if (h->p0.n == 0 || h->p1.n == 0) return 0;
     {
         const char* form = getenv("PNCOV_MATVEC_IDENT");  // "off": always direct differences
@@ -585,23 +580,25 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     }
     const int d = k.d;
     double* sums = nullptr;
-    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&sums), 16 * sizeof(double) + sizeof(unsigned long long), stream));
-    unsigned long long* max_norm = reinterpret_cast<unsigned long long*>(sums + 16);
+    const int dpad = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
+    h->mma_dpad = dpad;
+    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&sums), 64 * sizeof(double) + sizeof(unsigned long long), stream));
+    unsigned long long* max_norm = reinterpret_cast<unsigned long long*>(sums + 64);
     auto fail_free = [&](int rc) {
         pn_dev_free(sums, stream);
         return rc;
     };
     coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p0.aos, h->p0.n, d, sums);
-    coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p1.aos, h->p1.n, d, sums + 8);
+    coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p1.aos, h->p1.n, d, sums + 32);
     g_pn_launches += 2;
-    double host_sums[16];
+    double host_sums[64];
     cudaError_t e = cudaMemcpyAsync(host_sums, sums, sizeof(host_sums), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
-    double centre[8] = {0};
+    double centre[32] = {0};
     const double ntot = (double)h->p0.n + (h->symmetric ? 0.0 : (double)h->p1.n);
     for (int m = 0; m < d; ++m)
-        centre[m] = (host_sums[m] + (h->symmetric ? 0.0 : host_sums[8 + m])) / ntot;
+        centre[m] = (host_sums[m] + (h->symmetric ? 0.0 : host_sums[32 + m])) / ntot;
     e = cudaMemcpyAsync(sums, centre, sizeof(centre), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(max_norm, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
@@ -614,12 +611,12 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     const int nsets = h->symmetric ? 1 : 2;
     for (int sidx = 0; sidx < nsets; ++sidx) {
         const Points& P = sidx == 0 ? h->p0 : h->p1;
-        const size_t bytes = (size_t)P.npad * 12 * sizeof(double);
+        const size_t bytes = (size_t)P.npad * (dpad + 4) * sizeof(double);
         e = pn_dev_alloc(&h->a12[sidx], bytes, stream);
         if (e == cudaSuccess) e = pn_dev_alloc(&h->b12[sidx], bytes, stream);
         if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
         build_mma_operands_kernel<<<(unsigned)((P.npad + 255) / 256), 256, 0, stream>>>(
-            (const double*)P.aos, P.n, P.npad, d, sums, scale_dev, iso, (double*)h->a12[sidx],
+            (const double*)P.aos, P.n, P.npad, d, dpad, sums, scale_dev, iso, (double*)h->a12[sidx],
             (double*)h->b12[sidx], max_norm, expq ? 1 : 0);
         ++g_pn_launches;
     }
@@ -684,7 +681,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         int prc = mma_prepare(h, stream);
         if (prc) return prc;
     }
-    if (h->mma_state == 1 && h->opt_identity != 0) {
+    const bool wide_ok = h->k.d <= 8 || kc_max == 1;  // the 8 < d <= 32 kernels take one right-hand side
+    if (h->mma_state == 1 && h->opt_identity != 0 && wide_ok) {
         // norm identity: dot products on DMMA by default (fastest measured), DFMA form opt-in
         const char* form = getenv("PNCOV_MATVEC_IDENT");
         m.use_mma = (form && strcmp(form, "dfma") == 0) ? 1 : 2;
@@ -694,6 +692,12 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         const char* fenv = getenv("PNCOV_MATVEC_FACT");
         const bool fact_on = h->opt_factorised >= 0 ? h->opt_factorised != 0 : !(fenv && strcmp(fenv, "off") == 0);
         m.fact = (m.use_mma == 2 && h->k.kind == PNCOV_EXPQUAD && fact_on) ? 1 : 0;
+        if (h->k.d > 8 && (m.use_mma != 2 || (h->k.kind == PNCOV_EXPQUAD && !m.fact))) {
+            m.use_mma = 0;  // wide operands exist only as DMMA kernels, ExpQuad only in factorised form
+            m.a12 = m.b12 = nullptr;
+            m.epi = h->k.epi;
+            m.fact = 0;
+        }
     }
     {
         // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
@@ -708,6 +712,7 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.sym_part = sym_part;
         m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;
         h->last_sym = m.sym != 0;
+        h->last_use_mma = m.use_mma;
     }
     PN_CUDA(pn_plan_matvec(m, h->sm_count));
     const int jsplit = m.jsplit;
@@ -723,7 +728,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
             const unsigned blocks = (unsigned)((total + 255) / 256);
             if (m.fact)
                 pack_v_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc,
-                                                                 (const double*)m.b12, (double*)h->vpack);
+                                                                 (const double*)m.b12, h->mma_dpad + 4, h->mma_dpad + 1,
+                                                                 (double*)h->vpack);
             else if (es == 8)
                 pack_v_kernel<double><<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc, (double*)h->vpack);
             else
@@ -742,7 +748,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
             const unsigned blocks = (unsigned)((total + 255) / 256);
             if (m.fact)
                 unpack_y_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)h->ypack, R.n, kc, k, c0,
-                                                                   (const double*)m.a12, (double*)y, ldy);
+                                                                   (const double*)m.a12, h->mma_dpad + 4, h->mma_dpad + 1,
+                                                                   (double*)y, ldy);
             else if (es == 8)
                 unpack_y_kernel<double><<<blocks, 256, 0, stream>>>((const double*)h->ypack, R.n, kc, k, c0, (double*)y, ldy);
             else
@@ -1294,8 +1301,12 @@ PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value) {
 
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {
     if (!h || !path) return fail(PNCOV_EINVAL, "NULL argument");
-    const bool ident = h->mma_state == 1 && h->opt_identity != 0;
-    *path = (h->mma_state == 0 && h->opt_identity != 0) ? 0 : (ident ? (h->last_sym ? 3 : 1) : (h->last_sym ? 4 : 2));
+    if (h->last_use_mma < 0) {
+        *path = 0;
+        return 0;
+    }
+    const bool ident = h->last_use_mma != 0;
+    *path = ident ? (h->last_sym ? 3 : 1) : (h->last_sym ? 4 : 2);
     return 0;
 }
 

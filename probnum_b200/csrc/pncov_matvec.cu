@@ -247,9 +247,19 @@ __global__ void __launch_bounds__(MV_THREADS)
 constexpr int MM_THREADS = 128;
 constexpr int MM_RG = 4;                          // row groups of 8 per warp
 constexpr int MM_ROWS = (MM_THREADS / 32) * MM_RG * 8;  // rows per CTA = 128
-constexpr int MM_TJ = 128;                        // columns per pipeline stage
-constexpr int MM_LD = 12;                         // doubles per point in a12 / b12
 constexpr int MM_NS = 2;                          // 8-column steps per inner iteration (tools/mv_variants.cu)
+// Operand layout and tile width by the number of k = 4 steps of the contraction (d <= 4 KSTEPS):
+// a point occupies LD doubles [xt(4 KSTEPS, at least 8), |xt|^2, exp(-|xt|^2), 0, 0]; LD = 4 or 12
+// (mod 16), which keeps the B-fragment loads bank-conflict free.  Wider operands get narrower column
+// tiles so that the two pipeline stages stay around 25 KB.
+template <int KSTEPS>
+struct MmCfg {
+    static constexpr int DPAD = KSTEPS < 2 ? 8 : 4 * KSTEPS;
+    static constexpr int LD = DPAD + 4;
+    static constexpr int NRM = DPAD;                      // index of |xt|^2 (the factor follows it)
+    static constexpr int TJ = KSTEPS <= 2 ? 128 : (KSTEPS <= 4 ? 64 : 32);  // columns per pipeline stage
+    static constexpr int MINB = KSTEPS <= 2 ? 4 : 2;      // CTAs per SM the symmetric kernel is compiled for
+};
 
 __device__ __forceinline__ void pn_dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -260,6 +270,7 @@ __device__ __forceinline__ void pn_dmma884(double& c0, double& c1, double a, dou
 template <int KSTEPS, int KC, int EPI>
 __global__ void __launch_bounds__(MM_THREADS)
     matvec_mma_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split) {
+    using Cfg = MmCfg<KSTEPS>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -267,15 +278,15 @@ __global__ void __launch_bounds__(MM_THREADS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
-    constexpr int STAGE_DOUBLES = MM_TJ * (MM_LD + KC);
+    constexpr int STAGE_DOUBLES = Cfg::TJ * (Cfg::LD + KC);
     double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
 
-    const int64_t n_jt = a.n1pad / MM_TJ;
+    const int64_t n_jt = a.n1pad / Cfg::TJ;
     const int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
     const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
     const double* bg = static_cast<const double*>(a.b12);
     const double* vg = static_cast<const double*>(a.v);
-    constexpr uint32_t B_BYTES = MM_TJ * MM_LD * 8, V_BYTES = MM_TJ * KC * 8;
+    constexpr uint32_t B_BYTES = Cfg::TJ * Cfg::LD * 8, V_BYTES = Cfg::TJ * KC * 8;
 
     if (tid == 0) {
         pn_mbar_init(&bars[0], 1);
@@ -285,8 +296,8 @@ __global__ void __launch_bounds__(MM_THREADS)
     __syncthreads();
     if (tid == 0 && jt0 < jt1) {
         pn_mbar_expect_tx(&bars[0], B_BYTES + V_BYTES);
-        pn_bulk_g2s(stage0, bg + jt0 * MM_TJ * MM_LD, B_BYTES, &bars[0]);
-        pn_bulk_g2s(stage0 + MM_TJ * MM_LD, vg + jt0 * MM_TJ * KC, V_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0, bg + jt0 * Cfg::TJ * Cfg::LD, B_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + Cfg::TJ * Cfg::LD, vg + jt0 * Cfg::TJ * KC, V_BYTES, &bars[0]);
     }
     pn_stage_tables(tabE, tabL, tid, MM_THREADS);
 
@@ -296,10 +307,10 @@ __global__ void __launch_bounds__(MM_THREADS)
         const double* ag = static_cast<const double*>(a.a12);
 #pragma unroll
         for (int rg = 0; rg < MM_RG; ++rg) {
-            const double* pr = ag + (row0 + rg * 8 + g) * MM_LD;  // rows are padded to PN_PAD
+            const double* pr = ag + (row0 + rg * 8 + g) * Cfg::LD;  // rows are padded to PN_PAD
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) af[rg][kk] = pr[4 * kk + q];
-            nx[rg] = pr[8];
+            nx[rg] = pr[Cfg::NRM];
 #pragma unroll
             for (int k = 0; k < KC; ++k) acc[rg][k] = 0.0;
         }
@@ -312,15 +323,15 @@ __global__ void __launch_bounds__(MM_THREADS)
         if (tid == 0 && jt + 1 < jt1) {
             double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
             pn_mbar_expect_tx(&bars[buf ^ 1], B_BYTES + V_BYTES);
-            pn_bulk_g2s(dst, bg + (jt + 1) * MM_TJ * MM_LD, B_BYTES, &bars[buf ^ 1]);
-            pn_bulk_g2s(dst + MM_TJ * MM_LD, vg + (jt + 1) * MM_TJ * KC, V_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst, bg + (jt + 1) * Cfg::TJ * Cfg::LD, B_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + Cfg::TJ * Cfg::LD, vg + (jt + 1) * Cfg::TJ * KC, V_BYTES, &bars[buf ^ 1]);
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
         const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
-        const double* vt = bt + MM_TJ * MM_LD;
+        const double* vt = bt + Cfg::TJ * Cfg::LD;
 
 #pragma unroll 1
-        for (int jj = 0; jj < MM_TJ; jj += 8 * MM_NS) {
+        for (int jj = 0; jj < Cfg::TJ; jj += 8 * MM_NS) {
             // MM_NS steps of 8 columns: all DMMAs first, then the epilogues, so that the
             // epilogue chains of one step overlap the DMMA latency of the next
             double S[MM_NS][2 * MM_RG];
@@ -329,9 +340,9 @@ __global__ void __launch_bounds__(MM_THREADS)
                 const int j = jj + 8 * s;
                 double bf[KSTEPS];
 #pragma unroll
-                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * MM_LD + 4 * kk + q];
-                const double ny0 = bt[(j + 2 * q) * MM_LD + 8];
-                const double ny1 = bt[(j + 2 * q + 1) * MM_LD + 8];
+                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * Cfg::LD + 4 * kk + q];
+                const double ny0 = bt[(j + 2 * q) * Cfg::LD + Cfg::NRM];
+                const double ny1 = bt[(j + 2 * q + 1) * Cfg::LD + Cfg::NRM];
 #pragma unroll
                 for (int rg = 0; rg < MM_RG; ++rg) {
                     double c0, c1;
@@ -394,12 +405,11 @@ __global__ void __launch_bounds__(MM_THREADS)
 // between runs, not bit-for-bit (PNCOV_MATVEC_SYM=off selects the order-preserving kernel).
 // Row blocks are dealt round-robin to `nparts` callers (multi-GPU: rank r takes blocks
 // I = r mod nparts and the partial vectors are summed by an all-reduce).
-#ifndef MMS_MINB
-#define MMS_MINB 4
-#endif
 template <int KSTEPS, int EPI>
-__global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
+__global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
     matvec_mma_sym_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split, int part, int nparts) {
+    using Cfg = MmCfg<KSTEPS>;
+    constexpr int TPB = MM_ROWS / Cfg::TJ;  // column tiles per row block: the diagonal spans TPB tiles
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -407,22 +417,23 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
-    constexpr int STAGE_DOUBLES = MM_TJ * (MM_LD + 1);
+    constexpr int STAGE_DOUBLES = Cfg::TJ * (Cfg::LD + 1);
     double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
-    double* colw = stage0 + 2 * STAGE_DOUBLES;  // [2][warps][MM_TJ] per-warp column sums of a tile
+    double* colw = stage0 + 2 * STAGE_DOUBLES;  // [2][warps][Cfg::TJ] per-warp column sums of a tile
 
-    static_assert(MM_ROWS == MM_TJ, "row blocks and column tiles must coincide on the diagonal");
-    const int64_t n_jt = a.n1pad / MM_TJ;
-    const int64_t bx = (int64_t)blockIdx.x * nparts + part;  // this CTA's row block = its diagonal tile
-    if (bx >= n_jt) return;
+    static_assert(MM_ROWS % Cfg::TJ == 0, "a row block must span whole column tiles");
+    const int64_t n_jt = a.n1pad / Cfg::TJ;
+    const int64_t bx = (int64_t)blockIdx.x * nparts + part;  // this CTA's row block; diagonal tiles TPB bx .. TPB bx + TPB - 1
+    if (bx * TPB >= n_jt) return;
+    const int64_t jdiag_end = (bx + 1) * TPB;               // first tile right of the diagonal block
     int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
     const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
-    if (jt0 < bx) jt0 = bx;
+    if (jt0 < bx * TPB) jt0 = bx * TPB;
     if (jt0 >= jt1) return;
     const double* bg = static_cast<const double*>(a.b12);
     const double* vg = static_cast<const double*>(a.v);
     double* yg = static_cast<double*>(a.y);
-    constexpr uint32_t B_BYTES = MM_TJ * MM_LD * 8, V_BYTES = MM_TJ * 8;
+    constexpr uint32_t B_BYTES = Cfg::TJ * Cfg::LD * 8, V_BYTES = Cfg::TJ * 8;
 
     if (tid == 0) {
         pn_mbar_init(&bars[0], 1);
@@ -433,8 +444,8 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
     __syncthreads();
     if (tid == 0) {
         pn_mbar_expect_tx(&bars[0], B_BYTES + V_BYTES);
-        pn_bulk_g2s(stage0, bg + jt0 * MM_TJ * MM_LD, B_BYTES, &bars[0]);
-        pn_bulk_g2s(stage0 + MM_TJ * MM_LD, vg + jt0 * MM_TJ, V_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0, bg + jt0 * Cfg::TJ * Cfg::LD, B_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + Cfg::TJ * Cfg::LD, vg + jt0 * Cfg::TJ, V_BYTES, &bars[0]);
         pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
     }
 
@@ -445,10 +456,10 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
 #pragma unroll
         for (int rg = 0; rg < MM_RG; ++rg) {
             const int64_t row = row0 + rg * 8 + g;
-            const double* pr = ag + row * MM_LD;  // rows are padded to PN_PAD
+            const double* pr = ag + row * Cfg::LD;  // rows are padded to PN_PAD
 #pragma unroll
             for (int kk = 0; kk < KSTEPS; ++kk) af[rg][kk] = pr[4 * kk + q];
-            nx[rg] = pr[8];
+            nx[rg] = pr[Cfg::NRM];
             vrow[rg] = vg[row];  // zero in the padding, so padded rows add nothing to column sums
             acc[rg] = 0.0;
         }
@@ -461,36 +472,36 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
         if (tid == 0 && jt + 1 < jt1) {
             double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
             pn_mbar_expect_tx(&bars[buf ^ 1], B_BYTES + V_BYTES);
-            pn_bulk_g2s(dst, bg + (jt + 1) * MM_TJ * MM_LD, B_BYTES, &bars[buf ^ 1]);
-            pn_bulk_g2s(dst + MM_TJ * MM_LD, vg + (jt + 1) * MM_TJ, V_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst, bg + (jt + 1) * Cfg::TJ * Cfg::LD, B_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + Cfg::TJ * Cfg::LD, vg + (jt + 1) * Cfg::TJ, V_BYTES, &bars[buf ^ 1]);
         }
         // column sums of the previous tile: one atomic per column (the slot was completed before
         // the barrier that ended the previous iteration)
-        if (it > 0 && jt - 1 > bx) {
-            const double* cw = colw + (buf ^ 1) * (MM_THREADS / 32) * MM_TJ;
+        if (it > 0 && jt - 1 >= jdiag_end && tid < Cfg::TJ) {
+            const double* cw = colw + (buf ^ 1) * (MM_THREADS / 32) * Cfg::TJ;
             double s = cw[tid];
 #pragma unroll
-            for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * MM_TJ + tid];
-            const int64_t col = (jt - 1) * MM_TJ + tid;
+            for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * Cfg::TJ + tid];
+            const int64_t col = (jt - 1) * Cfg::TJ + tid;
             if (col < a.n1) atomicAdd(yg + col, s);
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
         const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
-        const double* vt = bt + MM_TJ * MM_LD;
-        double* cw = colw + buf * (MM_THREADS / 32) * MM_TJ + warp * MM_TJ;
-        const bool mirror = jt > bx;  // uniform; the diagonal tile holds both (i, j) and (j, i) itself
+        const double* vt = bt + Cfg::TJ * Cfg::LD;
+        double* cw = colw + buf * (MM_THREADS / 32) * Cfg::TJ + warp * Cfg::TJ;
+        const bool mirror = jt >= jdiag_end;  // uniform; the diagonal tiles hold both (i, j) and (j, i) themselves
 
 #pragma unroll 1
-        for (int jj = 0; jj < MM_TJ; jj += 8 * MM_NS) {
+        for (int jj = 0; jj < Cfg::TJ; jj += 8 * MM_NS) {
             double S[MM_NS][2 * MM_RG];
 #pragma unroll
             for (int s = 0; s < MM_NS; ++s) {
                 const int j = jj + 8 * s;
                 double bf[KSTEPS];
 #pragma unroll
-                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * MM_LD + 4 * kk + q];
-                const double ny0 = bt[(j + 2 * q) * MM_LD + 8];
-                const double ny1 = bt[(j + 2 * q + 1) * MM_LD + 8];
+                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * Cfg::LD + 4 * kk + q];
+                const double ny0 = bt[(j + 2 * q) * Cfg::LD + Cfg::NRM];
+                const double ny1 = bt[(j + 2 * q + 1) * Cfg::LD + Cfg::NRM];
 #pragma unroll
                 for (int rg = 0; rg < MM_RG; ++rg) {
                     double c0, c1;
@@ -540,12 +551,12 @@ __global__ void __launch_bounds__(MM_THREADS, MMS_MINB)
         __syncthreads();
     }
     // column sums of the last tile
-    if (jt1 - 1 > bx) {
-        const double* cw = colw + ((it - 1) & 1) * (MM_THREADS / 32) * MM_TJ;
+    if (jt1 - 1 >= jdiag_end && tid < Cfg::TJ) {
+        const double* cw = colw + ((it - 1) & 1) * (MM_THREADS / 32) * Cfg::TJ;
         double s = cw[tid];
 #pragma unroll
-        for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * MM_TJ + tid];
-        const int64_t col = (jt1 - 1) * MM_TJ + tid;
+        for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * Cfg::TJ + tid];
+        const int64_t col = (jt1 - 1) * Cfg::TJ + tid;
         if (col < a.n1) atomicAdd(yg + col, s);
     }
     // row sums
@@ -1033,9 +1044,10 @@ cudaError_t launch_main_d(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t str
 
 template <int KSTEPS, int KC, int EPI>
 cudaError_t launch_mma(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStream_t stream) {
+    using Cfg = MmCfg<KSTEPS>;
     auto kern = matvec_mma_kernel<KSTEPS, KC, EPI>;
-    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MM_TJ * (MM_LD + KC);
-    const int64_t n_jt = a.n1pad / MM_TJ;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * Cfg::TJ * (Cfg::LD + KC);
+    const int64_t n_jt = a.n1pad / Cfg::TJ;
     const int64_t row_ctas = (a.n0 + MM_ROWS - 1) / MM_ROWS;
     if (smem > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1125,15 +1137,20 @@ cudaError_t launch_direct_sym_d(const PnMatvecLaunch& a, cudaStream_t stream) {
 
 template <int KSTEPS, int EPI>
 cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
+    using Cfg = MmCfg<KSTEPS>;
+    constexpr int TPB = MM_ROWS / Cfg::TJ;
     auto kern = matvec_mma_sym_kernel<KSTEPS, EPI>;
-    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * MM_TJ * (MM_LD + 1) +
-                        2 * sizeof(double) * (MM_THREADS / 32) * MM_TJ;
-    const int64_t n_jt = a.n1pad / MM_TJ;
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * Cfg::TJ * (Cfg::LD + 1) +
+                        2 * sizeof(double) * (MM_THREADS / 32) * Cfg::TJ;
+    const int64_t n_jt = a.n1pad / Cfg::TJ;
+    const int64_t n_blocks = (n_jt + TPB - 1) / TPB;
     const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
-    const int64_t row_ctas = (n_jt + nparts - 1) / nparts;
-    // chunks of column tiles: short enough to balance the triangle, long enough to amortise the prologue
+    const int64_t row_ctas = (n_blocks + nparts - 1) / nparts;
+    // chunks of column tiles (in units of 128 columns): short enough to balance the triangle, long
+    // enough to amortise the prologue
     int64_t tps = 256;
-    while (tps > 8 && row_ctas * ((n_jt + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    tps *= TPB;
     const int64_t chunks = (n_jt + tps - 1) / tps;
     if (chunks > 65535) return cudaErrorInvalidConfiguration;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1158,7 +1175,33 @@ cudaError_t launch_mma_sym_epi(const PnMatvecLaunch& a, cudaStream_t stream) {
     }
 }
 
+// 8 < d <= 32 (KSTEPS 4, 8): one right-hand side, ExpQuad in factorised form or RatQuad
+template <int KSTEPS>
+cudaError_t launch_mma_wide(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_mma<KSTEPS, 1, PN_EPI_EXPQUAD_FACT>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD1: return launch_mma<KSTEPS, 1, PN_EPI_RATQUAD1>(a, sm, plan, stream);
+        case PN_EPI_RATQUAD2: return launch_mma<KSTEPS, 1, PN_EPI_RATQUAD2>(a, sm, plan, stream);
+        case PN_EPI_RATQUADG: return launch_mma<KSTEPS, 1, PN_EPI_RATQUADG>(a, sm, plan, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template <int KSTEPS>
+cudaError_t launch_mma_sym_wide(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD: return launch_mma_sym<KSTEPS, PN_EPI_EXPQUAD_FACT>(a, stream);
+        case PN_EPI_RATQUAD1: return launch_mma_sym<KSTEPS, PN_EPI_RATQUAD1>(a, stream);
+        case PN_EPI_RATQUAD2: return launch_mma_sym<KSTEPS, PN_EPI_RATQUAD2>(a, stream);
+        case PN_EPI_RATQUADG: return launch_mma_sym<KSTEPS, PN_EPI_RATQUADG>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 cudaError_t launch_mma_any(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
+    if (a.d > 8) {  // the caller admits this only for kc == 1 (and ExpQuad only in factorised form)
+        if (a.kc != 1) return cudaErrorInvalidValue;
+        return a.d <= 16 ? launch_mma_wide<4>(a, sm, plan, stream) : launch_mma_wide<8>(a, sm, plan, stream);
+    }
     const bool two = a.d > 4;
     if (a.kc == 1) return two ? launch_mma_epi<2, 1>(a, sm, plan, stream) : launch_mma_epi<1, 1>(a, sm, plan, stream);
     if (a.kc == 4) return two ? launch_mma_epi<2, 4>(a, sm, plan, stream) : launch_mma_epi<1, 4>(a, sm, plan, stream);
@@ -1246,6 +1289,7 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     const bool ard = a.scale != nullptr;
     cudaError_t err;
     if (a.use_mma == 2 && a.sym) {
+        if (a.d > 8) return a.d <= 16 ? launch_mma_sym_wide<4>(a, stream) : launch_mma_sym_wide<8>(a, stream);
         return a.d > 4 ? launch_mma_sym_epi<2>(a, stream) : launch_mma_sym_epi<1>(a, stream);
     } else if (a.sym && a.use_mma == 0 && uses_main_kernel(a)) {
         return ard ? launch_direct_sym_d<true>(a, stream) : launch_direct_sym_d<false>(a, stream);

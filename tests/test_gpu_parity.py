@@ -514,12 +514,23 @@ def test_symmetric_matvec_parts_sum_to_the_product():
         total += part
     assert_matvec_close(total.cpu().numpy(), orc.matvec(specm, x, None, v), orc.abs_matvec(specm, x, None, v), 1e-12)
     opm.close()
-    # d > 8 has no symmetric kernel: the library says so and the caller shards rows instead
-    x9 = rng.normal(size=(n, 9))
-    op9 = _lib.Operator(pb.ExpQuad((9,))._kernel_params(), x9)
+    # d > 32 has no symmetric kernel: the library says so and the caller shards rows instead
+    x40 = rng.normal(size=(n, 40))
+    op40 = _lib.Operator(pb.ExpQuad((40,), lengthscales=6.0)._kernel_params(), x40)
     with pytest.raises(NotImplementedError):
-        op9.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
-    op9.close()
+        op40.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
+    op40.close()
+    # ... while 8 < d <= 32 has the wide DMMA form of the decomposition
+    x20 = rng.normal(size=(n, 20))
+    spec20 = orc.KernelSpec("expquad", (20,), 4.0)
+    op20 = _lib.Operator(make_kernel(spec20)._kernel_params(), x20)
+    total.zero_()
+    for p in range(3):
+        op20.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), p, 3)
+        torch.cuda.synchronize()
+        total += part
+    assert_matvec_close(total.cpu().numpy(), orc.matvec(spec20, x20, None, v), orc.abs_matvec(spec20, x20, None, v), 1e-12)
+    op20.close()
 
 
 def test_symmetric_matvec_can_be_switched_off(monkeypatch):
@@ -556,3 +567,33 @@ def test_use_keops_false_selects_the_conservative_device_kernels():
     L._matmul_device(v)
     assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
     L.close()
+
+
+@pytest.mark.parametrize("kind,d,n", [("expquad", 9, 2100), ("expquad", 16, 3000), ("expquad", 17, 2500), ("expquad", 32, 2304),
+                                      ("ratquad", 12, 2600), ("ratquad", 29, 2200)])
+def test_wide_dmma_matvec_8_lt_d_le_32(kind, d, n):
+    """8 < d <= 32: the norm-identity kernels with K-chunked DMMA contraction (one right-hand side),
+    symmetric and rectangular, against the oracle; several columns fall back to the row-staged kernel."""
+    rng = np.random.default_rng(d)
+    ls = 0.9 * np.sqrt(d)
+    spec = orc.KernelSpec(kind, (d,), ls, alpha=1.3)
+    k = make_kernel(spec)
+    x = rng.normal(size=(n, d))
+    x1 = rng.normal(size=(n // 2 + 3, d))
+    v = rng.normal(size=(n, 1))
+    L = k.linop(x)
+    y = L._matmul_device(v)
+    assert L._device_op().matmul_path() == "norm-identity-dmma-symmetric"
+    assert_matvec_close(y, orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
+    Y = L._matmul_device(np.concatenate([v, 2 * v], axis=1))
+    assert L._device_op().matmul_path() == "direct-differences"
+    assert np.all(np.abs(Y[:, :1] - y) <= 1e-12 * orc.abs_matvec(spec, x, None, v))
+    L.close()
+    Lr = k.linop(x, x1)
+    w = rng.normal(size=(x1.shape[0], 1))
+    yr = Lr._matmul_device(w)
+    assert Lr._device_op().matmul_path() == "norm-identity-dmma"
+    assert_matvec_close(yr, orc.matvec(spec, x, x1, w), orc.abs_matvec(spec, x, x1, w), 1e-12)
+    yt = Lr.T @ v
+    assert_matvec_close(yt, orc.matvec(spec, x1, x, v), orc.abs_matvec(spec, x1, x, v), 1e-12)
+    Lr.close()
