@@ -703,11 +703,11 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
         // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
         const char* symenv = getenv("PNCOV_MATVEC_SYM");
-        const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 8);  // DMMA identity or direct differences
+        const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 96);  // DMMA identity or direct differences
         const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : !(symenv && strcmp(symenv, "off") == 0);
         const bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;
         if (sym_nparts > 0 && !sym_ok)
-            return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 8 and n >= 2048");
+            return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 96 and n >= 2048");
         m.sym = sym_ok ? 1 : 0;
         m.sym_part = sym_part;
         m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;

@@ -912,6 +912,115 @@ __global__ void __launch_bounds__(MR_THREADS)
     }
 }
 
+// ---- symmetric variant of the row-staged kernel (x1 is x0, one right-hand side, float64) -------------
+// Same halving as matvec_sym_kernel for 8 < d <= MR_DMAX: the CTA of row block I (128 rows = two
+// column tiles) walks the column tiles J >= 2 I and adds y_J += K_IJ^T v_I for the tiles right of its
+// diagonal pair.  The eight partial column sums of a register tile are folded over the warp by a
+// butterfly (8 -> 4 -> 2 -> 1 values over lane bits 4, 3, 2, then two plain rounds: 9 shuffles +
+// 9 DADDs per 8 columns), warps meet in shared memory, one atomic per column and tile.
+template <bool ARD>
+__global__ void __launch_bounds__(MR_THREADS)
+    matvec_rows_sym_kernel(const __grid_constant__ PnMatvecLaunch a, const double* __restrict__ x_soa, int64_t ld,
+                           int tiles_per_split, int part, int nparts) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = a.d;
+    constexpr int TPB = MR_THREADS / MR_TJ;  // column tiles per row block
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    double* sc = reinterpret_cast<double*>(smem + MV_HDR_BYTES);     // [d]
+    double* xr = sc + ((d + 3) / 4) * 4;                               // [d][MR_THREADS]
+    double* xt = xr + (size_t)d * MR_THREADS;                          // [d][MR_TJ]
+    double* vt = xt + (size_t)d * MR_TJ;                               // [MR_TJ]
+    double* colw = vt + MR_TJ;                                         // [2][warps][MR_TJ]
+
+    const int64_t n_jt = a.n1pad / MR_TJ;
+    const int64_t bx = (int64_t)blockIdx.x * nparts + part;
+    if (bx * TPB >= n_jt) return;
+    const int64_t jdiag_end = (bx + 1) * TPB;
+    int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+    if (jt0 < bx * TPB) jt0 = bx * TPB;
+    if (jt0 >= jt1) return;
+
+    pn_stage_tables(tabE, tabL, tid, MR_THREADS);
+    for (int m = tid; m < d; m += MR_THREADS) sc[m] = ARD ? static_cast<const double*>(a.scale)[m] : 1.0;
+    const int64_t row = bx * MR_THREADS + tid;  // padded rows are readable (zeros)
+    for (int m = 0; m < d; ++m) xr[m * MR_THREADS + tid] = x_soa[(size_t)m * ld + row];
+    const double* vg = static_cast<const double*>(a.v);
+    double* yg = static_cast<double*>(a.y);
+    const double vrow = vg[row];  // zero in the padding
+    double acc = 0.0;
+
+    int it = 0;
+    for (int64_t jt = jt0; jt < jt1; ++jt, ++it) {
+        const int buf = it & 1;
+        const int64_t jbase = jt * MR_TJ;
+        __syncthreads();  // previous tile: xt / vt consumed, its colw slot complete
+        if (it > 0 && jt - 1 >= jdiag_end && tid < MR_TJ) {
+            const double* cwp = colw + (buf ^ 1) * (MR_THREADS / 32) * MR_TJ;
+            double s = cwp[tid];
+#pragma unroll
+            for (int w = 1; w < MR_THREADS / 32; ++w) s += cwp[w * MR_TJ + tid];
+            const int64_t col = (jt - 1) * MR_TJ + tid;
+            if (col < a.n1) atomicAdd(yg + col, s);
+        }
+        for (int idx = tid; idx < d * MR_TJ; idx += MR_THREADS) {
+            const int m = idx / MR_TJ, j = idx % MR_TJ;
+            xt[idx] = x_soa[(size_t)m * ld + jbase + j];
+        }
+        if (tid < MR_TJ) vt[tid] = vg[jbase + tid];
+        __syncthreads();
+        double* cw = colw + buf * (MR_THREADS / 32) * MR_TJ + warp * MR_TJ;
+        const bool mirror = jt >= jdiag_end;  // uniform
+        for (int jj = 0; jj < MR_TJ; jj += MR_C) {
+            double S[MR_C];
+#pragma unroll
+            for (int c = 0; c < MR_C; ++c) S[c] = 0.0;
+            for (int m = 0; m < d; ++m) {
+                const double xa = xr[m * MR_THREADS + tid];
+                double s = 1.0;
+                if constexpr (ARD) s = sc[m];
+#pragma unroll
+                for (int c = 0; c < MR_C; ++c) {
+                    double df = xa - xt[m * MR_TJ + jj + c];
+                    if constexpr (ARD) df *= s;
+                    S[c] = pn_fma(df, df, S[c]);
+                }
+            }
+            mv_epi_dispatch(S, a.epi, tabE, tabL);
+#pragma unroll
+            for (int c = 0; c < MR_C; ++c) acc = pn_fma(S[c], vt[jj + c], acc);
+            if (mirror) {
+                static_assert(MR_C == 8, "the butterfly folds exactly eight columns");
+                const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+                double t[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {  // keep columns 4 b4 + c, send the other half
+                    const double keep = (b4 ? S[4 + c] : S[c]) * vrow, send = (b4 ? S[c] : S[4 + c]) * vrow;
+                    t[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+                double u0 = (b3 ? t[2] : t[0]) + __shfl_xor_sync(0xffffffffu, b3 ? t[0] : t[2], 8);
+                double u1 = (b3 ? t[3] : t[1]) + __shfl_xor_sync(0xffffffffu, b3 ? t[1] : t[3], 8);
+                double w = (b2 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, b2 ? u0 : u1, 4);
+                w += __shfl_xor_sync(0xffffffffu, w, 2);
+                w += __shfl_xor_sync(0xffffffffu, w, 1);
+                if ((lane & 3) == 0) cw[jj + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = w;
+            }
+        }
+    }
+    __syncthreads();
+    if (jt1 - 1 >= jdiag_end && tid < MR_TJ) {  // column sums of the last tile
+        const double* cwp = colw + ((it - 1) & 1) * (MR_THREADS / 32) * MR_TJ;
+        double s = cwp[tid];
+#pragma unroll
+        for (int w = 1; w < MR_THREADS / 32; ++w) s += cwp[w * MR_TJ + tid];
+        const int64_t col = (jt1 - 1) * MR_TJ + tid;
+        if (col < a.n1) atomicAdd(yg + col, s);
+    }
+    if (row < a.n0) atomicAdd(yg + row, acc);
+}
+
 // partial[s][i] summed over s in increasing order (deterministic)
 template <typename T>
 __global__ void reduce_partials_kernel(const double* __restrict__ partial, T* __restrict__ y,
@@ -1248,6 +1357,30 @@ cudaError_t launch_rows(const PnMatvecLaunch& a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+template <bool ARD>
+cudaError_t launch_rows_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
+    constexpr int TPB = MR_THREADS / MR_TJ;
+    const int64_t n_jt = a.n1pad / MR_TJ;
+    const int64_t n_blocks = (n_jt + TPB - 1) / TPB;
+    const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
+    const int64_t row_ctas = (n_blocks + nparts - 1) / nparts;
+    int64_t tps = 256;
+    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    tps *= TPB;
+    const int64_t chunks = (n_jt + tps - 1) / tps;
+    if (chunks > 65535) return cudaErrorInvalidConfiguration;
+    const size_t smem = MV_HDR_BYTES + sizeof(double) * (((a.d + 3) / 4) * 4 + (size_t)a.d * (MR_THREADS + MR_TJ) + MR_TJ +
+                                                         2 * (MR_THREADS / 32) * MR_TJ) + 16;
+    auto kern = matvec_rows_sym_kernel<ARD>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(a.y, 0, (size_t)a.n0 * sizeof(double), stream)) != cudaSuccess) return err;
+    dim3 grid((unsigned)row_ctas, (unsigned)chunks);
+    kern<<<grid, MR_THREADS, smem, stream>>>(a, static_cast<const double*>(a.x0_soa), a.ld0, (int)tps, a.sym_part, nparts);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 static bool uses_main_kernel(const PnMatvecLaunch& a) { return !a.in_f32 && a.d <= 8; }
@@ -1259,7 +1392,7 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
         a.jsplit = 1;
         return cudaSuccess;
     }
-    if (a.sym && (a.use_mma == 2 || (a.use_mma == 0 && !a.in_f32 && a.d <= 8))) {
+    if (a.sym && (a.use_mma == 2 || (a.use_mma == 0 && !a.in_f32 && a.d <= MR_DMAX))) {
         a.jsplit = 1;  // no partial buffers: the symmetric kernels accumulate with atomics
         return cudaSuccess;
     }
@@ -1293,6 +1426,8 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
         return a.d > 4 ? launch_mma_sym_epi<2>(a, stream) : launch_mma_sym_epi<1>(a, stream);
     } else if (a.sym && a.use_mma == 0 && uses_main_kernel(a)) {
         return ard ? launch_direct_sym_d<true>(a, stream) : launch_direct_sym_d<false>(a, stream);
+    } else if (a.sym && a.use_mma == 0 && !a.in_f32 && uses_rows_kernel(a)) {
+        return ard ? launch_rows_sym<true>(a, stream) : launch_rows_sym<false>(a, stream);
     } else if (a.use_mma == 2) {
         err = launch_mma_any(a, sm_count, false, stream);
     } else if (a.use_mma == 1) {

@@ -82,7 +82,7 @@ class ShardedCovarianceOperator:
         params = covfunc._kernel_params()
         if symmetric and is_symmetric and self.world > 1 and dt == np.float64:
             if local_factory is None:
-                if params.matrix_free and params.d <= 32 and self.shape[0] >= 2048:
+                if params.matrix_free and params.d <= 96 and self.shape[0] >= 2048:
                     self.local_sym = _lib.Operator(params, cols, None, device=device)
             else:
                 self.local_sym = local_factory(params, cols, None)

@@ -459,6 +459,7 @@ def test_wide_right_hand_sides(k_cols):
     ("expquad", 8, 5000, 0, 0.9), ("expquad", 3, 2177, 0, 0.9), ("ratquad", 4, 4096, 0, 0.9), ("ratquad", 8, 6001, 0, 0.9),
     ("matern", 8, 5000, 2.5, 0.9), ("matern", 3, 2305, 0.5, 0.9), ("matern", 5, 4096, 3.5, [0.5, 0.7, 0.9, 1.1, 1.3]),
     ("expquad", 6, 3000, 0, 0.01),  # wide cloud in lengthscale units: identity inadmissible -> direct differences
+    ("matern", 12, 2200, 1.5, 3.0), ("matern", 40, 2100, 2.5, 6.0),  # 8 < d <= 96: row-staged symmetric kernel
 ])
 def test_symmetric_matvec_matches_oracle(kind, d, n, nu, ls):
     rng = np.random.default_rng(n)
@@ -514,12 +515,12 @@ def test_symmetric_matvec_parts_sum_to_the_product():
         total += part
     assert_matvec_close(total.cpu().numpy(), orc.matvec(specm, x, None, v), orc.abs_matvec(specm, x, None, v), 1e-12)
     opm.close()
-    # d > 32 has no symmetric kernel: the library says so and the caller shards rows instead
-    x40 = rng.normal(size=(n, 40))
-    op40 = _lib.Operator(pb.ExpQuad((40,), lengthscales=6.0)._kernel_params(), x40)
+    # d > 96 has no symmetric kernel: the library says so and the caller shards rows instead
+    x100 = rng.normal(size=(n, 100))
+    op100 = _lib.Operator(pb.ExpQuad((100,), lengthscales=10.0)._kernel_params(), x100)
     with pytest.raises(NotImplementedError):
-        op40.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
-    op40.close()
+        op100.matmul_sym_part_device(vd.data_ptr(), part.data_ptr(), 0, 2)
+    op100.close()
     # ... while 8 < d <= 32 has the wide DMMA form of the decomposition
     x20 = rng.normal(size=(n, 20))
     spec20 = orc.KernelSpec("expquad", (20,), 4.0)
