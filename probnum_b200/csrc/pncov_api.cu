@@ -421,7 +421,7 @@ struct pncov_handle {
     bool used_foreign_stream = false;  // a *_device entry point ran on a caller-owned stream
     // norm-identity / DMMA matvec operands (built on the first product; see mma_prepare)
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
-    int mma_dpad = 8;            // coordinates per operand row (d padded to 8, 16 or 32)
+    int mma_dpad = 8;            // coordinates per operand row (d padded to 8, 16, 32 or 64)
     bool last_sym = false;       // the last product ran the symmetric-halving kernel
     int last_use_mma = -1;       // kernel family of the last product (-1: none yet)
     // per-handle kernel selection (pncov_set_option); -1 = default (environment / automatic)
@@ -572,7 +572,7 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     if (h->mma_state != 0) return 0;
     h->mma_state = -1;
     const KernelDesc& k = h->k;
-    if (k.dtype != PNCOV_F64 || k.d > 32 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
+    if (k.dtype != PNCOV_F64 || k.d > 64 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
     if (h->p0.n == 0 || h->p1.n == 0) return 0;
     {
         const char* form = getenv("PNCOV_MATVEC_IDENT");  // "off": always direct differences
@@ -580,25 +580,25 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     }
     const int d = k.d;
     double* sums = nullptr;
-    const int dpad = d <= 8 ? 8 : (d <= 16 ? 16 : 32);
+    const int dpad = d <= 8 ? 8 : (d <= 16 ? 16 : (d <= 32 ? 32 : 64));
     h->mma_dpad = dpad;
-    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&sums), 64 * sizeof(double) + sizeof(unsigned long long), stream));
-    unsigned long long* max_norm = reinterpret_cast<unsigned long long*>(sums + 64);
+    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&sums), 128 * sizeof(double) + sizeof(unsigned long long), stream));
+    unsigned long long* max_norm = reinterpret_cast<unsigned long long*>(sums + 128);
     auto fail_free = [&](int rc) {
         pn_dev_free(sums, stream);
         return rc;
     };
     coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p0.aos, h->p0.n, d, sums);
-    coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p1.aos, h->p1.n, d, sums + 32);
+    coord_sums_kernel<<<1, 1024, 0, stream>>>((const double*)h->p1.aos, h->p1.n, d, sums + 64);
     g_pn_launches += 2;
-    double host_sums[64];
+    double host_sums[128];
     cudaError_t e = cudaMemcpyAsync(host_sums, sums, sizeof(host_sums), cudaMemcpyDeviceToHost, stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
-    double centre[32] = {0};
+    double centre[64] = {0};
     const double ntot = (double)h->p0.n + (h->symmetric ? 0.0 : (double)h->p1.n);
     for (int m = 0; m < d; ++m)
-        centre[m] = (host_sums[m] + (h->symmetric ? 0.0 : host_sums[32 + m])) / ntot;
+        centre[m] = (host_sums[m] + (h->symmetric ? 0.0 : host_sums[64 + m])) / ntot;
     e = cudaMemcpyAsync(sums, centre, sizeof(centre), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(max_norm, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return fail_free(fail_cuda(e, "mma_prepare"));
@@ -681,7 +681,7 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         int prc = mma_prepare(h, stream);
         if (prc) return prc;
     }
-    const bool wide_ok = h->k.d <= 8 || kc_max == 1;  // the 8 < d <= 32 kernels take one right-hand side
+    const bool wide_ok = h->k.d <= 8 || kc_max == 1;  // the 8 < d <= 64 kernels take one right-hand side
     if (h->mma_state == 1 && h->opt_identity != 0 && wide_ok) {
         // norm identity: dot products on DMMA by default (fastest measured), DFMA form opt-in
         const char* form = getenv("PNCOV_MATVEC_IDENT");

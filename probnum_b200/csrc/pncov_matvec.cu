@@ -258,7 +258,7 @@ struct MmCfg {
     static constexpr int LD = DPAD + 4;
     static constexpr int NRM = DPAD;                      // index of |xt|^2 (the factor follows it)
     static constexpr int TJ = KSTEPS <= 2 ? 128 : (KSTEPS <= 4 ? 64 : 32);  // columns per pipeline stage
-    static constexpr int MINB = KSTEPS <= 2 ? 4 : 2;      // CTAs per SM the symmetric kernel is compiled for
+    static constexpr int MINB = KSTEPS <= 2 ? 4 : (KSTEPS <= 8 ? 2 : 1);  // CTAs per SM the symmetric kernel is compiled for
 };
 
 __device__ __forceinline__ void pn_dmma884(double& c0, double& c1, double a, double b) {
@@ -1284,7 +1284,7 @@ cudaError_t launch_mma_sym_epi(const PnMatvecLaunch& a, cudaStream_t stream) {
     }
 }
 
-// 8 < d <= 32 (KSTEPS 4, 8): one right-hand side, ExpQuad in factorised form or RatQuad
+// 8 < d <= 64 (KSTEPS 4, 8, 16): one right-hand side, ExpQuad in factorised form or RatQuad
 template <int KSTEPS>
 cudaError_t launch_mma_wide(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     switch (a.epi.epi) {
@@ -1309,7 +1309,8 @@ cudaError_t launch_mma_sym_wide(const PnMatvecLaunch& a, cudaStream_t stream) {
 cudaError_t launch_mma_any(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t stream) {
     if (a.d > 8) {  // the caller admits this only for kc == 1 (and ExpQuad only in factorised form)
         if (a.kc != 1) return cudaErrorInvalidValue;
-        return a.d <= 16 ? launch_mma_wide<4>(a, sm, plan, stream) : launch_mma_wide<8>(a, sm, plan, stream);
+        if (a.d <= 16) return launch_mma_wide<4>(a, sm, plan, stream);
+        return a.d <= 32 ? launch_mma_wide<8>(a, sm, plan, stream) : launch_mma_wide<16>(a, sm, plan, stream);
     }
     const bool two = a.d > 4;
     if (a.kc == 1) return two ? launch_mma_epi<2, 1>(a, sm, plan, stream) : launch_mma_epi<1, 1>(a, sm, plan, stream);
@@ -1422,6 +1423,7 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     const bool ard = a.scale != nullptr;
     cudaError_t err;
     if (a.use_mma == 2 && a.sym) {
+        if (a.d > 32) return launch_mma_sym_wide<16>(a, stream);
         if (a.d > 8) return a.d <= 16 ? launch_mma_sym_wide<4>(a, stream) : launch_mma_sym_wide<8>(a, stream);
         return a.d > 4 ? launch_mma_sym_epi<2>(a, stream) : launch_mma_sym_epi<1>(a, stream);
     } else if (a.sym && a.use_mma == 0 && uses_main_kernel(a)) {

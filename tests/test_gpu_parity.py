@@ -571,9 +571,10 @@ def test_use_keops_false_selects_the_conservative_device_kernels():
 
 
 @pytest.mark.parametrize("kind,d,n", [("expquad", 9, 2100), ("expquad", 16, 3000), ("expquad", 17, 2500), ("expquad", 32, 2304),
-                                      ("ratquad", 12, 2600), ("ratquad", 29, 2200)])
-def test_wide_dmma_matvec_8_lt_d_le_32(kind, d, n):
-    """8 < d <= 32: the norm-identity kernels with K-chunked DMMA contraction (one right-hand side),
+                                      ("ratquad", 12, 2600), ("ratquad", 29, 2200), ("expquad", 33, 2100), ("expquad", 64, 2300),
+                                      ("ratquad", 50, 2200)])
+def test_wide_dmma_matvec_8_lt_d_le_64(kind, d, n):
+    """8 < d <= 64: the norm-identity kernels with K-chunked DMMA contraction (one right-hand side),
     symmetric and rectangular, against the oracle; several columns fall back to the row-staged kernel."""
     rng = np.random.default_rng(d)
     ls = 0.9 * np.sqrt(d)
