@@ -405,6 +405,8 @@ struct pncov_handle {
     bool symmetric = false;  // x1 was NULL: p1 aliases p0
     void* scale_dev = nullptr;
     void* pm_dev = nullptr;  // ProductMatern per-dimension parameters
+    void* dot_ops[2] = {nullptr, nullptr};  // Linear / Polynomial, d > 16: zero-padded row-major operands (x0, x1)
+    int dot_dpad = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -540,6 +542,12 @@ cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0,
     if (h->k.extra_mode < 0) return pn_launch_gram(gram_launch(h, transpose, row0, rows, out, ld), stream);
     const Points& R = transpose ? h->p1 : h->p0;
     const Points& C = transpose ? h->p0 : h->p1;
+    if (h->dot_dpad > 0) {  // Linear / Polynomial with wide inputs: FP64 GEMM on DMMA
+        const double* A = static_cast<const double*>(h->dot_ops[transpose ? 1 : 0]) + (size_t)row0 * h->dot_dpad;
+        const double* B = static_cast<const double*>(h->dot_ops[transpose ? 0 : 1]);
+        return pn_launch_gram_dot_mma(A, B, h->dot_dpad, rows, C.n, static_cast<double*>(out), ld, h->k.constant,
+                                      h->k.exponent, stream);
+    }
     PnExtraLaunch g{};
     g.mode = h->k.extra_mode;
     g.x0_soa = static_cast<const char*>(R.soa) + (size_t)row0 * 8;
@@ -837,6 +845,20 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
         h->p1 = h->p0;
         h->symmetric = true;
     }
+    if (h->k.extra_mode == 0 && h->k.d > 16) {
+        // inner products as a GEMM: K-contiguous operands padded to a multiple of 16 coordinates
+        h->dot_dpad = ((h->k.d + 15) / 16) * 16;
+        const int nsets = h->symmetric ? 1 : 2;
+        for (int sidx = 0; sidx < nsets; ++sidx) {
+            const Points& P = sidx == 0 ? h->p0 : h->p1;
+            if ((e = pn_dev_alloc(&h->dot_ops[sidx], (size_t)P.npad * h->dot_dpad * 8, h->stream)) != cudaSuccess)
+                return bail(fail_cuda(e, "operand allocation"));
+            if ((e = pn_launch_pad_rows((const double*)P.aos, P.n, h->k.d, P.npad, h->dot_dpad, (double*)h->dot_ops[sidx],
+                                        h->stream)) != cudaSuccess)
+                return bail(fail_cuda(e, "pad_rows"));
+        }
+        if (h->symmetric) h->dot_ops[1] = h->dot_ops[0];
+    }
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(fail_cuda(e, "upload"));
     *out = h;
     return 0;
@@ -855,6 +877,8 @@ PNCOV_API int pncov_destroy(pncov_handle* h) {
     free_points(h->p0, fs);
     pn_dev_free(h->scale_dev, fs);
     pn_dev_free(h->pm_dev, fs);
+    pn_dev_free(h->dot_ops[0], fs);
+    if (!h->symmetric) pn_dev_free(h->dot_ops[1], fs);
     pn_dev_free(h->vpack, fs);
     pn_dev_free(h->ypack, fs);
     pn_dev_free(h->partial, fs);

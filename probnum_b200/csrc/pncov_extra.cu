@@ -239,6 +239,135 @@ __global__ void __launch_bounds__(X_THREADS)
     }
 }
 
+// ---- Linear / Polynomial for d > X_DC: the inner products as an FP64 GEMM on DMMA ------------------
+// K = X0 X1^T (+ c, ^q) is C = A B^T with K-contiguous operands, the "row.col" form of
+// mma.sync.m8n8k4.f64.  Operands are zero-padded row-major copies (npad x dpad, dpad a multiple of
+// XG_CK) built once per handle.  A CTA of 4 warps owns a 128 x 64 tile (a warp 32 x 64, 64
+// accumulators per lane), operands stream through a two-stage cp.async pipeline in K-chunks of 16
+// with a row stride of 20 doubles (conflict-free fragment loads) -- the GEMM of csrc/pncov_chol.cu
+// with a different epilogue.  C_ij and C_ji accumulate the same products in the same order, so a
+// symmetric Gram stays symmetric bit for bit.
+constexpr int XG_BM = 128, XG_BN = 64, XG_CK = 16, XG_LD = XG_CK + 4, XG_THREADS = 128;
+
+__device__ __forceinline__ void xg_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void xg_cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pn_smem_u32(smem)), "l"(gmem) : "memory");
+}
+
+struct XgLaunch {
+    const double* A;  // (rows padded to 128, dpad) row-major
+    const double* B;  // (cols padded to 128, dpad)
+    int dpad;
+    int64_t n0, n1;
+    double* out;
+    int64_t ldo;
+    double constant;
+    int exponent;
+    int vec_ok;
+};
+
+__global__ void __launch_bounds__(XG_THREADS, 3) gram_dot_mma_kernel(const __grid_constant__ XgLaunch p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* As = reinterpret_cast<double*>(smem);  // [2][XG_BM * XG_LD]
+    double* Bs = As + 2 * XG_BM * XG_LD;           // [2][XG_BN * XG_LD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const double* At = p.A + (int64_t)blockIdx.y * XG_BM * p.dpad;
+    const double* Bt = p.B + (int64_t)blockIdx.x * XG_BN * p.dpad;
+
+    auto load_chunk = [&](int kc, int buf) {
+        double* as = As + buf * XG_BM * XG_LD;
+        double* bs = Bs + buf * XG_BN * XG_LD;
+        constexpr int PIECES = XG_CK / 2;
+#pragma unroll
+        for (int i = 0; i < XG_BM * PIECES / XG_THREADS; ++i) {
+            const int idx = tid + i * XG_THREADS;
+            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
+            xg_cp_async16(as + row * XG_LD + c2, At + (int64_t)row * p.dpad + kc * XG_CK + c2);
+        }
+#pragma unroll
+        for (int i = 0; i < XG_BN * PIECES / XG_THREADS; ++i) {
+            const int idx = tid + i * XG_THREADS;
+            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
+            xg_cp_async16(bs + row * XG_LD + c2, Bt + (int64_t)row * p.dpad + kc * XG_CK + c2);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    const int nchunk = p.dpad / XG_CK;
+    load_chunk(0, 0);
+    for (int kc = 0; kc < nchunk; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nchunk) {
+            load_chunk(kc + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* as = As + buf * XG_BM * XG_LD + (warp * 32 + g) * XG_LD + q;
+        const double* bs = Bs + buf * XG_BN * XG_LD + g * XG_LD + q;
+#pragma unroll
+        for (int k4 = 0; k4 < XG_CK / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = as[r * 8 * XG_LD + k4 * 4];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) b[c] = bs[c * 8 * XG_LD + k4 * 4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) xg_dmma(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = (int64_t)blockIdx.y * XG_BM + warp * 32 + r * 8 + g;
+        if (row >= p.n0) continue;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int64_t col = (int64_t)blockIdx.x * XG_BN + c * 8 + 2 * q;
+            double k0 = acc[r][c][0] + p.constant, k1 = acc[r][c][1] + p.constant;
+            if (p.exponent != 1) {
+                k0 = x_powi(k0, p.exponent);
+                k1 = x_powi(k1, p.exponent);
+            }
+            double* dst = p.out + row * p.ldo + col;
+            if (col + 1 < p.n1) {
+                if (p.vec_ok) pn_store_cs2(dst, k0, k1);
+                else {
+                    pn_store_cs1(dst, k0);
+                    pn_store_cs1(dst + 1, k1);
+                }
+            } else if (col < p.n1) {
+                pn_store_cs1(dst, k0);
+            }
+        }
+    }
+}
+
+// (n, d) row-major -> (npad, dpad) row-major, zero padded
+__global__ void pad_rows_kernel(const double* __restrict__ aos, int64_t n, int d, int64_t npad, int dpad,
+                                double* __restrict__ outp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= npad * dpad) return;
+    const int64_t i = idx / dpad;
+    const int m = (int)(idx % dpad);
+    outp[idx] = (i < n && m < d) ? aos[i * d + m] : 0.0;
+}
+
 // out[b] = k(x0[b], x1[b]); one thread per pair
 template <int MODE>
 __global__ void pairs_extra_kernel(const __grid_constant__ PnExtraLaunch g) {
@@ -362,6 +491,39 @@ cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op,
         combine_kernel<1, true><<<(unsigned)blocks, 256, 0, stream>>>(dst, src, n2, n, alpha, beta);
     else
         return cudaErrorInvalidValue;
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t pn_launch_pad_rows(const double* aos, int64_t n, int d, int64_t npad, int dpad, double* outp, cudaStream_t stream) {
+    const int64_t total = npad * dpad;
+    pad_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(aos, n, d, npad, dpad, outp);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+// K = A B^T + c (^q) with A = rows [row0, row0 + n0) of the padded row operand, B = the padded column operand
+cudaError_t pn_launch_gram_dot_mma(const double* A, const double* B, int dpad, int64_t n0, int64_t n1, double* out,
+                                   int64_t ldo, double constant, int exponent, cudaStream_t stream) {
+    if (n0 <= 0 || n1 <= 0) return cudaSuccess;
+    XgLaunch p{};
+    p.A = A;
+    p.B = B;
+    p.dpad = dpad;
+    p.n0 = n0;
+    p.n1 = n1;
+    p.out = out;
+    p.ldo = ldo;
+    p.constant = constant;
+    p.exponent = exponent;
+    p.vec_ok = ((ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0) ? 1 : 0;
+    const size_t smem = sizeof(double) * 2 * (XG_BM + XG_BN) * XG_LD;
+    cudaError_t err = cudaFuncSetAttribute(gram_dot_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    const int64_t gx = (n1 + XG_BN - 1) / XG_BN, gy = (n0 + XG_BM - 1) / XG_BM;
+    if (gy > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)gx, (unsigned)gy);
+    gram_dot_mma_kernel<<<grid, XG_THREADS, smem, stream>>>(p);
     ++g_pn_launches;
     return cudaGetLastError();
 }

@@ -86,6 +86,10 @@ struct PnExtraLaunch {
     int vec_ok;          // filled by the launcher
 };
 cudaError_t pn_launch_gram_extra(const PnExtraLaunch& g, cudaStream_t stream);
+// Linear / Polynomial for wide inputs: zero-padded row-major operands and the DMMA GEMM on them
+cudaError_t pn_launch_pad_rows(const double* aos, int64_t n, int d, int64_t npad, int dpad, double* outp, cudaStream_t stream);
+cudaError_t pn_launch_gram_dot_mma(const double* A, const double* B, int dpad, int64_t n0, int64_t n1, double* out,
+                                   int64_t ldo, double constant, int exponent, cudaStream_t stream);
 cudaError_t pn_launch_pairs_extra(const PnExtraLaunch& g, cudaStream_t stream);
 cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op, double alpha, double beta,
                               cudaStream_t stream);

@@ -179,3 +179,22 @@ def test_edge_shapes_of_the_dense_only_families():
                                rtol=1e-12, atol=1e-12)
     # arithmetic with an empty operand set keeps shapes and dtypes
     assert (2.0 * pb.ExpQuad((3,)) + pb.Linear((3,))).matrix(np.empty((0, 3))).shape == (0, 0)
+
+
+def test_linear_gram_on_dmma_is_symmetric_and_matches_the_oracle():
+    """d > 16: the inner products run as an FP64 GEMM on DMMA (gram_dot_mma_kernel); C_ij and C_ji
+    accumulate the same products in the same order, so the symmetric Gram is symmetric bit for bit."""
+    rng = np.random.default_rng(14)
+    for d, n in ((17, 700), (40, 1300), (100, 513)):
+        x = rng.normal(size=(n, d))
+        y = rng.normal(size=(n // 3 + 5, d))
+        for k, spec in ((pb.Linear((d,), constant=0.25), dict(kind="linear", input_shape=[d], constant=0.25)),
+                        (pb.Polynomial((d,), constant=1.0, exponent=2), dict(kind="polynomial", input_shape=[d], constant=1.0, exponent=2))):
+            K = k.matrix(x)
+            np.testing.assert_array_equal(K, K.T)
+            scale = np.abs(x) @ np.abs(x).T + 1.0  # inner products cancel: compare on the scale of sum |x_i y_i|
+            ref = xo.gram(spec, x)
+            tol = 1e-12 * (scale if spec["kind"] == "linear" else 2 * np.abs(ref) ** 0.5 * scale + scale ** 2 * 1e-3)
+            assert np.all(np.abs(K - ref) <= tol + 1e-12)
+            Kc = k.matrix(x, y)
+            np.testing.assert_allclose(Kc, xo.gram(spec, x, y), rtol=1e-11, atol=1e-11)
