@@ -201,6 +201,18 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
  *                           handle: it is evaluated straight into the factorisation buffer and never
  *                           visits the host ("keep gram device-resident")
  *   pncov_chol_solve        x = (L L^T)^-1 b for b, x: (n, nrhs) row-major HOST arrays
+ *   pncov_chol_solve_gram    the prediction path of
+ *                           BQStandardBeliefUpdate.predict_integrand
+ *                           (quad/solvers/belief_updates/_standard_update.py:131-151) and
+ *                           IntegralVarianceReduction.__call__
+ *                           (quad/solvers/acquisition_functions/_integral_variance_reduction.py:60-75):
+ *                           with G = K(nodes, x), the (n, m) Gram matrix of operator h (x0 = the n
+ *                           factorised nodes, x1 = the m prediction points) and W = (L L^T)^-1 G,
+ *                             quad[j]           = sum_i W[i,j] G[i,j]             (np.sum(weights * kXx, axis=0))
+ *                             dots[t * ldd + j] = sum_i vecs[t * ldv + i] W[i,j]  (weights.T @ fun_evals,
+ *                                                                                 np.dot(kernel_means, weights))
+ *                           for nvec <= 4 host vectors of length n.  G and W (n x m each) never leave
+ *                           the device; *ms (may be NULL) = device time of the whole pass.
  *   pncov_chol_get_factor   lower-triangular factor to a host array (the strict upper triangle of
  *                           the output is unspecified, as with scipy.linalg.cho_factor)
  *   pncov_chol_last_factor_ms   device time of the last factorisation (CUDA events)
@@ -211,6 +223,8 @@ PNCOV_API int pncov_chol_destroy(pncov_chol* c);
 PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, double jitter, int a_on_device, int* info);
 PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitter, int* info);
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx);
+PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec, const double* vecs, int64_t ldv,
+                                    double* dots, int64_t ldd, double* quad, float* ms);
 PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld);
 PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms);
 

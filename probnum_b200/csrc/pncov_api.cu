@@ -1291,6 +1291,70 @@ PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int
     return 0;
 }
 
+PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec, const double* vecs, int64_t ldv,
+                                    double* dots, int64_t ldd, double* quad, float* ms) {
+    if (!c || !h || !quad) return fail(PNCOV_EINVAL, "NULL argument");
+    if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");
+    if (h->device != c->device) return fail(PNCOV_EINVAL, "operator and Cholesky handle live on different devices");
+    if (h->p0.n != c->n) return fail(PNCOV_EINVAL, "the operator's first point set is not the factorised one (n0 != n)");
+    if (h->k.gram_elem() != 8) return fail(PNCOV_EINVAL, "float64 Gram matrices only");
+    if (nvec < 0 || nvec > 4) return fail(PNCOV_EINVAL, "at most 4 vectors");
+    if (nvec > 0 && (!vecs || !dots || ldv < c->n)) return fail(PNCOV_EINVAL, "bad vector arguments");
+    const int64_t m = h->p1.n, n = c->n, npad = c->npad;
+    if (nvec > 0 && ldd < m) return fail(PNCOV_EINVAL, "ldd smaller than the number of prediction points");
+    if (ms) *ms = 0.f;
+    if (m == 0) return 0;
+    DeviceGuard guard(c->device);
+    // row chunks of the transposed right-hand sides: two (chunk, npad) buffers of at most 256 MiB each
+    int64_t chunk = std::max<int64_t>(128, ((int64_t)(256ll << 20) / (npad * 8)) / 128 * 128);
+    chunk = std::min<int64_t>(chunk, (m + 127) / 128 * 128);
+    void *Z = nullptr, *Y = nullptr, *vd = nullptr, *qd = nullptr, *dd = nullptr;
+    cudaStream_t s = c->stream;
+    auto release = [&]() {
+        pn_dev_free(Z, s);
+        pn_dev_free(Y, s);
+        pn_dev_free(vd, s);
+        pn_dev_free(qd, s);
+        pn_dev_free(dd, s);
+    };
+    auto run = [&]() -> cudaError_t {
+        cudaError_t e;
+        if ((e = pn_dev_alloc(&Z, (size_t)chunk * npad * 8, s)) != cudaSuccess) return e;
+        if ((e = pn_dev_alloc(&Y, (size_t)chunk * npad * 8, s)) != cudaSuccess) return e;
+        if ((e = pn_dev_alloc(&qd, (size_t)m * 8, s)) != cudaSuccess) return e;
+        if (nvec > 0) {
+            if ((e = pn_dev_alloc(&vd, (size_t)nvec * npad * 8, s)) != cudaSuccess) return e;
+            if ((e = pn_dev_alloc(&dd, (size_t)nvec * m * 8, s)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy2DAsync(vd, (size_t)npad * 8, vecs, (size_t)ldv * 8, (size_t)n * 8, (size_t)nvec,
+                                       cudaMemcpyHostToDevice, s)) != cudaSuccess)
+                return e;
+        }
+        if ((e = cudaEventRecord(c->ev0, s)) != cudaSuccess) return e;
+        for (int64_t r0 = 0; r0 < m; r0 += chunk) {
+            const int64_t mc = std::min<int64_t>(chunk, m - r0), mcpad = (mc + 127) / 128 * 128;
+            // padded columns must be exact zeros (they meet the identity block of the padded factor)
+            if (npad != n && (e = cudaMemsetAsync(Z, 0, (size_t)mcpad * npad * 8, s)) != cudaSuccess) return e;
+            if ((e = launch_gram_any(h, true, r0, mc, Z, npad, s)) != cudaSuccess) return e;  // rows: prediction points
+            if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, s)) != cudaSuccess) return e;
+            if ((e = launch_gram_any(h, true, r0, mc, Y, npad, s)) != cudaSuccess) return e;  // the Gram block again
+            if ((e = pn_chol_rowdots(static_cast<double*>(Z), static_cast<double*>(Y), npad, n, mc, static_cast<double*>(vd),
+                                     (int)nvec, static_cast<double*>(qd) + r0, static_cast<double*>(dd) + r0, m, s)) != cudaSuccess)
+                return e;
+        }
+        if ((e = cudaEventRecord(c->ev1, s)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(quad, qd, (size_t)m * 8, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if (nvec > 0 && (e = cudaMemcpy2DAsync(dots, (size_t)ldd * 8, dd, (size_t)m * 8, (size_t)m * 8, (size_t)nvec,
+                                               cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+            return e;
+        return cudaStreamSynchronize(s);
+    };
+    const cudaError_t e = run();
+    release();
+    if (e != cudaSuccess) return fail_cuda(e, "pncov_chol_solve_gram");
+    if (ms) PN_CUDA(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return 0;
+}
+
 PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld) {
     if (!c || !l) return fail(PNCOV_EINVAL, "NULL argument");
     if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");

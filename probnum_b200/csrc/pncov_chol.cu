@@ -10,8 +10,8 @@
 //   for every block column k
 //     chol_diag_kernel   one CTA: unblocked Cholesky of the 128 x 128 diagonal block in shared
 //                        memory (one barrier per column) and the explicit inverse of its factor
-//     chol_gemm_kernel   mode 0 ("TRSM as GEMM"): L[i,k] = A[i,k] inv(L_kk)^T for all i > k,
-//                        also copied into a contiguous panel
+//     chol_gemm_kernel   mode 0 ("TRSM as GEMM"): L[i,k] = A[i,k] inv(L_kk)^T for all i > k, into a
+//                        contiguous panel that is then copied over A[i,k]
 //                        mode 1: A[i,j] -= L[i,k] L[j,k]^T for all i >= j > k  (n^3/3 of the flops)
 // Both GEMM modes are C = A B^T with K-contiguous operands, i.e. exactly the "row.col" form of
 // mma.sync.m8n8k4.f64 (DMMA, the only FP64 tensor path of sm_100a): a CTA of 4 warps owns a
@@ -51,7 +51,7 @@ struct ChGemm {
     int64_t lda;
     const double* B;  // mode 0: inverse of the diagonal factor (128 x 128); mode 1: contiguous panel
     int64_t ldb;
-    double* C;        // mode 0: = A (in place); mode 1: first trailing tile
+    double* C;        // mode 0: unused (the panel is copied over A afterwards); mode 1: first trailing tile
     int64_t ldc;
     double* panel;    // mode 0: contiguous copy of the new block column (ld = 128)
     int mode;
@@ -145,9 +145,10 @@ __global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_c
             const int col = c * 8 + 2 * q;
             double2* dst = reinterpret_cast<double2*>(Ct + (int64_t)row * p.ldc + col);
             if (p.mode == 0) {
-                const double2 v = make_double2(acc[r][c][0], acc[r][c][1]);
-                *dst = v;
-                *reinterpret_cast<double2*>(p.panel + (bi * CB + row) * CB + h * CTN + col) = v;
+                // panel only: the two column halves of a row block are different CTAs and each reads
+                // all 128 columns of A, so A's own storage is filled by a copy after the kernel
+                *reinterpret_cast<double2*>(p.panel + (bi * CB + row) * CB + h * CTN + col) =
+                    make_double2(acc[r][c][0], acc[r][c][1]);
             } else {
                 double2 v = *dst;
                 v.x -= acc[r][c][0];
@@ -471,6 +472,158 @@ __global__ void __launch_bounds__(CB) chol_bwd_update_kernel(const double* __res
         if (r < nrhs) y[col * nrhs + r] -= s[r];
 }
 
+// ---- solves with many right-hand sides ------------------------------------------
+// The prediction path solves (L L^T) W = K(nodes, x) for hundreds to thousands of columns.  The
+// right-hand sides are kept TRANSPOSED, Z = K(x, nodes) (m x npad row-major, one prediction point per
+// row), so that every step of the blocked substitution is a product with K-contiguous left operand:
+//   forward  (k = 0 .. T-1):  Y_k = Z_k inv(L_kk)^T          ;  Z_i -= Y_k L_ik^T  for all i > k
+//   backward (k = T-1 .. 0):  X_k = Y_k inv(L_kk)            ;  Y_j -= X_k L_kj    for all j < k
+// The forward products have the second operand K-contiguous ("row.col", as the factorisation), the
+// backward ones N-contiguous; the kernel stages that operand as [k][n] with a row stride of 72
+// doubles (= 8 mod 16: conflict-free fragment loads).  Solved blocks are written to the OTHER of two
+// buffers (forward Z -> Y, backward Y -> Z): no CTA ever reads a location another CTA writes.
+constexpr int WLDN = CTN + 8;
+
+struct ChWide {
+    const double* A;  // (rows, 128) K-contiguous, leading dimension lda
+    int64_t lda;
+    const double* B;  // BKN = false: (cols, 128) K-contiguous; BKN = true: (128, cols) N-contiguous
+    int64_t ldb;
+    double* C;        // (rows, cols), leading dimension ldc
+    int64_t ldc;
+    int subtract;     // 0: C = A op(B), 1: C -= A op(B)
+};
+
+template <bool BKN>
+__global__ void __launch_bounds__(CG_THREADS, 3) chol_wide_gemm_kernel(const __grid_constant__ ChWide p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* As = reinterpret_cast<double*>(smem);  // [2][CB * CLD]
+    double* Bs = As + 2 * CB * CLD;                // [2][CTN * CLD] or [2][CK * WLDN]
+    constexpr int BSTAGE = BKN ? CK * WLDN : CTN * CLD;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const double* At = p.A + (int64_t)blockIdx.y * CB * p.lda;
+    const double* Bt = BKN ? p.B + (int64_t)blockIdx.x * CTN : p.B + (int64_t)blockIdx.x * CTN * p.ldb;
+    double* Ct = p.C + (int64_t)blockIdx.y * CB * p.ldc + (int64_t)blockIdx.x * CTN;
+
+    auto load_chunk = [&](int kc, int buf) {
+        double* as = As + buf * CB * CLD;
+        double* bs = Bs + buf * BSTAGE;
+        constexpr int PIECES = CK / 2;
+#pragma unroll
+        for (int i = 0; i < CB * PIECES / CG_THREADS; ++i) {
+            const int idx = tid + i * CG_THREADS;
+            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
+            ch_cp_async16(as + row * CLD + c2, At + (int64_t)row * p.lda + kc * CK + c2);
+        }
+        if (BKN) {
+            constexpr int NP = CTN / 2;  // 16-byte pieces per k row
+#pragma unroll
+            for (int i = 0; i < CK * NP / CG_THREADS; ++i) {
+                const int idx = tid + i * CG_THREADS;
+                const int kr = idx / NP, c2 = (idx % NP) * 2;
+                ch_cp_async16(bs + kr * WLDN + c2, Bt + (int64_t)(kc * CK + kr) * p.ldb + c2);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CTN * PIECES / CG_THREADS; ++i) {
+                const int idx = tid + i * CG_THREADS;
+                const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
+                ch_cp_async16(bs + row * CLD + c2, Bt + (int64_t)row * p.ldb + kc * CK + c2);
+            }
+        }
+        ch_cp_commit();
+    };
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+    load_chunk(0, 0);
+    constexpr int NCHUNK = CB / CK;
+    for (int kc = 0; kc < NCHUNK; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < NCHUNK) {
+            load_chunk(kc + 1, buf ^ 1);
+            ch_cp_wait<1>();
+        } else {
+            ch_cp_wait<0>();
+        }
+        __syncthreads();
+        const double* as = As + buf * CB * CLD + (warp * 32 + g) * CLD + q;
+        const double* bs = Bs + buf * BSTAGE + (BKN ? q * WLDN + g : g * CLD + q);
+#pragma unroll
+        for (int k4 = 0; k4 < CK / 4; ++k4) {
+            double a[4], b[8];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a[r] = as[r * 8 * CLD + k4 * 4];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) b[c] = BKN ? bs[k4 * 4 * WLDN + c * 8] : bs[c * 8 * CLD + k4 * 4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) ch_dmma(acc[r][c][0], acc[r][c][1], a[r], b[c]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int row = warp * 32 + r * 8 + g;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double2* dst = reinterpret_cast<double2*>(Ct + (int64_t)row * p.ldc + c * 8 + 2 * q);
+            if (p.subtract) {
+                double2 v = *dst;
+                v.x -= acc[r][c][0];
+                v.y -= acc[r][c][1];
+                *dst = v;
+            } else {
+                *dst = make_double2(acc[r][c][0], acc[r][c][1]);
+            }
+        }
+    }
+}
+
+// Row reductions of the prediction path: quad[j] = sum_i W[j,i] G[j,i] and dots[t,j] = sum_i vecs[t,i] W[j,i]
+// (W: the solved right-hand sides, G: the Gram block again, both (rows, ld); vecs: (nvec, ld), nvec <= 4).
+// One CTA per row, fixed summation order.
+constexpr int WR_THREADS = 256;
+__global__ void __launch_bounds__(WR_THREADS) chol_rowdots_kernel(const double* __restrict__ W, const double* __restrict__ G,
+                                                                  int64_t ld, int64_t n, const double* __restrict__ vecs,
+                                                                  int nvec, double* __restrict__ quad,
+                                                                  double* __restrict__ dots, int64_t ldd) {
+    __shared__ double red[5][WR_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* w = W + (int64_t)blockIdx.x * ld;
+    const double* gr = G + (int64_t)blockIdx.x * ld;
+    double s[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int64_t i = tid; i < n; i += WR_THREADS) {
+        const double wi = w[i];
+        s[0] = pn_fma(wi, gr[i], s[0]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (t < nvec) s[t + 1] = pn_fma(wi, vecs[(int64_t)t * ld + i], s[t + 1]);
+    }
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {
+        double v = s[t];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (lane == 0) red[t][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 5) {
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < WR_THREADS / 32; ++k) v += red[tid][k];
+        if (tid == 0) quad[blockIdx.x] = v;
+        else if (tid - 1 < nvec) dots[(int64_t)(tid - 1) * ldd + blockIdx.x] = v;
+    }
+}
+
 }  // namespace
 
 // M: (npad, npad) row-major with ld = npad (a multiple of 128); the Gram matrix occupies the leading
@@ -508,6 +661,10 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         chol_gemm_kernel<<<(unsigned)(2 * nb), CG_THREADS, smem_gemm, stream>>>(p);
         ++g_pn_launches;
         if ((err = cudaEventRecord(ev_panel, stream)) != cudaSuccess) return err;
+        // L[i,k] into the matrix (rows below the diagonal block of column k; nobody else touches them)
+        if ((err = cudaMemcpy2DAsync(const_cast<double*>(p.A), (size_t)npad * 8, panel, (size_t)CB * 8, (size_t)CB * 8,
+                                     (size_t)(nb * CB), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
+            return err;
         ChGemm u{};
         u.A = panel;
         u.lda = CB;
@@ -567,5 +724,76 @@ cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, dou
             ++g_pn_launches;
         }
     }
+    return cudaGetLastError();
+}
+
+// Z, Y: (mpad, npad) row-major (mpad a multiple of 128).  In: Z = right-hand sides, one per ROW (the
+// transposed layout of the kernel above); out: Z = the solutions of L L^T w = z for every row, Y scratch.
+cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
+                               cudaStream_t stream) {
+    cudaError_t err;
+    const size_t smem = sizeof(double) * (2 * CB * CLD + 2 * (CTN * CLD > CK * WLDN ? CTN * CLD : CK * WLDN));
+    if ((err = cudaFuncSetAttribute(chol_wide_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(chol_wide_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    const int64_t T = npad / CB;
+    const unsigned mt = (unsigned)(mpad / CB);
+    if (mt > 65535) return cudaErrorInvalidConfiguration;
+    for (int64_t k = 0; k < T; ++k) {  // L Y = Z
+        ChWide d{};
+        d.A = Z + k * CB;
+        d.lda = npad;
+        d.B = invd + k * CB * CB;
+        d.ldb = CB;
+        d.C = Y + k * CB;
+        d.ldc = npad;
+        d.subtract = 0;
+        chol_wide_gemm_kernel<false><<<dim3(CB / CTN, mt), CG_THREADS, smem, stream>>>(d);
+        ++g_pn_launches;
+        const int64_t rest = npad - (k + 1) * CB;
+        if (rest > 0) {
+            ChWide u{};
+            u.A = Y + k * CB;
+            u.lda = npad;
+            u.B = M + (k + 1) * CB * npad + k * CB;  // L[i, k] for the block rows i > k
+            u.ldb = npad;
+            u.C = Z + (k + 1) * CB;
+            u.ldc = npad;
+            u.subtract = 1;
+            chol_wide_gemm_kernel<false><<<dim3((unsigned)(rest / CTN), mt), CG_THREADS, smem, stream>>>(u);
+            ++g_pn_launches;
+        }
+    }
+    for (int64_t k = T - 1; k >= 0; --k) {  // L^T X = Y
+        ChWide d{};
+        d.A = Y + k * CB;
+        d.lda = npad;
+        d.B = invd + k * CB * CB;
+        d.ldb = CB;
+        d.C = Z + k * CB;
+        d.ldc = npad;
+        d.subtract = 0;
+        chol_wide_gemm_kernel<true><<<dim3(CB / CTN, mt), CG_THREADS, smem, stream>>>(d);
+        ++g_pn_launches;
+        if (k > 0) {
+            ChWide u{};
+            u.A = Z + k * CB;
+            u.lda = npad;
+            u.B = M + k * CB * npad;  // L[k, j] for the block columns j < k
+            u.ldb = npad;
+            u.C = Y;
+            u.ldc = npad;
+            u.subtract = 1;
+            chol_wide_gemm_kernel<true><<<dim3((unsigned)(k * CB / CTN), mt), CG_THREADS, smem, stream>>>(u);
+            ++g_pn_launches;
+        }
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t pn_chol_rowdots(const double* W, const double* G, int64_t ld, int64_t n, int64_t rows, const double* vecs,
+                            int nvec, double* quad, double* dots, int64_t ldd, cudaStream_t stream) {
+    if (rows <= 0) return cudaSuccess;
+    chol_rowdots_kernel<<<(unsigned)rows, WR_THREADS, 0, stream>>>(W, G, ld, n, vecs, nvec, quad, dots, ldd);
+    ++g_pn_launches;
     return cudaGetLastError();
 }

@@ -99,6 +99,11 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
                            int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
                            cudaEvent_t ev_diag);
 cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream);
+// many right-hand sides, one per ROW of Z (mpad x npad); Y: scratch of the same shape
+cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
+                               cudaStream_t stream);
+cudaError_t pn_chol_rowdots(const double* W, const double* G, int64_t ld, int64_t n, int64_t rows, const double* vecs,
+                            int nvec, double* quad, double* dots, int64_t ldd, cudaStream_t stream);
 
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
 // pn_plan_matvec fills m.jsplit (how many column-range splits the launch will use, which

@@ -358,6 +358,68 @@ def enable_quad_cholesky(backend: str = "pncov") -> None:
 
     cls.compute_gram_cho_factor = compute_gram_cho_factor
     cls.gram_cho_solve = staticmethod(gram_cho_solve)
+    if backend == "pncov":
+        _enable_quad_prediction()
+
+
+def _device_prediction(x, bq_state, vecs):
+    """``(k(x, x), quad, dots)`` of ``Cholesky.solve_gram`` for a BQ state whose factor lives on the
+    device, or None when the state is outside that path (no data yet, host factor, a kernel without
+    a single-launch Gram)."""
+    chol = bq_state.gram_cho_factor
+    chol = chol[0] if isinstance(chol, tuple) else chol
+    if not (isinstance(chol, DeviceCholesky) and chol.backend == "pncov") or bq_state.fun_evals.shape[0] == 0:
+        return None
+    twin = _mirror_of(bq_state.kernel)
+    try:
+        params = twin._kernel_params()
+    except (AttributeError, NotImplementedError):  # outside the scope, or an arithmetic node
+        return None
+    x = np.asarray(x, dtype=np.float64)
+    nodes = np.asarray(bq_state.nodes, dtype=np.float64)
+    if x.ndim != 2 or nodes.ndim != 2 or x.shape[0] == 0:
+        return None
+    with _mirror._lib.Operator(params, nodes, x) as op:
+        quad, dots = chol.factor.solve_gram(op, vecs)
+    return bq_state.kernel(x, x), quad, dots
+
+
+def _enable_quad_prediction() -> None:
+    """``BQStandardBeliefUpdate.predict_integrand``
+    (quad/solvers/belief_updates/_standard_update.py:131-151) and
+    ``IntegralVarianceReduction.__call__`` (acquisition_functions/_integral_variance_reduction.py:60-75)
+    with the cross Gram ``K(nodes, x)``, the solve against the device factor and the column
+    reductions in one device pass (``pncov_chol_solve_gram``); only length-m vectors come back."""
+    from probnum.quad.solvers.acquisition_functions import _integral_variance_reduction as ivr  # noqa: PLC0415
+    from probnum.quad.solvers.belief_updates import _standard_update as su  # noqa: PLC0415
+
+    upd, acq = su.BQStandardBeliefUpdate, ivr.IntegralVarianceReduction
+    if ("quad_predict", upd) in _ORIGINALS:
+        return
+    _ORIGINALS[("quad_predict", upd)] = upd.__dict__["predict_integrand"]
+    _ORIGINALS[("quad_predict", acq)] = acq.__dict__["__call__"]
+    predict0 = upd.__dict__["predict_integrand"].__func__
+    call0 = acq.__dict__["__call__"]
+
+    def predict_integrand(x, bq_state):
+        res = _device_prediction(x, bq_state, [bq_state.fun_evals])
+        if res is None:
+            return predict0(x, bq_state)
+        prior_var, quad, dots = res
+        return dots[0], bq_state.scale_sq * (prior_var - quad)
+
+    def __call__(self, x, bq_state):
+        res = _device_prediction(x, bq_state, [bq_state.kernel_means])
+        if res is None:
+            return call0(self, x, bq_state)
+        prior_var, quad, dots = res
+        y_predictive_var = bq_state.scale_sq * (prior_var - quad) + 0.0  # observation noise placeholder of the reference
+        predictive_embedding = bq_state.kernel_embedding.kernel_mean(x) - dots[0]
+        values = (bq_state.scale_sq * predictive_embedding) ** 2 / (bq_state.integral_belief.cov * y_predictive_var)
+        return values, None
+
+    upd.predict_integrand = staticmethod(predict_integrand)
+    acq.__call__ = __call__
 
 
 def disable() -> None:
@@ -369,6 +431,9 @@ def disable() -> None:
         factor, solve = _ORIGINALS.pop(key)
         key[1].compute_gram_cho_factor = factor
         key[1].gram_cho_solve = solve
+    for key in [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "quad_predict"]:
+        orig = _ORIGINALS.pop(key)
+        setattr(key[1], "predict_integrand" if isinstance(orig, staticmethod) else "__call__", orig)
     for key in [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "matrix"]:
         orig = _ORIGINALS.pop(key)
         if "_evaluate_matrix" in key[1].__dict__:

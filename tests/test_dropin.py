@@ -212,6 +212,53 @@ def test_bayesquad_with_device_cholesky_matches_cpu_run():
         assert abs(v_gpu - v_cpu) <= 1e-6 * abs(v_cpu) + 1e-13, backend
 
 
+@pytest.mark.gpu
+def test_prediction_path_on_the_device_matches_cpu_run():
+    """BQStandardBeliefUpdate.predict_integrand and IntegralVarianceReduction.__call__
+    with cross Gram, solve and column reductions in one device pass (pncov_chol_solve_gram)."""
+    from probnum.quad.solvers import BQState
+    from probnum.quad.solvers.acquisition_functions import IntegralVarianceReduction
+    from probnum.quad.solvers.belief_updates import BQStandardBeliefUpdate
+    from probnum.quad.solvers.belief_updates import _standard_update as su
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(11)
+    n, m, d = 900, 257, 2
+    nodes, x = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    fun_evals = np.sin(nodes).sum(axis=1)
+    measure = pn.quad.integration_measures.GaussianMeasure(mean=np.zeros(d), cov=np.eye(d))
+
+    def run():
+        kernel = cf.ExpQuad((d,), lengthscales=0.6)  # Matern has no Gaussian kernel embedding in the reference
+        update = BQStandardBeliefUpdate(jitter=1e-4, scale_estimation="mle")
+        state = BQState(measure=measure, kernel=kernel)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _, state = update(state, nodes, fun_evals)
+            mean, var = BQStandardBeliefUpdate.predict_integrand(x, state)
+            acq, _ = IntegralVarianceReduction()(x, state)
+        return mean, var, acq
+
+    mean_cpu, var_cpu, acq_cpu = run()
+    original = su.BQStandardBeliefUpdate.__dict__["predict_integrand"]
+    pb_patch.enable()
+    pb_patch.enable_quad_cholesky("pncov")
+    launches = _lib.launch_count()
+    try:
+        assert su.BQStandardBeliefUpdate.__dict__["predict_integrand"] is not original
+        mean_gpu, var_gpu, acq_gpu = run()
+    finally:
+        pb_patch.disable()
+    assert su.BQStandardBeliefUpdate.__dict__["predict_integrand"] is original
+    assert _lib.launch_count() - launches > 60
+    # two different solvers on the host (Cholesky vs LU) differ by 1e-13 (mean), 4e-15 (variance) and
+    # 5e-8 relative (acquisition, a quotient by variances down to 1e-7) on this problem
+    np.testing.assert_allclose(mean_gpu, mean_cpu, rtol=0, atol=1e-11 * np.abs(fun_evals).max())
+    # posterior variance = scale_sq (prior 1 minus a sum that nearly cancels it): absolute scale
+    np.testing.assert_allclose(var_gpu, var_cpu, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(acq_gpu, acq_cpu, rtol=1e-5, atol=0)
+
+
 def test_evaluate_hook_is_restored():
     before = {cls: cls.__dict__["_evaluate"] for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad)}
     pb_patch.enable()

@@ -98,3 +98,45 @@ def test_factor_from_operator_keeps_the_gram_on_the_device():
         assert covfuncs.gram_provenance(K.copy()) is None
         ch.close()
         ref.close()
+
+
+@pytest.mark.parametrize("n,m,d", [(640, 128, 3), (1000, 333, 4), (300, 1, 2), (129, 2100, 3)])
+def test_solve_gram_matches_host_linear_algebra(n, m, d):
+    """pncov_chol_solve_gram: W = (L L^T)^-1 K(nodes, x) by the blocked DMMA
+    substitution with transposed right-hand sides; column sums of W * K and vecs @ W against
+    scipy's cho_solve on the oracle's Gram block.  The solves amplify rounding by cond(K + jitter I)
+    (~1e4 here), hence 1e-9 rather than the Gram's 1e-12."""
+    from oracle import covfuncs_oracle as orc
+
+    rng = np.random.default_rng(n + m)
+    nodes, x = rng.normal(size=(n, d)), rng.normal(size=(m, d))
+    k = pb.Matern((d,), nu=1.5, lengthscales=0.7)
+    spec = orc.KernelSpec("matern", (d,), 0.7, nu=1.5)
+    jitter = 1e-3
+    K = orc.gram(spec, nodes) + jitter * np.eye(n)
+    G = orc.gram(spec, nodes, x)
+    W = scipy.linalg.cho_solve(scipy.linalg.cho_factor(K, lower=True), G)
+    vecs = rng.normal(size=(3, n))
+    with _lib.Operator(k._kernel_params(), nodes) as sq:
+        ch = _lib.Cholesky(sq, jitter=jitter)
+    before = _lib.launch_count()
+    with _lib.Operator(k._kernel_params(), nodes, x) as op:
+        quad, dots = ch.solve_gram(op, vecs)
+        quad0, dots0 = ch.solve_gram(op)  # no vectors
+        # the generic host-to-host solve gives the same W
+        np.testing.assert_allclose(ch.solve(G), W, rtol=1e-9, atol=1e-11)
+        with pytest.raises(ValueError):
+            ch.solve_gram(op, rng.normal(size=(5, n)))
+    assert _lib.launch_count() - before > 4 * ((n + 127) // 128) - 2
+    assert ch.last_solve_gram_ms > 0.0
+    scale = np.sum(np.abs(W * G), axis=0)
+    assert np.all(np.abs(quad - np.sum(W * G, axis=0)) <= 1e-9 * scale + 1e-13)
+    np.testing.assert_array_equal(quad0, quad)
+    assert dots0.shape == (0, m)
+    ref = vecs @ W
+    assert np.all(np.abs(dots - ref) <= 1e-9 * (np.abs(vecs) @ np.abs(W)) + 1e-13)
+    with _lib.Operator(k._kernel_params(), x, nodes) as wrong:
+        if m != n:
+            with pytest.raises(ValueError):
+                ch.solve_gram(wrong)
+    ch.close()
