@@ -213,6 +213,11 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
  *                                                                                 np.dot(kernel_means, weights))
  *                           for nvec <= 4 host vectors of length n.  G and W (n x m each) never leave
  *                           the device; *ms (may be NULL) = device time of the whole pass.
+ *                           mode PNCOV_SOLVE_GRAM_REFERENCE_ORDER: both substitutions, then the sums
+ *                           above, as the reference computes them.  PNCOV_SOLVE_GRAM_FORWARD_ONLY:
+ *                           the same quantities from Y = L^-1 G alone, quad[j] = |Y[:,j]|^2 and
+ *                           dots[t,j] = (L^-1 vecs[t]) . Y[:,j] -- half the flops, sums of squares
+ *                           instead of cancelling sums, error ~ sqrt(cond) eps instead of cond eps.
  *   pncov_chol_get_factor   lower-triangular factor to a host array (the strict upper triangle of
  *                           the output is unspecified, as with scipy.linalg.cho_factor)
  *   pncov_chol_last_factor_ms   device time of the last factorisation (CUDA events)
@@ -223,8 +228,10 @@ PNCOV_API int pncov_chol_destroy(pncov_chol* c);
 PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, double jitter, int a_on_device, int* info);
 PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitter, int* info);
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx);
+#define PNCOV_SOLVE_GRAM_REFERENCE_ORDER 0
+#define PNCOV_SOLVE_GRAM_FORWARD_ONLY 1
 PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec, const double* vecs, int64_t ldv,
-                                    double* dots, int64_t ldd, double* quad, float* ms);
+                                    double* dots, int64_t ldd, double* quad, int mode, float* ms);
 PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld);
 PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms);
 

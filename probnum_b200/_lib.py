@@ -65,7 +65,7 @@ SIGNATURES = {
     "pncov_chol_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "pncov_chol_factor_gram": (ctypes.c_int, [_c_vp, _c_vp, ctypes.c_double, ctypes.POINTER(ctypes.c_int)]),
     "pncov_chol_solve": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
-    "pncov_chol_solve_gram": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp,
+    "pncov_chol_solve_gram": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, ctypes.c_int,
                                              ctypes.POINTER(ctypes.c_float)]),
     "pncov_chol_get_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
     "pncov_chol_last_factor_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -410,12 +410,15 @@ class Cholesky:
             _check(self._lib.pncov_chol_solve(self._h, _ptr(b2), k, k, _ptr(x), k))
         return x.reshape(b.shape)
 
-    def solve_gram(self, op: "Operator", vecs=()):
+    def solve_gram(self, op: "Operator", vecs=(), *, forward_only: bool = False):
         """Prediction path: with ``G = K(nodes, x)`` the Gram matrix of ``op``
         (``op.shape == (n, m)``, first point set = the factorised nodes) and ``W = (L L^T)^-1 G``
         returns ``(quad, dots)`` with ``quad[j] = sum_i W[i, j] G[i, j]`` and
         ``dots[t, j] = vecs[t] @ W[:, j]`` for up to four host vectors of length n.  G and W stay
-        on the device.  ``self.last_solve_gram_ms`` holds the device time of the pass."""
+        on the device.  ``self.last_solve_gram_ms`` holds the device time of the pass.
+        ``forward_only``: the same quantities from ``Y = L^-1 G`` alone (``quad = |Y[:, j]|^2``,
+        ``dots = (L^-1 vecs[t]) . Y[:, j]``): half the flops and no cancelling sums; the default
+        follows the reference's order of operations (both substitutions, then the sums)."""
         if op.shape[0] != self.n:
             raise ValueError(f"the operator's first point set has {op.shape[0]} points, the factor has order {self.n}")
         m = op.shape[1]
@@ -426,7 +429,8 @@ class Cholesky:
         dots = np.empty((v.shape[0], m), dtype=np.float64)
         ms = ctypes.c_float(0.0)
         _check(self._lib.pncov_chol_solve_gram(self._h, op._h, v.shape[0], _ptr(v) if v.shape[0] else None, self.n,
-                                               _ptr(dots) if v.shape[0] else None, max(m, 1), _ptr(quad), ctypes.byref(ms)))
+                                               _ptr(dots) if v.shape[0] else None, max(m, 1), _ptr(quad),
+                                               1 if forward_only else 0, ctypes.byref(ms)))
         self.last_solve_gram_ms = float(ms.value)
         return quad, dots
 

@@ -1292,13 +1292,16 @@ PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int
 }
 
 PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec, const double* vecs, int64_t ldv,
-                                    double* dots, int64_t ldd, double* quad, float* ms) {
+                                    double* dots, int64_t ldd, double* quad, int mode, float* ms) {
     if (!c || !h || !quad) return fail(PNCOV_EINVAL, "NULL argument");
     if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");
     if (h->device != c->device) return fail(PNCOV_EINVAL, "operator and Cholesky handle live on different devices");
     if (h->p0.n != c->n) return fail(PNCOV_EINVAL, "the operator's first point set is not the factorised one (n0 != n)");
     if (h->k.gram_elem() != 8) return fail(PNCOV_EINVAL, "float64 Gram matrices only");
     if (nvec < 0 || nvec > 4) return fail(PNCOV_EINVAL, "at most 4 vectors");
+    if (mode != PNCOV_SOLVE_GRAM_REFERENCE_ORDER && mode != PNCOV_SOLVE_GRAM_FORWARD_ONLY)
+        return fail(PNCOV_EINVAL, "unknown mode");
+    const bool fwd = mode == PNCOV_SOLVE_GRAM_FORWARD_ONLY;
     if (nvec > 0 && (!vecs || !dots || ldv < c->n)) return fail(PNCOV_EINVAL, "bad vector arguments");
     const int64_t m = h->p1.n, n = c->n, npad = c->npad;
     if (nvec > 0 && ldd < m) return fail(PNCOV_EINVAL, "ldd smaller than the number of prediction points");
@@ -1323,19 +1326,31 @@ PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec
         if ((e = pn_dev_alloc(&Y, (size_t)chunk * npad * 8, s)) != cudaSuccess) return e;
         if ((e = pn_dev_alloc(&qd, (size_t)m * 8, s)) != cudaSuccess) return e;
         if (nvec > 0) {
-            if ((e = pn_dev_alloc(&vd, (size_t)nvec * npad * 8, s)) != cudaSuccess) return e;
+            // forward-only: vd holds the rows (L^-1 v_t)^T, produced by a 128-row substitution pass of its own
+            if ((e = pn_dev_alloc(&vd, (size_t)(fwd ? 128 : nvec) * npad * 8, s)) != cudaSuccess) return e;
             if ((e = pn_dev_alloc(&dd, (size_t)nvec * m * 8, s)) != cudaSuccess) return e;
-            if ((e = cudaMemcpy2DAsync(vd, (size_t)npad * 8, vecs, (size_t)ldv * 8, (size_t)n * 8, (size_t)nvec,
+            void* dst = fwd ? Z : vd;
+            if (fwd && (e = cudaMemsetAsync(Z, 0, (size_t)128 * npad * 8, s)) != cudaSuccess) return e;
+            if ((e = cudaMemcpy2DAsync(dst, (size_t)npad * 8, vecs, (size_t)ldv * 8, (size_t)n * 8, (size_t)nvec,
                                        cudaMemcpyHostToDevice, s)) != cudaSuccess)
                 return e;
         }
         if ((e = cudaEventRecord(c->ev0, s)) != cudaSuccess) return e;
+        if (fwd && nvec > 0 &&
+            (e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(vd), 128, 1, s)) != cudaSuccess)
+            return e;
         for (int64_t r0 = 0; r0 < m; r0 += chunk) {
             const int64_t mc = std::min<int64_t>(chunk, m - r0), mcpad = (mc + 127) / 128 * 128;
             // padded columns must be exact zeros (they meet the identity block of the padded factor)
             if (npad != n && (e = cudaMemsetAsync(Z, 0, (size_t)mcpad * npad * 8, s)) != cudaSuccess) return e;
             if ((e = launch_gram_any(h, true, r0, mc, Z, npad, s)) != cudaSuccess) return e;  // rows: prediction points
-            if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, s)) != cudaSuccess) return e;
+            if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, fwd ? 1 : 0, s)) != cudaSuccess) return e;
+            if (fwd) {  // rows of Y = (L^-1 g_j)^T: quad = |y_j|^2, dots = (L^-1 v_t) . y_j
+                if ((e = pn_chol_rowdots(static_cast<double*>(Y), static_cast<double*>(Y), npad, n, mc, static_cast<double*>(vd),
+                                         (int)nvec, static_cast<double*>(qd) + r0, static_cast<double*>(dd) + r0, m, s)) != cudaSuccess)
+                    return e;
+                continue;
+            }
             if ((e = launch_gram_any(h, true, r0, mc, Y, npad, s)) != cudaSuccess) return e;  // the Gram block again
             if ((e = pn_chol_rowdots(static_cast<double*>(Z), static_cast<double*>(Y), npad, n, mc, static_cast<double*>(vd),
                                      (int)nvec, static_cast<double*>(qd) + r0, static_cast<double*>(dd) + r0, m, s)) != cudaSuccess)

@@ -729,8 +729,9 @@ cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, dou
 
 // Z, Y: (mpad, npad) row-major (mpad a multiple of 128).  In: Z = right-hand sides, one per ROW (the
 // transposed layout of the kernel above); out: Z = the solutions of L L^T w = z for every row, Y scratch.
+// forward_only: stop after L y = z; the solutions y are the rows of Y (Z is clobbered).
 cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
-                               cudaStream_t stream) {
+                               int forward_only, cudaStream_t stream) {
     cudaError_t err;
     const size_t smem = sizeof(double) * (2 * CB * CLD + 2 * (CTN * CLD > CK * WLDN ? CTN * CLD : CK * WLDN));
     if ((err = cudaFuncSetAttribute(chol_wide_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
@@ -763,6 +764,7 @@ cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd
             ++g_pn_launches;
         }
     }
+    if (forward_only) return cudaGetLastError();
     for (int64_t k = T - 1; k >= 0; --k) {  // L^T X = Y
         ChWide d{};
         d.A = Y + k * CB;

@@ -362,6 +362,13 @@ def enable_quad_cholesky(backend: str = "pncov") -> None:
         _enable_quad_prediction()
 
 
+# pncov_chol_solve_gram mode of the patched prediction path.  False: both substitutions and the sums in
+# the reference's order.  True: everything from L^-1 K(nodes, x) alone (half the flops; sums of squares
+# instead of cancelling sums, so the result is the more accurate one when the Gram matrix is
+# ill-conditioned -- it then differs from the reference's by the reference's own rounding error).
+PREDICTION_FORWARD_ONLY = False
+
+
 def _device_prediction(x, bq_state, vecs):
     """``(k(x, x), quad, dots)`` of ``Cholesky.solve_gram`` for a BQ state whose factor lives on the
     device, or None when the state is outside that path (no data yet, host factor, a kernel without
@@ -380,7 +387,7 @@ def _device_prediction(x, bq_state, vecs):
     if x.ndim != 2 or nodes.ndim != 2 or x.shape[0] == 0:
         return None
     with _mirror._lib.Operator(params, nodes, x) as op:
-        quad, dots = chol.factor.solve_gram(op, vecs)
+        quad, dots = chol.factor.solve_gram(op, vecs, forward_only=PREDICTION_FORWARD_ONLY)
     return bq_state.kernel(x, x), quad, dots
 
 

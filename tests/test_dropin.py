@@ -247,8 +247,14 @@ def test_prediction_path_on_the_device_matches_cpu_run():
     try:
         assert su.BQStandardBeliefUpdate.__dict__["predict_integrand"] is not original
         mean_gpu, var_gpu, acq_gpu = run()
+        pb_patch.PREDICTION_FORWARD_ONLY = True
+        mean_fwd, var_fwd, acq_fwd = run()
     finally:
+        pb_patch.PREDICTION_FORWARD_ONLY = False
         pb_patch.disable()
+    np.testing.assert_allclose(mean_fwd, mean_cpu, rtol=0, atol=1e-11 * np.abs(fun_evals).max())
+    np.testing.assert_allclose(var_fwd, var_cpu, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(acq_fwd, acq_cpu, rtol=1e-5, atol=0)
     assert su.BQStandardBeliefUpdate.__dict__["predict_integrand"] is original
     assert _lib.launch_count() - launches > 60
     # two different solvers on the host (Cholesky vs LU) differ by 1e-13 (mean), 4e-15 (variance) and

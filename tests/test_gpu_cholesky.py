@@ -123,6 +123,8 @@ def test_solve_gram_matches_host_linear_algebra(n, m, d):
     with _lib.Operator(k._kernel_params(), nodes, x) as op:
         quad, dots = ch.solve_gram(op, vecs)
         quad0, dots0 = ch.solve_gram(op)  # no vectors
+        quad_f, dots_f = ch.solve_gram(op, vecs, forward_only=True)  # |L^-1 g|^2 and (L^-1 v).(L^-1 g)
+        quad_f0, _ = ch.solve_gram(op, forward_only=True)
         # the generic host-to-host solve gives the same W
         np.testing.assert_allclose(ch.solve(G), W, rtol=1e-9, atol=1e-11)
         with pytest.raises(ValueError):
@@ -135,6 +137,9 @@ def test_solve_gram_matches_host_linear_algebra(n, m, d):
     assert dots0.shape == (0, m)
     ref = vecs @ W
     assert np.all(np.abs(dots - ref) <= 1e-9 * (np.abs(vecs) @ np.abs(W)) + 1e-13)
+    assert np.all(np.abs(quad_f - np.sum(W * G, axis=0)) <= 1e-9 * scale + 1e-13)
+    assert np.all(np.abs(dots_f - ref) <= 1e-9 * (np.abs(vecs) @ np.abs(W)) + 1e-13)
+    np.testing.assert_array_equal(quad_f0, quad_f)
     with _lib.Operator(k._kernel_params(), x, nodes) as wrong:
         if m != n:
             with pytest.raises(ValueError):

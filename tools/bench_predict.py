@@ -20,6 +20,7 @@ from probnum_b200 import _lib  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 d = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+device_only = len(sys.argv) > 4 and sys.argv[4] == "device-only"  # for runs under ncu
 rng = np.random.default_rng(42)
 nodes, x = rng.normal(size=(n, d)), rng.normal(size=(m, d))
 fun_evals = np.sin(nodes).sum(axis=1)
@@ -39,6 +40,14 @@ with _lib.Operator(k._kernel_params(), nodes, x) as op:
     res["solve_gram_wall_ms"] = wall * 1e3
     flops = 2.0 * n * n * m  # forward + backward substitution
     res["solve_gram_tflops"] = flops / (ch.last_solve_gram_ms * 1e-3) / 1e12
+    for _ in range(2):
+        quad_f, dots_f = ch.solve_gram(op, [fun_evals], forward_only=True)
+    res["forward_only_device_ms"] = ch.last_solve_gram_ms
+    res["forward_only_tflops"] = 0.5 * flops / (ch.last_solve_gram_ms * 1e-3) / 1e12
+    res["forward_only_vs_reference_order_abs"] = [float(np.abs(quad_f - quad).max()), float(np.abs(dots_f - dots).max())]
+if device_only:
+    print(json.dumps(res))
+    sys.exit(0)
 
 # (a) generic solve on a column sample
 ms_ = min(m, 64)
