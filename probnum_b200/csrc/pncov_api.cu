@@ -1185,7 +1185,11 @@ PNCOV_API int pncov_chol_create(pncov_chol** out, int device, int64_t n) {
     c->npad = ((n + 127) / 128) * 128;
     DeviceGuard guard(device);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {  // look-ahead stream: highest priority, so its single CTA is dispatched first
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming);
@@ -1308,8 +1312,8 @@ PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec
     if (ms) *ms = 0.f;
     if (m == 0) return 0;
     DeviceGuard guard(c->device);
-    // row chunks of the transposed right-hand sides: two (chunk, npad) buffers of at most 256 MiB each
-    int64_t chunk = std::max<int64_t>(128, ((int64_t)(256ll << 20) / (npad * 8)) / 128 * 128);
+    // row chunks of the transposed right-hand sides: two (chunk, npad) buffers of at most 512 MiB each
+    int64_t chunk = std::max<int64_t>(128, ((int64_t)(512ll << 20) / (npad * 8)) / 128 * 128);
     chunk = std::min<int64_t>(chunk, (m + 127) / 128 * 128);
     void *Z = nullptr, *Y = nullptr, *vd = nullptr, *qd = nullptr, *dd = nullptr;
     cudaStream_t s = c->stream;

@@ -206,8 +206,12 @@ __device__ __forceinline__ void chol_diag_steps(double (&r)[8][8], double* colbu
 // distribution); per elimination step the owners publish one column through shared memory, one
 // barrier, and everybody updates its registers.  info receives the 1-based index of the first
 // non-positive pivot.
+// P != nullptr (look-ahead): the block first receives its own trailing update A -= P P^T from the 128 x 128
+// head of the current panel, so the kernel depends on the panel alone and can take an SM before the
+// wide update of the same step fills the machine.
 __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, int64_t lda, double* __restrict__ invL,
-                                                         int* __restrict__ info, int pivot_base) {
+                                                         int* __restrict__ info, int pivot_base,
+                                                         const double* __restrict__ P) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* a = reinterpret_cast<double*>(smem);  // [CB][CD_LD]: upper triangle L^T, lower triangle inv(L)
     double* dg = a + CB * CD_LD;                  // [CB] diagonal of L
@@ -222,6 +226,30 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
             const int i = ty + 16 * ii, c = tx + 16 * cc;
             r[ii][cc] = (c <= i) ? A[(int64_t)i * lda + c] : 0.0;
         }
+    if (P != nullptr) {
+        for (int idx = tid; idx < CB * CB; idx += 256) a[(idx >> 7) * CD_LD + (idx & (CB - 1))] = P[idx];
+        __syncthreads();
+        const double* pr = a + ty * CD_LD;
+        const double* pc = a + tx * CD_LD;
+#pragma unroll 2
+        for (int l = 0; l < CB; ++l) {
+            double vi[8], vc[8];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) vi[ii] = pr[16 * ii * CD_LD + l];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) vc[cc] = pc[16 * cc * CD_LD + l];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) r[ii][cc] = pn_fma(-vi[ii], vc[cc], r[ii][cc]);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii)
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+                if (tx + 16 * cc > ty + 16 * ii) r[ii][cc] = 0.0;
+        // `a` is written again only after the elimination steps, whose barriers order it after these reads
+    }
     chol_diag_steps<0>(r, colbuf, ty, tx, tid, info, pivot_base);
     chol_diag_steps<1>(r, colbuf, ty, tx, tid, info, pivot_base);
     chol_diag_steps<2>(r, colbuf, ty, tx, tid, info, pivot_base);
@@ -642,8 +670,9 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
     if ((err = cudaFuncSetAttribute(chol_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
     const int64_t T = npad / CB;
     // Look-ahead: the factorisation of diagonal block k + 1 (one CTA, latency-bound) runs on `side`
-    // as soon as ITS tile of the trailing update is done, under the rest of the update of step k.
-    chol_diag_kernel<<<1, 256, smem_diag, stream>>>(M, npad, invd, info_dev, 0);
+    // under the update of step k; it applies its own tile of that update itself, so it is runnable as
+    // soon as the panel is and gets its SM before the update's CTAs occupy every slot.
+    chol_diag_kernel<<<1, 256, smem_diag, stream>>>(M, npad, invd, info_dev, 0, nullptr);
     ++g_pn_launches;
     for (int64_t k = 0; k < T; ++k) {
         double* diag = M + k * CB * (npad + 1);
@@ -674,12 +703,11 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         u.ldc = npad;
         u.panel = nullptr;
         u.mode = 1;
-        // side stream: tile (k + 1, k + 1) of the update, then the next diagonal factorisation
+        // side stream (high priority, issued before the wide update): tile (k + 1, k + 1) of the update
+        // fused into the next diagonal factorisation
         if ((err = cudaStreamWaitEvent(side, ev_panel, 0)) != cudaSuccess) return err;
-        u.tile0 = 0;
-        chol_gemm_kernel<<<2, CG_THREADS, smem_gemm, side>>>(u);
-        ++g_pn_launches;
-        chol_diag_kernel<<<1, 256, smem_diag, side>>>(u.C, npad, invd + (k + 1) * CB * CB, info_dev, (int)((k + 1) * CB));
+        chol_diag_kernel<<<1, 256, smem_diag, side>>>(u.C, npad, invd + (k + 1) * CB * CB, info_dev, (int)((k + 1) * CB),
+                                                      panel);
         ++g_pn_launches;
         if ((err = cudaEventRecord(ev_diag, side)) != cudaSuccess) return err;
         // main stream: the other tiles of the trailing update
