@@ -145,3 +145,37 @@ def test_solve_gram_matches_host_linear_algebra(n, m, d):
             with pytest.raises(ValueError):
                 ch.solve_gram(wrong)
     ch.close()
+
+
+def test_solve_gram_edge_cases_and_errors():
+    """float32 operators (rejected: the factor is float64), a dense-only family
+    as the cross Gram, and the raw C ABI's argument checks."""
+    import ctypes
+
+    rng = np.random.default_rng(3)
+    n, d = 200, 3
+    nodes = rng.normal(size=(n, d))
+    k = pb.ExpQuad((d,), lengthscales=0.5)
+    with _lib.Operator(k._kernel_params(), nodes) as sq:
+        ch = _lib.Cholesky(sq, jitter=1e-6)
+    x32 = rng.normal(size=(10, d)).astype(np.float32)
+    with _lib.Operator(k._kernel_params(), nodes.astype(np.float32), x32) as op32:
+        with pytest.raises(ValueError, match="float64"):
+            ch.solve_gram(op32)
+    # ProductMatern cross Gram against an ExpQuad factor: any family the Gram launcher knows works
+    pm = pb.ProductMatern((d,), lengthscales=1.3, nus=1.5)
+    x = rng.normal(size=(37, d))
+    with _lib.Operator(pm._kernel_params(), nodes, x) as op:
+        quad, _ = ch.solve_gram(op)
+    G = pm.matrix(nodes, x)
+    W = ch.solve(G)
+    np.testing.assert_allclose(quad, np.sum(W * G, axis=0), rtol=1e-9, atol=1e-12)
+    # raw ABI: NULL output, bad mode, too many vectors
+    lib = _lib.load()
+    with _lib.Operator(k._kernel_params(), nodes, x) as op:
+        q = np.empty(37)
+        assert lib.pncov_chol_solve_gram(ch._h, op._h, 0, None, n, None, 37, None, 0, None) == -1
+        assert lib.pncov_chol_solve_gram(ch._h, op._h, 0, None, n, None, 37, q.ctypes.data_as(ctypes.c_void_p), 7, None) == -1
+        assert b"mode" in lib.pncov_last_error()
+        assert lib.pncov_chol_solve_gram(ch._h, op._h, 5, None, n, None, 37, q.ctypes.data_as(ctypes.c_void_p), 0, None) == -1
+    ch.close()
