@@ -235,6 +235,25 @@ PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec
 PNCOV_API int pncov_chol_get_factor(pncov_chol* c, double* l, int64_t ld);
 PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms);
 
+/* Update chains of the matrix-based linear solver (SURVEY.md 8f N2 ii) ---------------------------
+ * replaces the lazy sums of LambdaLinearOperators that SymmetricMatrixBasedSolver builds with
+ * _mean_update (u v^T + v u^T, linalg/solvers/matrixbased.py:751-762) and _covariance_update
+ * (Ws u^T, :764-775): the vectors live as rows of two device-resident (capacity, n) matrices U and
+ * V, and a product with the first k of them is two kernel launches instead of k Python lambdas.
+ *   pncov_chain_create   room for `capacity` vector pairs of length n on `device`
+ *   pncov_chain_set      vector pair number `index` from host memory (blocking)
+ *   pncov_chain_apply    y = C_k x for the ncols columns of x, (n, ncols) row-major host arrays, with
+ *                        mode 0: C_k = sum_{i<k} U_i V_i^T + V_i U_i^T   (mean update chain)
+ *                        mode 1: C_k = sum_{i<k} V_i U_i^T               (covariance update chain, V = Ws)
+ *                        mode 2: C_k = sum_{i<k} U_i V_i^T               (its transpose)
+ */
+typedef struct pncov_chain pncov_chain;
+PNCOV_API int pncov_chain_create(pncov_chain** out, int device, int64_t n, int64_t capacity);
+PNCOV_API int pncov_chain_destroy(pncov_chain* c);
+PNCOV_API int pncov_chain_set(pncov_chain* c, int64_t index, const double* u, const double* v);
+PNCOV_API int pncov_chain_apply(pncov_chain* c, int64_t k, int mode, const double* x, int64_t ncols, int64_t ldx,
+                                double* y, int64_t ldy);
+
 /* diagnostics ------------------------------------------------------------------------
  * number of kernel launches issued by this library in the calling process, and the
  * device time in ms of the last pncov_gram / pncov_matmul call of this handle (CUDA

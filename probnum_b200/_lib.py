@@ -65,6 +65,10 @@ SIGNATURES = {
     "pncov_chol_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "pncov_chol_factor_gram": (ctypes.c_int, [_c_vp, _c_vp, ctypes.c_double, ctypes.POINTER(ctypes.c_int)]),
     "pncov_chol_solve": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
+    "pncov_chain_create": (ctypes.c_int, [ctypes.POINTER(_c_vp), ctypes.c_int, _c_i64, _c_i64]),
+    "pncov_chain_destroy": (ctypes.c_int, [_c_vp]),
+    "pncov_chain_set": (ctypes.c_int, [_c_vp, _c_i64, _c_vp, _c_vp]),
+    "pncov_chain_apply": (ctypes.c_int, [_c_vp, _c_i64, ctypes.c_int, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
     "pncov_chol_solve_gram": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, ctypes.c_int,
                                              ctypes.POINTER(ctypes.c_float)]),
     "pncov_chol_get_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
@@ -448,6 +452,65 @@ class Cholesky:
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.pncov_chol_destroy(self._h)
+            self._h = _c_vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+
+class UpdateChain:
+    """Device-resident chain of vector pairs (SURVEY.md 8f N2 ii): the rank-2 / rank-1 update sums of
+    the matrix-based solver (linalg/solvers/matrixbased.py:751-775) as two (capacity, n) matrices in
+    HBM.  ``append`` adds a pair, ``apply(k, mode, x)`` multiplies the sum of the first k updates with
+    the columns of a host array; modes as in ``pncov_chain_apply``."""
+
+    SYMMETRIC_RANK2, RANK1, RANK1_TRANSPOSED = 0, 1, 2
+
+    def __init__(self, n: int, capacity: int = 64, *, device: Optional[int] = None):
+        self._lib = load()
+        self._h = _c_vp()
+        self.n, self.capacity = int(n), int(capacity)
+        self.device = default_device() if device is None else int(device)
+        self.pairs = []  # host copies: growth, copy-on-write, dense views
+        _check(self._lib.pncov_chain_create(ctypes.byref(self._h), self.device, self.n, self.capacity))
+
+    def __len__(self) -> int:
+        return len(self.pairs)
+
+    def append(self, u: np.ndarray, v: np.ndarray) -> int:
+        u = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(self.n))
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(self.n))
+        if len(self.pairs) == self.capacity:  # grow: new device matrices, vectors uploaded again
+            old = self._h
+            self._h = _c_vp()
+            self.capacity *= 2
+            _check(self._lib.pncov_chain_create(ctypes.byref(self._h), self.device, self.n, self.capacity))
+            self._lib.pncov_chain_destroy(old)
+            for i, (a, b) in enumerate(self.pairs):
+                _check(self._lib.pncov_chain_set(self._h, i, _ptr(a), _ptr(b)))
+        _check(self._lib.pncov_chain_set(self._h, len(self.pairs), _ptr(u), _ptr(v)))
+        self.pairs.append((u, v))
+        return len(self.pairs)
+
+    def apply(self, k: int, mode: int, x: np.ndarray) -> np.ndarray:
+        """``C_k @ x`` for a host array of shape (n, c)."""
+        x2 = np.ascontiguousarray(x, dtype=np.float64)
+        if x2.ndim != 2 or x2.shape[0] != self.n:
+            raise ValueError(f"expected an operand of shape ({self.n}, c)")
+        if not 0 <= k <= len(self.pairs):
+            raise ValueError("chain length out of range")
+        y = np.empty_like(x2)
+        c = x2.shape[1]
+        if c:
+            _check(self._lib.pncov_chain_apply(self._h, k, mode, _ptr(x2), c, c, _ptr(y), c))
+        return y
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.pncov_chain_destroy(self._h)
             self._h = _c_vp()
 
     def __del__(self):

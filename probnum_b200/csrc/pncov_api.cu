@@ -1393,6 +1393,94 @@ PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms) {
     return 0;
 }
 
+// ---- update chains of the matrix-based solver (SURVEY.md 8f N2 ii) -------------------------------------
+struct pncov_chain {
+    int device = 0;
+    int64_t n = 0, capacity = 0, ld = 0;
+    double *U = nullptr, *V = nullptr;  // (capacity, ld) row-major: one vector per row
+    double *x = nullptr, *y = nullptr, *partial = nullptr;
+    cudaStream_t stream = nullptr;
+};
+constexpr int kChainSplits = 32;
+
+PNCOV_API int pncov_chain_destroy(pncov_chain* c) {
+    if (!c) return 0;
+    DeviceGuard guard(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->U);
+    cudaFree(c->V);
+    cudaFree(c->x);
+    cudaFree(c->y);
+    cudaFree(c->partial);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+PNCOV_API int pncov_chain_create(pncov_chain** out, int device, int64_t n, int64_t capacity) {
+    if (!out) return fail(PNCOV_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n < 1 || capacity < 1 || capacity > 16384) return fail(PNCOV_EINVAL, "bad chain shape");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PNCOV_ENODEVICE, "no CUDA device available (libpncov has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(PNCOV_EINVAL, "device index out of range");
+    pncov_chain* c = new (std::nothrow) pncov_chain();
+    if (!c) return fail(PNCOV_ENOMEM, "out of host memory");
+    c->device = device;
+    c->n = n;
+    c->capacity = capacity;
+    c->ld = (n + 1) / 2 * 2;
+    DeviceGuard guard(device);
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    const size_t mat = (size_t)capacity * c->ld * 8;
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->U), mat);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->V), mat);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->x), (size_t)c->ld * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->y), (size_t)c->ld * 8);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->partial), (size_t)2 * capacity * kChainSplits * 8);
+    if (e != cudaSuccess) {
+        pncov_chain_destroy(c);
+        return fail_cuda(e, "pncov_chain_create");
+    }
+    *out = c;
+    return 0;
+}
+
+PNCOV_API int pncov_chain_set(pncov_chain* c, int64_t index, const double* u, const double* v) {
+    if (!c || !u || !v) return fail(PNCOV_EINVAL, "NULL argument");
+    if (index < 0 || index >= c->capacity) return fail(PNCOV_EINVAL, "chain index out of range");
+    DeviceGuard guard(c->device);
+    PN_CUDA(cudaMemcpyAsync(c->U + index * c->ld, u, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    PN_CUDA(cudaMemcpyAsync(c->V + index * c->ld, v, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+    PN_CUDA(cudaStreamSynchronize(c->stream));  // the host vectors may be freed after the call
+    return 0;
+}
+
+PNCOV_API int pncov_chain_apply(pncov_chain* c, int64_t k, int mode, const double* x, int64_t ncols, int64_t ldx, double* y,
+                                int64_t ldy) {
+    if (!c || !x || !y) return fail(PNCOV_EINVAL, "NULL argument");
+    if (k < 0 || k > c->capacity) return fail(PNCOV_EINVAL, "chain length out of range");
+    if (mode < 0 || mode > 2) return fail(PNCOV_EINVAL, "unknown mode");
+    if (ncols < 0 || ldx < ncols || ldy < ncols) return fail(PNCOV_EINVAL, "bad operand shape");
+    DeviceGuard guard(c->device);
+    for (int64_t col = 0; col < ncols; ++col) {
+        if (ldx == 1)
+            PN_CUDA(cudaMemcpyAsync(c->x, x, (size_t)c->n * 8, cudaMemcpyHostToDevice, c->stream));
+        else
+            PN_CUDA(cudaMemcpy2DAsync(c->x, 8, x + col, (size_t)ldx * 8, 8, (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+        PN_CUDA(pn_launch_chain_apply(c->U, c->V, c->ld, c->n, (int)k, mode, c->x, c->y, c->partial, kChainSplits, c->stream));
+        if (ldy == 1)
+            PN_CUDA(cudaMemcpyAsync(y, c->y, (size_t)c->n * 8, cudaMemcpyDeviceToHost, c->stream));
+        else
+            PN_CUDA(cudaMemcpy2DAsync(y + col, (size_t)ldy * 8, c->y, 8, 8, (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    PN_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
 
 PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value) {

@@ -527,3 +527,81 @@ cudaError_t pn_launch_gram_dot_mma(const double* A, const double* B, int dpad, i
     ++g_pn_launches;
     return cudaGetLastError();
 }
+
+// ---- update chains of the matrix-based solver (SURVEY.md 8f, row N2 ii) ---------------------------------
+// linalg/solvers/matrixbased.py:751-775 keeps the posterior means / covariance factors as a lazy sum
+// of k rank-2 (u v^T + v u^T) or rank-1 (w u^T) LambdaLinearOperators; every product walks k Python
+// lambdas.  Here the vectors are rows of two device-resident (capacity, n) matrices U and V and one
+// product is two launches: all dot products (fixed split of n, partial sums to a scratch array), then
+// y = sum_i U_i a_i + V_i b_i with the coefficients reduced from the partials in a fixed order.
+namespace {
+constexpr int R2_THREADS = 256;
+
+// partial[((z * k) + i) * splits + s] = sum_{j in slice s} W_i[j] x[j],  W = (z == 0 ? U : V)
+__global__ void __launch_bounds__(R2_THREADS) chain_dots_kernel(const double* __restrict__ U, const double* __restrict__ V,
+                                                                int64_t ld, int64_t n, int k, const double* __restrict__ x,
+                                                                double* __restrict__ partial, int splits) {
+    __shared__ double red[R2_THREADS / 32];
+    const int s = blockIdx.x, i = blockIdx.y, z = blockIdx.z;
+    const double* w = (z == 0 ? U : V) + (int64_t)i * ld;
+    const int64_t chunk = (n + splits - 1) / splits;
+    const int64_t j0 = (int64_t)s * chunk, j1 = (j0 + chunk < n) ? j0 + chunk : n;
+    double acc = 0.0;
+    for (int64_t j = j0 + threadIdx.x; j < j1; j += R2_THREADS) acc = pn_fma(w[j], x[j], acc);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < R2_THREADS / 32; ++q) t += red[q];
+        partial[((int64_t)z * k + i) * splits + s] = t;
+    }
+}
+
+// mode 0: y = sum_i U_i (V_i . x) + V_i (U_i . x);  mode 1: y = sum_i V_i (U_i . x);  mode 2: y = sum_i U_i (V_i . x)
+__global__ void __launch_bounds__(R2_THREADS) chain_apply_kernel(const double* __restrict__ U, const double* __restrict__ V,
+                                                                 int64_t ld, int64_t n, int k, const double* __restrict__ partial,
+                                                                 int splits, int mode, double* __restrict__ y) {
+    extern __shared__ double coef[];  // [k] dots with U, [k] dots with V
+    for (int t = threadIdx.x; t < 2 * k; t += R2_THREADS) {
+        double sum = 0.0;
+        for (int s = 0; s < splits; ++s) sum += partial[(int64_t)t * splits + s];
+        coef[t] = sum;
+    }
+    __syncthreads();
+    const int64_t j = ((int64_t)blockIdx.x * R2_THREADS + threadIdx.x) * 2;
+    if (j >= n) return;
+    const bool pair = j + 1 < n;
+    double y0 = 0.0, y1 = 0.0;
+    for (int i = 0; i < k; ++i) {
+        const double du = coef[i], dv = coef[k + i];
+        const double* u = U + (int64_t)i * ld + j;
+        const double* v = V + (int64_t)i * ld + j;
+        if (mode != 1) {  // U_i (V_i . x)
+            y0 = pn_fma(u[0], dv, y0);
+            if (pair) y1 = pn_fma(u[1], dv, y1);
+        }
+        if (mode != 2) {  // V_i (U_i . x)
+            y0 = pn_fma(v[0], du, y0);
+            if (pair) y1 = pn_fma(v[1], du, y1);
+        }
+    }
+    y[j] = y0;
+    if (pair) y[j + 1] = y1;
+}
+}  // namespace
+
+// x, y: device vectors of length n; partial: scratch of 2 * k * splits doubles
+cudaError_t pn_launch_chain_apply(const double* U, const double* V, int64_t ld, int64_t n, int k, int mode, const double* x,
+                                  double* y, double* partial, int splits, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    if (k <= 0) return cudaMemsetAsync(y, 0, (size_t)n * 8, stream);
+    chain_dots_kernel<<<dim3((unsigned)splits, (unsigned)k, 2), R2_THREADS, 0, stream>>>(U, V, ld, n, k, x, partial, splits);
+    ++g_pn_launches;
+    const unsigned blocks = (unsigned)((n + 2 * R2_THREADS - 1) / (2 * R2_THREADS));
+    chain_apply_kernel<<<blocks, R2_THREADS, (size_t)2 * k * 8, stream>>>(U, V, ld, n, k, partial, splits, mode, y);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}

@@ -94,6 +94,10 @@ cudaError_t pn_launch_pairs_extra(const PnExtraLaunch& g, cudaStream_t stream);
 cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op, double alpha, double beta,
                               cudaStream_t stream);
 
+// update chains of the matrix-based solver (pncov_extra.cu)
+cudaError_t pn_launch_chain_apply(const double* U, const double* V, int64_t ld, int64_t n, int k, int mode, const double* x,
+                                  double* y, double* partial, int splits, cudaStream_t stream);
+
 // FP64 Cholesky (pncov_chol.cu)
 cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, double* panel, double* invd,
                            int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,

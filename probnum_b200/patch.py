@@ -429,6 +429,163 @@ def _enable_quad_prediction() -> None:
     acq.__call__ = __call__
 
 
+# ---------------------------------------------------------------------------------------------
+# the update chains of the matrix-based solver on the device
+# ---------------------------------------------------------------------------------------------
+_CHAIN_CLASSES = None
+
+
+def _make_chain_classes():
+    """``ChainOperator`` subclasses of ``probnum.linops.LinearOperator``: the sum of the first k
+    updates of an ``_lib.UpdateChain``.  A fresh update (one vector pair, no device storage yet) is a
+    chain of length one; adding it to a sum that already holds a chain extends that chain instead of
+    growing the sum (registered in the reference's own dispatch table ``linops._arithmetic._add_fns``)."""
+    global _CHAIN_CLASSES
+    if _CHAIN_CLASSES is not None:
+        return _CHAIN_CLASSES
+    import probnum  # noqa: F401, PLC0415
+    from probnum import linops  # noqa: PLC0415
+    from probnum.linops import _arithmetic as arith  # noqa: PLC0415
+    from probnum.linops._arithmetic_fallbacks import SumLinearOperator  # noqa: PLC0415
+
+    UpdateChain = _mirror._lib.UpdateChain
+
+    class ChainOperator(linops.LinearOperator):
+        MODE = UpdateChain.SYMMETRIC_RANK2
+
+        def __init__(self, n, pairs, store=None, transposed=False):
+            self._pairs = pairs      # tuple of (u, v) host vectors of length n
+            self._store = store      # shared _lib.UpdateChain holding a prefix-compatible history, or None
+            self._transposed = transposed
+            super().__init__(shape=(n, n), dtype=np.dtype(np.float64))
+
+        # -- chain bookkeeping ----------------------------------------------------------------
+        def extended(self, other: "ChainOperator") -> "ChainOperator":
+            """This chain followed by the pairs of ``other`` (a new operator; storage is shared while
+            the history is linear, which is how the solver uses it)."""
+            n = self.shape[0]
+            store = self._store
+            if store is None or len(store) != len(self._pairs):  # first merge, or a fork: own storage
+                store = UpdateChain(n)
+                for u, v in self._pairs:
+                    store.append(u, v)
+            for u, v in other._pairs:
+                store.append(u, v)
+            return type(self)(n, self._pairs + other._pairs, store, self._transposed)
+
+        def _mode(self) -> int:
+            return self.MODE
+
+        # -- LinearOperator interface --------------------------------------------------------------
+        def _matmul(self, x: np.ndarray) -> np.ndarray:
+            n, k = self.shape[0], len(self._pairs)
+            if self._store is None:
+                self._store = UpdateChain(n)
+                for u, v in self._pairs:
+                    self._store.append(u, v)
+            x = np.asarray(x, dtype=np.float64)
+            if x.ndim == 2:
+                return self._store.apply(k, self._mode(), x)
+            batch = x.shape[:-2]
+            cols = np.moveaxis(x.reshape((-1,) + x.shape[-2:]), 0, -1).reshape(n, -1)  # (n, c * B)
+            y = self._store.apply(k, self._mode(), cols).reshape(n, x.shape[-1], -1)
+            return np.moveaxis(y, -1, 0).reshape(batch + (n, x.shape[-1]))
+
+        def _factors(self):
+            U = np.stack([u for u, _ in self._pairs], axis=1)
+            V = np.stack([v for _, v in self._pairs], axis=1)
+            return U, V
+
+        def _todense(self) -> np.ndarray:
+            U, V = self._factors()
+            return U @ V.T + V @ U.T
+
+        def _transpose(self):
+            return self
+
+        def _trace(self):
+            return 2.0 * sum(float(u @ v) for u, v in self._pairs)
+
+        def _diagonal(self) -> np.ndarray:
+            U, V = self._factors()
+            return 2.0 * np.sum(U * V, axis=1)
+
+    class Rank1ChainOperator(ChainOperator):
+        """sum_i Ws_i u_i^T with pairs stored as (u_i, Ws_i)."""
+
+        def _mode(self) -> int:
+            return UpdateChain.RANK1_TRANSPOSED if self._transposed else UpdateChain.RANK1
+
+        def _todense(self) -> np.ndarray:
+            U, V = self._factors()
+            return U @ V.T if self._transposed else V @ U.T
+
+        def _transpose(self):
+            return Rank1ChainOperator(self.shape[0], self._pairs, self._store, not self._transposed)
+
+        def _trace(self):
+            return sum(float(u @ v) for u, v in self._pairs)
+
+        def _diagonal(self) -> np.ndarray:
+            U, V = self._factors()
+            return np.sum(U * V, axis=1)
+
+    def add_to_sum(total, update):
+        """SumLinearOperator + fresh update: extend the chain the sum already holds, if any."""
+        parts = list(total._summands)
+        for i, part in enumerate(parts):
+            if type(part) is type(update) and part._transposed == update._transposed:
+                parts[i] = part.extended(update)
+                return SumLinearOperator(*parts)
+        return SumLinearOperator(total, update)
+
+    def add_chains(chain, update):
+        if chain._transposed != update._transposed:
+            return SumLinearOperator(chain, update)
+        return chain.extended(update)
+
+    for cls in (ChainOperator, Rank1ChainOperator):
+        arith._add_fns[(SumLinearOperator, cls)] = add_to_sum
+        arith._add_fns[(cls, cls)] = add_chains
+    _CHAIN_CLASSES = (ChainOperator, Rank1ChainOperator)
+    return _CHAIN_CLASSES
+
+
+def enable_solver_chains() -> None:
+    """Route ``SymmetricMatrixBasedSolver._mean_update`` / ``_covariance_update``
+    (linalg/solvers/matrixbased.py:751-775) through device-resident update chains.  The solver's own
+    loop is untouched: it still writes ``aslinop(mean) + self._mean_update(u, v)``; the sum it gets
+    back holds ONE chain operator instead of k lambdas, and a product with it is two kernel launches."""
+    numpy2_compat()
+    import probnum  # noqa: F401, PLC0415
+    from probnum.linalg.solvers import matrixbased as mb  # noqa: PLC0415
+
+    cls = mb.SymmetricMatrixBasedSolver
+    if ("solver_chain", cls) in _ORIGINALS:
+        return
+    Rank2, Rank1 = _make_chain_classes()
+    _ORIGINALS[("solver_chain", cls)] = (cls.__dict__["_mean_update"], cls.__dict__["_covariance_update"])
+
+    def _vec(a, n):
+        a = np.asarray(a, dtype=np.float64)
+        return a.reshape(n).copy() if a.size == n else None
+
+    def _mean_update(self, u, v):
+        uu, vv = _vec(u, self.n), _vec(v, self.n)
+        if uu is None or vv is None:  # several right-hand sides: not a vector pair
+            return _ORIGINALS[("solver_chain", cls)][0](self, u, v)
+        return Rank2(self.n, ((uu, vv),))
+
+    def _covariance_update(self, u, Ws):
+        uu, ww = _vec(u, self.n), _vec(Ws, self.n)
+        if uu is None or ww is None:
+            return _ORIGINALS[("solver_chain", cls)][1](self, u, Ws)
+        return Rank1(self.n, ((uu, ww),))
+
+    cls._mean_update = _mean_update
+    cls._covariance_update = _covariance_update
+
+
 def disable() -> None:
     """Undo :func:`enable`."""
     global _SHARDED, _LOCAL_FACTORY
@@ -438,6 +595,10 @@ def disable() -> None:
         factor, solve = _ORIGINALS.pop(key)
         key[1].compute_gram_cho_factor = factor
         key[1].gram_cho_solve = solve
+    for key in [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "solver_chain"]:
+        mean_update, covariance_update = _ORIGINALS.pop(key)
+        key[1]._mean_update = mean_update
+        key[1]._covariance_update = covariance_update
     for key in [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "quad_predict"]:
         orig = _ORIGINALS.pop(key)
         setattr(key[1], "predict_integrand" if isinstance(orig, staticmethod) else "__call__", orig)

@@ -265,6 +265,110 @@ def test_prediction_path_on_the_device_matches_cpu_run():
     np.testing.assert_allclose(acq_gpu, acq_cpu, rtol=1e-5, atol=0)
 
 
+class _HostChain:
+    """Host stand-in for _lib.UpdateChain (same interface): lets the CPU suite check the plumbing."""
+
+    SYMMETRIC_RANK2, RANK1, RANK1_TRANSPOSED = 0, 1, 2
+    created = 0
+
+    def __init__(self, n, capacity=64, device=None):
+        self.n, self.pairs = n, []
+        _HostChain.created += 1
+
+    def __len__(self):
+        return len(self.pairs)
+
+    def append(self, u, v):
+        self.pairs.append((u.copy(), v.copy()))
+        return len(self.pairs)
+
+    def apply(self, k, mode, x):
+        y = np.zeros_like(x)
+        for u, v in self.pairs[:k]:
+            if mode != 1:
+                y += np.outer(u, v @ x)
+            if mode != 2:
+                y += np.outer(v, u @ x)
+        return y
+
+
+def _solver_run(A, b, maxiter):
+    iterates = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        x, Ahat, Ainv, info = pn.linalg.problinsolve(
+            A, b, maxiter=maxiter, callback=lambda **kw: iterates.append(kw["xk"].mean.copy()))
+    return x, Ahat, Ainv, info, iterates
+
+
+def test_solver_chains_plumbing_on_the_host(monkeypatch):
+    """SURVEY 8f N2 (ii), host logic: with enable_solver_chains() the sums the solver builds hold ONE
+    chain operator (not k lambdas), four chains exist per solve, iterates and posterior operators are
+    those of the unmodified solver, and disable() restores the reference methods."""
+    from probnum.linalg.solvers import matrixbased as mb
+    from probnum_b200 import _lib
+
+    monkeypatch.setattr(_lib, "UpdateChain", _HostChain)
+    monkeypatch.setattr(pb_patch, "_CHAIN_CLASSES", None)
+    rng = np.random.default_rng(0)
+    n = 120
+    B = rng.normal(size=(n, n))
+    A, b = B @ B.T / n + np.eye(n), rng.normal(size=n)
+    x0, A0, Ainv0, info0, it0 = _solver_run(A, b, 30)
+    originals = (mb.SymmetricMatrixBasedSolver._mean_update, mb.SymmetricMatrixBasedSolver._covariance_update)
+    _HostChain.created = 0
+    pb_patch.enable_solver_chains()
+    try:
+        x1, A1, Ainv1, info1, it1 = _solver_run(A, b, 30)
+        names = [type(s).__name__ for s in Ainv1.mean._summands]
+        dense = Ainv1.mean.todense()
+        prod = Ainv1.mean @ np.eye(n)[:, :3]
+        stacked = Ainv1.mean @ np.stack([np.eye(n)[:, :2], np.eye(n)[:, 2:4]])
+    finally:
+        pb_patch.disable()
+    assert (mb.SymmetricMatrixBasedSolver._mean_update, mb.SymmetricMatrixBasedSolver._covariance_update) == originals
+    assert info1["iter"] == info0["iter"] > 3 and _HostChain.created == 4
+    assert names.count("ChainOperator") == 1 and len(names) == 2
+    for a, c in zip(it0, it1):
+        np.testing.assert_allclose(c, a, rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(dense, Ainv0.mean.todense(), rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(prod, dense[:, :3], rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(stacked[1], dense[:, 2:4], rtol=1e-12, atol=1e-13)
+    pb_patch._CHAIN_CLASSES = None  # the classes above captured the host stand-in
+
+
+@pytest.mark.gpu
+def test_solver_chains_on_the_device_match_the_reference_solver(patched):
+    """problinsolve on k.linop(X) + 1e-3 I with the update chains in HBM
+    (pncov_chain_apply) against the same solve with the reference's lambda chains."""
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(3)
+    n = 1500
+    X, y = rng.normal(size=(n, 3)), rng.normal(size=n)
+    k = cf.ExpQuad((3,), lengthscales=0.4)
+
+    def run():
+        return _solver_run(k.linop(X) + 1e-3 * pn.linops.Identity(n), y, 25)
+
+    x0, _, Ainv0, info0, it0 = run()
+    pb_patch.enable_solver_chains()
+    launches = _lib.launch_count()
+    try:
+        x1, _, Ainv1, info1, it1 = run()
+        v = rng.normal(size=(n, 2))
+        prod1 = Ainv1.mean @ v
+    finally:
+        pb_patch.disable()
+        pb_patch.enable()
+    assert info1["iter"] == info0["iter"] == 25
+    assert _lib.launch_count() - launches > 25 * 8  # products with the four chains, two launches each
+    scale = max(np.abs(a).max() for a in it0)
+    for a, c in zip(it0, it1):
+        np.testing.assert_allclose(c, a, rtol=0, atol=1e-9 * scale)
+    np.testing.assert_allclose(prod1, Ainv0.mean @ v, rtol=1e-9, atol=1e-9 * np.abs(v).max())
+
+
 def test_evaluate_hook_is_restored():
     before = {cls: cls.__dict__["_evaluate"] for cls in (cf.ExpQuad, cf.Matern, cf.RatQuad)}
     pb_patch.enable()

@@ -198,3 +198,29 @@ def test_linear_gram_on_dmma_is_symmetric_and_matches_the_oracle():
             assert np.all(np.abs(K - ref) <= tol + 1e-12)
             Kc = k.matrix(x, y)
             np.testing.assert_allclose(Kc, xo.gram(spec, x, y), rtol=1e-11, atol=1e-11)
+
+
+def test_update_chain_matches_numpy():
+    """pncov_chain_* (SURVEY 8f N2 ii): sums of rank-2 / rank-1 updates applied from device-resident
+    vector pairs; growth past the initial capacity; odd n; several columns."""
+    from probnum_b200 import _lib
+
+    rng = np.random.default_rng(21)
+    for n, pairs in ((1001, 5), (4096, 70)):
+        chain = _lib.UpdateChain(n, capacity=4 if pairs < 10 else 64)
+        U, V = rng.normal(size=(n, pairs)), rng.normal(size=(n, pairs))
+        for i in range(pairs):
+            assert chain.append(U[:, i], V[:, i]) == i + 1
+        x = rng.normal(size=(n, 3))
+        for k in (0, 1, pairs // 2, pairs):
+            Uk, Vk = U[:, :k], V[:, :k]
+            refs = {0: Uk @ (Vk.T @ x) + Vk @ (Uk.T @ x), 1: Vk @ (Uk.T @ x), 2: Uk @ (Vk.T @ x)}
+            bound = np.abs(Uk) @ (np.abs(Vk).T @ np.abs(x)) + np.abs(Vk) @ (np.abs(Uk).T @ np.abs(x))
+            for mode, ref in refs.items():
+                y = chain.apply(k, mode, x)
+                assert np.all(np.abs(y - ref) <= 1e-12 * bound + 1e-300), (n, k, mode)
+        with pytest.raises(ValueError):
+            chain.apply(pairs + 1, 0, x)
+        with pytest.raises(ValueError):
+            chain.apply(1, 0, x[:-1])
+        chain.close()
