@@ -1341,14 +1341,14 @@ PNCOV_API int pncov_chol_solve_gram(pncov_chol* c, pncov_handle* h, int64_t nvec
         }
         if ((e = cudaEventRecord(c->ev0, s)) != cudaSuccess) return e;
         if (fwd && nvec > 0 &&
-            (e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(vd), 128, 1, s)) != cudaSuccess)
+            (e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(vd), 128, 1, s, c->side, c->ev_panel, c->ev_diag)) != cudaSuccess)
             return e;
         for (int64_t r0 = 0; r0 < m; r0 += chunk) {
             const int64_t mc = std::min<int64_t>(chunk, m - r0), mcpad = (mc + 127) / 128 * 128;
             // padded columns must be exact zeros (they meet the identity block of the padded factor)
             if (npad != n && (e = cudaMemsetAsync(Z, 0, (size_t)mcpad * npad * 8, s)) != cudaSuccess) return e;
             if ((e = launch_gram_any(h, true, r0, mc, Z, npad, s)) != cudaSuccess) return e;  // rows: prediction points
-            if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, fwd ? 1 : 0, s)) != cudaSuccess) return e;
+            if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, fwd ? 1 : 0, s, c->side, c->ev_panel, c->ev_diag)) != cudaSuccess) return e;
             if (fwd) {  // rows of Y = (L^-1 g_j)^T: quad = |y_j|^2, dots = (L^-1 v_t) . y_j
                 if ((e = pn_chol_rowdots(static_cast<double*>(Y), static_cast<double*>(Y), npad, n, mc, static_cast<double*>(vd),
                                          (int)nvec, static_cast<double*>(qd) + r0, static_cast<double*>(dd) + r0, m, s)) != cudaSuccess)

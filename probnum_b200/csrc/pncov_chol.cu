@@ -759,7 +759,8 @@ cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, dou
 // transposed layout of the kernel above); out: Z = the solutions of L L^T w = z for every row, Y scratch.
 // forward_only: stop after L y = z; the solutions y are the rows of Y (Z is clobbered).
 cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
-                               int forward_only, cudaStream_t stream) {
+                               int forward_only, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_main,
+                               cudaEvent_t ev_side) {
     cudaError_t err;
     const size_t smem = sizeof(double) * (2 * CB * CLD + 2 * (CTN * CLD > CK * WLDN ? CTN * CLD : CK * WLDN));
     if ((err = cudaFuncSetAttribute(chol_wide_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
@@ -767,56 +768,63 @@ cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd
     const int64_t T = npad / CB;
     const unsigned mt = (unsigned)(mpad / CB);
     if (mt > 65535) return cudaErrorInvalidConfiguration;
-    for (int64_t k = 0; k < T; ++k) {  // L Y = Z
-        ChWide d{};
-        d.A = Z + k * CB;
-        d.lda = npad;
-        d.B = invd + k * CB * CB;
-        d.ldb = CB;
-        d.C = Y + k * CB;
-        d.ldc = npad;
-        d.subtract = 0;
-        chol_wide_gemm_kernel<false><<<dim3(CB / CTN, mt), CG_THREADS, smem, stream>>>(d);
+    auto gemm = [&](bool bkn, const double* A, const double* B, int64_t ldb, double* C, int subtract, int64_t cols,
+                    cudaStream_t st) {
+        ChWide p{};
+        p.A = A;
+        p.lda = npad;
+        p.B = B;
+        p.ldb = ldb;
+        p.C = C;
+        p.ldc = npad;
+        p.subtract = subtract;
+        const dim3 grid((unsigned)(cols / CTN), mt);
+        if (bkn) chol_wide_gemm_kernel<true><<<grid, CG_THREADS, smem, st>>>(p);
+        else chol_wide_gemm_kernel<false><<<grid, CG_THREADS, smem, st>>>(p);
         ++g_pn_launches;
-        const int64_t rest = npad - (k + 1) * CB;
-        if (rest > 0) {
-            ChWide u{};
-            u.A = Y + k * CB;
-            u.lda = npad;
-            u.B = M + (k + 1) * CB * npad + k * CB;  // L[i, k] for the block rows i > k
-            u.ldb = npad;
-            u.C = Z + (k + 1) * CB;
-            u.ldc = npad;
-            u.subtract = 1;
-            chol_wide_gemm_kernel<false><<<dim3((unsigned)(rest / CTN), mt), CG_THREADS, smem, stream>>>(u);
-            ++g_pn_launches;
-        }
+    };
+    // Look-ahead.  Step k of a pass is: the product with the inverse diagonal block ("diag", 2 x mt CTAs,
+    // latency-bound), the update of the NEXT block ("head", same size) and the update of everything
+    // beyond it ("rest", the bulk).  diag and head run on the high-priority side stream under the rest of
+    // the previous step, which stays alone on the critical path:
+    //   side:  diag_0 | head_0  diag_1 | head_1  diag_2 | ...     head_k waits for rest_{k-1} (same block)
+    //   main:         | rest_0         | rest_1         | ...     rest_k waits for diag_k
+    // head_k and rest_k touch different blocks; consecutive rests share blocks and stay in stream order.
+    if ((err = cudaEventRecord(ev_main, stream)) != cudaSuccess) return err;  // the right-hand sides are in place
+    if ((err = cudaStreamWaitEvent(side, ev_main, 0)) != cudaSuccess) return err;
+    gemm(false, Z, invd, CB, Y, 0, CB, side);  // diag_0: Y_0 = Z_0 inv(L_00)^T
+    if ((err = cudaEventRecord(ev_side, side)) != cudaSuccess) return err;
+    for (int64_t k = 0; k + 1 < T; ++k) {  // L Y = Z
+        if ((err = cudaStreamWaitEvent(stream, ev_side, 0)) != cudaSuccess) return err;  // Y_k
+        if (k > 0 && (err = cudaStreamWaitEvent(side, ev_main, 0)) != cudaSuccess) return err;  // rest_{k-1}
+        const double* Yk = Y + k * CB;
+        const double* Lk = M + (k + 1) * CB * npad + k * CB;  // L[i, k] for the block rows i > k
+        gemm(false, Yk, Lk, npad, Z + (k + 1) * CB, 1, CB, side);                                      // head_k
+        gemm(false, Z + (k + 1) * CB, invd + (k + 1) * CB * CB, CB, Y + (k + 1) * CB, 0, CB, side);  // diag_{k+1}
+        if ((err = cudaEventRecord(ev_side, side)) != cudaSuccess) return err;
+        const int64_t rest = npad - (k + 2) * CB;
+        if (rest > 0) gemm(false, Yk, Lk + CB * npad, npad, Z + (k + 2) * CB, 1, rest, stream);      // rest_k
+        if ((err = cudaEventRecord(ev_main, stream)) != cudaSuccess) return err;
     }
+    if ((err = cudaStreamWaitEvent(stream, ev_side, 0)) != cudaSuccess) return err;
     if (forward_only) return cudaGetLastError();
-    for (int64_t k = T - 1; k >= 0; --k) {  // L^T X = Y
-        ChWide d{};
-        d.A = Y + k * CB;
-        d.lda = npad;
-        d.B = invd + k * CB * CB;
-        d.ldb = CB;
-        d.C = Z + k * CB;
-        d.ldc = npad;
-        d.subtract = 0;
-        chol_wide_gemm_kernel<true><<<dim3(CB / CTN, mt), CG_THREADS, smem, stream>>>(d);
-        ++g_pn_launches;
-        if (k > 0) {
-            ChWide u{};
-            u.A = Z + k * CB;
-            u.lda = npad;
-            u.B = M + k * CB * npad;  // L[k, j] for the block columns j < k
-            u.ldb = npad;
-            u.C = Y;
-            u.ldc = npad;
-            u.subtract = 1;
-            chol_wide_gemm_kernel<true><<<dim3((unsigned)(k * CB / CTN), mt), CG_THREADS, smem, stream>>>(u);
-            ++g_pn_launches;
-        }
+    // L^T X = Y, blocks from the last to the first; here main has just waited for the side stream
+    if ((err = cudaEventRecord(ev_main, stream)) != cudaSuccess) return err;
+    if ((err = cudaStreamWaitEvent(side, ev_main, 0)) != cudaSuccess) return err;
+    gemm(true, Y + (T - 1) * CB, invd + (T - 1) * CB * CB, CB, Z + (T - 1) * CB, 0, CB, side);  // X_{T-1}
+    if ((err = cudaEventRecord(ev_side, side)) != cudaSuccess) return err;
+    for (int64_t k = T - 1; k > 0; --k) {
+        if ((err = cudaStreamWaitEvent(stream, ev_side, 0)) != cudaSuccess) return err;  // X_k
+        if (k < T - 1 && (err = cudaStreamWaitEvent(side, ev_main, 0)) != cudaSuccess) return err;  // rest_{k+1}
+        const double* Xk = Z + k * CB;
+        const double* Lk = M + k * CB * npad;  // L[k, j] for the block columns j < k
+        gemm(true, Xk, Lk + (k - 1) * CB, npad, Y + (k - 1) * CB, 1, CB, side);                            // head_k
+        gemm(true, Y + (k - 1) * CB, invd + (k - 1) * CB * CB, CB, Z + (k - 1) * CB, 0, CB, side);       // diag_{k-1}
+        if ((err = cudaEventRecord(ev_side, side)) != cudaSuccess) return err;
+        if (k > 1) gemm(true, Xk, Lk, npad, Y, 1, (k - 1) * CB, stream);                                   // rest_k
+        if ((err = cudaEventRecord(ev_main, stream)) != cudaSuccess) return err;
     }
+    if ((err = cudaStreamWaitEvent(stream, ev_side, 0)) != cudaSuccess) return err;
     return cudaGetLastError();
 }
 

@@ -105,7 +105,8 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
 cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream);
 // many right-hand sides, one per ROW of Z (mpad x npad); Y: scratch of the same shape
 cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
-                               int forward_only, cudaStream_t stream);
+                               int forward_only, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_main,
+                               cudaEvent_t ev_side);
 cudaError_t pn_chol_rowdots(const double* W, const double* G, int64_t ld, int64_t n, int64_t rows, const double* vecs,
                             int nvec, double* quad, double* dots, int64_t ldd, cudaStream_t stream);
 
