@@ -586,8 +586,16 @@ def enable_solver_chains() -> None:
     cls._covariance_update = _covariance_update
 
 
+def enable_all(sharded: Optional[bool] = None) -> None:
+    """:func:`enable` plus the opt-in rows of SURVEY.md 8f: the device Cholesky and prediction path of
+    the BQ belief update (N1, N4) and the solver's update chains (N2 ii)."""
+    enable(sharded)
+    enable_quad_cholesky("pncov")
+    enable_solver_chains()
+
+
 def disable() -> None:
-    """Undo :func:`enable`."""
+    """Undo :func:`enable`, :func:`enable_quad_cholesky` and :func:`enable_solver_chains`."""
     global _SHARDED, _LOCAL_FACTORY
     _SHARDED, _LOCAL_FACTORY = None, None
     quad = [k for k in _ORIGINALS if isinstance(k, tuple) and k[0] == "quad"]

@@ -265,6 +265,28 @@ def test_prediction_path_on_the_device_matches_cpu_run():
     np.testing.assert_allclose(acq_gpu, acq_cpu, rtol=1e-5, atol=0)
 
 
+def test_enable_all_and_disable_restore_every_patched_method():
+    from probnum.linalg.solvers import matrixbased as mb
+    from probnum.quad.solvers.acquisition_functions import _integral_variance_reduction as ivr
+    from probnum.quad.solvers.belief_updates import _belief_update as bu
+    from probnum.quad.solvers.belief_updates import _standard_update as su
+
+    def snapshot():
+        return (cf.ExpQuad._evaluate_matrix, cf.Matern._evaluate_linop, cf.Linear._evaluate_matrix,
+                bu.BQBeliefUpdate.__dict__["compute_gram_cho_factor"], bu.BQBeliefUpdate.__dict__["gram_cho_solve"],
+                su.BQStandardBeliefUpdate.__dict__["predict_integrand"], ivr.IntegralVarianceReduction.__dict__["__call__"],
+                mb.SymmetricMatrixBasedSolver.__dict__["_mean_update"],
+                mb.SymmetricMatrixBasedSolver.__dict__["_covariance_update"])
+
+    before = snapshot()
+    pb_patch.enable_all()
+    during = snapshot()
+    pb_patch.disable()
+    assert all(a is not b for a, b in zip(before, during))
+    assert all(a is b for a, b in zip(before, snapshot()))
+    assert not pb_patch.enabled()
+
+
 class _HostChain:
     """Host stand-in for _lib.UpdateChain (same interface): lets the CPU suite check the plumbing."""
 
