@@ -1269,11 +1269,50 @@ PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitt
     return 0;
 }
 
+constexpr int64_t kWideSolveMinRhs = 9;  // more than one 8-column sweep: the transposed DMMA substitution is faster
+
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx) {
     if (!c || !b || !x) return fail(PNCOV_EINVAL, "NULL argument");
     if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");
     if (nrhs < 0 || ldb < nrhs || ldx < nrhs) return fail(PNCOV_EINVAL, "bad right-hand-side shape");
     DeviceGuard guard(c->device);
+    if (nrhs >= kWideSolveMinRhs) {
+        // many right-hand sides: transposed on the device and solved by the blocked DMMA substitution of
+        // the prediction path (pn_chol_solve_wide), in column chunks of at most 512 MiB per buffer
+        const int64_t n = c->n, npad = c->npad;
+        int64_t chunk = std::max<int64_t>(128, ((int64_t)(512ll << 20) / (npad * 8)) / 128 * 128);
+        chunk = std::min<int64_t>(chunk, (nrhs + 127) / 128 * 128);
+        void *B = nullptr, *Z = nullptr, *Y = nullptr;
+        cudaStream_t s = c->stream;
+        auto run = [&]() -> cudaError_t {
+            cudaError_t e;
+            if ((e = pn_dev_alloc(&B, (size_t)n * chunk * 8, s)) != cudaSuccess) return e;
+            if ((e = pn_dev_alloc(&Z, (size_t)chunk * npad * 8, s)) != cudaSuccess) return e;
+            if ((e = pn_dev_alloc(&Y, (size_t)chunk * npad * 8, s)) != cudaSuccess) return e;
+            for (int64_t c0 = 0; c0 < nrhs; c0 += chunk) {
+                const int64_t mc = std::min<int64_t>(chunk, nrhs - c0), mcpad = (mc + 127) / 128 * 128;
+                if ((e = cudaMemcpy2DAsync(B, (size_t)mc * 8, b + c0, (size_t)ldb * 8, (size_t)mc * 8, (size_t)n,
+                                           cudaMemcpyHostToDevice, s)) != cudaSuccess)
+                    return e;
+                if ((e = cudaMemsetAsync(Z, 0, (size_t)mcpad * npad * 8, s)) != cudaSuccess) return e;
+                if ((e = pn_chol_transpose(static_cast<double*>(B), mc, n, mc, static_cast<double*>(Z), npad, s)) != cudaSuccess) return e;
+                if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, 0, s,
+                                            c->side, c->ev_panel, c->ev_diag)) != cudaSuccess)
+                    return e;
+                if ((e = pn_chol_transpose(static_cast<double*>(Z), npad, mc, n, static_cast<double*>(B), mc, s)) != cudaSuccess) return e;
+                if ((e = cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, B, (size_t)mc * 8, (size_t)mc * 8, (size_t)n,
+                                           cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+                    return e;
+            }
+            return cudaStreamSynchronize(s);
+        };
+        const cudaError_t e = run();
+        pn_dev_free(B, s);
+        pn_dev_free(Z, s);
+        pn_dev_free(Y, s);
+        if (e != cudaSuccess) return fail_cuda(e, "pncov_chol_solve (wide)");
+        return 0;
+    }
     for (int64_t c0 = 0; c0 < nrhs; c0 += 8) {
         const int k = (int)std::min<int64_t>(8, nrhs - c0);
         if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->rhs, 0, (size_t)c->npad * k * 8, c->stream));

@@ -828,6 +828,37 @@ cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd
     return cudaGetLastError();
 }
 
+// dst (cols, rows; ldd) = src (rows, cols; lds)^T, 32 x 32 tiles through shared memory
+namespace {
+__global__ void __launch_bounds__(256) chol_transpose_kernel(const double* __restrict__ src, int64_t lds, int64_t rows,
+                                                             int64_t cols, double* __restrict__ dst, int64_t ldd) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * i][tx] = src[r * lds + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t c = c0 + ty + 8 * i, r = r0 + tx;
+        if (r < rows && c < cols) dst[c * ldd + r] = tile[tx][ty + 8 * i];
+    }
+}
+}  // namespace
+
+cudaError_t pn_chol_transpose(const double* src, int64_t lds, int64_t rows, int64_t cols, double* dst, int64_t ldd,
+                              cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return cudaSuccess;
+    const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+    chol_transpose_kernel<<<grid, 256, 0, stream>>>(src, lds, rows, cols, dst, ldd);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
 cudaError_t pn_chol_rowdots(const double* W, const double* G, int64_t ld, int64_t n, int64_t rows, const double* vecs,
                             int nvec, double* quad, double* dots, int64_t ldd, cudaStream_t stream) {
     if (rows <= 0) return cudaSuccess;
