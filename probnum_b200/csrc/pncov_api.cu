@@ -1269,7 +1269,8 @@ PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitt
     return 0;
 }
 
-constexpr int64_t kWideSolveMinRhs = 9;  // more than one 8-column sweep: the transposed DMMA substitution is faster
+constexpr int64_t kWideSolveMinRhs = 4;  // n = 16384: sweeps take 6.7 / 7.9 / 17.6 ms for 1 / 2 / 8 columns, the
+                                         // transposed DMMA substitution ~10 ms for anything up to 128 (tools/solve_width_probe.py)
 
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx) {
     if (!c || !b || !x) return fail(PNCOV_EINVAL, "NULL argument");
@@ -1291,18 +1292,21 @@ PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int
             if ((e = pn_dev_alloc(&Y, (size_t)chunk * npad * 8, s)) != cudaSuccess) return e;
             for (int64_t c0 = 0; c0 < nrhs; c0 += chunk) {
                 const int64_t mc = std::min<int64_t>(chunk, nrhs - c0), mcpad = (mc + 127) / 128 * 128;
-                if ((e = cudaMemcpy2DAsync(B, (size_t)mc * 8, b + c0, (size_t)ldb * 8, (size_t)mc * 8, (size_t)n,
-                                           cudaMemcpyHostToDevice, s)) != cudaSuccess)
-                    return e;
+                // contiguous operands go as one linear copy (pitched copies of short rows from pageable memory are slow)
+                if (ldb == mc) e = cudaMemcpyAsync(B, b, (size_t)n * mc * 8, cudaMemcpyHostToDevice, s);
+                else e = cudaMemcpy2DAsync(B, (size_t)mc * 8, b + c0, (size_t)ldb * 8, (size_t)mc * 8, (size_t)n,
+                                           cudaMemcpyHostToDevice, s);
+                if (e != cudaSuccess) return e;
                 if ((e = cudaMemsetAsync(Z, 0, (size_t)mcpad * npad * 8, s)) != cudaSuccess) return e;
                 if ((e = pn_chol_transpose(static_cast<double*>(B), mc, n, mc, static_cast<double*>(Z), npad, s)) != cudaSuccess) return e;
                 if ((e = pn_chol_solve_wide(c->M, npad, c->invd, static_cast<double*>(Z), static_cast<double*>(Y), mcpad, 0, s,
                                             c->side, c->ev_panel, c->ev_diag)) != cudaSuccess)
                     return e;
                 if ((e = pn_chol_transpose(static_cast<double*>(Z), npad, mc, n, static_cast<double*>(B), mc, s)) != cudaSuccess) return e;
-                if ((e = cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, B, (size_t)mc * 8, (size_t)mc * 8, (size_t)n,
-                                           cudaMemcpyDeviceToHost, s)) != cudaSuccess)
-                    return e;
+                if (ldx == mc) e = cudaMemcpyAsync(x, B, (size_t)n * mc * 8, cudaMemcpyDeviceToHost, s);
+                else e = cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, B, (size_t)mc * 8, (size_t)mc * 8, (size_t)n,
+                                           cudaMemcpyDeviceToHost, s);
+                if (e != cudaSuccess) return e;
             }
             return cudaStreamSynchronize(s);
         };
