@@ -8,13 +8,25 @@ One "step" is one pass of the hot path over BASELINE.json configs[1]: the dense 
 Gram matrices of Matern-5/2 AND RatQuad over N = 32768 points in d = 3 (2 * N^2 entries,
 17.2 GB written).  With G > 1 GPUs (launched by torchrun, one rank per GPU) the units are
 independent point clouds: each rank builds the two Gram matrices of its own 32768-point cloud
-(seeded per rank) -- weak scaling, identical per-GPU work, no collective on the data path.  The JSON line also carries, under "extra", the single-kernel numbers (ExpQuad,
-Matern-5/2, RatQuad) and the matrix-free K.v of configs[2] (N = 2^20, d = 8), which IS
-row-sharded with an NCCL all-gather of the result vector.
+(seeded per rank) -- weak scaling, identical per-GPU work, no collective on the data path.  The
+JSON line also carries, under "extra": the single-kernel numbers (ExpQuad, Matern-5/2, RatQuad);
+ONE Gram matrix row-sharded over the ranks (`gram_row_sharded`, device-resident and host-assembled);
+the matrix-free K.v of configs[2] (N = 2^20, d = 8; K = 1 normal v and K = 8 uniform V), which IS
+sharded with one NCCL collective per product; `problinsolve` (configs[3]) and
+`bayesquad_from_data` (configs[4]) through the unmodified ProbNum with the drop-in installed; and
+configs[0] (ExpQuad Gram N = 1000, d = 10 and the asv shape d = 100).
 
 Timing: CUDA events on the stream the kernels are launched on, W warm-up steps, exactly K timed
 steps between barrier + synchronize, max over ranks.  Every step writes 8.6 GB per kernel, far
 more than the 126 MB L2, so no L2 flush is needed between iterations.
+
+Outside the timed region the run CHECKS what it timed and fails (exit code 1, "parity_failed" in the
+line) when a check does not hold: sampled rows of the K.v results -- at every --gpus N, on the
+vector the collective produced -- against the reference's own rows (baseline/_ref,
+`k.matrix(X[rows], X) @ v`), criterion |dy_i| <= 1e-12 (|K||v|)_i; sampled rows of the row-sharded
+Gram (rtol = atol = 1e-12); the iterate of `problinsolve` on N ranks against the one-rank run and
+against the unmodified reference at the largest size the reference finishes in seconds; and
+`bayesquad_from_data` against the unmodified reference likewise.
 """
 
 from __future__ import annotations
@@ -26,6 +38,7 @@ import subprocess
 import sys
 import threading
 import time
+import warnings
 
 import numpy as np
 
@@ -39,6 +52,7 @@ N_MV = 1 << 20
 D_MV = 8
 METRIC = "gram_entries_per_s"
 UNIT = "entries/s"
+PARITY_ROWS = 64
 
 
 def parse_args():
@@ -47,12 +61,25 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-matvec", action="store_true", help="skip the K.v extra (configs[2])")
+    ap.add_argument("--no-matvec", action="store_true", help="skip the K.v extras (configs[2])")
+    ap.add_argument("--no-callers", action="store_true", help="skip configs[0], [3], [4] and the row-sharded Gram")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--n", type=int, default=N_GRAM, help="Gram size (default: BASELINE config)")
     ap.add_argument("--n-mv", type=int, default=N_MV)
+    ap.add_argument("--n-solve", type=int, default=65536)
+    ap.add_argument("--n-bq", type=int, default=16384)
     return ap.parse_args()
+
+
+def workload_config(n: int, world: int) -> dict:
+    """The `config` object: identical in both arms for the same (n, world)."""
+    return {
+        "workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={D_GRAM}, float64 (BASELINE configs[1])"
+                    + ("" if world == 1 else f"; {world} independent point clouds, one per rank/GPU"),
+        "n": n, "d": D_GRAM, "kernels": ["Matern(nu=2.5)", "RatQuad"], "units_per_step": f"2*N^2*{world} entries",
+        "inputs": "default_rng(42 + 1000 rank).normal(size=(N, d))",
+    }
 
 
 def measured_peaks():
@@ -80,7 +107,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.device_index)],
+                 "-lms", "50", "-i", str(self.device_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -124,7 +151,7 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the oracle (NumPy restatement of the reference algorithm)
+# the unmodified reference (baseline/_ref) and the oracle port
 # --------------------------------------------------------------------------------------------
 def _oracle_specs():
     from oracle import covfuncs_oracle as orc  # noqa: PLC0415
@@ -133,9 +160,10 @@ def _oracle_specs():
             orc.KernelSpec("ratquad", (D_GRAM,), 1.0, alpha=1.0)]
 
 
-def _import_reference():
+def _import_reference(package: bool = False):
     """The unmodified reference (pip-installed into baseline/_ref, which travels to the GPU box),
-    or None.  Only the four NumPy-2 aliases of SURVEY.md 8c are added before the import."""
+    or None.  Only the four NumPy-2 aliases of SURVEY.md 8c are added before the import.
+    ``package``: return the whole ``probnum`` package instead of ``probnum.randprocs.covfuncs``."""
     ref = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref, "probnum")):
         return None
@@ -147,12 +175,11 @@ def _import_reference():
         if not hasattr(np, name):
             setattr(np, name, val)
     try:
-        import warnings  # noqa: PLC0415
-
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
+            import probnum  # noqa: PLC0415
             from probnum.randprocs import covfuncs  # noqa: PLC0415
-        return covfuncs
+        return probnum if package else covfuncs
     except Exception:  # noqa: BLE001 - any import problem means "not available"
         return None
 
@@ -207,6 +234,7 @@ def run_reference(args):
     import multiprocessing as mp  # noqa: PLC0415
 
     n = args.n
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, 64))
     rows_per_worker = 256
@@ -231,13 +259,47 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={D_GRAM}, float64 (BASELINE configs[1])",
-                   "sample": sample},
+        "config": workload_config(n, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# --------------------------------------------------------------------------------------------
+# parity checks (outside every timed region)
+# --------------------------------------------------------------------------------------------
+def reference_rows(kind: str, d: int, X: np.ndarray, rows: np.ndarray, **params):
+    """(K[rows, :], source) from the unmodified reference's `k.matrix(X[rows], X)`; the oracle port
+    only when baseline/_ref is missing."""
+    cf = _import_reference()
+    blocks = []
+    if cf is not None:
+        k = {"expquad": lambda: cf.ExpQuad((d,), **params), "matern": lambda: cf.Matern((d,), **params),
+             "ratquad": lambda: cf.RatQuad((d,), **params)}[kind]()
+        for r0 in range(0, len(rows), 8):  # bounds the reference's (rows, N, d) temporary
+            blocks.append(k.matrix(X[rows[r0:r0 + 8]], X))
+        return np.concatenate(blocks, axis=0), "probnum (baseline/_ref) k.matrix(X[rows], X)"
+    from oracle import covfuncs_oracle as orc  # noqa: PLC0415
+
+    spec = orc.KernelSpec(kind, (d,), params.get("lengthscales", params.get("lengthscale", 1.0)),
+                          nu=params.get("nu", 1.5), alpha=params.get("alpha", 1.0))
+    return orc.gram(spec, X[rows], X, row_block=8), "oracle port (baseline/_ref missing)"
+
+
+def matvec_parity(X: np.ndarray, V: np.ndarray, Y: np.ndarray, seed: int = 5) -> dict:
+    """Sampled rows of Y = K(X, X) @ V against the reference: |dy_i| <= 1e-12 (|K||v|)_i
+    (the reference is `k.matrix(X[rows], X) @ V`)."""
+    n = X.shape[0]
+    rows = np.sort(np.random.default_rng(seed).choice(n, size=min(PARITY_ROWS, n), replace=False))
+    Kr, source = reference_rows("expquad", X.shape[1], X, rows)
+    y_ref = Kr @ V
+    bound = np.abs(Kr) @ np.abs(V)
+    ratio = np.abs(Y[rows] - y_ref) / (1e-12 * bound)
+    finite = bool(np.all(np.isfinite(Y)))
+    return {"rows": int(len(rows)), "max_ratio": float(ratio.max()), "criterion": "|dy_i| <= 1e-12 (|K||v|)_i",
+            "reference": source, "ok": bool(finite and ratio.max() <= 1.0)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -263,37 +325,434 @@ def _bind_to_gpu_numa_node(index: int) -> None:
         print(f"[bench] no NUMA binding for GPU {index}: {exc}", file=sys.stderr)
 
 
-def run_ours(args):
-    import torch  # noqa: PLC0415
-    import torch.distributed as dist  # noqa: PLC0415
+class Ctx:
+    """What every leg of the GPU arm needs."""
 
+    def __init__(self):
+        import torch  # noqa: PLC0415
+        import torch.distributed as dist  # noqa: PLC0415
+
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device: probnum_b200 has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            _bind_to_gpu_numa_node(self.local_rank)
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self.failures = []
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_ok(self, ok: bool) -> bool:
+        return self.max_over_ranks(0.0 if ok else 1.0) == 0.0
+
+    def check(self, name: str, result: dict) -> dict:
+        if not result.get("ok", False):
+            self.failures.append(name)
+        return result
+
+
+def leg_matvec(ctx: Ctx, args, extra: dict) -> int:
+    """configs[2]: matrix-free ExpQuad K.v, N = 2^20, d = 8.  K = 1 (v ~ N(0,1)): symmetric halving,
+    round-robin row blocks + ONE all-reduce for G > 1.  K = 8 (V ~ U(0,1)): row-sharded + ONE all-gather.
+    Both results are checked on sampled rows against the reference."""
     import probnum_b200 as pb  # noqa: PLC0415
     from probnum_b200 import _lib  # noqa: PLC0415
     from probnum_b200.sharded import ShardedCovarianceOperator  # noqa: PLC0415
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: probnum_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    torch, world, dev = ctx.torch, ctx.world, ctx.dev
+    nm = args.n_mv
+    xm = np.random.default_rng(42).normal(size=(nm, D_MV))
+    kmv = pb.ExpQuad((D_MV,))
     if world > 1:
-        _bind_to_gpu_numa_node(local_rank)
-        dist.init_process_group("nccl", device_id=dev)
+        sop = ShardedCovarianceOperator(kmv, xm, device=ctx.local_rank)
+        local_op = sop.local
+    else:  # one GPU: the plain operator, no process group needed
+        sop = None
+        local_op = _lib.Operator(kmv._kernel_params(), np.ascontiguousarray(xm), None, device=ctx.local_rank)
+    launches = 0
+    peaks_mb = os.path.join(ROOT, "profiles", "r01_microbench.json")
+    dfma = None
+    if os.path.exists(peaks_mb):
+        with open(peaks_mb) as fh:
+            dfma = json.load(fh).get("dfma_tflops_sustained")
+    for key, kcols, gen in (("matvec", 1, lambda r: r.normal(size=(nm, 1))), ("matvec_k8", 8, lambda r: r.uniform(size=(nm, 8)))):
+        v_host = gen(np.random.default_rng(7))
+        v = torch.from_numpy(v_host).to(dev)
+        y = torch.empty((nm, kcols), dtype=torch.float64, device=dev)
+        if sop is not None:
+            run_product = lambda: sop.matmul_device(v, out=y)  # noqa: E731
+        else:
+            run_product = lambda: local_op.matmul_device(v.data_ptr(), kcols, kcols, y.data_ptr(), kcols, stream=ctx.stream)  # noqa: E731
+        run_product()
+        ctx.barrier()
+        reps = 2 if kcols == 1 else 1
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = _lib.launch_count()
+        e0.record()
+        for _ in range(reps):
+            run_product()
+        e1.record()
+        ctx.barrier()
+        launches += _lib.launch_count() - l0
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1) / reps)
+        flop_per_pair = 3 * D_MV + 1 + 2 * kcols  # SURVEY.md 8d: 3d + 1 + 2K, FMA = 2
+        path_op = sop.local_sym if (sop is not None and kcols == 1 and sop.local_sym is not None) else local_op
+        symmetric = path_op.matmul_path().endswith("symmetric")
+        rec = {
+            "kernel": path_op.matmul_path(),
+            "workload": f"ExpQuad K.V, N={nm}, d={D_MV}, K={kcols}, float64, V ~ " + ("N(0,1)" if kcols == 1 else "U(0,1)") + "; " + (
+                ("symmetric halving (each off-diagonal tile evaluated once)" + (
+                    "" if world == 1 else f", row blocks round-robin over {world} GPUs + all-reduce")) if symmetric
+                else f"row-sharded over {world} GPU(s)" + ("" if world == 1 else " + all-gather")),
+            "ms": ms, "pairs_per_s": float(nm) * nm / (ms * 1e-3),
+            "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,
+            "flop_per_pair": flop_per_pair, "scaling": "strong",
+        }
+        if dfma:
+            alg = rec["gflops"] / 1e3 / world
+            # the symmetric kernel evaluates each off-diagonal 128 x 128 tile once (plus one more FMA per
+            # pair for the mirrored sum): `achieved` counts the flops it EXECUTES (the claim against the
+            # FP64 pipe), `algorithmic` all N^2 ordered pairs (BASELINE's metric)
+            ach = alg * (0.5 * (1.0 + 128.0 / nm) * (flop_per_pair + 2) / flop_per_pair) if symmetric else alg
+            rec["roofline"] = {"bound": "fp64 pipe", "achieved": ach, "algorithmic": alg, "peak": dfma,
+                               "unit": "TFLOP/s", "frac": ach / dfma, "claim": "executed flops / measured DFMA rate",
+                               "peak_source": "profiles/r01_microbench.json dfma_tflops_sustained"}
+        # parity of what the collective produced, every rank holds the full y; rank 0 checks it
+        if ctx.rank == 0:
+            rec["parity"] = ctx.check(key, matvec_parity(xm, v_host, y.cpu().numpy()))
+        extra[key] = rec
+        del v, y
+    if sop is not None:
+        sop.close()
+    else:
+        local_op.close()
+    return launches
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+def leg_gram_row_sharded(ctx: Ctx, args, extra: dict, peaks: dict) -> int:
+    """ONE Gram matrix K(X, X), N = args.n, Matern-5/2, row-sharded: rank r owns rows
+    [lo_r, hi_r).  Device leg: each rank writes its row block into its own HBM (no collective), CUDA
+    events, max over ranks.  Host leg: each rank copies its block into ITS SLICE of one shared host
+    array (POSIX shared memory mapped by every rank, the slice page-locked by the rank that writes it).
+    Sampled rows of every rank's block are checked against the reference."""
+    import probnum_b200 as pb  # noqa: PLC0415
+    from probnum_b200 import _lib  # noqa: PLC0415
+    from probnum_b200.sharded import shard_bounds  # noqa: PLC0415
 
+    torch, world, rank = ctx.torch, ctx.world, ctx.rank
+    n, d = args.n, D_GRAM
+    X = np.random.default_rng(4242).normal(size=(n, d))
+    lo, hi = shard_bounds(n, world, rank)
+    k = pb.Matern((d,), nu=2.5)
+    op = _lib.Operator(k._kernel_params(), np.ascontiguousarray(X[lo:hi]), None if world == 1 else X, device=ctx.local_rank)
+    block = torch.empty((hi - lo, n), dtype=torch.float64, device=ctx.dev)
+    l0 = _lib.launch_count()
+    for _ in range(2):
+        op.gram_device(block.data_ptr(), n, stream=ctx.stream)
+    ctx.barrier()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        op.gram_device(block.data_ptr(), n, stream=ctx.stream)
+    e1.record()
+    ctx.barrier()
+    ms = ctx.max_over_ranks(e0.elapsed_time(e1) / reps)
+    # parity: 8 sampled rows of this rank's block
+    rows = lo + np.sort(np.random.default_rng(11 + rank).choice(hi - lo, size=min(8, hi - lo), replace=False))
+    Kr, source = reference_rows("matern", d, X, rows, nu=2.5)
+    got = block[torch.from_numpy(rows - lo).to(ctx.dev)].cpu().numpy()
+    ok_local = bool(np.allclose(got, Kr, rtol=1e-12, atol=1e-12))
+    rec = {
+        "workload": f"ONE Matern-5/2 Gram K(X, X), N={n}, d={d}, rows sharded contiguously over {world} rank(s); no collective",
+        "scaling": "strong", "device_ms": ms, "entries_per_s": float(n) * n / (ms * 1e-3),
+        "hbm_gbs_aggregate": 8.0 * n * n / (ms * 1e-3) / 1e9,
+        "frac_of_peak_per_gpu": 8.0 * n * n / world / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        "kernel": "gram_sym (upper triangle + mirror)" if world == 1 else "gram_fast (cross block: x0 = this rank's rows, x1 = all points)",
+        "parity": {"rows_per_rank": int(len(rows)), "criterion": "allclose(rtol=1e-12, atol=1e-12)", "reference": source,
+                   "ok": ctx.all_ok(ok_local)},
+    }
+    if ctx.rank == 0:
+        ctx.check("gram_row_sharded", rec["parity"])
+    del block
+    # host leg: one (n, n) host array shared by all ranks
+    if not args.no_e2e:
+        try:
+            rec["host_assembled"] = _gram_into_shared_host_array(ctx, op, X, n, lo, hi)
+            if ctx.rank == 0:
+                ctx.check("gram_row_sharded.host_assembled", rec["host_assembled"]["parity"])
+        except OSError as exc:  # e.g. /dev/shm too small on this box
+            rec["host_assembled"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+    launches = _lib.launch_count() - l0
+    op.close()
+    extra["gram_row_sharded"] = rec
+    return launches
+
+
+def _gram_into_shared_host_array(ctx: Ctx, op, X, n, lo, hi) -> dict:
+    import mmap  # noqa: PLC0415
+
+    torch, rank = ctx.torch, ctx.rank
+    nbytes = 8 * n * n
+    path = f"/dev/shm/pncov_bench_gram_{os.environ.get('MASTER_PORT', '0')}_{n}.bin"
+    st = os.statvfs("/dev/shm")
+    enough = st.f_bavail * st.f_frsize >= nbytes + (64 << 20)
+    if not ctx.all_ok(enough):
+        raise OSError(f"/dev/shm has {st.f_bavail * st.f_frsize >> 20} MiB free, need {nbytes >> 20} MiB")
+    if rank == 0:
+        with open(path, "wb") as fh:
+            fh.truncate(nbytes)
+    ctx.barrier()
+    fd = os.open(path, os.O_RDWR)
+    try:
+        mm = mmap.mmap(fd, nbytes)
+    finally:
+        os.close(fd)
+    K = np.frombuffer(mm, dtype=np.float64).reshape(n, n)
+    mine = K[lo:hi]
+    cudart = torch.cuda.cudart()
+    t0 = time.perf_counter()
+    mine[...] = 0.0  # touch: the pages are allocated on this rank's NUMA node
+    rc = cudart.cudaHostRegister(mine.ctypes.data, mine.nbytes, 0)
+    pinned = int(rc) == 0
+    t_pin = time.perf_counter() - t0
+    try:
+        op.gram(mine)  # warm-up (staging buffers)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        op.gram(mine)
+        ctx.barrier()
+        dt = ctx.max_over_ranks(time.perf_counter() - t0)
+        # rank 0 reads rows written by OTHER ranks through its own mapping of the shared array
+        ok = True
+        source = None
+        if rank == 0:
+            rows = np.sort(np.random.default_rng(13).choice(n, size=min(16, n), replace=False))
+            Kr, source = reference_rows("matern", X.shape[1], X, rows, nu=2.5)
+            ok = bool(np.allclose(K[rows], Kr, rtol=1e-12, atol=1e-12))
+        return {"api": "pncov_gram into this rank's slice of one shared host array (/dev/shm, slice page-locked by its writer)",
+                "ms": 1e3 * dt, "entries_per_s": float(n) * n / dt, "d2h_gbs_aggregate": nbytes / dt / 1e9,
+                "slice_pinned": pinned, "touch_and_pin_s_per_rank": ctx.max_over_ranks(t_pin),
+                "parity": {"rows": 16, "criterion": "allclose(rtol=1e-12, atol=1e-12), rows of all ranks read by rank 0",
+                           "reference": source, "ok": ctx.all_ok(ok)}}
+    finally:
+        if pinned:
+            cudart.cudaHostUnregister(mine.ctypes.data)
+        ctx.barrier()
+        del mine, K
+        try:
+            mm.close()
+        except BufferError:
+            pass
+        if rank == 0:
+            os.unlink(path)
+
+
+def _solve(pn, n, ell, maxiter):
+    rng = np.random.default_rng(42)
+    X = rng.normal(size=(n, 4))
+    y = rng.normal(size=n)
+    k = pn.randprocs.covfuncs.ExpQuad((4,), lengthscales=ell)
+    t0 = time.perf_counter()
+    L = k.linop(X)
+    x, _, _, info = pn.linalg.problinsolve(L + 1e-3 * pn.linops.Identity(n), y, maxiter=maxiter)
+    return np.asarray(x.mean), time.perf_counter() - t0, int(info["iter"]), float(info["resid_l2norm"]), type(L).__name__
+
+
+def leg_problinsolve(ctx: Ctx, args, extra: dict, with_cpu: bool) -> int:
+    """configs[3]: the reference's own `problinsolve` on (K_ExpQuad + 1e-3 I) x = y, N = 65536, d = 4,
+    lengthscale 0.25, fixed 50 iterations, with the drop-in installed (`patch.enable_all()`): the
+    operator is the matrix-free device product, sharded over the ranks (one NCCL collective per
+    product) when G > 1; the solver itself is the reference's sequential host loop, replicated."""
+    pn = _import_reference(package=True)
+    if pn is None:
+        extra["problinsolve"] = {"unavailable": "baseline/_ref is not importable"}
+        return 0
+    import probnum_b200.patch as gpu  # noqa: PLC0415
+    from probnum_b200 import _lib  # noqa: PLC0415
+
+    os.environ["PNCOV_DEVICE"] = str(ctx.local_rank)
+    n, ell, maxiter = args.n_solve, 0.25, 50
+    l0 = _lib.launch_count()
+    rec = {"workload": f"problinsolve, (K_ExpQuad(l={ell}) + 1e-3 I) x = y, N={n}, d=4, maxiter={maxiter}, "
+                       f"probnum (baseline/_ref) + patch.enable_all(), {ctx.world} rank(s)"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpu.enable_all(sharded=ctx.world > 1)
+        try:
+            _solve(pn, 4096, ell, 5)  # warm-up: contexts, pools, NCCL
+            ctx.barrier()
+            x_n, dt, it, res, kind = _solve(pn, n, ell, maxiter)
+        finally:
+            gpu.disable()
+        rec.update({"operator": kind, "seconds": ctx.max_over_ranks(dt), "iterations": it, "resid_l2norm": res})
+        if ctx.world > 1:
+            # the same solve on ONE rank's GPU (unsharded operator), rank 0 only; the others wait
+            if ctx.rank == 0:
+                gpu.enable_all(sharded=False)
+                try:
+                    x_1, dt1, it1, _, _ = _solve(pn, n, ell, maxiter)
+                finally:
+                    gpu.disable()
+                diff = float(np.abs(x_n - x_1).max() / np.abs(x_1).max())
+                rec["one_rank"] = {"seconds": dt1, "iterations": it1, "x_rel_diff_inf_vs_sharded": diff,
+                                   "criterion": "<= 1e-8 and the same iteration count",
+                                   "ok": bool(diff <= 1e-8 and it1 == it)}
+                ctx.check("problinsolve.one_rank", rec["one_rank"])
+            ctx.barrier()
+            # replicas must hold the same iterate bit for bit
+            t = ctx.torch.from_numpy(np.ascontiguousarray(x_n)).to(ctx.dev)
+            ref = t.clone()
+            ctx.dist.broadcast(ref, 0)
+            rec["replicas_identical"] = ctx.all_ok(bool(ctx.torch.equal(t, ref)))
+            if ctx.rank == 0 and not rec["replicas_identical"]:
+                ctx.failures.append("problinsolve.replicas_identical")
+        if with_cpu and ctx.rank == 0:
+            # the unmodified reference at the largest size it finishes in seconds (its operator caches
+            # the dense matrix: 34 GB at N = 65536), and the device path on the same problem
+            n_cmp = 4096
+            x_ref, dt_ref, it_ref, _, _ = _solve(pn, n_cmp, ell, maxiter)
+            gpu.enable_all(sharded=False)
+            try:
+                x_dev, dt_dev, it_dev, _, _ = _solve(pn, n_cmp, ell, maxiter)
+            finally:
+                gpu.disable()
+            diff = float(np.abs(x_dev - x_ref).max() / np.abs(x_ref).max())
+            rec["vs_reference"] = {"n": n_cmp, "reference_cpu_seconds": dt_ref, "device_seconds": dt_dev, "cores": os.cpu_count(),
+                                   "iterations": [it_ref, it_dev], "x_rel_diff_inf": diff,
+                                   "criterion": "x.mean within 1e-8 rel (SURVEY.md 8d), same iteration count",
+                                   "ok": bool(diff <= 1e-8 and it_ref == it_dev)}
+            ctx.check("problinsolve.vs_reference", rec["vs_reference"])
+    extra["problinsolve"] = rec
+    return _lib.launch_count() - l0
+
+
+def _bq(pn, n):
+    rng = np.random.default_rng(42)
+    nodes = rng.normal(size=(n, 4))
+    f = np.sin(nodes).sum(axis=1)
+    measure = pn.quad.integration_measures.GaussianMeasure(mean=np.zeros(4), cov=np.eye(4))
+    t0 = time.perf_counter()
+    F, _ = pn.quad.bayesquad_from_data(nodes=nodes, fun_evals=f, measure=measure)
+    return float(F.mean), float(F.var), time.perf_counter() - t0
+
+
+def leg_bayesquad(ctx: Ctx, args, extra: dict, with_cpu: bool) -> int:
+    """configs[4]: `bayesquad_from_data`, ExpQuad + Gaussian measure, 16384 nodes, d = 4, with
+    `patch.enable_all()` (Gram, Cholesky and solves on the device).  A sequential host algorithm:
+    rank 0 only ("replicas only" above the operator)."""
+    pn = _import_reference(package=True)
+    if pn is None:
+        extra["bayesquad"] = {"unavailable": "baseline/_ref is not importable"}
+        return 0
+    import probnum_b200.patch as gpu  # noqa: PLC0415
+    from probnum_b200 import _lib  # noqa: PLC0415
+
+    os.environ["PNCOV_DEVICE"] = str(ctx.local_rank)
+    l0 = _lib.launch_count()
+    n = args.n_bq
+    rec = {"workload": f"bayesquad_from_data, ExpQuad + GaussianMeasure, {n} nodes, d=4, probnum (baseline/_ref) + patch.enable_all()"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gpu.enable_all(sharded=False)
+        try:
+            m0, v0, cold = _bq(pn, n)
+            m1, v1, warm = _bq(pn, n)
+            rec.update({"first_call_seconds": cold, "seconds": warm, "mean": m1, "var": v1,
+                        "repeatable": bool(m0 == m1 and v0 == v1)})
+            if with_cpu:
+                n_cmp = 4096
+                m_dev, v_dev, dt_dev = _bq(pn, n_cmp)
+        finally:
+            gpu.disable()
+        if with_cpu:
+            m_ref, v_ref, dt_ref = _bq(pn, n_cmp)
+            dm = abs(m_dev - m_ref) / max(abs(m_ref), 1e-300)
+            # F.var = k_PP - w.kmean is a difference of two O(1) numbers that cancels to ~1e-6..1e-9: its relative
+            # error is the solver's error amplified by that cancellation, so it is checked on the scale of the
+            # un-cancelled terms (the initial integral variance, here (1/3)^(d/2) for ExpQuad(l=1) under N(0, I))
+            kpp = (1.0 / 3.0) ** 2.0
+            dv = abs(v_dev - v_ref) / kpp
+            rec["vs_reference"] = {"n": n_cmp, "reference_cpu_seconds": dt_ref, "device_seconds": dt_dev, "cores": os.cpu_count(),
+                                   "mean_rel_diff": dm, "var_abs_diff_over_prior_var": dv, "var_reference": v_ref, "var_device": v_dev,
+                                   "criterion": "F.mean 1e-9 rel; F.var 1e-9 on the scale of the un-cancelled prior variance",
+                                   "ok": bool(dm <= 1e-9 and dv <= 1e-9)}
+            ctx.check("bayesquad.vs_reference", rec["vs_reference"])
+    extra["bayesquad"] = rec
+    return _lib.launch_count() - l0
+
+
+def leg_config0(ctx: Ctx, extra: dict, with_cpu: bool) -> int:
+    """configs[0]: ExpQuad Gram N = 1000, d = 10 and the true asv shape d = 100
+    (benchmarks/covfuncs.py:20,55-66) through `k.matrix(X)` of the patched reference classes."""
+    pn = _import_reference(package=True)
+    if pn is None:
+        extra["config0"] = {"unavailable": "baseline/_ref is not importable"}
+        return 0
+    import probnum_b200.patch as gpu  # noqa: PLC0415
+    from probnum_b200 import _lib  # noqa: PLC0415
+
+    os.environ["PNCOV_DEVICE"] = str(ctx.local_rank)
+    l0 = _lib.launch_count()
+    out = {}
+    for d in (10, 100):
+        X = np.random.default_rng(42).normal(size=(1000, d))
+        k = pn.randprocs.covfuncs.ExpQuad((d,))
+        rec = {}
+        if with_cpu:
+            best = 1e30
+            for _ in range(2):
+                t0 = time.perf_counter()
+                K_ref = k.matrix(X)
+                best = min(best, time.perf_counter() - t0)
+            rec["reference_cpu_ms"] = 1e3 * best
+        gpu.enable()
+        try:
+            k.matrix(X)
+            best = 1e30
+            for _ in range(10):
+                t0 = time.perf_counter()
+                K_dev = k.matrix(X)
+                best = min(best, time.perf_counter() - t0)
+        finally:
+            gpu.disable()
+        rec["device_api_ms"] = 1e3 * best
+        rec["entries_per_s"] = 1e6 / best
+        if with_cpu:
+            rec["parity"] = ctx.check(f"config0.d{d}", {"criterion": "allclose(rtol=1e-12, atol=1e-12), symmetric, unit diagonal",
+                                                        "max_abs_diff": float(np.abs(K_dev - K_ref).max()),
+                                                        "ok": bool(np.allclose(K_dev, K_ref, rtol=1e-12, atol=1e-12)
+                                                                   and np.array_equal(K_dev, K_dev.T)
+                                                                   and np.all(np.diag(K_dev) == 1.0))})
+        out[f"expquad_gram_n1000_d{d}"] = rec
+    extra["config0"] = out
+    return _lib.launch_count() - l0
+
+
+def run_ours(args):
+    ctx = Ctx()
+    torch, dist = ctx.torch, ctx.dist
+    world, rank, local_rank, dev, stream = ctx.world, ctx.rank, ctx.local_rank, ctx.dev, ctx.stream
+    import probnum_b200 as pb  # noqa: PLC0415
+    from probnum_b200 import _lib  # noqa: PLC0415
+
+    barrier, max_over_ranks = ctx.barrier, ctx.max_over_ranks
     n, d = args.n, D_GRAM
     # synthetic inputs as in benchmarks/covfuncs.py:56 (default_rng(42), standard normal)
     x0_host = np.random.default_rng(42 + 1000 * rank).normal(size=(n, d))
@@ -308,7 +767,6 @@ def run_ours(args):
         ops[name] = _lib.Operator(k._kernel_params(), x0_dev.data_ptr(), None,
                                   device=local_rank, on_device=True, n0=n, n1=n, dtype=np.float64)
     out = torch.empty((n, n), dtype=torch.float64, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
 
     def gram(name):
         ops[name].gram_device(out.data_ptr(), n, stream=stream)
@@ -320,7 +778,7 @@ def run_ours(args):
             gram(name)
 
     sampler = ClockSampler(local_rank)
-    sampler.start()  # samples every 100 ms through warm-up and the timed region
+    sampler.start()  # samples every 50 ms through warm-up and the timed region
     for _ in range(args.warmup):
         step()
     barrier()
@@ -349,22 +807,27 @@ def run_ours(args):
     dom = max(per_kernel_ms, key=per_kernel_ms.get)
     alg_bytes = 8.0 * n * n + 8.0 * d * (n + n)
     achieved = alg_bytes / (per_kernel_ms[dom] * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_source = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and n == N_GRAM:
         with open(tpath) as fh:
             tr = json.load(fh)
-            traffic = tr.get("gram_sym_kernel_bytes_per_launch" if dom == "matern52" else "gram_fast_kernel_bytes_per_launch")
+            tkey = "gram_sym_kernel_bytes_per_launch" if dom == "matern52" else "gram_fast_kernel_bytes_per_launch"
+            traffic = tr.get(tkey)
+            traffic_source = f"profiles/traffic.json[{tkey}] ({tr.get('source', 'ncu --set full capture')})"
     roofline = {
-        "bound": "hbm", "kernel": (f"gram_sym_kernel<D=3, {dom}> (upper triangle + mirrored stores)" if dom == "matern52"
+        "bound": "hbm", "kernel": (f"gram_sym kernel <D=3, {dom}> (upper triangle + mirrored stores)" if dom == "matern52"
                                     else f"gram_fast_kernel<D=3, {dom}>"),
         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-        "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, copy read+write)",
+        "traffic": traffic, "traffic_source": traffic_source,
+        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}, copy read+write)",
         "algorithmic_bytes_per_launch": alg_bytes,
+        "timing": "CUDA events on the launching stream around this kernel, mean over the timed steps",
     }
 
     extra = {"per_kernel_ms": per_kernel_ms,
-             "per_kernel_entries_per_s": {k: n * n / (v * 1e-3) for k, v in per_kernel_ms.items()}}
+             "per_kernel_entries_per_s": {k: n * n / (v * 1e-3) for k, v in per_kernel_ms.items()},
+             "per_kernel_frac_of_peak": {k: alg_bytes / (v * 1e-3) / 1e9 / peaks["hbm_gbs"] for k, v in per_kernel_ms.items()}}
 
     # ExpQuad Gram alone (north_star's 70 % target is quoted on it)
     for _ in range(2):
@@ -378,116 +841,119 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+    launches += reps + 2
     extra["expquad_gram"] = {"ms": ms, "entries_per_s": n * n * world / (ms * 1e-3),
                              "hbm_gbs": alg_bytes / (ms * 1e-3) / 1e9,
                              "frac_of_peak": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 
+    # cross Gram K(X0, X1), X1 != X0 ("x1 = None and a distinct X1 of the same size")
+    x1_dev = torch.from_numpy(np.random.default_rng(43 + 1000 * rank).normal(size=(n, d))).to(dev)
+    cross = {}
+    for name in step_kernels:
+        opx = _lib.Operator(kernels[name]._kernel_params(), x0_dev.data_ptr(), x1_dev.data_ptr(), device=local_rank,
+                            on_device=True, n0=n, n1=n, dtype=np.float64)
+        for _ in range(2):
+            opx.gram_device(out.data_ptr(), n, stream=stream)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            opx.gram_device(out.data_ptr(), n, stream=stream)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / reps)
+        cross[name] = {"ms": ms, "frac_of_peak": alg_bytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+        launches += reps + 2
+        opx.close()
+    extra["cross_gram"] = cross
+    del x1_dev
+
     # ---- end to end through the public API: host arrays in, host ndarray out ------------------
     e2e = None
     if not args.no_e2e:
-        ks = [kernels[name] for name in step_kernels]
-        for k in ks:  # warm-up: pins the result buffers once
-            k.matrix(x0_host)
-        barrier()
-        e2e_steps = max(1, min(args.steps, 3))
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            for k in ks:
+        # through the reference's own classes with the drop-in installed when baseline/_ref is there
+        pn = _import_reference(package=True)
+        if pn is not None:
+            import probnum_b200.patch as gpu  # noqa: PLC0415
+
+            os.environ["PNCOV_DEVICE"] = str(local_rank)
+            gpu.enable()
+            ks = [pn.randprocs.covfuncs.Matern((d,), nu=2.5), pn.randprocs.covfuncs.RatQuad((d,))]
+            api = "probnum (baseline/_ref) + probnum_b200.patch.enable(): {Matern,RatQuad}.matrix(X) -> numpy.ndarray"
+        else:
+            gpu = None
+            ks = [kernels[name] for name in step_kernels]
+            api = "probnum_b200.covfuncs.{Matern,RatQuad}.matrix(X) -> numpy.ndarray"
+        l0 = _lib.launch_count()
+        try:
+            barrier()
+            t0 = time.perf_counter()
+            for k in ks:  # cold: the first call page-locks the result blocks (cudaHostAlloc of 8.6 GB each)
                 K = k.matrix(x0_host)
                 del K
-        barrier()
-        dt = max_over_ranks(time.perf_counter() - t0)
+            barrier()
+            cold = max_over_ranks(time.perf_counter() - t0)
+            e2e_steps = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                for k in ks:
+                    K = k.matrix(x0_host)
+                    del K
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+        finally:
+            if gpu is not None:
+                gpu.disable()
+        launches += _lib.launch_count() - l0
         e2e = {
             "value": entries_per_step * e2e_steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": 2 * 8 * d * n * world,
             "d2h_bytes_per_step": int(2 * 8 * n * n) * world,
             "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-            "api": "probnum_b200.covfuncs.{Matern,RatQuad}.matrix(X) -> numpy.ndarray (pinned result pool)",
+            "d2h_gbs_aggregate": 2 * 8.0 * n * n * world * e2e_steps / dt / 1e9,
+            "first_step_cold_ms": 1e3 * cold,
+            "api": api + " (result arrays from the page-locked pool of probnum_b200.hostmem: warm steps re-use the "
+                         "blocks the cold step pinned)",
         }
     del out
     torch.cuda.empty_cache()
 
-    # ---- configs[2]: matrix-free ExpQuad K.v, N = 2^20, d = 8, row-sharded + all-gather -----------
+    if not args.no_callers:
+        launches += leg_gram_row_sharded(ctx, args, extra, peaks)
     if not args.no_matvec:
-        nm = args.n_mv
-        xm = np.random.default_rng(42).normal(size=(nm, D_MV))
-        kmv = pb.ExpQuad((D_MV,))
-        if world > 1:
-            sop = ShardedCovarianceOperator(kmv, xm, device=local_rank)
-            local_op = sop.local
-            run_product = lambda: sop.matmul_device(v, out=y)  # noqa: E731
-        else:  # one GPU: the plain operator, no process group needed
-            sop = None
-            local_op = _lib.Operator(kmv._kernel_params(), np.ascontiguousarray(xm), None, device=local_rank)
-            run_product = lambda: local_op.matmul_device(v.data_ptr(), 1, 1, y.data_ptr(), 1, stream=stream)  # noqa: E731
-        v = torch.from_numpy(np.random.default_rng(7).normal(size=(nm, 1))).to(dev)
-        y = torch.empty((nm, 1), dtype=torch.float64, device=dev)
-        run_product()
+        launches += leg_matvec(ctx, args, extra)
+    with_cpu = world == 1 and not args.no_cpu_baseline
+    if not args.no_callers:
+        launches += leg_problinsolve(ctx, args, extra, with_cpu)
+        if rank == 0:
+            launches += leg_bayesquad(ctx, args, extra, with_cpu)
+            launches += leg_config0(ctx, extra, with_cpu)
         barrier()
-        reps = 2
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = _lib.launch_count()
-        e0.record()
-        for _ in range(reps):
-            run_product()
-        e1.record()
-        barrier()
-        launches += _lib.launch_count() - l0
-        ms = max_over_ranks(e0.elapsed_time(e1) / reps)
-        flop_per_pair = 3 * D_MV + 1 + 2  # 3d + 1 + 2K, FMA = 2
-        path_op = sop.local_sym if (sop is not None and sop.local_sym is not None) else local_op
-        symmetric = path_op.matmul_path().endswith("symmetric")
-        extra["matvec"] = {
-            "kernel": path_op.matmul_path(),
-            "workload": f"ExpQuad K.v, N={nm}, d={D_MV}, K=1, float64, " + (
-                ("symmetric halving (each off-diagonal tile evaluated once)" + (
-                    "" if world == 1 else f", row blocks round-robin over {world} GPUs + all-reduce")) if symmetric
-                else f"row-sharded over {world} GPU(s) + all-gather"),
-            "ms": ms, "pairs_per_s": float(nm) * nm / (ms * 1e-3),
-            "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,
-            "flop_per_pair": flop_per_pair, "scaling": "strong",
-        }
-        # FP64 roofline of this kernel: algorithmic flops against the DFMA rate measured on this
-        # pool by tools/microbench.cu (profiles/r01_microbench.json), per GPU
-        mb = os.path.join(ROOT, "profiles", "r01_microbench.json")
-        if os.path.exists(mb):
-            with open(mb) as fh:
-                dfma = json.load(fh).get("dfma_tflops_sustained")
-            if dfma:
-                alg = extra["matvec"]["gflops"] / 1e3 / world
-                # the symmetric kernel evaluates each off-diagonal 128 x 128 tile once (plus one more
-                # FMA per pair for the mirrored sum): the roofline fraction is taken on the flops it
-                # EXECUTES, the algorithmic figure (all N^2 pairs, BASELINE's metric) is kept beside it
-                ach = alg * (0.5 * (1.0 + 128.0 / nm) * (flop_per_pair + 2) / flop_per_pair) if symmetric else alg
-                extra["matvec"]["roofline"] = {"bound": "fp64 pipe", "achieved": ach, "algorithmic": alg, "peak": dfma,
-                                               "unit": "TFLOP/s", "frac": ach / dfma,
-                                               "peak_source": "profiles/r01_microbench.json dfma_tflops_sustained"}
-        if sop is not None:
-            sop.close()
-        else:
-            local_op.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(n)
 
+    failed = False
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": f"Matern-5/2 + RatQuad Gram, N={n}, d={d}, float64 (BASELINE configs[1])"
-                            + ("" if world == 1 else f"; {world} independent point clouds, one per rank/GPU"),
-                "l2": "each launch writes 8.6 GB >> 126 MB L2; no flush needed",
-                "inputs": "default_rng(42).normal, resident in HBM",
-            },
+            "config": workload_config(n, world),
+            "timing": {"l2": "each launch writes 8.6 GB >> 126 MB L2; no flush needed",
+                       "inputs": "resident in HBM when the timed region starts"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "extra": extra,
         }
+        if ctx.failures:
+            line["parity_failed"] = ctx.failures
+            failed = True
         emit(line)
     if dist.is_initialized():
         dist.destroy_process_group()
+    if failed:
+        sys.exit(1)
 
 
 _JSON_FD = None

@@ -17,6 +17,18 @@
 
 int64_t g_pn_launches = 0;
 
+int pn_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached[dev] = sms;
+    }
+    return cached[dev];
+}
+
 namespace {
 
 thread_local std::string t_err;
@@ -399,7 +411,7 @@ struct Points {
 
 struct pncov_handle {
     int device = 0;
-    int sm_count = 148;
+    int sm_count = 0;  // set at creation from the device
     KernelDesc k;
     Points p0, p1;
     bool symmetric = false;  // x1 was NULL: p1 aliases p0
@@ -523,6 +535,7 @@ PnGramLaunch gram_launch(const pncov_handle* h, bool transpose, int64_t row0, in
     g.in_f32 = h->k.dtype == PNCOV_F32;
     g.out_f32 = h->k.gram_f32();
     g.symmetric = (h->symmetric && row0 == 0 && rows == R.n) ? 1 : 0;
+    g.sm_count = h->sm_count;
     g.epi = h->k.epi;
     return g;
 }
@@ -829,7 +842,8 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
     if (!guard.ok) return bail(fail(PNCOV_ENODEVICE, "cudaSetDevice failed"));
     int cc_major = 0, sms = 0;
     cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device);
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->sm_count = sms;
+    (void)sms;
+    h->sm_count = pn_sm_count();
     if (cc_major < 10) return bail(fail(PNCOV_ENODEVICE, "libpncov is built for sm_100a (B200) only"));
     cudaError_t e;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(fail_cuda(e, "cudaStreamCreate"));

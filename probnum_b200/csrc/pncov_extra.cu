@@ -434,7 +434,7 @@ cudaError_t launch_gram_mode(const PnExtraLaunch& g, cudaStream_t stream) {
     // ~16 CTAs per SM; whole row stages per CTA
     const int64_t unit = g.d <= X_DC ? X_RS : X_R;
     const int64_t n_units = (g.n0 + unit - 1) / unit;
-    int64_t upc = (n_units * strips) / (148 * 16);
+    int64_t upc = (n_units * strips) / ((int64_t)pn_sm_count() * 16);
     upc = upc < 1 ? 1 : (upc > 64 ? 64 : upc);
     const int64_t gy = (n_units + upc - 1) / upc;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
@@ -482,7 +482,8 @@ cudaError_t pn_launch_combine(double* dst, const double* src, int64_t n, int op,
         return cudaErrorMisalignedAddress;
     const int64_t n2 = n / 2;
     int64_t blocks = (n2 + 255) / 256;
-    blocks = blocks < 1 ? 1 : (blocks > 148 * 32 ? 148 * 32 : blocks);
+    const int64_t max_blocks = (int64_t)pn_sm_count() * 32;
+    blocks = blocks < 1 ? 1 : (blocks > max_blocks ? max_blocks : blocks);
     if (op == 0 && src)
         combine_kernel<0, true><<<(unsigned)blocks, 256, 0, stream>>>(dst, src, n2, n, alpha, beta);
     else if (op == 0)

@@ -319,26 +319,50 @@ __global__ void __launch_bounds__(G_THREADS)
 // only change sign), so the result is bit-identical to the general kernel.  FP64 work per stored
 // entry halves, which moves Matern / general RatQuad from FP64-pipe-bound to HBM-bound.
 //
-// The DRAM side wants LONG contiguous runs in both directions (measured: scattered 128-byte
-// lines of a mirrored half cost 20 % of the launch, 512-byte runs cost nothing), so the CTA tile
-// is 64 x 64: a warp owns 8 rows of it (two 4-row register tiles over the warp's 64 columns, two
-// columns per lane), direct rows leave as one 512-byte STG.128 per warp, the tile is staged
-// transposed in XOR-swizzled shared memory (conflict-free both ways), and after ONE CTA barrier
-// per tile (the staging buffer is double-buffered) each warp writes 8 mirrored rows, again as one
-// 512-byte STG.128 per row.
-constexpr int Y_T = 64;                               // tile edge
-constexpr int Y_STAGE_BYTES = Y_T * Y_T * 8;          // one transposed tile
+// The DRAM side wants LONG contiguous runs in both directions (measured in round 1: scattered
+// 128-byte lines of a mirrored half cost 20 % of the launch, 512-byte runs cost nothing), so the
+// CTA tile is 64 x 64 and a warp owns whole rows of it (two adjacent columns per lane):
+//   * direct rows leave from registers, one 512-byte STG.128 per row and warp;
+//   * the transposed tile is written to shared memory (rows padded to 528 bytes) and leaves through
+//     the TMA engine: lane 0 of every warp issues one 512-byte bulk copy per mirrored row
+//     (cp.async.bulk.global.shared::cta, SASS UBLKCP) after ONE CTA barrier per tile.  No mirrored value
+//     passes through a register again and no warp waits on LSU back-pressure for that half.
+// A CTA is 4 warps with ONE staging buffer (53 KB with the exp2 table), four CTAs per SM: while one
+// CTA drains its tile the other three compute.  Measured on B200, N = 32768, d = 3, Matern-5/2
+// (profiles/README.md, round 2; the first kernel staged through XOR-swizzled shared memory and
+// re-read the tile to store it with STG): 1.48 ms -> 1.32 ms = 0.99 of the copy peak.  Larger CTAs
+// with two or three staging buffers at 1-2 CTAs per SM, direct rows through the TMA engine as well,
+// an L2 evict-first hint and a supertile rasterisation of the grid were all slower (1.36 - 2.3 ms).
+constexpr int Y_T = 64;          // tile edge
+constexpr int Y_TLD = Y_T + 2;   // doubles per staged transposed row (528 bytes: bulk-copy sources are 16-byte aligned)
+constexpr int Y_WARPS = 4;
+constexpr int Y_RPW = Y_T / Y_WARPS;  // rows of the tile per warp
+constexpr int Y_TPC = 8;              // row tiles per CTA (4 .. 32 measured within 2 %)
+
+__device__ __forceinline__ void pn_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(pn_smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void pn_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pn_bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void pn_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int EPI>
+struct SymHdr {  // barriers + exp2 table (+ log2 table for the general RatQuad epilogue only)
+    static constexpr int BYTES = 128 + 8 * PN_EXP2_N + (EPI == PN_EPI_RATQUADG ? 16 * PN_LOG2_N : 0);
+};
+
 template <int D, bool ARD, int EPI>
-__global__ void __launch_bounds__(G_THREADS, 2)
+__global__ void __launch_bounds__(Y_WARPS * 32, 4)
     gram_sym_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages, [2]: tables
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
-    double* x0s = reinterpret_cast<double*>(smem + G_HDR_BYTES);  // [2][D][Y_T]
-    // transposed staging: [2 buffers][64 columns][32 chunks of 2 rows], chunk index ^ ((column >> 1) & 7)
-    double2* mir = reinterpret_cast<double2*>(smem + G_HDR_BYTES + 2 * D * Y_T * 8);
+    double* x0s = reinterpret_cast<double*>(smem + SymHdr<EPI>::BYTES);  // [2][D][Y_T]
+    double* Ts = x0s + 2 * D * Y_T;                                         // [Y_T][Y_TLD] transposed tile
 
     const int t_diag = (int)blockIdx.x;  // the strip's diagonal tile
     const int t0 = blockIdx.y * tiles_per_cta;
@@ -351,7 +375,7 @@ __global__ void __launch_bounds__(G_THREADS, 2)
     if (tid == 0) {
         pn_mbar_init(&bars[0], 1);
         pn_mbar_init(&bars[1], 1);
-        pn_mbar_init(&bars[2], 1);  // tables
+        pn_mbar_init(&bars[2], 1);
         pn_mbar_fence_init();
     }
     __syncthreads();
@@ -362,7 +386,6 @@ __global__ void __launch_bounds__(G_THREADS, 2)
             pn_bulk_g2s(x0s + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)t0 * Y_T, Y_T * 8, &bars[0]);
         pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
     }
-
     double xb0[D], xb1[D], sc[D];
 #pragma unroll
     for (int m = 0; m < D; ++m) {
@@ -372,11 +395,7 @@ __global__ void __launch_bounds__(G_THREADS, 2)
         if constexpr (ARD) sc[m] = static_cast<const double*>(g.scale)[m];
     }
     const size_t row_stride = (size_t)g.ldo;
-    // direct: row (t * 64 + 8 * warp + r), columns c0 + 2 * lane
-    double* optr = static_cast<double*>(g.out) + ((size_t)t0 * Y_T + 8 * warp) * row_stride + c0 + 2 * lane;
-    // mirrored: row (c0 + 8 * warp + i), columns t * 64 + 2 * lane
-    double* mptr = static_cast<double*>(g.out) + ((size_t)c0 + 8 * warp) * row_stride + (size_t)t0 * Y_T + 2 * lane;
-    const int sw = lane & 7;  // swizzle key of this lane's columns: ((2 * lane) >> 1) & 7
+    double* const out = static_cast<double*>(g.out);
     pn_mbar_wait(&bars[2], 0);
 
     int it = 0;
@@ -390,31 +409,17 @@ __global__ void __launch_bounds__(G_THREADS, 2)
                 pn_bulk_g2s(dst + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)(t + 1) * Y_T, Y_T * 8, &bars[buf ^ 1]);
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
-        const double* x0t = x0s + buf * (D * Y_T) + 8 * warp;
-        double2* stage = mir + buf * (Y_T * 32);
-        const double2* prev = mir + (buf ^ 1) * (Y_T * 32);  // transposed tile t - 1 (always a mirrored one)
-        double2* s0 = stage + (2 * lane) * 32;  // this lane's first column
-        double2* s1 = s0 + 32;
+        const double* x0t = x0s + buf * (D * Y_T) + Y_RPW * warp;
         const bool mirror = t < t_diag;  // uniform per tile
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            // mirrored rows of the previous tile, spread over this tile's arithmetic so that the
-            // stores leave the SM as a steady stream rather than a burst after the barrier
-            if (it > 0) {
-#pragma unroll
-                for (int i = 4 * h; i < 4 * h + 4; ++i) {
-                    const int c = 8 * warp + i;
-                    const double2 v = prev[c * 32 + (lane ^ ((c >> 1) & 7))];
-                    pn_store_cs2(mptr + (size_t)i * row_stride, v.x, v.y);
-                }
-            }
+        for (int h = 0; h < Y_RPW / G_R; ++h) {
             double S[2 * G_R];
 #pragma unroll
             for (int i = 0; i < 2 * G_R; ++i) S[i] = 0.0;
 #pragma unroll
             for (int m = 0; m < D; ++m) {
-                const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + 4 * h);
-                const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * Y_T + 4 * h + 2);
+                const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h);
+                const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h + 2);
                 const double xa[G_R] = {a01.x, a01.y, a23.x, a23.y};
 #pragma unroll
                 for (int r = 0; r < G_R; ++r) {
@@ -430,33 +435,31 @@ __global__ void __launch_bounds__(G_THREADS, 2)
             }
             double K[2 * G_R];
             epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+            const int r0 = Y_RPW * warp + G_R * h;  // first row of this register tile within the tile
+            double* optr = out + ((size_t)t * Y_T + r0) * row_stride + c0 + 2 * lane;
 #pragma unroll
-            for (int r = 0; r < G_R; ++r) {
-                pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
-                optr += row_stride;
-            }
-            if (mirror) {
-                const int k = 4 * warp + 2 * h;  // chunk (row pair) index of rows 8 * warp + 4 * h
-                s0[k ^ sw] = make_double2(K[0], K[2]);
-                s0[(k + 1) ^ sw] = make_double2(K[4], K[6]);
-                s1[k ^ sw] = make_double2(K[1], K[3]);
-                s1[(k + 1) ^ sw] = make_double2(K[5], K[7]);
+            for (int r = 0; r < G_R; ++r) pn_store_cs2(optr + r * row_stride, K[2 * r], K[2 * r + 1]);
+            if (mirror) {  // transposed: row = this lane's column, 4 consecutive entries = this tile's rows
+                double* s0 = Ts + (2 * lane) * Y_TLD + r0;
+                *reinterpret_cast<double2*>(s0) = make_double2(K[0], K[2]);
+                *reinterpret_cast<double2*>(s0 + 2) = make_double2(K[4], K[6]);
+                *reinterpret_cast<double2*>(s0 + Y_TLD) = make_double2(K[1], K[3]);
+                *reinterpret_cast<double2*>(s0 + Y_TLD + 2) = make_double2(K[5], K[7]);
             }
         }
-        optr += (size_t)(Y_T - 8) * row_stride;
-        if (it > 0) mptr += Y_T;
-        // staging buffer `buf` is complete and buffer buf^1 (tile t-1) has been drained by everyone;
+        if (mirror) {  // uniform
+            pn_fence_proxy_async();  // generic-proxy writes above -> visible to the TMA engine
+            __syncthreads();
+            if (lane == 0) {
+                double* mptr = out + ((size_t)c0 + Y_RPW * warp) * row_stride + (size_t)t * Y_T;
+#pragma unroll
+                for (int r = 0; r < Y_RPW; ++r) pn_bulk_s2g(mptr + r * row_stride, Ts + (Y_RPW * warp + r) * Y_TLD, Y_T * 8);
+                pn_bulk_commit();
+                pn_bulk_wait_read_all();  // the staging buffer is rewritten by the next tile
+            }
+        }
         // also orders this tile's reads of x0 stage `buf` before its refill two iterations on
         __syncthreads();
-    }
-    if (t1 - 1 < t_diag) {  // the last tile of this CTA was a mirrored one: drain it
-        const double2* prev = mir + ((it - 1) & 1) * (Y_T * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = 8 * warp + i;
-            const double2 v = prev[c * 32 + (lane ^ ((c >> 1) & 7))];
-            pn_store_cs2(mptr + (size_t)i * row_stride, v.x, v.y);
-        }
     }
 }
 
@@ -560,7 +563,7 @@ template <int D, bool ARD, int EPI>
 cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
     const int64_t strips = g.n1 / G_TN;
     const int64_t n_tiles = g.n0 / G_TM;
-    int64_t tpc = (n_tiles * strips) / (148 * 48);
+    int64_t tpc = (n_tiles * strips) / ((int64_t)g.sm_count * 48);
     tpc = tpc < 1 ? 1 : (tpc > 32 ? 32 : tpc);
     const int64_t gy = (n_tiles + tpc - 1) / tpc;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
@@ -574,15 +577,14 @@ cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
 template <int D, bool ARD, int EPI>
 cudaError_t launch_sym_inst(const PnGramLaunch& g, cudaStream_t stream) {
     const int64_t n_tiles = g.n0 / Y_T;
-    const int64_t tpc = 16;  // row tiles per CTA: amortises the prologue; 8..32 measured within 3 %
-    const int64_t gy = (n_tiles + tpc - 1) / tpc;
+    const int64_t gy = (n_tiles + Y_TPC - 1) / Y_TPC;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
-    const size_t smem = G_HDR_BYTES + 2 * sizeof(double) * D * Y_T + 2 * Y_STAGE_BYTES;
+    const size_t smem = SymHdr<EPI>::BYTES + 2 * sizeof(double) * D * Y_T + sizeof(double) * Y_T * Y_TLD;
     auto kern = gram_sym_kernel<D, ARD, EPI>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)n_tiles, (unsigned)gy);
-    kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc);
+    kern<<<grid, Y_WARPS * 32, smem, stream>>>(g, Y_TPC);
     ++g_pn_launches;
     return cudaGetLastError();
 }
@@ -633,8 +635,8 @@ cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
     const int vec_ok = ((g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % (2 * sizeof(TOut))) == 0) ? 1 : 0;
     if (g.d <= G_DMAX) {
         const int64_t n_tiles = (g.n0 + G_TM - 1) / G_TM;
-        // enough CTAs for ~16 waves on 148 SMs, at least one row tile each
-        int64_t tpc = (n_tiles * strips) / (148 * 48);
+        // enough CTAs for ~16 waves over the SMs, at least one row tile each
+        int64_t tpc = (n_tiles * strips) / ((int64_t)g.sm_count * 48);
         if (tpc < 1) tpc = 1;
         if (tpc > 32) tpc = 32;
         const int64_t gy = (n_tiles + tpc - 1) / tpc;

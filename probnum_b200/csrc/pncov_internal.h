@@ -22,6 +22,7 @@ struct PnGramLaunch {
     int in_f32;          // points are float32
     int out_f32;         // Gram entries are float32 (only ExpQuad on float32 points)
     int symmetric;       // x1 is x0 and the whole square matrix is requested: mirror stores allowed
+    int sm_count;        // multiProcessorCount of the handle's device (grid sizing)
     PnEpiParams epi;
 };
 
@@ -119,5 +120,7 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& m, int sm_count);
 cudaError_t pn_launch_matvec(const PnMatvecLaunch& m, int sm_count, cudaStream_t stream);
 cudaError_t pn_launch_pairs(const PnPairsLaunch& p, cudaStream_t stream);
 
-// small utility kernels (pncov_api.cu)
+// pncov_api.cu
 extern int64_t g_pn_launches;
+// multiProcessorCount of the CURRENT device (queried once per device): grids are sized from it
+int pn_sm_count();

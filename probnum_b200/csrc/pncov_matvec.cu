@@ -1203,7 +1203,7 @@ cudaError_t launch_direct_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
     const int64_t row_ctas = (n_blocks + nparts - 1) / nparts;
     int64_t tps = 256;
-    while (tps > 8 && row_ctas * ((n_jt + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    while (tps > 8 && row_ctas * ((n_jt + tps - 1) / tps) < (int64_t)pn_sm_count() * 4 * 8) tps /= 2;
     const int64_t chunks = (n_jt + tps - 1) / tps;
     if (chunks > 65535) return cudaErrorInvalidConfiguration;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1258,7 +1258,7 @@ cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     // chunks of column tiles (in units of 128 columns): short enough to balance the triangle, long
     // enough to amortise the prologue
     int64_t tps = 256;
-    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < (int64_t)pn_sm_count() * 4 * 8) tps /= 2;
     tps *= TPB;
     const int64_t chunks = (n_jt + tps - 1) / tps;
     if (chunks > 65535) return cudaErrorInvalidConfiguration;
@@ -1366,7 +1366,7 @@ cudaError_t launch_rows_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
     const int64_t row_ctas = (n_blocks + nparts - 1) / nparts;
     int64_t tps = 256;
-    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < 148 * 4 * 8) tps /= 2;
+    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < (int64_t)pn_sm_count() * 4 * 8) tps /= 2;
     tps *= TPB;
     const int64_t chunks = (n_jt + tps - 1) / tps;
     if (chunks > 65535) return cudaErrorInvalidConfiguration;
