@@ -646,7 +646,7 @@ def leg_problinsolve(ctx: Ctx, args, extra: dict, with_cpu: bool) -> int:
 def _bq(pn, n):
     rng = np.random.default_rng(42)
     nodes = rng.normal(size=(n, 4))
-    f = np.sin(nodes).sum(axis=1)
+    f = np.cos(nodes).sum(axis=1)  # integral 4 exp(-1/2): F.mean is not a cancellation to ~0
     measure = pn.quad.integration_measures.GaussianMeasure(mean=np.zeros(4), cov=np.eye(4))
     t0 = time.perf_counter()
     F, _ = pn.quad.bayesquad_from_data(nodes=nodes, fun_evals=f, measure=measure)

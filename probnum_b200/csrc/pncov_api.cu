@@ -419,6 +419,18 @@ struct pncov_handle {
     void* pm_dev = nullptr;  // ProductMatern per-dimension parameters
     void* dot_ops[2] = {nullptr, nullptr};  // Linear / Polynomial, d > 16: zero-padded row-major operands (x0, x1)
     int dot_dpad = 0;
+    // ExpQuad / RatQuad, d > 16: operands of the guarded norm-identity DMMA Gram (pncov_gram_mma.cu), per point set
+    int gm_dpad = 0;  // > 0: that kernel serves the dense Gram of this handle
+    void* gm_A[2] = {nullptr, nullptr};
+    void* gm_B[2] = {nullptr, nullptr};
+    void* gm_nrm[2] = {nullptr, nullptr};
+    void* gm_thr[2] = {nullptr, nullptr};
+    PnEpiParams gm_epi{};
+    unsigned gm_v_hi = 0;
+    // kernel-selection switches of the environment, read ONCE when the handle is created
+    int env_ident = -1;   // PNCOV_MATVEC_IDENT: -1 unset, 0 "off", 1 "dfma"
+    int env_fact = -1;    // PNCOV_MATVEC_FACT: 0 "off"
+    int env_sym = -1;     // PNCOV_MATVEC_SYM: 0 "off", 1 "on"
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -552,9 +564,34 @@ int upload_pm(const KernelDesc& k, void** dev, cudaStream_t stream) {
 // one Gram launch (rows [row0, row0 + rows) of K or K^T) of whichever family the handle holds
 cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0, int64_t rows, void* out, int64_t ld,
                             cudaStream_t stream) {
-    if (h->k.extra_mode < 0) return pn_launch_gram(gram_launch(h, transpose, row0, rows, out, ld), stream);
     const Points& R = transpose ? h->p1 : h->p0;
     const Points& C = transpose ? h->p0 : h->p1;
+    if (h->gm_dpad > 0) {  // ExpQuad / RatQuad with wide inputs: guarded norm identity on DMMA
+        const int r = transpose ? 1 : 0, c = transpose ? 0 : 1;
+        PnGramMmaLaunch p{};
+        p.A = static_cast<const double*>(h->gm_A[r]) + (size_t)row0 * h->gm_dpad;
+        p.B = static_cast<const double*>(h->gm_B[c]);
+        p.nrmA = static_cast<const double*>(h->gm_nrm[r]) + row0;
+        p.nrmB = static_cast<const double*>(h->gm_nrm[c]);
+        p.thrA = static_cast<const int*>(h->gm_thr[r]) + row0;
+        p.thrB = static_cast<const int*>(h->gm_thr[c]);
+        p.x0_aos = static_cast<const double*>(R.aos) + (size_t)row0 * h->k.d;
+        p.x1_aos = static_cast<const double*>(C.aos);
+        p.scale = static_cast<const double*>(h->scale_dev);
+        p.d = h->k.d;
+        p.dpad = h->gm_dpad;
+        p.n0 = rows;
+        p.n1 = C.n;
+        p.row0 = row0;
+        p.same_points = h->symmetric ? 1 : 0;
+        p.out = static_cast<double*>(out);
+        p.ldo = ld;
+        p.v_hi = h->gm_v_hi;
+        p.epi = h->gm_epi;
+        p.epi_direct = h->k.epi;
+        return pn_launch_gram_mma(p, stream);
+    }
+    if (h->k.extra_mode < 0) return pn_launch_gram(gram_launch(h, transpose, row0, rows, out, ld), stream);
     if (h->dot_dpad > 0) {  // Linear / Polynomial with wide inputs: FP64 GEMM on DMMA
         const double* A = static_cast<const double*>(h->dot_ops[transpose ? 1 : 0]) + (size_t)row0 * h->dot_dpad;
         const double* B = static_cast<const double*>(h->dot_ops[transpose ? 0 : 1]);
@@ -578,6 +615,70 @@ cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0,
     return pn_launch_gram_extra(g, stream);
 }
 
+// Operands of the guarded norm-identity Gram (pncov_gram_mma.cu) for ExpQuad / RatQuad on wide inputs.  Unlike the
+// matrix-free product (mma_prepare below) nothing is decided per handle: the guard is per ENTRY inside the kernel.
+constexpr int64_t kGmRowSlack = 128;  // a launch may start at any row: its last 128-row tile may read past npad
+int gram_mma_prepare(pncov_handle* h) {
+    const KernelDesc& k = h->k;
+    if (k.dtype != PNCOV_F64 || k.d <= 16 || k.d > 4096 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
+    if (h->p0.n == 0 || h->p1.n == 0) return 0;
+    {
+        const char* env = getenv("PNCOV_GRAM_IDENT");  // "off": direct differences at every d (read once per handle)
+        if (env && strcmp(env, "off") == 0) return 0;
+    }
+    cudaStream_t stream = h->stream;
+    const int d = k.d, dpad = ((d + 15) / 16) * 16;
+    const bool expq = k.kind == PNCOV_EXPQUAD;
+    double* centre = nullptr;
+    PN_CUDA(pn_dev_alloc(reinterpret_cast<void**>(&centre), (size_t)d * sizeof(double), stream));
+    const double ntot = (double)h->p0.n + (h->symmetric ? 0.0 : (double)h->p1.n);
+    cudaError_t e = pn_launch_gram_mma_centre((const double*)h->p0.soa, h->p0.npad, h->symmetric ? nullptr : (const double*)h->p1.soa,
+                                              h->p1.npad, ntot, d, centre, stream);
+    // ExpQuad: operands carry the scale factors, the exponent constant becomes -log2(e); RatQuad: unscaled
+    double iso = 1.0;
+    if (expq && !k.ard) iso = sqrt(-k.epi.c_u / kLog2e);
+    const double* scale_dev = (expq && k.ard) ? (const double*)h->scale_dev : nullptr;
+    const double gamma = (4.0 * d + 24.0) * ldexp(1.0, -53);
+    const double gam_over_tol = (expq ? 1.0 : k.epi.alpha * k.epi.c_s) * gamma / 2e-13;
+    const double dup_factor = 64.0 * 2e-13 / (expq ? 1.0 : k.epi.alpha);  // 64 gamma nrm (times c for RatQuad) = dup_factor * w
+    const int nsets = h->symmetric ? 1 : 2;
+    for (int sidx = 0; sidx < nsets && e == cudaSuccess; ++sidx) {
+        const Points& P = sidx == 0 ? h->p0 : h->p1;
+        const int64_t rows_alloc = P.npad + kGmRowSlack;
+        if (e == cudaSuccess) e = pn_dev_alloc(&h->gm_A[sidx], (size_t)rows_alloc * dpad * 8, stream);
+        if (e == cudaSuccess) e = pn_dev_alloc(&h->gm_B[sidx], (size_t)rows_alloc * dpad * 8, stream);
+        if (e == cudaSuccess) e = pn_dev_alloc(&h->gm_nrm[sidx], (size_t)rows_alloc * 8, stream);
+        if (e == cudaSuccess) e = pn_dev_alloc(&h->gm_thr[sidx], (size_t)rows_alloc * 4, stream);
+        if (e == cudaSuccess)
+            e = pn_launch_gram_mma_operands((const double*)P.aos, P.n, rows_alloc, d, dpad, centre, scale_dev, iso, gam_over_tol,
+                                            dup_factor, expq ? 1 : 0, (double*)h->gm_A[sidx], (double*)h->gm_B[sidx], (double*)h->gm_nrm[sidx],
+                                            (int*)h->gm_thr[sidx], stream);
+    }
+    pn_dev_free(centre, stream);
+    if (e != cudaSuccess) return fail_cuda(e, "gram_mma_prepare");
+    if (h->symmetric) {
+        h->gm_A[1] = h->gm_A[0];
+        h->gm_B[1] = h->gm_B[0];
+        h->gm_nrm[1] = h->gm_nrm[0];
+        h->gm_thr[1] = h->gm_thr[0];
+    }
+    h->gm_epi = k.epi;
+    if (expq) {
+        h->gm_epi.c_u = -kLog2e;
+        h->gm_epi.c_s = 1.0;
+        h->gm_epi.c_su = -kLog2e;
+        fill_window(h->gm_epi);
+        h->gm_v_hi = h->gm_epi.s_hi_word;  // v = S
+    } else {
+        // v = 1 + c S: pn_rcp_core / pn_log2_core need v < 2^990 (and alpha log2 v < 1021 for the general form)
+        double b_log2_max = 990.0;
+        if (k.epi.epi == PN_EPI_RATQUADG) b_log2_max = fmin(b_log2_max, 1021.0 / k.epi.alpha);
+        h->gm_v_hi = hi_word(exp2(b_log2_max));
+    }
+    h->gm_dpad = dpad;
+    return 0;
+}
+
 // Decide whether the norm-identity kernel may serve this handle and build its operands.
 //
 // With xt = (x - c) s the identity S = |xt_i|^2 + |yt_j|^2 - 2 xt_i.yt_j carries an absolute
@@ -595,10 +696,7 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
     const KernelDesc& k = h->k;
     if (k.dtype != PNCOV_F64 || k.d > 64 || (k.kind != PNCOV_EXPQUAD && k.kind != PNCOV_RATQUAD)) return 0;
     if (h->p0.n == 0 || h->p1.n == 0) return 0;
-    {
-        const char* form = getenv("PNCOV_MATVEC_IDENT");  // "off": always direct differences
-        if (h->opt_identity < 0 && form && strcmp(form, "off") == 0) return 0;
-    }
+    if (h->opt_identity < 0 && h->env_ident == 0) return 0;  // PNCOV_MATVEC_IDENT=off: always direct differences
     const int d = k.d;
     double* sums = nullptr;
     const int dpad = d <= 8 ? 8 : (d <= 16 ? 16 : (d <= 32 ? 32 : 64));
@@ -705,13 +803,11 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     const bool wide_ok = h->k.d <= 8 || kc_max == 1;  // the 8 < d <= 64 kernels take one right-hand side
     if (h->mma_state == 1 && h->opt_identity != 0 && wide_ok) {
         // norm identity: dot products on DMMA by default (fastest measured), DFMA form opt-in
-        const char* form = getenv("PNCOV_MATVEC_IDENT");
-        m.use_mma = (form && strcmp(form, "dfma") == 0) ? 1 : 2;
+        m.use_mma = h->env_ident == 1 ? 1 : 2;
         m.a12 = h->a12[transpose ? 1 : 0];
         m.b12 = h->b12[transpose ? 0 : 1];
         m.epi = h->mma_epi;
-        const char* fenv = getenv("PNCOV_MATVEC_FACT");
-        const bool fact_on = h->opt_factorised >= 0 ? h->opt_factorised != 0 : !(fenv && strcmp(fenv, "off") == 0);
+        const bool fact_on = h->opt_factorised >= 0 ? h->opt_factorised != 0 : h->env_fact != 0;
         m.fact = (m.use_mma == 2 && h->k.kind == PNCOV_EXPQUAD && fact_on) ? 1 : 0;
         if (h->k.d > 8 && (m.use_mma != 2 || (h->k.kind == PNCOV_EXPQUAD && !m.fact))) {
             m.use_mma = 0;  // wide operands exist only as DMMA kernels, ExpQuad only in factorised form
@@ -723,9 +819,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     {
         // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
         // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
-        const char* symenv = getenv("PNCOV_MATVEC_SYM");
         const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 96);  // DMMA identity or direct differences
-        const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : !(symenv && strcmp(symenv, "off") == 0);
+        const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : h->env_sym != 0;
         const bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;
         if (sym_nparts > 0 && !sym_ok)
             return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 96 and n >= 2048");
@@ -873,6 +968,10 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
         }
         if (h->symmetric) h->dot_ops[1] = h->dot_ops[0];
     }
+    if ((rc = gram_mma_prepare(h))) return bail(rc);
+    if (const char* v = getenv("PNCOV_MATVEC_IDENT")) h->env_ident = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "dfma") == 0 ? 1 : -1);
+    if (const char* v = getenv("PNCOV_MATVEC_FACT")) h->env_fact = strcmp(v, "off") == 0 ? 0 : -1;
+    if (const char* v = getenv("PNCOV_MATVEC_SYM")) h->env_sym = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "on") == 0 ? 1 : -1);
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(fail_cuda(e, "upload"));
     *out = h;
     return 0;
@@ -893,6 +992,12 @@ PNCOV_API int pncov_destroy(pncov_handle* h) {
     pn_dev_free(h->pm_dev, fs);
     pn_dev_free(h->dot_ops[0], fs);
     if (!h->symmetric) pn_dev_free(h->dot_ops[1], fs);
+    for (int sidx = 0; sidx < (h->symmetric ? 1 : 2); ++sidx) {
+        pn_dev_free(h->gm_A[sidx], fs);
+        pn_dev_free(h->gm_B[sidx], fs);
+        pn_dev_free(h->gm_nrm[sidx], fs);
+        pn_dev_free(h->gm_thr[sidx], fs);
+    }
     pn_dev_free(h->vpack, fs);
     pn_dev_free(h->ypack, fs);
     pn_dev_free(h->partial, fs);

@@ -20,9 +20,9 @@
 //     The thresholds are per POINT (monotone in nrm: the larger of the two applies to the pair),
 //     stored as high words and compared with integer instructions; entries that fail -- near
 //     duplicates, the diagonal of a symmetric Gram (always redone: exact 1.0 like the reference),
-//     S rounded below zero -- are recomputed by direct differences from the ORIGINAL points with the
-//     robust epilogue, exactly like gram_chunk_kernel.  Matern (sqrt(S) near 0) stays on the direct
-//     kernels.
+//     S rounded below zero or within 64 error bounds of zero (so that coincident points give exactly
+//     1.0) -- are recomputed by direct differences from the ORIGINAL points with the robust epilogue,
+//     exactly like gram_chunk_kernel.  Matern (sqrt(S) near 0) stays on the direct kernels.
 //
 // Layout: the FP64 GEMM core of csrc/pncov_chol.cu (CTA = 4 warps = 128 x 64 tile, warp 32 x 64,
 // 64 accumulators per lane, two-stage cp.async pipeline in K-chunks of 16, row stride 20 doubles).
@@ -34,12 +34,11 @@
 namespace {
 
 constexpr int GM_BM = 128, GM_BN = 64, GM_CK = 16, GM_LD = GM_CK + 4, GM_THREADS = 128;
-constexpr int GM_SLD = 72;                                             // staging row stride (doubles)
 constexpr int GM_STAGE_BYTES = (GM_BM + GM_BN) * GM_LD * 8;            // one operand stage: 30720
 constexpr int GM_TAB_BYTES = 8 * PN_EXP2_N + 16 * PN_LOG2_N;           // 20480
 constexpr int GM_SMEM_BYTES = 2 * GM_STAGE_BYTES + 128;                // + barrier
 static_assert(GM_TAB_BYTES <= GM_STAGE_BYTES, "the tables fit the idle operand stage");
-static_assert(4 * 16 * GM_SLD * 8 <= 2 * GM_STAGE_BYTES - GM_TAB_BYTES, "result staging fits beside the tables");
+static_assert(4 * 16 * 64 * 8 <= 2 * GM_STAGE_BYTES - GM_TAB_BYTES, "result staging fits beside the tables");
 
 __device__ __forceinline__ void gm_dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -64,6 +63,20 @@ static __device__ __noinline__ double gm_redo(const PnGramMmaLaunch& p, int64_t 
     return pn_epilogue(S, p.epi_direct, tabE, tabL);
 }
 
+// An entry the fast path did not accept.  Accuracy failures (value below the guard threshold of its two points,
+// negative, the diagonal of a symmetric Gram) are recomputed from the original points; values that only left the
+// window of the FAST epilogue (results at or below the underflow threshold) keep their S -- its relative error is
+// as small as anywhere else -- and go through the robust epilogue, ExpQuad results far below the smallest
+// subnormal (S > 750 in scaled units, the reference's exp gives 0.0 from 745.14 on) are 0 directly.
+static __device__ __noinline__ double gm_fix(const PnGramMmaLaunch& p, int64_t row, int64_t col, double s, int hi, int thr,
+                                             bool on_diag, const double* tabE, const double* tabL) {
+    if (row >= p.n0 || col >= p.n1) return 0.0;  // padding
+    if (on_diag || hi < thr) return gm_redo(p, row, col, tabE, tabL);
+    if (s != s) return gm_redo(p, row, col, tabE, tabL);  // NaN: let the direct form decide
+    if (p.epi.epi == PN_EPI_EXPQUAD && s > 750.0) return 0.0;
+    return pn_epilogue(s, p.epi, tabE, tabL);
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_constant__ PnGramMmaLaunch p) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -71,6 +84,7 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
     const int64_t row_base = (int64_t)blockIdx.y * GM_BM, col_base = (int64_t)blockIdx.x * GM_BN;
+    if (p.mirror && col_base < row_base) return;  // below the diagonal block: written by the mirrored tile
     const double* At = p.A + row_base * p.dpad;
     const double* Bt = p.B + col_base * p.dpad;
 
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
     unsigned char* free_stage = smem + (last_buf ^ 1) * GM_STAGE_BYTES;
     double* tabE = reinterpret_cast<double*>(last_buf == 0 ? smem + 2 * GM_STAGE_BYTES - GM_TAB_BYTES : smem);
     double* tabL = tabE + PN_EXP2_N;
-    double* stg = reinterpret_cast<double*>(last_buf == 0 ? smem : smem + GM_TAB_BYTES) + warp * (16 * GM_SLD);
+    double* stg = reinterpret_cast<double*>(last_buf == 0 ? smem : smem + GM_TAB_BYTES) + warp * (16 * 64);
     (void)free_stage;
 
     load_chunk(0, 0);
@@ -159,80 +173,103 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
     }
     pn_mbar_wait(bar, 0);
 
-    // ---- epilogue: guard, kernel function, staged 512-byte row stores ---------------------------------
+    // ---- epilogue ---------------------------------------------------------------------------------------------
+    // The accumulator fragments (S) of 16 rows x 64 columns per warp go to shared memory, are read back one ROW per
+    // step (two adjacent columns per lane: the guard thresholds of the columns stay in registers, the row's is warp
+    // uniform, and no accumulator is live any more, so several rows are in flight per lane), pass the guard and the
+    // kernel function and leave as 512 contiguous bytes per row.  Rows are 32 chunks of 16 bytes, chunk p of row i at
+    // position p ^ sw(i), sw(i) = 4 (i & 1) | ((i >> 1) & 3): fragment stores and row reads are conflict free, the
+    // column reads of the mirrored half are two-way.
     const PnEpiParams& P = p.epi;
     const bool diag_tile = p.same_points && (p.row0 + row_base < col_base + GM_BN) && (col_base < p.row0 + row_base + GM_BM);
-    const unsigned v_hi = P.s_hi_word;
+    const bool mirror = p.mirror && col_base >= row_base + GM_BM;  // strictly above the diagonal block: K[j][i] = K[i][j]
+    const unsigned v_hi = p.v_hi;
+    const int64_t col = col_base + 2 * lane;
+    const int2 thr_c = *reinterpret_cast<const int2*>(p.thrB + col);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const int r = 2 * h + rr;
-            const int64_t lrow = row_base + warp * 32 + r * 8 + g;  // row within this launch
-            const int thr_r = p.thrA[lrow];
+            const int i = rr * 8 + g;
+            const int sw = ((i & 1) << 2) | ((i >> 1) & 3);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int64_t col = col_base + c * 8 + 2 * q;
-                const int2 thr_c = *reinterpret_cast<const int2*>(p.thrB + col);
-                const double s0 = acc[r][c][0], s1 = acc[r][c][1];
-                double v0, v1, k0, k1;
-                if constexpr (EPI == PN_EPI_EXPQUAD) {
-                    v0 = s0;
-                    v1 = s1;
-                    k0 = pn_exp2_prod_core(s0, P.c_u, P, tabE);
-                    k1 = pn_exp2_prod_core(s1, P.c_u, P, tabE);
-                } else {
-                    v0 = pn_fma(s0, P.c_s, 1.0);
-                    v1 = pn_fma(s1, P.c_s, 1.0);
-                    if constexpr (EPI == PN_EPI_RATQUAD1) {
-                        k0 = pn_rcp_core(v0);
-                        k1 = pn_rcp_core(v1);
-                    } else if constexpr (EPI == PN_EPI_RATQUAD2) {
-                        k0 = pn_rcp_core(v0);
-                        k1 = pn_rcp_core(v1);
-                        k0 *= k0;
-                        k1 *= k1;
-                    } else {
-                        k0 = pn_exp2_prod_core(pn_log2_core(v0, P, tabL), -P.alpha, P, tabE);
-                        k1 = pn_exp2_prod_core(pn_log2_core(v1, P, tabL), -P.alpha, P, tabE);
-                    }
-                }
-                // keep the entry iff thr <= hi(v) < v_hi (signed hi words as unsigned differences: a negative
-                // or NaN value fails as well)
-                const int t0 = max(thr_r, thr_c.x), t1 = max(thr_r, thr_c.y);
-                bool bad0 = (unsigned)(pn_hi(v0) - t0) >= v_hi - (unsigned)t0;
-                bool bad1 = (unsigned)(pn_hi(v1) - t1) >= v_hi - (unsigned)t1;
-                if (diag_tile) {
-                    bad0 |= p.row0 + lrow == col;
-                    bad1 |= p.row0 + lrow == col + 1;
-                }
-                if (bad0 | bad1) {  // rare: near duplicates, the diagonal, underflowing results
-                    if (bad0 && lrow < p.n0 && col < p.n1) k0 = gm_redo(p, lrow, col, tabE, tabL);
-                    if (bad1 && lrow < p.n0 && col + 1 < p.n1) k1 = gm_redo(p, lrow, col + 1, tabE, tabL);
-                }
-                *reinterpret_cast<double2*>(stg + (rr * 8 + g) * GM_SLD + c * 8 + 2 * q) = make_double2(k0, k1);
-            }
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<double2*>(stg + i * 64 + (((4 * c + q) ^ sw) << 1)) =
+                    make_double2(acc[2 * h + rr][c][0], acc[2 * h + rr][c][1]);
         }
         __syncwarp();
         const int64_t lrow0 = row_base + warp * 32 + h * 16;
-        const int64_t col = col_base + 2 * lane;
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {
-            const int64_t lrow = lrow0 + i;
-            if (lrow >= p.n0) break;
-            const double2 v = *reinterpret_cast<const double2*>(stg + i * GM_SLD + 2 * lane);
-            double* dst = p.out + lrow * p.ldo + col;
-            if (col + 1 < p.n1) {
-                if (p.vec_ok) pn_store_cs2(dst, v.x, v.y);
-                else {
-                    pn_store_cs1(dst, v.x);
-                    pn_store_cs1(dst + 1, v.y);
+            const int64_t lrow = lrow0 + i;  // row within this launch
+            const int sw = ((i & 1) << 2) | ((i >> 1) & 3);
+            double2* slot = reinterpret_cast<double2*>(stg + i * 64 + ((lane ^ sw) << 1));
+            const double2 s = *slot;
+            const int thr_r = p.thrA[lrow];
+            double v0, v1, k0, k1;
+            if constexpr (EPI == PN_EPI_EXPQUAD) {
+                v0 = s.x;
+                v1 = s.y;
+                k0 = pn_exp2_prod_core(s.x, P.c_u, P, tabE);
+                k1 = pn_exp2_prod_core(s.y, P.c_u, P, tabE);
+            } else {
+                v0 = pn_fma(s.x, P.c_s, 1.0);
+                v1 = pn_fma(s.y, P.c_s, 1.0);
+                if constexpr (EPI == PN_EPI_RATQUAD1) {
+                    k0 = pn_rcp_core(v0);
+                    k1 = pn_rcp_core(v1);
+                } else if constexpr (EPI == PN_EPI_RATQUAD2) {
+                    k0 = pn_rcp_core(v0);
+                    k1 = pn_rcp_core(v1);
+                    k0 *= k0;
+                    k1 *= k1;
+                } else {
+                    k0 = pn_exp2_prod_core(pn_log2_core(v0, P, tabL), -P.alpha, P, tabE);
+                    k1 = pn_exp2_prod_core(pn_log2_core(v1, P, tabL), -P.alpha, P, tabE);
                 }
-            } else if (col < p.n1) {
-                pn_store_cs1(dst, v.x);
+            }
+            // keep the entry iff thr <= hi(v) < v_hi: one unsigned comparison (a negative or NaN value fails too)
+            const int t0 = max(thr_r, thr_c.x), t1 = max(thr_r, thr_c.y);
+            const int h0 = pn_hi(v0), h1 = pn_hi(v1);
+            bool bad0 = (unsigned)(h0 - t0) >= v_hi - (unsigned)t0;
+            bool bad1 = (unsigned)(h1 - t1) >= v_hi - (unsigned)t1;
+            if (diag_tile) {
+                bad0 |= p.row0 + lrow == col;
+                bad1 |= p.row0 + lrow == col + 1;
+            }
+            if (bad0 | bad1) {  // rare: near duplicates, the diagonal, results at the underflow threshold
+                if (bad0) k0 = gm_fix(p, lrow, col, s.x, h0, t0, diag_tile && p.row0 + lrow == col, tabE, tabL);
+                if (bad1) k1 = gm_fix(p, lrow, col + 1, s.y, h1, t1, diag_tile && p.row0 + lrow == col + 1, tabE, tabL);
+            }
+            if (mirror) *slot = make_double2(k0, k1);
+            if (lrow < p.n0) {
+                double* dst = p.out + lrow * p.ldo + col;
+                if (col + 1 < p.n1) {
+                    if (p.vec_ok) pn_store_cs2(dst, k0, k1);
+                    else {
+                        pn_store_cs1(dst, k0);
+                        pn_store_cs1(dst + 1, k1);
+                    }
+                } else if (col < p.n1) {
+                    pn_store_cs1(dst, k0);
+                }
             }
         }
         __syncwarp();
+        if (mirror) {  // uniform per CTA: the transposed 64 x 16 block, 128 contiguous bytes per mirrored row
+            const int t = lane & 15;
+            const int sw = ((t & 1) << 2) | ((t >> 1) & 3);
+            const int64_t mcol = lrow0 + t;  // column of the mirrored entry
+            const double* srow = stg + t * 64;
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+                const int j = 2 * jj + (lane >> 4);
+                const double v = srow[((jj ^ sw) << 1) + (lane >> 4)];
+                const int64_t mrow = col_base + j;
+                if (mrow < p.n1 && mcol < p.n0) pn_store_cs1(p.out + mrow * p.ldo + mcol, v);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -249,39 +286,90 @@ cudaError_t launch_gm(const PnGramMmaLaunch& p, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-// centred + scaled GEMM operands of one point set: A = xt, B = -2 xt (npad x dpad, zero padded), nrm = |xt|^2 and the
-// guard threshold of every point as a high word (see the header comment; `gam_over_tol` = gamma / 2e-13 for ExpQuad,
-// alpha c gamma / 2e-13 for RatQuad)
-__global__ void gm_build_operands_kernel(const double* __restrict__ aos, int64_t n, int64_t npad, int d, int dpad,
-                                         const double* __restrict__ centre, const double* __restrict__ scale, double iso_scale,
-                                         double gam_over_tol, int expquad, double* __restrict__ A, double* __restrict__ B,
-                                         double* __restrict__ nrm, int* __restrict__ thr) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npad) return;
+// centre of both point sets: one CTA per coordinate sums its row of the coordinate-major copies (zero padded, so
+// the padding does not count) in a fixed order
+__global__ void __launch_bounds__(256) gm_centre_kernel(const double* __restrict__ soa0, int64_t ld0,
+                                                        const double* __restrict__ soa1, int64_t ld1, double ntot,
+                                                        double* __restrict__ centre) {
+    __shared__ double red[256];
+    const int m = blockIdx.x;
     double s = 0.0;
-    for (int m = 0; m < dpad; ++m) {
+    // non-finite coordinates do not move the centre: they poison only their own rows and columns, like the reference
+    for (int64_t i = threadIdx.x; i < ld0; i += 256) {
+        const double v = soa0[(size_t)m * ld0 + i];
+        if (isfinite(v)) s += v;
+    }
+    if (soa1)
+        for (int64_t i = threadIdx.x; i < ld1; i += 256) {
+            const double v = soa1[(size_t)m * ld1 + i];
+            if (isfinite(v)) s += v;
+        }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) centre[m] = isfinite(red[0]) ? red[0] / ntot : 0.0;
+}
+
+// centred + scaled GEMM operands of one point set: A = xt, B = -2 xt (rows_alloc x dpad, zero padded), nrm = |xt|^2
+// and the guard threshold of every point as a high word (see the header comment; `gam_over_tol` = gamma / 2e-13 for
+// ExpQuad, alpha c gamma / 2e-13 for RatQuad).  One warp per point: coalesced along the coordinates.
+__global__ void __launch_bounds__(256) gm_build_operands_kernel(const double* __restrict__ aos, int64_t n, int64_t rows_alloc,
+                                                                int d, int dpad, const double* __restrict__ centre,
+                                                                const double* __restrict__ scale, double iso_scale,
+                                                                double gam_over_tol, double dup_factor, int expquad,
+                                                                double* __restrict__ A,
+                                                                double* __restrict__ B, double* __restrict__ nrm,
+                                                                int* __restrict__ thr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= rows_alloc) return;
+    // |xt|^2 in index order (one lane would do; all lanes compute the same chain so that no shuffle tree
+    // changes the order): the value the DMMA chain cancels against
+    double s = 0.0;
+    for (int m0 = 0; m0 < dpad; m0 += 32) {
+        const int m = m0 + lane;
         double v = 0.0;
         if (i < n && m < d) v = (aos[i * d + m] - centre[m]) * (scale ? scale[m] : iso_scale);
-        A[i * dpad + m] = v;
-        B[i * dpad + m] = -2.0 * v;
-        s = fma(v, v, s);
+        if (m < dpad) {
+            A[i * dpad + m] = v;
+            B[i * dpad + m] = -2.0 * v;
+        }
+        for (int l = 0; l < 32; ++l) {
+            const double vl = __shfl_sync(0xffffffffu, v, l);
+            s = fma(vl, vl, s);
+        }
     }
+    if (lane != 0) return;
     nrm[i] = s;
     // ExpQuad: S >= ln(w);  RatQuad: 1 + c S >= w;  w = gam_over_tol * nrm.  Rounded UP to the next high word.
+    // Second guard: v below 64 error bounds of S (near-coincident points) is redone as well, so that coincident
+    // points give exactly 1.0 like the reference's direct differences.
     const double w = gam_over_tol * s;
-    double t = expquad ? (w > 1.0 ? log(w) : 0.0) : w;
+    double t = expquad ? fmax(w > 1.0 ? log(w) : 0.0, dup_factor * w) : fmax(w, 1.0 + dup_factor * w);
     int word = 0;
     if (t > 0.0) word = __double2hiint(t) + 1;
+    if (!(w < 1e12)) word = 0x7ff00000;  // absurd or non-finite norms: every entry of this point is redone
     thr[i] = (i < n) ? word : 0;
 }
 
 }  // namespace
 
-cudaError_t pn_launch_gram_mma_operands(const double* aos, int64_t n, int64_t npad, int d, int dpad, const double* centre,
-                                        const double* scale, double iso_scale, double gam_over_tol, int expquad, double* A,
-                                        double* B, double* nrm, int* thr, cudaStream_t stream) {
-    gm_build_operands_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, stream>>>(aos, n, npad, d, dpad, centre, scale, iso_scale,
-                                                                                  gam_over_tol, expquad, A, B, nrm, thr);
+cudaError_t pn_launch_gram_mma_centre(const double* soa0, int64_t ld0, const double* soa1, int64_t ld1, double ntot, int d,
+                                      double* centre, cudaStream_t stream) {
+    gm_centre_kernel<<<(unsigned)d, 256, 0, stream>>>(soa0, ld0, soa1, ld1, ntot, centre);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t pn_launch_gram_mma_operands(const double* aos, int64_t n, int64_t rows_alloc, int d, int dpad, const double* centre,
+                                        const double* scale, double iso_scale, double gam_over_tol, double dup_factor,
+                                        int expquad, double* A, double* B, double* nrm, int* thr, cudaStream_t stream) {
+    gm_build_operands_kernel<<<(unsigned)((rows_alloc + 7) / 8), 256, 0, stream>>>(aos, n, rows_alloc, d, dpad, centre, scale,
+                                                                                    iso_scale, gam_over_tol, dup_factor, expquad,
+                                                                                    A, B, nrm, thr);
     ++g_pn_launches;
     return cudaGetLastError();
 }
@@ -290,6 +378,7 @@ cudaError_t pn_launch_gram_mma(const PnGramMmaLaunch& p0, cudaStream_t stream) {
     if (p0.n0 <= 0 || p0.n1 <= 0) return cudaSuccess;
     PnGramMmaLaunch p = p0;
     p.vec_ok = ((p.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16) == 0) ? 1 : 0;
+    p.mirror = (p.same_points && p.row0 == 0 && p.n0 == p.n1) ? 1 : 0;
     switch (p.epi.epi) {
         case PN_EPI_EXPQUAD: return launch_gm<PN_EPI_EXPQUAD>(p, stream);
         case PN_EPI_RATQUAD1: return launch_gm<PN_EPI_RATQUAD1>(p, stream);

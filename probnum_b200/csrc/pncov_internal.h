@@ -113,6 +113,37 @@ cudaError_t pn_chol_transpose(const double* src, int64_t lds, int64_t rows, int6
 cudaError_t pn_chol_rowdots(const double* W, const double* G, int64_t ld, int64_t n, int64_t rows, const double* vecs,
                             int nvec, double* quad, double* dots, int64_t ldd, cudaStream_t stream);
 
+// ExpQuad / RatQuad Gram for wide inputs (d > 16): guarded norm identity on FP64 tensor cores
+// (pncov_gram_mma.cu).  All row-side pointers are already offset to the first row of the launch.
+struct PnGramMmaLaunch {
+    const double* A;       // (rows padded to 128, dpad) centred + scaled row points xt
+    const double* B;       // (columns padded to 64, dpad) -2 xt of the column points
+    const double* nrmA;    // |xt|^2 per row point
+    const double* nrmB;
+    const int* thrA;       // guard threshold of every point (high word, see the kernel's header)
+    const int* thrB;
+    const double* x0_aos;  // original points (n, d) row-major: direct-difference redo
+    const double* x1_aos;
+    const double* scale;   // d per-dimension scale factors of the direct form or nullptr
+    int d, dpad;
+    int64_t n0, n1;        // rows / columns of this launch
+    int64_t row0;          // index of the first row within its point set (diagonal detection)
+    int same_points;       // rows and columns are the same point set: entries (i, i) are redone (exact 1)
+    double* out;
+    int64_t ldo;
+    int vec_ok;            // filled by the launcher
+    int mirror;            // filled by the launcher: whole symmetric matrix, tiles below the diagonal blocks are mirrored copies
+    unsigned v_hi;         // fast epilogue valid while hi(v) < v_hi (v = S for ExpQuad, 1 + c S for RatQuad)
+    PnEpiParams epi;       // epilogue in the units of the operands
+    PnEpiParams epi_direct;  // epilogue of the direct form (original units)
+};
+cudaError_t pn_launch_gram_mma_centre(const double* soa0, int64_t ld0, const double* soa1, int64_t ld1, double ntot, int d,
+                                      double* centre, cudaStream_t stream);
+cudaError_t pn_launch_gram_mma_operands(const double* aos, int64_t n, int64_t rows_alloc, int d, int dpad, const double* centre,
+                                        const double* scale, double iso_scale, double gam_over_tol, double dup_factor,
+                                        int expquad, double* A, double* B, double* nrm, int* thr, cudaStream_t stream);
+cudaError_t pn_launch_gram_mma(const PnGramMmaLaunch& p, cudaStream_t stream);
+
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
 // pn_plan_matvec fills m.jsplit (how many column-range splits the launch will use, which
 // sizes the `partial` scratch); pn_launch_matvec then runs with that plan
