@@ -45,9 +45,6 @@ __device__ __forceinline__ void gm_dmma(double& c0, double& c1, double a, double
         : "+d"(c0), "+d"(c1)
         : "d"(a), "d"(b));
 }
-__device__ __forceinline__ void gm_cp_async16(void* smem, const void* gmem) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(pn_smem_u32(smem)), "l"(gmem) : "memory");
-}
 
 // one entry by direct differences from the original points (the reference's arithmetic)
 static __device__ __noinline__ double gm_redo(const PnGramMmaLaunch& p, int64_t row, int64_t col, const double* tabE,
@@ -55,9 +52,21 @@ static __device__ __noinline__ double gm_redo(const PnGramMmaLaunch& p, int64_t 
     const double* a = p.x0_aos + row * p.d;
     const double* b = p.x1_aos + col * p.d;
     double S = 0.0;
-    for (int m = 0; m < p.d; ++m) {
-        double df = a[m] - b[m];
-        if (p.scale) df *= p.scale[m];
+    int m = 0;
+    for (; m + 4 <= p.d; m += 4) {  // four independent loads per operand in flight
+        double df[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) df[u] = __ldg(a + m + u) - __ldg(b + m + u);
+        if (p.scale) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) df[u] *= __ldg(p.scale + m + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) S = pn_fma(df[u], df[u], S);
+    }
+    for (; m < p.d; ++m) {
+        double df = __ldg(a + m) - __ldg(b + m);
+        if (p.scale) df *= __ldg(p.scale + m);
         S = pn_fma(df, df, S);
     }
     return pn_epilogue(S, p.epi_direct, tabE, tabL);
@@ -71,6 +80,9 @@ static __device__ __noinline__ double gm_redo(const PnGramMmaLaunch& p, int64_t 
 static __device__ __noinline__ double gm_fix(const PnGramMmaLaunch& p, int64_t row, int64_t col, double s, int hi, int thr,
                                              bool on_diag, const double* tabE, const double* tabL) {
     if (row >= p.n0 || col >= p.n1) return 0.0;  // padding
+    // k(x, x): the reference's differences are exactly 0 and ExpQuad / RatQuad give exactly 1 -- unless the point has
+    // non-finite coordinates (s is NaN then), which the direct form below turns into the reference's NaN
+    if (on_diag && s == s) return 1.0;
     if (on_diag || hi < thr) return gm_redo(p, row, col, tabE, tabL);
     if (s != s) return gm_redo(p, row, col, tabE, tabL);  // NaN: let the direct form decide
     if (p.epi.epi == PN_EPI_EXPQUAD && s > 750.0) return 0.0;
@@ -83,8 +95,21 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 2 * GM_STAGE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, q = lane & 3;
-    const int64_t row_base = (int64_t)blockIdx.y * GM_BM, col_base = (int64_t)blockIdx.x * GM_BN;
-    if (p.mirror && col_base < row_base) return;  // below the diagonal block: written by the mirrored tile
+    int64_t row_base, col_base;
+    if (p.mirror) {
+        // 1-D grid over the tiles on and above the diagonal blocks only: row block I holds the column tiles 2 I .. gx - 1,
+        // c(I) = I (gx + 1) - I^2 tiles precede it
+        const int64_t t = blockIdx.x, gx = p.mirror;
+        int64_t I = (int64_t)(0.5 * ((double)(gx + 1) - sqrt((double)((gx + 1) * (gx + 1) - 4 * t))));
+        I = I < 0 ? 0 : I;
+        while (I * (gx + 1) - I * I > t) --I;
+        while ((I + 1) * (gx + 1) - (I + 1) * (I + 1) <= t) ++I;
+        row_base = I * GM_BM;
+        col_base = (2 * I + (t - (I * (gx + 1) - I * I))) * GM_BN;
+    } else {
+        row_base = (int64_t)blockIdx.y * GM_BM;
+        col_base = (int64_t)blockIdx.x * GM_BN;
+    }
     const double* At = p.A + row_base * p.dpad;
     const double* Bt = p.B + col_base * p.dpad;
 
@@ -93,22 +118,27 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
         pn_mbar_fence_init();
     }
 
+    // every thread copies the same 16-byte pieces of each chunk: rows tid / 8 + 16 i, doubles 2 (tid % 8) .. + 1
+    constexpr int PIECES = GM_CK / 2;
+    const double* srcA = At + (int64_t)(tid / PIECES) * p.dpad + (tid % PIECES) * 2;
+    const double* srcB = Bt + (int64_t)(tid / PIECES) * p.dpad + (tid % PIECES) * 2;
+    const int64_t src_step = (int64_t)(GM_THREADS / PIECES) * p.dpad;
+    const uint32_t dst0 = pn_smem_u32(smem) + (uint32_t)(((tid / PIECES) * GM_LD + (tid % PIECES) * 2) * 8);
     auto load_chunk = [&](int kc, int buf) {
-        double* as = reinterpret_cast<double*>(smem + buf * GM_STAGE_BYTES);
-        double* bs = as + GM_BM * GM_LD;
-        constexpr int PIECES = GM_CK / 2;
+        const uint32_t da = dst0 + (uint32_t)(buf * GM_STAGE_BYTES);
+        const double* sa = srcA + kc * GM_CK;
 #pragma unroll
-        for (int i = 0; i < GM_BM * PIECES / GM_THREADS; ++i) {
-            const int idx = tid + i * GM_THREADS;
-            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
-            gm_cp_async16(as + row * GM_LD + c2, At + (int64_t)row * p.dpad + kc * GM_CK + c2);
-        }
+        for (int i = 0; i < GM_BM * PIECES / GM_THREADS; ++i)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(da + (uint32_t)(i * (GM_THREADS / PIECES) * GM_LD * 8)),
+                         "l"(sa + i * src_step)
+                         : "memory");
+        const uint32_t db = da + (uint32_t)(GM_BM * GM_LD * 8);
+        const double* sb = srcB + kc * GM_CK;
 #pragma unroll
-        for (int i = 0; i < GM_BN * PIECES / GM_THREADS; ++i) {
-            const int idx = tid + i * GM_THREADS;
-            const int row = idx / PIECES, c2 = (idx % PIECES) * 2;
-            gm_cp_async16(bs + row * GM_LD + c2, Bt + (int64_t)row * p.dpad + kc * GM_CK + c2);
-        }
+        for (int i = 0; i < GM_BN * PIECES / GM_THREADS; ++i)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(db + (uint32_t)(i * (GM_THREADS / PIECES) * GM_LD * 8)),
+                         "l"(sb + i * src_step)
+                         : "memory");
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
@@ -157,8 +187,10 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
         __syncthreads();
         const double* as = reinterpret_cast<const double*>(smem + buf * GM_STAGE_BYTES) + (warp * 32 + g) * GM_LD + q;
         const double* bs = reinterpret_cast<const double*>(smem + buf * GM_STAGE_BYTES) + GM_BM * GM_LD + g * GM_LD + q;
+        const int k4n = kc + 1 < nchunk ? GM_CK / 4 : p.k4_last;  // the last chunk may hold fewer than 16 coordinates
 #pragma unroll
         for (int k4 = 0; k4 < GM_CK / 4; ++k4) {
+            if (k4 >= k4n) break;
             double a[4], b[8];
 #pragma unroll
             for (int r = 0; r < 4; ++r) a[r] = as[r * 8 * GM_LD + k4 * 4];
@@ -184,6 +216,7 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
     const bool diag_tile = p.same_points && (p.row0 + row_base < col_base + GM_BN) && (col_base < p.row0 + row_base + GM_BM);
     const bool mirror = p.mirror && col_base >= row_base + GM_BM;  // strictly above the diagonal block: K[j][i] = K[i][j]
     const unsigned v_hi = p.v_hi;
+    const bool interior = p.vec_ok && row_base + GM_BM <= p.n0 && col_base + GM_BN <= p.n1;
     const int64_t col = col_base + 2 * lane;
     const int2 thr_c = *reinterpret_cast<const int2*>(p.thrB + col);
 #pragma unroll
@@ -199,13 +232,14 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
         }
         __syncwarp();
         const int64_t lrow0 = row_base + warp * 32 + h * 16;
+        double* dst = p.out + lrow0 * p.ldo + col;
+        const int* thr_rows = p.thrA + lrow0;
 #pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-            const int64_t lrow = lrow0 + i;  // row within this launch
+        for (int i = 0; i < 16; ++i, dst += p.ldo) {
             const int sw = ((i & 1) << 2) | ((i >> 1) & 3);
             double2* slot = reinterpret_cast<double2*>(stg + i * 64 + ((lane ^ sw) << 1));
             const double2 s = *slot;
-            const int thr_r = p.thrA[lrow];
+            const int thr_r = thr_rows[i];
             double v0, v1, k0, k1;
             if constexpr (EPI == PN_EPI_EXPQUAD) {
                 v0 = s.x;
@@ -234,24 +268,22 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
             bool bad0 = (unsigned)(h0 - t0) >= v_hi - (unsigned)t0;
             bool bad1 = (unsigned)(h1 - t1) >= v_hi - (unsigned)t1;
             if (diag_tile) {
-                bad0 |= p.row0 + lrow == col;
-                bad1 |= p.row0 + lrow == col + 1;
+                bad0 |= p.row0 + lrow0 + i == col;
+                bad1 |= p.row0 + lrow0 + i == col + 1;
             }
             if (bad0 | bad1) {  // rare: near duplicates, the diagonal, results at the underflow threshold
+                const int64_t lrow = lrow0 + i;  // row within this launch
                 if (bad0) k0 = gm_fix(p, lrow, col, s.x, h0, t0, diag_tile && p.row0 + lrow == col, tabE, tabL);
                 if (bad1) k1 = gm_fix(p, lrow, col + 1, s.y, h1, t1, diag_tile && p.row0 + lrow == col + 1, tabE, tabL);
             }
             if (mirror) *slot = make_double2(k0, k1);
-            if (lrow < p.n0) {
-                double* dst = p.out + lrow * p.ldo + col;
-                if (col + 1 < p.n1) {
-                    if (p.vec_ok) pn_store_cs2(dst, k0, k1);
-                    else {
-                        pn_store_cs1(dst, k0);
-                        pn_store_cs1(dst + 1, k1);
-                    }
-                } else if (col < p.n1) {
-                    pn_store_cs1(dst, k0);
+            if (interior) {  // uniform per CTA: no bounds to check, 16-byte aligned rows
+                pn_store_cs2(dst, k0, k1);
+            } else if (lrow0 + i < p.n0) {
+                if (col + 1 < p.n1 && p.vec_ok) pn_store_cs2(dst, k0, k1);
+                else {
+                    if (col < p.n1) pn_store_cs1(dst, k0);
+                    if (col + 1 < p.n1) pn_store_cs1(dst + 1, k1);
                 }
             }
         }
@@ -260,13 +292,13 @@ __global__ void __launch_bounds__(GM_THREADS, 3) gram_mma_kernel(const __grid_co
             const int t = lane & 15;
             const int sw = ((t & 1) << 2) | ((t >> 1) & 3);
             const int64_t mcol = lrow0 + t;  // column of the mirrored entry
-            const double* srow = stg + t * 64;
+            const double* srow = stg + t * 64 + (lane >> 4);
+            double* mdst = p.out + (col_base + (lane >> 4)) * p.ldo + mcol;
+            const int64_t mstep = 2 * p.ldo;
 #pragma unroll 8
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = 2 * jj + (lane >> 4);
-                const double v = srow[((jj ^ sw) << 1) + (lane >> 4)];
-                const int64_t mrow = col_base + j;
-                if (mrow < p.n1 && mcol < p.n0) pn_store_cs1(p.out + mrow * p.ldo + mcol, v);
+            for (int jj = 0; jj < 32; ++jj, mdst += mstep) {
+                const double v = srow[(jj ^ sw) << 1];
+                if (interior || (col_base + 2 * jj + (lane >> 4) < p.n1 && mcol < p.n0)) pn_store_cs1(mdst, v);
             }
             __syncwarp();
         }
@@ -281,6 +313,11 @@ cudaError_t launch_gm(const PnGramMmaLaunch& p, cudaStream_t stream) {
     const int64_t gx = (p.n1 + GM_BN - 1) / GM_BN, gy = (p.n0 + GM_BM - 1) / GM_BM;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
     dim3 grid((unsigned)gx, (unsigned)gy);
+    if (p.mirror) {
+        const int64_t tiles = gy * gx - gy * (gy - 1);
+        if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        grid = dim3((unsigned)tiles, 1);
+    }
     kern<<<grid, GM_THREADS, GM_SMEM_BYTES, stream>>>(p);
     ++g_pn_launches;
     return cudaGetLastError();
@@ -378,7 +415,9 @@ cudaError_t pn_launch_gram_mma(const PnGramMmaLaunch& p0, cudaStream_t stream) {
     if (p0.n0 <= 0 || p0.n1 <= 0) return cudaSuccess;
     PnGramMmaLaunch p = p0;
     p.vec_ok = ((p.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(p.out) % 16) == 0) ? 1 : 0;
-    p.mirror = (p.same_points && p.row0 == 0 && p.n0 == p.n1) ? 1 : 0;
+    // whole symmetric matrix: `mirror` carries the number of column tiles (> 0)
+    p.mirror = (p.same_points && p.row0 == 0 && p.n0 == p.n1) ? (int)((p.n1 + GM_BN - 1) / GM_BN) : 0;
+    p.k4_last = (p.d + 3) / 4 - (GM_CK / 4) * (p.dpad / GM_CK - 1);  // DMMA k-steps (of 4 coordinates) in the last chunk
     switch (p.epi.epi) {
         case PN_EPI_EXPQUAD: return launch_gm<PN_EPI_EXPQUAD>(p, stream);
         case PN_EPI_RATQUAD1: return launch_gm<PN_EPI_RATQUAD1>(p, stream);

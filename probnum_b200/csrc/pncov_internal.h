@@ -132,7 +132,9 @@ struct PnGramMmaLaunch {
     double* out;
     int64_t ldo;
     int vec_ok;            // filled by the launcher
-    int mirror;            // filled by the launcher: whole symmetric matrix, tiles below the diagonal blocks are mirrored copies
+    int mirror;            // filled by the launcher: > 0 (the number of column tiles) for a whole symmetric matrix,
+                           // whose tiles below the diagonal blocks are written as mirrored copies
+    int k4_last;           // filled by the launcher: DMMA k-steps in the last 16-coordinate chunk (1 .. 4)
     unsigned v_hi;         // fast epilogue valid while hi(v) < v_hi (v = S for ExpQuad, 1 + c S for RatQuad)
     PnEpiParams epi;       // epilogue in the units of the operands
     PnEpiParams epi_direct;  // epilogue of the direct form (original units)
