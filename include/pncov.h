@@ -159,6 +159,36 @@ PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void*
 #define PNCOV_OPT_FACTORISED 2 /* ExpQuad as exp(-|x|^2) exp(-|y|^2) exp(2 x.y) */
 PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value);
 
+/* covariance arithmetic in ONE launch ----------------------------------------------------
+ * replaces ScaledCovarianceFunction / SumCovarianceFunction / ProductCovarianceFunction._evaluate
+ * (/root/reference/src/probnum/randprocs/covfuncs/_arithmetic_fallbacks.py:55-56, :101-104, :163-166)
+ * for expressions whose leaves are isotropic ExpQuad / Matern / RatQuad kernels and WhiteNoise on the
+ * same points: the leaves share the squared distance S_ij, so the whole expression is evaluated per
+ * entry and written once (8 bytes per entry instead of one write per operand plus 24 bytes per
+ * combination).  After this call every dense-Gram entry point of the handle (pncov_gram*,
+ * pncov_chol_factor_gram, pncov_chol_solve_gram) evaluates the program; the matrix-free product
+ * returns PNCOV_ENOTIMPL.  The handle must hold float64 points, d <= 16, and have been created with
+ * an isotropic kernel (its own kernel is ignored from here on).
+ *   leaves (n_leaves <= 6, and at most 6 leaf evaluations in the steps): kinds[l] with lengthscales[l], nus[l] (Matern), alphas[l] (RatQuad alpha;
+ *     WhiteNoise sigma^2);
+ *   steps (n_steps <= 12, at most 4 between two leaf evaluations) over two values per entry, `acc` and `val`:
+ *     PNCOV_F_LOAD     val = leaf[leaf_index](S)      PNCOV_F_MULLEAF  val = val * leaf[leaf_index](S)
+ *     PNCOV_F_SCALEVAL val = val * a                  PNCOV_F_SET      acc = val
+ *     PNCOV_F_LIN      acc = fma(b, val, a * acc)     PNCOV_F_MUL      acc = acc * val
+ *     PNCOV_F_SCALEACC acc = acc * a
+ *   -- the arithmetic of pncov_combine_device, so the result is bit-identical to building the
+ *   operands one by one.  n_leaves = n_steps = 0 removes the program. */
+#define PNCOV_F_LOAD 0
+#define PNCOV_F_MULLEAF 1
+#define PNCOV_F_SCALEVAL 2
+#define PNCOV_F_SET 3
+#define PNCOV_F_LIN 4
+#define PNCOV_F_MUL 5
+#define PNCOV_F_SCALEACC 6
+PNCOV_API int pncov_set_program(pncov_handle* h, int n_leaves, const int* kinds, const double* lengthscales,
+                                const double* nus, const double* alphas, int n_steps, const int* ops,
+                                const int* leaf_index, const double* a, const double* b);
+
 /* elementwise evaluation out[b] = k(x0[b], x1[b]) -------------------------------------
  * replaces the broadcasting path of CovarianceFunction.__call__
  * (_covariance_function.py:280-357) after the caller has broadcast both arguments

@@ -20,6 +20,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpncov.so")
 EXPQUAD, MATERN, RATQUAD = 0, 1, 2
 LINEAR, POLYNOMIAL, WHITENOISE, PRODUCT_MATERN = 3, 4, 5, 6
 COMBINE_LINEAR, COMBINE_MULTIPLY = 0, 1
+F_LOAD, F_MULLEAF, F_SCALEVAL, F_SET, F_LIN, F_MUL, F_SCALEACC = range(7)  # pncov_set_program steps
+FUSED_MAX_LEAVES, FUSED_MAX_STEPS, FUSED_MAX_POST = 6, 12, 4
 OPT_IDENTITY, OPT_SYMMETRIC, OPT_FACTORISED = 0, 1, 2
 F64, F32 = 0, 1
 MAX_MATERN_P = 8
@@ -50,6 +52,9 @@ SIGNATURES = {
         ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int, _c_vp]),
     "pncov_matmul_sym_part_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
     "pncov_set_option": (ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.c_int]),
+    "pncov_set_program": (
+        ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp, _c_dp, ctypes.c_int,
+                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp]),
     "pncov_pairs": (
         ctypes.c_int,
         [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64, ctypes.c_double,
@@ -269,6 +274,20 @@ class Operator:
     def set_option(self, option: int, value: Optional[bool]) -> None:
         """OPT_IDENTITY / OPT_SYMMETRIC / OPT_FACTORISED: True, False or None (automatic)."""
         _check(self._lib.pncov_set_option(self._h, int(option), -1 if value is None else int(bool(value))))
+
+    def set_program(self, leaves, steps) -> None:
+        """Covariance arithmetic in one launch (pncov_set_program).  ``leaves``: sequence of
+        ``(kind, lengthscale, nu, alpha)``; ``steps``: sequence of ``(op, leaf_index, a, b)``."""
+        nl, ns = len(leaves), len(steps)
+        kinds = (ctypes.c_int * max(nl, 1))(*[int(l[0]) for l in leaves])
+        ls = (ctypes.c_double * max(nl, 1))(*[float(l[1]) for l in leaves])
+        nus = (ctypes.c_double * max(nl, 1))(*[float(l[2]) for l in leaves])
+        al = (ctypes.c_double * max(nl, 1))(*[float(l[3]) for l in leaves])
+        ops = (ctypes.c_int * max(ns, 1))(*[int(t[0]) for t in steps])
+        li = (ctypes.c_int * max(ns, 1))(*[int(t[1]) for t in steps])
+        aa = (ctypes.c_double * max(ns, 1))(*[float(t[2]) for t in steps])
+        bb = (ctypes.c_double * max(ns, 1))(*[float(t[3]) for t in steps])
+        _check(self._lib.pncov_set_program(self._h, nl, kinds, ls, nus, al, ns, ops, li, aa, bb))
 
     def conservative(self) -> None:
         """Direct differences and a fixed summation order for every product of this operator."""

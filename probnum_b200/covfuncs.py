@@ -646,6 +646,91 @@ class ProductMatern(_DenseOnly):
 
 # -- arithmetic (_arithmetic.py, _arithmetic_fallbacks.py) ----------------------------------------------
 _ARITH_BLOCK_BYTES = 4 << 30  # device-side row blocks of arithmetic results
+_FUSED_ARITHMETIC = True      # one-launch evaluation where the expression allows it (tests switch it off to compare)
+
+
+class _Unfusable(Exception):
+    pass
+
+
+def _compile_program(node):
+    """Translate an arithmetic expression into the program of ``pncov_set_program`` -- step for step the
+    operations `_combine_into` below applies to whole matrices, so both paths give the same bits -- or
+    return None when the expression does not fit: leaves must be isotropic ExpQuad / Matern / RatQuad or
+    WhiteNoise with d <= 16, at most 6 leaf evaluations, and the tree must evaluate with two values per entry
+    (a sum of [scaled] leaves or [scaled] products of leaves, optionally scaled as a whole)."""
+    leaves, steps = [], []
+
+    def leaf_index(k):
+        if isinstance(k, _ArithmeticNode) or max(k.input_size, 1) > 16:
+            raise _Unfusable
+        if isinstance(k, WhiteNoise):
+            desc = (_lib.WHITENOISE, 1.0, 0.5, float(k.sigma_sq))
+        elif isinstance(k, (ExpQuad, Matern, RatQuad)):
+            try:
+                kp = k._kernel_params()
+            except NotImplementedError:
+                raise _Unfusable from None
+            if kp.lengthscales.size != 1:
+                raise _Unfusable  # per-dimension lengthscales: S differs between the leaves
+            desc = (kp.kind, float(kp.lengthscales[0]), kp.nu, kp.alpha)
+        else:
+            raise _Unfusable
+        if desc not in leaves:
+            leaves.append(desc)
+        return leaves.index(desc)
+
+    def into_val(k):  # `val` = k, without touching `acc`
+        if isinstance(k, ScaledCovarianceFunction):
+            into_val(k._covfunc)
+            steps.append((_lib.F_SCALEVAL, 0, float(k._scalar), 0.0))
+        elif isinstance(k, ProductCovarianceFunction):
+            if any(isinstance(f, _ArithmeticNode) for f in k._factors):
+                raise _Unfusable
+            steps.append((_lib.F_LOAD, leaf_index(k._factors[0]), 0.0, 0.0))
+            for f in k._factors[1:]:
+                steps.append((_lib.F_MULLEAF, leaf_index(f), 0.0, 0.0))
+        elif isinstance(k, _ArithmeticNode):
+            raise _Unfusable
+        else:
+            steps.append((_lib.F_LOAD, leaf_index(k), 0.0, 0.0))
+
+    def into_acc(k):  # `acc` = k; mirrors _combine_into of each node type
+        if isinstance(k, ScaledCovarianceFunction):
+            into_acc(k._covfunc)
+            steps.append((_lib.F_SCALEACC, 0, float(k._scalar), 0.0))
+        elif isinstance(k, SumCovarianceFunction):
+            into_acc(k._summands[0])
+            for s_ in k._summands[1:]:
+                if isinstance(s_, ScaledCovarianceFunction):
+                    into_val(s_._covfunc)
+                    steps.append((_lib.F_LIN, 0, 1.0, float(s_._scalar)))
+                else:
+                    into_val(s_)
+                    steps.append((_lib.F_LIN, 0, 1.0, 1.0))
+        elif isinstance(k, ProductCovarianceFunction):
+            into_acc(k._factors[0])
+            for f in k._factors[1:]:
+                into_val(f)
+                steps.append((_lib.F_MUL, 0, 0.0, 0.0))
+        else:
+            into_val(k)
+            steps.append((_lib.F_SET, 0, 0.0, 0.0))
+
+    try:
+        into_acc(node)
+    except _Unfusable:
+        return None
+    evaluations = sum(1 for st in steps if st[0] in (_lib.F_LOAD, _lib.F_MULLEAF))
+    run = longest = 0
+    for st in steps:  # steps between two leaf evaluations
+        run = 0 if st[0] in (_lib.F_LOAD, _lib.F_MULLEAF) else run + 1
+        longest = max(longest, run)
+    if evaluations > _lib.FUSED_MAX_LEAVES or len(steps) > _lib.FUSED_MAX_STEPS or longest > _lib.FUSED_MAX_POST:
+        return None
+    # the handle only carries the points: any isotropic description with the right d will do
+    params = _lib.KernelParams(_lib.EXPQUAD, max(node.input_size, 1), np.ones(1))
+    return leaves, steps, params
 
 
 class _ArithmeticNode(CovarianceFunction):
@@ -694,6 +779,15 @@ class _ArithmeticNode(CovarianceFunction):
         if n0 == 0 or n1 == 0:
             return np.empty((n0, n1), dtype=out_dt)
         K = hostmem.empty((n0, n1), np.float64)
+        prog = _compile_program(self) if _FUSED_ARITHMETIC else None
+        if prog is not None and np.dtype(in_dt) == np.float64:
+            # all leaves share S_ij: the whole expression in ONE launch per row block, written once
+            leaves, steps, params = prog
+            pts0 = self._points(x0, np.float64)
+            with _lib.Operator(params, pts0, None if x1 is None else self._points(x1, np.float64)) as op:
+                op.set_program(leaves, steps)
+                op.gram(K)
+            return K if out_dt == np.float64 else K.astype(out_dt)
         rows = max(1, min(n0, _ARITH_BLOCK_BYTES // (8 * n1)))
         if rows >= n0:  # one block: keeps x1 = None, so the symmetric kernels apply
             with _lib.DeviceBuffer(8 * n0 * n1) as acc:

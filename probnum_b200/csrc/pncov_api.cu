@@ -427,6 +427,9 @@ struct pncov_handle {
     void* gm_thr[2] = {nullptr, nullptr};
     PnEpiParams gm_epi{};
     unsigned gm_v_hi = 0;
+    // covariance arithmetic in one launch (pncov_set_program): the dense Gram of this handle evaluates `prog`
+    bool has_prog = false;
+    PnFusedProgram prog{};
     // kernel-selection switches of the environment, read ONCE when the handle is created
     int env_ident = -1;   // PNCOV_MATVEC_IDENT: -1 unset, 0 "off", 1 "dfma"
     int env_fact = -1;    // PNCOV_MATVEC_FACT: 0 "off"
@@ -566,6 +569,7 @@ cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0,
                             cudaStream_t stream) {
     const Points& R = transpose ? h->p1 : h->p0;
     const Points& C = transpose ? h->p0 : h->p1;
+    if (h->has_prog) return pn_launch_gram_fused(gram_launch(h, transpose, row0, rows, out, ld), h->prog, stream);
     if (h->gm_dpad > 0) {  // ExpQuad / RatQuad with wide inputs: guarded norm identity on DMMA
         const int r = transpose ? 1 : 0, c = transpose ? 0 : 1;
         PnGramMmaLaunch p{};
@@ -612,6 +616,26 @@ cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0,
     g.exponent = h->k.exponent;
     g.out = out;
     g.ldo = ld;
+    if (h->k.extra_mode == 2 && h->symmetric && row0 == 0 && rows == R.n && h->k.d <= 8) {
+        // whole symmetric ProductMatern Gram: upper triangle + mirrored stores on the 64 grid, general kernel on the edges
+        int64_t ni = 0;
+        cudaError_t err = pn_launch_gram_pm_sym(gram_launch(h, transpose, row0, rows, out, ld), h->k.pm.data(), stream, &ni);
+        if (err != cudaSuccess) return err;
+        if (ni > 0) {
+            if (ni == g.n1) return cudaSuccess;
+            PnExtraLaunch e = g;  // right edge: all rows, remaining columns
+            e.x1_soa = static_cast<const char*>(C.soa) + (size_t)ni * 8;
+            e.n1 = g.n1 - ni;
+            e.out = static_cast<double*>(out) + ni;
+            if ((err = pn_launch_gram_extra(e, stream)) != cudaSuccess) return err;
+            e = g;  // bottom edge: remaining rows, interior columns
+            e.x0_soa = static_cast<const char*>(R.soa) + (size_t)ni * 8;
+            e.n0 = g.n0 - ni;
+            e.n1 = ni;
+            e.out = static_cast<double*>(out) + ni * ld;
+            return pn_launch_gram_extra(e, stream);
+        }
+    }
     return pn_launch_gram_extra(g, stream);
 }
 
@@ -777,6 +801,7 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         PN_CUDA(cudaMemset2DAsync(y, (size_t)ldy * es, 0, (size_t)k * es, (size_t)R.n, stream));
         return 0;
     }
+    if (h->has_prog) return fail(PNCOV_ENOTIMPL, "a handle with a program (pncov_set_program) serves the dense Gram only");
     if (h->k.extra_mode >= 0)
         return fail(PNCOV_ENOTIMPL, "the matrix-free product covers ExpQuad, Matern and RatQuad; use the dense Gram for this kernel");
     if (h->k.d > 1024) return fail(PNCOV_ENOTIMPL, "matrix-free product supports d <= 1024");
@@ -1654,6 +1679,62 @@ PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value) {
         case PNCOV_OPT_FACTORISED: h->opt_factorised = value; return 0;
         default: return fail(PNCOV_EINVAL, "unknown option");
     }
+}
+
+PNCOV_API int pncov_set_program(pncov_handle* h, int n_leaves, const int* kinds, const double* lengthscales, const double* nus,
+                                const double* alphas, int n_steps, const int* ops, const int* leaf_index, const double* a,
+                                const double* b) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (n_leaves == 0 && n_steps == 0) {  // back to the handle's own kernel
+        h->has_prog = false;
+        return 0;
+    }
+    if (n_leaves < 1 || n_leaves > PN_FUSED_MAX_LEAVES || n_steps < 1 || n_steps > PN_FUSED_MAX_STEPS)
+        return fail(PNCOV_ENOTIMPL, "programs hold 1..6 leaves and 1..12 steps");
+    if (!kinds || !lengthscales || !nus || !alphas || !ops || !leaf_index || !a || !b) return fail(PNCOV_EINVAL, "NULL argument");
+    if (h->k.dtype != PNCOV_F64 || h->k.ard || h->k.d > 16)
+        return fail(PNCOV_ENOTIMPL, "programs need float64 points, isotropic leaves and d <= 16");
+    PnFusedSlot leaves[PN_FUSED_MAX_LEAVES] = {};
+    for (int l = 0; l < n_leaves; ++l) {
+        PnFusedSlot& L = leaves[l];
+        if (kinds[l] == PNCOV_WHITENOISE) {  // _white_noise.py:38-55; sigma^2 travels in `alphas`
+            if (!(alphas[l] >= 0)) return fail(PNCOV_EINVAL, "sigma_sq must be non-negative");
+            L.whitenoise = 1;
+            L.sigma_sq = alphas[l];
+            continue;
+        }
+        if (kinds[l] != PNCOV_EXPQUAD && kinds[l] != PNCOV_MATERN && kinds[l] != PNCOV_RATQUAD)
+            return fail(PNCOV_ENOTIMPL, "program leaves are ExpQuad, Matern, RatQuad and WhiteNoise");
+        KernelDesc kd;
+        int rc = build_desc(kd, kinds[l], PNCOV_F64, h->k.d, &lengthscales[l], 1, nus[l], alphas[l]);
+        if (rc) return rc;
+        L.epi = kd.epi;
+    }
+    // regroup by leaf evaluation: a LOAD / MULLEAF opens a slot, the steps after it are its post-steps
+    PnFusedProgram F{};
+    for (int i = 0; i < n_steps; ++i) {
+        if (ops[i] < PN_F_LOAD || ops[i] > PN_F_SCALEACC) return fail(PNCOV_EINVAL, "unknown program step");
+        if (ops[i] <= PN_F_MULLEAF) {
+            if (leaf_index[i] < 0 || leaf_index[i] >= n_leaves) return fail(PNCOV_EINVAL, "leaf index out of range");
+            if (F.n_slots == PN_FUSED_MAX_LEAVES) return fail(PNCOV_ENOTIMPL, "programs evaluate at most 6 leaves");
+            PnFusedSlot& S = F.slots[F.n_slots++];
+            S = leaves[leaf_index[i]];
+            S.mul = ops[i] == PN_F_MULLEAF ? 1 : 0;
+            if (S.whitenoise) F.has_wn = 1;
+            if (!S.whitenoise && S.epi.epi == PN_EPI_RATQUADG) F.need_log = 1;
+        } else {
+            if (F.n_slots == 0) return fail(PNCOV_EINVAL, "a program starts with PNCOV_F_LOAD");
+            PnFusedSlot& S = F.slots[F.n_slots - 1];
+            if (S.n_post == PN_FUSED_MAX_POST) return fail(PNCOV_ENOTIMPL, "at most 4 steps between two leaf evaluations");
+            PnFusedStep& st = S.post[S.n_post++];
+            st.op = ops[i];
+            st.a = a[i];
+            st.b = b[i];
+        }
+    }
+    h->prog = F;
+    h->has_prog = true;
+    return 0;
 }
 
 PNCOV_API int pncov_matmul_path(const pncov_handle* h, int* path) {

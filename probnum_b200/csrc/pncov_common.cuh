@@ -22,6 +22,14 @@ enum PnEpi : int {
     // matrix-free product only: ExpQuad through exp(-|x|^2) exp(-|y|^2) exp(2 x.y); the kernel sees
     // u = -2 x.y straight from the DMMA accumulators and the two outer factors ride on v and y
     PN_EPI_EXPQUAD_FACT = 8,
+    // dense Gram only: a short program over several isotropic leaves that share S (covariance arithmetic)
+    PN_EPI_FUSED = 9,
+    // dense symmetric Gram only: ProductMatern whose dimensions share the degree p = 0 .. 3
+    // (_product_matern.py:103-122); the per-dimension parameters travel as PnPmProgram
+    PN_EPI_PM0 = 10,
+    PN_EPI_PM1 = 11,
+    PN_EPI_PM2 = 12,
+    PN_EPI_PM3 = 13,
 };
 
 struct PnEpiParams {
@@ -39,6 +47,52 @@ struct PnEpiParams {
     double g1, g2, g3, g4, g5;
     // validity window of the fast epilogue in terms of the hi word of S (see PnFlags)
     unsigned s_lo_word, s_hi_word;
+};
+
+// ---------------------------------------------------------------------------------------
+// Covariance arithmetic in one launch (Scaled / Sum / Product nodes of
+// /root/reference/src/probnum/randprocs/covfuncs/_arithmetic_fallbacks.py:55-56, :101-104, :163-166).
+// All leaves are isotropic kernels on the same points, so they share S_ij; the program below runs per
+// register tile over two values per entry, `acc` (the result so far) and `val` (the operand being
+// built), with exactly the arithmetic the operand-by-operand path applies to whole matrices
+// (combine_kernel in pncov_extra.cu): results are bit-identical to that path.
+// ---------------------------------------------------------------------------------------
+#define PN_FUSED_MAX_LEAVES 6   // leaf evaluations per program
+#define PN_FUSED_MAX_STEPS 12
+enum PnFusedOp : int {
+    PN_F_LOAD = 0,      // val = leaf(S)
+    PN_F_MULLEAF = 1,   // val = val * leaf(S)
+    PN_F_SCALEVAL = 2,  // val = val * a
+    PN_F_SET = 3,       // acc = val
+    PN_F_LIN = 4,       // acc = fma(b, val, a * acc)
+    PN_F_MUL = 5,       // acc = acc * val
+    PN_F_SCALEACC = 6,  // acc = acc * a
+};
+struct PnFusedStep {
+    int op, pad_;
+    double a, b;
+};
+// The kernels see the program regrouped by leaf evaluation ("slot"): evaluate the leaf (LOAD or MULLEAF), then
+// the steps that follow it up to the next leaf.  Slots are unrolled at compile time, so every epilogue constant
+// is an immediate constant-bank operand exactly as in the single-kernel launches.
+#define PN_FUSED_MAX_POST 4
+struct PnFusedSlot {
+    PnEpiParams epi;
+    double sigma_sq;  // WhiteNoise: sigma^2 where x0_i == x1_j (all coordinates), else 0
+    int whitenoise;
+    int mul;          // 0: val = leaf(S) (LOAD), 1: val = val * leaf(S) (MULLEAF)
+    int n_post, pad_;
+    PnFusedStep post[PN_FUSED_MAX_POST];
+};
+struct PnFusedProgram {
+    int n_slots;
+    int has_wn, need_log, pad_;
+    PnFusedSlot slots[PN_FUSED_MAX_LEAVES];
+};
+struct PnNoProgram {};
+// ProductMatern, d <= 8: per dimension {scale, p, c_0 .. c_8, pad} (PN_PM_LD doubles, pncov_internal.h)
+struct PnPmProgram {
+    double pm[8][12];
 };
 
 inline void pn_fill_math_constants(PnEpiParams& P) {

@@ -58,10 +58,11 @@ __device__ __forceinline__ void x_pm_dim(double (&A)[2 * X_R], double (&B)[2 * X
     for (int i = 0; i <= P; ++i) c[i] = pm[2 + i];
 #pragma unroll
     for (int r = 0; r < X_R; ++r) {
-        const double ra = fabs(xa[r] - xb.x) * s;
-        const double rb = fabs(xa[r] - xb.y) * s;
-        A[2 * r] += ra;
-        A[2 * r + 1] += rb;
+        // rounded product, then a plain addition (no FMA contraction): the reference's r_m and their sum
+        const double ra = __dmul_rn(fabs(xa[r] - xb.x), s);
+        const double rb = __dmul_rn(fabs(xa[r] - xb.y), s);
+        A[2 * r] = __dadd_rn(A[2 * r], ra);
+        A[2 * r + 1] = __dadd_rn(A[2 * r + 1], rb);
         if constexpr (P > 0) {
             double pa = c[P], pb = c[P];
 #pragma unroll
@@ -106,10 +107,10 @@ __device__ __forceinline__ void x_accumulate(double (&A)[2 * X_R], double (&B)[2
                 default:
 #pragma unroll
                     for (int r = 0; r < X_R; ++r) {
-                        const double ra = fabs(xa[r] - xb.x) * pm[0];
-                        const double rb = fabs(xa[r] - xb.y) * pm[0];
-                        A[2 * r] += ra;
-                        A[2 * r + 1] += rb;
+                        const double ra = __dmul_rn(fabs(xa[r] - xb.x), pm[0]);
+                        const double rb = __dmul_rn(fabs(xa[r] - xb.y), pm[0]);
+                        A[2 * r] = __dadd_rn(A[2 * r], ra);
+                        A[2 * r + 1] = __dadd_rn(A[2 * r + 1], rb);
                         B[2 * r] *= x_matern_poly(ra, pm);
                         B[2 * r + 1] *= x_matern_poly(rb, pm);
                     }
@@ -386,8 +387,8 @@ __global__ void pairs_extra_kernel(const __grid_constant__ PnExtraLaunch g) {
         else if constexpr (MODE == X_EQUAL) A += (a[m] == c[m]) ? 0.0 : 1.0;
         else {
             const double* pm = static_cast<const double*>(g.pm) + (size_t)m * PN_PM_LD;
-            const double r = fabs(a[m] - c[m]) * pm[0];
-            A += r;
+            const double r = __dmul_rn(fabs(a[m] - c[m]), pm[0]);
+            A = __dadd_rn(A, r);
             B *= x_matern_poly(r, pm);
         }
     }

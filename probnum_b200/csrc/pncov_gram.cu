@@ -56,8 +56,13 @@ __device__ __forceinline__ void epi_tile(const T (&S)[N], TOut (&K)[N], const Pn
 #pragma unroll
         for (int i = 0; i < N; ++i) K[i] = PnEpilogue<EPI>::fast((double)S[i], P, tabE, tabL, f);
         if (f.flagged(P)) {  // rare: diagonal tiles (sqrt of 0), subnormal results
+            // only the entries outside the window are redone: which path an entry takes depends on its own S alone,
+            // so K_ij and K_ji (equal S) get equal bits wherever they are evaluated
 #pragma unroll
-            for (int i = 0; i < N; ++i) K[i] = pn_epilogue((double)S[i], P, tabE, tabL);
+            for (int i = 0; i < N; ++i) {
+                const unsigned w = (unsigned)pn_hi((double)S[i]);
+                if (w < P.s_lo_word || w >= P.s_hi_word) K[i] = pn_epilogue((double)S[i], P, tabE, tabL);
+            }
         }
     }
 }
@@ -77,6 +82,66 @@ __device__ __forceinline__ void epi_dispatch(const T (&S)[N], TOut (&K)[N], cons
     }
 }
 
+// covariance arithmetic: the program of PnFusedProgram over one register tile (see pncov_common.cuh).
+// `eq` has bit i set where the two points of entry i are equal in every coordinate (WhiteNoise leaves).
+template <int N>
+__device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N], const PnFusedProgram& F, unsigned eq,
+                                           const double* tabE, const double* tabL) {
+    double val[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        K[i] = 0.0;
+        val[i] = 1.0;
+    }
+    // slots are unrolled at compile time: every epilogue constant is an immediate constant-bank operand.  Measured
+    // alternatives (profiles/README.md, round 2): a dynamic step loop, three merged code bodies instead of the eight
+    // compile-time epilogues, half tiles, and leaves behind a call were all slower (3.9 - 5.3 ms against 3.9 ms for
+    // the three-leaf sum at N = 32768); what limits this kernel is the register traffic at the control-flow merges
+    // of whole tiles (a third of the executed instructions are moves), not the FP64 pipe.
+#pragma unroll
+    for (int l = 0; l < PN_FUSED_MAX_LEAVES; ++l) {
+        if (l < F.n_slots) {  // uniform across the grid
+            const PnFusedSlot& L = F.slots[l];
+            double t[N];
+            if (L.whitenoise) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) t[i] = ((eq >> i) & 1u) ? L.sigma_sq : 0.0;
+            } else {
+                epi_dispatch(S, t, L.epi, tabE, tabL);
+            }
+            if (L.mul) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) val[i] *= t[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) val[i] = t[i];
+            }
+#pragma unroll
+            for (int j = 0; j < PN_FUSED_MAX_POST; ++j) {
+                if (j < L.n_post) {
+                    const PnFusedStep& st = L.post[j];
+                    if (st.op == PN_F_SCALEVAL) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) val[i] *= st.a;
+                    } else if (st.op == PN_F_SET) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) K[i] = val[i];
+                    } else if (st.op == PN_F_LIN) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) K[i] = pn_fma(st.b, val[i], st.a * K[i]);
+                    } else if (st.op == PN_F_MUL) {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) K[i] *= val[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < N; ++i) K[i] *= st.a;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <typename TOut>
 __device__ __forceinline__ void store_pair(TOut* row, int64_t j0, int64_t n1, TOut a, TOut b,
                                            bool vec_ok) {
@@ -93,9 +158,10 @@ __device__ __forceinline__ void store_pair(TOut* row, int64_t j0, int64_t n1, TO
 }
 
 // ---- strip kernel (d <= G_DMAX) ----------------------------------------------------------
-template <typename T, typename TOut, bool ARD>
+template <typename T, typename TOut, bool ARD, typename PROG>
 __global__ void __launch_bounds__(G_THREADS)
-    gram_strip_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta, int vec_ok) {
+    gram_strip_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta, int vec_ok, const __grid_constant__ PROG F) {
+    constexpr bool FUSED = !std::is_same<PROG, PnNoProgram>::value;
     extern __shared__ __align__(128) unsigned char smem[];
     using P2 = typename Pair<T>::type;
 
@@ -196,7 +262,27 @@ __global__ void __launch_bounds__(G_THREADS)
                 }
             }
             TOut K[2 * G_R];
-            epi_dispatch(S, K, g.epi, tabE, tabL);
+            if constexpr (FUSED) {
+                unsigned eq = 0;
+                if (F.has_wn) {  // S == 0 is necessary for equal points; squares may underflow, so confirm
+#pragma unroll
+                    for (int i = 0; i < 2 * G_R; ++i) eq |= (S[i] == T(0) ? 1u : 0u) << i;
+                    if (eq) {
+                        for (int m = 0; m < d; ++m) {
+                            const P2 xb = *reinterpret_cast<const P2*>(x1t + (size_t)m * G_TN);
+#pragma unroll
+                            for (int r = 0; r < G_R; ++r) {
+                                const T xa = x0t[m * G_TM + rg + r];
+                                if (!(xa == xb.x)) eq &= ~(1u << (2 * r));
+                                if (!(xa == xb.y)) eq &= ~(1u << (2 * r + 1));
+                            }
+                        }
+                    }
+                }
+                fused_tile(S, K, F, eq, tabE, tabL);
+            } else {
+                epi_dispatch(S, K, g.epi, tabE, tabL);
+            }
             const int rows_left = rows_here - rg;  // >= 1
 #pragma unroll
             for (int r = 0; r < G_R; ++r) {
@@ -349,13 +435,18 @@ __device__ __forceinline__ void pn_bulk_wait_read_all() { asm volatile("cp.async
 __device__ __forceinline__ void pn_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int EPI>
-struct SymHdr {  // barriers + exp2 table (+ log2 table for the general RatQuad epilogue only)
-    static constexpr int BYTES = 128 + 8 * PN_EXP2_N + (EPI == PN_EPI_RATQUADG ? 16 * PN_LOG2_N : 0);
+struct SymHdr {  // barriers + exp2 table (+ log2 table for the general RatQuad epilogue and for programs)
+    static constexpr int BYTES = 128 + 8 * PN_EXP2_N + (EPI == PN_EPI_RATQUADG || EPI == PN_EPI_FUSED ? 16 * PN_LOG2_N : 0);
 };
 
-template <int D, bool ARD, int EPI>
+template <int D, bool ARD, int EPI, typename PROG>
 __global__ void __launch_bounds__(Y_WARPS * 32, 4)
-    gram_sym_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta) {
+    gram_sym_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta, const __grid_constant__ PROG F) {
+    constexpr bool FUSED = EPI == PN_EPI_FUSED;
+    constexpr bool PM = EPI >= PN_EPI_PM0 && EPI <= PN_EPI_PM3;  // ProductMatern of uniform degree PMP
+    constexpr int PMP = PM ? EPI - PN_EPI_PM0 : 0;
+    static_assert(FUSED == std::is_same<PROG, PnFusedProgram>::value && PM == std::is_same<PROG, PnPmProgram>::value,
+                  "PN_EPI_FUSED comes with a PnFusedProgram, PN_EPI_PMx with a PnPmProgram");
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages, [2]: tables
@@ -384,7 +475,7 @@ __global__ void __launch_bounds__(Y_WARPS * 32, 4)
 #pragma unroll
         for (int m = 0; m < D; ++m)
             pn_bulk_g2s(x0s + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)t0 * Y_T, Y_T * 8, &bars[0]);
-        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
+        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG || FUSED);
     }
     double xb0[D], xb1[D], sc[D];
 #pragma unroll
@@ -416,6 +507,39 @@ __global__ void __launch_bounds__(Y_WARPS * 32, 4)
             double S[2 * G_R];
 #pragma unroll
             for (int i = 0; i < 2 * G_R; ++i) S[i] = 0.0;
+            double K[2 * G_R];
+            if constexpr (PM) {
+                // prod_m poly_p(r_m) exp(-r_m), r_m = |x0_m - x1_m| s_m: S accumulates sum_m r_m, K the polynomials
+                // (the operations and their order are those of gram_extra_kernel<X_PRODMATERN>: same bits)
+#pragma unroll
+                for (int i = 0; i < 2 * G_R; ++i) K[i] = 1.0;
+#pragma unroll
+                for (int m = 0; m < D; ++m) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h);
+                    const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h + 2);
+                    const double xa[G_R] = {a01.x, a01.y, a23.x, a23.y};
+                    const double s = F.pm[m][0];
+#pragma unroll
+                    for (int r = 0; r < G_R; ++r) {
+                        const double ra = __dmul_rn(fabs(xa[r] - xb0[m]), s);
+                        const double rb = __dmul_rn(fabs(xa[r] - xb1[m]), s);
+                        S[2 * r] = __dadd_rn(S[2 * r], ra);
+                        S[2 * r + 1] = __dadd_rn(S[2 * r + 1], rb);
+                        if constexpr (PMP > 0) {
+                            double pa = F.pm[m][2 + PMP], pb = F.pm[m][2 + PMP];
+#pragma unroll
+                            for (int i = PMP - 1; i >= 0; --i) {
+                                pa = pn_fma(pa, ra, F.pm[m][2 + i]);
+                                pb = pn_fma(pb, rb, F.pm[m][2 + i]);
+                            }
+                            K[2 * r] *= pa;
+                            K[2 * r + 1] *= pb;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2 * G_R; ++i) K[i] = K[i] * pn_exp2(S[i] * -1.4426950408889634074, tabE);
+            } else {
 #pragma unroll
             for (int m = 0; m < D; ++m) {
                 const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h);
@@ -433,8 +557,29 @@ __global__ void __launch_bounds__(Y_WARPS * 32, 4)
                     S[2 * r + 1] = pn_fma(db, db, S[2 * r + 1]);
                 }
             }
-            double K[2 * G_R];
-            epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+            }
+            if constexpr (PM) {
+            } else if constexpr (FUSED) {
+                unsigned eq = 0;
+                if (F.has_wn) {  // S == 0 is necessary for equal points; squares may underflow, so confirm
+#pragma unroll
+                    for (int i = 0; i < 2 * G_R; ++i) eq |= (S[i] == 0.0 ? 1u : 0u) << i;
+                    if (eq) {
+#pragma unroll
+                        for (int m = 0; m < D; ++m) {
+#pragma unroll
+                            for (int r = 0; r < G_R; ++r) {
+                                const double xa = x0t[m * Y_T + G_R * h + r];
+                                if (!(xa == xb0[m])) eq &= ~(1u << (2 * r));
+                                if (!(xa == xb1[m])) eq &= ~(1u << (2 * r + 1));
+                            }
+                        }
+                    }
+                }
+                fused_tile(S, K, F, eq, tabE, tabL);
+            } else {
+                epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+            }
             const int r0 = Y_RPW * warp + G_R * h;  // first row of this register tile within the tile
             double* optr = out + ((size_t)t * Y_T + r0) * row_stride + c0 + 2 * lane;
 #pragma unroll
@@ -574,17 +719,17 @@ cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int D, bool ARD, int EPI>
-cudaError_t launch_sym_inst(const PnGramLaunch& g, cudaStream_t stream) {
+template <int D, bool ARD, int EPI, typename PROG = PnNoProgram>
+cudaError_t launch_sym_inst(const PnGramLaunch& g, cudaStream_t stream, const PROG& F = PROG()) {
     const int64_t n_tiles = g.n0 / Y_T;
     const int64_t gy = (n_tiles + Y_TPC - 1) / Y_TPC;
     if (gy > 65535) return cudaErrorInvalidConfiguration;
     const size_t smem = SymHdr<EPI>::BYTES + 2 * sizeof(double) * D * Y_T + sizeof(double) * Y_T * Y_TLD;
-    auto kern = gram_sym_kernel<D, ARD, EPI>;
+    auto kern = gram_sym_kernel<D, ARD, EPI, PROG>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     dim3 grid((unsigned)n_tiles, (unsigned)gy);
-    kern<<<grid, Y_WARPS * 32, smem, stream>>>(g, Y_TPC);
+    kern<<<grid, Y_WARPS * 32, smem, stream>>>(g, Y_TPC, F);
     ++g_pn_launches;
     return cudaGetLastError();
 }
@@ -628,8 +773,8 @@ cudaError_t launch_fast(const PnGramLaunch& g, cudaStream_t stream) {
     }
 }
 
-template <typename T, typename TOut, bool ARD>
-cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
+template <typename T, typename TOut, bool ARD, typename PROG = PnNoProgram>
+cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream, const PROG& F = PROG()) {
     if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
     const int64_t strips = (g.n1 + G_TN - 1) / G_TN;
     const int vec_ok = ((g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % (2 * sizeof(TOut))) == 0) ? 1 : 0;
@@ -642,12 +787,13 @@ cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
         const int64_t gy = (n_tiles + tpc - 1) / tpc;
         if (gy > 65535) return cudaErrorInvalidConfiguration;
         const size_t smem = G_HDR_BYTES + 128 + sizeof(T) * ((size_t)g.d * G_TN + 2 * (size_t)g.d * G_TM);
-        auto kern = gram_strip_kernel<T, TOut, ARD>;
+        auto kern = gram_strip_kernel<T, TOut, ARD, PROG>;
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
         dim3 grid((unsigned)strips, (unsigned)gy);
-        kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc, vec_ok);
+        kern<<<grid, G_THREADS, smem, stream>>>(g, (int)tpc, vec_ok, F);
     } else {
+        if (!std::is_same<PROG, PnNoProgram>::value) return cudaErrorInvalidValue;  // programs: d <= G_DMAX
         const int64_t gy = (g.n0 + G_CHUNK_ROWS - 1) / G_CHUNK_ROWS;
         if (gy > 65535) {
             // split tall outputs into several launches
@@ -658,7 +804,7 @@ cudaError_t launch_typed(const PnGramLaunch& g, cudaStream_t stream) {
                 part.n0 = (g.n0 - r0 < rows_per_launch) ? g.n0 - r0 : rows_per_launch;
                 part.x0_soa = static_cast<const T*>(g.x0_soa) + r0;
                 part.out = static_cast<TOut*>(g.out) + r0 * g.ldo;
-                err = launch_typed<T, TOut, ARD>(part, stream);
+                err = launch_typed<T, TOut, ARD, PROG>(part, stream, F);
             }
             return err;
         }
@@ -723,4 +869,101 @@ cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
         if ((err = launch_generic(e, stream)) != cudaSuccess) return err;
     }
     return cudaSuccess;
+}
+
+// Covariance arithmetic in one launch: the program F over isotropic float64 leaves that share S (d <= 16).
+// A whole symmetric matrix (d <= 8, aligned) takes the mirrored-store kernel on its 64-grid interior -- the
+// leaves' FP64 work per stored entry halves, which is what keeps a three-leaf sum HBM-bound -- and the
+// general strip kernel on the edges; everything else is the strip kernel.
+template <int D>
+static cudaError_t launch_fused_sym(const PnGramLaunch& g, const PnFusedProgram& F, cudaStream_t stream) {
+    return launch_sym_inst<D, false, PN_EPI_FUSED, PnFusedProgram>(g, stream, F);
+}
+
+cudaError_t pn_launch_gram_fused(const PnGramLaunch& g, const PnFusedProgram& F, cudaStream_t stream) {
+    if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
+    if (g.in_f32 || g.scale != nullptr || g.d > G_DMAX || F.n_slots < 1 || F.n_slots > PN_FUSED_MAX_LEAVES) return cudaErrorInvalidValue;
+    const bool aligned = (g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
+    const bool sym = g.symmetric && g.n0 == g.n1 && g.x0_soa == g.x1_soa && g.d <= 8 && aligned && g.n0 >= 4 * Y_T;
+    if (!sym) return launch_typed<double, double, false, PnFusedProgram>(g, stream, F);
+    const int64_t ni = (g.n0 / Y_T) * Y_T;
+    PnGramLaunch in = g;
+    in.n0 = in.n1 = ni;
+    in.symmetric = 1;
+    cudaError_t err;
+    switch (g.d) {
+        case 1: err = launch_fused_sym<1>(in, F, stream); break;
+        case 2: err = launch_fused_sym<2>(in, F, stream); break;
+        case 3: err = launch_fused_sym<3>(in, F, stream); break;
+        case 4: err = launch_fused_sym<4>(in, F, stream); break;
+        case 5: err = launch_fused_sym<5>(in, F, stream); break;
+        case 6: err = launch_fused_sym<6>(in, F, stream); break;
+        case 7: err = launch_fused_sym<7>(in, F, stream); break;
+        default: err = launch_fused_sym<8>(in, F, stream); break;
+    }
+    if (err != cudaSuccess) return err;
+    if (ni < g.n1) {  // right edge: all rows, remaining columns
+        PnGramLaunch e = g;
+        e.symmetric = 0;
+        e.x1_soa = static_cast<const double*>(g.x1_soa) + ni;
+        e.n1 = g.n1 - ni;
+        e.out = static_cast<double*>(g.out) + ni;
+        if ((err = launch_typed<double, double, false, PnFusedProgram>(e, stream, F)) != cudaSuccess) return err;
+        // bottom edge: remaining rows, interior columns
+        e = g;
+        e.symmetric = 0;
+        e.x0_soa = static_cast<const double*>(g.x0_soa) + ni;
+        e.n0 = g.n0 - ni;
+        e.n1 = ni;
+        e.out = static_cast<double*>(g.out) + ni * g.ldo;
+        if ((err = launch_typed<double, double, false, PnFusedProgram>(e, stream, F)) != cudaSuccess) return err;
+    }
+    return cudaSuccess;
+}
+
+// ProductMatern whose dimensions share the degree p <= 3: symmetric interior (64 grid) of a whole symmetric Gram
+// through the mirrored-store kernel.  Returns the interior extent in *done (0: not applicable, nothing launched);
+// the caller writes the edges with the general kernel (pn_launch_gram_extra).
+template <int D, int EPI>
+static cudaError_t launch_pm_sym(const PnGramLaunch& g, const PnPmProgram& F, cudaStream_t stream) {
+    return launch_sym_inst<D, false, EPI, PnPmProgram>(g, stream, F);
+}
+template <int D>
+static cudaError_t launch_pm_sym_d(const PnGramLaunch& g, const PnPmProgram& F, int p, cudaStream_t stream) {
+    switch (p) {
+        case 0: return launch_pm_sym<D, PN_EPI_PM0>(g, F, stream);
+        case 1: return launch_pm_sym<D, PN_EPI_PM1>(g, F, stream);
+        case 2: return launch_pm_sym<D, PN_EPI_PM2>(g, F, stream);
+        default: return launch_pm_sym<D, PN_EPI_PM3>(g, F, stream);
+    }
+}
+
+cudaError_t pn_launch_gram_pm_sym(const PnGramLaunch& g, const double* pm_host, cudaStream_t stream, int64_t* done) {
+    *done = 0;
+    const bool aligned = (g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
+    if (!(g.symmetric && g.n0 == g.n1 && g.x0_soa == g.x1_soa && g.d <= 8 && aligned && g.n0 >= 4 * Y_T)) return cudaSuccess;
+    const int p = (int)pm_host[1];
+    if (p < 0 || p > 3) return cudaSuccess;
+    PnPmProgram F{};
+    for (int m = 0; m < g.d; ++m) {
+        if ((int)pm_host[m * PN_PM_LD + 1] != p) return cudaSuccess;  // mixed degrees: general kernel
+        for (int i = 0; i < PN_PM_LD; ++i) F.pm[m][i] = pm_host[m * PN_PM_LD + i];
+    }
+    const int64_t ni = (g.n0 / Y_T) * Y_T;
+    PnGramLaunch in = g;
+    in.n0 = in.n1 = ni;
+    in.symmetric = 1;
+    cudaError_t err;
+    switch (g.d) {
+        case 1: err = launch_pm_sym_d<1>(in, F, p, stream); break;
+        case 2: err = launch_pm_sym_d<2>(in, F, p, stream); break;
+        case 3: err = launch_pm_sym_d<3>(in, F, p, stream); break;
+        case 4: err = launch_pm_sym_d<4>(in, F, p, stream); break;
+        case 5: err = launch_pm_sym_d<5>(in, F, p, stream); break;
+        case 6: err = launch_pm_sym_d<6>(in, F, p, stream); break;
+        case 7: err = launch_pm_sym_d<7>(in, F, p, stream); break;
+        default: err = launch_pm_sym_d<8>(in, F, p, stream); break;
+    }
+    if (err == cudaSuccess) *done = ni;
+    return err;
 }

@@ -147,6 +147,11 @@ cudaError_t pn_launch_gram_mma_operands(const double* aos, int64_t n, int64_t ro
 cudaError_t pn_launch_gram_mma(const PnGramMmaLaunch& p, cudaStream_t stream);
 
 cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream);
+// ProductMatern of uniform degree, whole symmetric Gram: the 64-grid interior through the mirrored-store kernel; *done =
+// its extent (0: not applicable), the edges are the caller's
+cudaError_t pn_launch_gram_pm_sym(const PnGramLaunch& g, const double* pm_host, cudaStream_t stream, int64_t* done);
+// covariance arithmetic (Scaled / Sum / Product of isotropic leaves) in one launch; g.epi is ignored
+cudaError_t pn_launch_gram_fused(const PnGramLaunch& g, const PnFusedProgram& F, cudaStream_t stream);
 // pn_plan_matvec fills m.jsplit (how many column-range splits the launch will use, which
 // sizes the `partial` scratch); pn_launch_matvec then runs with that plan
 cudaError_t pn_plan_matvec(PnMatvecLaunch& m, int sm_count);
