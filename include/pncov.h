@@ -135,19 +135,28 @@ PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ld
 PNCOV_API int pncov_matmul_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y,
                         int64_t ldy, int transpose, void* stream);
 
-/* Symmetric operators (x1 == NULL at creation), one right-hand side, float64, d <= 8, n >= 2048:
- * pncov_matmul* evaluate every off-diagonal tile of K once and use it for both y_I and
- * y_J (half the exp / DMMA work; the partial sums are combined with atomic adds, so the summation
- * order, not the set of addends, varies between runs; PNCOV_MATVEC_SYM=off in the environment
- * selects the order-preserving kernel).
+/* Symmetric operators (x1 == NULL at creation), one right-hand side, float64, n >= 2048:
+ * pncov_matmul* evaluate every off-diagonal tile of K once and use it for both y_I and y_J (half the
+ * exp / DMMA work).  The partial sums of the CTAs are accumulated order-independently: each is split
+ * exactly into two integers on a per-component power-of-two grid and added with integer atomics, so the
+ * product is bit-for-bit reproducible from run to run (PNCOV_MATVEC_SYM=off in the environment still
+ * selects the kernel that evaluates all N^2 pairs).
  * pncov_matmul_sym_part_device is the multi-GPU form: caller `part` of `nparts` (one per GPU, each
  * with a handle over the SAME full point set) gets the contribution of row blocks part,
  * part + nparts, ... in the full-length vector y (n0 doubles, device memory, overwritten); the sum
  * of all parts (an all-reduce) is K @ v.  This is the reduce-scatter form of the row-sharded
- * product + all-gather named in SURVEY.md 8e.  Returns PNCOV_ENOTIMPL when the symmetric kernel
- * does not apply to the handle. */
+ * product + all-gather named in SURVEY.md 8e.
+ * pncov_matmul_sym_part_bins_device leaves the part's integer planes instead (3 n0 words of 8 bytes:
+ * two int64 planes and one float64 plane holding non-finite contributions only): summing the first
+ * 2 n0 words as int64 and the last n0 as float64 over the parts and passing the sums to
+ * pncov_matmul_sym_finish_device on any of the handles gives K @ v with the SAME bits for every
+ * nparts, including 1 (integer addition is associative).
+ * All return PNCOV_ENOTIMPL when the symmetric kernel does not apply to the handle. */
 PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void* y, int part, int nparts,
                                            void* stream);
+PNCOV_API int pncov_matmul_sym_part_bins_device(pncov_handle* h, const void* v, void* bins, int part, int nparts,
+                                                void* stream);
+PNCOV_API int pncov_matmul_sym_finish_device(pncov_handle* h, const void* bins, void* y, void* stream);
 
 /* Per-handle choice of the product kernels (value: 1 on, 0 off, -1 default = automatic, subject to the
  * PNCOV_MATVEC_IDENT / _SYM / _FACT environment switches).  Switching all three off selects the most
@@ -271,7 +280,7 @@ PNCOV_API int pncov_chol_last_factor_ms(pncov_chol* c, float* ms);
  * _mean_update (u v^T + v u^T, linalg/solvers/matrixbased.py:751-762) and _covariance_update
  * (Ws u^T, :764-775): the vectors live as rows of two device-resident (capacity, n) matrices U and
  * V, and a product with the first k of them is two kernel launches instead of k Python lambdas.
- *   pncov_chain_create   room for `capacity` vector pairs of length n on `device`
+ *   pncov_chain_create   room for `capacity` (<= 12800) vector pairs of length n on `device`
  *   pncov_chain_set      vector pair number `index` from host memory (blocking)
  *   pncov_chain_apply    y = C_k x for the ncols columns of x, (n, ncols) row-major host arrays, with
  *                        mode 0: C_k = sum_{i<k} U_i V_i^T + V_i U_i^T   (mean update chain)

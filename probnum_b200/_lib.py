@@ -22,6 +22,7 @@ LINEAR, POLYNOMIAL, WHITENOISE, PRODUCT_MATERN = 3, 4, 5, 6
 COMBINE_LINEAR, COMBINE_MULTIPLY = 0, 1
 F_LOAD, F_MULLEAF, F_SCALEVAL, F_SET, F_LIN, F_MUL, F_SCALEACC = range(7)  # pncov_set_program steps
 FUSED_MAX_LEAVES, FUSED_MAX_STEPS, FUSED_MAX_POST = 6, 12, 4
+CHAIN_MAX_CAPACITY = 12800  # pncov_chain_create: 2 * capacity coefficients fit the shared memory of one CTA
 OPT_IDENTITY, OPT_SYMMETRIC, OPT_FACTORISED = 0, 1, 2
 F64, F32 = 0, 1
 MAX_MATERN_P = 8
@@ -51,6 +52,8 @@ SIGNATURES = {
     "pncov_matmul_device": (
         ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64, ctypes.c_int, _c_vp]),
     "pncov_matmul_sym_part_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
+    "pncov_matmul_sym_part_bins_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
+    "pncov_matmul_sym_finish_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp]),
     "pncov_set_option": (ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.c_int]),
     "pncov_set_program": (
         ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp, _c_dp, ctypes.c_int,
@@ -308,6 +311,15 @@ class Operator:
         _check(self._lib.pncov_matmul_sym_part_device(self._h, _c_vp(v_ptr), _c_vp(y_ptr), int(part), int(nparts),
                                                       _c_vp(stream)))
 
+    def matmul_sym_part_bins_device(self, v_ptr: int, bins_ptr: int, part: int, nparts: int, stream: int = 0) -> None:
+        """Integer planes (3 n0 words of 8 bytes) of the contribution of row blocks part, part + nparts, ..."""
+        _check(self._lib.pncov_matmul_sym_part_bins_device(self._h, _c_vp(v_ptr), _c_vp(bins_ptr), int(part), int(nparts),
+                                                           _c_vp(stream)))
+
+    def matmul_sym_finish_device(self, bins_ptr: int, y_ptr: int, stream: int = 0) -> None:
+        """Summed integer planes -> y (n0 doubles)."""
+        _check(self._lib.pncov_matmul_sym_finish_device(self._h, _c_vp(bins_ptr), _c_vp(y_ptr), _c_vp(stream)))
+
     def last_kernel_ms(self) -> float:
         ms = ctypes.c_float()
         _check(self._lib.pncov_last_kernel_ms(self._h, ctypes.byref(ms)))
@@ -505,7 +517,9 @@ class UpdateChain:
         if len(self.pairs) == self.capacity:  # grow: new device matrices, vectors uploaded again
             old = self._h
             self._h = _c_vp()
-            self.capacity *= 2
+            if self.capacity >= CHAIN_MAX_CAPACITY:
+                raise MemoryError(f"an update chain holds at most {CHAIN_MAX_CAPACITY} rank-1 updates")
+            self.capacity = min(2 * self.capacity, CHAIN_MAX_CAPACITY)
             _check(self._lib.pncov_chain_create(ctypes.byref(self._h), self.device, self.n, self.capacity))
             self._lib.pncov_chain_destroy(old)
             for i, (a, b) in enumerate(self.pairs):

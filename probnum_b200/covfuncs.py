@@ -353,7 +353,7 @@ class CovarianceLinearOperator(linops.LinearOperator):
             for opt in (_lib.OPT_IDENTITY, _lib.OPT_SYMMETRIC, _lib.OPT_FACTORISED):
                 root._op.set_option(opt, False if want else None)
             root._op_conservative = want
-            root._last_product = None
+            root._memo_epoch = getattr(root, "_memo_epoch", 0) + 1  # invalidates the memos of root and transpose
         return root._op
 
     @property
@@ -362,17 +362,23 @@ class CovarianceLinearOperator(linops.LinearOperator):
 
     def _matmul(self, x: np.ndarray) -> np.ndarray:
         # The matrix-based solver applies A to the same vector twice per iteration
-        # (linalg/solvers/matrixbased.py:872 and :885).  The product is deterministic, so
-        # serving the repeat from the last (operand, result) pair is bit-identical and halves
-        # the device work of problinsolve.
+        # (linalg/solvers/matrixbased.py:872 and :885).  Every product kernel is deterministic (the
+        # symmetric-halving ones accumulate in exact integer planes), so serving the repeat from the
+        # last (operand, result) pair gives the bits a second launch would give and halves the device
+        # work of problinsolve.  The memo belongs to one kernel selection: the
+        # device operator is fetched first (it applies `_use_keops` and bumps the epoch on a change).
+        self._device_op()
+        root = self._parent if self._parent is not None else self
+        epoch = getattr(root, "_memo_epoch", 0)
         narrow = x.ndim == 2 and x.shape[-1] <= 8
         if narrow and self._last_product is not None:
-            last_x, last_y = self._last_product
-            if last_x.shape == x.shape and last_x.dtype == x.dtype and np.array_equal(last_x, x):
+            last_x, last_y, last_epoch = self._last_product
+            if (last_epoch == epoch and last_x.shape == x.shape and last_x.dtype == x.dtype
+                    and np.array_equal(last_x, x)):
                 return last_y.copy()
         y = self._matmul_device(x)
         if narrow:
-            self._last_product = (np.array(x, copy=True), y.copy())
+            self._last_product = (np.array(x, copy=True), y.copy(), epoch)
         return y
 
     def _matmul_device(self, x: np.ndarray) -> np.ndarray:

@@ -445,6 +445,9 @@ struct pncov_handle {
     size_t ypack_bytes = 0;
     void* partial = nullptr;
     size_t partial_bytes = 0;
+    void* bins = nullptr;  // symmetric-halving products: integer planes (2 n0 int64 + n0 doubles) and max |v|
+    size_t bins_bytes = 0;
+    void* vmax_dev = nullptr;
     void* stage = nullptr;  // device staging for host entry points
     size_t stage_bytes = 0;
     bool used_foreign_stream = false;  // a *_device entry point ran on a caller-owned stream
@@ -452,6 +455,7 @@ struct pncov_handle {
     int mma_state = 0;           // 0 = not examined, 1 = ready, -1 = not admissible for this data
     int mma_dpad = 8;            // coordinates per operand row (d padded to 8, 16, 32 or 64)
     bool last_sym = false;       // the last product ran the symmetric-halving kernel
+    bool last_fact = false;      // ... in the factorised ExpQuad form (row factors applied when the planes are finished)
     int last_use_mma = -1;       // kernel family of the last product (-1: none yet)
     // per-handle kernel selection (pncov_set_option); -1 = default (environment / automatic)
     int opt_identity = -1, opt_symmetric = -1, opt_factorised = -1;
@@ -791,8 +795,29 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
 // sym_nparts > 0 asks for the symmetric-halving kernel restricted to row blocks sym_part, sym_part +
 // sym_nparts, ... (the caller sums the partial vectors of all parts); it fails with PNCOV_ENOTIMPL
 // when that kernel does not apply to this handle.  sym_nparts == 0: whole product, best kernel.
+// integer planes of a symmetric-halving product -> y (row factors of the factorised ExpQuad form applied)
+int sym_finish(pncov_handle* h, const void* bins, void* y, int64_t ldy, cudaStream_t stream) {
+    const int64_t n = h->p0.n;
+    int rc;
+    if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)n * 8, h->stream))) return rc;
+    const double* fac = h->last_fact ? (const double*)h->a12[0] : nullptr;
+    PN_CUDA(pn_launch_unbin((const long long*)bins, n, n, (const double*)h->vmax_dev, fac, h->mma_dpad + 4, h->mma_dpad + 1,
+                            (double*)h->ypack, stream));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (h->last_fact)
+        unpack_y_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)h->ypack, n, 1, 1, 0, fac, h->mma_dpad + 4,
+                                                           h->mma_dpad + 1, (double*)y, ldy);
+    else
+        unpack_y_kernel<double><<<blocks, 256, 0, stream>>>((const double*)h->ypack, n, 1, 1, 0, (double*)y, ldy);
+    ++g_pn_launches;
+    PN_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// `bins_out`: with sym_nparts > 0, leave the integer planes of the partial product there (3 n0 words of 8 bytes,
+// overwritten) instead of finishing it into y
 int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy,
-                       bool transpose, cudaStream_t stream, int sym_part = 0, int sym_nparts = 0) {
+                       bool transpose, cudaStream_t stream, int sym_part = 0, int sym_nparts = 0, void* bins_out = nullptr) {
     const Points& R = transpose ? h->p1 : h->p0;
     const Points& C = transpose ? h->p0 : h->p1;
     const size_t es = h->k.elem();
@@ -854,10 +879,25 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;
         h->last_sym = m.sym != 0;
         h->last_use_mma = m.use_mma;
+        h->last_fact = m.sym != 0 && m.fact != 0;
     }
     PN_CUDA(pn_plan_matvec(m, h->sm_count));
     const int jsplit = m.jsplit;
     int rc;
+    void* bins = nullptr;
+    if (m.sym) {
+        // order-independent accumulation (pn_bin_add): max |v| and zeroed integer planes
+        if (!h->vmax_dev) PN_CUDA(pn_dev_alloc(&h->vmax_dev, sizeof(double), h->stream));
+        bins = bins_out;
+        if (!bins) {
+            if ((rc = ensure(&h->bins, &h->bins_bytes, (size_t)R.n * 24, h->stream))) return rc;
+            bins = h->bins;
+        }
+        PN_CUDA(pn_launch_vmax((const double*)v, ldv, C.n, (double*)h->vmax_dev, stream));
+        PN_CUDA(cudaMemsetAsync(bins, 0, (size_t)R.n * 24, stream));
+        m.bins = (long long*)bins;
+        m.vmax = (const double*)h->vmax_dev;
+    }
     if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * kc_max * es, h->stream))) return rc;
     if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)R.n * kc_max * es, h->stream))) return rc;
     if (jsplit > 1 && (rc = ensure(&h->partial, &h->partial_bytes, (size_t)jsplit * R.n * kc_max * 8, h->stream))) return rc;
@@ -884,6 +924,10 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.partial = h->partial;
         m.jsplit = jsplit;
         PN_CUDA(pn_launch_matvec(m, h->sm_count, stream));
+        if (m.sym) {
+            if (!bins_out && (rc = sym_finish(h, bins, y, ldy, stream))) return rc;
+            break;  // one right-hand side
+        }
         {
             const int64_t total = R.n * kc;
             const unsigned blocks = (unsigned)((total + 255) / 256);
@@ -1026,6 +1070,8 @@ PNCOV_API int pncov_destroy(pncov_handle* h) {
     pn_dev_free(h->vpack, fs);
     pn_dev_free(h->ypack, fs);
     pn_dev_free(h->partial, fs);
+    pn_dev_free(h->bins, fs);
+    pn_dev_free(h->vmax_dev, fs);
     pn_dev_free(h->stage, fs);
     pn_dev_free(h->a12[0], fs);
     pn_dev_free(h->b12[0], fs);
@@ -1152,6 +1198,31 @@ PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void*
     PN_CUDA(cudaEventRecord(h->ev1, stream));
     h->timed = true;
     return 0;
+}
+
+PNCOV_API int pncov_matmul_sym_part_bins_device(pncov_handle* h, const void* v, void* bins, int part, int nparts, void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNCOV_EINVAL, "bad part / nparts");
+    if (!v || !bins) return fail(PNCOV_EINVAL, "NULL operand");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
+    PN_CUDA(cudaEventRecord(h->ev0, stream));
+    int rc = matmul_device_impl(h, v, 1, 1, nullptr, 1, false, stream, part, nparts, bins);
+    if (rc) return rc;
+    PN_CUDA(cudaEventRecord(h->ev1, stream));
+    h->timed = true;
+    return 0;
+}
+
+PNCOV_API int pncov_matmul_sym_finish_device(pncov_handle* h, const void* bins, void* y, void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (!bins || !y) return fail(PNCOV_EINVAL, "NULL operand");
+    if (!h->last_sym || !h->vmax_dev) return fail(PNCOV_EINVAL, "no symmetric partial product was computed on this handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
+    return sym_finish(h, bins, y, 1, stream);
 }
 
 PNCOV_API int pncov_matmul(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy, int transpose) {
@@ -1607,7 +1678,8 @@ PNCOV_API int pncov_chain_destroy(pncov_chain* c) {
 PNCOV_API int pncov_chain_create(pncov_chain** out, int device, int64_t n, int64_t capacity) {
     if (!out) return fail(PNCOV_EINVAL, "out is NULL");
     *out = nullptr;
-    if (n < 1 || capacity < 1 || capacity > 16384) return fail(PNCOV_EINVAL, "bad chain shape");
+    // 2 * capacity coefficients live in the shared memory of chain_apply_kernel (at most 200 KB)
+    if (n < 1 || capacity < 1 || capacity > 12800) return fail(PNCOV_EINVAL, "bad chain shape (capacity is at most 12800 updates)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();

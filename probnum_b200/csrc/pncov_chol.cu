@@ -724,6 +724,7 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
 
 // b: (npad, nrhs) row-major, nrhs <= 8, overwritten with the solution of L L^T x = b
 cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream) {
+    if (nrhs < 1 || nrhs > 8) return cudaErrorInvalidValue;  // the kernels' shared arrays hold at most 8 right-hand sides
     const int64_t T = npad / CB;
     const int64_t SB = (T + CS - 1) / CS;
     for (int64_t sb = 0; sb < SB; ++sb) {  // L y = b

@@ -348,6 +348,42 @@ __device__ __forceinline__ void pn_stage_tables_tma(double* tabE, double* tabL, 
     if (need_log) pn_bulk_g2s(tabL, pn_log2_table_g, 16u * PN_LOG2_N, bar);
 }
 
+// ---------------------------------------------------------------------------------------
+// Order-independent accumulation for the symmetric-halving products.  Those kernels add the partial
+// sums of many CTAs into one vector; floating-point atomics would make the result depend on the order
+// in which the CTAs retire.  Instead every partial sum s is split exactly into two integers on a
+// per-target power-of-two grid, s = hi 2^(E-52) + lo 2^(E-100) + (|.| <= 2^(E-101)), and the integers
+// are added with 64-bit integer atomics: integer addition is associative, so the vector comes out bit
+// for bit the same on every run -- and for every split of the row blocks over GPUs, whose integer
+// planes are summed by an all-reduce.  2^E bounds the sum of the magnitudes of everything that can
+// reach the target (n1 max|v| / f_t for the factorised ExpQuad form, n1 max|v| otherwise), so neither
+// plane overflows; the resolution 2^(E-101) is far below the rounding of the partial sums themselves.
+// Non-finite partial sums (NaN / Inf in v or in the points) are added as doubles to a third plane:
+// their sums do not depend on the order either (IEEE: Inf + Inf = Inf, Inf - Inf = NaN, x + NaN = NaN).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double pn_pow2(int e) { return pn_make((e + 1023) << 20, 0); }
+// E for a target with factor f (1 when the product is not factorised); bound0 = n1 * max|v|
+__device__ __forceinline__ int pn_bin_exponent(double bound0, double f) {
+    const int e = ((pn_hi(bound0) >> 20) & 0x7ff) - ((pn_hi(f) >> 20) & 0x7ff) + 2;
+    return max(-920, min(1023, e));  // 2^(E-100) stays a normal number, 2^E a finite one
+}
+__device__ __forceinline__ void pn_bin_add(long long* hi_plane, long long* lo_plane, double* nf_plane, int64_t idx, double s,
+                                           int E) {
+    if (!(fabs(s) <= pn_pow2(E))) {  // NaN, Inf (or a bound violated by non-finite input)
+        atomicAdd(nf_plane + idx, s);
+        return;
+    }
+    const long long hi = __double2ll_rn(s * pn_pow2(52 - E));
+    const double rem = fma(-(double)hi, pn_pow2(E - 52), s);  // exact: |hi| <= 2^52
+    const long long lo = __double2ll_rn(rem * pn_pow2(100 - E));
+    if (hi) atomicAdd(reinterpret_cast<unsigned long long*>(hi_plane + idx), (unsigned long long)hi);
+    if (lo) atomicAdd(reinterpret_cast<unsigned long long*>(lo_plane + idx), (unsigned long long)lo);
+}
+__device__ __forceinline__ double pn_bin_value(long long hi, long long lo, double nf, int E) {
+    const double y = fma((double)lo, pn_pow2(E - 100), (double)hi * pn_pow2(E - 52));
+    return nf != 0.0 ? nf + y : y;
+}
+
 // streaming (evict-first) stores for write-once outputs
 __device__ __forceinline__ void pn_store_cs2(double* p, double a, double b) {
     __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));

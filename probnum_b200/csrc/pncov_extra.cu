@@ -603,7 +603,13 @@ cudaError_t pn_launch_chain_apply(const double* U, const double* V, int64_t ld, 
     chain_dots_kernel<<<dim3((unsigned)splits, (unsigned)k, 2), R2_THREADS, 0, stream>>>(U, V, ld, n, k, x, partial, splits);
     ++g_pn_launches;
     const unsigned blocks = (unsigned)((n + 2 * R2_THREADS - 1) / (2 * R2_THREADS));
-    chain_apply_kernel<<<blocks, R2_THREADS, (size_t)2 * k * 8, stream>>>(U, V, ld, n, k, partial, splits, mode, y);
+    const size_t coef_bytes = (size_t)2 * k * 8;  // above 48 KB (k > 3072) the launch needs the opt-in attribute
+    if (coef_bytes > 48 * 1024) {
+        if (coef_bytes > 200 * 1024) return cudaErrorInvalidValue;  // pncov_chain_create caps the capacity accordingly
+        cudaError_t err = cudaFuncSetAttribute(chain_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)coef_bytes);
+        if (err != cudaSuccess) return err;
+    }
+    chain_apply_kernel<<<blocks, R2_THREADS, coef_bytes, stream>>>(U, V, ld, n, k, partial, splits, mode, y);
     ++g_pn_launches;
     return cudaGetLastError();
 }

@@ -48,10 +48,12 @@ struct PnMatvecLaunch {
     const void* a12;
     const void* b12;
     int use_mma;         // 0: direct differences, 1: norm identity with DFMA, 2: norm identity with DMMA
-    // symmetric halving (x1 is x0, kc == 1, use_mma == 2): each off-diagonal tile is evaluated once
-    // and serves y_I and y_J; row blocks part, part + nparts, ... only (multi-GPU), y accumulated
-    // with atomics from zero
+    // symmetric halving (x1 is x0, kc == 1): each off-diagonal tile is evaluated once and serves y_I and
+    // y_J; row blocks part, part + nparts, ... only (multi-GPU).  The partial sums go to the integer
+    // planes `bins` (see pn_bin_add in pncov_common.cuh; zero on entry), not to y
     int sym, sym_part, sym_nparts;
+    long long* bins;      // [hi plane (n0) | lo plane (n0)] followed by the non-finite plane (n0 doubles)
+    const double* vmax;   // device scalar: max |v_j| over the original right-hand side
     // ExpQuad in factorised form (use_mma == 2): a12[.][9] / b12[.][9] hold exp(-|xt|^2); v arrives
     // multiplied by the column factors, y leaves to be multiplied by the row factors
     int fact;
@@ -157,6 +159,11 @@ cudaError_t pn_launch_gram_fused(const PnGramLaunch& g, const PnFusedProgram& F,
 cudaError_t pn_plan_matvec(PnMatvecLaunch& m, int sm_count);
 cudaError_t pn_launch_matvec(const PnMatvecLaunch& m, int sm_count, cudaStream_t stream);
 cudaError_t pn_launch_pairs(const PnPairsLaunch& p, cudaStream_t stream);
+// symmetric-halving products: max |v| into *vmax (device), and the integer planes back to doubles
+// (fac: operand rows holding the factor of the factorised ExpQuad form at [i * fac_ld + fac_idx], or nullptr)
+cudaError_t pn_launch_vmax(const double* v, int64_t ldv, int64_t n, double* vmax, cudaStream_t stream);
+cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int64_t n1, const double* vmax, const double* fac, int fac_ld,
+                            int fac_idx, double* y, cudaStream_t stream);
 
 // pncov_api.cu
 extern int64_t g_pn_launches;

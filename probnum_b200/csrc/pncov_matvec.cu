@@ -432,7 +432,11 @@ __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
     if (jt0 >= jt1) return;
     const double* bg = static_cast<const double*>(a.b12);
     const double* vg = static_cast<const double*>(a.v);
-    double* yg = static_cast<double*>(a.y);
+    long long* const bhi = a.bins;
+    long long* const blo = a.bins + a.n0;
+    double* const bnf = reinterpret_cast<double*>(a.bins + 2 * a.n0);
+    const double bound0 = (double)a.n1 * *a.vmax;
+    constexpr bool FACT = EPI == PN_EPI_EXPQUAD_FACT;
     constexpr uint32_t B_BYTES = Cfg::TJ * Cfg::LD * 8, V_BYTES = Cfg::TJ * 8;
 
     if (tid == 0) {
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
 #pragma unroll
             for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * Cfg::TJ + tid];
             const int64_t col = (jt - 1) * Cfg::TJ + tid;
-            if (col < a.n1) atomicAdd(yg + col, s);
+            if (col < a.n1) pn_bin_add(bhi, blo, bnf, col, s, pn_bin_exponent(bound0, FACT ? bg[col * Cfg::LD + Cfg::NRM + 1] : 1.0));
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
         const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
@@ -557,7 +561,7 @@ __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
 #pragma unroll
         for (int w = 1; w < MM_THREADS / 32; ++w) s += cw[w * Cfg::TJ + tid];
         const int64_t col = (jt1 - 1) * Cfg::TJ + tid;
-        if (col < a.n1) atomicAdd(yg + col, s);
+        if (col < a.n1) pn_bin_add(bhi, blo, bnf, col, s, pn_bin_exponent(bound0, FACT ? bg[col * Cfg::LD + Cfg::NRM + 1] : 1.0));
     }
     // row sums
 #pragma unroll
@@ -566,7 +570,9 @@ __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
         double s = acc[rg];
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (q == 0 && row < a.n0) atomicAdd(yg + row, s);
+        if (q == 0 && row < a.n0)
+            pn_bin_add(bhi, blo, bnf, row, s,
+                       pn_bin_exponent(bound0, FACT ? static_cast<const double*>(a.a12)[row * Cfg::LD + Cfg::NRM + 1] : 1.0));
     }
 }
 
@@ -603,7 +609,10 @@ __global__ void __launch_bounds__(MV_THREADS)
     if (jt0 >= jt1) return;
     const double* x1g = static_cast<const double*>(a.x1_aos);
     const double* vg = static_cast<const double*>(a.v);
-    double* yg = static_cast<double*>(a.y);
+    long long* const bhi = a.bins;
+    long long* const blo = a.bins + a.n0;
+    double* const bnf = reinterpret_cast<double*>(a.bins + 2 * a.n0);
+    const int binE = pn_bin_exponent((double)a.n1 * *a.vmax, 1.0);  // every kernel value is <= 1
     constexpr uint32_t X_BYTES = MV_TJ * D * 8, V_BYTES = MV_TJ * 8;
 
     if (tid == 0) {
@@ -654,7 +663,7 @@ __global__ void __launch_bounds__(MV_THREADS)
 #pragma unroll
             for (int w = 1; w < MV_THREADS / 32; ++w) s += cwp[w * MV_TJ + tid];
             const int64_t col = (jt - 1) * MV_TJ + tid;
-            if (col < a.n1) atomicAdd(yg + col, s);
+            if (col < a.n1) pn_bin_add(bhi, blo, bnf, col, s, binE);
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
         const double* xt = stage0 + (size_t)buf * STAGE_DOUBLES;
@@ -711,12 +720,12 @@ __global__ void __launch_bounds__(MV_THREADS)
 #pragma unroll
         for (int w = 1; w < MV_THREADS / 32; ++w) s += cwp[w * MV_TJ + tid];
         const int64_t col = (jt1 - 1) * MV_TJ + tid;
-        if (col < a.n1) atomicAdd(yg + col, s);
+        if (col < a.n1) pn_bin_add(bhi, blo, bnf, col, s, binE);
     }
 #pragma unroll
     for (int r = 0; r < MV_R; ++r) {
         const int64_t row = row0 + (int64_t)r * MV_THREADS;
-        if (row < a.n0) atomicAdd(yg + row, acc[r]);
+        if (row < a.n0) pn_bin_add(bhi, blo, bnf, row, acc[r], binE);
     }
 }
 
@@ -948,7 +957,10 @@ __global__ void __launch_bounds__(MR_THREADS)
     const int64_t row = bx * MR_THREADS + tid;  // padded rows are readable (zeros)
     for (int m = 0; m < d; ++m) xr[m * MR_THREADS + tid] = x_soa[(size_t)m * ld + row];
     const double* vg = static_cast<const double*>(a.v);
-    double* yg = static_cast<double*>(a.y);
+    long long* const bhi = a.bins;
+    long long* const blo = a.bins + a.n0;
+    double* const bnf = reinterpret_cast<double*>(a.bins + 2 * a.n0);
+    const int binE = pn_bin_exponent((double)a.n1 * *a.vmax, 1.0);  // every kernel value is <= 1
     const double vrow = vg[row];  // zero in the padding
     double acc = 0.0;
 
@@ -963,7 +975,7 @@ __global__ void __launch_bounds__(MR_THREADS)
 #pragma unroll
             for (int w = 1; w < MR_THREADS / 32; ++w) s += cwp[w * MR_TJ + tid];
             const int64_t col = (jt - 1) * MR_TJ + tid;
-            if (col < a.n1) atomicAdd(yg + col, s);
+            if (col < a.n1) pn_bin_add(bhi, blo, bnf, col, s, binE);
         }
         for (int idx = tid; idx < d * MR_TJ; idx += MR_THREADS) {
             const int m = idx / MR_TJ, j = idx % MR_TJ;
@@ -1016,9 +1028,32 @@ __global__ void __launch_bounds__(MR_THREADS)
 #pragma unroll
         for (int w = 1; w < MR_THREADS / 32; ++w) s += cwp[w * MR_TJ + tid];
         const int64_t col = (jt1 - 1) * MR_TJ + tid;
-        if (col < a.n1) atomicAdd(yg + col, s);
+        if (col < a.n1) pn_bin_add(bhi, blo, bnf, col, s, binE);
     }
-    if (row < a.n0) atomicAdd(yg + row, acc);
+    if (row < a.n0) pn_bin_add(bhi, blo, bnf, row, acc, binE);
+}
+
+// max |v_j| as the bit pattern of a non-negative double (unsigned order = numeric order; NaN sorts above Inf)
+__global__ void vmax_kernel(const double* __restrict__ v, int64_t ldv, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[i * ldv]));
+        m = b > m ? b : m;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = t > m ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// integer planes -> y (the same exponents the kernels used: pn_bin_exponent of the same inputs)
+__global__ void unbin_kernel(const long long* __restrict__ bins, int64_t n0, int64_t n1, const double* __restrict__ vmax,
+                             const double* __restrict__ fac, int fac_ld, int fac_idx, double* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0) return;
+    const int E = pn_bin_exponent((double)n1 * *vmax, fac ? fac[i * fac_ld + fac_idx] : 1.0);
+    y[i] = pn_bin_value(bins[i], bins[n0 + i], reinterpret_cast<const double*>(bins + 2 * n0)[i], E);
 }
 
 // partial[s][i] summed over s in increasing order (deterministic)
@@ -1208,7 +1243,7 @@ cudaError_t launch_direct_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     if (chunks > 65535) return cudaErrorInvalidConfiguration;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    if ((err = cudaMemsetAsync(a.y, 0, (size_t)a.n0 * sizeof(double), stream)) != cudaSuccess) return err;
+    if (!a.bins || !a.vmax) return cudaErrorInvalidValue;  // zeroed integer planes + max |v| come from the caller
     dim3 grid((unsigned)row_ctas, (unsigned)chunks);
     kern<<<grid, MV_THREADS, smem, stream>>>(a, (int)tps, a.sym_part, nparts);
     ++g_pn_launches;
@@ -1264,7 +1299,7 @@ cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     if (chunks > 65535) return cudaErrorInvalidConfiguration;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    if ((err = cudaMemsetAsync(a.y, 0, (size_t)a.n0 * sizeof(double), stream)) != cudaSuccess) return err;
+    if (!a.bins || !a.vmax) return cudaErrorInvalidValue;  // zeroed integer planes + max |v| come from the caller
     dim3 grid((unsigned)row_ctas, (unsigned)chunks);
     kern<<<grid, MM_THREADS, smem, stream>>>(a, (int)tps, a.sym_part, nparts);
     ++g_pn_launches;
@@ -1375,7 +1410,7 @@ cudaError_t launch_rows_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     auto kern = matvec_rows_sym_kernel<ARD>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    if ((err = cudaMemsetAsync(a.y, 0, (size_t)a.n0 * sizeof(double), stream)) != cudaSuccess) return err;
+    if (!a.bins || !a.vmax) return cudaErrorInvalidValue;  // zeroed integer planes + max |v| come from the caller
     dim3 grid((unsigned)row_ctas, (unsigned)chunks);
     kern<<<grid, MR_THREADS, smem, stream>>>(a, static_cast<const double*>(a.x0_soa), a.ld0, (int)tps, a.sym_part, nparts);
     ++g_pn_launches;
@@ -1463,4 +1498,22 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
         err = cudaGetLastError();
     }
     return err;
+}
+
+cudaError_t pn_launch_vmax(const double* v, int64_t ldv, int64_t n, double* vmax, cudaStream_t stream) {
+    cudaError_t err = cudaMemsetAsync(vmax, 0, sizeof(double), stream);
+    if (err != cudaSuccess || n <= 0) return err;
+    int64_t blocks = (n + 255) / 256;
+    blocks = blocks > 1024 ? 1024 : blocks;
+    vmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(v, ldv, n, reinterpret_cast<unsigned long long*>(vmax));
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int64_t n1, const double* vmax, const double* fac, int fac_ld,
+                            int fac_idx, double* y, cudaStream_t stream) {
+    if (n0 <= 0) return cudaSuccess;
+    unbin_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(bins, n0, n1, vmax, fac, fac_ld, fac_idx, y);
+    ++g_pn_launches;
+    return cudaGetLastError();
 }

@@ -12,6 +12,7 @@ cost again.  Small results use ordinary pageable memory.
 from __future__ import annotations
 
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -19,8 +20,11 @@ import numpy as np
 from . import _lib
 
 PINNED_THRESHOLD_BYTES = 4 << 20
-_MAX_CACHED_BYTES = 20 << 30
-_free = {}  # nbytes -> [ptr, ...]
+# Page-locked memory kept on the free list per process after its arrays are gone (unswappable: with one process
+# per GPU this is multiplied by the number of ranks).  PNCOV_PINNED_CACHE_GIB overrides the default of 18 GiB,
+# which holds the two 8.6 GB results of BASELINE configs[1]; 0 disables the cache.
+_MAX_CACHED_BYTES = int(float(os.environ.get("PNCOV_PINNED_CACHE_GIB", "18")) * (1 << 30))
+_free = {}  # nbytes -> [ptr, ...] (dict order = insertion order: the oldest size class is evicted first)
 _cached_bytes = 0
 _lock = threading.Lock()
 
@@ -55,12 +59,24 @@ class _PinnedBlock:
         if ptr is None:
             return
         try:
+            evicted = []
             with _lock:
-                if _cached_bytes + self.nbytes <= _MAX_CACHED_BYTES:
+                if self.nbytes <= _MAX_CACHED_BYTES:
+                    # make room by dropping the oldest cached blocks (differently sized results never reuse them)
+                    while _cached_bytes + self.nbytes > _MAX_CACHED_BYTES and _free:
+                        size = next(iter(_free))
+                        lst = _free[size]
+                        evicted.append(lst.pop(0))
+                        _cached_bytes -= size
+                        if not lst:
+                            del _free[size]
                     _free.setdefault(self.nbytes, []).append(ptr)
                     _cached_bytes += self.nbytes
-                    return
-            _lib.load().pncov_host_free(ctypes.c_void_p(ptr))
+                    ptr = None
+            for p in evicted:
+                _lib.load().pncov_host_free(ctypes.c_void_p(p))
+            if ptr is not None:
+                _lib.load().pncov_host_free(ctypes.c_void_p(ptr))
         except Exception:  # pragma: no cover - interpreter shutdown
             pass
 

@@ -30,6 +30,7 @@ reference's behaviour for them, not a fallback of ours.
 
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import numpy as np
@@ -278,15 +279,12 @@ def enable(sharded: Optional[bool] = None, _local_factory=None) -> None:
 # ---------------------------------------------------------------------------------------------
 class DeviceCholesky:
     """Stand-in for the ``(c, lower)`` pair of ``scipy.linalg.cho_factor``: the factor of
-    ``gram + jitter I`` stays in HBM; only right-hand sides and solutions cross PCIe.
+    ``gram + jitter I`` stays in HBM (the hand-written blocked FP64 Cholesky of libpncov,
+    csrc/pncov_chol.cu, DMMA trailing updates); only right-hand sides and solutions cross PCIe.
+    (The cuSOLVER baseline the survey names for this row lives in tools/cusolver_baseline.py.)"""
 
-    ``backend="pncov"`` (default): the hand-written blocked FP64 Cholesky of libpncov
-    (csrc/pncov_chol.cu, DMMA trailing updates).  ``backend="cusolver"``: cuSOLVER ``potrf`` /
-    ``potrs`` through torch, the library baseline the survey names for this row."""
-
-    def __init__(self, factor, backend: str):
-        self.factor = factor  # _lib.Cholesky, or an (n, n) lower-triangular torch.float64 CUDA tensor
-        self.backend = backend
+    def __init__(self, factor):
+        self.factor = factor  # _lib.Cholesky
 
     # scipy returns a 2-tuple; the reference only ever passes it back to gram_cho_solve
     def __iter__(self):
@@ -297,58 +295,41 @@ class DeviceCholesky:
 
     def solve(self, z: np.ndarray) -> np.ndarray:
         zz = np.asarray(z, dtype=np.float64)
-        if self.backend == "pncov":
-            return self.factor.solve(zz.reshape(zz.shape[0], -1)).reshape(zz.shape)
-        import torch  # noqa: PLC0415
-
-        rhs = torch.from_numpy(np.ascontiguousarray(zz.reshape(zz.shape[0], -1))).to(self.factor.device)
-        sol = torch.cholesky_solve(rhs, self.factor, upper=False)
-        return sol.cpu().numpy().reshape(zz.shape)
+        return self.factor.solve(zz.reshape(zz.shape[0], -1)).reshape(zz.shape)
 
 
-def enable_quad_cholesky(backend: str = "pncov") -> None:
+def enable_quad_cholesky() -> None:
     """Route ``BQBeliefUpdate.compute_gram_cho_factor`` / ``gram_cho_solve``
     (quad/solvers/belief_updates/_belief_update.py:61-103) through the GPU.  At 16384 nodes
     the host ``dpotrf`` (1.5 TFLOP) takes ~15 s and dominates ``bayesquad_from_data`` once the
     Gram matrix itself is built on the device."""
-    if backend not in ("pncov", "cusolver"):
-        raise ValueError("backend must be 'pncov' or 'cusolver'")
     numpy2_compat()
     import probnum  # noqa: F401, PLC0415
     from probnum.quad.solvers.belief_updates import _belief_update as bu  # noqa: PLC0415
 
     cls = bu.BQBeliefUpdate
     if ("quad", cls) in _ORIGINALS:
-        factor0, solve0 = _ORIGINALS.pop(("quad", cls))  # switching backends: start from the originals
+        factor0, solve0 = _ORIGINALS.pop(("quad", cls))  # enabling twice: start from the originals
         cls.compute_gram_cho_factor = factor0
         cls.gram_cho_solve = solve0
     _ORIGINALS[("quad", cls)] = (cls.__dict__["compute_gram_cho_factor"], cls.__dict__["gram_cho_solve"])
 
-    if backend == "pncov":
-        def compute_gram_cho_factor(self, gram):
-            # raises numpy.linalg.LinAlgError for a non-positive pivot, like scipy.  A Gram matrix that
-            # this module built itself (and that is unchanged) is re-evaluated on the device straight
-            # into the factorisation buffer: a millisecond instead of an N^2 host-to-device copy.
-            origin = _mirror.gram_provenance(gram) if isinstance(gram, np.ndarray) else None
-            if origin is not None:
-                params, pts = origin
-                with _mirror._lib.Operator(params, pts) as op:
-                    chol = _mirror._lib.Cholesky(op, jitter=float(self.jitter))
-            else:
-                chol = _mirror._lib.Cholesky(gram, jitter=float(self.jitter))
-            return DeviceCholesky(chol, "pncov"), True
-    else:
-        import torch  # noqa: PLC0415
-
-        device = torch.device("cuda", _mirror._lib.default_device())
-
-        def compute_gram_cho_factor(self, gram):
-            g = torch.from_numpy(np.ascontiguousarray(gram, dtype=np.float64)).to(device)
-            g.diagonal().add_(self.jitter)
-            factor, info = torch.linalg.cholesky_ex(g, upper=False)
-            if int(info.item()) != 0:
-                raise np.linalg.LinAlgError(f"{int(info.item())}-th leading minor of the array is not positive definite")
-            return DeviceCholesky(factor, "cusolver"), True
+    def compute_gram_cho_factor(self, gram):
+        # raises numpy.linalg.LinAlgError for a non-positive pivot, like scipy.  The array that is
+        # handed in is what gets factorised (uploaded), exactly like the reference.  Opt-in
+        # (TRUST_GRAM_PROVENANCE): a Gram matrix that this module built itself and whose sampled
+        # entries are unchanged is re-evaluated on the device straight into the factorisation
+        # buffer -- a millisecond instead of an N^2 host-to-device copy, at the price of not
+        # noticing an in-place edit that misses the samples.
+        origin = (_mirror.gram_provenance(gram)
+                  if TRUST_GRAM_PROVENANCE and isinstance(gram, np.ndarray) else None)
+        if origin is not None:
+            params, pts = origin
+            with _mirror._lib.Operator(params, pts) as op:
+                chol = _mirror._lib.Cholesky(op, jitter=float(self.jitter))
+        else:
+            chol = _mirror._lib.Cholesky(gram, jitter=float(self.jitter))
+        return DeviceCholesky(chol), True
 
     def gram_cho_solve(gram_cho_factor, z):
         chol = gram_cho_factor[0] if isinstance(gram_cho_factor, tuple) else gram_cho_factor
@@ -358,9 +339,13 @@ def enable_quad_cholesky(backend: str = "pncov") -> None:
 
     cls.compute_gram_cho_factor = compute_gram_cho_factor
     cls.gram_cho_solve = staticmethod(gram_cho_solve)
-    if backend == "pncov":
-        _enable_quad_prediction()
+    _enable_quad_prediction()
 
+
+# compute_gram_cho_factor: rebuild a Gram matrix of known provenance on the device instead of uploading the
+# host array (sampled check only, see there).  Off by default: the reference always factors the array it is
+# handed.  PNCOV_TRUST_GRAM_PROVENANCE=1 in the environment switches it on.
+TRUST_GRAM_PROVENANCE = os.environ.get("PNCOV_TRUST_GRAM_PROVENANCE", "0") not in ("", "0", "off", "false")
 
 # pncov_chol_solve_gram mode of the patched prediction path.  False: both substitutions and the sums in
 # the reference's order.  True: everything from L^-1 K(nodes, x) alone (half the flops; sums of squares
@@ -375,7 +360,7 @@ def _device_prediction(x, bq_state, vecs):
     a single-launch Gram)."""
     chol = bq_state.gram_cho_factor
     chol = chol[0] if isinstance(chol, tuple) else chol
-    if not (isinstance(chol, DeviceCholesky) and chol.backend == "pncov") or bq_state.fun_evals.shape[0] == 0:
+    if not isinstance(chol, DeviceCholesky) or bq_state.fun_evals.shape[0] == 0:
         return None
     twin = _mirror_of(bq_state.kernel)
     try:
@@ -590,7 +575,7 @@ def enable_all(sharded: Optional[bool] = None) -> None:
     """:func:`enable` plus the opt-in rows of SURVEY.md 8f: the device Cholesky and prediction path of
     the BQ belief update (N1, N4) and the solver's update chains (N2 ii)."""
     enable(sharded)
-    enable_quad_cholesky("pncov")
+    enable_quad_cholesky()
     enable_solver_chains()
 
 
@@ -625,6 +610,10 @@ def disable() -> None:
                 setattr(cls, name, orig)
         cls._evaluate = evaluate  # defined on the class itself
     _ORIGINALS.clear()
+    # page-locked result blocks that no array uses any more go back to the system
+    from . import hostmem  # noqa: PLC0415
+
+    hostmem.release_cache()
 
 
 def enabled() -> bool:

@@ -115,7 +115,7 @@ class ShardedCovarianceOperator:
         return out[:, 0] if vec else out
 
     def _matmul_symmetric_host(self, v2: np.ndarray) -> Optional[np.ndarray]:
-        """One column, symmetric operator: partial vector of this rank's row blocks + all-reduce."""
+        """One column, symmetric operator: this rank's row blocks + all-reduce."""
         import torch  # noqa: PLC0415
 
         dist = _dist()
@@ -124,27 +124,36 @@ class ShardedCovarianceOperator:
             part = torch.from_numpy(np.ascontiguousarray(self.local_sym.matmul_sym_part(v2, self.rank, self.world)))
             if backend == "nccl":
                 part = part.cuda()
-        else:
-            vd = torch.from_numpy(v2).cuda(self.local_sym.device)
-            part = self._sym_part_device(vd)
-            if part is None:
-                return None
-        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
-        return part.cpu().numpy()
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+            return part.cpu().numpy()
+        vd = torch.from_numpy(v2).cuda(self.local_sym.device)
+        y = self._sym_product_device(vd)
+        return None if y is None else y.cpu().numpy()
 
-    def _sym_part_device(self, v):
-        """This rank's partial vector (CUDA tensor) or None if the symmetric kernel does not apply."""
+    def _sym_product_device(self, v, out=None):
+        """Full product (CUDA tensor, on every rank) through the symmetric-halving kernel, or None if it
+        does not apply.  Every rank accumulates its row blocks into integer planes (pncov.h:
+        pncov_matmul_sym_part_bins_device), the planes are summed by ONE all-reduce each (int64 for the
+        two integer planes, float64 for the plane of non-finite contributions) and converted: integer
+        addition is associative, so the result has the same bits for every number of ranks."""
         import torch  # noqa: PLC0415
 
-        part = torch.empty((self.shape[0], 1), dtype=v.dtype, device=v.device)
+        dist = _dist()
+        n = self.shape[0]
+        bins = torch.empty(3 * n, dtype=torch.int64, device=v.device)
         stream = torch.cuda.current_stream(v.device).cuda_stream
         try:
-            self.local_sym.matmul_sym_part_device(v.data_ptr(), part.data_ptr(), self.rank, self.world, stream=stream)
+            self.local_sym.matmul_sym_part_bins_device(v.data_ptr(), bins.data_ptr(), self.rank, self.world, stream=stream)
         except NotImplementedError:
             self.local_sym.close()
             self.local_sym = None
             return None
-        return part
+        dist.all_reduce(bins[: 2 * n], op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(bins[2 * n:].view(torch.float64), op=dist.ReduceOp.SUM, group=self.group)
+        if out is None:
+            out = torch.empty((n, 1), dtype=torch.float64, device=v.device)
+        self.local_sym.matmul_sym_finish_device(bins.data_ptr(), out.data_ptr(), stream=stream)
+        return out
 
     def __matmul__(self, v):
         return self.matmul(np.asarray(v))
@@ -177,13 +186,11 @@ class ShardedCovarianceOperator:
         k = v.shape[1]
         rows = self.hi - self.lo
         if self.local_sym is not None and k == 1 and v.dtype == torch.float64:
-            part = self._sym_part_device(v)
-            if part is not None:
-                dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
-                if out is None:
-                    return part
-                out.copy_(part)
-                return out
+            if out is not None and not (out.is_contiguous() and out.dtype == torch.float64 and tuple(out.shape) == (n0, 1)):
+                raise ValueError("out must be a contiguous float64 (N0, 1) CUDA tensor")
+            y = self._sym_product_device(v, out)
+            if y is not None:
+                return y
         if out is None:
             out = torch.empty((n0, k), dtype=v.dtype, device=v.device)
         y_local = out[self.lo:self.hi]  # contiguous row block of the result

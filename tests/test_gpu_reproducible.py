@@ -1,0 +1,102 @@
+"""The symmetric-halving products accumulate the partial sums of their CTAs order-independently
+(csrc/pncov_common.cuh: pn_bin_add -- exact integer planes on a per-component power-of-two grid), so
+the DEFAULT K @ v is bit-for-bit reproducible like the reference's NumPy product
+(_covariance_linear_operator.py:78-81), for every kernel family of the symmetric path and for every
+split of the row blocks over ranks."""
+
+import numpy as np
+import pytest
+import torch
+
+import probnum_b200 as pb
+from oracle import covfuncs_oracle as orc
+from probnum_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("expquad", 8, dict(lengthscales=1.0), "norm-identity-dmma-symmetric"),      # factorised ExpQuad on DMMA
+    ("ratquad", 5, dict(lengthscale=1.3, alpha=1.7), "norm-identity-dmma-symmetric"),
+    ("matern", 3, dict(nu=2.5, lengthscales=0.7), "direct-differences-symmetric"),
+    ("expquad", 20, dict(lengthscales=4.0), "norm-identity-dmma-symmetric"),     # wide DMMA operands
+    ("matern", 40, dict(nu=1.5, lengthscales=5.0), "direct-differences-symmetric"),  # row-staged kernel
+]
+
+
+def kernel(kind, d, kw):
+    return {"expquad": pb.ExpQuad, "matern": pb.Matern, "ratquad": pb.RatQuad}[kind]((d,), **kw)
+
+
+def spec_of(kind, d, kw):
+    return orc.KernelSpec(kind, (d,), kw.get("lengthscales", kw.get("lengthscale", 1.0)), nu=kw.get("nu", 1.5),
+                          alpha=kw.get("alpha", 1.0))
+
+
+@pytest.mark.parametrize("kind,d,kw,path", CASES, ids=[f"{c[0]}-d{c[1]}" for c in CASES])
+def test_default_product_is_bit_reproducible_and_rank_count_independent(kind, d, kw, path):
+    n = 6000
+    rng = np.random.default_rng(17)
+    x = rng.normal(size=(n, d))
+    v = rng.normal(size=(n, 1)) * np.exp(rng.normal(size=(n, 1)) * 3.0)  # wide dynamic range in v
+    k = kernel(kind, d, kw)
+    op = _lib.Operator(k._kernel_params(), x)
+    y0 = op.matmul(v)
+    assert op.matmul_path() == path
+    for _ in range(4):
+        assert np.array_equal(op.matmul(v), y0)
+    spec = spec_of(kind, d, kw)
+    bound = orc.abs_matvec(spec, x, None, v)
+    assert np.all(np.abs(y0 - orc.matvec(spec, x, None, v)) <= 1e-12 * bound)
+    # the row blocks dealt to 2, 3 and 8 "ranks" (all on this device): integer planes summed, then finished
+    vd = torch.from_numpy(v).cuda()
+    for nparts in (2, 3, 8):
+        total = torch.zeros(3 * n, dtype=torch.int64, device="cuda")
+        bins = torch.empty(3 * n, dtype=torch.int64, device="cuda")
+        for p in range(nparts):
+            op.matmul_sym_part_bins_device(vd.data_ptr(), bins.data_ptr(), p, nparts)
+            torch.cuda.synchronize()
+            total[: 2 * n] += bins[: 2 * n]
+            total[2 * n:].view(torch.float64).add_(bins[2 * n:].view(torch.float64))
+        y = torch.empty((n, 1), dtype=torch.float64, device="cuda")
+        op.matmul_sym_finish_device(total.data_ptr(), y.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(y.cpu().numpy(), y0), nparts
+    op.close()
+
+
+def test_non_finite_right_hand_sides_propagate_like_numpy():
+    n, d = 4096, 4
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(n, d))
+    k = pb.Matern((d,), nu=1.5)
+    K = k.matrix(x)
+    op = _lib.Operator(k._kernel_params(), x)
+    for bad in (np.inf, -np.inf, np.nan):
+        v = rng.normal(size=(n, 1))
+        v[100, 0] = bad
+        y = op.matmul(v)
+        with np.errstate(invalid="ignore"):
+            want = K @ v
+        assert np.array_equal(np.isnan(y), np.isnan(want))
+        assert np.array_equal(np.isinf(y), np.isinf(want))
+        assert np.array_equal(np.sign(y[np.isinf(y)]), np.sign(want[np.isinf(want)]))
+    v = rng.normal(size=(n, 1))
+    v[7, 0], v[9, 0] = np.inf, -np.inf
+    assert np.all(np.isnan(op.matmul(v)))  # Inf - Inf in every row, as in NumPy
+    assert np.array_equal(op.matmul(np.zeros((n, 1))), np.zeros((n, 1)))
+    op.close()
+
+
+def test_tiny_and_huge_right_hand_sides():
+    n, d = 3000, 8
+    rng = np.random.default_rng(6)
+    x = rng.normal(size=(n, d))
+    spec = orc.KernelSpec("expquad", (d,), 1.0)
+    op = _lib.Operator(pb.ExpQuad((d,))._kernel_params(), x)
+    for scale in (1e-290, 1e-150, 1.0, 1e150, 1e290):
+        v = rng.normal(size=(n, 1)) * scale
+        y = op.matmul(v)
+        bound = orc.abs_matvec(spec, x, None, v)
+        assert np.all(np.abs(y - orc.matvec(spec, x, None, v)) <= 1e-12 * bound + 1e-320), scale
+        assert np.array_equal(op.matmul(v), y)
+    op.close()

@@ -114,8 +114,14 @@ m_big, v_big = bq(args.n_bq, tim_big)
 t0 = time.perf_counter()
 K = cf.ExpQuad((4,)).matrix(np.random.default_rng(42).normal(size=(args.n_bq, 4)))
 tim_big["gram_only_s"] = time.perf_counter() - t0
+import tools.cusolver_baseline as cusolver_baseline  # noqa: E402
+
 for backend in ("cusolver", "pncov"):
-    gpu.enable_quad_cholesky(backend)
+    if backend == "pncov":
+        cusolver_baseline.disable()
+        gpu.enable_quad_cholesky()
+    else:
+        cusolver_baseline.enable()
     tim_chol = {}
     m_ch, v_ch = bq(args.n_bq, tim_chol)  # first call pays library initialisation / allocation
     tim_chol2 = {}

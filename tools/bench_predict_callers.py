@@ -59,7 +59,7 @@ mean_c, var_c, acq_c, tp_c, ta_c = predict(state_cpu, x[:m_host])
 out["reference"] = {"fit_s": fit_cpu, "predict_integrand_s_per_point": tp_c / m_host, "ivr_s_per_point": ta_c / m_host}
 
 gpu.enable()
-gpu.enable_quad_cholesky("pncov")
+gpu.enable_quad_cholesky()
 for mode in ("reference_order", "forward_only"):
     gpu.PREDICTION_FORWARD_ONLY = mode == "forward_only"
     state, fit_gpu = fit()

@@ -8,7 +8,7 @@ from probnum.quad.solvers import BQState
 from probnum.quad.solvers.belief_updates import BQStandardBeliefUpdate
 d=4
 measure = pn.quad.integration_measures.GaussianMeasure(mean=np.zeros(d), cov=np.eye(d))
-gpu.enable(); gpu.enable_quad_cholesky("pncov")
+gpu.enable(); gpu.enable_quad_cholesky()
 for n in (8192, 16384):
     rng = np.random.default_rng(42)
     nodes = rng.normal(size=(n, d)); f = np.sin(nodes).sum(axis=1)
