@@ -434,6 +434,7 @@ struct pncov_handle {
     int env_ident = -1;   // PNCOV_MATVEC_IDENT: -1 unset, 0 "off", 1 "dfma"
     int env_fact = -1;    // PNCOV_MATVEC_FACT: 0 "off"
     int env_sym = -1;     // PNCOV_MATVEC_SYM: 0 "off", 1 "on"
+    int env_mirror = -1;  // PNCOV_GRAM_MIRROR: 0 "off"
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -830,7 +831,7 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
     if (h->k.extra_mode >= 0)
         return fail(PNCOV_ENOTIMPL, "the matrix-free product covers ExpQuad, Matern and RatQuad; use the dense Gram for this kernel");
     if (h->k.d > 1024) return fail(PNCOV_ENOTIMPL, "matrix-free product supports d <= 1024");
-    const int kc_max = (k == 1) ? 1 : 4;
+    int kc_max = (k == 1) ? 1 : 4;
     PnMatvecLaunch m{};
     m.x0_aos = R.aos;
     m.x1_aos = C.aos;
@@ -851,6 +852,11 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         if (prc) return prc;
     }
     const bool wide_ok = h->k.d <= 8 || kc_max == 1;  // the 8 < d <= 64 kernels take one right-hand side
+    // five or more right-hand sides on the DMMA identity kernel (d <= 8): passes of eight columns
+    if (h->mma_state == 1 && h->opt_identity != 0 && h->env_ident != 1 && h->k.d <= 8 && k > 4) {
+        kc_max = 8;
+        m.kc = 8;
+    }
     if (h->mma_state == 1 && h->opt_identity != 0 && wide_ok) {
         // norm identity: dot products on DMMA by default (fastest measured), DFMA form opt-in
         m.use_mma = h->env_ident == 1 ? 1 : 2;
@@ -1041,6 +1047,7 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
     if (const char* v = getenv("PNCOV_MATVEC_IDENT")) h->env_ident = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "dfma") == 0 ? 1 : -1);
     if (const char* v = getenv("PNCOV_MATVEC_FACT")) h->env_fact = strcmp(v, "off") == 0 ? 0 : -1;
     if (const char* v = getenv("PNCOV_MATVEC_SYM")) h->env_sym = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "on") == 0 ? 1 : -1);
+    if (const char* v = getenv("PNCOV_GRAM_MIRROR")) h->env_mirror = strcmp(v, "off") == 0 ? 0 : -1;
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(fail_cuda(e, "upload"));
     *out = h;
     return 0;
@@ -1129,11 +1136,21 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
     // the staging rows are padded to an even length so that every row starts 16-byte aligned
     // (the fast kernel's vector stores); the copy below strips the padding again
     const int64_t ld_stage = cols + (cols & 1);
-    int64_t block_rows = (int64_t)((1ull << 30) / ((size_t)ld_stage * ge));
+    // A whole symmetric matrix (x1 = NULL; every kernel gives K_ij and K_ji the same bits): only the columns from
+    // the diagonal block on cross PCIe, the blocks below the diagonal are written by host threads as mirror
+    // images while the next row blocks are in flight (pncov_host.cu).  Blocks of 128 MiB let the mirroring start
+    // early.  Measured (tools/e2e_mirror_sweep.py, N = 32768, 16 host threads): 157 -> 119 ms per matrix; the
+    // limit is then the host's memory bandwidth (8 threads mirror as fast as 16), so copying the last rows whole
+    // to balance link and host (PNCOV_GRAM_MIRROR_FULL_DIV) does not pay.  PNCOV_GRAM_MIRROR=off copies everything.
+    const bool mirror = h->symmetric && rows == cols && (size_t)rows * ld_stage * ge > (1ull << 30) && h->env_mirror != 0;
+    static const int mirror_mib = getenv("PNCOV_GRAM_MIRROR_BLOCK_MIB") ? atoi(getenv("PNCOV_GRAM_MIRROR_BLOCK_MIB")) : 128;
+    static const int mirror_div = getenv("PNCOV_GRAM_MIRROR_FULL_DIV") ? atoi(getenv("PNCOV_GRAM_MIRROR_FULL_DIV")) : 0;
+    int64_t block_rows = (int64_t)((mirror ? ((size_t)std::max(mirror_mib, 16) << 20) : (1ull << 30)) / ((size_t)ld_stage * ge));
     block_rows = std::max<int64_t>(PN_PAD, (block_rows / PN_PAD) * PN_PAD);
     block_rows = std::min<int64_t>(block_rows, pad_up(rows));
     const size_t block_bytes = (size_t)block_rows * ld_stage * ge;
     const int nbuf = rows > block_rows ? 2 : 1;
+    const int64_t full_from = (mirror && mirror_div > 0) ? rows - ((rows / mirror_div) / 256) * 256 : rows;  // rows from here on are copied whole
     int rc;
     if ((rc = ensure(&h->stage, &h->stage_bytes, block_bytes * nbuf, h->stream))) return rc;
     cudaEvent_t done[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
@@ -1141,6 +1158,7 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
         PN_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
         PN_CUDA(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
     }
+    std::vector<cudaEvent_t> landed;  // mirror: one event per row block, recorded after its copy
     cudaError_t err = cudaSuccess;
     err = cudaEventRecord(h->ev0, h->stream);
     int b = 0;
@@ -1152,12 +1170,39 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
         if (err == cudaSuccess) err = launch_gram_any(h, transpose != 0, r0, nr, dbuf, ld_stage, h->stream);
         if (err == cudaSuccess) err = cudaEventRecord(done[buf], h->stream);
         if (err == cudaSuccess) err = cudaStreamWaitEvent(h->copy_stream, done[buf], 0);
-        if (err == cudaSuccess)
-            err = cudaMemcpy2DAsync(static_cast<char*>(out) + (size_t)r0 * ld * ge, (size_t)ld * ge, dbuf, (size_t)ld_stage * ge,
-                                    (size_t)cols * ge, (size_t)nr, cudaMemcpyDeviceToHost, h->copy_stream);
+        // rows below full_from are copied whole, the others from their diagonal block on
+        const int64_t split = std::min(std::max(full_from, r0), r0 + nr);  // rows [r0, split): upper part only
+        if (err == cudaSuccess && split > r0) {
+            const int64_t c_first = mirror ? r0 : 0;
+            err = cudaMemcpy2DAsync(static_cast<char*>(out) + ((size_t)r0 * ld + c_first) * ge, (size_t)ld * ge,
+                                    dbuf + (size_t)c_first * ge, (size_t)ld_stage * ge, (size_t)(cols - c_first) * ge,
+                                    (size_t)(split - r0), cudaMemcpyDeviceToHost, h->copy_stream);
+        }
+        if (err == cudaSuccess && split < r0 + nr)
+            err = cudaMemcpy2DAsync(static_cast<char*>(out) + (size_t)split * ld * ge, (size_t)ld * ge,
+                                    dbuf + (size_t)(split - r0) * ld_stage * ge, (size_t)ld_stage * ge, (size_t)cols * ge,
+                                    (size_t)(r0 + nr - split), cudaMemcpyDeviceToHost, h->copy_stream);
         if (err == cudaSuccess) err = cudaEventRecord(copied[buf], h->copy_stream);
+        if (mirror && err == cudaSuccess) {
+            cudaEvent_t ev = nullptr;
+            err = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (err == cudaSuccess) {
+                landed.push_back(ev);
+                err = cudaEventRecord(ev, h->copy_stream);
+            }
+        }
     }
     if (err == cudaSuccess) err = cudaEventRecord(h->ev1, h->stream);
+    if (mirror) {
+        // as each row block lands, its part right of the diagonal block is mirrored below the diagonal
+        int64_t r0 = 0;
+        for (size_t i = 0; i < landed.size(); ++i, r0 += block_rows) {
+            if (err == cudaSuccess) err = cudaEventSynchronize(landed[i]);
+            if (err == cudaSuccess) pn_host_mirror_async(out, ld, full_from, r0, std::min(r0 + block_rows, rows), (int)ge);
+        }
+        pn_host_mirror_wait();
+        for (cudaEvent_t ev : landed) cudaEventDestroy(ev);
+    }
     if (err == cudaSuccess) err = cudaStreamSynchronize(h->copy_stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
     for (int i = 0; i < nbuf; ++i) {

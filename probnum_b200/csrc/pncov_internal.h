@@ -169,3 +169,8 @@ cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int64_t n1, const
 extern int64_t g_pn_launches;
 // multiProcessorCount of the CURRENT device (queried once per device): grids are sized from it
 int pn_sm_count();
+
+// host worker threads (pncov_host.cu): mirror image of the upper blocks of a symmetric host matrix
+int pn_host_threads();
+void pn_host_mirror_async(void* out, int64_t ld, int64_t n, int64_t r0, int64_t r1, int elem);
+void pn_host_mirror_wait();

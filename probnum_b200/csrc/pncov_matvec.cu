@@ -1350,6 +1350,9 @@ cudaError_t launch_mma_any(PnMatvecLaunch& a, int sm, bool plan, cudaStream_t st
     const bool two = a.d > 4;
     if (a.kc == 1) return two ? launch_mma_epi<2, 1>(a, sm, plan, stream) : launch_mma_epi<1, 1>(a, sm, plan, stream);
     if (a.kc == 4) return two ? launch_mma_epi<2, 4>(a, sm, plan, stream) : launch_mma_epi<1, 4>(a, sm, plan, stream);
+    // eight right-hand sides per pass: the kernel values (17 of the 25 FP64-pipe slots per pair) are evaluated once
+    // for all eight columns instead of once per group of four
+    if (a.kc == 8) return two ? launch_mma_epi<2, 8>(a, sm, plan, stream) : launch_mma_epi<1, 8>(a, sm, plan, stream);
     return cudaErrorInvalidValue;
 }
 
