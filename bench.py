@@ -426,10 +426,10 @@ def leg_matvec(ctx: Ctx, args, extra: dict) -> int:
         }
         if dfma:
             alg = rec["gflops"] / 1e3 / world
-            # the symmetric kernel evaluates each off-diagonal 128 x 128 tile once (plus one more FMA per
-            # pair for the mirrored sum): `achieved` counts the flops it EXECUTES (the claim against the
+            # the symmetric kernel evaluates each off-diagonal 128 x 128 tile once (plus one more FMA per pair
+            # and right-hand side for the mirrored sum): `achieved` counts the flops it EXECUTES (the claim against the
             # FP64 pipe), `algorithmic` all N^2 ordered pairs (BASELINE's metric)
-            ach = alg * (0.5 * (1.0 + 128.0 / nm) * (flop_per_pair + 2) / flop_per_pair) if symmetric else alg
+            ach = alg * (0.5 * (1.0 + 128.0 / nm) * (flop_per_pair + 2 * kcols) / flop_per_pair) if symmetric else alg
             rec["roofline"] = {"bound": "fp64 pipe", "achieved": ach, "algorithmic": alg, "peak": dfma,
                                "unit": "TFLOP/s", "frac": ach / dfma, "claim": "executed flops / measured DFMA rate",
                                "peak_source": "profiles/r01_microbench.json dfma_tflops_sustained"}
@@ -894,6 +894,7 @@ def run_ours(args):
             barrier()
             cold = max_over_ranks(time.perf_counter() - t0)
             e2e_steps = max(1, min(args.steps, 3))
+            d2h0 = _lib.d2h_bytes()
             t0 = time.perf_counter()
             for _ in range(e2e_steps):
                 for k in ks:
@@ -905,15 +906,21 @@ def run_ours(args):
             if gpu is not None:
                 gpu.disable()
         launches += _lib.launch_count() - l0
+        # a whole symmetric Gram may cross PCIe as its upper block triangle, host threads of libpncov writing the rest
+        # as mirror images (csrc/pncov_host.cu); the library keeps whichever way it measured faster on this host
+        pcie_step = max_over_ranks(float(_lib.d2h_bytes() - d2h0)) / e2e_steps  # counted by the library
+        mirrored = pcie_step < 0.9 * 2 * 8 * n * n
         e2e = {
             "value": entries_per_step * e2e_steps / dt, "unit": UNIT,
             "h2d_bytes_per_step": 2 * 8 * d * n * world,
-            "d2h_bytes_per_step": int(2 * 8 * n * n) * world,
+            "d2h_bytes_per_step": int(pcie_step) * world,
+            "host_result_bytes_per_step": int(2 * 8 * n * n) * world,
             "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-            "d2h_gbs_aggregate": 2 * 8.0 * n * n * world * e2e_steps / dt / 1e9,
+            "d2h_gbs_aggregate": pcie_step * world * e2e_steps / dt / 1e9,
+            "host_result_gbs_aggregate": 2 * 8.0 * n * n * world * e2e_steps / dt / 1e9,
             "first_step_cold_ms": 1e3 * cold,
             "api": api + " (result arrays from the page-locked pool of probnum_b200.hostmem: warm steps re-use the "
-                         "blocks the cold step pinned)",
+                         "blocks the cold step pinned" + ("; symmetric result: upper block triangle over PCIe, the rest mirrored by host threads" if mirrored else "") + ")",
         }
     del out
     torch.cuda.empty_cache()

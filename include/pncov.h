@@ -299,6 +299,12 @@ PNCOV_API int pncov_chain_apply(pncov_chain* c, int64_t k, int mode, const doubl
  * device time in ms of the last pncov_gram / pncov_matmul call of this handle (CUDA
  * events on the handle's stream around the kernels, excluding host<->device copies). */
 PNCOV_API int64_t pncov_launch_count(void);
+
+/* Bytes pncov_gram has copied device-to-host in this process.  A whole symmetric result (x1 == NULL) may cross
+ * PCIe as its blocks on and above the diagonal only, host threads of the library writing the rest as mirror
+ * images; the library measures both ways on the process's first large symmetric results and keeps the faster
+ * (PNCOV_GRAM_MIRROR=on|off in the environment forces one). */
+PNCOV_API int64_t pncov_d2h_bytes(void);
 /* which kernel family serves pncov_matmul for this handle: 0 = not decided yet (no product
  * so far), 1 = norm-identity + DMMA (ExpQuad / RatQuad, d <= 8, error bound satisfied),
  * 2 = direct differences, 3 = norm-identity + DMMA with symmetric halving, 4 = direct differences

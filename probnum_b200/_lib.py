@@ -81,6 +81,7 @@ SIGNATURES = {
                                              ctypes.POINTER(ctypes.c_float)]),
     "pncov_chol_get_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
     "pncov_chol_last_factor_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
+    "pncov_d2h_bytes": (ctypes.c_int64, []),
     "pncov_launch_count": (_c_i64, []),
     "pncov_matmul_path": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_int)]),
     "pncov_last_kernel_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
@@ -137,6 +138,11 @@ def device_count() -> int:
 def default_device() -> int:
     """One process per GPU: LOCAL_RANK selects the device under torchrun."""
     return int(os.environ.get("PNCOV_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def d2h_bytes() -> int:
+    """Bytes ``pncov_gram`` has copied device-to-host in this process."""
+    return int(load().pncov_d2h_bytes())
 
 
 def launch_count() -> int:

@@ -8,6 +8,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -16,6 +18,7 @@
 #include "pncov_internal.h"
 
 int64_t g_pn_launches = 0;
+static int64_t g_pn_d2h_bytes = 0;  // bytes pncov_gram moved over PCIe (a symmetric result may cross as its upper blocks only)
 
 int pn_sm_count() {
     static int cached[64] = {0};
@@ -32,6 +35,30 @@ int pn_sm_count() {
 namespace {
 
 thread_local std::string t_err;
+
+// Symmetric host return path: mirror on the host or copy everything?  Halving the PCIe bytes pays when the link
+// is the limit (one GPU per host: 157 -> 119 ms per 8.6 GB matrix) and loses when the host's memory bandwidth
+// is (eight ranks sharing one socket: the mirror reads and writes what the DMA engine would only write).  The
+// library measures both on the process's first two large symmetric results and keeps the faster, re-probing the
+// other one every 16th call.
+struct MirrorPolicy {
+    std::mutex m;
+    double rate[2] = {0.0, 0.0};  // result bytes per second: [0] full copy, [1] mirrored
+    int calls = 0;
+    bool choose() {
+        std::lock_guard<std::mutex> lk(m);
+        ++calls;
+        if (rate[1] == 0.0) return true;
+        if (rate[0] == 0.0) return false;
+        const bool best = rate[1] >= rate[0];
+        return (calls % 16 == 0) ? !best : best;
+    }
+    void record(bool mirrored, double bytes, double seconds) {
+        if (seconds <= 0) return;
+        std::lock_guard<std::mutex> lk(m);
+        rate[mirrored ? 1 : 0] = bytes / seconds;
+    }
+} g_mirror_policy;
 
 int fail(int code, const std::string& msg) {
     t_err = msg;
@@ -93,12 +120,12 @@ __global__ void aos_to_soa_kernel(const T* __restrict__ aos, T* __restrict__ soa
 // V (rows, k) with leading dimension ldv -> packed (rows_pad, kc) chunk starting at column c0
 template <typename T>
 __global__ void pack_v_kernel(const T* __restrict__ v, int64_t ldv, int64_t rows, int64_t rows_pad,
-                              int64_t k, int64_t c0, int kc, T* __restrict__ vp) {
+                              int64_t k, int64_t c0, int kc, int vstride, T* __restrict__ vp) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows_pad * kc) return;
-    const int64_t j = idx / kc;
-    const int c = (int)(idx % kc);
-    vp[idx] = (j < rows && c0 + c < k) ? v[j * ldv + c0 + c] : T(0);
+    if (idx >= rows_pad * vstride) return;
+    const int64_t j = idx / vstride;
+    const int c = (int)(idx % vstride);
+    vp[idx] = (j < rows && c < kc && c0 + c < k) ? v[j * ldv + c0 + c] : T(0);
 }
 
 template <typename T>
@@ -114,13 +141,13 @@ __global__ void unpack_y_kernel(const T* __restrict__ yp, int64_t rows, int kc, 
 // factorised ExpQuad product: v'_j = f_j v_j on the way in, y_i = f_i y'_i on the way out, with
 // f = slot 9 of the 12-double operand rows built by build_mma_operands_kernel
 __global__ void pack_v_scaled_kernel(const double* __restrict__ v, int64_t ldv, int64_t rows, int64_t rows_pad,
-                                     int64_t k, int64_t c0, int kc, const double* __restrict__ op12, int ld, int fi,
+                                     int64_t k, int64_t c0, int kc, int vstride, const double* __restrict__ op12, int ld, int fi,
                                      double* __restrict__ vp) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows_pad * kc) return;
-    const int64_t j = idx / kc;
-    const int c = (int)(idx % kc);
-    vp[idx] = (j < rows && c0 + c < k) ? v[j * ldv + c0 + c] * op12[j * ld + fi] : 0.0;
+    if (idx >= rows_pad * vstride) return;
+    const int64_t j = idx / vstride;
+    const int c = (int)(idx % vstride);
+    vp[idx] = (j < rows && c < kc && c0 + c < k) ? v[j * ldv + c0 + c] * op12[j * ld + fi] : 0.0;
 }
 __global__ void unpack_y_scaled_kernel(const double* __restrict__ yp, int64_t rows, int kc, int64_t k, int64_t c0,
                                        const double* __restrict__ op12, int ld, int fi, double* __restrict__ y,
@@ -434,7 +461,7 @@ struct pncov_handle {
     int env_ident = -1;   // PNCOV_MATVEC_IDENT: -1 unset, 0 "off", 1 "dfma"
     int env_fact = -1;    // PNCOV_MATVEC_FACT: 0 "off"
     int env_sym = -1;     // PNCOV_MATVEC_SYM: 0 "off", 1 "on"
-    int env_mirror = -1;  // PNCOV_GRAM_MIRROR: 0 "off"
+    int env_mirror = -1;  // PNCOV_GRAM_MIRROR: 0 "off", 1 "on" (always), unset: measured policy
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -796,20 +823,22 @@ int mma_prepare(pncov_handle* h, cudaStream_t stream) {
 // sym_nparts > 0 asks for the symmetric-halving kernel restricted to row blocks sym_part, sym_part +
 // sym_nparts, ... (the caller sums the partial vectors of all parts); it fails with PNCOV_ENOTIMPL
 // when that kernel does not apply to this handle.  sym_nparts == 0: whole product, best kernel.
-// integer planes of a symmetric-halving product -> y (row factors of the factorised ExpQuad form applied)
-int sym_finish(pncov_handle* h, const void* bins, void* y, int64_t ldy, cudaStream_t stream) {
+// integer planes of a symmetric-halving product -> columns c0 .. c0 + kc - 1 of y (row factors of the factorised
+// ExpQuad form applied)
+int sym_finish(pncov_handle* h, const void* bins, void* y, int64_t ldy, cudaStream_t stream, int kc = 1, int64_t k = 1,
+               int64_t c0 = 0) {
     const int64_t n = h->p0.n;
     int rc;
-    if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)n * 8, h->stream))) return rc;
+    if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)n * kc * 8, h->stream))) return rc;
     const double* fac = h->last_fact ? (const double*)h->a12[0] : nullptr;
-    PN_CUDA(pn_launch_unbin((const long long*)bins, n, n, (const double*)h->vmax_dev, fac, h->mma_dpad + 4, h->mma_dpad + 1,
+    PN_CUDA(pn_launch_unbin((const long long*)bins, n, kc, n, (const double*)h->vmax_dev, fac, h->mma_dpad + 4, h->mma_dpad + 1,
                             (double*)h->ypack, stream));
-    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const unsigned blocks = (unsigned)((n * kc + 255) / 256);
     if (h->last_fact)
-        unpack_y_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)h->ypack, n, 1, 1, 0, fac, h->mma_dpad + 4,
+        unpack_y_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)h->ypack, n, kc, k, c0, fac, h->mma_dpad + 4,
                                                            h->mma_dpad + 1, (double*)y, ldy);
     else
-        unpack_y_kernel<double><<<blocks, 256, 0, stream>>>((const double*)h->ypack, n, 1, 1, 0, (double*)y, ldy);
+        unpack_y_kernel<double><<<blocks, 256, 0, stream>>>((const double*)h->ypack, n, kc, k, c0, (double*)y, ldy);
     ++g_pn_launches;
     PN_CUDA(cudaGetLastError());
     return 0;
@@ -877,9 +906,15 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
         const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 96);  // DMMA identity or direct differences
         const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : h->env_sym != 0;
-        const bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;
+        bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;
         if (sym_nparts > 0 && !sym_ok)
             return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 96 and n >= 2048");
+        // several right-hand sides on the DMMA identity kernel (d <= 8): symmetric passes of eight columns (zero padded)
+        if (h->symmetric && m.use_mma == 2 && h->k.d <= 8 && k > 1 && es == 8 && R.n >= 2048 && sym_on && sym_nparts == 0) {
+            sym_ok = true;
+            kc_max = 8;
+            m.kc = kc_max;
+        }
         m.sym = sym_ok ? 1 : 0;
         m.sym_part = sym_part;
         m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;
@@ -896,31 +931,32 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         if (!h->vmax_dev) PN_CUDA(pn_dev_alloc(&h->vmax_dev, sizeof(double), h->stream));
         bins = bins_out;
         if (!bins) {
-            if ((rc = ensure(&h->bins, &h->bins_bytes, (size_t)R.n * 24, h->stream))) return rc;
+            if ((rc = ensure(&h->bins, &h->bins_bytes, (size_t)R.n * kc_max * 24, h->stream))) return rc;
             bins = h->bins;
         }
-        PN_CUDA(pn_launch_vmax((const double*)v, ldv, C.n, (double*)h->vmax_dev, stream));
-        PN_CUDA(cudaMemsetAsync(bins, 0, (size_t)R.n * 24, stream));
+        PN_CUDA(pn_launch_vmax((const double*)v, ldv, C.n, (int)k, (double*)h->vmax_dev, stream));
         m.bins = (long long*)bins;
         m.vmax = (const double*)h->vmax_dev;
     }
-    if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * kc_max * es, h->stream))) return rc;
+    if ((rc = ensure(&h->vpack, &h->vpack_bytes, (size_t)C.npad * (kc_max + 2) * es, h->stream))) return rc;
     if ((rc = ensure(&h->ypack, &h->ypack_bytes, (size_t)R.n * kc_max * es, h->stream))) return rc;
     if (jsplit > 1 && (rc = ensure(&h->partial, &h->partial_bytes, (size_t)jsplit * R.n * kc_max * 8, h->stream))) return rc;
 
     for (int64_t c0 = 0; c0 < k; c0 += kc_max) {
         const int kc = kc_max;
         {
-            const int64_t total = C.npad * kc;
+            const int vstride = kc == 8 ? 10 : kc;  // the eight-column DMMA kernels read V in padded rows (conflict-free fragments)
+            m.vstride = vstride;
+            const int64_t total = C.npad * vstride;
             const unsigned blocks = (unsigned)((total + 255) / 256);
             if (m.fact)
-                pack_v_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc,
+                pack_v_scaled_kernel<<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc, vstride,
                                                                  (const double*)m.b12, h->mma_dpad + 4, h->mma_dpad + 1,
                                                                  (double*)h->vpack);
             else if (es == 8)
-                pack_v_kernel<double><<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc, (double*)h->vpack);
+                pack_v_kernel<double><<<blocks, 256, 0, stream>>>((const double*)v, ldv, C.n, C.npad, k, c0, kc, vstride, (double*)h->vpack);
             else
-                pack_v_kernel<float><<<blocks, 256, 0, stream>>>((const float*)v, ldv, C.n, C.npad, k, c0, kc, (float*)h->vpack);
+                pack_v_kernel<float><<<blocks, 256, 0, stream>>>((const float*)v, ldv, C.n, C.npad, k, c0, kc, vstride, (float*)h->vpack);
             ++g_pn_launches;
             PN_CUDA(cudaGetLastError());
         }
@@ -929,10 +965,11 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         m.kc = kc;
         m.partial = h->partial;
         m.jsplit = jsplit;
+        if (m.sym) PN_CUDA(cudaMemsetAsync(bins, 0, (size_t)R.n * kc * 24, stream));
         PN_CUDA(pn_launch_matvec(m, h->sm_count, stream));
         if (m.sym) {
-            if (!bins_out && (rc = sym_finish(h, bins, y, ldy, stream))) return rc;
-            break;  // one right-hand side
+            if (!bins_out && (rc = sym_finish(h, bins, y, ldy, stream, kc, k, c0))) return rc;
+            continue;
         }
         {
             const int64_t total = R.n * kc;
@@ -1047,7 +1084,7 @@ PNCOV_API int pncov_create(pncov_handle** out, int device, int kind, int dtype, 
     if (const char* v = getenv("PNCOV_MATVEC_IDENT")) h->env_ident = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "dfma") == 0 ? 1 : -1);
     if (const char* v = getenv("PNCOV_MATVEC_FACT")) h->env_fact = strcmp(v, "off") == 0 ? 0 : -1;
     if (const char* v = getenv("PNCOV_MATVEC_SYM")) h->env_sym = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "on") == 0 ? 1 : -1);
-    if (const char* v = getenv("PNCOV_GRAM_MIRROR")) h->env_mirror = strcmp(v, "off") == 0 ? 0 : -1;
+    if (const char* v = getenv("PNCOV_GRAM_MIRROR")) h->env_mirror = strcmp(v, "off") == 0 ? 0 : (strcmp(v, "on") == 0 ? 1 : -1);
     if ((e = cudaStreamSynchronize(h->stream)) != cudaSuccess) return bail(fail_cuda(e, "upload"));
     *out = h;
     return 0;
@@ -1142,7 +1179,10 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
     // early.  Measured (tools/e2e_mirror_sweep.py, N = 32768, 16 host threads): 157 -> 119 ms per matrix; the
     // limit is then the host's memory bandwidth (8 threads mirror as fast as 16), so copying the last rows whole
     // to balance link and host (PNCOV_GRAM_MIRROR_FULL_DIV) does not pay.  PNCOV_GRAM_MIRROR=off copies everything.
-    const bool mirror = h->symmetric && rows == cols && (size_t)rows * ld_stage * ge > (1ull << 30) && h->env_mirror != 0;
+    const bool mirror_ok = h->symmetric && rows == cols && (size_t)rows * ld_stage * ge > (1ull << 30) && h->env_mirror != 0;
+    // PNCOV_GRAM_MIRROR=on forces the mirrored path, unset lets the measured policy decide
+    const bool mirror = mirror_ok && (h->env_mirror == 1 || g_mirror_policy.choose());
+    const auto t_begin = std::chrono::steady_clock::now();
     static const int mirror_mib = getenv("PNCOV_GRAM_MIRROR_BLOCK_MIB") ? atoi(getenv("PNCOV_GRAM_MIRROR_BLOCK_MIB")) : 128;
     static const int mirror_div = getenv("PNCOV_GRAM_MIRROR_FULL_DIV") ? atoi(getenv("PNCOV_GRAM_MIRROR_FULL_DIV")) : 0;
     int64_t block_rows = (int64_t)((mirror ? ((size_t)std::max(mirror_mib, 16) << 20) : (1ull << 30)) / ((size_t)ld_stage * ge));
@@ -1172,6 +1212,7 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
         if (err == cudaSuccess) err = cudaStreamWaitEvent(h->copy_stream, done[buf], 0);
         // rows below full_from are copied whole, the others from their diagonal block on
         const int64_t split = std::min(std::max(full_from, r0), r0 + nr);  // rows [r0, split): upper part only
+        g_pn_d2h_bytes += (int64_t)ge * ((split - r0) * (cols - (mirror ? r0 : 0)) + (r0 + nr - split) * cols);
         if (err == cudaSuccess && split > r0) {
             const int64_t c_first = mirror ? r0 : 0;
             err = cudaMemcpy2DAsync(static_cast<char*>(out) + ((size_t)r0 * ld + c_first) * ge, (size_t)ld * ge,
@@ -1205,6 +1246,9 @@ PNCOV_API int pncov_gram(pncov_handle* h, void* out, int64_t ld, int transpose) 
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(h->copy_stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(h->stream);
+    if (mirror_ok && h->env_mirror != 1 && err == cudaSuccess)
+        g_mirror_policy.record(mirror, (double)rows * cols * ge,
+                               std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count());
     for (int i = 0; i < nbuf; ++i) {
         cudaEventDestroy(done[i]);
         cudaEventDestroy(copied[i]);
@@ -1786,6 +1830,8 @@ PNCOV_API int pncov_chain_apply(pncov_chain* c, int64_t k, int mode, const doubl
 }
 
 PNCOV_API int64_t pncov_launch_count(void) { return g_pn_launches; }
+
+PNCOV_API int64_t pncov_d2h_bytes(void) { return g_pn_d2h_bytes; }
 
 PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value) {
     if (!h) return fail(PNCOV_EINVAL, "handle is NULL");

@@ -52,7 +52,8 @@ struct PnMatvecLaunch {
     // y_J; row blocks part, part + nparts, ... only (multi-GPU).  The partial sums go to the integer
     // planes `bins` (see pn_bin_add in pncov_common.cuh; zero on entry), not to y
     int sym, sym_part, sym_nparts;
-    long long* bins;      // [hi plane (n0) | lo plane (n0)] followed by the non-finite plane (n0 doubles)
+    long long* bins;      // [hi plane | lo plane] (n0 * kc int64 each) followed by the non-finite plane (n0 * kc doubles)
+    int vstride;          // doubles per row of the packed right-hand sides v (kc, or kc + 2 for the symmetric multi-column kernel)
     const double* vmax;   // device scalar: max |v_j| over the original right-hand side
     // ExpQuad in factorised form (use_mma == 2): a12[.][9] / b12[.][9] hold exp(-|xt|^2); v arrives
     // multiplied by the column factors, y leaves to be multiplied by the row factors
@@ -161,9 +162,9 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& m, int sm_count, cudaStream_t
 cudaError_t pn_launch_pairs(const PnPairsLaunch& p, cudaStream_t stream);
 // symmetric-halving products: max |v| into *vmax (device), and the integer planes back to doubles
 // (fac: operand rows holding the factor of the factorised ExpQuad form at [i * fac_ld + fac_idx], or nullptr)
-cudaError_t pn_launch_vmax(const double* v, int64_t ldv, int64_t n, double* vmax, cudaStream_t stream);
-cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int64_t n1, const double* vmax, const double* fac, int fac_ld,
-                            int fac_idx, double* y, cudaStream_t stream);
+cudaError_t pn_launch_vmax(const double* v, int64_t ldv, int64_t n, int k, double* vmax, cudaStream_t stream);
+cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int kc, int64_t n1, const double* vmax, const double* fac,
+                            int fac_ld, int fac_idx, double* y, cudaStream_t stream);
 
 // pncov_api.cu
 extern int64_t g_pn_launches;

@@ -278,7 +278,11 @@ __global__ void __launch_bounds__(MM_THREADS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     double* tabE = reinterpret_cast<double*>(smem + 128);
     double* tabL = tabE + PN_EXP2_N;
-    constexpr int STAGE_DOUBLES = Cfg::TJ * (Cfg::LD + KC);
+    // eight right-hand sides: K V_J as a DMMA itself (see matvec_mma_symd_kernel), V in rows of 10 doubles
+    constexpr bool ACC_MMA = KC == 8;
+    constexpr int KCP = ACC_MMA ? 10 : KC;
+    constexpr int NACC = ACC_MMA ? 2 : KC;
+    constexpr int STAGE_DOUBLES = Cfg::TJ * (Cfg::LD + KCP);
     double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
 
     const int64_t n_jt = a.n1pad / Cfg::TJ;
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(MM_THREADS)
     const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
     const double* bg = static_cast<const double*>(a.b12);
     const double* vg = static_cast<const double*>(a.v);
-    constexpr uint32_t B_BYTES = Cfg::TJ * Cfg::LD * 8, V_BYTES = Cfg::TJ * KC * 8;
+    constexpr uint32_t B_BYTES = Cfg::TJ * Cfg::LD * 8, V_BYTES = Cfg::TJ * KCP * 8;
 
     if (tid == 0) {
         pn_mbar_init(&bars[0], 1);
@@ -297,12 +301,12 @@ __global__ void __launch_bounds__(MM_THREADS)
     if (tid == 0 && jt0 < jt1) {
         pn_mbar_expect_tx(&bars[0], B_BYTES + V_BYTES);
         pn_bulk_g2s(stage0, bg + jt0 * Cfg::TJ * Cfg::LD, B_BYTES, &bars[0]);
-        pn_bulk_g2s(stage0 + Cfg::TJ * Cfg::LD, vg + jt0 * Cfg::TJ * KC, V_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + Cfg::TJ * Cfg::LD, vg + jt0 * Cfg::TJ * KCP, V_BYTES, &bars[0]);
     }
     pn_stage_tables(tabE, tabL, tid, MM_THREADS);
 
     const int64_t row0 = (int64_t)blockIdx.x * MM_ROWS + warp * (MM_RG * 8);
-    double af[MM_RG][KSTEPS], nx[MM_RG], acc[MM_RG][KC];
+    double af[MM_RG][KSTEPS], nx[MM_RG], acc[MM_RG][NACC];
     {
         const double* ag = static_cast<const double*>(a.a12);
 #pragma unroll
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(MM_THREADS)
             for (int kk = 0; kk < KSTEPS; ++kk) af[rg][kk] = pr[4 * kk + q];
             nx[rg] = pr[Cfg::NRM];
 #pragma unroll
-            for (int k = 0; k < KC; ++k) acc[rg][k] = 0.0;
+            for (int k = 0; k < NACC; ++k) acc[rg][k] = 0.0;
         }
     }
     __syncthreads();
@@ -324,7 +328,7 @@ __global__ void __launch_bounds__(MM_THREADS)
             double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
             pn_mbar_expect_tx(&bars[buf ^ 1], B_BYTES + V_BYTES);
             pn_bulk_g2s(dst, bg + (jt + 1) * Cfg::TJ * Cfg::LD, B_BYTES, &bars[buf ^ 1]);
-            pn_bulk_g2s(dst + Cfg::TJ * Cfg::LD, vg + (jt + 1) * Cfg::TJ * KC, V_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + Cfg::TJ * Cfg::LD, vg + (jt + 1) * Cfg::TJ * KCP, V_BYTES, &bars[buf ^ 1]);
         }
         pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
         const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
@@ -363,14 +367,24 @@ __global__ void __launch_bounds__(MM_THREADS)
             for (int s = 0; s < MM_NS; ++s) {
                 const int j = jj + 8 * s;
                 mm_epi_tile<EPI>(S[s], a.epi, tabE, tabL);
-#pragma unroll
-                for (int k = 0; k < KC; ++k) {
-                    const double v0 = vt[(j + 2 * q) * KC + k];
-                    const double v1 = vt[(j + 2 * q + 1) * KC + k];
+                if constexpr (ACC_MMA) {
+                    // K as the A operand (even / odd columns), V[column][right-hand side g] as B: two DMMAs per 8 x 8 block
+                    const double be = vt[(j + 2 * q) * KCP + g], bo = vt[(j + 2 * q + 1) * KCP + g];
 #pragma unroll
                     for (int rg = 0; rg < MM_RG; ++rg) {
-                        acc[rg][k] = pn_fma(S[s][2 * rg], v0, acc[rg][k]);
-                        acc[rg][k] = pn_fma(S[s][2 * rg + 1], v1, acc[rg][k]);
+                        pn_dmma884(acc[rg][0], acc[rg][1], S[s][2 * rg], be);
+                        pn_dmma884(acc[rg][0], acc[rg][1], S[s][2 * rg + 1], bo);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) {
+                        const double v0 = vt[(j + 2 * q) * KC + k];
+                        const double v1 = vt[(j + 2 * q + 1) * KC + k];
+#pragma unroll
+                        for (int rg = 0; rg < MM_RG; ++rg) {
+                            acc[rg][k] = pn_fma(S[s][2 * rg], v0, acc[rg][k]);
+                            acc[rg][k] = pn_fma(S[s][2 * rg + 1], v1, acc[rg][k]);
+                        }
                     }
                 }
             }
@@ -383,12 +397,16 @@ __global__ void __launch_bounds__(MM_THREADS)
 #pragma unroll
     for (int rg = 0; rg < MM_RG; ++rg) {
         const int64_t row = row0 + rg * 8 + g;
+        if constexpr (ACC_MMA) {  // lane (g, q) holds right-hand sides 2 q, 2 q + 1 of row g, complete
+            if (row < a.n0) *reinterpret_cast<double2*>(dst + row * KC + 2 * q) = make_double2(acc[rg][0], acc[rg][1]);
+        } else {
 #pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            double s = acc[rg][k];
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (q == 0 && row < a.n0) dst[row * KC + k] = s;
+            for (int k = 0; k < KC; ++k) {
+                double s = acc[rg][k];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (q == 0 && row < a.n0) dst[row * KC + k] = s;
+            }
         }
     }
 }
@@ -573,6 +591,191 @@ __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
         if (q == 0 && row < a.n0)
             pn_bin_add(bhi, blo, bnf, row, s,
                        pn_bin_exponent(bound0, FACT ? static_cast<const double*>(a.a12)[row * Cfg::LD + Cfg::NRM + 1] : 1.0));
+    }
+}
+
+// ---- symmetric variant for two to eight right-hand sides per pass: both accumulations on the tensor cores ----
+// With eight columns the products K_IJ V_J and K_IJ^T V_I are small GEMMs themselves.  The kernel values of an 8 x 8
+// block sit in the C-fragment layout of the distance DMMA (lane (g, q): row g, columns 2 q, 2 q + 1), which is an
+// A operand as it stands (k-index = column, even and odd columns as two DMMAs): y_I += K V_J costs two DMMAs per
+// block for all eight right-hand sides, accumulators two doubles per row group.  For K^T V_I the block is transposed
+// through 512 bytes of shared memory per row group (one 16-byte store, two 8-byte loads per lane), the B operand
+// -- V of this lane's rows -- lives in registers for the whole kernel, and the 8 x 8 result IS the tile's column-sum
+// fragment: no shuffle butterfly (a DFMA form with a butterfly over the eight lanes of a column pair spent as many
+// instructions on selects and shuffles as on arithmetic: 168 ms against 82 ms for eight columns at N = 262144, where
+// one column takes 44 ms).  Column sums and row sums leave through the integer planes (pn_bin_add) as everywhere.
+// Fewer than eight columns are padded with zeros: the tensor-core tile is eight wide either way.
+constexpr int MD_KC = 8, MD_KCP = 10;  // columns per pass, doubles per packed row of V (conflict-free B-fragment loads)
+constexpr int MD_TJ = 64;               // columns per tile: 16 KB of per-warp column-sum slots, three CTAs per SM
+template <int KSTEPS, int EPI>
+__global__ void __launch_bounds__(MM_THREADS, 3)
+    matvec_mma_symd_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split, int part, int nparts) {
+    using Cfg = MmCfg<KSTEPS>;
+    constexpr int TJ = MD_TJ, TPB = MM_ROWS / MD_TJ, LD = Cfg::LD, KC = MD_KC, KCP = MD_KCP;
+    constexpr bool FACT = EPI == PN_EPI_EXPQUAD_FACT;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    double* tabE = reinterpret_cast<double*>(smem + 128);
+    double* tabL = tabE + PN_EXP2_N;
+    constexpr int STAGE_DOUBLES = TJ * (LD + KCP);
+    double* stage0 = reinterpret_cast<double*>(smem + MV_HDR_BYTES);
+    double* colw = stage0 + 2 * STAGE_DOUBLES;                      // [warps][TJ][KC]
+    double* tr = colw + (MM_THREADS / 32) * TJ * KC + warp * (MM_RG * 64);  // per warp: [MM_RG][8][8] blocks
+
+    const int64_t n_jt = a.n1pad / TJ;
+    const int64_t bx = (int64_t)blockIdx.x * nparts + part;  // this CTA's row block; diagonal tiles TPB bx .. TPB bx + TPB - 1
+    if (bx * TPB >= n_jt) return;
+    const int64_t jdiag_end = (bx + 1) * TPB;
+    int64_t jt0 = (int64_t)blockIdx.y * tiles_per_split;
+    const int64_t jt1 = (jt0 + tiles_per_split < n_jt) ? jt0 + tiles_per_split : n_jt;
+    if (jt0 < bx * TPB) jt0 = bx * TPB;
+    if (jt0 >= jt1) return;
+    const double* bg = static_cast<const double*>(a.b12);
+    const double* vg = static_cast<const double*>(a.v);  // (n1pad, KCP) packed
+    const int64_t plane = a.n0 * KC;
+    long long* const bhi = a.bins;
+    long long* const blo = a.bins + plane;
+    double* const bnf = reinterpret_cast<double*>(a.bins + 2 * plane);
+    const double bound0 = (double)a.n1 * *a.vmax;
+    constexpr uint32_t B_BYTES = TJ * LD * 8, V_BYTES = TJ * KCP * 8;
+
+    if (tid == 0) {
+        pn_mbar_init(&bars[0], 1);
+        pn_mbar_init(&bars[1], 1);
+        pn_mbar_init(&bars[2], 1);
+        pn_mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        pn_mbar_expect_tx(&bars[0], B_BYTES + V_BYTES);
+        pn_bulk_g2s(stage0, bg + jt0 * TJ * LD, B_BYTES, &bars[0]);
+        pn_bulk_g2s(stage0 + TJ * LD, vg + jt0 * TJ * KCP, V_BYTES, &bars[0]);
+        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG);
+    }
+
+    const int64_t row0 = bx * MM_ROWS + warp * (MM_RG * 8);
+    double af[MM_RG][KSTEPS], nx[MM_RG], vrb[MM_RG][2], acc[MM_RG][2];
+    {
+        const double* ag = static_cast<const double*>(a.a12);
+#pragma unroll
+        for (int rg = 0; rg < MM_RG; ++rg) {
+            const double* pr = ag + (row0 + rg * 8 + g) * LD;  // rows are padded to PN_PAD
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) af[rg][kk] = pr[4 * kk + q];
+            nx[rg] = pr[Cfg::NRM];
+            // B operand of the transposed product: V[row q (+ 4) of the group][right-hand side g]; zero in the padding
+            vrb[rg][0] = vg[(row0 + rg * 8 + q) * KCP + g];
+            vrb[rg][1] = vg[(row0 + rg * 8 + q + 4) * KCP + g];
+            acc[rg][0] = 0.0;
+            acc[rg][1] = 0.0;
+        }
+    }
+    pn_mbar_wait(&bars[2], 0);
+
+    int it = 0;
+    for (int64_t jt = jt0; jt < jt1; ++jt, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && jt + 1 < jt1) {
+            double* dst = stage0 + (size_t)(buf ^ 1) * STAGE_DOUBLES;
+            pn_mbar_expect_tx(&bars[buf ^ 1], B_BYTES + V_BYTES);
+            pn_bulk_g2s(dst, bg + (jt + 1) * TJ * LD, B_BYTES, &bars[buf ^ 1]);
+            pn_bulk_g2s(dst + TJ * LD, vg + (jt + 1) * TJ * KCP, V_BYTES, &bars[buf ^ 1]);
+        }
+        // column sums of the previous tile (its slots were completed before the barrier that ended that iteration;
+        // the barrier below keeps this tile's sums out of them until everybody has read)
+        if (it > 0 && jt - 1 >= jdiag_end) {
+            const double* cwp = colw;
+            for (int e = tid; e < TJ * KC; e += MM_THREADS) {
+                double s = cwp[e];
+#pragma unroll
+                for (int w = 1; w < MM_THREADS / 32; ++w) s += cwp[w * TJ * KC + e];
+                const int64_t col = (jt - 1) * TJ + e / KC;
+                if (col < a.n1)
+                    pn_bin_add(bhi, blo, bnf, col * KC + e % KC, s, pn_bin_exponent(bound0, FACT ? bg[col * LD + Cfg::NRM + 1] : 1.0));
+            }
+        }
+        if (it > 0) __syncthreads();
+        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        const double* bt = stage0 + (size_t)buf * STAGE_DOUBLES;
+        const double* vt = bt + TJ * LD;
+        double* cw = colw + warp * TJ * KC;
+        const bool mirror = jt >= jdiag_end;  // uniform; the diagonal tiles hold both (i, j) and (j, i) themselves
+
+#pragma unroll 1
+        for (int j = 0; j < TJ; j += 8) {
+            double S[2 * MM_RG];
+            {
+                double bf[KSTEPS];
+#pragma unroll
+                for (int kk = 0; kk < KSTEPS; ++kk) bf[kk] = bt[(j + g) * LD + 4 * kk + q];
+                const double ny0 = bt[(j + 2 * q) * LD + Cfg::NRM];
+                const double ny1 = bt[(j + 2 * q + 1) * LD + Cfg::NRM];
+#pragma unroll
+                for (int rg = 0; rg < MM_RG; ++rg) {
+                    double c0, c1;
+                    if constexpr (FACT) {
+                        c0 = 0.0;
+                        c1 = 0.0;
+                    } else {
+                        c0 = nx[rg] + ny0;
+                        c1 = nx[rg] + ny1;
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < KSTEPS; ++kk) pn_dmma884(c0, c1, af[rg][kk], bf[kk]);
+                    S[2 * rg] = c0;
+                    S[2 * rg + 1] = c1;
+                }
+            }
+            mm_epi_tile<EPI>(S, a.epi, tabE, tabL);
+            // y_I += K V_J: K as the A operand (even / odd columns), V[column][right-hand side g] as B
+            const double be = vt[(j + 2 * q) * KCP + g], bo = vt[(j + 2 * q + 1) * KCP + g];
+#pragma unroll
+            for (int rg = 0; rg < MM_RG; ++rg) {
+                pn_dmma884(acc[rg][0], acc[rg][1], S[2 * rg], be);
+                pn_dmma884(acc[rg][0], acc[rg][1], S[2 * rg + 1], bo);
+            }
+            if (mirror) {
+                // y_J += K^T V_I: the blocks transposed through shared memory, V of this warp's rows from registers
+#pragma unroll
+                for (int rg = 0; rg < MM_RG; ++rg)
+                    *reinterpret_cast<double2*>(tr + rg * 64 + g * 8 + 2 * q) = make_double2(S[2 * rg], S[2 * rg + 1]);
+                __syncwarp();
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int rg = 0; rg < MM_RG; ++rg) {
+                    pn_dmma884(c0, c1, tr[rg * 64 + q * 8 + g], vrb[rg][0]);
+                    pn_dmma884(c0, c1, tr[rg * 64 + (q + 4) * 8 + g], vrb[rg][1]);
+                }
+                *reinterpret_cast<double2*>(cw + (j + g) * KC + 2 * q) = make_double2(c0, c1);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+    // column sums of the last tile
+    if (jt1 - 1 >= jdiag_end) {
+        const double* cwp = colw;
+        for (int e = tid; e < TJ * KC; e += MM_THREADS) {
+            double s = cwp[e];
+#pragma unroll
+            for (int w = 1; w < MM_THREADS / 32; ++w) s += cwp[w * TJ * KC + e];
+            const int64_t col = (jt1 - 1) * TJ + e / KC;
+            if (col < a.n1)
+                pn_bin_add(bhi, blo, bnf, col * KC + e % KC, s, pn_bin_exponent(bound0, FACT ? bg[col * LD + Cfg::NRM + 1] : 1.0));
+        }
+    }
+    // row sums: lane (g, q) holds rows rg * 8 + g, right-hand sides 2 q and 2 q + 1, complete
+#pragma unroll
+    for (int rg = 0; rg < MM_RG; ++rg) {
+        const int64_t row = row0 + rg * 8 + g;
+        if (row < a.n0) {
+            const int E = pn_bin_exponent(bound0, FACT ? static_cast<const double*>(a.a12)[row * LD + Cfg::NRM + 1] : 1.0);
+            pn_bin_add(bhi, blo, bnf, row * KC + 2 * q, acc[rg][0], E);
+            pn_bin_add(bhi, blo, bnf, row * KC + 2 * q + 1, acc[rg][1], E);
+        }
     }
 }
 
@@ -1034,10 +1237,10 @@ __global__ void __launch_bounds__(MR_THREADS)
 }
 
 // max |v_j| as the bit pattern of a non-negative double (unsigned order = numeric order; NaN sorts above Inf)
-__global__ void vmax_kernel(const double* __restrict__ v, int64_t ldv, int64_t n, unsigned long long* __restrict__ out) {
+__global__ void vmax_kernel(const double* __restrict__ v, int64_t ldv, int64_t n, int k, unsigned long long* __restrict__ out) {
     unsigned long long m = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[i * ldv]));
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * k; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v[(i / k) * ldv + i % k]));
         m = b > m ? b : m;
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -1048,12 +1251,13 @@ __global__ void vmax_kernel(const double* __restrict__ v, int64_t ldv, int64_t n
 }
 
 // integer planes -> y (the same exponents the kernels used: pn_bin_exponent of the same inputs)
-__global__ void unbin_kernel(const long long* __restrict__ bins, int64_t n0, int64_t n1, const double* __restrict__ vmax,
+__global__ void unbin_kernel(const long long* __restrict__ bins, int64_t n0, int kc, int64_t n1, const double* __restrict__ vmax,
                              const double* __restrict__ fac, int fac_ld, int fac_idx, double* __restrict__ y) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n0) return;
-    const int E = pn_bin_exponent((double)n1 * *vmax, fac ? fac[i * fac_ld + fac_idx] : 1.0);
-    y[i] = pn_bin_value(bins[i], bins[n0 + i], reinterpret_cast<const double*>(bins + 2 * n0)[i], E);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // row * kc + column
+    const int64_t plane = n0 * kc;
+    if (i >= plane) return;
+    const int E = pn_bin_exponent((double)n1 * *vmax, fac ? fac[(i / kc) * fac_ld + fac_idx] : 1.0);
+    y[i] = pn_bin_value(bins[i], bins[plane + i], reinterpret_cast<const double*>(bins + 2 * plane)[i], E);
 }
 
 // partial[s][i] summed over s in increasing order (deterministic)
@@ -1190,7 +1394,7 @@ template <int KSTEPS, int KC, int EPI>
 cudaError_t launch_mma(PnMatvecLaunch& a, int sm_count, bool plan_only, cudaStream_t stream) {
     using Cfg = MmCfg<KSTEPS>;
     auto kern = matvec_mma_kernel<KSTEPS, KC, EPI>;
-    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * Cfg::TJ * (Cfg::LD + KC);
+    const size_t smem = MV_HDR_BYTES + 2 * sizeof(double) * Cfg::TJ * (Cfg::LD + (KC == 8 ? 10 : KC));
     const int64_t n_jt = a.n1pad / Cfg::TJ;
     const int64_t row_ctas = (a.n0 + MM_ROWS - 1) / MM_ROWS;
     if (smem > 48 * 1024) {
@@ -1304,6 +1508,44 @@ cudaError_t launch_mma_sym(const PnMatvecLaunch& a, cudaStream_t stream) {
     kern<<<grid, MM_THREADS, smem, stream>>>(a, (int)tps, a.sym_part, nparts);
     ++g_pn_launches;
     return cudaGetLastError();
+}
+
+template <int KSTEPS, int EPI>
+cudaError_t launch_mma_symd(const PnMatvecLaunch& a, cudaStream_t stream) {
+    using Cfg = MmCfg<KSTEPS>;
+    auto kern = matvec_mma_symd_kernel<KSTEPS, EPI>;
+    constexpr int TPB = MM_ROWS / MD_TJ;
+    const size_t smem = MV_HDR_BYTES + sizeof(double) * (2 * MD_TJ * (Cfg::LD + MD_KCP) + (MM_THREADS / 32) * MD_TJ * MD_KC +
+                                                         (MM_THREADS / 32) * MM_RG * 64);
+    const int64_t n_jt = a.n1pad / MD_TJ;
+    const int64_t n_blocks = (n_jt + TPB - 1) / TPB;
+    const int nparts = a.sym_nparts > 0 ? a.sym_nparts : 1;
+    const int64_t row_ctas = (n_blocks + nparts - 1) / nparts;
+    int64_t tps = 256;
+    while (tps > 8 && row_ctas * ((n_blocks + tps - 1) / tps) < (int64_t)pn_sm_count() * 3 * 8) tps /= 2;
+    tps *= TPB;
+    const int64_t chunks = (n_jt + tps - 1) / tps;
+    if (chunks > 65535) return cudaErrorInvalidConfiguration;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    if (!a.bins || !a.vmax) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)row_ctas, (unsigned)chunks);
+    kern<<<grid, MM_THREADS, smem, stream>>>(a, (int)tps, a.sym_part, nparts);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+template <int KSTEPS>
+cudaError_t launch_mma_symd_epi(const PnMatvecLaunch& a, cudaStream_t stream) {
+    switch (a.epi.epi) {
+        case PN_EPI_EXPQUAD:
+            if (a.fact) return launch_mma_symd<KSTEPS, PN_EPI_EXPQUAD_FACT>(a, stream);
+            return launch_mma_symd<KSTEPS, PN_EPI_EXPQUAD>(a, stream);
+        case PN_EPI_RATQUAD1: return launch_mma_symd<KSTEPS, PN_EPI_RATQUAD1>(a, stream);
+        case PN_EPI_RATQUAD2: return launch_mma_symd<KSTEPS, PN_EPI_RATQUAD2>(a, stream);
+        case PN_EPI_RATQUADG: return launch_mma_symd<KSTEPS, PN_EPI_RATQUADG>(a, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 template <int KSTEPS>
@@ -1460,6 +1702,10 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     const int64_t ld1 = a.ld1;
     const bool ard = a.scale != nullptr;
     cudaError_t err;
+    if (a.use_mma == 2 && a.sym && a.kc > 1) {  // several right-hand sides: d <= 8 (checked by the caller), passes of eight
+        if (a.kc != MD_KC) return cudaErrorInvalidValue;
+        return a.d > 4 ? launch_mma_symd_epi<2>(a, stream) : launch_mma_symd_epi<1>(a, stream);
+    }
     if (a.use_mma == 2 && a.sym) {
         if (a.d > 32) return launch_mma_sym_wide<16>(a, stream);
         if (a.d > 8) return a.d <= 16 ? launch_mma_sym_wide<4>(a, stream) : launch_mma_sym_wide<8>(a, stream);
@@ -1503,20 +1749,20 @@ cudaError_t pn_launch_matvec(const PnMatvecLaunch& a_in, int sm_count, cudaStrea
     return err;
 }
 
-cudaError_t pn_launch_vmax(const double* v, int64_t ldv, int64_t n, double* vmax, cudaStream_t stream) {
+cudaError_t pn_launch_vmax(const double* v, int64_t ldv, int64_t n, int k, double* vmax, cudaStream_t stream) {
     cudaError_t err = cudaMemsetAsync(vmax, 0, sizeof(double), stream);
-    if (err != cudaSuccess || n <= 0) return err;
-    int64_t blocks = (n + 255) / 256;
+    if (err != cudaSuccess || n <= 0 || k <= 0) return err;
+    int64_t blocks = (n * k + 255) / 256;
     blocks = blocks > 1024 ? 1024 : blocks;
-    vmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(v, ldv, n, reinterpret_cast<unsigned long long*>(vmax));
+    vmax_kernel<<<(unsigned)blocks, 256, 0, stream>>>(v, ldv, n, k, reinterpret_cast<unsigned long long*>(vmax));
     ++g_pn_launches;
     return cudaGetLastError();
 }
 
-cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int64_t n1, const double* vmax, const double* fac, int fac_ld,
-                            int fac_idx, double* y, cudaStream_t stream) {
+cudaError_t pn_launch_unbin(const long long* bins, int64_t n0, int kc, int64_t n1, const double* vmax, const double* fac,
+                            int fac_ld, int fac_idx, double* y, cudaStream_t stream) {
     if (n0 <= 0) return cudaSuccess;
-    unbin_kernel<<<(unsigned)((n0 + 255) / 256), 256, 0, stream>>>(bins, n0, n1, vmax, fac, fac_ld, fac_idx, y);
+    unbin_kernel<<<(unsigned)((n0 * kc + 255) / 256), 256, 0, stream>>>(bins, n0, kc, n1, vmax, fac, fac_ld, fac_idx, y);
     ++g_pn_launches;
     return cudaGetLastError();
 }

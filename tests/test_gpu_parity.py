@@ -358,8 +358,9 @@ def test_matvec_path_selection_and_parity_of_both_paths():
     x = rng.normal(size=(n, d)) + 300.0  # far from the origin: the centring has to cope
     v = rng.normal(size=(n, 2))
     for spec, want_path in [
-        (orc.KernelSpec("expquad", (d,), 1.0), "norm-identity-dmma"),
-        (orc.KernelSpec("ratquad", (d,), 1.0, alpha=1.7), "norm-identity-dmma"),
+        # x1 = None, two right-hand sides, n >= 2048: the symmetric multi-column form of the identity kernel
+        (orc.KernelSpec("expquad", (d,), 1.0), "norm-identity-dmma-symmetric"),
+        (orc.KernelSpec("ratquad", (d,), 1.0, alpha=1.7), "norm-identity-dmma-symmetric"),
         (orc.KernelSpec("expquad", (d,), 0.02), "direct-differences"),   # R^2 ~ 1e5 scaled units
         (orc.KernelSpec("matern", (d,), 1.0, nu=1.5), "direct-differences"),
     ]:
@@ -474,10 +475,11 @@ def test_symmetric_matvec_matches_oracle(kind, d, n, nu, ls):
         y = L._matmul_device(v)
         assert L._device_op().matmul_path() == family + "-symmetric"
         assert_matvec_close(y, orc.matvec(spec, x, None, v), orc.abs_matvec(spec, x, None, v), 1e-12)
-    # several columns take the ordered kernel and must agree with the one-column results
+    # several columns: the symmetric multi-column form where the DMMA identity kernel serves (d <= 8), the ordered
+    # kernel otherwise; either must agree with the one-column results
     V = rng.normal(size=(n, 3))
     Y = L._matmul_device(V)
-    assert L._device_op().matmul_path() == family
+    assert L._device_op().matmul_path() == (family + "-symmetric" if not direct and d <= 8 else family)
     y0 = L._matmul_device(V[:, :1])
     bound = orc.abs_matvec(spec, x, None, V[:, :1])
     assert np.all(np.abs(Y[:, :1] - y0) <= 1e-13 * bound)

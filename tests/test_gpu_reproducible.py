@@ -100,3 +100,25 @@ def test_tiny_and_huge_right_hand_sides():
         assert np.all(np.abs(y - orc.matvec(spec, x, None, v)) <= 1e-12 * bound + 1e-320), scale
         assert np.array_equal(op.matmul(v), y)
     op.close()
+
+
+@pytest.mark.parametrize("kind,d,kw", [("expquad", 8, dict(lengthscales=1.0)), ("expquad", 3, dict(lengthscales=0.6)),
+                                       ("ratquad", 6, dict(lengthscale=1.3, alpha=1.7))])
+@pytest.mark.parametrize("k", [2, 3, 4, 5, 8, 11, 16])
+def test_symmetric_products_with_several_right_hand_sides(kind, d, kw, k):
+    """x1 = None and 2 .. 16 right-hand sides: symmetric passes of eight columns with both accumulations on the
+    tensor cores (matvec_mma_symd_kernel); same parity bound, bit-reproducible, consistent with the single-column product."""
+    n = 5000
+    rng = np.random.default_rng(23 + k)
+    x = rng.normal(size=(n, d))
+    V = rng.uniform(size=(n, k)) * np.exp(rng.normal(size=(1, k)) * 2.0)
+    op = _lib.Operator(kernel(kind, d, kw)._kernel_params(), x)
+    Y = op.matmul(V)
+    assert op.matmul_path() == "norm-identity-dmma-symmetric"
+    spec = spec_of(kind, d, kw)
+    bound = orc.abs_matvec(spec, x, None, V)
+    assert np.all(np.abs(Y - orc.matvec(spec, x, None, V)) <= 1e-12 * bound)
+    assert np.array_equal(op.matmul(V), Y)
+    y0 = op.matmul(V[:, :1])
+    assert np.all(np.abs(Y[:, :1] - y0) <= 1e-13 * bound[:, :1])
+    op.close()

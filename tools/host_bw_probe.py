@@ -6,7 +6,7 @@
 Every rank copies `--gib` GiB from its GPU into its OWN pinned host buffer, all ranks at once
 (barrier on both sides), in chunks of `--chunk-mib` like pncov_gram's row blocks.  Prints one JSON
 line: per-rank GB/s (min / max) and the aggregate = total bytes / slowest rank's time.  With
-`--numa` each rank first binds itself to the CPUs NVML reports as local to its GPU (what bench.py
+`--bind` each rank first binds itself to the CPUs NVML reports as local to its GPU (what bench.py
 does), so the pinned buffer is allocated on the GPU's own NUMA node.
 """
 import argparse
@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--gib", type=float, default=4.0)
     ap.add_argument("--chunk-mib", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--numa", action="store_true")
+    ap.add_argument("--bind", dest="numa", action="store_true")
     ap.add_argument("--h2d", action="store_true", help="host-to-device instead")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
