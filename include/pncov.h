@@ -298,6 +298,28 @@ PNCOV_API int pncov_chain_apply(pncov_chain* c, int64_t k, int mode, const doubl
  * number of kernel launches issued by this library in the calling process, and the
  * device time in ms of the last pncov_gram / pncov_matmul call of this handle (CUDA
  * events on the handle's stream around the kernels, excluding host<->device copies). */
+/* one operator over several GPUs of ONE process -------------------------------------------------
+ * "device_ids[], n_dev" in the ABI, so that a caller that binds this library without torch
+ * or a process launcher (the reference's FFI: ctypes) can shard.  The rows of x0 are dealt contiguously to the
+ * devices (host pointers, same argument meaning as pncov_create; a device id may repeat).
+ *   pncov_sharded_gram    every device builds its row block and copies it into its slice of the host array
+ *                         (CovarianceFunction.matrix, _covariance_function.py:359-413); no exchange between devices
+ *   pncov_sharded_matmul  K @ V (CovarianceLinearOperator._matmul, _covariance_linear_operator.py:78-81), host
+ *                         operands.  Symmetric operators (x1 == NULL) with one right-hand side use the
+ *                         symmetric-halving kernel: device i takes the row blocks I = i (mod n_dev) of the triangle
+ *                         into exact integer planes, which are added on the host -- the result has the bits a
+ *                         single device gives.  Otherwise every device multiplies its row block.
+ * Devices exchange nothing with each other on this path (results are assembled in host memory), so the library
+ * needs no communicator; device-resident multi-process operands use torch.distributed / NCCL above the ABI
+ * (probnum_b200/sharded.py) with pncov_matmul_sym_part_bins_device. */
+typedef struct pncov_sharded pncov_sharded;
+PNCOV_API int pncov_sharded_create(pncov_sharded** out, const int* device_ids, int n_dev, int kind, int dtype, int64_t d,
+                                   const double* lengthscales, int64_t n_lengthscales, double nu, double alpha,
+                                   const void* x0, int64_t n0, const void* x1, int64_t n1);
+PNCOV_API int pncov_sharded_gram(pncov_sharded* s, void* out, int64_t ld);
+PNCOV_API int pncov_sharded_matmul(pncov_sharded* s, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy);
+PNCOV_API int pncov_sharded_destroy(pncov_sharded* s);
+
 PNCOV_API int64_t pncov_launch_count(void);
 
 /* Bytes pncov_gram has copied device-to-host in this process.  A whole symmetric result (x1 == NULL) may cross

@@ -13,7 +13,7 @@ kernels behind the C ABI of ``include/pncov.h``.  See DESIGN.md.
 """
 
 from . import covfuncs, linops
-from .covfuncs import (CovarianceFunction, CovarianceLinearOperator, ExpQuad, Linear, Matern, Polynomial,
+from .covfuncs import (CovarianceFunction, CovarianceLinearOperator, DeviceMatrix, ExpQuad, Linear, Matern, Polynomial,
                        ProductCovarianceFunction, ProductMatern, RatQuad, ScaledCovarianceFunction,
                        SumCovarianceFunction, WhiteNoise)
 
@@ -22,6 +22,7 @@ __all__ = [
     "linops",
     "CovarianceFunction",
     "CovarianceLinearOperator",
+    "DeviceMatrix",
     "ExpQuad",
     "Matern",
     "RatQuad",

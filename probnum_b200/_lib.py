@@ -81,6 +81,13 @@ SIGNATURES = {
                                              ctypes.POINTER(ctypes.c_float)]),
     "pncov_chol_get_factor": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
     "pncov_chol_last_factor_ms": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_float)]),
+    "pncov_sharded_create": (
+        ctypes.c_int,
+        [ctypes.POINTER(_c_vp), ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_i64, _c_dp, _c_i64,
+         ctypes.c_double, ctypes.c_double, _c_vp, _c_i64, _c_vp, _c_i64]),
+    "pncov_sharded_gram": (ctypes.c_int, [_c_vp, _c_vp, _c_i64]),
+    "pncov_sharded_matmul": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
+    "pncov_sharded_destroy": (ctypes.c_int, [_c_vp]),
     "pncov_d2h_bytes": (ctypes.c_int64, []),
     "pncov_launch_count": (_c_i64, []),
     "pncov_matmul_path": (ctypes.c_int, [_c_vp, ctypes.POINTER(ctypes.c_int)]),
@@ -330,6 +337,63 @@ class Operator:
         ms = ctypes.c_float()
         _check(self._lib.pncov_last_kernel_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
+
+
+class ShardedOperator:
+    """One operator over several GPUs of this process (``pncov_sharded_*``): host arrays in and out, the rows
+    of ``x0`` dealt contiguously to ``devices`` (an id may repeat).  No torch, no process launcher."""
+
+    def __init__(self, params: KernelParams, x0: np.ndarray, x1: Optional[np.ndarray] = None, *, devices=None):
+        self._lib = load()
+        devices = list(range(device_count())) if devices is None else [int(i) for i in devices]
+        self.dtype = np.dtype(x0.dtype)
+        self.x0 = np.ascontiguousarray(x0)
+        self.x1 = None if x1 is None else np.ascontiguousarray(x1, dtype=self.dtype)
+        if self.x0.ndim != 2 or self.x0.shape[1] != params.d:
+            raise ValueError("x0 must have shape (n0, d)")
+        self.shape = (self.x0.shape[0], self.x0.shape[0] if self.x1 is None else self.x1.shape[0])
+        self.gram_dtype = np.dtype(np.float32 if (self.dtype == np.float32 and params.kind == EXPQUAD) else np.float64)
+        ids = (ctypes.c_int * len(devices))(*devices)
+        ls, nls = params._ls()
+        self._h = _c_vp()
+        _check(self._lib.pncov_sharded_create(ctypes.byref(self._h), ids, len(devices), params.kind, _dtype_code(self.dtype),
+                                              params.d, ls, nls, params.nu, params.alpha, _ptr(self.x0), self.shape[0],
+                                              _ptr(self.x1), 0 if self.x1 is None else self.shape[1]))
+
+    def gram(self, out: Optional[np.ndarray] = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, dtype=self.gram_dtype)
+        if out.shape != self.shape or out.dtype != self.gram_dtype or (out.size and out.strides[1] != out.itemsize):
+            raise ValueError("output array has the wrong shape, dtype or layout")
+        ld = out.strides[0] // out.itemsize if self.shape[0] > 1 else max(self.shape[1], 1)
+        _check(self._lib.pncov_sharded_gram(self._h, _ptr(out), ld))
+        return out
+
+    def matmul(self, v: np.ndarray) -> np.ndarray:
+        v = np.ascontiguousarray(v, dtype=self.dtype)
+        if v.ndim != 2 or v.shape[0] != self.shape[1]:
+            raise ValueError("v must have shape (n1, k)")
+        k = v.shape[1]
+        y = np.zeros((self.shape[0], k), dtype=self.dtype) if self.shape[1] == 0 else np.empty((self.shape[0], k), dtype=self.dtype)
+        _check(self._lib.pncov_sharded_matmul(self._h, _ptr(v), k, max(k, 1), _ptr(y), max(k, 1)))
+        return y
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._lib.pncov_sharded_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def pairs(params: KernelParams, x0: np.ndarray, x1: np.ndarray, device: Optional[int] = None) -> np.ndarray:

@@ -96,6 +96,34 @@ def _as_numpy_scalar(x, dtype=np.double):
     return np.asarray(x, dtype=dtype)[()]
 
 
+class DeviceMatrix:
+    """A row-major float64 matrix in the memory of one GPU (``CovarianceFunction.matrix_device``)."""
+
+    def __init__(self, buffer: "_lib.DeviceBuffer", shape):
+        self.buffer, self.shape, self.dtype = buffer, tuple(shape), np.dtype(np.float64)
+
+    @property
+    def ptr(self) -> int:
+        return self.buffer.ptr
+
+    @property
+    def device(self) -> int:
+        return self.buffer.device
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": self.shape, "typestr": "<f8", "data": (self.buffer.ptr, False), "version": 3, "strides": None}
+
+    def to_host(self) -> np.ndarray:
+        out = hostmem.empty(self.shape, np.float64)
+        if out.size:
+            self.buffer.to_host(out)
+        return out
+
+    def close(self) -> None:
+        self.buffer.close()
+
+
 class CovarianceFunction(abc.ABC):
     """(Cross-)covariance function with scalar output, evaluated on the GPU.
 
@@ -162,6 +190,22 @@ class CovarianceFunction(abc.ABC):
         assert isinstance(K, np.ndarray)
         assert K.shape == (x0.shape[0], x1.shape[0] if x1 is not None else x0.shape[0])
         return K
+
+    def matrix_device(self, x0, x1=None, device: Optional[int] = None) -> "DeviceMatrix":
+        """The float64 Gram matrix of ``matrix(x0, x1)`` left in HBM (not part of the reference's API): for
+        consumers on the device -- a factorisation, further arithmetic, a torch / CuPy computation through
+        ``__cuda_array_interface__`` -- that would otherwise pay two PCIe crossings of N0 x N1 doubles.
+        ``.to_host()`` gives the array ``matrix`` returns."""
+        x0 = self._preprocess_linop_input(x0, argnum=0)
+        if x1 is not None:
+            x1 = self._preprocess_linop_input(x1, argnum=1)
+        n0 = x0.shape[0]
+        n1 = n0 if x1 is None else x1.shape[0]
+        buf = _lib.DeviceBuffer(8 * max(n0 * n1, 1), device=device)
+        if n0 and n1:
+            x0f = np.asarray(x0, dtype=np.float64)
+            self._gram_to_device(x0f, None if x1 is None else np.asarray(x1, dtype=np.float64), buf)
+        return DeviceMatrix(buf, (n0, n1))
 
     def linop(self, x0, x1=None) -> linops.LinearOperator:
         """Matrix-free operator for the Gram matrix (:415-488)."""
@@ -758,6 +802,15 @@ class _ArithmeticNode(CovarianceFunction):
 
     def _gram_to_device(self, x0, x1, out) -> None:
         n1 = x0.shape[0] if x1 is None else x1.shape[0]
+        prog = _compile_program(self) if _FUSED_ARITHMETIC else None
+        if prog is not None:  # one launch (see _evaluate_matrix)
+            leaves, steps, params = prog
+            dt = np.dtype(np.float64)
+            with _lib.Operator(params, self._points(x0, dt), None if x1 is None else self._points(x1, dt),
+                               device=out.device) as op:
+                op.set_program(leaves, steps)
+                op.gram_device(out.ptr, n1)
+            return
         self._combine_into(x0, x1, out, x0.shape[0] * n1)
 
     def _result_dtype(self, compute_dtype: np.dtype) -> np.dtype:

@@ -9,7 +9,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -1918,6 +1920,170 @@ PNCOV_API int pncov_last_kernel_ms(const pncov_handle* h, float* ms) {
     PN_CUDA(cudaEventSynchronize(h->ev1));
     PN_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return 0;
+}
+
+
+// ---- one operator over several GPUs of this process (no torch, no launcher) --------------------------------------
+struct pncov_sharded {
+    int n_dev = 0;
+    int64_t n0 = 0, n1 = 0, d = 0;
+    size_t es = 8;
+    bool symmetric = false;
+    std::vector<int> devices;
+    std::vector<int64_t> lo, hi;          // row block of every device
+    std::vector<pncov_handle*> rows;      // K(x0[lo:hi], x1) on device i
+    std::vector<pncov_handle*> whole;     // symmetric only: K(x0, x0) on device i (round-robin row blocks of the triangle)
+    std::vector<void*> v_dev, bins_dev;   // symmetric one-column products: right-hand side and integer planes per device
+    void* y_dev = nullptr;
+    int whole_state = 0;                  // 0 = untried, 1 = symmetric kernel serves, -1 = it does not
+};
+
+namespace {
+
+// run fn(i) for every device on its own thread; first failure wins (its message becomes this thread's last error)
+int for_each_device(int n, const std::function<int(int)>& fn) {
+    std::vector<int> rc(n, 0);
+    std::vector<std::string> msg(n);
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i)
+        th.emplace_back([&, i] {
+            rc[i] = fn(i);
+            if (rc[i]) msg[i] = t_err;
+        });
+    for (auto& t : th) t.join();
+    for (int i = 0; i < n; ++i)
+        if (rc[i]) return fail(rc[i], msg[i]);
+    return 0;
+}
+
+}  // namespace
+
+PNCOV_API int pncov_sharded_destroy(pncov_sharded* s) {
+    if (!s) return 0;
+    for (int i = 0; i < s->n_dev; ++i) {
+        if (i < (int)s->rows.size()) pncov_destroy(s->rows[i]);
+        if (i < (int)s->whole.size()) pncov_destroy(s->whole[i]);
+        if (i < (int)s->v_dev.size() && s->v_dev[i]) pncov_device_free(s->devices[i], s->v_dev[i]);
+        if (i < (int)s->bins_dev.size() && s->bins_dev[i]) pncov_device_free(s->devices[i], s->bins_dev[i]);
+    }
+    if (s->y_dev) pncov_device_free(s->devices[0], s->y_dev);
+    delete s;
+    return 0;
+}
+
+PNCOV_API int pncov_sharded_create(pncov_sharded** out, const int* device_ids, int n_dev, int kind, int dtype, int64_t d,
+                                   const double* lengthscales, int64_t n_lengthscales, double nu, double alpha, const void* x0,
+                                   int64_t n0, const void* x1, int64_t n1) {
+    if (!out) return fail(PNCOV_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!device_ids || n_dev < 1 || n_dev > 64) return fail(PNCOV_EINVAL, "1 .. 64 device ids");
+    if (n0 < 0 || (x1 && n1 < 0) || (n0 > 0 && !x0)) return fail(PNCOV_EINVAL, "bad point sets");
+    if (dtype != PNCOV_F64 && dtype != PNCOV_F32) return fail(PNCOV_EINVAL, "unknown dtype");
+    pncov_sharded* s = new (std::nothrow) pncov_sharded();
+    if (!s) return fail(PNCOV_ENOMEM, "out of host memory");
+    s->n_dev = n_dev;
+    s->n0 = n0;
+    s->n1 = x1 ? n1 : n0;
+    s->d = d;
+    s->es = dtype == PNCOV_F32 ? 4 : 8;
+    s->symmetric = x1 == nullptr;
+    s->devices.assign(device_ids, device_ids + n_dev);
+    s->rows.assign(n_dev, nullptr);
+    s->whole.assign(n_dev, nullptr);
+    s->v_dev.assign(n_dev, nullptr);
+    s->bins_dev.assign(n_dev, nullptr);
+    const int64_t per = (n0 + n_dev - 1) / n_dev;
+    for (int i = 0; i < n_dev; ++i) {
+        s->lo.push_back(std::min<int64_t>(n0, i * per));
+        s->hi.push_back(std::min<int64_t>(n0, (i + 1) * per));
+    }
+    const void* cols = x1 ? x1 : x0;
+    const int64_t ncols = s->n1;
+    int rc = for_each_device(n_dev, [&](int i) {
+        const char* block = static_cast<const char*>(x0) + (size_t)s->lo[i] * d * s->es;
+        // one device: keep x1 = NULL so that the symmetric kernels serve the whole operator
+        if (n_dev == 1 && s->symmetric)
+            return pncov_create(&s->rows[i], s->devices[i], kind, dtype, d, lengthscales, n_lengthscales, nu, alpha, x0, n0, nullptr, 0, 0);
+        return pncov_create(&s->rows[i], s->devices[i], kind, dtype, d, lengthscales, n_lengthscales, nu, alpha, block,
+                            s->hi[i] - s->lo[i], cols, ncols, 0);
+    });
+    if (rc == 0 && s->symmetric && n_dev > 1 && dtype == PNCOV_F64 && kind <= PNCOV_RATQUAD && n0 >= 2048 && d <= 96)
+        rc = for_each_device(n_dev, [&](int i) {
+            return pncov_create(&s->whole[i], s->devices[i], kind, dtype, d, lengthscales, n_lengthscales, nu, alpha, x0, n0, nullptr, 0, 0);
+        });
+    if (rc) {
+        const std::string keep = t_err;
+        pncov_sharded_destroy(s);
+        return fail(rc, keep);
+    }
+    *out = s;
+    return 0;
+}
+
+PNCOV_API int pncov_sharded_gram(pncov_sharded* s, void* out, int64_t ld) {
+    if (!s) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (s->n0 == 0 || s->n1 == 0) return 0;
+    if (!out || ld < s->n1) return fail(PNCOV_EINVAL, "bad output buffer / leading dimension");
+    return for_each_device(s->n_dev, [&](int i) {
+        if (s->hi[i] == s->lo[i]) return 0;
+        int gdt = PNCOV_F64;
+        pncov_gram_dtype(s->rows[i], &gdt);
+        const size_t ge = gdt == PNCOV_F32 ? 4 : 8;
+        return pncov_gram(s->rows[i], static_cast<char*>(out) + (size_t)s->lo[i] * ld * ge, ld, 0);
+    });
+}
+
+PNCOV_API int pncov_sharded_matmul(pncov_sharded* s, const void* v, int64_t k, int64_t ldv, void* y, int64_t ldy) {
+    if (!s) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (k < 0 || ldv < k || ldy < k) return fail(PNCOV_EINVAL, "bad column count / leading dimension");
+    if (k == 0 || s->n0 == 0) return 0;
+    if (!v || !y) return fail(PNCOV_EINVAL, "NULL operand");
+    const int64_t n = s->n0;
+    // symmetric operator, one right-hand side: every device takes the row blocks I = i (mod n_dev) of the triangle into
+    // exact integer planes, the host adds the planes (integer addition: the result is the bits one device would give)
+    if (s->whole[0] && k == 1 && s->whole_state >= 0) {
+        std::vector<std::vector<long long>> planes(s->n_dev, std::vector<long long>((size_t)3 * n));
+        int rc = for_each_device(s->n_dev, [&](int i) {
+            const int dev = s->devices[i];
+            int r;
+            if (!s->v_dev[i] && (r = pncov_device_alloc(dev, &s->v_dev[i], n * 8))) return r;
+            if (!s->bins_dev[i] && (r = pncov_device_alloc(dev, &s->bins_dev[i], n * 24))) return r;
+            DeviceGuard guard(dev);
+            cudaStream_t st = s->whole[i]->stream;
+            PN_CUDA(cudaMemcpy2DAsync(s->v_dev[i], 8, v, (size_t)ldv * 8, 8, (size_t)n, cudaMemcpyHostToDevice, st));
+            if ((r = pncov_matmul_sym_part_bins_device(s->whole[i], s->v_dev[i], s->bins_dev[i], i, s->n_dev, st))) return r;
+            PN_CUDA(cudaMemcpyAsync(planes[i].data(), s->bins_dev[i], (size_t)n * 24, cudaMemcpyDeviceToHost, st));
+            PN_CUDA(cudaStreamSynchronize(st));
+            return 0;
+        });
+        if (rc == PNCOV_ENOTIMPL && s->whole_state == 0) {
+            s->whole_state = -1;  // the symmetric kernel does not apply to this data: row-sharded products below
+        } else if (rc) {
+            return rc;
+        } else {
+            s->whole_state = 1;
+            std::vector<long long>& acc = planes[0];
+            for (int i = 1; i < s->n_dev; ++i) {
+                for (int64_t j = 0; j < 2 * n; ++j) acc[j] += planes[i][j];
+                double* a = reinterpret_cast<double*>(acc.data() + 2 * n);
+                const double* b = reinterpret_cast<const double*>(planes[i].data() + 2 * n);
+                for (int64_t j = 0; j < n; ++j) a[j] += b[j];
+            }
+            const int dev = s->devices[0];
+            if (!s->y_dev && (rc = pncov_device_alloc(dev, &s->y_dev, n * 8))) return rc;
+            DeviceGuard guard(dev);
+            cudaStream_t st = s->whole[0]->stream;
+            PN_CUDA(cudaMemcpyAsync(s->bins_dev[0], acc.data(), (size_t)n * 24, cudaMemcpyHostToDevice, st));
+            if ((rc = pncov_matmul_sym_finish_device(s->whole[0], s->bins_dev[0], s->y_dev, st))) return rc;
+            PN_CUDA(cudaMemcpy2DAsync(y, (size_t)ldy * 8, s->y_dev, 8, 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+            PN_CUDA(cudaStreamSynchronize(st));
+            return 0;
+        }
+    }
+    return for_each_device(s->n_dev, [&](int i) {
+        if (s->hi[i] == s->lo[i]) return 0;
+        return pncov_matmul(s->rows[i], v, k, ldv, static_cast<char*>(y) + (size_t)s->lo[i] * ldy * s->es, ldy, 0);
+    });
 }
 
 }  // extern "C"

@@ -143,3 +143,22 @@ def test_product_matern_symmetric_kernel(d, nu):
         km = pb.ProductMatern((d,), lengthscales=1.0, nus=np.array([0.5, 1.5, 2.5]))
         Km = km.matrix(x)
         assert np.array_equal(Km, km.matrix(x, x.copy()))
+
+
+def test_matrix_device_keeps_the_result_in_hbm():
+    """`matrix_device` (not in the reference): the Gram matrix stays on the GPU, readable through
+    `__cuda_array_interface__`; `.to_host()` is the array `matrix` returns."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    x0, x1 = rng.normal(size=(700, 3)), rng.normal(size=(300, 3))
+    for k in (pb.Matern((3,), nu=2.5), 2.0 * pb.ExpQuad((3,)) + pb.WhiteNoise((3,), sigma_sq=0.1), pb.Linear((3,), constant=1.0)):
+        for a, b in ((x0, None), (x0, x1)):
+            D = k.matrix_device(a, b)
+            want = k.matrix(a, b)
+            assert D.shape == want.shape
+            assert np.array_equal(D.to_host(), want)
+            t = torch.as_tensor(D, device=f"cuda:{D.device}")
+            assert np.array_equal(t.cpu().numpy(), want)
+            D.close()
+    assert pb.ExpQuad((3,)).matrix_device(np.zeros((0, 3))).to_host().shape == (0, 0)
