@@ -369,8 +369,8 @@ class Ctx:
 
 def leg_matvec(ctx: Ctx, args, extra: dict) -> int:
     """configs[2]: matrix-free ExpQuad K.v, N = 2^20, d = 8.  K = 1 (v ~ N(0,1)): symmetric halving,
-    round-robin row blocks + ONE all-reduce for G > 1.  K = 8 (V ~ U(0,1)): row-sharded + ONE all-gather.
-    Both results are checked on sampled rows against the reference."""
+    round-robin row blocks + ONE all-reduce of the exact integer planes for G > 1.  K = 8 (V ~ U(0,1)): the same with
+    both accumulations on the tensor cores.  Both results are checked on sampled rows against the reference."""
     import probnum_b200 as pb  # noqa: PLC0415
     from probnum_b200 import _lib  # noqa: PLC0415
     from probnum_b200.sharded import ShardedCovarianceOperator  # noqa: PLC0415
@@ -412,13 +412,13 @@ def leg_matvec(ctx: Ctx, args, extra: dict) -> int:
         launches += _lib.launch_count() - l0
         ms = ctx.max_over_ranks(e0.elapsed_time(e1) / reps)
         flop_per_pair = 3 * D_MV + 1 + 2 * kcols  # 3d + 1 + 2K, FMA = 2
-        path_op = sop.local_sym if (sop is not None and kcols == 1 and sop.local_sym is not None) else local_op
+        path_op = sop.local_sym if (sop is not None and sop.local_sym is not None) else local_op
         symmetric = path_op.matmul_path().endswith("symmetric")
         rec = {
             "kernel": path_op.matmul_path(),
             "workload": f"ExpQuad K.V, N={nm}, d={D_MV}, K={kcols}, float64, V ~ " + ("N(0,1)" if kcols == 1 else "U(0,1)") + "; " + (
                 ("symmetric halving (each off-diagonal tile evaluated once)" + (
-                    "" if world == 1 else f", row blocks round-robin over {world} GPUs + all-reduce")) if symmetric
+                    "" if world == 1 else f", row blocks round-robin over {world} GPUs + all-reduce of the exact integer planes")) if symmetric
                 else f"row-sharded over {world} GPU(s)" + ("" if world == 1 else " + all-gather")),
             "ms": ms, "pairs_per_s": float(nm) * nm / (ms * 1e-3),
             "gflops": float(nm) * nm * flop_per_pair / (ms * 1e-3) / 1e9,

@@ -157,6 +157,13 @@ PNCOV_API int pncov_matmul_sym_part_device(pncov_handle* h, const void* v, void*
 PNCOV_API int pncov_matmul_sym_part_bins_device(pncov_handle* h, const void* v, void* bins, int part, int nparts,
                                                 void* stream);
 PNCOV_API int pncov_matmul_sym_finish_device(pncov_handle* h, const void* bins, void* y, void* stream);
+/* The same for 1 .. 8 right-hand sides at once (v: (n, k) with leading dimension ldv, device memory).  For k > 1 the
+ * planes hold 3 * 8 * n0 words (eight columns per pass, unused ones zero) and the kernel is the tensor-core form
+ * (d <= 8, admissible norm identity); k = 1 is the call above.  PNCOV_ENOTIMPL when that kernel does not apply. */
+PNCOV_API int pncov_matmulk_sym_part_bins_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* bins,
+                                                 int part, int nparts, void* stream);
+PNCOV_API int pncov_matmulk_sym_finish_device(pncov_handle* h, const void* bins, int64_t k, void* y, int64_t ldy,
+                                              void* stream);
 
 /* Per-handle choice of the product kernels (value: 1 on, 0 off, -1 default = automatic, subject to the
  * PNCOV_MATVEC_IDENT / _SYM / _FACT environment switches).  Switching all three off selects the most

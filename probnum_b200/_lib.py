@@ -54,6 +54,8 @@ SIGNATURES = {
     "pncov_matmul_sym_part_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
     "pncov_matmul_sym_part_bins_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
     "pncov_matmul_sym_finish_device": (ctypes.c_int, [_c_vp, _c_vp, _c_vp, _c_vp]),
+    "pncov_matmulk_sym_part_bins_device": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, ctypes.c_int, ctypes.c_int, _c_vp]),
+    "pncov_matmulk_sym_finish_device": (ctypes.c_int, [_c_vp, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp]),
     "pncov_set_option": (ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.c_int]),
     "pncov_set_program": (
         ctypes.c_int, [_c_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int), _c_dp, _c_dp, _c_dp, ctypes.c_int,
@@ -328,6 +330,15 @@ class Operator:
         """Integer planes (3 n0 words of 8 bytes) of the contribution of row blocks part, part + nparts, ..."""
         _check(self._lib.pncov_matmul_sym_part_bins_device(self._h, _c_vp(v_ptr), _c_vp(bins_ptr), int(part), int(nparts),
                                                            _c_vp(stream)))
+
+    def matmulk_sym_part_bins_device(self, v_ptr: int, k: int, ldv: int, bins_ptr: int, part: int, nparts: int,
+                                     stream: int = 0) -> None:
+        """1 .. 8 right-hand sides: integer planes (3 n0 words for k = 1, 24 n0 for k > 1) of this part's row blocks."""
+        _check(self._lib.pncov_matmulk_sym_part_bins_device(self._h, _c_vp(v_ptr), int(k), int(ldv), _c_vp(bins_ptr), int(part),
+                                                            int(nparts), _c_vp(stream)))
+
+    def matmulk_sym_finish_device(self, bins_ptr: int, k: int, y_ptr: int, ldy: int, stream: int = 0) -> None:
+        _check(self._lib.pncov_matmulk_sym_finish_device(self._h, _c_vp(bins_ptr), int(k), _c_vp(y_ptr), int(ldy), _c_vp(stream)))
 
     def matmul_sym_finish_device(self, bins_ptr: int, y_ptr: int, stream: int = 0) -> None:
         """Summed integer planes -> y (n0 doubles)."""

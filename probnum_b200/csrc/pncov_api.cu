@@ -909,14 +909,18 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 96);  // DMMA identity or direct differences
         const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : h->env_sym != 0;
         bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;
-        if (sym_nparts > 0 && !sym_ok)
+        if (sym_nparts > 0 && !sym_ok && k == 1)
             return fail(PNCOV_ENOTIMPL, "symmetric partial product needs x1 = x0, one column, float64, d <= 96 and n >= 2048");
         // several right-hand sides on the DMMA identity kernel (d <= 8): symmetric passes of eight columns (zero padded)
-        if (h->symmetric && m.use_mma == 2 && h->k.d <= 8 && k > 1 && es == 8 && R.n >= 2048 && sym_on && sym_nparts == 0) {
+        if (h->symmetric && m.use_mma == 2 && h->k.d <= 8 && k > 1 && es == 8 && R.n >= 2048 && sym_on &&
+            (sym_nparts == 0 || (bins_out && k <= 8))) {
             sym_ok = true;
             kc_max = 8;
             m.kc = kc_max;
         }
+        if (sym_nparts > 0 && !sym_ok)
+            return fail(PNCOV_ENOTIMPL, "symmetric partial products with 2 .. 8 columns need x1 = x0, float64, d <= 8, n >= 2048 and "
+                                        "an admissible norm-identity kernel");
         m.sym = sym_ok ? 1 : 0;
         m.sym_part = sym_part;
         m.sym_nparts = sym_nparts > 0 ? sym_nparts : 1;
@@ -1304,6 +1308,33 @@ PNCOV_API int pncov_matmul_sym_part_bins_device(pncov_handle* h, const void* v, 
     PN_CUDA(cudaEventRecord(h->ev1, stream));
     h->timed = true;
     return 0;
+}
+
+PNCOV_API int pncov_matmulk_sym_part_bins_device(pncov_handle* h, const void* v, int64_t k, int64_t ldv, void* bins, int part,
+                                                 int nparts, void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(PNCOV_EINVAL, "bad part / nparts");
+    if (k < 1 || k > 8 || ldv < k) return fail(PNCOV_EINVAL, "1 .. 8 columns per call");
+    if (!v || !bins) return fail(PNCOV_EINVAL, "NULL operand");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
+    PN_CUDA(cudaEventRecord(h->ev0, stream));
+    int rc = matmul_device_impl(h, v, k, ldv, nullptr, 1, false, stream, part, nparts, bins);
+    if (rc) return rc;
+    PN_CUDA(cudaEventRecord(h->ev1, stream));
+    h->timed = true;
+    return 0;
+}
+
+PNCOV_API int pncov_matmulk_sym_finish_device(pncov_handle* h, const void* bins, int64_t k, void* y, int64_t ldy, void* stream_) {
+    if (!h) return fail(PNCOV_EINVAL, "handle is NULL");
+    if (!bins || !y || k < 1 || k > 8 || ldy < k) return fail(PNCOV_EINVAL, "bad arguments");
+    if (!h->last_sym || !h->vmax_dev) return fail(PNCOV_EINVAL, "no symmetric partial product was computed on this handle");
+    DeviceGuard guard(h->device);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    h->used_foreign_stream = true;
+    return sym_finish(h, bins, y, ldy, stream, k == 1 ? 1 : 8, k, 0);
 }
 
 PNCOV_API int pncov_matmul_sym_finish_device(pncov_handle* h, const void* bins, void* y, void* stream_) {

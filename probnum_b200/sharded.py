@@ -96,7 +96,7 @@ class ShardedCovarianceOperator:
         vec = v.ndim == 1
         v2 = np.ascontiguousarray(v.reshape(v.shape[0], -1), dtype=self.dtype)
         k = v2.shape[1]
-        if self.local_sym is not None and k == 1:
+        if self.local_sym is not None and (k == 1 or not hasattr(self.local_sym, "matmul_sym_part")):
             y = self._matmul_symmetric_host(v2)
             if y is not None:
                 return y[:, 0] if vec else y
@@ -131,28 +131,33 @@ class ShardedCovarianceOperator:
         return None if y is None else y.cpu().numpy()
 
     def _sym_product_device(self, v, out=None):
-        """Full product (CUDA tensor, on every rank) through the symmetric-halving kernel, or None if it
-        does not apply.  Every rank accumulates its row blocks into integer planes (pncov.h:
-        pncov_matmul_sym_part_bins_device), the planes are summed by ONE all-reduce each (int64 for the
-        two integer planes, float64 for the plane of non-finite contributions) and converted: integer
-        addition is associative, so the result has the same bits for every number of ranks."""
+        """Full product (CUDA tensor (N, K), on every rank) through the symmetric-halving kernels, or None if they
+        do not apply.  Every rank accumulates its row blocks into integer planes (pncov.h:
+        pncov_matmulk_sym_part_bins_device; passes of up to eight columns), the planes are summed by ONE all-reduce
+        each (int64 for the two integer planes, float64 for the plane of non-finite contributions) and converted:
+        integer addition is associative, so the result has the same bits for every number of ranks."""
         import torch  # noqa: PLC0415
 
         dist = _dist()
-        n = self.shape[0]
-        bins = torch.empty(3 * n, dtype=torch.int64, device=v.device)
+        n, k = self.shape[0], v.shape[1]
         stream = torch.cuda.current_stream(v.device).cuda_stream
-        try:
-            self.local_sym.matmul_sym_part_bins_device(v.data_ptr(), bins.data_ptr(), self.rank, self.world, stream=stream)
-        except NotImplementedError:
-            self.local_sym.close()
-            self.local_sym = None
-            return None
-        dist.all_reduce(bins[: 2 * n], op=dist.ReduceOp.SUM, group=self.group)
-        dist.all_reduce(bins[2 * n:].view(torch.float64), op=dist.ReduceOp.SUM, group=self.group)
         if out is None:
-            out = torch.empty((n, 1), dtype=torch.float64, device=v.device)
-        self.local_sym.matmul_sym_finish_device(bins.data_ptr(), out.data_ptr(), stream=stream)
+            out = torch.empty((n, k), dtype=torch.float64, device=v.device)
+        for c0 in range(0, k, 8):
+            kk = min(8, k - c0)
+            words = n if kk == 1 else 8 * n  # per plane
+            bins = torch.empty(3 * words, dtype=torch.int64, device=v.device)
+            try:
+                self.local_sym.matmulk_sym_part_bins_device(v.data_ptr() + 8 * c0, kk, k, bins.data_ptr(), self.rank, self.world,
+                                                            stream=stream)
+            except NotImplementedError:
+                if k == 1:  # no symmetric kernel for this data at all
+                    self.local_sym.close()
+                    self.local_sym = None
+                return None
+            dist.all_reduce(bins[: 2 * words], op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(bins[2 * words:].view(torch.float64), op=dist.ReduceOp.SUM, group=self.group)
+            self.local_sym.matmulk_sym_finish_device(bins.data_ptr(), kk, out.data_ptr() + 8 * c0, k, stream=stream)
         return out
 
     def __matmul__(self, v):
@@ -185,9 +190,9 @@ class ShardedCovarianceOperator:
             raise ValueError("v must be a contiguous (N1, K) CUDA tensor")
         k = v.shape[1]
         rows = self.hi - self.lo
-        if self.local_sym is not None and k == 1 and v.dtype == torch.float64:
-            if out is not None and not (out.is_contiguous() and out.dtype == torch.float64 and tuple(out.shape) == (n0, 1)):
-                raise ValueError("out must be a contiguous float64 (N0, 1) CUDA tensor")
+        if self.local_sym is not None and v.dtype == torch.float64:
+            if out is not None and not (out.is_contiguous() and out.dtype == torch.float64 and tuple(out.shape) == (n0, k)):
+                raise ValueError("out must be a contiguous float64 (N0, K) CUDA tensor")
             y = self._sym_product_device(v, out)
             if y is not None:
                 return y
