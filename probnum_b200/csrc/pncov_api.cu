@@ -7,7 +7,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sys/mman.h>
+
 #include <algorithm>
+#include <map>
 #include <chrono>
 #include <functional>
 #include <mutex>
@@ -1013,16 +1016,60 @@ PNCOV_API int pncov_device_count(int* count) {
     return 0;
 }
 
+// Large page-locked blocks: an anonymous mapping advised towards transparent huge pages, populated by all host
+// worker threads at once and then registered with the driver.  cudaHostAlloc populates and pins 4 KB pages from one
+// thread (0.2 s per GB on this pool's hosts: 3.5 s before the first 2 x 8.6 GB result); huge pages also take the
+// TLB pressure off the host-side mirroring of symmetric results (pncov_host.cu).  PNCOV_HOST_ALLOC=cuda keeps
+// cudaHostAlloc for everything.
+namespace {
+std::mutex g_host_map_mutex;
+std::map<void*, size_t> g_host_maps;  // blocks that came from mmap + cudaHostRegister
+}  // namespace
+
 PNCOV_API int pncov_host_alloc(void** ptr, int64_t nbytes) {
     if (!ptr || nbytes < 0) return fail(PNCOV_EINVAL, "bad arguments");
     *ptr = nullptr;
     if (nbytes == 0) return 0;
+    static const bool use_mmap = !(getenv("PNCOV_HOST_ALLOC") && strcmp(getenv("PNCOV_HOST_ALLOC"), "cuda") == 0);
+    static const bool use_thp = !(getenv("PNCOV_HOST_ALLOC") && strcmp(getenv("PNCOV_HOST_ALLOC"), "mmap4k") == 0);
+    if (use_mmap && nbytes >= (64ll << 20)) {
+        const size_t len = ((size_t)nbytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            madvise(p, len, use_thp ? MADV_HUGEPAGE : MADV_NOHUGEPAGE);
+            pn_host_touch(p, len);
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_host_map_mutex);
+                g_host_maps[p] = len;
+                *ptr = p;
+                return 0;
+            }
+            cudaGetLastError();
+            munmap(p, len);
+        }
+    }
     PN_CUDA(cudaHostAlloc(ptr, (size_t)nbytes, cudaHostAllocPortable));
     return 0;
 }
 
 PNCOV_API int pncov_host_free(void* ptr) {
-    if (ptr) PN_CUDA(cudaFreeHost(ptr));
+    if (!ptr) return 0;
+    size_t len = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_host_map_mutex);
+        auto it = g_host_maps.find(ptr);
+        if (it != g_host_maps.end()) {
+            len = it->second;
+            g_host_maps.erase(it);
+        }
+    }
+    if (len) {
+        cudaError_t e = cudaHostUnregister(ptr);
+        munmap(ptr, len);
+        if (e != cudaSuccess) return fail_cuda(e, "cudaHostUnregister");
+        return 0;
+    }
+    PN_CUDA(cudaFreeHost(ptr));
     return 0;
 }
 

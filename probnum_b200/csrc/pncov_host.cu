@@ -167,6 +167,19 @@ void mirror_rect(T* base, int64_t ld, int64_t r0, int64_t r1, int64_t c0, int64_
 
 int pn_host_threads() { return pool()->size(); }
 
+// write zeros to [p, p + bytes) from all worker threads: populates the pages of a fresh mapping in parallel
+// (page faults, not bandwidth, bound a single thread to ~2 GB/s)
+void pn_host_touch(void* p, size_t bytes) {
+    HostPool* hp = pool();
+    const size_t chunk = (size_t)32 << 20;
+    for (size_t o = 0; o < bytes; o += chunk) {
+        const size_t len = bytes - o < chunk ? bytes - o : chunk;
+        char* q = static_cast<char*>(p) + o;
+        hp->submit([=] { memset(q, 0, len); });
+    }
+    hp->wait_idle();
+}
+
 // Queue the mirror image of rows [r0, r1) x columns [r1, n) of the (n, n) host matrix `out`: destination rows
 // [r1, n), columns [r0, r1).  Split over the pool by destination rows.  elem = 4 or 8 bytes.
 void pn_host_mirror_async(void* out, int64_t ld, int64_t n, int64_t r0, int64_t r1, int elem) {

@@ -175,3 +175,4 @@ int pn_sm_count();
 int pn_host_threads();
 void pn_host_mirror_async(void* out, int64_t ld, int64_t n, int64_t r0, int64_t r1, int elem);
 void pn_host_mirror_wait();
+void pn_host_touch(void* p, size_t bytes);

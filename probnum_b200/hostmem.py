@@ -3,8 +3,10 @@
 ``CovarianceFunction.matrix`` must hand a NumPy array back to the caller
 (/root/reference/src/probnum/randprocs/covfuncs/_covariance_function.py:407-411).
 A Gram matrix of several GiB leaves the device at PCIe rate only if the destination
-is page-locked, so large result arrays are carved from ``cudaHostAlloc`` blocks
-owned by this module.  A block returns to a small free list when the array that
+is page-locked, so large result arrays are carved from page-locked blocks owned by this
+module (``pncov_host_alloc``: an anonymous mapping advised towards huge pages, populated by
+all host worker threads of the library and registered with the driver -- 0.3-0.6 s for
+8.6 GB where ``cudaHostAlloc`` takes 3.1-3.5 s).  A block returns to a small free list when the array that
 wraps it is garbage collected, which keeps repeated calls from paying the pinning
 cost again.  Small results use ordinary pageable memory.
 """
