@@ -171,7 +171,7 @@ PNCOV_API int pncov_matmulk_sym_finish_device(pncov_handle* h, const void* bins,
  * analogue of the reference's `_use_keops = False`
  * (tests/test_randprocs/test_covfuncs/test_linop_matrix.py:38-43). */
 #define PNCOV_OPT_IDENTITY 0   /* norm identity |x|^2 + |y|^2 - 2 x.y on DMMA (ExpQuad / RatQuad) */
-#define PNCOV_OPT_SYMMETRIC 1  /* symmetric halving (atomics: run-dependent summation order) */
+#define PNCOV_OPT_SYMMETRIC 1  /* symmetric halving (each off-diagonal tile evaluated once; reproducible) */
 #define PNCOV_OPT_FACTORISED 2 /* ExpQuad as exp(-|x|^2) exp(-|y|^2) exp(2 x.y) */
 PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value);
 

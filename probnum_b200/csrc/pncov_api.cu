@@ -907,8 +907,8 @@ int matmul_device_impl(pncov_handle* h, const void* v, int64_t k, int64_t ldv, v
         }
     }
     {
-        // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible.  Its
-        // atomics make the summation order run-dependent; PNCOV_MATVEC_SYM=off keeps the ordered kernel.
+        // symmetric halving: x1 is x0, one right-hand side, DMMA identity kernel admissible or direct differences.
+        // Reproducible (integer planes); PNCOV_MATVEC_SYM=off selects the kernel that evaluates all N^2 pairs.
         const bool kernel_ok = m.use_mma == 2 || (m.use_mma == 0 && h->k.d <= 96);  // DMMA identity or direct differences
         const bool sym_on = h->opt_symmetric >= 0 ? h->opt_symmetric != 0 : h->env_sym != 0;
         bool sym_ok = h->symmetric && kernel_ok && kc_max == 1 && es == 8 && R.n >= 2048 && sym_on;

@@ -416,13 +416,14 @@ __global__ void __launch_bounds__(MM_THREADS)
 // the CTA of row block I walks the column tiles J >= I, accumulates y_I += K_IJ v_J in registers
 // as above and ALSO y_J += K_IJ^T v_I: per 8-column step one more DFMA per pair, a shuffle
 // reduction over the eight lanes that hold the same columns, a per-warp slot in shared memory,
-// and once per tile 128 `red.global.add.f64` (one per column).  The exp2 / DMMA work per
-// ordered pair halves: 19.25 instead of 35 FP64-pipe slots per two ordered pairs.  Row sums leave
-// through the same atomics at the end of the CTA, so y must be zero on entry (the launcher
-// memsets it) and the summation order of a component is not fixed: results agree to rounding
-// between runs, not bit-for-bit (PNCOV_MATVEC_SYM=off selects the order-preserving kernel).
-// Row blocks are dealt round-robin to `nparts` callers (multi-GPU: rank r takes blocks
-// I = r mod nparts and the partial vectors are summed by an all-reduce).
+// and once per tile one update of the integer planes per column (pn_bin_add, pncov_common.cuh: the
+// partial sum split exactly into two integers and added with 64-bit integer atomics).  The exp2 /
+// DMMA work per ordered pair halves: 19.25 instead of 35 FP64-pipe slots per two ordered pairs.  Row
+// sums leave through the same planes at the end of the CTA.  Integer addition is associative, so the
+// product is bit-for-bit reproducible although the CTAs retire in any order; the caller zeroes the
+// planes and converts them afterwards (pn_launch_unbin).  Row blocks are dealt round-robin to
+// `nparts` callers (multi-GPU: rank r takes blocks I = r mod nparts and the planes of all ranks are
+// summed by an all-reduce: the same bits for every number of ranks).
 template <int KSTEPS, int EPI>
 __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
     matvec_mma_sym_kernel(const __grid_constant__ PnMatvecLaunch a, int tiles_per_split, int part, int nparts) {
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(MM_THREADS, MmCfg<KSTEPS>::MINB)
             pn_bulk_g2s(dst, bg + (jt + 1) * Cfg::TJ * Cfg::LD, B_BYTES, &bars[buf ^ 1]);
             pn_bulk_g2s(dst + Cfg::TJ * Cfg::LD, vg + (jt + 1) * Cfg::TJ, V_BYTES, &bars[buf ^ 1]);
         }
-        // column sums of the previous tile: one atomic per column (the slot was completed before
+        // column sums of the previous tile: one integer-plane update per column (the slot was completed before
         // the barrier that ended the previous iteration)
         if (it > 0 && jt - 1 >= jdiag_end && tid < Cfg::TJ) {
             const double* cw = colw + (buf ^ 1) * (MM_THREADS / 32) * Cfg::TJ;
@@ -786,7 +787,7 @@ __global__ void __launch_bounds__(MM_THREADS, 3)
 // accumulates y_J += K_IJ^T v_I.  A thread holds K for its 2 rows x 2 columns: two DFMAs give
 // the partial column sums, one butterfly step folds the two columns onto the two half-warps and
 // four more shuffle rounds finish the warp sum (1.25 DADD per pair); warps meet in shared memory
-// and one atomic per column leaves the CTA per tile.  Matern-5/2, d = 8: 32 -> 17.75 FP64
+// and one integer-plane update per column leaves the CTA per tile.  Matern-5/2, d = 8: 32 -> 17.75 FP64
 // instructions per ordered pair.
 constexpr int MS_ROWS = MV_THREADS * MV_R;
 static_assert(MS_ROWS == 2 * MV_TJ, "a row block must span exactly two column tiles");
@@ -1129,7 +1130,7 @@ __global__ void __launch_bounds__(MR_THREADS)
 // column tiles) walks the column tiles J >= 2 I and adds y_J += K_IJ^T v_I for the tiles right of its
 // diagonal pair.  The eight partial column sums of a register tile are folded over the warp by a
 // butterfly (8 -> 4 -> 2 -> 1 values over lane bits 4, 3, 2, then two plain rounds: 9 shuffles +
-// 9 DADDs per 8 columns), warps meet in shared memory, one atomic per column and tile.
+// 9 DADDs per 8 columns), warps meet in shared memory, one integer-plane update per column and tile.
 template <bool ARD>
 __global__ void __launch_bounds__(MR_THREADS)
     matvec_rows_sym_kernel(const __grid_constant__ PnMatvecLaunch a, const double* __restrict__ x_soa, int64_t ld,
@@ -1674,7 +1675,7 @@ cudaError_t pn_plan_matvec(PnMatvecLaunch& a, int sm_count) {
         return cudaSuccess;
     }
     if (a.sym && (a.use_mma == 2 || (a.use_mma == 0 && !a.in_f32 && a.d <= MR_DMAX))) {
-        a.jsplit = 1;  // no partial buffers: the symmetric kernels accumulate with atomics
+        a.jsplit = 1;  // no partial buffers: the symmetric kernels accumulate in the integer planes
         return cudaSuccess;
     }
     if (a.use_mma == 2) return launch_mma_any(a, sm_count, true, nullptr);
