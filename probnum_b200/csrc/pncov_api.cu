@@ -462,6 +462,8 @@ struct pncov_handle {
     // covariance arithmetic in one launch (pncov_set_program): the dense Gram of this handle evaluates `prog`
     bool has_prog = false;
     PnFusedProgram prog{};
+    bool prog_simple = false;  // the program is `[o *] k [+ WhiteNoise]`: prog_epi on the specialised kernels
+    PnEpiParams prog_epi{};
     // kernel-selection switches of the environment, read ONCE when the handle is created
     int env_ident = -1;   // PNCOV_MATVEC_IDENT: -1 unset, 0 "off", 1 "dfma"
     int env_fact = -1;    // PNCOV_MATVEC_FACT: 0 "off"
@@ -606,6 +608,11 @@ cudaError_t launch_gram_any(const pncov_handle* h, bool transpose, int64_t row0,
                             cudaStream_t stream) {
     const Points& R = transpose ? h->p1 : h->p0;
     const Points& C = transpose ? h->p0 : h->p1;
+    if (h->has_prog && h->prog_simple) {
+        PnGramLaunch g = gram_launch(h, transpose, row0, rows, out, ld);
+        g.epi = h->prog_epi;
+        return pn_launch_gram(g, stream);
+    }
     if (h->has_prog) return pn_launch_gram_fused(gram_launch(h, transpose, row0, rows, out, ld), h->prog, stream);
     if (h->gm_dpad > 0) {  // ExpQuad / RatQuad with wide inputs: guarded norm identity on DMMA
         const int r = transpose ? 1 : 0, c = transpose ? 0 : 1;
@@ -1985,6 +1992,48 @@ PNCOV_API int pncov_set_program(pncov_handle* h, int n_leaves, const int* kinds,
     }
     h->prog = F;
     h->has_prog = true;
+    // `[o *] k [+ WhiteNoise]` (either order): one isotropic leaf, folded into the compile-time specialised kernels
+    h->prog_simple = false;
+    {
+        const PnFusedSlot* leaf = nullptr;
+        const PnFusedSlot* wn = nullptr;
+        double scale = 1.0;
+        bool scaled = false, ok = F.n_slots >= 1 && F.n_slots <= 2;
+        for (int l = 0; ok && l < F.n_slots; ++l) {
+            const PnFusedSlot& S = F.slots[l];
+            if (S.mul) ok = false;
+            if (S.whitenoise) {
+                if (wn) ok = false;
+                wn = &S;
+            } else {
+                if (leaf) ok = false;
+                leaf = &S;
+            }
+            // first slot: SET [, SCALEACC o]; second slot: LIN(1, o) (o = 1 for the WhiteNoise term itself)
+            if (l == 0) {
+                if (S.n_post < 1 || S.n_post > 2 || S.post[0].op != PN_F_SET) ok = false;
+                if (ok && S.n_post == 2) {
+                    if (S.post[1].op != PN_F_SCALEACC || S.whitenoise) ok = false;
+                    scale = S.post[1].a;
+                    scaled = true;
+                }
+            } else {
+                if (S.n_post != 1 || S.post[0].op != PN_F_LIN || S.post[0].a != 1.0) ok = false;
+                if (ok && S.whitenoise && S.post[0].b != 1.0) ok = false;
+                if (ok && !S.whitenoise && S.post[0].b != 1.0) {
+                    scale = S.post[0].b;  // acc = fma(o, k, sigma^2 [x0 == x1]): same bits as o * k (+ sigma^2 on equal points)
+                    scaled = true;
+                }
+            }
+        }
+        if (ok && leaf && h->k.d <= 8) {
+            h->prog_simple = true;
+            h->prog_epi = leaf->epi;
+            h->prog_epi.post_flags = (scaled ? 1 : 0) | (wn ? 2 : 0);
+            h->prog_epi.post_scale = scale;
+            h->prog_epi.post_sigma_sq = wn ? wn->sigma_sq : 0.0;
+        }
+    }
     return 0;
 }
 

@@ -47,6 +47,11 @@ struct PnEpiParams {
     double g1, g2, g3, g4, g5;
     // validity window of the fast epilogue in terms of the hi word of S (see PnFlags)
     unsigned s_lo_word, s_hi_word;
+    // dense Gram only: the common covariance arithmetic `[o *] k [+ WhiteNoise]` folded into the compile-time
+    // specialised kernels (pncov_set_program recognises it): K = K * post_scale (bit 0), then K += post_sigma_sq where
+    // the two points are equal in every coordinate (bit 1) -- the operations, in the order, of the operand path
+    int post_flags, post_pad_;
+    double post_scale, post_sigma_sq;
 };
 
 // ---------------------------------------------------------------------------------------

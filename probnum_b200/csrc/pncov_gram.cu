@@ -142,6 +142,21 @@ __device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N],
     }
 }
 
+// `[o *] k [+ WhiteNoise]` after the kernel function (PnEpiParams::post_*); `eq`: bit i set where entry i's points
+// are equal in every coordinate
+template <int N>
+__device__ __forceinline__ void post_tile(double (&K)[N], const PnEpiParams& P, unsigned eq) {
+    if (P.post_flags & 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) K[i] *= P.post_scale;
+    }
+    if (eq) {  // rare: the diagonal, duplicated points
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if ((eq >> i) & 1u) K[i] += P.post_sigma_sq;
+    }
+}
+
 template <typename TOut>
 __device__ __forceinline__ void store_pair(TOut* row, int64_t j0, int64_t n1, TOut a, TOut b,
                                            bool vec_ok) {
@@ -282,6 +297,27 @@ __global__ void __launch_bounds__(G_THREADS)
                 fused_tile(S, K, F, eq, tabE, tabL);
             } else {
                 epi_dispatch(S, K, g.epi, tabE, tabL);
+                if constexpr (std::is_same<TOut, double>::value && std::is_same<T, double>::value) {
+                    if (g.epi.post_flags) {  // uniform
+                        unsigned eq = 0;
+                        if (g.epi.post_flags & 2) {
+#pragma unroll
+                            for (int i = 0; i < 2 * G_R; ++i) eq |= (S[i] == 0.0 ? 1u : 0u) << i;
+                            if (eq) {
+                                for (int m = 0; m < d; ++m) {
+                                    const P2 xb = *reinterpret_cast<const P2*>(x1t + (size_t)m * G_TN);
+#pragma unroll
+                                    for (int r = 0; r < G_R; ++r) {
+                                        const T xa = x0t[m * G_TM + rg + r];
+                                        if (!(xa == xb.x)) eq &= ~(1u << (2 * r));
+                                        if (!(xa == xb.y)) eq &= ~(1u << (2 * r + 1));
+                                    }
+                                }
+                            }
+                        }
+                        post_tile(K, g.epi, eq);
+                    }
+                }
             }
             const int rows_left = rows_here - rg;  // >= 1
 #pragma unroll
@@ -389,6 +425,7 @@ __global__ void __launch_bounds__(G_THREADS)
             }
             double K[2 * G_R];
             epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+            if (g.epi.post_flags & 1) post_tile(K, g.epi, 0u);  // uniform; a WhiteNoise term keeps launches off this kernel
 #pragma unroll
             for (int r = 0; r < G_R; ++r) {
                 pn_store_cs2(optr, K[2 * r], K[2 * r + 1]);
@@ -579,6 +616,25 @@ __global__ void __launch_bounds__(Y_WARPS * 32, 4)
                 fused_tile(S, K, F, eq, tabE, tabL);
             } else {
                 epi_tile<EPI>(S, K, g.epi, tabE, tabL);
+                if (g.epi.post_flags) {  // uniform
+                    unsigned eq = 0;
+                    if (g.epi.post_flags & 2) {
+#pragma unroll
+                        for (int i = 0; i < 2 * G_R; ++i) eq |= (S[i] == 0.0 ? 1u : 0u) << i;
+                        if (eq) {
+#pragma unroll
+                            for (int m = 0; m < D; ++m) {
+#pragma unroll
+                                for (int r = 0; r < G_R; ++r) {
+                                    const double xa = x0t[m * Y_T + G_R * h + r];
+                                    if (!(xa == xb0[m])) eq &= ~(1u << (2 * r));
+                                    if (!(xa == xb1[m])) eq &= ~(1u << (2 * r + 1));
+                                }
+                            }
+                        }
+                    }
+                    post_tile(K, g.epi, eq);
+                }
             }
             const int r0 = Y_RPW * warp + G_R * h;  // first row of this register tile within the tile
             double* optr = out + ((size_t)t * Y_T + r0) * row_stride + c0 + 2 * lane;
@@ -737,7 +793,12 @@ cudaError_t launch_sym_inst(const PnGramLaunch& g, cudaStream_t stream, const PR
 template <int D, bool ARD>
 cudaError_t launch_fast_epi(const PnGramLaunch& g, cudaStream_t stream) {
     switch (g.epi.epi) {
-        case PN_EPI_EXPQUAD: return launch_fast_inst<D, ARD, PN_EPI_EXPQUAD>(g, stream);
+        case PN_EPI_EXPQUAD:
+            // symmetric launches of the HBM-bound kernels exist for `+ WhiteNoise` only (isotropic leaves)
+            if constexpr (!ARD) {
+                if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_EXPQUAD>(g, stream);
+            }
+            return launch_fast_inst<D, ARD, PN_EPI_EXPQUAD>(g, stream);
         case PN_EPI_MATERN0:
             if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
             return launch_fast_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
@@ -750,8 +811,12 @@ cudaError_t launch_fast_epi(const PnGramLaunch& g, cudaStream_t stream) {
         case PN_EPI_MATERNP:
             if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
             return launch_fast_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
-        case PN_EPI_RATQUAD1: return launch_fast_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
-        case PN_EPI_RATQUAD2: return launch_fast_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
+        case PN_EPI_RATQUAD1:
+            if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
+            return launch_fast_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
+        case PN_EPI_RATQUAD2:
+            if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
+            return launch_fast_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
         default:
             if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUADG>(g, stream);
             return launch_fast_inst<D, false, PN_EPI_RATQUADG>(g, stream);
@@ -837,11 +902,12 @@ cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
     const bool aligned = (g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
     int64_t n0i = (g.n0 / G_TM) * G_TM, n1i = (g.n1 / G_TN) * G_TN;  // interior extent
     // mirror stores pay only where the FP64 pipe, not HBM, limits the general kernel
-    const bool fp64_heavy = g.epi.epi != PN_EPI_EXPQUAD && g.epi.epi != PN_EPI_RATQUAD1 && g.epi.epi != PN_EPI_RATQUAD2;
+    const bool post_wn = (g.epi.post_flags & 2) != 0;  // `+ WhiteNoise`: needs the kernels that can compare points
+    const bool fp64_heavy = post_wn || (g.epi.epi != PN_EPI_EXPQUAD && g.epi.epi != PN_EPI_RATQUAD1 && g.epi.epi != PN_EPI_RATQUAD2);
     const bool sym = g.symmetric && fp64_heavy && g.n0 == g.n1 && g.x0_soa == g.x1_soa && !g.in_f32 && g.d <= 8 &&
-                     aligned && g.n0 >= 4 * Y_T;
+                     aligned && g.n0 >= 4 * Y_T && !(post_wn && g.scale != nullptr);
     if (sym) n0i = n1i = (g.n0 / Y_T) * Y_T;  // the symmetric kernel works on the 64 grid
-    if (g.in_f32 || g.d > 8 || !aligned || n0i == 0 || n1i == 0) return launch_generic(g, stream);
+    if (g.in_f32 || g.d > 8 || !aligned || n0i == 0 || n1i == 0 || (post_wn && !sym)) return launch_generic(g, stream);
     // interior: whole 64-row tiles x whole 512-column strips, unpredicated specialised kernel
     PnGramLaunch in = g;
     in.n0 = n0i;

@@ -36,6 +36,12 @@ def specs(d):
                                    dict(kind="scaled", scalar=0.2, child=dict(kind="product", children=[m52, eq]))]),
         dict(kind="product", children=[dict(kind="sum", children=[m72, wn]), dict(kind="scaled", scalar=3.0, child=rq)]),
         dict(kind="sum", children=[wn, m32]),
+        # `[o *] k [+ WhiteNoise]`: folded into the compile-time specialised kernels (PnEpiParams::post_*)
+        dict(kind="sum", children=[dict(kind="scaled", scalar=2.0, child=m52), wn]),
+        dict(kind="sum", children=[wn, dict(kind="scaled", scalar=0.5, child=eq)]),
+        dict(kind="sum", children=[rq1, wn]),
+        dict(kind="scaled", scalar=3.0, child=rq),
+        dict(kind="scaled", scalar=-1.5, child=eq),
     ]
 
 

@@ -34,6 +34,8 @@ def timed(fn, reps=10):
 
 
 exprs = {
+    "2*Matern52 + WhiteNoise": 2.0 * pb.Matern((d,), nu=2.5) + pb.WhiteNoise((d,), sigma_sq=0.5),
+    "WhiteNoise + 0.5*ExpQuad": pb.WhiteNoise((d,), sigma_sq=0.5) + 0.5 * pb.ExpQuad((d,)),
     "2*Matern52 + 0.1*ExpQuad + WhiteNoise": 2.0 * pb.Matern((d,), nu=2.5) + 0.1 * pb.ExpQuad((d,)) + pb.WhiteNoise((d,), sigma_sq=0.5),
     "Matern32 * ExpQuad": pb.Matern((d,), nu=1.5) * pb.ExpQuad((d,)),
     "ExpQuad + RatQuad": pb.ExpQuad((d,)) + pb.RatQuad((d,)),
