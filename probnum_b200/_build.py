@@ -15,8 +15,8 @@ from concurrent.futures import ThreadPoolExecutor
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(CSRC, "libpncov.so")
-SOURCES = ["pncov_api.cu", "pncov_gram.cu", "pncov_gram_mma.cu", "pncov_matvec.cu", "pncov_extra.cu", "pncov_chol.cu", "pncov_host.cu"]
-HEADERS = ["pncov_common.cuh", "pncov_math.cuh", "pncov_tables.h", "pncov_internal.h",
+SOURCES = ["pncov_api.cu", "pncov_gram.cu", "pncov_gram_sym_lo.cu", "pncov_gram_sym_hi.cu", "pncov_gram_mma.cu", "pncov_matvec.cu", "pncov_extra.cu", "pncov_chol.cu", "pncov_host.cu"]
+HEADERS = ["pncov_common.cuh", "pncov_math.cuh", "pncov_tables.h", "pncov_internal.h", "pncov_gram_tile.cuh", "pncov_gram_sym.inc",
            os.path.join(ROOT, "include", "pncov.h")]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

@@ -18,159 +18,9 @@
 //     two-stage TMA + mbarrier pipeline, and are read back as warp-wide broadcasts;
 //   * distances are direct differences ((x0 - x1) * s)^2 like the reference, so there
 //     is no cancellation problem for near-duplicate or un-centred points.
-#include <type_traits>
-
-#include "pncov_internal.h"
+#include "pncov_gram_tile.cuh"
 
 namespace {
-
-constexpr int G_THREADS = 256;
-constexpr int G_TN = 2 * G_THREADS;  // columns per strip
-constexpr int G_TM = 64;             // rows per pipelined x0 tile
-constexpr int G_R = 4;               // rows per register tile
-constexpr int G_DMAX = 16;           // strip kernel: all coordinates of a strip live in smem
-constexpr int G_CHUNK_ROWS = 8;      // chunk kernel (d > G_DMAX): rows per CTA tile
-constexpr int G_HDR_BYTES = 128 + 8 * (PN_EXP2_N + 2 * PN_LOG2_N);  // barriers + tables
-
-template <typename T>
-struct Pair;
-template <>
-struct Pair<double> {
-    using type = double2;
-};
-template <>
-struct Pair<float> {
-    using type = float2;
-};
-
-// ---- epilogue over a register tile ------------------------------------------------------
-template <int EPI, int N, typename T, typename TOut>
-__device__ __forceinline__ void epi_tile(const T (&S)[N], TOut (&K)[N], const PnEpiParams& P,
-                                         const double* tabE, const double* tabL) {
-    if constexpr (std::is_same<TOut, float>::value) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) K[i] = exp2f(S[i] * (float)P.c_u);  // float32 ExpQuad stays in float
-    } else {
-        PnFlags f;
-        f.reset();
-#pragma unroll
-        for (int i = 0; i < N; ++i) K[i] = PnEpilogue<EPI>::fast((double)S[i], P, tabE, tabL, f);
-        if (f.flagged(P)) {  // rare: diagonal tiles (sqrt of 0), subnormal results
-            // only the entries outside the window are redone: which path an entry takes depends on its own S alone,
-            // so K_ij and K_ji (equal S) get equal bits wherever they are evaluated
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const unsigned w = (unsigned)pn_hi((double)S[i]);
-                if (w < P.s_lo_word || w >= P.s_hi_word) K[i] = pn_epilogue((double)S[i], P, tabE, tabL);
-            }
-        }
-    }
-}
-
-template <int N, typename T, typename TOut>
-__device__ __forceinline__ void epi_dispatch(const T (&S)[N], TOut (&K)[N], const PnEpiParams& P,
-                                             const double* tabE, const double* tabL) {
-    switch (P.epi) {  // uniform across the grid
-        case PN_EPI_EXPQUAD: epi_tile<PN_EPI_EXPQUAD>(S, K, P, tabE, tabL); break;
-        case PN_EPI_MATERN0: epi_tile<PN_EPI_MATERN0>(S, K, P, tabE, tabL); break;
-        case PN_EPI_MATERN1: epi_tile<PN_EPI_MATERN1>(S, K, P, tabE, tabL); break;
-        case PN_EPI_MATERN2: epi_tile<PN_EPI_MATERN2>(S, K, P, tabE, tabL); break;
-        case PN_EPI_MATERNP: epi_tile<PN_EPI_MATERNP>(S, K, P, tabE, tabL); break;
-        case PN_EPI_RATQUAD1: epi_tile<PN_EPI_RATQUAD1>(S, K, P, tabE, tabL); break;
-        case PN_EPI_RATQUAD2: epi_tile<PN_EPI_RATQUAD2>(S, K, P, tabE, tabL); break;
-        default: epi_tile<PN_EPI_RATQUADG>(S, K, P, tabE, tabL); break;
-    }
-}
-
-// covariance arithmetic: the program of PnFusedProgram over one register tile (see pncov_common.cuh).
-// `eq` has bit i set where the two points of entry i are equal in every coordinate (WhiteNoise leaves).
-template <int N>
-__device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N], const PnFusedProgram& F, unsigned eq,
-                                           const double* tabE, const double* tabL) {
-    double val[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        K[i] = 0.0;
-        val[i] = 1.0;
-    }
-    // slots are unrolled at compile time: every epilogue constant is an immediate constant-bank operand.  Measured
-    // alternatives (profiles/README.md, round 2): a dynamic step loop, three merged code bodies instead of the eight
-    // compile-time epilogues, half tiles, and leaves behind a call were all slower (3.9 - 5.3 ms against 3.9 ms for
-    // the three-leaf sum at N = 32768); what limits this kernel is the register traffic at the control-flow merges
-    // of whole tiles (a third of the executed instructions are moves), not the FP64 pipe.
-#pragma unroll
-    for (int l = 0; l < PN_FUSED_MAX_LEAVES; ++l) {
-        if (l < F.n_slots) {  // uniform across the grid
-            const PnFusedSlot& L = F.slots[l];
-            double t[N];
-            if (L.whitenoise) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) t[i] = ((eq >> i) & 1u) ? L.sigma_sq : 0.0;
-            } else {
-                epi_dispatch(S, t, L.epi, tabE, tabL);
-            }
-            if (L.mul) {
-#pragma unroll
-                for (int i = 0; i < N; ++i) val[i] *= t[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < N; ++i) val[i] = t[i];
-            }
-#pragma unroll
-            for (int j = 0; j < PN_FUSED_MAX_POST; ++j) {
-                if (j < L.n_post) {
-                    const PnFusedStep& st = L.post[j];
-                    if (st.op == PN_F_SCALEVAL) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) val[i] *= st.a;
-                    } else if (st.op == PN_F_SET) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] = val[i];
-                    } else if (st.op == PN_F_LIN) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] = pn_fma(st.b, val[i], st.a * K[i]);
-                    } else if (st.op == PN_F_MUL) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] *= val[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] *= st.a;
-                    }
-                }
-            }
-        }
-    }
-}
-
-// `[o *] k [+ WhiteNoise]` after the kernel function (PnEpiParams::post_*); `eq`: bit i set where entry i's points
-// are equal in every coordinate
-template <int N>
-__device__ __forceinline__ void post_tile(double (&K)[N], const PnEpiParams& P, unsigned eq) {
-    if (P.post_flags & 1) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) K[i] *= P.post_scale;
-    }
-    if (eq) {  // rare: the diagonal, duplicated points
-#pragma unroll
-        for (int i = 0; i < N; ++i)
-            if ((eq >> i) & 1u) K[i] += P.post_sigma_sq;
-    }
-}
-
-template <typename TOut>
-__device__ __forceinline__ void store_pair(TOut* row, int64_t j0, int64_t n1, TOut a, TOut b,
-                                           bool vec_ok) {
-    if (j0 + 1 < n1) {
-        if (vec_ok) {
-            pn_store_cs2(row + j0, a, b);
-        } else {
-            pn_store_cs1(row + j0, a);
-            pn_store_cs1(row + j0 + 1, b);
-        }
-    } else if (j0 < n1) {
-        pn_store_cs1(row + j0, a);
-    }
-}
 
 // ---- strip kernel (d <= G_DMAX) ----------------------------------------------------------
 template <typename T, typename TOut, bool ARD, typename PROG>
@@ -436,233 +286,6 @@ __global__ void __launch_bounds__(G_THREADS)
     }
 }
 
-// ---- symmetric kernel: x1 is x0, square interior on the 64 grid ---------------------------------
-// Only tiles on or above the diagonal are computed; every tile strictly above it is also stored
-// transposed.  K[i][j] and K[j][i] come from the very same instruction sequence (the differences
-// only change sign), so the result is bit-identical to the general kernel.  FP64 work per stored
-// entry halves, which moves Matern / general RatQuad from FP64-pipe-bound to HBM-bound.
-//
-// The DRAM side wants LONG contiguous runs in both directions (measured in round 1: scattered
-// 128-byte lines of a mirrored half cost 20 % of the launch, 512-byte runs cost nothing), so the
-// CTA tile is 64 x 64 and a warp owns whole rows of it (two adjacent columns per lane):
-//   * direct rows leave from registers, one 512-byte STG.128 per row and warp;
-//   * the transposed tile is written to shared memory (rows padded to 528 bytes) and leaves through
-//     the TMA engine: lane 0 of every warp issues one 512-byte bulk copy per mirrored row
-//     (cp.async.bulk.global.shared::cta, SASS UBLKCP) after ONE CTA barrier per tile.  No mirrored value
-//     passes through a register again and no warp waits on LSU back-pressure for that half.
-// A CTA is 4 warps with ONE staging buffer (53 KB with the exp2 table), four CTAs per SM: while one
-// CTA drains its tile the other three compute.  Measured on B200, N = 32768, d = 3, Matern-5/2
-// (profiles/README.md, round 2; the first kernel staged through XOR-swizzled shared memory and
-// re-read the tile to store it with STG): 1.48 ms -> 1.32 ms = 0.99 of the copy peak.  Larger CTAs
-// with two or three staging buffers at 1-2 CTAs per SM, direct rows through the TMA engine as well,
-// an L2 evict-first hint and a supertile rasterisation of the grid were all slower (1.36 - 2.3 ms).
-constexpr int Y_T = 64;          // tile edge
-constexpr int Y_TLD = Y_T + 2;   // doubles per staged transposed row (528 bytes: bulk-copy sources are 16-byte aligned)
-constexpr int Y_WARPS = 4;
-constexpr int Y_RPW = Y_T / Y_WARPS;  // rows of the tile per warp
-constexpr int Y_TPC = 8;              // row tiles per CTA (4 .. 32 measured within 2 %)
-
-__device__ __forceinline__ void pn_bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
-                 "r"(pn_smem_u32(src_smem)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void pn_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void pn_bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void pn_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int EPI>
-struct SymHdr {  // barriers + exp2 table (+ log2 table for the general RatQuad epilogue and for programs)
-    static constexpr int BYTES = 128 + 8 * PN_EXP2_N + (EPI == PN_EPI_RATQUADG || EPI == PN_EPI_FUSED ? 16 * PN_LOG2_N : 0);
-};
-
-template <int D, bool ARD, int EPI, typename PROG>
-__global__ void __launch_bounds__(Y_WARPS * 32, 4)
-    gram_sym_kernel(const __grid_constant__ PnGramLaunch g, int tiles_per_cta, const __grid_constant__ PROG F) {
-    constexpr bool FUSED = EPI == PN_EPI_FUSED;
-    constexpr bool PM = EPI >= PN_EPI_PM0 && EPI <= PN_EPI_PM3;  // ProductMatern of uniform degree PMP
-    constexpr int PMP = PM ? EPI - PN_EPI_PM0 : 0;
-    static_assert(FUSED == std::is_same<PROG, PnFusedProgram>::value && PM == std::is_same<PROG, PnPmProgram>::value,
-                  "PN_EPI_FUSED comes with a PnFusedProgram, PN_EPI_PMx with a PnPmProgram");
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0],[1]: x0 stages, [2]: tables
-    double* tabE = reinterpret_cast<double*>(smem + 128);
-    double* tabL = tabE + PN_EXP2_N;
-    double* x0s = reinterpret_cast<double*>(smem + SymHdr<EPI>::BYTES);  // [2][D][Y_T]
-    double* Ts = x0s + 2 * D * Y_T;                                         // [Y_T][Y_TLD] transposed tile
-
-    const int t_diag = (int)blockIdx.x;  // the strip's diagonal tile
-    const int t0 = blockIdx.y * tiles_per_cta;
-    const int t1 = min(t0 + tiles_per_cta, t_diag + 1);
-    if (t0 >= t1) return;
-    const int64_t c0 = (int64_t)blockIdx.x * Y_T;
-    const double* xg = static_cast<const double*>(g.x0_soa);
-    constexpr uint32_t TILE_BYTES = D * Y_T * 8;
-
-    if (tid == 0) {
-        pn_mbar_init(&bars[0], 1);
-        pn_mbar_init(&bars[1], 1);
-        pn_mbar_init(&bars[2], 1);
-        pn_mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
-        pn_mbar_expect_tx(&bars[0], TILE_BYTES);
-#pragma unroll
-        for (int m = 0; m < D; ++m)
-            pn_bulk_g2s(x0s + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)t0 * Y_T, Y_T * 8, &bars[0]);
-        pn_stage_tables_tma(tabE, tabL, &bars[2], EPI == PN_EPI_RATQUADG || FUSED);
-    }
-    double xb0[D], xb1[D], sc[D];
-#pragma unroll
-    for (int m = 0; m < D; ++m) {
-        const double2 t = *reinterpret_cast<const double2*>(xg + (size_t)m * g.ld0 + c0 + 2 * lane);
-        xb0[m] = t.x;
-        xb1[m] = t.y;
-        if constexpr (ARD) sc[m] = static_cast<const double*>(g.scale)[m];
-    }
-    const size_t row_stride = (size_t)g.ldo;
-    double* const out = static_cast<double*>(g.out);
-    pn_mbar_wait(&bars[2], 0);
-
-    int it = 0;
-    for (int t = t0; t < t1; ++t, ++it) {
-        const int buf = it & 1;
-        if (tid == 0 && t + 1 < t1) {
-            double* dst = x0s + (buf ^ 1) * (D * Y_T);
-            pn_mbar_expect_tx(&bars[buf ^ 1], TILE_BYTES);
-#pragma unroll
-            for (int m = 0; m < D; ++m)
-                pn_bulk_g2s(dst + m * Y_T, xg + (size_t)m * g.ld0 + (size_t)(t + 1) * Y_T, Y_T * 8, &bars[buf ^ 1]);
-        }
-        pn_mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
-        const double* x0t = x0s + buf * (D * Y_T) + Y_RPW * warp;
-        const bool mirror = t < t_diag;  // uniform per tile
-#pragma unroll
-        for (int h = 0; h < Y_RPW / G_R; ++h) {
-            double S[2 * G_R];
-#pragma unroll
-            for (int i = 0; i < 2 * G_R; ++i) S[i] = 0.0;
-            double K[2 * G_R];
-            if constexpr (PM) {
-                // prod_m poly_p(r_m) exp(-r_m), r_m = |x0_m - x1_m| s_m: S accumulates sum_m r_m, K the polynomials
-                // (the operations and their order are those of gram_extra_kernel<X_PRODMATERN>: same bits)
-#pragma unroll
-                for (int i = 0; i < 2 * G_R; ++i) K[i] = 1.0;
-#pragma unroll
-                for (int m = 0; m < D; ++m) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h);
-                    const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h + 2);
-                    const double xa[G_R] = {a01.x, a01.y, a23.x, a23.y};
-                    const double s = F.pm[m][0];
-#pragma unroll
-                    for (int r = 0; r < G_R; ++r) {
-                        const double ra = __dmul_rn(fabs(xa[r] - xb0[m]), s);
-                        const double rb = __dmul_rn(fabs(xa[r] - xb1[m]), s);
-                        S[2 * r] = __dadd_rn(S[2 * r], ra);
-                        S[2 * r + 1] = __dadd_rn(S[2 * r + 1], rb);
-                        if constexpr (PMP > 0) {
-                            double pa = F.pm[m][2 + PMP], pb = F.pm[m][2 + PMP];
-#pragma unroll
-                            for (int i = PMP - 1; i >= 0; --i) {
-                                pa = pn_fma(pa, ra, F.pm[m][2 + i]);
-                                pb = pn_fma(pb, rb, F.pm[m][2 + i]);
-                            }
-                            K[2 * r] *= pa;
-                            K[2 * r + 1] *= pb;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 2 * G_R; ++i) K[i] = K[i] * pn_exp2(S[i] * -1.4426950408889634074, tabE);
-            } else {
-#pragma unroll
-            for (int m = 0; m < D; ++m) {
-                const double2 a01 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h);
-                const double2 a23 = *reinterpret_cast<const double2*>(x0t + m * Y_T + G_R * h + 2);
-                const double xa[G_R] = {a01.x, a01.y, a23.x, a23.y};
-#pragma unroll
-                for (int r = 0; r < G_R; ++r) {
-                    double da = xa[r] - xb0[m];
-                    double db = xa[r] - xb1[m];
-                    if constexpr (ARD) {
-                        da *= sc[m];
-                        db *= sc[m];
-                    }
-                    S[2 * r] = pn_fma(da, da, S[2 * r]);
-                    S[2 * r + 1] = pn_fma(db, db, S[2 * r + 1]);
-                }
-            }
-            }
-            if constexpr (PM) {
-            } else if constexpr (FUSED) {
-                unsigned eq = 0;
-                if (F.has_wn) {  // S == 0 is necessary for equal points; squares may underflow, so confirm
-#pragma unroll
-                    for (int i = 0; i < 2 * G_R; ++i) eq |= (S[i] == 0.0 ? 1u : 0u) << i;
-                    if (eq) {
-#pragma unroll
-                        for (int m = 0; m < D; ++m) {
-#pragma unroll
-                            for (int r = 0; r < G_R; ++r) {
-                                const double xa = x0t[m * Y_T + G_R * h + r];
-                                if (!(xa == xb0[m])) eq &= ~(1u << (2 * r));
-                                if (!(xa == xb1[m])) eq &= ~(1u << (2 * r + 1));
-                            }
-                        }
-                    }
-                }
-                fused_tile(S, K, F, eq, tabE, tabL);
-            } else {
-                epi_tile<EPI>(S, K, g.epi, tabE, tabL);
-                if (g.epi.post_flags) {  // uniform
-                    unsigned eq = 0;
-                    if (g.epi.post_flags & 2) {
-#pragma unroll
-                        for (int i = 0; i < 2 * G_R; ++i) eq |= (S[i] == 0.0 ? 1u : 0u) << i;
-                        if (eq) {
-#pragma unroll
-                            for (int m = 0; m < D; ++m) {
-#pragma unroll
-                                for (int r = 0; r < G_R; ++r) {
-                                    const double xa = x0t[m * Y_T + G_R * h + r];
-                                    if (!(xa == xb0[m])) eq &= ~(1u << (2 * r));
-                                    if (!(xa == xb1[m])) eq &= ~(1u << (2 * r + 1));
-                                }
-                            }
-                        }
-                    }
-                    post_tile(K, g.epi, eq);
-                }
-            }
-            const int r0 = Y_RPW * warp + G_R * h;  // first row of this register tile within the tile
-            double* optr = out + ((size_t)t * Y_T + r0) * row_stride + c0 + 2 * lane;
-#pragma unroll
-            for (int r = 0; r < G_R; ++r) pn_store_cs2(optr + r * row_stride, K[2 * r], K[2 * r + 1]);
-            if (mirror) {  // transposed: row = this lane's column, 4 consecutive entries = this tile's rows
-                double* s0 = Ts + (2 * lane) * Y_TLD + r0;
-                *reinterpret_cast<double2*>(s0) = make_double2(K[0], K[2]);
-                *reinterpret_cast<double2*>(s0 + 2) = make_double2(K[4], K[6]);
-                *reinterpret_cast<double2*>(s0 + Y_TLD) = make_double2(K[1], K[3]);
-                *reinterpret_cast<double2*>(s0 + Y_TLD + 2) = make_double2(K[5], K[7]);
-            }
-        }
-        if (mirror) {  // uniform
-            pn_fence_proxy_async();  // generic-proxy writes above -> visible to the TMA engine
-            __syncthreads();
-            if (lane == 0) {
-                double* mptr = out + ((size_t)c0 + Y_RPW * warp) * row_stride + (size_t)t * Y_T;
-#pragma unroll
-                for (int r = 0; r < Y_RPW; ++r) pn_bulk_s2g(mptr + r * row_stride, Ts + (Y_RPW * warp + r) * Y_TLD, Y_T * 8);
-                pn_bulk_commit();
-                pn_bulk_wait_read_all();  // the staging buffer is rewritten by the next tile
-            }
-        }
-        // also orders this tile's reads of x0 stage `buf` before its refill two iterations on
-        __syncthreads();
-    }
-}
 
 // ---- chunk kernel (any d): coordinates streamed through shared memory in chunks ------------
 // d > G_DMAX.  The strip's column coordinates and the CTA's row coordinates arrive G_CD
@@ -775,50 +398,23 @@ cudaError_t launch_fast_inst(const PnGramLaunch& g, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-template <int D, bool ARD, int EPI, typename PROG = PnNoProgram>
-cudaError_t launch_sym_inst(const PnGramLaunch& g, cudaStream_t stream, const PROG& F = PROG()) {
-    const int64_t n_tiles = g.n0 / Y_T;
-    const int64_t gy = (n_tiles + Y_TPC - 1) / Y_TPC;
-    if (gy > 65535) return cudaErrorInvalidConfiguration;
-    const size_t smem = SymHdr<EPI>::BYTES + 2 * sizeof(double) * D * Y_T + sizeof(double) * Y_T * Y_TLD;
-    auto kern = gram_sym_kernel<D, ARD, EPI, PROG>;
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return err;
-    dim3 grid((unsigned)n_tiles, (unsigned)gy);
-    kern<<<grid, Y_WARPS * 32, smem, stream>>>(g, Y_TPC, F);
-    ++g_pn_launches;
-    return cudaGetLastError();
-}
-
 template <int D, bool ARD>
 cudaError_t launch_fast_epi(const PnGramLaunch& g, cudaStream_t stream) {
     switch (g.epi.epi) {
-        case PN_EPI_EXPQUAD:
-            // symmetric launches of the HBM-bound kernels exist for `+ WhiteNoise` only (isotropic leaves)
-            if constexpr (!ARD) {
-                if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_EXPQUAD>(g, stream);
-            }
-            return launch_fast_inst<D, ARD, PN_EPI_EXPQUAD>(g, stream);
+        case PN_EPI_EXPQUAD: return launch_fast_inst<D, ARD, PN_EPI_EXPQUAD>(g, stream);
         case PN_EPI_MATERN0:
-            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
             return launch_fast_inst<D, ARD, PN_EPI_MATERN0>(g, stream);
         case PN_EPI_MATERN1:
-            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN1>(g, stream);
             return launch_fast_inst<D, ARD, PN_EPI_MATERN1>(g, stream);
         case PN_EPI_MATERN2:
-            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERN2>(g, stream);
             return launch_fast_inst<D, ARD, PN_EPI_MATERN2>(g, stream);
         case PN_EPI_MATERNP:
-            if (g.symmetric) return launch_sym_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
             return launch_fast_inst<D, ARD, PN_EPI_MATERNP>(g, stream);
         case PN_EPI_RATQUAD1:
-            if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
             return launch_fast_inst<D, false, PN_EPI_RATQUAD1>(g, stream);
         case PN_EPI_RATQUAD2:
-            if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
             return launch_fast_inst<D, false, PN_EPI_RATQUAD2>(g, stream);
         default:
-            if (g.symmetric) return launch_sym_inst<D, false, PN_EPI_RATQUADG>(g, stream);
             return launch_fast_inst<D, false, PN_EPI_RATQUADG>(g, stream);
     }
 }
@@ -915,7 +511,8 @@ cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
     in.symmetric = sym ? 1 : 0;
     if (in.symmetric) in.n0 = n1i;  // square interior; the rest goes to the edge launches
     const int64_t n0_done = in.n0;
-    cudaError_t err = g.scale ? launch_fast<true>(in, stream) : launch_fast<false>(in, stream);
+    cudaError_t err = in.symmetric ? pn_gram_sym_launch(in, stream)  // pncov_gram_sym.cu
+                                   : (g.scale ? launch_fast<true>(in, stream) : launch_fast<false>(in, stream));
     if (err != cudaSuccess) return err;
     if (n1i < g.n1) {  // right edge: all rows, remaining columns
         PnGramLaunch e = g;
@@ -941,11 +538,6 @@ cudaError_t pn_launch_gram(const PnGramLaunch& g, cudaStream_t stream) {
 // A whole symmetric matrix (d <= 8, aligned) takes the mirrored-store kernel on its 64-grid interior -- the
 // leaves' FP64 work per stored entry halves, which is what keeps a three-leaf sum HBM-bound -- and the
 // general strip kernel on the edges; everything else is the strip kernel.
-template <int D>
-static cudaError_t launch_fused_sym(const PnGramLaunch& g, const PnFusedProgram& F, cudaStream_t stream) {
-    return launch_sym_inst<D, false, PN_EPI_FUSED, PnFusedProgram>(g, stream, F);
-}
-
 cudaError_t pn_launch_gram_fused(const PnGramLaunch& g, const PnFusedProgram& F, cudaStream_t stream) {
     if (g.n0 <= 0 || g.n1 <= 0) return cudaSuccess;
     if (g.in_f32 || g.scale != nullptr || g.d > G_DMAX || F.n_slots < 1 || F.n_slots > PN_FUSED_MAX_LEAVES) return cudaErrorInvalidValue;
@@ -956,17 +548,7 @@ cudaError_t pn_launch_gram_fused(const PnGramLaunch& g, const PnFusedProgram& F,
     PnGramLaunch in = g;
     in.n0 = in.n1 = ni;
     in.symmetric = 1;
-    cudaError_t err;
-    switch (g.d) {
-        case 1: err = launch_fused_sym<1>(in, F, stream); break;
-        case 2: err = launch_fused_sym<2>(in, F, stream); break;
-        case 3: err = launch_fused_sym<3>(in, F, stream); break;
-        case 4: err = launch_fused_sym<4>(in, F, stream); break;
-        case 5: err = launch_fused_sym<5>(in, F, stream); break;
-        case 6: err = launch_fused_sym<6>(in, F, stream); break;
-        case 7: err = launch_fused_sym<7>(in, F, stream); break;
-        default: err = launch_fused_sym<8>(in, F, stream); break;
-    }
+    cudaError_t err = pn_gram_sym_launch_fused(in, F, stream);  // pncov_gram_sym.cu
     if (err != cudaSuccess) return err;
     if (ni < g.n1) {  // right edge: all rows, remaining columns
         PnGramLaunch e = g;
@@ -990,20 +572,6 @@ cudaError_t pn_launch_gram_fused(const PnGramLaunch& g, const PnFusedProgram& F,
 // ProductMatern whose dimensions share the degree p <= 3: symmetric interior (64 grid) of a whole symmetric Gram
 // through the mirrored-store kernel.  Returns the interior extent in *done (0: not applicable, nothing launched);
 // the caller writes the edges with the general kernel (pn_launch_gram_extra).
-template <int D, int EPI>
-static cudaError_t launch_pm_sym(const PnGramLaunch& g, const PnPmProgram& F, cudaStream_t stream) {
-    return launch_sym_inst<D, false, EPI, PnPmProgram>(g, stream, F);
-}
-template <int D>
-static cudaError_t launch_pm_sym_d(const PnGramLaunch& g, const PnPmProgram& F, int p, cudaStream_t stream) {
-    switch (p) {
-        case 0: return launch_pm_sym<D, PN_EPI_PM0>(g, F, stream);
-        case 1: return launch_pm_sym<D, PN_EPI_PM1>(g, F, stream);
-        case 2: return launch_pm_sym<D, PN_EPI_PM2>(g, F, stream);
-        default: return launch_pm_sym<D, PN_EPI_PM3>(g, F, stream);
-    }
-}
-
 cudaError_t pn_launch_gram_pm_sym(const PnGramLaunch& g, const double* pm_host, cudaStream_t stream, int64_t* done) {
     *done = 0;
     const bool aligned = (g.ldo % 2) == 0 && (reinterpret_cast<uintptr_t>(g.out) % 16) == 0;
@@ -1019,17 +587,7 @@ cudaError_t pn_launch_gram_pm_sym(const PnGramLaunch& g, const double* pm_host, 
     PnGramLaunch in = g;
     in.n0 = in.n1 = ni;
     in.symmetric = 1;
-    cudaError_t err;
-    switch (g.d) {
-        case 1: err = launch_pm_sym_d<1>(in, F, p, stream); break;
-        case 2: err = launch_pm_sym_d<2>(in, F, p, stream); break;
-        case 3: err = launch_pm_sym_d<3>(in, F, p, stream); break;
-        case 4: err = launch_pm_sym_d<4>(in, F, p, stream); break;
-        case 5: err = launch_pm_sym_d<5>(in, F, p, stream); break;
-        case 6: err = launch_pm_sym_d<6>(in, F, p, stream); break;
-        case 7: err = launch_pm_sym_d<7>(in, F, p, stream); break;
-        default: err = launch_pm_sym_d<8>(in, F, p, stream); break;
-    }
+    cudaError_t err = pn_gram_sym_launch_pm(in, F, p, stream);  // pncov_gram_sym.cu
     if (err == cudaSuccess) *done = ni;
     return err;
 }
