@@ -187,7 +187,8 @@ PNCOV_API int pncov_set_option(pncov_handle* h, int option, int value);
  * an isotropic kernel (its own kernel is ignored from here on).
  *   leaves (n_leaves <= 6, and at most 6 leaf evaluations in the steps): kinds[l] with lengthscales[l], nus[l] (Matern), alphas[l] (RatQuad alpha;
  *     WhiteNoise sigma^2);
- *   steps (n_steps <= 12, at most 4 between two leaf evaluations) over two values per entry, `acc` and `val`:
+ *   steps (n_steps <= 12; between two leaf evaluations [SCALEVAL] [SET | LIN | MUL] [SCALEACC], each at most once and
+ *   in this order, else PNCOV_ENOTIMPL) over two values per entry, `acc` and `val`:
  *     PNCOV_F_LOAD     val = leaf[leaf_index](S)      PNCOV_F_MULLEAF  val = val * leaf[leaf_index](S)
  *     PNCOV_F_SCALEVAL val = val * a                  PNCOV_F_SET      acc = val
  *     PNCOV_F_LIN      acc = fma(b, val, a * acc)     PNCOV_F_MUL      acc = acc * val

@@ -21,7 +21,7 @@ EXPQUAD, MATERN, RATQUAD = 0, 1, 2
 LINEAR, POLYNOMIAL, WHITENOISE, PRODUCT_MATERN = 3, 4, 5, 6
 COMBINE_LINEAR, COMBINE_MULTIPLY = 0, 1
 F_LOAD, F_MULLEAF, F_SCALEVAL, F_SET, F_LIN, F_MUL, F_SCALEACC = range(7)  # pncov_set_program steps
-FUSED_MAX_LEAVES, FUSED_MAX_STEPS, FUSED_MAX_POST = 6, 12, 4
+FUSED_MAX_LEAVES, FUSED_MAX_STEPS = 6, 12
 CHAIN_MAX_CAPACITY = 12800  # pncov_chain_create: 2 * capacity coefficients fit the shared memory of one CTA
 OPT_IDENTITY, OPT_SYMMETRIC, OPT_FACTORISED = 0, 1, 2
 F64, F32 = 0, 1

@@ -772,12 +772,19 @@ def _compile_program(node):
     except _Unfusable:
         return None
     evaluations = sum(1 for st in steps if st[0] in (_lib.F_LOAD, _lib.F_MULLEAF))
-    run = longest = 0
-    for st in steps:  # steps between two leaf evaluations
-        run = 0 if st[0] in (_lib.F_LOAD, _lib.F_MULLEAF) else run + 1
-        longest = max(longest, run)
-    if evaluations > _lib.FUSED_MAX_LEAVES or len(steps) > _lib.FUSED_MAX_STEPS or longest > _lib.FUSED_MAX_POST:
+    if evaluations > _lib.FUSED_MAX_LEAVES or len(steps) > _lib.FUSED_MAX_STEPS:
         return None
+    # between two leaf evaluations the kernel's canonical slot takes [SCALEVAL] [SET | LIN | MUL] [SCALEACC], each at
+    # most once and in this order (e.g. a scalar times a scalar times a kernel does not fit)
+    stage = 0
+    for st in steps:
+        if st[0] in (_lib.F_LOAD, _lib.F_MULLEAF):
+            stage = 0
+            continue
+        this = 1 if st[0] == _lib.F_SCALEVAL else (3 if st[0] == _lib.F_SCALEACC else 2)
+        if this <= stage:
+            return None
+        stage = this
     # the handle only carries the points: any isotropic description with the right d will do
     params = _lib.KernelParams(_lib.EXPQUAD, max(node.input_size, 1), np.ones(1))
     return leaves, steps, params

@@ -1968,7 +1968,8 @@ PNCOV_API int pncov_set_program(pncov_handle* h, int n_leaves, const int* kinds,
         if (rc) return rc;
         L.epi = kd.epi;
     }
-    // regroup by leaf evaluation: a LOAD / MULLEAF opens a slot, the steps after it are its post-steps
+    // regroup by leaf evaluation: a LOAD / MULLEAF opens a slot, the steps after it -- [SCALEVAL] [SET | LIN | MUL]
+    // [SCALEACC], each at most once and in this order -- become its canonical parameters
     PnFusedProgram F{};
     for (int i = 0; i < n_steps; ++i) {
         if (ops[i] < PN_F_LOAD || ops[i] > PN_F_SCALEACC) return fail(PNCOV_EINVAL, "unknown program step");
@@ -1978,17 +1979,44 @@ PNCOV_API int pncov_set_program(pncov_handle* h, int n_leaves, const int* kinds,
             PnFusedSlot& S = F.slots[F.n_slots++];
             S = leaves[leaf_index[i]];
             S.mul = ops[i] == PN_F_MULLEAF ? 1 : 0;
+            if (S.mul && F.n_slots == 1) return fail(PNCOV_EINVAL, "a program starts with PNCOV_F_LOAD");
+            S.kind = 1;  // no update of acc until a step says otherwise: fma(0, val, 1 * acc)
+            S.a = 1.0;
+            S.b = 0.0;
+            S.s_val = 1.0;
+            S.s_acc = 1.0;
+            S.n_post = 0;
             if (S.whitenoise) F.has_wn = 1;
             if (!S.whitenoise && S.epi.epi == PN_EPI_RATQUADG) F.need_log = 1;
         } else {
             if (F.n_slots == 0) return fail(PNCOV_EINVAL, "a program starts with PNCOV_F_LOAD");
             PnFusedSlot& S = F.slots[F.n_slots - 1];
-            if (S.n_post == PN_FUSED_MAX_POST) return fail(PNCOV_ENOTIMPL, "at most 4 steps between two leaf evaluations");
+            // stage of the canonical form this step belongs to; stages must not go backwards or repeat
+            const int stage = ops[i] == PN_F_SCALEVAL ? 1 : (ops[i] == PN_F_SCALEACC ? 3 : 2);
+            int last = 0;
+            for (int j = 0; j < S.n_post; ++j) {
+                const int o = S.post[j].op;
+                last = o == PN_F_SCALEVAL ? 1 : (o == PN_F_SCALEACC ? 3 : 2);
+            }
+            if (stage <= last || S.n_post == 4)
+                return fail(PNCOV_ENOTIMPL, "between two leaf evaluations: [SCALEVAL] [SET | LIN | MUL] [SCALEACC], each at most once");
             PnFusedStep& st = S.post[S.n_post++];
             st.op = ops[i];
             st.a = a[i];
             st.b = b[i];
+            if (ops[i] == PN_F_SCALEVAL) S.s_val = a[i];
+            else if (ops[i] == PN_F_SCALEACC) S.s_acc = a[i];
+            else if (ops[i] == PN_F_SET) { S.kind = 1; S.a = 0.0; S.b = 1.0; }
+            else if (ops[i] == PN_F_LIN) { S.kind = 1; S.a = a[i]; S.b = b[i]; }
+            else S.kind = 2;
         }
+    }
+    // a WhiteNoise leaf that is simply added (LOAD, LIN(1, b)) after the first slot touches only entries of equal points
+    for (int l = 1; l < F.n_slots; ++l) {
+        PnFusedSlot& S = F.slots[l];
+        const bool next_is_product = l + 1 < F.n_slots && F.slots[l + 1].mul;
+        if (S.whitenoise && !S.mul && S.kind == 1 && S.a == 1.0 && S.s_val == 1.0 && S.s_acc == 1.0 && !next_is_product)
+            S.whitenoise = 2;
     }
     h->prog = F;
     h->has_prog = true;

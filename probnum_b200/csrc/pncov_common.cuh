@@ -77,17 +77,23 @@ struct PnFusedStep {
     int op, pad_;
     double a, b;
 };
-// The kernels see the program regrouped by leaf evaluation ("slot"): evaluate the leaf (LOAD or MULLEAF), then
-// the steps that follow it up to the next leaf.  Slots are unrolled at compile time, so every epilogue constant
-// is an immediate constant-bank operand exactly as in the single-kernel launches.
-#define PN_FUSED_MAX_POST 4
+// The kernels see the program regrouped by leaf evaluation ("slot") in a canonical form that runs without copies
+// and almost without branches: evaluate the leaf t, then
+//     val = (mul ? val : 1) * t * s_val          (LOAD / MULLEAF, then an optional SCALEVAL)
+//     acc = kind == MUL ? acc * val : fma(b, val, a * acc)    (SET is a = 0, b = 1; "no update" is a = 1, b = 0)
+//     acc = acc * s_acc                          (an optional SCALEACC)
+// Multiplications by 1.0 and additions of 0.0 are exact, so the bits are those of the step list.  Slots are
+// unrolled at compile time: every epilogue constant is an immediate constant-bank operand exactly as in the
+// single-kernel launches.
 struct PnFusedSlot {
     PnEpiParams epi;
     double sigma_sq;  // WhiteNoise: sigma^2 where x0_i == x1_j (all coordinates), else 0
     int whitenoise;
     int mul;          // 0: val = leaf(S) (LOAD), 1: val = val * leaf(S) (MULLEAF)
-    int n_post, pad_;
-    PnFusedStep post[PN_FUSED_MAX_POST];
+    int kind;         // 1: acc = fma(b, val, a * acc); 2: acc = acc * val
+    int n_post;       // host bookkeeping while the step list is regrouped
+    double s_val, a, b, s_acc;
+    PnFusedStep post[4];  // the slot's steps as given (recognition of `[o *] k [+ WhiteNoise]`)
 };
 struct PnFusedProgram {
     int n_slots;

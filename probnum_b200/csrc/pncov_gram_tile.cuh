@@ -79,15 +79,25 @@ __device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N],
         K[i] = 0.0;
         val[i] = 1.0;
     }
-    // slots are unrolled at compile time: every epilogue constant is an immediate constant-bank operand.  Measured
-    // alternatives (profiles/README.md, round 2): a dynamic step loop, three merged code bodies instead of the eight
-    // compile-time epilogues, half tiles, and leaves behind a call were all slower (3.9 - 5.3 ms against 3.9 ms for
-    // the three-leaf sum at N = 32768); what limits this kernel is the register traffic at the control-flow merges
-    // of whole tiles (a third of the executed instructions are moves), not the FP64 pipe.
+    // Canonical slots (PnFusedSlot), unrolled at compile time.  Only the leaf's kernel function is a run-time switch;
+    // LOAD vs MULLEAF is a select of the multiplicand and the optional scalings are multiplications by 1.0, because
+    // what limited the first forms of this kernel (profiles/README.md, round 2) was neither the FP64 pipe nor HBM
+    // but register copies (`val = t`, `acc = val`) and the merges after run-time branches over whole register tiles:
+    // a third of the executed instructions were moves.
 #pragma unroll
     for (int l = 0; l < PN_FUSED_MAX_LEAVES; ++l) {
         if (l < F.n_slots) {  // uniform across the grid
             const PnFusedSlot& L = F.slots[l];
+            if (L.whitenoise == 2) {
+                // a WhiteNoise summand, acc = fma(b, sigma^2 [x0 == x1], acc): acc + 0 is acc, so only entries whose
+                // points are equal change (the diagonal, duplicated points)
+                if (eq) {
+#pragma unroll
+                    for (int i = 0; i < N; ++i)
+                        if ((eq >> i) & 1u) K[i] = pn_fma(L.b, L.sigma_sq, K[i]);
+                }
+                continue;
+            }
             double t[N];
             if (L.whitenoise) {
 #pragma unroll
@@ -95,35 +105,18 @@ __device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N],
             } else {
                 epi_dispatch(S, t, L.epi, tabE, tabL);
             }
-            if (L.mul) {
+            const bool mul = L.mul != 0;
 #pragma unroll
-                for (int i = 0; i < N; ++i) val[i] *= t[i];
+            for (int i = 0; i < N; ++i) val[i] = ((mul ? val[i] : 1.0) * t[i]) * L.s_val;
+            if (L.kind == 2) {
+#pragma unroll
+                for (int i = 0; i < N; ++i) K[i] *= val[i];
             } else {
 #pragma unroll
-                for (int i = 0; i < N; ++i) val[i] = t[i];
+                for (int i = 0; i < N; ++i) K[i] = pn_fma(L.b, val[i], L.a * K[i]);
             }
 #pragma unroll
-            for (int j = 0; j < PN_FUSED_MAX_POST; ++j) {
-                if (j < L.n_post) {
-                    const PnFusedStep& st = L.post[j];
-                    if (st.op == PN_F_SCALEVAL) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) val[i] *= st.a;
-                    } else if (st.op == PN_F_SET) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] = val[i];
-                    } else if (st.op == PN_F_LIN) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] = pn_fma(st.b, val[i], st.a * K[i]);
-                    } else if (st.op == PN_F_MUL) {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] *= val[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < N; ++i) K[i] *= st.a;
-                    }
-                }
-            }
+            for (int i = 0; i < N; ++i) K[i] *= L.s_acc;
         }
     }
 }
