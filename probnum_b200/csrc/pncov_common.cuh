@@ -30,6 +30,10 @@ enum PnEpi : int {
     PN_EPI_PM1 = 11,
     PN_EPI_PM2 = 12,
     PN_EPI_PM3 = 13,
+    // PN_EPI_FUSED compiled for programs of at most 2 / 3 leaf evaluations (the unrolled slots of the full form are
+    // 400 KB of code: instruction fetch, not arithmetic, then limits short programs)
+    PN_EPI_FUSED2 = 14,
+    PN_EPI_FUSED3 = 15,
 };
 
 struct PnEpiParams {

@@ -70,7 +70,7 @@ __device__ __forceinline__ void epi_dispatch(const T (&S)[N], TOut (&K)[N], cons
 
 // covariance arithmetic: the program of PnFusedProgram over one register tile (see pncov_common.cuh).
 // `eq` has bit i set where the two points of entry i are equal in every coordinate (WhiteNoise leaves).
-template <int N>
+template <int N, int NSLOTS = PN_FUSED_MAX_LEAVES>
 __device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N], const PnFusedProgram& F, unsigned eq,
                                            const double* tabE, const double* tabL) {
     double val[N];
@@ -85,7 +85,7 @@ __device__ __forceinline__ void fused_tile(const double (&S)[N], double (&K)[N],
     // but register copies (`val = t`, `acc = val`) and the merges after run-time branches over whole register tiles:
     // a third of the executed instructions were moves.
 #pragma unroll
-    for (int l = 0; l < PN_FUSED_MAX_LEAVES; ++l) {
+    for (int l = 0; l < NSLOTS; ++l) {
         if (l < F.n_slots) {  // uniform across the grid
             const PnFusedSlot& L = F.slots[l];
             if (L.whitenoise == 2) {
