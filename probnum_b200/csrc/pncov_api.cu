@@ -1849,11 +1849,11 @@ PNCOV_API int pncov_chain_destroy(pncov_chain* c) {
     if (!c) return 0;
     DeviceGuard guard(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->U);
-    cudaFree(c->V);
-    cudaFree(c->x);
-    cudaFree(c->y);
-    cudaFree(c->partial);
+    pn_dev_free(c->U, c->stream);
+    pn_dev_free(c->V, c->stream);
+    pn_dev_free(c->x, c->stream);
+    pn_dev_free(c->y, c->stream);
+    pn_dev_free(c->partial, c->stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -1879,11 +1879,11 @@ PNCOV_API int pncov_chain_create(pncov_chain** out, int device, int64_t n, int64
     DeviceGuard guard(device);
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     const size_t mat = (size_t)capacity * c->ld * 8;
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->U), mat);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->V), mat);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->x), (size_t)c->ld * 8);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->y), (size_t)c->ld * 8);
-    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&c->partial), (size_t)2 * capacity * kChainSplits * 8);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->U), mat, c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->V), mat, c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->x), (size_t)c->ld * 8, c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->y), (size_t)c->ld * 8, c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->partial), (size_t)2 * capacity * kChainSplits * 8, c->stream);
     if (e != cudaSuccess) {
         pncov_chain_destroy(c);
         return fail_cuda(e, "pncov_chain_create");

@@ -358,6 +358,7 @@ def test_solver_chains_plumbing_on_the_host(monkeypatch):
     originals = (mb.SymmetricMatrixBasedSolver._mean_update, mb.SymmetricMatrixBasedSolver._covariance_update)
     _HostChain.created = 0
     pb_patch.enable_solver_chains()
+    assert isinstance(mb.np, pb_patch._GrowingHstack)
     try:
         x1, A1, Ainv1, info1, it1 = _solver_run(A, b, 30)
         names = [type(s).__name__ for s in Ainv1.mean._summands]
@@ -367,6 +368,7 @@ def test_solver_chains_plumbing_on_the_host(monkeypatch):
     finally:
         pb_patch.disable()
     assert (mb.SymmetricMatrixBasedSolver._mean_update, mb.SymmetricMatrixBasedSolver._covariance_update) == originals
+    assert mb.np is np
     assert info1["iter"] == info0["iter"] > 3 and _HostChain.created == 4
     assert names.count("ChainOperator") == 1 and len(names) == 2
     for a, c in zip(it0, it1):
@@ -407,6 +409,38 @@ def test_solver_chains_on_the_device_match_the_reference_solver(patched):
     for a, c in zip(it0, it1):
         np.testing.assert_allclose(c, a, rtol=0, atol=1e-9 * scale)
     np.testing.assert_allclose(prod1, Ainv0.mean @ v, rtol=1e-9, atol=1e-9 * np.abs(v).max())
+
+
+def test_growing_hstack_returns_what_numpy_returns():
+    """The shim enable_solver_chains() puts in place of matrixbased's ``np`` (linalg/solvers/matrixbased.py:615-616,
+    :661, :927, :936 call np.hstack on lists that grow by one column per iteration): same values and layout as
+    np.hstack for a growing list, for a list that was rebuilt, for short columns and for non-list input."""
+    shim = pb_patch._GrowingHstack()
+    rng = np.random.default_rng(5)
+    n = 5000
+    cols = []
+    for k in range(1, 140):  # crosses the initial capacity of 64 columns and one regrowth
+        cols.append(rng.normal(size=(n, 1)))
+        got = shim.hstack(cols)
+        if k in (1, 2, 3, 64, 65, 128, 129, 139):
+            want = np.hstack(cols)
+            assert got.shape == want.shape and got.dtype == want.dtype
+            np.testing.assert_array_equal(got, want)
+            assert got.strides[1] == 8  # row-major like np.hstack's result: products with it round the same way
+    earlier = shim.hstack(cols[:])  # another list object holding the same columns
+    np.testing.assert_array_equal(earlier, np.hstack(cols))
+    cols[3] = rng.normal(size=(n, 1))  # a held column was replaced: the cached copy must not be served
+    np.testing.assert_array_equal(shim.hstack(cols), np.hstack(cols))
+    del cols[10:]  # the list shrank
+    np.testing.assert_array_equal(shim.hstack(cols), np.hstack(cols))
+    cols.append(rng.normal(size=(n, 2)))  # not a single column: NumPy's own path
+    np.testing.assert_array_equal(shim.hstack(cols), np.hstack(cols))
+    small = [rng.normal(size=(7, 1)) for _ in range(3)]
+    np.testing.assert_array_equal(shim.hstack(small), np.hstack(small))
+    np.testing.assert_array_equal(shim.hstack(tuple(small)), np.hstack(small))
+    with pytest.raises(ValueError):
+        shim.hstack([np.zeros((n, 1)), np.zeros((n + 1, 1))])
+    assert shim.vstack is np.vstack and shim.float64 is np.float64
 
 
 def test_evaluate_hook_is_restored():
