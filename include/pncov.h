@@ -247,8 +247,9 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
  *   pncov_chol_factor_gram  same, but the matrix is the Gram matrix of a (square, float64) operator
  *                           handle: it is evaluated straight into the factorisation buffer and never
  *                           visits the host ("keep gram device-resident")
- *   pncov_chol_solve        x = (L L^T)^-1 b for b, x: (n, nrhs) row-major HOST arrays (nrhs < 4: one
- *                           substitution sweep; from 4: transposed on the device, blocked DMMA substitution)
+ *   pncov_chol_solve        x = (L L^T)^-1 b for b, x: (n, nrhs) row-major HOST arrays (nrhs <= 12: chained
+ *                           substitution, one launch per direction for every three columns; from 13:
+ *                           transposed on the device, blocked DMMA substitution)
  *   pncov_chol_solve_gram    the prediction path of
  *                           BQStandardBeliefUpdate.predict_integrand
  *                           (quad/solvers/belief_updates/_standard_update.py:131-151) and

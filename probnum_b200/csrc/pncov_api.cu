@@ -1551,14 +1551,20 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
 }
 
 // ---- Cholesky factor of a Gram matrix + jitter I, resident on the device ---------------------------
+// n = 16384: a pass of the chained substitution (1-3 columns, two launches) takes 1.4-1.7 ms, the transposed DMMA
+// substitution 9.4 ms for anything up to 128 columns; 4.3 against 0.9 ms at n = 8192, 2.3 against 0.45 ms at n = 4096
+// (tools/bench_cholesky.py): four passes are still ahead of it
+constexpr int64_t kWideSolveMinRhs = 13;
+
 struct pncov_chol {
     int device = 0;
     int64_t n = 0, npad = 0;
     double* M = nullptr;      // (npad, npad) row-major; lower triangle = L after pncov_chol_factor
     double* panel = nullptr;  // (npad, 128) contiguous block column
     double* invd = nullptr;   // (npad / 128) inverse diagonal blocks, 128 x 128 each
-    double* rhs = nullptr;    // (npad, 8)
+    double* rhs = nullptr;    // (npad, kWideSolveMinRhs - 1)
     int* info = nullptr;
+    int* solve_sync = nullptr;  // 2 + 2 npad / 128: tickets and flags of the chained substitution
     cudaStream_t stream = nullptr, side = nullptr;  // side: look-ahead factorisation of the next diagonal block
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_panel = nullptr, ev_diag = nullptr;
     bool factored = false;
@@ -1595,8 +1601,9 @@ PNCOV_API int pncov_chol_create(pncov_chol** out, int device, int64_t n) {
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->M), (size_t)c->npad * c->npad * 8, c->stream);
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->panel), (size_t)c->npad * 128 * 8, c->stream);
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->invd), (size_t)c->npad * 128 * 8, c->stream);
-    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->rhs), (size_t)c->npad * 8 * 8, c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->rhs), (size_t)c->npad * (kWideSolveMinRhs - 1) * 8, c->stream);
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->info), sizeof(int), c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->solve_sync), sizeof(int) * (2 + 2 * (size_t)(c->npad / 128)), c->stream);
     if (e != cudaSuccess) {
         const bool oom = e == cudaErrorMemoryAllocation;
         int rc = oom ? fail(PNCOV_ENOMEM, "out of device memory") : fail_cuda(e, "pncov_chol_create");
@@ -1618,6 +1625,7 @@ PNCOV_API int pncov_chol_destroy(pncov_chol* c) {
     pn_dev_free(c->invd, c->stream);
     pn_dev_free(c->rhs, c->stream);
     pn_dev_free(c->info, c->stream);
+    pn_dev_free(c->solve_sync, c->stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1668,9 +1676,6 @@ PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitt
     return 0;
 }
 
-constexpr int64_t kWideSolveMinRhs = 4;  // n = 16384: sweeps take 6.7 / 7.9 / 17.6 ms for 1 / 2 / 8 columns, the
-                                         // transposed DMMA substitution ~10 ms for anything up to 128 (tools/solve_width_probe.py)
-
 PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int64_t ldb, double* x, int64_t ldx) {
     if (!c || !b || !x) return fail(PNCOV_EINVAL, "NULL argument");
     if (!c->factored) return fail(PNCOV_EINVAL, "no successful factorisation in this handle");
@@ -1716,23 +1721,24 @@ PNCOV_API int pncov_chol_solve(pncov_chol* c, const double* b, int64_t nrhs, int
         if (e != cudaSuccess) return fail_cuda(e, "pncov_chol_solve (wide)");
         return 0;
     }
-    for (int64_t c0 = 0; c0 < nrhs; c0 += 8) {
-        const int k = (int)std::min<int64_t>(8, nrhs - c0);
-        if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->rhs, 0, (size_t)c->npad * k * 8, c->stream));
-        // contiguous operands (the usual case) go as one linear copy: a pitched copy of 16-byte rows
-        // from pageable memory costs milliseconds
-        if (ldb == k)
-            PN_CUDA(cudaMemcpyAsync(c->rhs, b + c0, (size_t)c->n * k * 8, cudaMemcpyHostToDevice, c->stream));
-        else
-            PN_CUDA(cudaMemcpy2DAsync(c->rhs, (size_t)k * 8, b + c0, (size_t)ldb * 8, (size_t)k * 8, (size_t)c->n,
-                                      cudaMemcpyHostToDevice, c->stream));
-        PN_CUDA(pn_chol_solve(c->M, c->npad, c->invd, c->rhs, k, c->stream));
-        if (ldx == k)
-            PN_CUDA(cudaMemcpyAsync(x + c0, c->rhs, (size_t)c->n * k * 8, cudaMemcpyDeviceToHost, c->stream));
-        else
-            PN_CUDA(cudaMemcpy2DAsync(x + c0, (size_t)ldx * 8, c->rhs, (size_t)k * 8, (size_t)k * 8, (size_t)c->n,
-                                      cudaMemcpyDeviceToHost, c->stream));
-    }
+    // up to kWideSolveMinRhs - 1 columns: the whole block goes to the device once (one linear copy when contiguous:
+    // a pitched copy of 16-byte rows from pageable memory costs milliseconds); the chained substitution then runs
+    // over it in place, three adjacent columns per pass
+    if (nrhs == 0) return 0;
+    if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->rhs, 0, (size_t)c->npad * nrhs * 8, c->stream));
+    if (ldb == nrhs)
+        PN_CUDA(cudaMemcpyAsync(c->rhs, b, (size_t)c->n * nrhs * 8, cudaMemcpyHostToDevice, c->stream));
+    else
+        PN_CUDA(cudaMemcpy2DAsync(c->rhs, (size_t)nrhs * 8, b, (size_t)ldb * 8, (size_t)nrhs * 8, (size_t)c->n,
+                                  cudaMemcpyHostToDevice, c->stream));
+    for (int64_t c0 = 0; c0 < nrhs; c0 += 3)
+        PN_CUDA(pn_chol_solve(c->M, c->npad, c->invd, c->rhs + c0, nrhs, (int)std::min<int64_t>(3, nrhs - c0), c->solve_sync,
+                              c->stream));
+    if (ldx == nrhs)
+        PN_CUDA(cudaMemcpyAsync(x, c->rhs, (size_t)c->n * nrhs * 8, cudaMemcpyDeviceToHost, c->stream));
+    else
+        PN_CUDA(cudaMemcpy2DAsync(x, (size_t)ldx * 8, c->rhs, (size_t)nrhs * 8, (size_t)nrhs * 8, (size_t)c->n,
+                                  cudaMemcpyDeviceToHost, c->stream));
     PN_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }

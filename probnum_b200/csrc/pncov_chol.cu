@@ -330,174 +330,230 @@ __global__ void chol_prepare_diag_kernel(double* M, int64_t ld, int64_t n, int64
 }
 
 // ---- solves -------------------------------------------------------------------------------------------
-// Substitution runs over SUPER blocks of CS = 4 diagonal blocks (512 rows): one CTA resolves the
-// 512 x 512 triangle of a super block (diagonal blocks through their stored inverses, the six
-// off-diagonal blocks as 128 x 128 products), then one wide kernel applies the super block to
-// everything below (forward) or left of it (backward).  The dependency chain is 2 x n / 512
-// launches instead of 2 x n / 128.
-constexpr int CS = 4;
-constexpr int SV_THREADS = 256;
+// One to three right-hand sides: ONE launch per direction.  The substitution is a chain of T = n / 128
+// dependent block steps; as launches (one per step or per group of steps) the chain costs 50 us a link.  Here
+// every block row (forward) / block column (backward) has a CTA of its own, CTAs hand the solved blocks to each
+// other through flags in global memory, and the only thing left on the critical path of step i is
+//     see flag i-1  ->  load x_{i-1} (512 B..3 KB from L2)  ->  one 128 x 128 product  ->  the product with
+//     inv(L_ii)  ->  store x_i, release flag i.
+// CTA i streams its blocks L[i, 0..i-1] (forward) or L[T-1..i+1, i] (backward) through a three-stage cp.async
+// ring of half blocks (64 x 128 doubles) as fast as the flags allow: far behind the frontier that is a plain
+// streaming pass over the row, which all rows do at the same time.  Partial sums stay in registers over the whole
+// row; they are reduced once, before the product with the inverse diagonal block.
+// Block indices are handed out by an atomic ticket in start order, so a CTA only ever waits for CTAs that are
+// already running: no co-residency requirement, any T.
+constexpr int SC_THREADS = 256;
+constexpr int SC_UR = 64;               // rows of a pipeline unit (half a block)
+constexpr int SC_STAGES = 3;
+constexpr int SC_UNIT = SC_UR * CB;     // doubles per unit
 
-// out (op)= op(M) v for a 128 x 128 block M, v in shared memory as [nrhs][CB]; (row-major, ld); trans = 0: M v, 1: M^T v.
-// acc = 0: out = result, acc = 1: out -= result (out: global [CB][nrhs]).  All SV_THREADS threads call it.
-__device__ __forceinline__ void sv_block_apply(const double* __restrict__ M, int64_t ld, int trans,
-                                               const double* __restrict__ vs, double* __restrict__ out, int nrhs,
-                                               int acc, double* __restrict__ red) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (!trans) {  // a warp per row, lanes read 4 adjacent columns: coalesced 1 KB per row
-        constexpr int RPW = CB / (SV_THREADS / 32);  // rows per warp; all loads in flight before the math
-        double4 mr[RPW];
+struct ChChain {
+    const double* M;     // factor, row-major, lower triangle
+    int64_t ld;
+    const double* invd;  // T inverse diagonal blocks
+    double* b;           // NR adjacent columns of a row-major (T * 128, ldb) array: right-hand sides in, solutions out
+    int64_t ldb;
+    int* ticket;         // zero before the launch
+    int* flags;          // [T], zero before the launch; flags[j] = 1: block j of the solution is in b
+    int T;
+};
+
+__device__ __forceinline__ int sc_ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sc_st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// forward: sums over the 32 lanes of 16 values per lane in 16 shuffles (halving exchange); on return v[0] of
+// lane L is the total of value ((L >> 1) & 15) bit-reversed as: bit 4 of L -> 8, bit 3 -> 4, bit 2 -> 2, bit 1 -> 1
+__device__ __forceinline__ double sc_reduce16(double (&v)[16], int lane) {
 #pragma unroll
-        for (int i = 0; i < RPW; ++i)
-            mr[i] = *reinterpret_cast<const double4*>(M + (int64_t)(warp + i * (SV_THREADS / 32)) * ld + 4 * lane);
+    for (int k = 0; k < 8; ++k) {
+        const bool up = lane & 16;
+        const double send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
 #pragma unroll
-        for (int i = 0; i < RPW; ++i) {
-            const int row = warp + i * (SV_THREADS / 32);
-            const double4 m = mr[i];
-            for (int r = 0; r < nrhs; ++r) {
-                const double4 v4 = *reinterpret_cast<const double4*>(vs + r * CB + 4 * lane);  // vs is [rhs][CB]
-                double s = m.x * v4.x;
-                s = pn_fma(m.y, v4.y, s);
-                s = pn_fma(m.z, v4.z, s);
-                s = pn_fma(m.w, v4.w, s);
+    for (int k = 0; k < 4; ++k) {
+        const bool up = lane & 8;
+        const double send = up ? v[k] : v[k + 4], keep = up ? v[k + 4] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
 #pragma unroll
-                for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
-                if (lane == 0) out[row * nrhs + r] = acc ? out[row * nrhs + r] - s : s;
-            }
+    for (int k = 0; k < 2; ++k) {
+        const bool up = lane & 4;
+        const double send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool up = lane & 2;
+        const double send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// forward unit H of a block: acc[8 H + q][r] += sum_c S[warp + 8 q][c] v_r[c] over this lane's 4 columns
+template <int NR, int H>
+__device__ __forceinline__ void sc_apply_rows(const double* __restrict__ S, const double* __restrict__ v,
+                                              double (&acc)[NR][16], int warp, int lane) {
+    double4 v4[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v4[r] = *reinterpret_cast<const double4*>(v + r * CB + 4 * lane);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const double4 m = *reinterpret_cast<const double4*>(S + (warp + 8 * q) * CB + 4 * lane);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double a = acc[r][8 * H + q];
+            a = pn_fma(m.x, v4[r].x, a);
+            a = pn_fma(m.y, v4[r].y, a);
+            a = pn_fma(m.z, v4[r].z, a);
+            a = pn_fma(m.w, v4[r].w, a);
+            acc[r][8 * H + q] = a;
         }
-    } else {  // a thread per column, the two halves of the rows on the two thread halves; one pass over
-              // the block for all right-hand sides
-        const int col = tid & (CB - 1), half = tid >> 7;
-        double s[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) s[r] = 0.0;
-#pragma unroll 8
-        for (int l = half * (CB / 2); l < (half + 1) * (CB / 2); ++l) {
-            const double m = M[(int64_t)l * ld + col];
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < nrhs) s[r] = pn_fma(m, vs[r * CB + l], s[r]);
-        }
-        if (half) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < nrhs) red[r * CB + col] = s[r];
-        }
-        __syncthreads();
-        if (!half) {
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < nrhs) {
-                    const double t = s[r] + red[r * CB + col];
-                    out[col * nrhs + r] = acc ? out[col * nrhs + r] - t : t;
-                }
-        }
-        __syncthreads();
     }
 }
 
-// One CTA: the triangle of a super block.  fwd: for j = 0..nb-1: y_j = invL_j b_j; b_{j2} -= L[j2,j] y_j (j2 > j).
-// bwd: for j = nb-1..0: x_j = invL_j^T y_j; y_{j2} -= L[j,j2]^T x_j (j2 < j).  Ld: the (sb,sb) diagonal
-// super block of L (row-major, ld), invd: its nb inverse diagonal blocks, b: its rows of the rhs.
-__global__ void __launch_bounds__(SV_THREADS) chol_super_diag_kernel(const double* __restrict__ Ld, int64_t ld,
-                                                                      const double* __restrict__ invd,
-                                                                      double* __restrict__ b, int nrhs, int nb, int bwd) {
-    __shared__ double bs[CS * CB * 8];  // the super block's rows of the right-hand side live here throughout
-    __shared__ __align__(32) double vs[CB * 8];  // [rhs][CB]
-    __shared__ double red[CB * 8];
-    const int tid = threadIdx.x;
-    for (int idx = tid; idx < nb * CB * nrhs; idx += SV_THREADS) bs[idx] = b[idx];
-    for (int step = 0; step < nb; ++step) {
-        const int j = bwd ? nb - 1 - step : step;
-        double* bj = bs + j * CB * nrhs;
-        __syncthreads();
-        for (int idx = tid; idx < CB * nrhs; idx += SV_THREADS) vs[(idx % nrhs) * CB + idx / nrhs] = bj[idx];
-        __syncthreads();
-        sv_block_apply(invd + (int64_t)j * CB * CB, CB, bwd, vs, bj, nrhs, 0, red);
-        __syncthreads();
-        for (int idx = tid; idx < CB * nrhs; idx += SV_THREADS) vs[(idx % nrhs) * CB + idx / nrhs] = bj[idx];  // the solved block
-        __syncthreads();
-        if (!bwd) {
-            for (int j2 = j + 1; j2 < nb; ++j2)
-                sv_block_apply(Ld + ((int64_t)j2 * CB) * ld + j * CB, ld, 0, vs, bs + j2 * CB * nrhs, nrhs, 1, red);
+// backward unit h of a block: acc[r] += sum_l S[l][col] v_r[64 h + l] over this thread's 32 rows of the unit
+template <int NR>
+__device__ __forceinline__ void sc_apply_cols(const double* __restrict__ S, const double* __restrict__ v, int h,
+                                              double (&acc)[NR], int col, int half) {
+    const double* sp = S + (half * 32) * CB + col;
+    const double* vp = v + 64 * h + half * 32;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+        const double m = sp[l * CB];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r] = pn_fma(m, vp[r * CB + l], acc[r]);
+    }
+}
+
+template <int NR, bool BWD>
+__global__ void __launch_bounds__(SC_THREADS, 1) chol_chain_solve_kernel(const __grid_constant__ ChChain p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* stage = reinterpret_cast<double*>(smem);  // [SC_STAGES][SC_UR][CB]
+    double* vs = stage + SC_STAGES * SC_UNIT;         // [2][NR][CB]: the operand of the current / next block
+    double* bs = vs + 2 * NR * CB;                    // [CB][NR]: this CTA's block of the right-hand side
+    double* red = bs + CB * NR;                       // [NR][CB]
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+    __syncthreads();
+    const int t = s_ticket;  // = number of off-diagonal blocks of this CTA
+    if (t >= p.T) return;
+    const int i = BWD ? p.T - 1 - t : t;
+    double* bi = p.b + (int64_t)i * CB * p.ldb;
+    for (int idx = tid; idx < CB * NR; idx += SC_THREADS) bs[idx] = bi[(idx / NR) * p.ldb + idx % NR];
+    __syncthreads();
+    const int U = 2 * (t + 1);
+    auto issue = [&](int u) {
+        if (u < U) {
+            const int s = u >> 1;
+            const double* src;
+            int64_t ld;
+            if (s < t) {
+                const int j = BWD ? p.T - 1 - s : s;
+                src = BWD ? p.M + ((int64_t)j * CB) * p.ld + (int64_t)i * CB : p.M + ((int64_t)i * CB) * p.ld + (int64_t)j * CB;
+                ld = p.ld;
+            } else {
+                src = p.invd + (int64_t)i * CB * CB;
+                ld = CB;
+            }
+            src += (int64_t)(u & 1) * SC_UR * ld;
+            double* dst = stage + (u % SC_STAGES) * SC_UNIT;
+#pragma unroll
+            for (int k = 0; k < SC_UNIT / 2 / SC_THREADS; ++k) {
+                const int c = tid + SC_THREADS * k, row = c >> 6, q = c & 63;
+                ch_cp_async16(dst + row * CB + 2 * q, src + (int64_t)row * ld + 2 * q);
+            }
+        }
+        ch_cp_commit();
+    };
+    constexpr int NACC = BWD ? 1 : 16;
+    double acc[NR][NACC];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) acc[r][a] = 0.0;
+    const int col = tid & (CB - 1), half = tid >> 7;  // backward: a thread per column, the rows on the two thread halves
+    // totals of the partial sums: fin(r, row, total) is called by exactly one thread per (row, r)
+    auto reduce = [&](auto fin) {
+        if constexpr (!BWD) {
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const double tot = sc_reduce16(acc[r], lane);
+                const int a = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                if (!(lane & 1)) fin(r, 64 * (a >> 3) + warp + 8 * (a & 7), tot);
+            }
         } else {
-            for (int j2 = 0; j2 < j; ++j2)
-                sv_block_apply(Ld + ((int64_t)j * CB) * ld + j2 * CB, ld, 1, vs, bs + j2 * CB * nrhs, nrhs, 1, red);
-        }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < nb * CB * nrhs; idx += SV_THREADS) b[idx] = bs[idx];
-}
-
-// forward: b_rows -= L[rows, super block] y_sb for the rows below the super block.  One CTA per 8
-// rows, a warp per row; width = columns of the super block (<= 512).
-__global__ void __launch_bounds__(128) chol_fwd_update_kernel(const double* __restrict__ L, int64_t ld,
-                                                               const double* __restrict__ ysb, double* __restrict__ b,
-                                                               int64_t rows, int nrhs, int width) {
-    __shared__ double ys[CS * CB * 8];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int idx = tid; idx < width * nrhs; idx += 128) ys[idx] = ysb[idx];
-    __syncthreads();
-    for (int rr = 0; rr < 2; ++rr) {
-        const int64_t row = (int64_t)blockIdx.x * 8 + warp * 2 + rr;
-        if (row >= rows) break;
-        const double* lr = L + row * ld;
-        double s[8];
+            if (half) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) s[r] = 0.0;
-        double4 lvs[CS];  // the whole row segment in flight before the math
-#pragma unroll
-        for (int c = 0; c < CS; ++c)
-            if (c * CB < width) lvs[c] = *reinterpret_cast<const double4*>(lr + c * CB + 4 * lane);
-#pragma unroll
-        for (int c = 0; c < CS; ++c) {
-            if (c * CB >= width) break;
-            const int c0 = c * CB;
-            const double4 lv = lvs[c];
-            const double* yv = ys + (c0 + 4 * lane) * nrhs;
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-                if (r < nrhs) {
-                    s[r] = pn_fma(lv.x, yv[r], s[r]);
-                    s[r] = pn_fma(lv.y, yv[nrhs + r], s[r]);
-                    s[r] = pn_fma(lv.z, yv[2 * nrhs + r], s[r]);
-                    s[r] = pn_fma(lv.w, yv[3 * nrhs + r], s[r]);
-                }
-        }
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (r < nrhs) {
-                double t = s[r];
-#pragma unroll
-                for (int m = 16; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-                if (lane == 0) b[row * nrhs + r] -= t;
+                for (int r = 0; r < NR; ++r) red[r * CB + col] = acc[r][0];
             }
+            __syncthreads();
+            if (!half) {
+#pragma unroll
+                for (int r = 0; r < NR; ++r) fin(r, col, acc[r][0] + red[r * CB + col]);
+            }
+        }
+    };
+    issue(0);
+    issue(1);
+    for (int s = 0; s <= t; ++s) {
+        double* v = vs + (s & 1) * NR * CB;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int u = 2 * s + h;
+            ch_cp_wait<1>();
+            if (h == 0) {
+                if (s < t) {
+                    if (warp == 0) {  // the other warps are still on the previous block or wait at the barrier below
+                        const int j = BWD ? p.T - 1 - s : s;
+                        while (sc_ld_acquire(p.flags + j) == 0) {
+                        }
+                        const double* xj = p.b + (int64_t)j * CB * p.ldb;
+                        for (int idx = lane; idx < CB * NR; idx += 32)
+                            v[(idx % NR) * CB + idx / NR] = __ldcg(xj + (idx / NR) * p.ldb + idx % NR);
+                    }
+                } else {
+                    // every off-diagonal block is in: own block -= sums; it becomes the operand of inv(L_ii)
+                    reduce([&](int r, int row, double tot) { bs[row * NR + r] -= tot; });
+                    __syncthreads();
+                    for (int idx = tid; idx < CB * NR; idx += SC_THREADS) v[(idx % NR) * CB + idx / NR] = bs[idx];
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+#pragma unroll
+                        for (int a = 0; a < NACC; ++a) acc[r][a] = 0.0;
+                }
+            }
+            __syncthreads();  // unit u and the operand are in shared memory; everybody is done with unit u - 1
+            issue(u + 2);     // into the stage unit u - 1 occupied
+            const double* S = stage + (u % SC_STAGES) * SC_UNIT;
+            if constexpr (!BWD) {
+                if (h == 0) sc_apply_rows<NR, 0>(S, v, acc, warp, lane);
+                else sc_apply_rows<NR, 1>(S, v, acc, warp, lane);
+            } else {
+                double a1[NR];
+#pragma unroll
+                for (int r = 0; r < NR; ++r) a1[r] = acc[r][0];
+                sc_apply_cols<NR>(S, v, h, a1, col, half);
+#pragma unroll
+                for (int r = 0; r < NR; ++r) acc[r][0] = a1[r];
+            }
+        }
     }
-}
-
-// backward: y_cols -= L[super block rows, cols]^T x_sb for all columns left of the super block.  One
-// CTA per 128 columns, a thread per column, coalesced reads of the `height` rows of the super block.
-__global__ void __launch_bounds__(CB) chol_bwd_update_kernel(const double* __restrict__ Li, int64_t ld,
-                                                              const double* __restrict__ xsb, double* __restrict__ y,
-                                                              int nrhs, int height) {
-    __shared__ double xs[CS * CB * 8];
-    const int t = threadIdx.x;
-    for (int idx = t; idx < height * nrhs; idx += CB) xs[idx] = xsb[idx];
+    reduce([&](int r, int row, double tot) { bs[row * NR + r] = tot; });
     __syncthreads();
-    const int64_t col = (int64_t)blockIdx.x * CB + t;
-    double s[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) s[r] = 0.0;
-#pragma unroll 8
-    for (int l = 0; l < height; ++l) {
-        const double v = Li[(int64_t)l * ld + col];
-#pragma unroll
-        for (int r = 0; r < 8; ++r)
-            if (r < nrhs) s[r] = pn_fma(v, xs[l * nrhs + r], s[r]);
+    for (int idx = tid; idx < CB * NR; idx += SC_THREADS) bi[(idx / NR) * p.ldb + idx % NR] = bs[idx];
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        sc_st_release(p.flags + i, 1);
     }
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-        if (r < nrhs) y[col * nrhs + r] -= s[r];
 }
 
 // ---- solves with many right-hand sides ------------------------------------------
@@ -722,38 +778,37 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
     return cudaGetLastError();
 }
 
-// b: (npad, nrhs) row-major, nrhs <= 8, overwritten with the solution of L L^T x = b
-cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream) {
-    if (nrhs < 1 || nrhs > 8) return cudaErrorInvalidValue;  // the kernels' shared arrays hold at most 8 right-hand sides
-    const int64_t T = npad / CB;
-    const int64_t SB = (T + CS - 1) / CS;
-    for (int64_t sb = 0; sb < SB; ++sb) {  // L y = b
-        const int64_t k0 = sb * CS;
-        const int nb = (int)((T - k0 < CS) ? T - k0 : CS);
-        double* bk = b + k0 * CB * nrhs;
-        chol_super_diag_kernel<<<1, SV_THREADS, 0, stream>>>(M + k0 * CB * (npad + 1), npad, invd + k0 * CB * CB, bk, nrhs,
-                                                             nb, 0);
-        ++g_pn_launches;
-        const int64_t rows = npad - (k0 + nb) * CB;
-        if (rows > 0) {
-            chol_fwd_update_kernel<<<(unsigned)((rows + 7) / 8), 128, 0, stream>>>(
-                M + (k0 + nb) * CB * npad + k0 * CB, npad, bk, bk + (int64_t)nb * CB * nrhs, rows, nrhs, nb * CB);
-            ++g_pn_launches;
-        }
-    }
-    for (int64_t sb = SB - 1; sb >= 0; --sb) {  // L^T x = y
-        const int64_t k0 = sb * CS;
-        const int nb = (int)((T - k0 < CS) ? T - k0 : CS);
-        double* bk = b + k0 * CB * nrhs;
-        chol_super_diag_kernel<<<1, SV_THREADS, 0, stream>>>(M + k0 * CB * (npad + 1), npad, invd + k0 * CB * CB, bk, nrhs,
-                                                             nb, 1);
-        ++g_pn_launches;
-        if (k0 > 0) {
-            chol_bwd_update_kernel<<<(unsigned)k0, CB, 0, stream>>>(M + k0 * CB * npad, npad, bk, b, nrhs, nb * CB);
-            ++g_pn_launches;
-        }
-    }
+// b: nrhs <= 3 adjacent columns of a row-major array with npad rows and row stride ldb, overwritten with the
+// solution of L L^T x = b.  sync: 2 + 2 npad / 128 ints of device scratch (tickets and flags of the two launches).
+namespace {
+template <int NR>
+cudaError_t chol_chain_launch(const double* M, int64_t npad, const double* invd, double* b, int64_t ldb, int* sync,
+                              cudaStream_t stream) {
+    const int T = (int)(npad / CB);
+    const size_t smem = sizeof(double) * (SC_STAGES * SC_UNIT + 2 * NR * CB + 2 * CB * NR);
+    cudaError_t err;
+    if ((err = cudaFuncSetAttribute(chol_chain_solve_kernel<NR, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    if ((err = cudaFuncSetAttribute(chol_chain_solve_kernel<NR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(sync, 0, sizeof(int) * (2 + 2 * (size_t)T), stream)) != cudaSuccess) return err;
+    ChChain p{M, npad, invd, b, ldb, sync, sync + 2, T};
+    chol_chain_solve_kernel<NR, false><<<(unsigned)T, SC_THREADS, smem, stream>>>(p);  // L y = b
+    ++g_pn_launches;
+    p.ticket = sync + 1;
+    p.flags = sync + 2 + T;
+    chol_chain_solve_kernel<NR, true><<<(unsigned)T, SC_THREADS, smem, stream>>>(p);  // L^T x = y
+    ++g_pn_launches;
     return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int64_t ldb, int nrhs, int* sync,
+                          cudaStream_t stream) {
+    switch (nrhs) {
+        case 1: return chol_chain_launch<1>(M, npad, invd, b, ldb, sync, stream);
+        case 2: return chol_chain_launch<2>(M, npad, invd, b, ldb, sync, stream);
+        case 3: return chol_chain_launch<3>(M, npad, invd, b, ldb, sync, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 // Z, Y: (mpad, npad) row-major (mpad a multiple of 128).  In: Z = right-hand sides, one per ROW (the

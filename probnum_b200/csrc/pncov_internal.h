@@ -106,7 +106,8 @@ cudaError_t pn_launch_chain_apply(const double* U, const double* V, int64_t ld, 
 cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, double* panel, double* invd,
                            int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
                            cudaEvent_t ev_diag);
-cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int nrhs, cudaStream_t stream);
+cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int64_t ldb, int nrhs, int* sync,
+                          cudaStream_t stream);
 // many right-hand sides, one per ROW of Z (mpad x npad); Y: scratch of the same shape
 cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
                                int forward_only, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_main,

@@ -24,7 +24,7 @@ def test_factor_and_solve_match_lapack(n):
     want = np.linalg.cholesky(A)
     np.testing.assert_allclose(L, want, rtol=1e-11, atol=1e-13)
     rng = np.random.default_rng(1)
-    for k in (1, 3, 11):
+    for k in (1, 2, 3, 11):
         b = rng.normal(size=(n, k))
         x = ch.solve(b)
         ref = scipy.linalg.cho_solve((want, True), b)
@@ -32,6 +32,29 @@ def test_factor_and_solve_match_lapack(n):
         assert np.linalg.norm(A @ x - b) <= 1e-11 * np.linalg.norm(A) * np.linalg.norm(x)
     v = rng.normal(size=n)
     np.testing.assert_allclose(ch.solve(v), scipy.linalg.cho_solve((want, True), v), rtol=1e-9, atol=1e-12)
+    ch.close()
+
+
+def test_chained_substitution_with_more_block_rows_than_sms():
+    """pncov_chol_solve for 1-3 columns is one launch per direction whose CTAs wait for each other
+    (chol_chain_solve_kernel): 150 block rows do not fit the 148 SMs at once, so the last CTAs start only when the
+    first ones have left.  Checked by the residual on the device and by bit-reproducibility of a second solve."""
+    import torch
+
+    n = 150 * 128 - 37
+    g = torch.Generator(device="cuda").manual_seed(11)
+    R = torch.rand((n, n), dtype=torch.float64, device="cuda", generator=g)
+    A = (R + R.T) * (0.5 / n ** 0.5)
+    del R
+    A.diagonal().add_(2.0 + torch.rand(n, dtype=torch.float64, device="cuda", generator=g))
+    ch = _lib.Cholesky(A.data_ptr(), on_device=True, n=n)
+    rng = np.random.default_rng(4)
+    for k in (1, 3):
+        b = rng.normal(size=(n, k))
+        x = ch.solve(b)
+        r = (A @ torch.from_numpy(x).cuda()).cpu().numpy() - b
+        assert np.linalg.norm(r) <= 1e-12 * n * np.linalg.norm(b)
+        np.testing.assert_array_equal(ch.solve(b), x)
     ch.close()
 
 
