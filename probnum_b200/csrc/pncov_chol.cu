@@ -46,6 +46,18 @@ __device__ __forceinline__ void ch_cp_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// phase time stamps of chol_diag_kernel for tools/chol_diag_probe.cu (compiled out of the library)
+#ifdef PN_DIAG_CLOCKS
+__device__ long long g_diag_clk[16];
+#define PN_DIAG_STAMP(k)                              \
+    do {                                              \
+        __syncthreads();                              \
+        if (threadIdx.x == 0) g_diag_clk[k] = clock64(); \
+    } while (0)
+#else
+#define PN_DIAG_STAMP(k)
+#endif
+
 struct ChGemm {
     const double* A;  // mode 0: first row block of the panel inside the matrix; mode 1: contiguous panel
     int64_t lda;
@@ -159,53 +171,177 @@ __global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_c
     }
 }
 
-// 16 elimination steps j = 16 JJ .. 16 JJ + 15 of the in-register Cholesky of chol_diag_kernel.
-// Thread (ty, tx) owns a[ty + 16 ii][tx + 16 cc] in r[ii][cc]; column block JJ is a compile-time
-// constant, so every register index is static and finished column blocks cost nothing.
+// 1 / sqrt(a) for a pivot a > 0: hardware seed (22 bits) and two Newton steps, branch-free.  The library rsqrt() is on
+// the critical chain of every elimination step and costs ~250 cycles there (special-case handling, a call); this one
+// is seven dependent operations.  Relative error below 2 ulp; subnormal pivots are flushed to zero by the seed and end
+// as a non-finite factor, which the next pivot test reports.
+__device__ __forceinline__ double ch_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    double e = pn_fma(-(h * y), y, 0.5);
+    y = pn_fma(y, e, y);
+    e = pn_fma(-(h * y), y, 0.5);
+    return pn_fma(y, e, y);
+}
+
+// 16 elimination steps j = 16 JJ .. 16 JJ + 15 of the in-register Cholesky of chol_diag_kernel, two columns per
+// barrier.  Thread (ty, tx) owns a[ty + 16 ii][tx + 16 cc] in r[ii][cc] for the 16 x 16 groups on and below the
+// diagonal (cc <= ii); column group JJ is a compile-time constant, so every register index is static and finished
+// column groups and the groups above the diagonal cost nothing.  The owners publish columns j and j + 1 as they are
+// (column j + 1 without the update from column j); every thread derives L[.][j], then column j + 1 updated and scaled,
+// for its own rows and columns from the published values -- the same operations, in the same order, as two single
+// steps, with one barrier and one shared-memory round trip (the step is latency-bound).  rd receives 1 / L[j][j].
 template <int JJ>
-__device__ __forceinline__ void chol_diag_steps(double (&r)[8][8], double* colbuf, int ty, int tx, int tid, int* info,
-                                                int pivot_base) {
+__device__ __forceinline__ void chol_diag_steps(double (&r)[8][8], double* colbuf, double* rd, int ty, int tx, int tid,
+                                                int* info, int pivot_base) {
 #pragma unroll 1
-    for (int jt = 0; jt < 16; ++jt) {
+    for (int jt = 0; jt < 16; jt += 2) {
         const int j = 16 * JJ + jt;
-        double* cb = colbuf + (j & 1) * CB;  // double-buffered: one barrier per step
-        if (tx == jt) {                       // the owners of column j publish it (unscaled)
+        double* cb0 = colbuf + (jt & 2) * CB;  // [2][CB] per pair, double-buffered over pairs: one barrier per pair
+        double* cb1 = cb0 + CB;
+        if (tx == jt) {
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) cb[ty + 16 * ii] = r[ii][JJ];
+            for (int ii = JJ; ii < 8; ++ii) cb0[ty + 16 * ii] = r[ii][JJ];
+        } else if (tx == jt + 1) {
+#pragma unroll
+            for (int ii = JJ; ii < 8; ++ii) cb1[ty + 16 * ii] = r[ii][JJ];
         }
         __syncthreads();
-        double ajj = cb[j];
+        double ajj = cb0[j];
         if (!(ajj > 0.0)) {  // not positive definite (or NaN): record the first offender, keep going
             if (tid == 0) atomicCAS(info, 0, pivot_base + j + 1);
             ajj = 1.0;
         }
-        const double dj = rsqrt(ajj);
-        double li[8], lc[8 - JJ];
+        const double d0 = ch_rsqrt(ajj);
+        const double l10 = cb0[j + 1] * d0;  // L[j+1][j]
+        double a11 = pn_fma(-l10, l10, cb1[j + 1]);
+        if (!(a11 > 0.0)) {
+            if (tid == 0) atomicCAS(info, 0, pivot_base + j + 2);
+            a11 = 1.0;
+        }
+        const double d1 = ch_rsqrt(a11);
+        if (tid == 0) {
+            rd[j] = d0;
+            rd[j + 1] = d1;
+        }
+        double li0[8 - JJ], lc0[8 - JJ], li1[8 - JJ], lc1[8 - JJ];
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) li[ii] = cb[ty + 16 * ii] * dj;  // L[i][j] for my rows (i >= j)
+        for (int ii = JJ; ii < 8; ++ii) {  // L[i][j], L[i][j+1] for my rows
+            li0[ii - JJ] = cb0[ty + 16 * ii] * d0;
+            li1[ii - JJ] = pn_fma(-li0[ii - JJ], l10, cb1[ty + 16 * ii]) * d1;
+        }
 #pragma unroll
-        for (int cc = JJ; cc < 8; ++cc) lc[cc - JJ] = cb[tx + 16 * cc] * dj;  // L[c][j] for my columns
-        // a[i][c] -= L[i][j] L[c][j] for the columns right of j; rows above the diagonal hold dead
-        // values that never feed a live one, so they need no predicate
+        for (int cc = JJ; cc < 8; ++cc) {  // L[c][j], L[c][j+1] for my columns
+            lc0[cc - JJ] = cb0[tx + 16 * cc] * d0;
+            lc1[cc - JJ] = pn_fma(-lc0[cc - JJ], l10, cb1[tx + 16 * cc]) * d1;
+        }
+        // a[i][c] -= L[i][j] L[c][j], then -= L[i][j+1] L[c][j+1], for the columns right of j resp. j + 1; entries above
+        // the diagonal inside a diagonal group hold dead values that never feed a live one, so they need no predicate
 #pragma unroll
         for (int cc = JJ; cc < 8; ++cc) {
-            const bool upd = (cc > JJ) || (tx > jt);
+            const bool upd0 = (cc > JJ) || (tx > jt), upd1 = (cc > JJ) || (tx > jt + 1);
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii)
-                if (upd) r[ii][cc] = pn_fma(-li[ii], lc[cc - JJ], r[ii][cc]);
+            for (int ii = cc; ii < 8; ++ii) {
+                if (upd0) r[ii][cc] = pn_fma(-li0[ii - JJ], lc0[cc - JJ], r[ii][cc]);
+                if (upd1) r[ii][cc] = pn_fma(-li1[ii - JJ], lc1[cc - JJ], r[ii][cc]);
+            }
         }
         if (tx == jt) {  // column j is final: L[j][j] = a_jj / sqrt(a_jj), L[i][j] = a_ij / sqrt(a_jj)
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) r[ii][JJ] = li[ii];
+            for (int ii = JJ; ii < 8; ++ii) r[ii][JJ] = li0[ii - JJ];
+        } else if (tx == jt + 1) {
+#pragma unroll
+            for (int ii = JJ; ii < 8; ++ii) r[ii][JJ] = li1[ii - JJ];
         }
     }
 }
 
+// Off-diagonal blocks of the inverse at block distance DIST (32 x 32 blocks): X_ib = -X_ii T_ib with
+// T_ib = sum_{m=b}^{i-1} L_im X_mb, for the 4 - DIST pairs (i, b = i - DIST) at once.  L[i][l] sits at a[l][i] (upper
+// triangle), X[i][c] at a[i][c] (lower triangle); T: (4 - DIST) blocks with row stride 33.  A thread owns a TR x TC
+// micro tile of one block (unit-stride operands along a row of `a` for both factors).
+template <int DIST, int TR, int TC>
+__device__ __forceinline__ void chol_inv_offdiag(double* __restrict__ a, double* __restrict__ T, int tid) {
+    constexpr int PER = (32 / TR) * (32 / TC);  // threads per block
+    constexpr int NBLK = 4 - DIST;
+    static_assert(PER * NBLK <= 256, "micro tiles do not fit the CTA");
+    const int blk = tid / PER, u = tid % PER;
+    const int r0 = (u / (32 / TC)) * TR, q0 = (u % (32 / TC)) * TC;  // tile origin inside the block
+    const int i = blk + DIST, b = blk;
+    const bool on = blk < NBLK;
+    if (on) {
+        double acc[TR][TC];
+#pragma unroll
+        for (int x = 0; x < TR; ++x)
+#pragma unroll
+            for (int y = 0; y < TC; ++y) acc[x][y] = 0.0;
+        const double* lrow = a + 32 * i + r0;  // + l * CD_LD: L[32 i + r0 ..][l]
+        const double* xcol = a + 32 * b + q0;  // + l * CD_LD: X[l][32 b + q0 ..]
+        // m = b: X_bb is lower triangular and its upper part is not stored (L^T lives there)
+#pragma unroll 4
+        for (int l = 32 * b; l < 32 * b + 32; ++l) {
+            double lv[TR], xv[TC];
+#pragma unroll
+            for (int x = 0; x < TR; ++x) lv[x] = lrow[l * CD_LD + x];
+#pragma unroll
+            for (int y = 0; y < TC; ++y) xv[y] = (l >= 32 * b + q0 + y) ? xcol[l * CD_LD + y] : 0.0;
+#pragma unroll
+            for (int x = 0; x < TR; ++x)
+#pragma unroll
+                for (int y = 0; y < TC; ++y) acc[x][y] = pn_fma(lv[x], xv[y], acc[x][y]);
+        }
+#pragma unroll 4
+        for (int l = 32 * b + 32; l < 32 * i; ++l) {
+            double lv[TR], xv[TC];
+#pragma unroll
+            for (int x = 0; x < TR; ++x) lv[x] = lrow[l * CD_LD + x];
+#pragma unroll
+            for (int y = 0; y < TC; ++y) xv[y] = xcol[l * CD_LD + y];
+#pragma unroll
+            for (int x = 0; x < TR; ++x)
+#pragma unroll
+                for (int y = 0; y < TC; ++y) acc[x][y] = pn_fma(lv[x], xv[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < TR; ++x)
+#pragma unroll
+            for (int y = 0; y < TC; ++y) T[(blk * 32 + r0 + x) * 33 + q0 + y] = acc[x][y];
+    }
+    __syncthreads();
+    if (on) {  // X_ib = -X_ii T: X_ii[r][k] = a[32 i + r][32 i + k] for k <= r
+        double acc[TR][TC];
+#pragma unroll
+        for (int x = 0; x < TR; ++x)
+#pragma unroll
+            for (int y = 0; y < TC; ++y) acc[x][y] = 0.0;
+        const double* xi = a + (32 * i + r0) * CD_LD + 32 * i;
+        const double* tc = T + blk * 32 * 33 + q0;
+#pragma unroll 4
+        for (int k = 0; k < r0 + TR; ++k) {
+            double xv[TR], tv[TC];
+#pragma unroll
+            for (int x = 0; x < TR; ++x) xv[x] = (k <= r0 + x) ? xi[x * CD_LD + k] : 0.0;
+#pragma unroll
+            for (int y = 0; y < TC; ++y) tv[y] = tc[k * 33 + y];
+#pragma unroll
+            for (int x = 0; x < TR; ++x)
+#pragma unroll
+                for (int y = 0; y < TC; ++y) acc[x][y] = pn_fma(xv[x], tv[y], acc[x][y]);
+        }
+#pragma unroll
+        for (int x = 0; x < TR; ++x)
+#pragma unroll
+            for (int y = 0; y < TC; ++y) a[(32 * i + r0 + x) * CD_LD + 32 * b + q0 + y] = -acc[x][y];
+    }
+    __syncthreads();
+}
+
 // One CTA: Cholesky of the 128 x 128 diagonal block (lower triangle of A, row-major) and the
 // inverse of its factor.  The block lives in registers (8 x 8 per thread, cyclic 16 x 16
-// distribution); per elimination step the owners publish one column through shared memory, one
-// barrier, and everybody updates its registers.  info receives the 1-based index of the first
-// non-positive pivot.
+// distribution, groups on and below the diagonal); per elimination step the owners publish one column through
+// shared memory, one barrier, and everybody updates its registers.  info receives the 1-based index of the first
+// non-positive pivot.  Phase times (tools/chol_diag_probe.cu) are in DESIGN.md 4.5.
 // P != nullptr (look-ahead): the block first receives its own trailing update A -= P P^T from the 128 x 128
 // head of the current panel, so the kernel depends on the panel alone and can take an SM before the
 // wide update of the same step fills the machine.
@@ -214,20 +350,28 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
                                                          const double* __restrict__ P) {
     extern __shared__ __align__(16) unsigned char smem[];
     double* a = reinterpret_cast<double*>(smem);  // [CB][CD_LD]: upper triangle L^T, lower triangle inv(L)
-    double* dg = a + CB * CD_LD;                  // [CB] diagonal of L
-    double* colbuf = dg + CB;                     // [2][CB]
+    double* rd = a + CB * CD_LD;                  // [CB] reciprocals of the diagonal of L
+    double* colbuf = rd + CB;                     // [4][CB]
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
+    PN_DIAG_STAMP(0);
     double r[8][8];
+    if (P != nullptr) {
+        // the head of the panel goes to shared memory asynchronously (row stride CD_LD: 8-byte pieces) while the
+        // block itself is loaded
+        for (int idx = tid; idx < CB * CB; idx += 256)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(pn_smem_u32(a + (idx >> 7) * CD_LD + (idx & (CB - 1)))),
+                         "l"(P + idx)
+                         : "memory");
+        ch_cp_commit();
+    }
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-            const int i = ty + 16 * ii, c = tx + 16 * cc;
-            r[ii][cc] = (c <= i) ? A[(int64_t)i * lda + c] : 0.0;
-        }
+        for (int cc = 0; cc <= ii; ++cc) r[ii][cc] = A[(int64_t)(ty + 16 * ii) * lda + tx + 16 * cc];
     if (P != nullptr) {
-        for (int idx = tid; idx < CB * CB; idx += 256) a[(idx >> 7) * CD_LD + (idx & (CB - 1))] = P[idx];
+        // own tile of the trailing update, A -= P P^T (groups on and below the diagonal)
+        ch_cp_wait<0>();
         __syncthreads();
         const double* pr = a + ty * CD_LD;
         const double* pc = a + tx * CD_LD;
@@ -241,85 +385,69 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
 #pragma unroll
             for (int ii = 0; ii < 8; ++ii)
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) r[ii][cc] = pn_fma(-vi[ii], vc[cc], r[ii][cc]);
+                for (int cc = 0; cc <= ii; ++cc) r[ii][cc] = pn_fma(-vi[ii], vc[cc], r[ii][cc]);
         }
-#pragma unroll
-        for (int ii = 0; ii < 8; ++ii)
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc)
-                if (tx + 16 * cc > ty + 16 * ii) r[ii][cc] = 0.0;
         // `a` is written again only after the elimination steps, whose barriers order it after these reads
     }
-    chol_diag_steps<0>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<1>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<2>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<3>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<4>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<5>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<6>(r, colbuf, ty, tx, tid, info, pivot_base);
-    chol_diag_steps<7>(r, colbuf, ty, tx, tid, info, pivot_base);
+    PN_DIAG_STAMP(1);
+    chol_diag_steps<0>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<1>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    PN_DIAG_STAMP(2);
+    chol_diag_steps<2>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<3>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    PN_DIAG_STAMP(3);
+    chol_diag_steps<4>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<5>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    PN_DIAG_STAMP(4);
+    chol_diag_steps<6>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    chol_diag_steps<7>(r, colbuf, rd, ty, tx, tid, info, pivot_base);
+    PN_DIAG_STAMP(5);
     // L to global memory (lower triangle) and, transposed, to shared memory for the inverse
 #pragma unroll
     for (int ii = 0; ii < 8; ++ii)
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
+        for (int cc = 0; cc <= ii; ++cc) {
             const int i = ty + 16 * ii, c = tx + 16 * cc;
             if (c <= i) A[(int64_t)i * lda + c] = r[ii][cc];
             if (c < i) a[c * CD_LD + i] = r[ii][cc];
-            else if (c == i) dg[i] = r[ii][cc];
         }
     __syncthreads();
+    PN_DIAG_STAMP(6);
     // inverse X of L, blocked 4 x 4 with 32 x 32 blocks.  L[i][l] sits at a[l][i] (upper triangle),
     // X[i][c] goes to a[i][c] (lower triangle, free now).
-    // (A) diagonal blocks: forward substitution inside the block, one column per thread
+    // (A) diagonal blocks: a thread per column, the column in registers; once x_k is final it goes into the rows
+    // below (independent FMAs; L[i][k] is the same address for the whole warp)
     if (tid < CB) {
-        const int c = tid, b0 = (tid >> 5) << 5;
-        for (int i = b0; i < b0 + 32; ++i) {
-            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
-            int l = b0;
-            for (; l + 1 < i; l += 2) {
-                s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
-                s1 = pn_fma(-a[(l + 1) * CD_LD + i], (l + 1 >= c) ? a[(l + 1) * CD_LD + c] : 0.0, s1);
-            }
-            if (l < i) s0 = pn_fma(-a[l * CD_LD + i], (l >= c) ? a[l * CD_LD + c] : 0.0, s0);
-            if (i >= c) a[i * CD_LD + c] = (s0 + s1) / dg[i];  // own column only
+        const int b0 = (tid >> 5) << 5, cl = tid & 31;
+        double x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = (i == cl) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            x[k] *= rd[b0 + k];
+#pragma unroll
+            for (int i = k + 1; i < 32; ++i) x[i] = pn_fma(-a[(b0 + k) * CD_LD + b0 + i], x[k], x[i]);
         }
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i >= cl) a[(b0 + i) * CD_LD + tid] = x[i];
     }
     __syncthreads();
-    // (B) off-diagonal blocks by block distance: X_ib = -X_ii (sum_{m=b}^{i-1} L_im X_mb); the blocks
-    // of one distance are independent.  The inner sums T (up to 3 blocks of 32 x 32 at a time, row
-    // stride 33) have their own shared-memory area: both triangles of `a` are still in use.
-    double* T = colbuf + 2 * CB;
-    const int cc = tid & 31, rr0 = tid >> 5;  // a warp walks 32 adjacent columns of one row: L broadcasts
-    for (int dist = 1; dist < 4; ++dist) {
-        const int nblk = 4 - dist;
-        for (int o = rr0; o < nblk * 32; o += 8) {  // T[blk][rr][cc]
-            const int blk = o >> 5, rr = o & 31;
-            const int b = blk, i = blk + dist;
-            const int row = 32 * i + rr, col = 32 * b + cc;
-            double s0 = 0.0, s1 = 0.0;
-            for (int l = 32 * b; l < 32 * i; l += 2) {
-                s0 = pn_fma(a[l * CD_LD + row], (l >= col) ? a[l * CD_LD + col] : 0.0, s0);
-                s1 = pn_fma(a[(l + 1) * CD_LD + row], (l + 1 >= col) ? a[(l + 1) * CD_LD + col] : 0.0, s1);
-            }
-            T[(blk * 32 + rr) * 33 + cc] = s0 + s1;
-        }
-        __syncthreads();
-        for (int o = rr0; o < nblk * 32; o += 8) {  // X_ib = -X_ii T
-            const int blk = o >> 5, rr = o & 31;
-            const int b = blk, i = blk + dist;
-            const int row = 32 * i + rr, col = 32 * b + cc;
-            double s = 0.0;
-            for (int k = 0; k <= rr; ++k) s = pn_fma(a[row * CD_LD + 32 * i + k], T[(blk * 32 + k) * 33 + cc], s);
-            a[row * CD_LD + col] = -s;
-        }
-        __syncthreads();
-    }
+    PN_DIAG_STAMP(7);
+    // (B) off-diagonal blocks by block distance; the blocks of one distance are independent
+    double* T = colbuf + 4 * CB;
+    chol_inv_offdiag<1, 4, 4>(a, T, tid);
+    PN_DIAG_STAMP(8);
+    chol_inv_offdiag<2, 4, 2>(a, T, tid);
+    PN_DIAG_STAMP(9);
+    chol_inv_offdiag<3, 2, 2>(a, T, tid);
+    PN_DIAG_STAMP(10);
     // X to global memory, row-major, zeros above the diagonal
     for (int idx = tid; idx < CB * CB; idx += 256) {
         const int i = idx / CB, c = idx % CB;
         invL[idx] = (c <= i) ? a[i * CD_LD + c] : 0.0;
     }
+    PN_DIAG_STAMP(11);
 }
 
 // M[i][i] += jitter for i < n; padded diagonal (i >= n) = 1
@@ -720,7 +848,7 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
     if ((err = cudaMemsetAsync(info_dev, 0, sizeof(int), stream)) != cudaSuccess) return err;
     chol_prepare_diag_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(M, npad, n, npad, jitter);
     ++g_pn_launches;
-    const size_t smem_diag = sizeof(double) * (CB * CD_LD + 3 * CB + 3 * 32 * 33);
+    const size_t smem_diag = sizeof(double) * (CB * CD_LD + 5 * CB + 3 * 32 * 33);
     const size_t smem_gemm = sizeof(double) * 2 * (CB + CTN) * CLD;
     if ((err = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(chol_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
