@@ -698,6 +698,53 @@ def leg_bayesquad(ctx: Ctx, args, extra: dict, with_cpu: bool) -> int:
     return _lib.launch_count() - l0
 
 
+def leg_cholesky(ctx: Ctx, extra: dict) -> int:
+    """the hand-written FP64 Cholesky behind `compute_gram_cho_factor` / `gram_cho_solve`
+    (csrc/pncov_chol.cu) at the order of configs[4] and a small one, with cuSOLVER `potrf` (through torch) on the same
+    matrix beside it.  Device time of the factorisation (CUDA events inside the library); wall time of a
+    one-column `pncov_chol_solve` with host operands; the solution checked against cuSOLVER's."""
+    from probnum_b200 import _lib  # noqa: PLC0415
+
+    torch = ctx.torch
+    l0 = _lib.launch_count()
+    out = {}
+    for n in (4096, 16384):
+        torch.manual_seed(n)
+        B = torch.randn((n, n + 64), dtype=torch.float64, device=ctx.dev)
+        A = B @ B.T / n
+        A.diagonal().add_(0.1)
+        del B
+        ch = _lib.Cholesky(A.data_ptr(), on_device=True, n=n, device=ctx.local_rank)
+        ch.close()
+        ch = _lib.Cholesky(A.data_ptr(), on_device=True, n=n, device=ctx.local_rank)
+        ms = ch.last_factor_ms()
+        b = np.random.default_rng(0).normal(size=(n, 1))
+        x = ch.solve(b)
+        ts = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            ch.solve(b)
+            ts.append(time.perf_counter() - t0)
+        ch.close()
+        torch.linalg.cholesky_ex(A)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Lt, _ = torch.linalg.cholesky_ex(A)
+        e1.record()
+        torch.cuda.synchronize()
+        xb = torch.cholesky_solve(torch.from_numpy(b).to(ctx.dev), Lt).cpu().numpy()
+        diff = float(np.abs(x - xb).max() / np.abs(xb).max())
+        out[str(n)] = {"factor_ms": ms, "factor_tflops": n ** 3 / 3.0 / (ms * 1e-3) / 1e12, "solve_1col_ms": 1e3 * min(ts),
+                       "cusolver_potrf_ms": e0.elapsed_time(e1), "solution_rel_diff_vs_cusolver": diff,
+                       "criterion": "<= 1e-10", "ok": bool(diff <= 1e-10)}
+        ctx.check(f"cholesky.{n}", out[str(n)])
+        del A, Lt
+        torch.cuda.empty_cache()
+    extra["cholesky"] = out
+    return _lib.launch_count() - l0
+
+
 def leg_config0(ctx: Ctx, extra: dict, with_cpu: bool) -> int:
     """configs[0]: ExpQuad Gram N = 1000, d = 10 and the true asv shape d = 100
     (benchmarks/covfuncs.py:20,55-66) through `k.matrix(X)` of the patched reference classes."""
@@ -935,6 +982,7 @@ def run_ours(args):
         if rank == 0:
             launches += leg_bayesquad(ctx, args, extra, with_cpu)
             launches += leg_config0(ctx, extra, with_cpu)
+            launches += leg_cholesky(ctx, extra)
         barrier()
 
     cpu = None

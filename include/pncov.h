@@ -240,9 +240,12 @@ PNCOV_API int pncov_combine_device(int device, void* dst, const void* src, int64
  * right-looking factorisation with the trailing updates on FP64 DMMA (csrc/pncov_chol.cu).
  *   pncov_chol_create       handle for matrices of order n on `device` (owns the n x n device copy)
  *   pncov_chol_factor       a: (n, n) row-major symmetric matrix, leading dimension ld, host memory
- *                           (a_on_device = 0) or device memory on the handle's device (the call waits
- *                           for all work already queued on that device first); only the lower
- *                           triangle is read.  *info = 0 on success, else the 1-based index of the
+ *                           (a_on_device = 0) or device memory on the handle's device (= 1; the call
+ *                           waits for all work already queued on that device first); only the lower
+ *                           triangle is read.  a_on_device = 2: host memory of which only the UPPER
+ *                           triangle is read -- what scipy.linalg.cho_factor(a) (lower=False, the call of
+ *                           _belief_update.py:79) uses; half the host-to-device bytes, mirrored on the device.
+ *                           *info = 0 on success, else the 1-based index of the
  *                           first non-positive pivot (scipy raises LinAlgError there); blocking.
  *   pncov_chol_factor_gram  same, but the matrix is the Gram matrix of a (square, float64) operator
  *                           handle: it is evaluated straight into the factorisation buffer and never

@@ -471,11 +471,13 @@ class Cholesky:
     """Device-resident Cholesky factor of ``a + jitter * I`` (float64, lower triangle of ``a`` read).
 
     ``a`` is a host array or, with ``on_device``, an integer device address of an (n, n) row-major
-    matrix.  Raises ``numpy.linalg.LinAlgError`` like ``scipy.linalg.cho_factor`` if the matrix is
+    matrix.  ``upper=True`` (host arrays): the UPPER triangle is the one that counts, as in
+    ``scipy.linalg.cho_factor(a)`` with its default ``lower=False``; only that half is uploaded.
+    Raises ``numpy.linalg.LinAlgError`` like ``scipy.linalg.cho_factor`` if the matrix is
     not positive definite."""
 
     def __init__(self, a, jitter: float = 0.0, *, device: Optional[int] = None, on_device: bool = False,
-                 n: Optional[int] = None, ld: Optional[int] = None):
+                 n: Optional[int] = None, ld: Optional[int] = None, upper: bool = False):
         lib = load()
         self._lib = lib
         self._h = _c_vp()
@@ -508,7 +510,8 @@ class Cholesky:
         _check(lib.pncov_chol_create(ctypes.byref(self._h), self.device, self.n))
         info = ctypes.c_int(0)
         try:
-            _check(lib.pncov_chol_factor(self._h, ptr, lda, float(jitter), 1 if on_device else 0, ctypes.byref(info)))
+            _check(lib.pncov_chol_factor(self._h, ptr, lda, float(jitter), 1 if on_device else (2 if upper else 0),
+                                         ctypes.byref(info)))
         except Exception:
             self.close()
             raise

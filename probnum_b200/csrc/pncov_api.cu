@@ -1644,10 +1644,24 @@ PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, doub
     c->factored = false;
     // a device-resident input may still be in flight on the caller's stream: the handle works on
     // its own stream, so wait for the device once (microseconds next to the factorisation)
-    if (a_on_device) PN_CUDA(cudaDeviceSynchronize());
+    if (a_on_device < 0 || a_on_device > 2) return fail(PNCOV_EINVAL, "a_on_device must be 0, 1 or 2");
+    if (a_on_device == 1) PN_CUDA(cudaDeviceSynchronize());
     if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->M, 0, (size_t)c->npad * c->npad * 8, c->stream));
-    PN_CUDA(cudaMemcpy2DAsync(c->M, (size_t)c->npad * 8, a, (size_t)ld * 8, (size_t)c->n * 8, (size_t)c->n,
-                              a_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (a_on_device == 2) {
+        // host array of which the UPPER triangle counts (scipy.linalg.cho_factor's default, lower=False): only the
+        // blocks on and above the diagonal cross PCIe -- half the bytes of the dominant step of a factorisation
+        // from a host Gram matrix -- and the lower triangle the kernels work on is mirrored from them on the device
+        const int64_t n = c->n, rb = 512;
+        for (int64_t r0 = 0; r0 < n; r0 += rb) {
+            const int64_t rows = std::min<int64_t>(rb, n - r0);
+            PN_CUDA(cudaMemcpy2DAsync(c->M + r0 * c->npad + r0, (size_t)c->npad * 8, a + r0 * ld + r0, (size_t)ld * 8,
+                                      (size_t)(n - r0) * 8, (size_t)rows, cudaMemcpyHostToDevice, c->stream));
+        }
+        PN_CUDA(pn_chol_mirror_upper(c->M, c->npad, n, c->stream));
+    } else {
+        PN_CUDA(cudaMemcpy2DAsync(c->M, (size_t)c->npad * 8, a, (size_t)ld * 8, (size_t)c->n * 8, (size_t)c->n,
+                                  a_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    }
     PN_CUDA(cudaEventRecord(c->ev0, c->stream));
     PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->stream, c->side, c->ev_panel, c->ev_diag));
     PN_CUDA(cudaEventRecord(c->ev1, c->stream));

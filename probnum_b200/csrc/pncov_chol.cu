@@ -373,6 +373,7 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
         // own tile of the trailing update, A -= P P^T (groups on and below the diagonal)
         ch_cp_wait<0>();
         __syncthreads();
+        PN_DIAG_STAMP(12);
         const double* pr = a + ty * CD_LD;
         const double* pc = a + tx * CD_LD;
 #pragma unroll 2
@@ -474,6 +475,7 @@ constexpr int SC_THREADS = 256;
 constexpr int SC_UR = 64;               // rows of a pipeline unit (half a block)
 constexpr int SC_STAGES = 3;
 constexpr int SC_UNIT = SC_UR * CB;     // doubles per unit
+static_assert(sizeof(double) * (SC_STAGES * SC_UNIT + 4 * 3 * CB) <= 227 * 1024, "chain kernel: ring + operands exceed the shared memory of an SM");
 
 struct ChChain {
     const double* M;     // factor, row-major, lower triangle
@@ -1039,6 +1041,37 @@ cudaError_t pn_chol_transpose(const double* src, int64_t lds, int64_t rows, int6
     const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
     if (grid.y > 65535) return cudaErrorInvalidConfiguration;
     chol_transpose_kernel<<<grid, 256, 0, stream>>>(src, lds, rows, cols, dst, ldd);
+    ++g_pn_launches;
+    return cudaGetLastError();
+}
+
+// M[i][j] = M[j][i] for all i > j of the leading n x n block (row-major, ld): the lower triangle becomes the mirror
+// image of the upper one.  32 x 32 tiles through shared memory; tiles left of the diagonal exit.
+namespace {
+__global__ void __launch_bounds__(256) chol_mirror_upper_kernel(double* __restrict__ M, int64_t ld, int64_t n) {
+    if (blockIdx.x < blockIdx.y) return;
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;  // source tile: rows r0.., columns c0.. >= r0
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t r = r0 + ty + 8 * i, c = c0 + tx;
+        if (r < n && c < n) tile[ty + 8 * i][tx] = M[r * ld + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t c = c0 + ty + 8 * i, r = r0 + tx;  // destination M[c][r] = source M[r][c]
+        if (r < n && c < n && c > r) M[c * ld + r] = tile[tx][ty + 8 * i];
+    }
+}
+}  // namespace
+
+cudaError_t pn_chol_mirror_upper(double* M, int64_t ld, int64_t n, cudaStream_t stream) {
+    const unsigned t = (unsigned)((n + 31) / 32);
+    if (t == 0) return cudaSuccess;
+    if (t > 65535) return cudaErrorInvalidConfiguration;
+    chol_mirror_upper_kernel<<<dim3(t, t), 256, 0, stream>>>(M, ld, n);
     ++g_pn_launches;
     return cudaGetLastError();
 }

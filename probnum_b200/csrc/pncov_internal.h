@@ -112,6 +112,7 @@ cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, dou
 cudaError_t pn_chol_solve_wide(const double* M, int64_t npad, const double* invd, double* Z, double* Y, int64_t mpad,
                                int forward_only, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_main,
                                cudaEvent_t ev_side);
+cudaError_t pn_chol_mirror_upper(double* M, int64_t ld, int64_t n, cudaStream_t stream);
 cudaError_t pn_chol_transpose(const double* src, int64_t lds, int64_t rows, int64_t cols, double* dst, int64_t ldd,
                               cudaStream_t stream);
 cudaError_t pn_chol_rowdots(const double* W, const double* G, int64_t ld, int64_t n, int64_t rows, const double* vecs,

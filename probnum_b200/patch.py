@@ -328,7 +328,8 @@ def enable_quad_cholesky() -> None:
             with _mirror._lib.Operator(params, pts) as op:
                 chol = _mirror._lib.Cholesky(op, jitter=float(self.jitter))
         else:
-            chol = _mirror._lib.Cholesky(gram, jitter=float(self.jitter))
+            # cho_factor(a) reads the upper triangle (lower=False): so does the upload, and only that half crosses PCIe
+            chol = _mirror._lib.Cholesky(gram, jitter=float(self.jitter), upper=True)
         return DeviceCholesky(chol), True
 
     def gram_cho_solve(gram_cho_factor, z):

@@ -58,6 +58,26 @@ def test_chained_substitution_with_more_block_rows_than_sms():
     ch.close()
 
 
+@pytest.mark.parametrize("n", [1, 33, 512, 700, 1500])
+def test_upper_triangle_input_like_scipy_cho_factor(n):
+    """scipy.linalg.cho_factor(a) (lower=False, _belief_update.py:79) reads the upper triangle only: with
+    ``upper=True`` an array whose lower triangle is garbage factors like its symmetric completion, and only the blocks
+    on and above the diagonal are uploaded."""
+    A = _spd(n, n + 1)
+    want = np.linalg.cholesky(A)
+    junk = np.triu(A) + np.tril(np.full((n, n), np.nan), -1)
+    ch = _lib.Cholesky(junk, upper=True)
+    np.testing.assert_allclose(ch.factor(), want, rtol=1e-11, atol=1e-13)
+    b = np.random.default_rng(2).normal(size=(n, 2))
+    ref = scipy.linalg.cho_solve(scipy.linalg.cho_factor(junk, check_finite=False), b, check_finite=False)
+    np.testing.assert_allclose(ch.solve(b), ref, rtol=1e-9, atol=1e-12)
+    ch.close()
+    # the default keeps reading the lower triangle
+    ch = _lib.Cholesky(junk.T)
+    np.testing.assert_allclose(ch.factor(), want, rtol=1e-11, atol=1e-13)
+    ch.close()
+
+
 def test_gram_plus_jitter_like_the_belief_update():
     """_belief_update.py:61-79: cho_factor(gram + jitter * I), then cho_solve (:81-103)."""
     rng = np.random.default_rng(3)

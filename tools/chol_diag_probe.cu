@@ -40,6 +40,7 @@ int main() {
                            "inverse (B) dist 1", "inverse (B) dist 2", "inverse (B) dist 3", "inverse out"};
     constexpr int NPH = 11;
     double acc[NPH] = {0};
+    long long last_load = 0;
     float ms_sum = 0;
     const int reps = 20;
     for (int it = 0; it < reps + 2; ++it) {
@@ -55,6 +56,7 @@ int main() {
         if (it >= 2) {
             ms_sum += ms;
             for (int k = 0; k < NPH; ++k) acc[k] += (double)(clk[k + 1] - clk[k]);
+            last_load = clk[12] - clk[0];
         }
     }
     int hinfo = -1;
@@ -65,5 +67,6 @@ int main() {
     for (int k = 0; k < NPH; ++k) tot += acc[k] / reps;
     for (int k = 0; k < NPH; ++k) printf("%-20s %9.0f cycles  %5.1f %%\n", names[k], acc[k] / reps, 100.0 * acc[k] / reps / tot);
     printf("%-20s %9.0f cycles\n", "total", tot);
+    printf("(block and panel head in shared memory / registers after %lld cycles of the first phase, last launch)\n", last_load);
     return 0;
 }
