@@ -58,8 +58,8 @@ PARITY_ROWS = 64
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-matvec", action="store_true", help="skip the K.v extras (configs[2])")
     ap.add_argument("--no-callers", action="store_true", help="skip configs[0], [3], [4] and the row-sharded Gram")
