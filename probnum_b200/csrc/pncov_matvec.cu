@@ -784,9 +784,10 @@ __global__ void __launch_bounds__(MM_THREADS, 3)
 // Same halving for the kernels that cannot use the norm identity (Matern: sqrt(S) near 0; ExpQuad /
 // RatQuad on clouds that are wide in lengthscale units): the CTA of row block I (256 rows = two
 // column tiles) walks the column tiles J >= 2I, and for tiles right of its diagonal pair also
-// accumulates y_J += K_IJ^T v_I.  A thread holds K for its 2 rows x 2 columns: two DFMAs give
-// the partial column sums, one butterfly step folds the two columns onto the two half-warps and
-// four more shuffle rounds finish the warp sum (1.25 DADD per pair); warps meet in shared memory
+// accumulates y_J += K_IJ^T v_I.  A thread holds K for its 2 rows x 4 columns: the DFMAs with the row
+// operand give four partial column sums, two halving exchanges fold the four columns onto the four
+// quarter-warps and three more shuffle rounds finish the warp sums (0.75 DADD and 1.5 SHFL per pair; two
+// columns per step cost 1.25 and 2.5: the kernel is co-bound by issue slots); warps meet in shared memory
 // and one integer-plane update per column leaves the CTA per tile.  Matern-5/2, d = 8: 32 -> 17.75 FP64
 // instructions per ordered pair.
 constexpr int MS_ROWS = MV_THREADS * MV_R;
@@ -876,44 +877,44 @@ __global__ void __launch_bounds__(MV_THREADS)
         const bool mirror = jt > 2 * bx + 1;  // uniform
 
 #pragma unroll 1
-        for (int jj = 0; jj < MV_TJ; jj += 2) {
-            double xb[2][D];
+        for (int jj = 0; jj < MV_TJ; jj += 4) {
+            double S[4 * MV_R];  // S[4 r + c]: row r, column jj + c
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < 4; ++c) {
+                double xb[D];
 #pragma unroll
-                for (int m = 0; m < D; ++m) xb[c][m] = xt[(jj + c) * D + m];
-            double S[2 * MV_R];
+                for (int m = 0; m < D; ++m) xb[m] = xt[(jj + c) * D + m];
 #pragma unroll
-            for (int r = 0; r < MV_R; ++r)
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int r = 0; r < MV_R; ++r) {
                     double s = 0.0;
 #pragma unroll
                     for (int m = 0; m < D; ++m) {
-                        double df = xr[r][m] - xb[c][m];
+                        double df = xr[r][m] - xb[m];
                         if constexpr (ARD) df *= sc[m];
                         s = pn_fma(df, df, s);
                     }
-                    S[2 * r + c] = s;
+                    S[4 * r + c] = s;
                 }
-            mv_epi_tile<EPI, 2 * MV_R>(S, a.epi, tabE, tabL);
-            const double v0 = vt[jj], v1 = vt[jj + 1];
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-            for (int r = 0; r < MV_R; ++r) {
-                acc[r] = pn_fma(S[2 * r], v0, acc[r]);
-                acc[r] = pn_fma(S[2 * r + 1], v1, acc[r]);
-                t0 = pn_fma(S[2 * r], vrow[r], t0);
-                t1 = pn_fma(S[2 * r + 1], vrow[r], t1);
             }
-            if (mirror) {
-                // butterfly: the lower half-warp ends up with column jj, the upper with jj + 1
-                const bool upper = (lane & 16) != 0;
-                const double send = upper ? t0 : t1;
-                double t = (upper ? t1 : t0) + __shfl_xor_sync(0xffffffffu, send, 16);
+            mv_epi_tile<EPI, 4 * MV_R>(S, a.epi, tabE, tabL);
+            double tc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-                for (int m = 8; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
-                if ((lane & 15) == 0) cw[jj + (lane >> 4)] = t;
+            for (int r = 0; r < MV_R; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    acc[r] = pn_fma(S[4 * r + c], vt[jj + c], acc[r]);
+                    tc[c] = pn_fma(S[4 * r + c], vrow[r], tc[c]);
+                }
+            if (mirror) {
+                // halving exchange: after the first step the lower half-warp holds columns jj, jj + 1 and the upper
+                // jj + 2, jj + 3; after the second every quarter holds one column; three plain steps finish the sums
+                const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+                const double a0 = (up16 ? tc[2] : tc[0]) + __shfl_xor_sync(0xffffffffu, up16 ? tc[0] : tc[2], 16);
+                const double a1 = (up16 ? tc[3] : tc[1]) + __shfl_xor_sync(0xffffffffu, up16 ? tc[1] : tc[3], 16);
+                double t = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+#pragma unroll
+                for (int m = 4; m > 0; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+                if ((lane & 7) == 0) cw[jj + (lane >> 3)] = t;
             }
         }
         __syncthreads();
