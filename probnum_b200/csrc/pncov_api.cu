@@ -1560,7 +1560,7 @@ struct pncov_chol {
     int device = 0;
     int64_t n = 0, npad = 0;
     double* M = nullptr;      // (npad, npad) row-major; lower triangle = L after pncov_chol_factor
-    double* panel = nullptr;  // (npad, 128) contiguous block column
+    double* panel = nullptr;  // 2 x (npad, 128): contiguous block columns of two consecutive steps
     double* invd = nullptr;   // (npad / 128) inverse diagonal blocks, 128 x 128 each
     double* rhs = nullptr;    // (npad, kWideSolveMinRhs - 1)
     int* info = nullptr;
@@ -1599,7 +1599,7 @@ PNCOV_API int pncov_chol_create(pncov_chol** out, int device, int64_t n) {
     // from the stream-ordered pool (kept up to its release threshold): a cudaMalloc / cudaFree pair of the 2.1 GB
     // factor buffer cost 0.03 + 0.6 s per Bayesian-quadrature update at 16384 nodes
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->M), (size_t)c->npad * c->npad * 8, c->stream);
-    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->panel), (size_t)c->npad * 128 * 8, c->stream);
+    if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->panel), (size_t)2 * c->npad * 128 * 8, c->stream);
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->invd), (size_t)c->npad * 128 * 8, c->stream);
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->rhs), (size_t)c->npad * (kWideSolveMinRhs - 1) * 8, c->stream);
     if (e == cudaSuccess) e = pn_dev_alloc(reinterpret_cast<void**>(&c->info), sizeof(int), c->stream);
@@ -1663,10 +1663,12 @@ PNCOV_API int pncov_chol_factor(pncov_chol* c, const double* a, int64_t ld, doub
                                   a_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     }
     PN_CUDA(cudaEventRecord(c->ev0, c->stream));
-    PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->stream, c->side, c->ev_panel, c->ev_diag));
+    PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->solve_sync, c->stream, c->side, c->ev_panel,
+                           c->ev_diag));
     PN_CUDA(cudaEventRecord(c->ev1, c->stream));
     PN_CUDA(cudaMemcpyAsync(info, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PN_CUDA(cudaStreamSynchronize(c->stream));
+    if (*info < 0) return fail(PNCOV_EINVAL, "internal: a hand-over wait of the factorisation gave up");
     c->factored = *info == 0;
     return 0;
 }
@@ -1682,10 +1684,12 @@ PNCOV_API int pncov_chol_factor_gram(pncov_chol* c, pncov_handle* h, double jitt
     if (c->npad != c->n) PN_CUDA(cudaMemsetAsync(c->M, 0, (size_t)c->npad * c->npad * 8, c->stream));
     PN_CUDA(launch_gram_any(h, false, 0, c->n, c->M, c->npad, c->stream));
     PN_CUDA(cudaEventRecord(c->ev0, c->stream));
-    PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->stream, c->side, c->ev_panel, c->ev_diag));
+    PN_CUDA(pn_chol_factor(c->M, c->n, c->npad, jitter, c->panel, c->invd, c->info, c->solve_sync, c->stream, c->side, c->ev_panel,
+                           c->ev_diag));
     PN_CUDA(cudaEventRecord(c->ev1, c->stream));
     PN_CUDA(cudaMemcpyAsync(info, c->info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     PN_CUDA(cudaStreamSynchronize(c->stream));
+    if (*info < 0) return fail(PNCOV_EINVAL, "internal: a hand-over wait of the factorisation gave up");
     c->factored = *info == 0;
     return 0;
 }

@@ -21,6 +21,8 @@
 // fragment loads bank-conflict free.
 // Solves use the stored inverse diagonal blocks: every substitution step is a 128 x 128 product
 // plus one pass over a block row / block column of L.
+#include <cstdlib>
+
 #include "pncov_internal.h"
 
 namespace {
@@ -63,11 +65,19 @@ struct ChGemm {
     int64_t lda;
     const double* B;  // mode 0: inverse of the diagonal factor (128 x 128); mode 1: contiguous panel
     int64_t ldb;
-    double* C;        // mode 0: unused (the panel is copied over A afterwards); mode 1: first trailing tile
+    double* C;        // mode 0: unused (the panel is copied over A afterwards); mode 1: block (0, 0) of the trailing matrix
     int64_t ldc;
     double* panel;    // mode 0: contiguous copy of the new block column (ld = 128)
+    double* Lcol;     // mode 1: block (0, -1) of the trailing matrix' frame, i.e. where the panel belongs in the matrix (ld = ldc)
     int mode;
-    int tile0;        // index of the first half tile of this launch (mode 1: half tiles 0, 1 = the next diagonal block)
+    int nb;           // mode 1: block rows of the trailing matrix (its block (0, 0) belongs to the diagonal kernel)
+    // hand-over between the update of step k and the panel of step k + 1, which run concurrently on two streams:
+    // the update's tiles of its first block column come first in its grid and count themselves into rowcount[global
+    // block row] when stored; a panel CTA waits until its row has `target` of them
+    int* rowcount;    // [npad / 128], zero before the factorisation; nullptr: no hand-over
+    int row0;         // global block row of local block row 0
+    int target;       // mode 0: completed first-column half tiles this row must have seen (0: do not wait)
+    int* err;         // set to 1 if a wait gave up (never in a correct schedule; keeps a broken one from hanging)
 };
 
 __global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_constant__ ChGemm p) {
@@ -80,17 +90,56 @@ __global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_c
 
     // a CTA owns 128 rows x 64 columns: block (bi, bj), column half h
     int64_t bi, bj;
-    const int64_t t2 = (int64_t)blockIdx.x + p.tile0;
+    const int64_t t2 = (int64_t)blockIdx.x;
     const int h = (int)(t2 & 1);
     if (p.mode == 0) {
         bi = t2 >> 1;
         bj = 0;
-    } else {  // linear index over the lower triangle (bj <= bi)
+        if (p.target > 0) {  // this row of the block column must have received the update of the previous step
+            if (tid == 0) {
+                const int* cnt = p.rowcount + p.row0 + bi;
+                long long spins = 0;
+                for (;;) {
+                    int seen;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+                    if (seen >= p.target) break;
+                    if (++spins > (1ll << 27)) {  // seconds: the schedule is broken; report instead of hanging
+                        atomicExch(p.err, -1);
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        // the nb - 1 tiles of the first block column first (the next panel waits for them), then the lower triangle
+        // of the remaining blocks row by row; block (0, 0) is not in the grid
         const int64_t t = t2 >> 1;
-        bi = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-        while (bi * (bi + 1) / 2 > t) --bi;
-        bj = t - bi * (bi + 1) / 2;
+        const int64_t ntiles = (int64_t)p.nb * (p.nb + 1) / 2 - 1;
+        if (t >= ntiles) {
+            // the last 2 nb CTAs of the grid put the panel into the matrix (rows below the diagonal block of its
+            // column; nobody else touches them): they fill the slots of the update's last wave
+            const int64_t rb = t - ntiles;
+            const double2* src = reinterpret_cast<const double2*>(p.A + rb * CB * CB + h * CTN);
+            double* dst = p.Lcol + rb * CB * p.ldc + h * CTN;
+#pragma unroll 4
+            for (int idx = tid; idx < CB * (CTN / 2); idx += CG_THREADS) {
+                const int row = idx / (CTN / 2), c2 = idx % (CTN / 2);
+                *reinterpret_cast<double2*>(dst + (int64_t)row * p.ldc + 2 * c2) = src[row * (CB / 2) + c2];
+            }
+            return;
+        }
+        if (t < p.nb - 1) {
+            bi = t + 1;
+            bj = 0;
+        } else {
+            const int64_t u = t - (p.nb - 1);
+            int64_t r = (int64_t)((sqrt(8.0 * (double)u + 1.0) - 1.0) * 0.5);
+            while ((r + 1) * (r + 2) / 2 <= u) ++r;
+            while (r * (r + 1) / 2 > u) --r;
+            bi = r + 1;
+            bj = u - r * (r + 1) / 2 + 1;
+        }
     }
     const double* At = p.A + bi * CB * p.lda;
     const double* Bt = (p.mode == 0 ? p.B : p.B + bj * CB * p.ldb) + (int64_t)h * CTN * p.ldb;
@@ -167,6 +216,13 @@ __global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_c
                 v.y -= acc[r][c][1];
                 *dst = v;
             }
+        }
+    }
+    if (p.mode == 1 && bj == 0 && p.rowcount != nullptr) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(p.rowcount + p.row0 + bi, 1);
         }
     }
 }
@@ -842,69 +898,117 @@ __global__ void __launch_bounds__(WR_THREADS) chol_rowdots_kernel(const double* 
 
 // M: (npad, npad) row-major with ld = npad (a multiple of 128); the Gram matrix occupies the leading
 // n x n block (lower triangle is read).  On return the lower triangle holds L, invd the inverses
-// of the diagonal blocks of L; *info_dev the 1-based index of the first bad pivot (0: success).
+// of the diagonal blocks of L; *info_dev the 1-based index of the first bad pivot (0: success, -1: a hand-over wait
+// gave up).  panel: TWO contiguous block columns (2 x npad x 128 doubles); scratch: npad / 128 ints.
+//
+// Schedule (two streams; D = diagonal block, P = panel, U = trailing update of a step):
+//   main:  U_0            | U_1            | U_2 ...         U_k waits for P_k; consecutive updates stay in stream order
+//   side:  D_1 P_1        | D_2 P_2        | ...             D_{k+1} waits for U_{k-1}, P_{k+1} for D_{k+1}
+// D_{k+1} applies its own tile of update k itself (from the head of panel k), so it needs nothing of U_k.  P_{k+1}
+// needs block column k + 1 AFTER update k: U_k runs the tiles of that column first and counts them into `scratch`
+// per block row; the CTAs of P_{k+1} wait for their row's count (chol_gemm_kernel).  With that the panel step -- a
+// launch that cannot fill the machine -- runs under the update instead of between two updates.  P_{k+1} writes
+// the panel buffer U_k does not read.  A waiting panel CTA holds an SM slot: the overlap is used only while the
+// panel's grid leaves at least one of the three slots of every SM to the update (always up to n = 19072).
 cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, double* panel, double* invd,
-                           int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
-                           cudaEvent_t ev_diag) {
+                           int* info_dev, int* scratch, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
+                           cudaEvent_t ev_update) {
     cudaError_t err;
+    const int64_t T = npad / CB;
     if ((err = cudaMemsetAsync(info_dev, 0, sizeof(int), stream)) != cudaSuccess) return err;
+    if ((err = cudaMemsetAsync(scratch, 0, sizeof(int) * (size_t)T, stream)) != cudaSuccess) return err;
     chol_prepare_diag_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, stream>>>(M, npad, n, npad, jitter);
     ++g_pn_launches;
     const size_t smem_diag = sizeof(double) * (CB * CD_LD + 5 * CB + 3 * 32 * 33);
     const size_t smem_gemm = sizeof(double) * 2 * (CB + CTN) * CLD;
     if ((err = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag)) != cudaSuccess) return err;
     if ((err = cudaFuncSetAttribute(chol_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
-    const int64_t T = npad / CB;
-    // Look-ahead: the factorisation of diagonal block k + 1 (one CTA, latency-bound) runs on `side`
-    // under the update of step k; it applies its own tile of that update itself, so it is runnable as
-    // soon as the panel is and gets its SM before the update's CTAs occupy every slot.
-    chol_diag_kernel<<<1, 256, smem_diag, stream>>>(M, npad, invd, info_dev, 0, nullptr);
-    ++g_pn_launches;
-    for (int64_t k = 0; k < T; ++k) {
-        double* diag = M + k * CB * (npad + 1);
+    const int max_waiting = 2 * pn_sm_count();  // panel CTAs that may wait while an update runs
+    cudaEvent_t ev_diag;
+    if ((err = cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming)) != cudaSuccess) return err;
+    static const int kOverlapMinBlocks = getenv("PNCOV_CHOL_OVERLAP_MIN") ? atoi(getenv("PNCOV_CHOL_OVERLAP_MIN")) : 32;
+    double* pbuf[2] = {panel, panel + npad * CB};
+    // panel of block column k into pbuf[k & 1]; the update of step k copies it into the matrix
+    auto launch_panel = [&](int64_t k, int target, cudaStream_t st) -> cudaError_t {
         const int64_t nb = T - k - 1;
-        if (nb == 0) break;
+        if (nb <= 0) return cudaSuccess;
         ChGemm p{};
-        p.A = diag + CB * npad;  // block (k + 1, k)
+        p.A = M + k * CB * (npad + 1) + CB * npad;  // block (k + 1, k)
         p.lda = npad;
         p.B = invd + k * CB * CB;
         p.ldb = CB;
         p.C = const_cast<double*>(p.A);
         p.ldc = npad;
-        p.panel = panel;
+        p.panel = pbuf[k & 1];
         p.mode = 0;
-        chol_gemm_kernel<<<(unsigned)(2 * nb), CG_THREADS, smem_gemm, stream>>>(p);
+        p.rowcount = scratch;
+        p.row0 = (int)(k + 1);
+        p.target = target;
+        p.err = info_dev;
+        chol_gemm_kernel<<<(unsigned)(2 * nb), CG_THREADS, smem_gemm, st>>>(p);
         ++g_pn_launches;
-        if ((err = cudaEventRecord(ev_panel, stream)) != cudaSuccess) return err;
-        // L[i,k] into the matrix (rows below the diagonal block of column k; nobody else touches them)
-        if ((err = cudaMemcpy2DAsync(const_cast<double*>(p.A), (size_t)npad * 8, panel, (size_t)CB * 8, (size_t)CB * 8,
-                                     (size_t)(nb * CB), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
-            return err;
-        ChGemm u{};
-        u.A = panel;
-        u.lda = CB;
-        u.B = panel;
-        u.ldb = CB;
-        u.C = diag + CB * (npad + 1);  // block (k + 1, k + 1)
-        u.ldc = npad;
-        u.panel = nullptr;
-        u.mode = 1;
-        // side stream (high priority, issued before the wide update): tile (k + 1, k + 1) of the update
-        // fused into the next diagonal factorisation
+        return cudaSuccess;
+    };
+    chol_diag_kernel<<<1, 256, smem_diag, stream>>>(M, npad, invd, info_dev, 0, nullptr);
+    ++g_pn_launches;
+    if ((err = launch_panel(0, 0, stream)) != cudaSuccess) return err;
+    if ((err = cudaEventRecord(ev_panel, stream)) != cudaSuccess) return err;  // P_0
+    if ((err = cudaEventRecord(ev_update, stream)) != cudaSuccess) return err;  // "U_{-1}"
+    for (int64_t k = 0; k + 1 < T; ++k) {
+        const int64_t nb = T - k - 1;  // block rows of the trailing matrix
+        double* trail = M + (k + 1) * CB * (npad + 1);  // block (k + 1, k + 1)
+        // side: wait for U_{k-1} (its event is re-recorded below, so this call comes first) and P_k
+        if ((err = cudaStreamWaitEvent(side, ev_update, 0)) != cudaSuccess) return err;
         if ((err = cudaStreamWaitEvent(side, ev_panel, 0)) != cudaSuccess) return err;
-        chol_diag_kernel<<<1, 256, smem_diag, side>>>(u.C, npad, invd + (k + 1) * CB * CB, info_dev, (int)((k + 1) * CB),
-                                                      panel);
+        // side: D_{k+1} (own tile of update k from the head of panel k fused in); issued BEFORE the update so that its
+        // one large CTA (135 KB of shared memory) finds an SM before the update's CTAs fill them all
+        chol_diag_kernel<<<1, 256, smem_diag, side>>>(trail, npad, invd + (k + 1) * CB * CB, info_dev, (int)((k + 1) * CB),
+                                                      pbuf[k & 1]);
         ++g_pn_launches;
-        if ((err = cudaEventRecord(ev_diag, side)) != cudaSuccess) return err;
-        // main stream: the other tiles of the trailing update
+        // main: U_k, every tile but block (k + 1, k + 1)
+        if ((err = cudaStreamWaitEvent(stream, ev_panel, 0)) != cudaSuccess) return err;
         const int64_t tiles = nb * (nb + 1) / 2 - 1;
-        if (tiles > 0) {
-            u.tile0 = 2;
-            chol_gemm_kernel<<<(unsigned)(2 * tiles), CG_THREADS, smem_gemm, stream>>>(u);
+        // panel k into the matrix: in the last CTAs of a long update; ahead of a short one as a copy of its own, which
+        // also gives D_{k+1}, released by the same event, the head start it needs to find an SM
+        const bool fused_copy = nb >= kOverlapMinBlocks;
+        if (!fused_copy &&
+            (err = cudaMemcpy2DAsync(trail - CB, (size_t)npad * 8, pbuf[k & 1], (size_t)CB * 8, (size_t)CB * 8, (size_t)(nb * CB),
+                                     cudaMemcpyDeviceToDevice, stream)) != cudaSuccess)
+            return err;
+        if (tiles > 0 || fused_copy) {
+            ChGemm u{};
+            u.A = pbuf[k & 1];
+            u.lda = CB;
+            u.B = pbuf[k & 1];
+            u.ldb = CB;
+            u.C = trail;
+            u.ldc = npad;
+            u.mode = 1;
+            u.nb = (int)nb;
+            u.rowcount = scratch;
+            u.row0 = (int)(k + 1);
+            u.Lcol = trail - CB;  // block (k + 1, k)
+            chol_gemm_kernel<<<(unsigned)(2 * (tiles + (fused_copy ? nb : 0))), CG_THREADS, smem_gemm, stream>>>(u);
             ++g_pn_launches;
         }
-        if ((err = cudaStreamWaitEvent(stream, ev_diag, 0)) != cudaSuccess) return err;
+        if ((err = cudaEventRecord(ev_update, stream)) != cudaSuccess) return err;
+        // side: P_{k+1}, after the update in issue order (its CTAs may wait for tiles of U_k)
+        // worth it only while the update outlasts the diagonal block and the panel (0.07 nb^2 us against ~90 us):
+        // under a short update the panel would share the SMs with it and both sit on the critical path
+        const bool overlap = nb - 1 > 0 && 2 * (nb - 1) <= max_waiting && nb >= kOverlapMinBlocks;
+        if (overlap) {
+            if ((err = launch_panel(k + 1, (int)(2 * (k + 1)), side)) != cudaSuccess) return err;
+            if ((err = cudaEventRecord(ev_panel, side)) != cudaSuccess) return err;  // D_{k+1} and P_{k+1}
+        } else {
+            // P_{k+1} on the main stream behind U_k, once D_{k+1} is done
+            if ((err = cudaEventRecord(ev_diag, side)) != cudaSuccess) return err;
+            if ((err = cudaStreamWaitEvent(stream, ev_diag, 0)) != cudaSuccess) return err;
+            if ((err = launch_panel(k + 1, 0, stream)) != cudaSuccess) return err;
+            if ((err = cudaEventRecord(ev_panel, stream)) != cudaSuccess) return err;
+        }
     }
+    if ((err = cudaStreamWaitEvent(stream, ev_panel, 0)) != cudaSuccess) return err;
+    cudaEventDestroy(ev_diag);  // released once the work that refers to it has completed
     return cudaGetLastError();
 }
 

@@ -104,8 +104,8 @@ cudaError_t pn_launch_chain_apply(const double* U, const double* V, int64_t ld, 
 
 // FP64 Cholesky (pncov_chol.cu)
 cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, double* panel, double* invd,
-                           int* info_dev, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
-                           cudaEvent_t ev_diag);
+                           int* info_dev, int* scratch, cudaStream_t stream, cudaStream_t side, cudaEvent_t ev_panel,
+                           cudaEvent_t ev_update);
 cudaError_t pn_chol_solve(const double* M, int64_t npad, const double* invd, double* b, int64_t ldb, int nrhs, int* sync,
                           cudaStream_t stream);
 // many right-hand sides, one per ROW of Z (mpad x npad); Y: scratch of the same shape
