@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(CG_THREADS, 3) chol_gemm_kernel(const __grid_c
                     int seen;
                     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
                     if (seen >= p.target) break;
-                    if (++spins > (1ll << 27)) {  // seconds: the schedule is broken; report instead of hanging
+                    if (++spins > (1ll << 22)) {  // seconds (a legitimate wait is microseconds): report instead of hanging
                         atomicExch(p.err, -1);
                         break;
                     }
