@@ -922,7 +922,8 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
     const size_t smem_diag = sizeof(double) * (CB * CD_LD + 5 * CB + 3 * 32 * 33);
     const size_t smem_gemm = sizeof(double) * 2 * (CB + CTN) * CLD;
     if ((err = cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_diag)) != cudaSuccess) return err;
-    if ((err = cudaFuncSetAttribute(chol_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
+    auto gemm = chol_gemm_kernel;
+    if ((err = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
     const int max_waiting = 2 * pn_sm_count();  // panel CTAs that may wait while an update runs
     cudaEvent_t ev_diag;
     if ((err = cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming)) != cudaSuccess) return err;
@@ -945,7 +946,7 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         p.row0 = (int)(k + 1);
         p.target = target;
         p.err = info_dev;
-        chol_gemm_kernel<<<(unsigned)(2 * nb), CG_THREADS, smem_gemm, st>>>(p);
+        gemm<<<(unsigned)(2 * nb), CG_THREADS, smem_gemm, st>>>(p);
         ++g_pn_launches;
         return cudaSuccess;
     };
@@ -988,7 +989,7 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
             u.rowcount = scratch;
             u.row0 = (int)(k + 1);
             u.Lcol = trail - CB;  // block (k + 1, k)
-            chol_gemm_kernel<<<(unsigned)(2 * (tiles + (fused_copy ? nb : 0))), CG_THREADS, smem_gemm, stream>>>(u);
+            gemm<<<(unsigned)(2 * (tiles + (fused_copy ? nb : 0))), CG_THREADS, smem_gemm, stream>>>(u);
             ++g_pn_launches;
         }
         if ((err = cudaEventRecord(ev_update, stream)) != cudaSuccess) return err;
