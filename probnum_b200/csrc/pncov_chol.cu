@@ -925,8 +925,14 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
     auto gemm = chol_gemm_kernel;
     if ((err = cudaFuncSetAttribute(gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_gemm)) != cudaSuccess) return err;
     const int max_waiting = 2 * pn_sm_count();  // panel CTAs that may wait while an update runs
-    cudaEvent_t ev_diag;
-    if ((err = cudaEventCreateWithFlags(&ev_diag, cudaEventDisableTiming)) != cudaSuccess) return err;
+    struct LocalEvent {  // released (after the work that refers to it) on every way out
+        cudaEvent_t e = nullptr;
+        ~LocalEvent() {
+            if (e) cudaEventDestroy(e);
+        }
+    } local;
+    if ((err = cudaEventCreateWithFlags(&local.e, cudaEventDisableTiming)) != cudaSuccess) return err;
+    const cudaEvent_t ev_diag = local.e;
     static const int kOverlapMinBlocks = getenv("PNCOV_CHOL_OVERLAP_MIN") ? atoi(getenv("PNCOV_CHOL_OVERLAP_MIN")) : 32;
     double* pbuf[2] = {panel, panel + npad * CB};
     // panel of block column k into pbuf[k & 1]; the update of step k copies it into the matrix
@@ -1009,7 +1015,6 @@ cudaError_t pn_chol_factor(double* M, int64_t n, int64_t npad, double jitter, do
         }
     }
     if ((err = cudaStreamWaitEvent(stream, ev_panel, 0)) != cudaSuccess) return err;
-    cudaEventDestroy(ev_diag);  // released once the work that refers to it has completed
     return cudaGetLastError();
 }
 
